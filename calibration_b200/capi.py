@@ -1,0 +1,189 @@
+"""ctypes binding of libcalib_b200.so — the thin host layer over the C ABI.
+
+Everything that computes lives in the shared library (CUDA kernels for sm_100a);
+this module only marshals numpy buffers.  There is no CPU fallback: without the
+library or without a CUDA device the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi, build as _build
+
+CAL_OK, CAL_ERR_INVALID_ARGUMENT, CAL_ERR_RUNTIME, CAL_ERR_CUDA, CAL_ERR_COMM = range(5)
+
+
+class CalibCudaError(RuntimeError):
+    """CUDA device missing or a CUDA call failed (the product has no CPU path)."""
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        path = _build.build()
+    L = C.CDLL(path)
+    dp, ip, u8p, i64 = abi.c_double_p, abi.c_int32_p, abi.c_uint8_p, C.c_int64
+    hp = C.c_void_p
+    L.cal_last_error.restype = C.c_char_p
+    L.cal_device_count.restype = C.c_int
+    L.cal_refine_create.argtypes = [C.POINTER(abi.ProblemDesc), C.c_int, C.POINTER(hp)]
+    L.cal_refine_destroy.argtypes = [hp]
+    L.cal_refine_param_count.restype = i64
+    L.cal_refine_param_count.argtypes = [hp]
+    L.cal_refine_tangent_count.restype = i64
+    L.cal_refine_tangent_count.argtypes = [hp]
+    L.cal_refine_eval.argtypes = [hp, dp, dp, dp, dp]
+    L.cal_refine_cost.argtypes = [hp, dp, dp, dp]
+    L.cal_refine_bench_pass.argtypes = [hp, dp, C.c_int, C.c_int, C.POINTER(C.c_float), dp]
+    L.cal_refine_solve.argtypes = [hp, C.POINTER(abi.OptimOptions), dp, C.POINTER(abi.OptimResult), dp]
+    L.cal_comm_unique_id.argtypes = [u8p]
+    L.cal_refine_attach_comm.argtypes = [hp, u8p, C.c_int, C.c_int]
+    for name, argt in (
+        ("cal_axxb_create", [C.POINTER(abi.AxxbDesc), C.c_int, C.POINTER(hp)]),
+        ("cal_axxb_destroy", [hp]),
+        ("cal_axxb_eval", [hp, dp, dp, dp, dp]),
+        ("cal_axxb_solve", [hp, C.POINTER(abi.OptimOptions), dp, C.POINTER(abi.OptimResult), dp]),
+        ("cal_ransac_homography_batch", [i64, C.c_int32, dp, dp, dp, dp, C.POINTER(abi.RansacOptions), C.c_int, C.c_int,
+                                         C.POINTER(abi.RansacResult), u8p]),
+        ("cal_ransac_homography_batch_dev", [i64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.POINTER(abi.RansacOptions), C.c_int, C.c_void_p, C.c_void_p,
+                                             C.POINTER(C.c_float)]),
+    ):
+        if hasattr(L, name):
+            getattr(L, name).argtypes = argt
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc == CAL_OK:
+        return
+    msg = lib().cal_last_error().decode(errors="replace")
+    if rc == CAL_ERR_INVALID_ARGUMENT:
+        raise ValueError(msg)           # the reference throws std::invalid_argument
+    if rc == CAL_ERR_CUDA:
+        raise CalibCudaError(msg)
+    raise RuntimeError(msg)             # std::runtime_error
+
+
+def device_count():
+    return int(lib().cal_device_count())
+
+
+class RefineHandle:
+    """cal_refine_handle: observations resident on one GPU, laid out for the kernels."""
+
+    def __init__(self, problem, device=0):
+        self.problem = problem  # keeps the host buffers alive during create
+        self._h = C.c_void_p()
+        _check(lib().cal_refine_create(C.byref(problem.desc), device, C.byref(self._h)))
+        self.n_amb = int(lib().cal_refine_param_count(self._h))
+        self.n_tan = int(lib().cal_refine_tangent_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().cal_refine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def eval(self, x, jac=True):
+        x = abi.as_f64(x)
+        assert len(x) == self.n_amb
+        cost = C.c_double()
+        g = np.zeros(self.n_tan) if jac else None
+        H = np.zeros((self.n_tan, self.n_tan)) if jac else None
+        _check(lib().cal_refine_eval(self._h, abi.dptr(x), C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g), abi.dptr(H)))
+        return cost.value, g, H
+
+    def cost(self, x, want_block_ssr=False):
+        x = abi.as_f64(x)
+        cost = C.c_double()
+        ssr = np.zeros(self.problem.desc.n_blocks) if want_block_ssr else None
+        _check(lib().cal_refine_cost(self._h, abi.dptr(x), C.cast(C.byref(cost), abi.c_double_p), abi.dptr(ssr)))
+        return (cost.value, ssr) if want_block_ssr else cost.value
+
+    def bench_pass(self, x, reps=1, jacobian=True):
+        x = abi.as_f64(x)
+        ms = C.c_float(); cost = C.c_double()
+        _check(lib().cal_refine_bench_pass(self._h, abi.dptr(x), reps, int(jacobian), C.byref(ms),
+                                           C.cast(C.byref(cost), abi.c_double_p)))
+        return ms.value, cost.value
+
+    def solve(self, x0, opts=None, want_cov=True):
+        x = abi.as_f64(x0).copy()
+        assert len(x) == self.n_amb
+        opts = opts or abi.OptimOptions.default()
+        res = abi.OptimResult()
+        cov = np.zeros((self.n_amb, self.n_amb)) if (want_cov and opts.compute_covariance) else None
+        _check(lib().cal_refine_solve(self._h, C.byref(opts), abi.dptr(x), C.byref(res), abi.dptr(cov)))
+        return x, res, cov
+
+    def attach_comm(self, unique_id, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        _check(lib().cal_refine_attach_comm(self._h, buf, rank, world))
+
+
+def comm_unique_id():
+    buf = (C.c_uint8 * 128)()
+    _check(lib().cal_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class AxxbHandle:
+    def __init__(self, rot_a, rot_b, tra_a, tra_b, huber_delta=1.0, device=0):
+        self._keep = [abi.as_f64(a) for a in (rot_a, rot_b, tra_a, tra_b)]
+        d = abi.AxxbDesc()
+        d.n_pairs = len(self._keep[2].reshape(-1, 3))
+        d.rot_a, d.rot_b, d.tra_a, d.tra_b = (abi.dptr(a) for a in self._keep)
+        d.huber_delta = huber_delta
+        self.desc = d
+        self._h = C.c_void_p()
+        _check(lib().cal_axxb_create(C.byref(d), device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().cal_axxb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def eval(self, x7):
+        cost = C.c_double(); g = np.zeros(6); H = np.zeros((6, 6))
+        _check(lib().cal_axxb_eval(self._h, abi.dptr(abi.as_f64(x7)), C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g), abi.dptr(H)))
+        return cost.value, g, H
+
+    def solve(self, x7, opts=None):
+        x = abi.as_f64(x7).copy()
+        opts = opts or abi.OptimOptions.default()
+        res = abi.OptimResult(); cov = np.zeros((7, 7))
+        _check(lib().cal_axxb_solve(self._h, C.byref(opts), abi.dptr(x), C.byref(res), abi.dptr(cov)))
+        return x, res, cov
+
+
+def ransac_homography_batch(x, y, u, v, opts=None, seed_per_problem=True, device=0, want_mask=True):
+    """x, y, u, v: (n_problems, n) float64.  Returns (results array, inlier mask)."""
+    x, y, u, v = (abi.as_f64(a) for a in (x, y, u, v))
+    npb, n = x.shape
+    opts = opts or abi.RansacOptions.default()
+    res = (abi.RansacResult * npb)()
+    mask = np.zeros((npb, n), dtype=np.uint8) if want_mask else None
+    _check(lib().cal_ransac_homography_batch(npb, n, abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v), C.byref(opts),
+                                             int(seed_per_problem), device, res,
+                                             mask.ctypes.data_as(abi.c_uint8_p) if want_mask else None))
+    return res, mask

@@ -1,0 +1,835 @@
+// Host side of the refinement path: the C ABI of include/calib_b200.h, the
+// problem set-up (replacing the reference's Ceres problem builders) and the
+// Levenberg–Marquardt driver (replacing ceres::Solve as configured by
+// solve_problem, reference src/estimation/detail/ceresutils.h:27-43).
+// Damping, step acceptance, convergence tests and the covariance assembly run
+// here on the host; every O(observations) or O(views) pass is a kernel of
+// refine_kernels.cu.  There is no CPU fallback: a missing device is an error.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/calib_b200.h"
+#include "comm.h"
+#include "refine_kernels.cuh"
+
+using namespace calk;
+
+namespace {
+
+thread_local std::string g_err;
+cal_status fail(cal_status s, const std::string& m) { g_err = m; return s; }
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) return fail(CAL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+enum PBType { PB_EUCLID = 0, PB_QUAT = 1, PB_INTR = 2 };
+struct PB { int off, size, tsize, type; bool constant; int toff; };
+
+template <class T> cudaError_t dev_alloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)); }
+template <class T> cudaError_t upload(T* dst, const std::vector<T>& src, cudaStream_t st) {
+    if (src.empty()) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+
+// dense lower Cholesky / solve (host, shared block only: ns <= a few hundred)
+bool chol_host(std::vector<double>& A, int n) {
+    for (int j = 0; j < n; ++j) {
+        double s = A[(size_t)j * n + j];
+        for (int k = 0; k < j; ++k) s -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+        if (!(s > 0.0) || !std::isfinite(s)) return false;
+        const double l = std::sqrt(s);
+        A[(size_t)j * n + j] = l;
+        for (int i = j + 1; i < n; ++i) {
+            double t = A[(size_t)i * n + j];
+            for (int k = 0; k < j; ++k) t -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+            A[(size_t)i * n + j] = t / l;
+        }
+    }
+    return true;
+}
+void chol_solve_host(const std::vector<double>& L, int n, double* b) {
+    for (int i = 0; i < n; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[(size_t)i * n + k] * b[k]; b[i] = s / L[(size_t)i * n + i]; }
+    for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int k = i + 1; k < n; ++k) s -= L[(size_t)k * n + i] * b[k]; b[i] = s / L[(size_t)i * n + i]; }
+}
+
+void quat_plus_jacobian(const double* q, double* J) {  // QuaternionManifold::PlusJacobian, 4x3 row-major
+    J[0] = -q[1]; J[1] = -q[2]; J[2] = -q[3];
+    J[3] = q[0];  J[4] = q[3];  J[5] = -q[2];
+    J[6] = -q[3]; J[7] = q[0];  J[8] = q[1];
+    J[9] = q[2];  J[10] = -q[1]; J[11] = q[0];
+}
+
+}  // namespace
+
+struct cal_refine_handle {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    ProblemShape S{};
+    DevLayout L{};
+    EvalBuffers B{};
+    ViewBuffers V{};
+    std::vector<void*> allocs;
+    std::vector<PB> pbs;
+    int n_amb = 0, n_tan = 0, ns = 0;
+    bool constrained = false;
+    int64_t n_blocks = 0, n_obs = 0;
+    int n_red_blocks = 1;
+    int n_syrk_cta = 1;
+    std::vector<int64_t> blk_orig_host;   // device block -> original block
+    std::vector<int32_t> blk_cam_host, blk_view_host;
+    std::vector<char> view_free_host;
+    std::vector<int32_t> view_blk_off_host, view_blk_idx_host;
+    // host mirrors of the last Jacobian evaluation (shared block)
+    std::vector<double> Hss, gs, cam_sums;
+    double cost = 0;
+    calcomm::Comm* comm = nullptr;
+    // counters
+    int64_t launches = 0;
+
+    int pb_intr(int c) const { return S.kind == CAL_KIND_INTRINSICS ? 0 : c; }
+    int pb_viewq(int v) const { return S.kind == CAL_KIND_INTRINSICS ? 1 + v : 3 * S.n_cams + v; }
+    int pb_viewt(int v) const { return S.kind == CAL_KIND_INTRINSICS ? 1 + S.n_views + v : 3 * S.n_cams + S.n_views + v; }
+    int pb_camq(int c) const { return S.n_cams + c; }
+    int pb_camt(int c) const { return 2 * S.n_cams + c; }
+    int pb_bq() const { return 3 * S.n_cams; }
+    int pb_bt() const { return 3 * S.n_cams + 1; }
+
+    template <class T> cudaError_t alloc(T** p, size_t n) {
+        cudaError_t e = dev_alloc(p, n);
+        if (e == cudaSuccess) allocs.push_back(*p);
+        return e;
+    }
+    ~cal_refine_handle() {
+        for (void* p : allocs) cudaFree(p);
+        if (st) cudaStreamDestroy(st);
+        delete comm;
+    }
+};
+
+namespace {
+
+void build_param_blocks(cal_refine_handle& h, const cal_problem_desc& d) {
+    const bool sk = d.optimize_skew != 0;
+    const int P = h.S.P;
+    auto add = [&](int size, int type, bool constant) {
+        PB b; b.off = h.n_amb; b.size = size; b.type = type; b.constant = constant;
+        b.tsize = type == PB_QUAT ? 3 : (type == PB_INTR && !sk ? size - 1 : size);
+        b.toff = -1; h.n_amb += size; h.pbs.push_back(b);
+    };
+    if (d.kind == CAL_KIND_INTRINSICS) {
+        add(P, PB_INTR, false);
+        for (int v = 0; v < d.n_views; ++v) add(4, PB_QUAT, false);
+        for (int v = 0; v < d.n_views; ++v) add(3, PB_EUCLID, false);
+        h.constrained = true;  // lower bounds on fx, fy (intrinsics.cpp:81-82)
+    } else if (d.kind == CAL_KIND_EXTRINSICS) {
+        const bool oi = d.optimize_intrinsics, oe = d.optimize_extrinsics;  // extrinsics.cpp:110-150
+        for (int c = 0; c < d.n_cams; ++c) add(P, PB_INTR, !oi);
+        for (int c = 0; c < d.n_cams; ++c) add(4, PB_QUAT, !oe || c == 0);
+        for (int c = 0; c < d.n_cams; ++c) add(3, PB_EUCLID, !oe || c == 0);
+        for (int v = 0; v < d.n_views; ++v) add(4, PB_QUAT, oi && v == 0);
+        for (int v = 0; v < d.n_views; ++v) add(3, PB_EUCLID, oi && v == 0);
+        h.constrained = oi;
+    } else {
+        const bool oi = d.optimize_intrinsics, oh = d.optimize_hand_eye, ot = d.optimize_target_pose;  // bundle.cpp:98-131
+        for (int c = 0; c < d.n_cams; ++c) add(P, PB_INTR, !oi);
+        for (int c = 0; c < d.n_cams; ++c) add(4, PB_QUAT, !oh);
+        for (int c = 0; c < d.n_cams; ++c) add(3, PB_EUCLID, !oh);
+        add(4, PB_QUAT, !ot);
+        add(3, PB_EUCLID, !ot);
+        h.constrained = oi;
+    }
+    for (auto& b : h.pbs) if (!b.constant) { b.toff = h.n_tan; h.n_tan += b.tsize; }
+    // shared block = everything that is not a per-view pose; for the per-view
+    // kinds the view blocks come last in x, so shared tangent indices are 0..ns-1
+    h.ns = h.n_tan;
+    if (d.kind != CAL_KIND_BUNDLE) {
+        h.ns = 0;
+        const int first_view_pb = h.pb_viewq(0);
+        for (int i = 0; i < first_view_pb; ++i) if (!h.pbs[i].constant) h.ns += h.pbs[i].tsize;
+    }
+}
+
+cal_status validate(const cal_problem_desc& d) {
+    if (d.kind < 0 || d.kind > 2 || d.model < 0 || d.model > 1) return fail(CAL_ERR_INVALID_ARGUMENT, "unknown problem kind / camera model");
+    if (d.n_cams <= 0) return fail(CAL_ERR_INVALID_ARGUMENT, "No camera intrinsics provided");            // bundle.cpp:139-141
+    if (d.kind == CAL_KIND_INTRINSICS && d.n_views < 4)
+        return fail(CAL_ERR_INVALID_ARGUMENT, "Insufficient views for calibration (at least 4 required).");  // intrinsics.cpp:92-96
+    if (d.n_blocks <= 0 || d.n_obs <= 0) return fail(CAL_ERR_INVALID_ARGUMENT, "No observations provided");    // bundle.cpp:142-144
+    if (!d.obj_x || !d.obj_y || !d.img_u || !d.img_v || !d.block_offset || !d.block_cam)
+        return fail(CAL_ERR_INVALID_ARGUMENT, "null observation arrays");
+    if (d.kind == CAL_KIND_INTRINSICS && (d.n_cams != 1 || d.n_blocks != d.n_views))
+        return fail(CAL_ERR_INVALID_ARGUMENT, "intrinsics: one camera and one residual block per view expected");
+    if (d.kind == CAL_KIND_EXTRINSICS && !d.block_view) return fail(CAL_ERR_INVALID_ARGUMENT, "extrinsics: block_view required");
+    if (d.kind == CAL_KIND_BUNDLE && !d.block_b_se3_g) return fail(CAL_ERR_INVALID_ARGUMENT, "bundle: block_b_se3_g required");
+    if (d.block_offset[0] != 0 || d.block_offset[d.n_blocks] != d.n_obs) return fail(CAL_ERR_INVALID_ARGUMENT, "block_offset does not span the observations");
+    for (int64_t b = 0; b < d.n_blocks; ++b) {
+        // *Residual::create throws on an empty view (intrinsicresidual.h:38-40, bundleresidual.h:59-61)
+        if (d.block_offset[b + 1] <= d.block_offset[b]) return fail(CAL_ERR_INVALID_ARGUMENT, "No observations provided");
+        if (d.block_cam[b] < 0 || d.block_cam[b] >= d.n_cams) return fail(CAL_ERR_INVALID_ARGUMENT, "block_cam out of range");
+        if (d.kind == CAL_KIND_EXTRINSICS && (d.block_view[b] < 0 || d.block_view[b] >= d.n_views))
+            return fail(CAL_ERR_INVALID_ARGUMENT, "Incompatible pose vector sizes for joint optimization");  // extrinsics.cpp:163-171
+    }
+    return CAL_OK;
+}
+
+}  // namespace
+
+extern "C" const char* cal_last_error(void) { return g_err.c_str(); }
+
+extern "C" int cal_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, cal_refine_handle** out) {
+    if (!dp || !out) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    const cal_problem_desc& d = *dp;
+    if (cal_status s = validate(d)) return s;
+    if (cal_device_count() <= device) return fail(CAL_ERR_CUDA, "no CUDA device: calib_b200 has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(device));
+    std::unique_ptr<cal_refine_handle> hp(new cal_refine_handle);
+    cal_refine_handle& h = *hp;
+    h.device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&h.st, cudaStreamNonBlocking));
+    ProblemShape& S = h.S;
+    S.kind = d.kind; S.model = d.model; S.n_cams = d.n_cams;
+    S.n_views = d.kind == CAL_KIND_BUNDLE ? 0 : d.n_views;
+    S.P = d.model == CAL_MODEL_SCHEIMPFLUG_BC5 ? 12 : 10;
+    const bool intr_free = d.kind == CAL_KIND_INTRINSICS || d.optimize_intrinsics;
+    S.imode = !intr_free ? INTR_NONE : (d.optimize_skew ? INTR_SKEW : INTR_NOSKEW);
+    S.PI = S.imode == INTR_NONE ? 0 : (S.imode == INTR_NOSKEW ? S.P - 1 : S.P);
+    S.NC = 6 + S.PI; S.NL = S.NC + 1; S.NE = S.NL * (S.NL + 1) / 2;
+    S.huber_delta = d.huber_delta;
+    S.cam_pose_kind = d.kind == CAL_KIND_EXTRINSICS ? 1 : (d.kind == CAL_KIND_BUNDLE ? 2 : 0);
+    S.view_free_global = d.kind == CAL_KIND_BUNDLE ? (d.optimize_target_pose != 0) : 1;
+    S.NV = S.NE + 1 + (d.kind == CAL_KIND_BUNDLE ? 63 + 6 * S.PI : 0);
+    h.n_blocks = d.n_blocks; h.n_obs = d.n_obs;
+    build_param_blocks(h, d);
+    if (d.kind != CAL_KIND_BUNDLE && h.ns + 1 > kSyrkMaxN)
+        return fail(CAL_ERR_INVALID_ARGUMENT, "shared block too large for the Schur kernel (ns + 1 > 176)");
+    S.off_intr = 0;
+    if (d.kind == CAL_KIND_INTRINSICS) { S.off_camq = S.off_camt = 0; S.off_viewq = S.P; S.off_viewt = S.P + 4 * d.n_views; }
+    else if (d.kind == CAL_KIND_EXTRINSICS) {
+        S.off_camq = S.P * d.n_cams; S.off_camt = S.off_camq + 4 * d.n_cams;
+        S.off_viewq = S.off_camt + 3 * d.n_cams; S.off_viewt = S.off_viewq + 4 * d.n_views;
+    } else {
+        S.off_camq = S.P * d.n_cams; S.off_camt = S.off_camq + 4 * d.n_cams;
+        S.off_viewq = S.off_camt + 3 * d.n_cams; S.off_viewt = S.off_viewq + 4;  // b_q_t, b_t_t
+    }
+
+    // ---- device block order: by camera, camera groups padded to 32 ----
+    std::vector<int64_t> order(d.n_blocks);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return d.block_cam[a] < d.block_cam[b]; });
+    std::vector<int64_t>& borig = h.blk_orig_host;
+    std::vector<int32_t>&bcam = h.blk_cam_host, &bview = h.blk_view_host;
+    {
+        size_t i = 0;
+        while (i < order.size()) {
+            const int cam = d.block_cam[order[i]];
+            while (i < order.size() && d.block_cam[order[i]] == cam) {
+                borig.push_back(order[i]); bcam.push_back(cam);
+                bview.push_back(d.kind == CAL_KIND_INTRINSICS ? (int32_t)order[i] : (d.kind == CAL_KIND_EXTRINSICS ? d.block_view[order[i]] : -1));
+                ++i;
+            }
+            while (borig.size() % 32) { borig.push_back(-1); bcam.push_back(cam); bview.push_back(-1); }
+        }
+    }
+    const int64_t nblk = (int64_t)borig.size();
+    h.L.n_blk = nblk;
+    // ---- segments ----
+    int64_t max_len = 0;
+    for (int64_t b = 0; b < d.n_blocks; ++b) max_len = std::max<int64_t>(max_len, d.block_offset[b + 1] - d.block_offset[b]);
+    const int64_t target = std::min<int64_t>(std::max<int64_t>(8, (d.n_obs + 65535) / 65536), std::max<int64_t>(max_len, 1));
+    std::vector<int32_t> seg_len, seg_blk, seg_cam, blk_seg_off(nblk + 1, 0), blk_vfree(nblk, 0);
+    std::vector<int64_t> seg_src;
+    h.view_free_host.assign(std::max(S.n_views, 0), 0);
+    for (int v = 0; v < S.n_views; ++v) h.view_free_host[v] = !h.pbs[h.pb_viewq(v)].constant;
+    for (int64_t b = 0; b < nblk; ++b) {
+        blk_seg_off[b] = (int32_t)seg_len.size();
+        if (borig[b] < 0) continue;
+        const int64_t o0 = d.block_offset[borig[b]], len = d.block_offset[borig[b] + 1] - o0;
+        const int64_t nseg = (len + target - 1) / target, sl = (len + nseg - 1) / nseg;
+        for (int64_t k = 0; k < len; k += sl) {
+            seg_len.push_back((int32_t)std::min<int64_t>(sl, len - k)); seg_blk.push_back((int32_t)b);
+            seg_cam.push_back(bcam[b]); seg_src.push_back(o0 + k);
+        }
+        blk_vfree[b] = d.kind == CAL_KIND_BUNDLE ? (d.optimize_target_pose != 0) : (bview[b] >= 0 && h.view_free_host[bview[b]]);
+    }
+    blk_seg_off[nblk] = (int32_t)seg_len.size();
+    while (seg_len.size() % 32) { seg_len.push_back(0); seg_blk.push_back(0); seg_cam.push_back(0); seg_src.push_back(0); }
+    const int64_t nseg = (int64_t)seg_len.size(), ntiles = nseg / 32;
+    h.L.n_seg = nseg; h.L.n_tiles = ntiles;
+    std::vector<int64_t> tile_off(ntiles); std::vector<int32_t> tile_depth(ntiles);
+    int64_t slices = 0;
+    for (int64_t t = 0; t < ntiles; ++t) {
+        int32_t dep = 0; for (int l = 0; l < 32; ++l) dep = std::max(dep, seg_len[t * 32 + l]);
+        tile_off[t] = slices; tile_depth[t] = dep; slices += dep;
+    }
+    h.L.n_slices = slices;
+
+    // ---- uploads ----
+    DevLayout& L = h.L;
+    CUDA_TRY(h.alloc(&L.obs, (size_t)slices * 128));
+    CUDA_TRY(h.alloc(&L.tile_off, ntiles)); CUDA_TRY(h.alloc(&L.tile_depth, ntiles));
+    CUDA_TRY(h.alloc(&L.seg_len, nseg)); CUDA_TRY(h.alloc(&L.seg_blk, nseg)); CUDA_TRY(h.alloc(&L.seg_cam, nseg));
+    CUDA_TRY(h.alloc(&L.blk_cam, nblk)); CUDA_TRY(h.alloc(&L.blk_view, nblk)); CUDA_TRY(h.alloc(&L.blk_orig, nblk));
+    CUDA_TRY(h.alloc(&L.blk_seg_off, nblk + 1)); CUDA_TRY(h.alloc(&L.blk_vfree, nblk));
+    CUDA_TRY(upload(L.tile_off, tile_off, h.st)); CUDA_TRY(upload(L.tile_depth, tile_depth, h.st));
+    CUDA_TRY(upload(L.seg_len, seg_len, h.st)); CUDA_TRY(upload(L.seg_blk, seg_blk, h.st)); CUDA_TRY(upload(L.seg_cam, seg_cam, h.st));
+    CUDA_TRY(upload(L.blk_cam, bcam, h.st)); CUDA_TRY(upload(L.blk_view, bview, h.st)); CUDA_TRY(upload(L.blk_orig, borig, h.st));
+    CUDA_TRY(upload(L.blk_seg_off, blk_seg_off, h.st)); CUDA_TRY(upload(L.blk_vfree, blk_vfree, h.st));
+    if (d.kind == CAL_KIND_BUNDLE) {
+        std::vector<double> bTg((size_t)12 * nblk, 0.0);
+        for (int64_t b = 0; b < nblk; ++b)
+            for (int i = 0; i < 12; ++i) bTg[(size_t)i * nblk + b] = borig[b] >= 0 ? d.block_b_se3_g[12 * borig[b] + i] : (i % 4 == 0 && i < 9 ? 1.0 : 0.0);
+        CUDA_TRY(h.alloc(&L.blk_bTg, bTg.size())); CUDA_TRY(upload(L.blk_bTg, bTg, h.st));
+    }
+    {   // raw SoA upload + one-time repack into the tile-transposed layout
+        double *rx, *ry, *ru, *rv; int64_t* dsrc;
+        CUDA_TRY(dev_alloc(&rx, d.n_obs)); CUDA_TRY(dev_alloc(&ry, d.n_obs)); CUDA_TRY(dev_alloc(&ru, d.n_obs)); CUDA_TRY(dev_alloc(&rv, d.n_obs));
+        CUDA_TRY(dev_alloc(&dsrc, nseg));
+        const size_t nb = (size_t)d.n_obs * sizeof(double);
+        CUDA_TRY(cudaMemcpyAsync(rx, d.obj_x, nb, cudaMemcpyHostToDevice, h.st));
+        CUDA_TRY(cudaMemcpyAsync(ry, d.obj_y, nb, cudaMemcpyHostToDevice, h.st));
+        CUDA_TRY(cudaMemcpyAsync(ru, d.img_u, nb, cudaMemcpyHostToDevice, h.st));
+        CUDA_TRY(cudaMemcpyAsync(rv, d.img_v, nb, cudaMemcpyHostToDevice, h.st));
+        CUDA_TRY(upload(dsrc, seg_src, h.st));
+        launch_repack(L, rx, ry, ru, rv, dsrc, h.st);
+        CUDA_TRY(cudaStreamSynchronize(h.st));
+        cudaFree(rx); cudaFree(ry); cudaFree(ru); cudaFree(rv); cudaFree(dsrc);
+        CUDA_TRY(cudaGetLastError());
+    }
+    // ---- evaluation buffers ----
+    EvalBuffers& B = h.B;
+    h.n_red_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 2, (nblk / 32 + kRedWarpsPerBlock - 1) / kRedWarpsPerBlock));
+    const int nrw = h.n_red_blocks * kRedWarpsPerBlock;
+    CUDA_TRY(h.alloc(&B.x, h.n_amb)); CUDA_TRY(h.alloc(&B.camc, S.n_cams)); CUDA_TRY(h.alloc(&B.camT, (size_t)S.n_cams * 36));
+    CUDA_TRY(h.alloc(&B.seg_frame, (size_t)9 * nseg)); CUDA_TRY(h.alloc(&B.blk_Tv, (size_t)36 * nblk));
+    CUDA_TRY(h.alloc(&B.segN, (size_t)S.NE * nseg)); CUDA_TRY(h.alloc(&B.seg_ssr, nseg)); CUDA_TRY(h.alloc(&B.blk_ssr, nblk));
+    CUDA_TRY(h.alloc(&B.partial, (size_t)S.n_cams * nrw * S.NV)); CUDA_TRY(h.alloc(&B.cam_sums, (size_t)S.n_cams * S.NV));
+    CUDA_TRY(cudaMemsetAsync(B.seg_frame, 0, sizeof(double) * 9 * nseg, h.st));
+    CUDA_TRY(cudaMemsetAsync(B.segN, 0, sizeof(double) * S.NE * nseg, h.st));
+    CUDA_TRY(cudaMemsetAsync(B.seg_ssr, 0, sizeof(double) * nseg, h.st));
+    if (S.n_views > 0) {
+        CUDA_TRY(h.alloc(&B.blk_Hvv, (size_t)21 * nblk)); CUDA_TRY(h.alloc(&B.blk_gv, (size_t)6 * nblk));
+        CUDA_TRY(h.alloc(&B.blk_Evc, (size_t)36 * nblk)); CUDA_TRY(h.alloc(&B.blk_Evi, (size_t)6 * std::max(S.PI, 1) * nblk));
+        CUDA_TRY(cudaMemsetAsync(B.blk_Hvv, 0, sizeof(double) * 21 * nblk, h.st)); CUDA_TRY(cudaMemsetAsync(B.blk_gv, 0, sizeof(double) * 6 * nblk, h.st));
+        CUDA_TRY(cudaMemsetAsync(B.blk_Evc, 0, sizeof(double) * 36 * nblk, h.st));
+        CUDA_TRY(cudaMemsetAsync(B.blk_Evi, 0, sizeof(double) * 6 * std::max(S.PI, 1) * nblk, h.st));
+        // view CSR over device blocks
+        ViewBuffers& V = h.V;
+        std::vector<int32_t>& off = h.view_blk_off_host; std::vector<int32_t>& idx = h.view_blk_idx_host;
+        off.assign(S.n_views + 1, 0);
+        for (int64_t b = 0; b < nblk; ++b) if (bview[b] >= 0) off[bview[b] + 1]++;
+        for (int v = 0; v < S.n_views; ++v) off[v + 1] += off[v];
+        idx.assign(off[S.n_views], 0);
+        { std::vector<int32_t> cur(off.begin(), off.end() - 1); for (int64_t b = 0; b < nblk; ++b) if (bview[b] >= 0) idx[cur[bview[b]]++] = (int32_t)b; }
+        std::vector<int32_t> vfree(S.n_views), cq(S.n_cams), ct(S.n_cams), ci(S.n_cams);
+        for (int v = 0; v < S.n_views; ++v) vfree[v] = h.view_free_host[v];
+        for (int c = 0; c < S.n_cams; ++c) {
+            cq[c] = d.kind == CAL_KIND_EXTRINSICS ? h.pbs[h.pb_camq(c)].toff : -1;
+            ct[c] = d.kind == CAL_KIND_EXTRINSICS ? h.pbs[h.pb_camt(c)].toff : -1;
+            ci[c] = h.pbs[h.pb_intr(c)].toff;
+        }
+        const int nv = S.n_views, ns = h.ns;
+        h.n_syrk_cta = schur_num_ctas(nv);
+        CUDA_TRY(h.alloc(&V.view_blk_off, nv + 1)); CUDA_TRY(h.alloc(&V.view_blk_idx, idx.size())); CUDA_TRY(h.alloc(&V.view_free, nv));
+        CUDA_TRY(h.alloc(&V.cam_col_q, S.n_cams)); CUDA_TRY(h.alloc(&V.cam_col_t, S.n_cams)); CUDA_TRY(h.alloc(&V.cam_col_i, S.n_cams));
+        CUDA_TRY(upload(V.view_blk_off, off, h.st)); CUDA_TRY(upload(V.view_blk_idx, idx, h.st)); CUDA_TRY(upload(V.view_free, vfree, h.st));
+        CUDA_TRY(upload(V.cam_col_q, cq, h.st)); CUDA_TRY(upload(V.cam_col_t, ct, h.st)); CUDA_TRY(upload(V.cam_col_i, ci, h.st));
+        CUDA_TRY(h.alloc(&V.Hpp, (size_t)nv * 36)); CUDA_TRY(h.alloc(&V.gp, (size_t)nv * 6)); CUDA_TRY(h.alloc(&V.sp, (size_t)nv * 6));
+        CUDA_TRY(h.alloc(&V.dp, (size_t)nv * 6)); CUDA_TRY(h.alloc(&V.Lp, (size_t)nv * 36)); CUDA_TRY(h.alloc(&V.view_f, (size_t)nv * 6));
+        CUDA_TRY(h.alloc(&V.blk_F, (size_t)6 * (6 + S.PI) * nblk)); CUDA_TRY(h.alloc(&V.delta_p, (size_t)nv * 6));
+        CUDA_TRY(h.alloc(&V.s_shared, ns)); CUDA_TRY(h.alloc(&V.y_shared, ns)); CUDA_TRY(h.alloc(&V.C, (size_t)ns * ns)); CUDA_TRY(h.alloc(&V.c, ns));
+        CUDA_TRY(h.alloc(&V.partialC, (size_t)h.n_syrk_cta * (ns + 1) * (ns + 1))); CUDA_TRY(h.alloc(&V.red, (size_t)nv * 4));
+        CUDA_TRY(h.alloc(&V.red_out, 4)); CUDA_TRY(h.alloc(&V.fail, 1));
+        CUDA_TRY(cudaMemsetAsync(V.red, 0, sizeof(double) * nv * 4, h.st)); CUDA_TRY(cudaMemsetAsync(V.fail, 0, sizeof(int32_t), h.st));
+        CUDA_TRY(cudaMemsetAsync(V.blk_F, 0, sizeof(double) * 6 * (6 + S.PI) * nblk, h.st));
+        CUDA_TRY(cudaMemsetAsync(V.delta_p, 0, sizeof(double) * nv * 6, h.st));
+        CUDA_TRY(cudaMemsetAsync(V.sp, 0, sizeof(double) * nv * 6, h.st));
+    }
+    CUDA_TRY(h.alloc(&h.V.x_cand, h.n_amb));
+    CUDA_TRY(cudaStreamSynchronize(h.st));
+    *out = hp.release();
+    return CAL_OK;
+}
+
+extern "C" void cal_refine_destroy(cal_refine_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    delete h;
+}
+extern "C" int64_t cal_refine_param_count(const cal_refine_handle* h) { return h ? h->n_amb : 0; }
+extern "C" int64_t cal_refine_tangent_count(const cal_refine_handle* h) { return h ? h->n_tan : 0; }
+
+namespace {
+
+// ---- device passes -----------------------------------------------------------
+// x_dev must already hold the parameters.  After a Jacobian pass the host
+// mirrors h.Hss / h.gs / h.cost describe the shared block; per-view blocks stay
+// on the device (h.V.Hpp, h.V.gp, B.blk_E*).
+cal_status device_pass(cal_refine_handle& h, double* x_dev, bool jac, const double* x_host) {
+    EvalBuffers B = h.B; B.x = x_dev;
+    const ProblemShape& S = h.S;
+    launch_setup(S, h.L, B, h.st);
+    if (jac) launch_k1(S, h.L, B, h.st); else launch_cost(S, h.L, B, h.st);
+    launch_assemble(S, h.L, B, h.n_red_blocks, jac ? 1 : 0, h.st);
+    h.launches += 5 + (jac ? k1_num_passes(S) - 1 : 0);
+    const int NV = jac ? S.NV : 1;
+    if (h.comm) {
+        if (!h.comm->allreduce_sum(B.cam_sums, (size_t)S.n_cams * NV, h.st)) return fail(CAL_ERR_COMM, h.comm->error());
+    }
+    h.cam_sums.resize((size_t)S.n_cams * NV);
+    CUDA_TRY(cudaMemcpyAsync(h.cam_sums.data(), B.cam_sums, h.cam_sums.size() * sizeof(double), cudaMemcpyDeviceToHost, h.st));
+    if (jac && S.n_views > 0) { launch_view_gather(S, h.L, B, h.V, h.st); h.launches++; }
+    CUDA_TRY(cudaStreamSynchronize(h.st));
+    CUDA_TRY(cudaGetLastError());
+    double cost = 0;
+    for (int c = 0; c < S.n_cams; ++c) cost += h.cam_sums[(size_t)c * NV + (jac ? S.NE : 0)];
+    h.cost = cost;
+    if (!jac) return CAL_OK;
+    // ---- finish the shared block on the host (per-camera constant transforms) ----
+    const int ns = h.ns, NE = S.NE, NC = S.NC, PI = S.PI, NL = S.NL;
+    auto idx = [NL](int a, int b) { if (a > b) std::swap(a, b); return a * NL - a * (a - 1) / 2 + (b - a); };
+    h.Hss.assign((size_t)ns * ns, 0.0); h.gs.assign(ns, 0.0);
+    for (int c = 0; c < S.n_cams; ++c) {
+        const double* sums = &h.cam_sums[(size_t)c * S.NV];
+        const PB& pi = h.pbs[h.pb_intr(c)];
+        int pose_idx[6]; bool pose_free = false;
+        double Tc[36];
+        if (S.cam_pose_kind) {
+            const PB& pq = h.pbs[h.pb_camq(c)]; const PB& pt = h.pbs[h.pb_camt(c)];
+            pose_free = !pq.constant;
+            for (int k = 0; k < 3; ++k) { pose_idx[k] = pq.toff + k; pose_idx[3 + k] = pt.toff + k; }
+            CamConst cc; cam_const_from_intr(x_host + pi.off, S.model, cc);
+            if (S.cam_pose_kind == 1) cam_transform_extrinsics(x_host + pt.off, cc.Rs, Tc);
+            else cam_transform_bundle(x_host + pq.off, cc.Rs, Tc);
+        }
+        const bool intr_free = !pi.constant && PI > 0;
+        if (pose_free) {
+            double Q[36];  // T_c^T N_xixi
+            for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double a = 0; for (int k = 0; k < 6; ++k) a += Tc[6 * k + i] * sums[idx(k, j)]; Q[6 * i + j] = a; }
+            for (int i = 0; i < 6; ++i) {
+                for (int j = 0; j < 6; ++j) { double a = 0; for (int k = 0; k < 6; ++k) a += Q[6 * i + k] * Tc[6 * k + j]; h.Hss[(size_t)pose_idx[i] * ns + pose_idx[j]] += a; }
+                double g = 0; for (int k = 0; k < 6; ++k) g += Tc[6 * k + i] * sums[idx(k, NC)];
+                h.gs[pose_idx[i]] += g;
+                if (intr_free) for (int j = 0; j < PI; ++j) {
+                    double a = 0; for (int k = 0; k < 6; ++k) a += Tc[6 * k + i] * sums[idx(k, 6 + j)];
+                    h.Hss[(size_t)pose_idx[i] * ns + pi.toff + j] += a; h.Hss[(size_t)(pi.toff + j) * ns + pose_idx[i]] += a;
+                }
+            }
+        }
+        if (intr_free) for (int i = 0; i < PI; ++i) {
+            h.gs[pi.toff + i] += sums[idx(6 + i, NC)];
+            for (int j = 0; j < PI; ++j) h.Hss[(size_t)(pi.toff + i) * ns + pi.toff + j] += sums[idx(6 + i, 6 + j)];
+        }
+        if (S.kind == CAL_KIND_BUNDLE && S.view_free_global) {
+            const PB& bq = h.pbs[h.pb_bq()]; const PB& bt = h.pbs[h.pb_bt()];
+            int bidx[6]; for (int k = 0; k < 3; ++k) { bidx[k] = bq.toff + k; bidx[3 + k] = bt.toff + k; }
+            const double* Hvv = sums + NE + 1; const double* gv = Hvv + 21; const double* Qs = gv + 6; const double* Evi = Qs + 36;
+            int o = 0;
+            for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { const double a = Hvv[o++]; h.Hss[(size_t)bidx[i] * ns + bidx[j]] += a; if (i != j) h.Hss[(size_t)bidx[j] * ns + bidx[i]] += a; }
+            for (int i = 0; i < 6; ++i) h.gs[bidx[i]] += gv[i];
+            if (pose_free) for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) {
+                double a = 0; for (int k = 0; k < 6; ++k) a += Qs[6 * i + k] * Tc[6 * k + j];
+                h.Hss[(size_t)bidx[i] * ns + pose_idx[j]] += a; h.Hss[(size_t)pose_idx[j] * ns + bidx[i]] += a;
+            }
+            if (intr_free) for (int i = 0; i < 6; ++i) for (int j = 0; j < PI; ++j) {
+                const double a = Evi[PI * i + j];
+                h.Hss[(size_t)bidx[i] * ns + pi.toff + j] += a; h.Hss[(size_t)(pi.toff + j) * ns + bidx[i]] += a;
+            }
+        }
+    }
+    return CAL_OK;
+}
+
+// x [+] delta for the shared parameter blocks (host); per-view blocks are copied.
+void plus_shared(const cal_refine_handle& h, const double* x, const double* delta_shared, double t, double* xp) {
+    const int n_shared_pb = h.S.kind == CAL_KIND_BUNDLE ? (int)h.pbs.size() : h.pb_viewq(0);
+    for (int i = 0; i < (int)h.pbs.size(); ++i) {
+        const PB& pb = h.pbs[i];
+        if (pb.constant || i >= n_shared_pb) { for (int j = 0; j < pb.size; ++j) xp[pb.off + j] = x[pb.off + j]; continue; }
+        double dl[12];
+        for (int k = 0; k < pb.tsize; ++k) dl[k] = t * delta_shared[pb.toff + k];
+        if (pb.type == PB_QUAT) quat_plus(x + pb.off, dl, xp + pb.off);
+        else if (pb.type == PB_INTR) {
+            int k = 0;
+            for (int j = 0; j < pb.size; ++j) {
+                if (pb.tsize == pb.size - 1 && j == 4) { xp[pb.off + j] = x[pb.off + j]; continue; }
+                xp[pb.off + j] = x[pb.off + j] + dl[k++];
+            }
+            // SetParameterLowerBound(fx, 0) / (fy, 0): projection inside Program::Plus
+            xp[pb.off + 0] = std::max(xp[pb.off + 0], 0.0); xp[pb.off + 1] = std::max(xp[pb.off + 1], 0.0);
+        } else for (int j = 0; j < pb.size; ++j) xp[pb.off + j] = x[pb.off + j] + dl[j];
+    }
+}
+
+struct LMState {
+    std::vector<double> x, xp;            // host ambient (view part only meaningful at start/end)
+    std::vector<double> s, diag, y, step, delta, gsv;
+};
+
+// Build the dense tangent-space system (canonical order) from the last Jacobian pass.
+cal_status dense_system(cal_refine_handle& h, std::vector<double>& H, std::vector<double>& g) {
+    const int n = h.n_tan, ns = h.ns;
+    H.assign((size_t)n * n, 0.0); g.assign(n, 0.0);
+    for (int i = 0; i < ns; ++i) { g[i] = h.gs[i]; for (int j = 0; j < ns; ++j) H[(size_t)i * n + j] = h.Hss[(size_t)i * ns + j]; }
+    const ProblemShape& S = h.S;
+    if (S.n_views == 0) return CAL_OK;
+    const int nv = S.n_views, PI = S.PI; const int64_t nblk = h.L.n_blk;
+    std::vector<double> Hpp((size_t)nv * 36), gp((size_t)nv * 6), Evc((size_t)36 * nblk), Evi((size_t)6 * std::max(PI, 1) * nblk);
+    CUDA_TRY(cudaMemcpy(Hpp.data(), h.V.Hpp, Hpp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(gp.data(), h.V.gp, gp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(Evc.data(), h.B.blk_Evc, Evc.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(Evi.data(), h.B.blk_Evi, Evi.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int v = 0; v < nv; ++v) {
+        if (!h.view_free_host[v]) continue;
+        const PB& q = h.pbs[h.pb_viewq(v)]; const PB& t = h.pbs[h.pb_viewt(v)];
+        int vi[6]; for (int k = 0; k < 3; ++k) { vi[k] = q.toff + k; vi[3 + k] = t.toff + k; }
+        for (int i = 0; i < 6; ++i) { g[vi[i]] = gp[(size_t)v * 6 + i]; for (int j = 0; j < 6; ++j) H[(size_t)vi[i] * n + vi[j]] = Hpp[(size_t)v * 36 + 6 * i + j]; }
+        for (int k = h.view_blk_off_host[v]; k < h.view_blk_off_host[v + 1]; ++k) {
+            const int64_t b = h.view_blk_idx_host[k]; const int cam = h.blk_cam_host[b];
+            const PB& pi = h.pbs[h.pb_intr(cam)];
+            if (S.cam_pose_kind == 1 && !h.pbs[h.pb_camq(cam)].constant) {
+                const int cq = h.pbs[h.pb_camq(cam)].toff, ct = h.pbs[h.pb_camt(cam)].toff;
+                for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) {
+                    const int col = j < 3 ? cq + j : ct + j - 3; const double a = Evc[(size_t)(6 * i + j) * nblk + b];
+                    H[(size_t)vi[i] * n + col] += a; H[(size_t)col * n + vi[i]] += a;
+                }
+            }
+            if (!pi.constant && PI > 0) for (int i = 0; i < 6; ++i) for (int j = 0; j < PI; ++j) {
+                const double a = Evi[(size_t)(PI * i + j) * nblk + b];
+                H[(size_t)vi[i] * n + pi.toff + j] += a; H[(size_t)(pi.toff + j) * n + vi[i]] += a;
+            }
+        }
+    }
+    return CAL_OK;
+}
+
+}  // namespace
+
+extern "C" cal_status cal_refine_eval(cal_refine_handle* h, const double* x, double* cost, double* g, double* H) {
+    if (!h || !x) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(h->B.x, x, sizeof(double) * h->n_amb, cudaMemcpyHostToDevice, h->st));
+    const bool jac = g || H;
+    if (cal_status s = device_pass(*h, h->B.x, jac, x)) return s;
+    if (cost) *cost = h->cost;
+    if (jac) {
+        if (h->n_tan > 8192) return fail(CAL_ERR_INVALID_ARGUMENT, "dense H is only produced for n_tan <= 8192");
+        std::vector<double> Hd, gd;
+        if (cal_status s = dense_system(*h, Hd, gd)) return s;
+        if (g) std::memcpy(g, gd.data(), gd.size() * sizeof(double));
+        if (H) std::memcpy(H, Hd.data(), Hd.size() * sizeof(double));
+    }
+    return CAL_OK;
+}
+
+extern "C" cal_status cal_refine_cost(cal_refine_handle* h, const double* x, double* cost, double* block_ssr) {
+    if (!h || !x) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(h->B.x, x, sizeof(double) * h->n_amb, cudaMemcpyHostToDevice, h->st));
+    if (cal_status s = device_pass(*h, h->B.x, false, x)) return s;
+    if (cost) *cost = h->cost;
+    if (block_ssr) {
+        std::vector<double> tmp(h->L.n_blk);
+        CUDA_TRY(cudaMemcpy(tmp.data(), h->B.blk_ssr, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int64_t b = 0; b < h->L.n_blk; ++b) if (h->blk_orig_host[b] >= 0) block_ssr[h->blk_orig_host[b]] = tmp[b];
+    }
+    return CAL_OK;
+}
+
+extern "C" cal_status cal_refine_bench_pass(cal_refine_handle* h, const double* x, int reps, int jacobian, float* ms_total,
+                                            double* cost) {
+    if (!h || !x || reps <= 0) return fail(CAL_ERR_INVALID_ARGUMENT, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(h->B.x, x, sizeof(double) * h->n_amb, cudaMemcpyHostToDevice, h->st));
+    cudaEvent_t e0, e1; CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaStreamSynchronize(h->st));
+    CUDA_TRY(cudaEventRecord(e0, h->st));
+    for (int r = 0; r < reps; ++r) {
+        launch_setup(h->S, h->L, h->B, h->st);
+        if (jacobian) launch_k1(h->S, h->L, h->B, h->st); else launch_cost(h->S, h->L, h->B, h->st);
+        launch_assemble(h->S, h->L, h->B, h->n_red_blocks, jacobian ? 1 : 0, h->st);
+        if (h->comm && !h->comm->allreduce_sum(h->B.cam_sums, (size_t)h->S.n_cams * (jacobian ? h->S.NV : 1), h->st))
+            return fail(CAL_ERR_COMM, h->comm->error());
+        if (jacobian && h->S.n_views > 0) launch_view_gather(h->S, h->L, h->B, h->V, h->st);
+    }
+    CUDA_TRY(cudaEventRecord(e1, h->st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_total) *ms_total = ms;
+    if (cost) {
+        const int NV = jacobian ? h->S.NV : 1;
+        std::vector<double> cs((size_t)h->S.n_cams * NV);
+        CUDA_TRY(cudaMemcpy(cs.data(), h->B.cam_sums, cs.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        double c = 0; for (int k = 0; k < h->S.n_cams; ++k) c += cs[(size_t)k * NV + (jacobian ? h->S.NE : 0)];
+        *cost = c;
+    }
+    return CAL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Levenberg–Marquardt (Ceres 2.2 trust-region semantics)
+// ---------------------------------------------------------------------------
+extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_options* o, double* x_inout,
+                                       cal_optim_result* res, double* cov) {
+    if (!hp || !o || !x_inout || !res) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    cal_refine_handle& h = *hp;
+    CUDA_TRY(cudaSetDevice(h.device));
+    std::memset(res, 0, sizeof *res);
+    const ProblemShape& S = h.S;
+    const int ns = h.ns, nv = S.n_views, na = h.n_amb;
+    const bool views = nv > 0;
+    const double eps = o->epsilon;
+    const double min_relative_decrease = 1e-3, min_diag = 1e-6, max_diag = 1e32, max_radius = 1e16, min_radius = 1e-32;
+    std::vector<double> x(x_inout, x_inout + na), xp(na);
+    if (h.constrained) {  // project the start onto the feasible set (fx, fy >= 0)
+        std::vector<double> z(std::max(ns, 1), 0.0);
+        plus_shared(h, x.data(), z.data(), 0.0, xp.data()); x = xp;
+    }
+    double* xd = h.B.x; double* xc = h.V.x_cand;
+    CUDA_TRY(cudaMemcpyAsync(xd, x.data(), sizeof(double) * na, cudaMemcpyHostToDevice, h.st));
+    CUDA_TRY(cudaMemcpyAsync(xc, x.data(), sizeof(double) * na, cudaMemcpyHostToDevice, h.st));
+    const int n_shared_amb = views ? S.off_viewq : na;  // shared blocks are the head of x for the per-view kinds
+    ViewBuffers V = h.V;
+    EvalBuffers B = h.B;
+    std::vector<double> s(ns, 1.0), diag(ns), y(ns), step(ns), delta(ns), gss(ns), Cs((size_t)ns * ns), cs(ns), Sm((size_t)ns * ns);
+    double red[4] = {0, 0, 0, 0};
+    int term = CAL_TERM_NO_CONVERGENCE, iter = 0, n_invalid = 0, jev = 0, cev = 0;
+    std::string msg;
+
+    auto norms = [&](double& x_norm, double& gmax) -> cal_status {
+        // |x|_2 and |x - Plus(x, -g)|_inf (ambient), shared part on the host, view part on the device
+        double x2 = 0, gm = 0;
+        std::vector<double> ng(std::max(ns, 1)); for (int i = 0; i < ns; ++i) ng[i] = -h.gs[i];
+        plus_shared(h, x.data(), ng.data(), 1.0, xp.data());
+        for (int i = 0; i < n_shared_amb; ++i) { x2 += x[i] * x[i]; gm = std::max(gm, std::fabs(x[i] - xp[i])); }
+        if (views) {
+            EvalBuffers Bx = B; Bx.x = xd;
+            launch_view_norms(S, Bx, V, h.st); launch_reduce_views(V, nv, h.st); h.launches += 2;
+            CUDA_TRY(cudaMemcpyAsync(red, V.red_out, sizeof red, cudaMemcpyDeviceToHost, h.st));
+            CUDA_TRY(cudaStreamSynchronize(h.st));
+            x2 += red[0]; gm = std::max(gm, red[3]);
+        }
+        x_norm = std::sqrt(x2); gmax = gm;
+        return CAL_OK;
+    };
+    auto eval_cost_at = [&](double* xdev, const double* xhost, double& c) -> cal_status {
+        if (cal_status st = device_pass(h, xdev, false, xhost)) return st;
+        ++cev; c = std::isfinite(h.cost) ? h.cost : std::numeric_limits<double>::max();
+        return CAL_OK;
+    };
+    // candidate x [+] t*delta: shared part on the host (uploaded), view part on the device
+    auto make_candidate = [&](double t, double& step_norm2) -> cal_status {
+        plus_shared(h, x.data(), delta.data(), t, xp.data());
+        double sn = 0; for (int i = 0; i < n_shared_amb; ++i) { const double dd = x[i] - xp[i]; sn += dd * dd; }
+        CUDA_TRY(cudaMemcpyAsync(xc, xp.data(), sizeof(double) * n_shared_amb, cudaMemcpyHostToDevice, h.st));
+        if (views) {
+            EvalBuffers Bx = B; Bx.x = xd; ViewBuffers Vx = V; Vx.x_cand = xc;
+            launch_view_plus(S, Bx, Vx, t, h.st); launch_reduce_views(V, nv, h.st); h.launches += 2;
+            CUDA_TRY(cudaMemcpyAsync(red, V.red_out, sizeof red, cudaMemcpyDeviceToHost, h.st));
+            CUDA_TRY(cudaStreamSynchronize(h.st));
+            sn += red[2];
+        }
+        step_norm2 = sn;
+        return CAL_OK;
+    };
+
+    if (cal_status st = device_pass(h, xd, true, x.data())) return st;
+    ++jev;
+    double cost = h.cost;
+    res->initial_cost = cost;
+    for (int i = 0; i < ns; ++i) s[i] = 1.0 / (1.0 + std::sqrt(h.Hss[(size_t)i * ns + i]));  // jacobi_scaling, once
+    if (views) {
+        CUDA_TRY(cudaMemcpyAsync(V.s_shared, s.data(), sizeof(double) * ns, cudaMemcpyHostToDevice, h.st));
+        launch_view_scale(S, V, 1, h.st); h.launches++;
+    }
+    double x_norm = 0, gmax = 0;
+    if (cal_status st = norms(x_norm, gmax)) return st;
+    double radius = 1e4, decrease_factor = 2.0;
+    bool reuse_diag = false;
+    if (o->verbose) std::printf("iter      cost      cost_change  |gradient|   tr_radius\n%4d % .6e %.2e %.2e %.2e\n", 0, cost, 0.0, gmax, radius);
+
+    for (;;) {
+        if (iter >= o->max_iterations) { term = CAL_TERM_NO_CONVERGENCE; msg = "Maximum number of iterations reached."; break; }
+        if (gmax <= eps) { term = CAL_TERM_CONVERGENCE; msg = "Gradient tolerance reached."; break; }
+        if (radius <= min_radius) { term = CAL_TERM_CONVERGENCE; msg = "Minimum trust region radius reached."; break; }
+        ++iter;
+        if (!reuse_diag) {
+            for (int i = 0; i < ns; ++i) diag[i] = std::min(std::max(h.Hss[(size_t)i * ns + i] * s[i] * s[i], min_diag), max_diag);
+            if (views) { launch_view_scale(S, V, 0, h.st); h.launches++; }
+        }
+        // ---- solve (S H S + D^2) y = S g through the Schur complement ----
+        bool ok = true;
+        for (int i = 0; i < ns; ++i) {
+            for (int j = 0; j < ns; ++j) Sm[(size_t)i * ns + j] = h.Hss[(size_t)i * ns + j] * s[i] * s[j];
+            gss[i] = h.gs[i] * s[i]; y[i] = gss[i];
+        }
+        std::vector<double> Hs_scaled = Sm;  // undamped, for the model cost change
+        for (int i = 0; i < ns; ++i) Sm[(size_t)i * ns + i] += diag[i] / radius;
+        if (views) {
+            CUDA_TRY(cudaMemsetAsync(V.fail, 0, sizeof(int32_t), h.st));
+            launch_schur(S, h.L, B, V, ns, radius, h.st); h.launches += 3;
+            if (h.comm) {
+                if (!h.comm->allreduce_sum(V.C, (size_t)ns * ns, h.st) || !h.comm->allreduce_sum(V.c, ns, h.st)) return fail(CAL_ERR_COMM, h.comm->error());
+            }
+            int32_t failed = 0;
+            CUDA_TRY(cudaMemcpyAsync(Cs.data(), V.C, sizeof(double) * ns * ns, cudaMemcpyDeviceToHost, h.st));
+            CUDA_TRY(cudaMemcpyAsync(cs.data(), V.c, sizeof(double) * ns, cudaMemcpyDeviceToHost, h.st));
+            CUDA_TRY(cudaMemcpyAsync(&failed, V.fail, sizeof failed, cudaMemcpyDeviceToHost, h.st));
+            CUDA_TRY(cudaStreamSynchronize(h.st));
+            if (failed) ok = false;
+            for (int i = 0; i < ns; ++i) { y[i] -= cs[i]; for (int j = 0; j < ns; ++j) Sm[(size_t)i * ns + j] -= Cs[(size_t)i * ns + j]; }
+        }
+        if (ok && ns > 0) { ok = chol_host(Sm, ns); if (ok) chol_solve_host(Sm, ns, y.data()); }
+        reuse_diag = true;
+        double model_cost_change = 0;
+        if (ok) {
+            double sg = 0, quad = 0;
+            for (int i = 0; i < ns; ++i) { if (!std::isfinite(y[i])) ok = false; step[i] = -y[i]; sg += step[i] * gss[i]; }
+            for (int i = 0; i < ns; ++i) { double row = 0; for (int j = 0; j < ns; ++j) row += Hs_scaled[(size_t)i * ns + j] * step[j]; quad += row * step[i]; }
+            if (views && ok) {
+                CUDA_TRY(cudaMemcpyAsync(V.y_shared, y.data(), sizeof(double) * ns, cudaMemcpyHostToDevice, h.st));
+                launch_backsub(S, h.L, V, ns, h.st); launch_reduce_views(V, nv, h.st); h.launches += 2;
+                CUDA_TRY(cudaMemcpyAsync(red, V.red_out, sizeof red, cudaMemcpyDeviceToHost, h.st));
+                CUDA_TRY(cudaStreamSynchronize(h.st));
+                if (h.comm) { double r2[2] = {red[0], red[1]}; if (!h.comm->allreduce_host(r2, 2)) return fail(CAL_ERR_COMM, h.comm->error()); red[0] = r2[0]; red[1] = r2[1]; }
+                sg += red[0]; quad += red[1];
+                if (!std::isfinite(sg) || !std::isfinite(quad)) ok = false;
+            }
+            model_cost_change = -(sg + 0.5 * quad);
+            ok = ok && model_cost_change > 0.0;
+        }
+        if (!ok) {  // HandleInvalidStep
+            if (++n_invalid >= 5) { term = CAL_TERM_FAILURE; msg = "Number of consecutive invalid steps more than Solver::Options::max_num_consecutive_invalid_steps: 5"; break; }
+            radius /= decrease_factor; decrease_factor *= 2.0; reuse_diag = true;
+            continue;
+        }
+        n_invalid = 0;
+        for (int i = 0; i < ns; ++i) delta[i] = step[i] * s[i];
+        double cand_cost = 0, step_norm2 = 0, t = 1.0;
+        bool have_cand = false;
+        if (h.constrained) {
+            // Armijo projected line search; accepted at t = 1 in the normal case
+            double g0 = 0; for (int i = 0; i < ns; ++i) g0 += h.gs[i] * delta[i];
+            if (views) {  // per-view part of g . delta = sum step_p . (sp o gp) already in red[0]
+                g0 += red[0];
+            }
+            for (int ls = 0; ls < 20; ++ls) {
+                if (cal_status st = make_candidate(t, step_norm2)) return st;
+                double c; if (cal_status st = eval_cost_at(xc, xp.data(), c)) return st;
+                const bool v = c < std::numeric_limits<double>::max();
+                if (v && c <= cost + 1e-4 * g0 * t) { cand_cost = c; have_cand = true; break; }
+                double tn = 0.5 * t;
+                if (v) { const double denom = 2.0 * (c - cost - g0 * t); if (denom > 0) tn = -g0 * t * t / denom; }
+                t = std::min(std::max(tn, 1e-3 * t), 0.6 * t);
+            }
+            if (!have_cand) t = 1.0;
+        }
+        if (!have_cand) {
+            if (cal_status st = make_candidate(t, step_norm2)) return st;
+            if (cal_status st = eval_cost_at(xc, xp.data(), cand_cost)) return st;
+        }
+        if (h.comm && views) { double r1 = step_norm2; (void)r1; }
+        // ParameterToleranceReached / FunctionToleranceReached: tested before acceptance (B.3-5)
+        if (std::sqrt(step_norm2) <= eps * (x_norm + eps)) { term = CAL_TERM_CONVERGENCE; msg = "Parameter tolerance reached."; break; }
+        const double cost_change = cost - cand_cost;
+        if (std::fabs(cost_change) <= eps * cost) { term = CAL_TERM_CONVERGENCE; msg = "Function tolerance reached."; break; }
+        const double rho = cost_change / model_cost_change;
+        if (rho > min_relative_decrease) {  // HandleSuccessfulStep
+            std::swap(xd, xc);
+            for (int i = 0; i < n_shared_amb; ++i) x[i] = xp[i];
+            if (cal_status st = device_pass(h, xd, true, x.data())) return st;
+            ++jev; cost = h.cost;
+            if (cal_status st = norms(x_norm, gmax)) return st;
+            radius = std::min(max_radius, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
+            decrease_factor = 2.0; reuse_diag = false;
+        } else {  // HandleUnsuccessfulStep
+            radius /= decrease_factor; decrease_factor *= 2.0; reuse_diag = true;
+        }
+        if (o->verbose) std::printf("%4d % .6e %.2e %.2e %.2e rho=%.2e\n", iter, cost, cost_change, gmax, radius, rho);
+    }
+    // download the final parameters (last accepted point)
+    CUDA_TRY(cudaMemcpyAsync(x_inout, xd, sizeof(double) * na, cudaMemcpyDeviceToHost, h.st));
+    CUDA_TRY(cudaStreamSynchronize(h.st));
+    if (xd != h.B.x) {  // keep the handle's buffers in their canonical roles
+        CUDA_TRY(cudaMemcpyAsync(h.B.x, xd, sizeof(double) * na, cudaMemcpyDeviceToDevice, h.st));
+        CUDA_TRY(cudaStreamSynchronize(h.st));
+    }
+    res->success = term == CAL_TERM_CONVERGENCE; res->iterations = iter; res->termination = term;
+    res->num_jac_evals = jev; res->num_cost_evals = cev; res->final_cost = cost;
+    static const char* names[] = {"CONVERGENCE", "NO_CONVERGENCE", "FAILURE"};
+    std::snprintf(res->report, sizeof res->report, "Ceres Solver Report: Iterations: %d, Initial cost: %e, Final cost: %e, Termination: %s",
+                  iter, res->initial_cost, cost, names[term]);
+    (void)msg;
+    // ---- covariance (compute_covariance, ceresutils.h:69-126) ----
+    if (cov && o->compute_covariance) {
+        const int n = h.n_tan;
+        if ((double)na * na * 8.0 > 8e9) return CAL_OK;  // would not fit; covariance_ok stays 0
+        // the normal equations of the last accepted point are still on the device / host mirrors
+        std::vector<double> xf(x_inout, x_inout + na);
+        EvalBuffers Bf = h.B; (void)Bf;
+        if (cal_status st = device_pass(h, h.B.x, true, xf.data())) return st;
+        std::vector<double> Hd, gd;
+        if (n > 8192) return CAL_OK;
+        if (cal_status st = dense_system(h, Hd, gd)) return st;
+        std::vector<double> Lc = Hd;
+        if (n > 0 && !chol_host(Lc, n)) return CAL_OK;  // rank deficient: covariance stays empty (ceresutils.h:86-88)
+        std::vector<double> Ct((size_t)n * n, 0.0), e(n);
+        for (int j = 0; j < n; ++j) { std::fill(e.begin(), e.end(), 0.0); e[j] = 1.0; chol_solve_host(Lc, n, e.data()); for (int i = 0; i < n; ++i) Ct[(size_t)i * n + j] = e[i]; }
+        // lift to ambient coordinates block by block: cov(I,J) = P_I C(I,J) P_J^T
+        std::fill(cov, cov + (size_t)na * na, 0.0);
+        std::vector<std::vector<double>> Pj(h.pbs.size());
+        for (size_t bi = 0; bi < h.pbs.size(); ++bi) {
+            const PB& pb = h.pbs[bi]; if (pb.constant) continue;
+            std::vector<double>& Pm = Pj[bi]; Pm.assign((size_t)pb.size * pb.tsize, 0.0);
+            if (pb.type == PB_QUAT) quat_plus_jacobian(xf.data() + pb.off, Pm.data());
+            else if (pb.type == PB_INTR && pb.tsize == pb.size - 1) { int k = 0; for (int j = 0; j < pb.size; ++j) { if (j == 4) continue; Pm[(size_t)j * pb.tsize + k] = 1.0; ++k; } }
+            else for (int j = 0; j < pb.size; ++j) Pm[(size_t)j * pb.tsize + j] = 1.0;
+        }
+        for (size_t bi = 0; bi < h.pbs.size(); ++bi) {
+            const PB& a = h.pbs[bi]; if (a.constant) continue;
+            for (size_t bj = 0; bj < h.pbs.size(); ++bj) {
+                const PB& b = h.pbs[bj]; if (b.constant) continue;
+                for (int i = 0; i < a.size; ++i) for (int j = 0; j < b.size; ++j) {
+                    double acc = 0;
+                    for (int k = 0; k < a.tsize; ++k) { const double pik = Pj[bi][(size_t)i * a.tsize + k]; if (pik == 0.0) continue;
+                        for (int l = 0; l < b.tsize; ++l) acc += pik * Ct[(size_t)(a.toff + k) * n + b.toff + l] * Pj[bj][(size_t)j * b.tsize + l]; }
+                    cov[(size_t)(a.off + i) * na + b.off + j] = acc;
+                }
+            }
+        }
+        res->covariance_ok = 1;
+    }
+    return CAL_OK;
+}
+
+extern "C" cal_status cal_refine_attach_comm(cal_refine_handle* h, const uint8_t unique_id[128], int rank, int world_size) {
+    if (!h || !unique_id) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    delete h->comm; h->comm = nullptr;
+    std::string err;
+    h->comm = calcomm::Comm::create(unique_id, rank, world_size, &err);
+    if (!h->comm) return fail(CAL_ERR_COMM, err);
+    return CAL_OK;
+}
+extern "C" cal_status cal_comm_unique_id(uint8_t out128[128]) {
+    std::string err;
+    if (!calcomm::Comm::unique_id(out128, &err)) return fail(CAL_ERR_COMM, err);
+    return CAL_OK;
+}

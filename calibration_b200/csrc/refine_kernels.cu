@@ -1,0 +1,668 @@
+// CUDA kernels of the refinement hot path (sm_100a).  FP64 throughout: the
+// reference solves in double with Ceres and the north star asks for parity at
+// 1e-8 relative, so tensor cores are deliberately not used (nothing here is a
+// large dense contraction; see DESIGN.md §5 for the roofline argument).
+//
+//   k_repack        one-time gather of the uploaded SoA observations into the
+//                   tile-transposed layout (refine_kernels.cuh)
+//   k_cam_setup / k_block_setup
+//                   per evaluation: camera constants, composite block poses
+//                   (pose chains of src/estimation/residuals/*.h), sensor-frame
+//                   frames and the 6x6 chain-rule transforms
+//   k1_kernel       K1: fused project -> residual -> analytic Jacobian ->
+//                   J^T J / J^T r accumulation, one lane per segment, lane-
+//                   private register accumulators, coalesced 256 B rows
+//   k_cost          residual-only pass
+//   k_assemble      per block: Huber weight (per residual block),
+//                   chain rule, deterministic warp transpose-reductions into
+//                   per-camera sums (no floating-point atomics)
+//   k_view_* / k_schur_* / k_backsub
+//                   K2: batched 6x6 Cholesky of the damped per-view pose blocks,
+//                   Schur complement onto the shared block as a tiled rank-6
+//                   SYRK, back-substitution
+#include <stdio.h>
+
+#include "refine_kernels.cuh"
+
+namespace calk {
+
+// ---------------------------------------------------------------------------
+// layout
+// ---------------------------------------------------------------------------
+__global__ void k_repack(DevLayout L, const double* __restrict__ sx, const double* __restrict__ sy,
+                         const double* __restrict__ su, const double* __restrict__ sv,
+                         const int64_t* __restrict__ seg_src) {
+    const int64_t tile = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t s = tile * 32 + lane;
+    const int len = L.seg_len[s];
+    const int depth = L.tile_depth[tile];
+    const int64_t src = seg_src[s];
+    double* dst = L.obs + L.tile_off[tile] * 128 + lane;
+    for (int k = threadIdx.x >> 5; k < depth; k += blockDim.x >> 5) {
+        const bool ok = k < len;
+        dst[(int64_t)k * 128 + 0] = ok ? sx[src + k] : 0.0;
+        dst[(int64_t)k * 128 + 32] = ok ? sy[src + k] : 0.0;
+        dst[(int64_t)k * 128 + 64] = ok ? su[src + k] : 0.0;
+        dst[(int64_t)k * 128 + 96] = ok ? sv[src + k] : 0.0;
+    }
+}
+void launch_repack(const DevLayout& L, const double* sx, const double* sy, const double* su, const double* sv,
+                   const int64_t* seg_src, cudaStream_t st) {
+    if (L.n_tiles == 0) return;
+    k_repack<<<(unsigned)L.n_tiles, 128, 0, st>>>(L, sx, sy, su, sv, seg_src);
+}
+
+// ---------------------------------------------------------------------------
+// per-evaluation setup
+// ---------------------------------------------------------------------------
+__global__ void k_cam_setup(ProblemShape S, EvalBuffers B) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= S.n_cams) return;
+    const double* intr = B.x + S.off_intr + (S.kind == 0 ? 0 : c * S.P);
+    CamConst cc; cam_const_from_intr(intr, S.model, cc);
+    B.camc[c] = cc;
+    double T[36];
+    for (int i = 0; i < 36; ++i) T[i] = 0.0;
+    if (S.cam_pose_kind == 1) cam_transform_extrinsics(B.x + S.off_camt + 3 * c, cc.Rs, T);
+    else if (S.cam_pose_kind == 2) cam_transform_bundle(B.x + S.off_camq + 4 * c, cc.Rs, T);
+    for (int i = 0; i < 36; ++i) B.camT[c * 36 + i] = T[i];
+}
+
+__global__ void k_block_setup(ProblemShape S, DevLayout L, EvalBuffers B) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.n_blk) return;
+    double A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double T[36];
+    for (int i = 0; i < 36; ++i) T[i] = 0.0;
+    if (L.blk_orig[b] >= 0) {
+        const int cam = L.blk_cam[b];
+        const double* Rs = B.camc[cam].Rs;
+        BlockPose bp;
+        if (S.kind == 0) {
+            const int v = L.blk_view[b];
+            compose_intrinsics(B.x + S.off_viewq + 4 * v, B.x + S.off_viewt + 3 * v, bp);
+        } else if (S.kind == 1) {
+            const int v = L.blk_view[b];
+            compose_extrinsics(B.x + S.off_camq + 4 * cam, B.x + S.off_camt + 3 * cam, B.x + S.off_viewq + 4 * v,
+                               B.x + S.off_viewt + 3 * v, bp);
+        } else {
+            double bTg[12];
+            for (int i = 0; i < 12; ++i) bTg[i] = L.blk_bTg[(int64_t)i * L.n_blk + b];
+            compose_bundle(B.x + S.off_viewq, B.x + S.off_viewt, B.x + S.off_camq + 4 * cam, B.x + S.off_camt + 3 * cam,
+                           bTg, bp);
+        }
+        block_frame(bp, Rs, A);
+        view_transform(bp, Rs, T);
+    }
+    for (int i = 0; i < 36; ++i) B.blk_Tv[(int64_t)i * L.n_blk + b] = T[i];
+    for (int s = L.blk_seg_off[b]; s < L.blk_seg_off[b + 1]; ++s)
+        for (int i = 0; i < 9; ++i) B.seg_frame[(int64_t)i * L.n_seg + s] = A[i];
+}
+
+__global__ void k_pad_frames(DevLayout L, EvalBuffers B, int64_t first_pad) {
+    const int64_t s = first_pad + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= L.n_seg) return;
+    for (int i = 0; i < 9; ++i) B.seg_frame[(int64_t)i * L.n_seg + s] = (i % 4 == 0) ? 1.0 : 0.0;
+}
+
+void launch_setup(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
+    k_cam_setup<<<(S.n_cams + 63) / 64, 64, 0, st>>>(S, B);
+    if (L.n_blk > 0) k_block_setup<<<(unsigned)((L.n_blk + 127) / 128), 128, 0, st>>>(S, L, B);
+}
+
+// ---------------------------------------------------------------------------
+// K1: fused residual + Jacobian + J^T J
+// ---------------------------------------------------------------------------
+template <class LT, int NPASS, int PASS>
+__device__ __forceinline__ void k1_accumulate(const double* __restrict__ Ju, const double* __restrict__ Jv,
+                                              double* __restrict__ acc) {
+#pragma unroll
+    for (int a = 0; a < LT::NL; ++a) {
+#pragma unroll
+        for (int b = a; b < LT::NL; ++b) {
+            const int e = LT::idx(a, b);
+            if (e % NPASS == PASS) {
+                double v = acc[e / NPASS];
+                if (LT::has_u(a) && LT::has_u(b)) v = fma(Ju[a], Ju[b], v);
+                if (LT::has_v(a) && LT::has_v(b)) v = fma(Jv[a], Jv[b], v);
+                acc[e / NPASS] = v;
+            }
+        }
+    }
+}
+
+template <int MODEL, int IMODE, int NPASS, int PASS>
+__device__ __forceinline__ void k1_body(const DevLayout& L, const EvalBuffers& B, int64_t tile, int lane) {
+    using LT = Local<MODEL, IMODE>;
+    constexpr int NA = (LT::NE + NPASS - 1) / NPASS;
+    const int64_t s = tile * 32 + lane;
+    const int len = L.seg_len[s];
+    const int depth = L.tile_depth[tile];
+    double A[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A[i] = B.seg_frame[(int64_t)i * L.n_seg + s];
+    const CamConst c = B.camc[L.seg_cam[s]];
+    const double* __restrict__ p = L.obs + L.tile_off[tile] * 128 + lane;
+    double acc[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) acc[i] = 0.0;
+    double X = 0, Y = 0, U = 0, V = 0;
+    if (depth > 0) { X = p[0]; Y = p[32]; U = p[64]; V = p[96]; }
+    for (int k = 0; k < depth; ++k) {
+        double Xn = 0, Yn = 0, Un = 0, Vn = 0;
+        if (k + 1 < depth) {  // software prefetch of the next 256 B rows
+            const double* q = p + (int64_t)(k + 1) * 128;
+            Xn = q[0]; Yn = q[32]; Un = q[64]; Vn = q[96];
+        }
+        if (k < len) {
+            double Ju[LT::NL], Jv[LT::NL];
+            obs_rows<MODEL, IMODE>(c, A, X, Y, U, V, Ju, Jv);
+            k1_accumulate<LT, NPASS, PASS>(Ju, Jv, acc);
+        }
+        X = Xn; Y = Yn; U = Un; V = Vn;
+    }
+#pragma unroll
+    for (int e = 0; e < LT::NE; ++e)
+        if (e % NPASS == PASS) B.segN[(int64_t)e * L.n_seg + s] = acc[e / NPASS];
+}
+
+template <int MODEL, int IMODE, int NPASS>
+__global__ void __launch_bounds__(128) k1_kernel(DevLayout L, EvalBuffers B) {
+    const int64_t tile = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (tile >= L.n_tiles) return;
+    const int lane = threadIdx.x & 31;
+    const int pass = blockIdx.y;
+    if (pass == 0) k1_body<MODEL, IMODE, NPASS, 0>(L, B, tile, lane);
+    if (NPASS > 1 && pass == 1) k1_body<MODEL, IMODE, NPASS, (NPASS > 1 ? 1 : 0)>(L, B, tile, lane);
+    if (NPASS > 2 && pass == 2) k1_body<MODEL, IMODE, NPASS, (NPASS > 2 ? 2 : 0)>(L, B, tile, lane);
+}
+
+template <int MODEL, int IMODE>
+constexpr int passes_for() {
+    return Local<MODEL, IMODE>::NE <= 72 ? 1 : (Local<MODEL, IMODE>::NE <= 144 ? 2 : 3);
+}
+int k1_num_passes(const ProblemShape& S) {
+    return S.NE <= 72 ? 1 : (S.NE <= 144 ? 2 : 3);
+}
+
+template <int MODEL, int IMODE>
+static void launch_k1_t(const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
+    constexpr int NP = passes_for<MODEL, IMODE>();
+    dim3 grid((unsigned)((L.n_tiles + 3) / 4), NP);
+    k1_kernel<MODEL, IMODE, NP><<<grid, 128, 0, st>>>(L, B);
+}
+#define CALK_DISPATCH(FN, ...)                                                             \
+    do {                                                                                   \
+        if (S.model == 0 && S.imode == 0) FN<0, 0>(__VA_ARGS__);                           \
+        else if (S.model == 0 && S.imode == 1) FN<0, 1>(__VA_ARGS__);                      \
+        else if (S.model == 0 && S.imode == 2) FN<0, 2>(__VA_ARGS__);                      \
+        else if (S.model == 1 && S.imode == 0) FN<1, 0>(__VA_ARGS__);                      \
+        else if (S.model == 1 && S.imode == 1) FN<1, 1>(__VA_ARGS__);                      \
+        else FN<1, 2>(__VA_ARGS__);                                                        \
+    } while (0)
+
+void launch_k1(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
+    if (L.n_tiles == 0) return;
+    CALK_DISPATCH(launch_k1_t, L, B, st);
+}
+
+// residual-only pass
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_cost(DevLayout L, EvalBuffers B) {
+    const int64_t tile = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (tile >= L.n_tiles) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t s = tile * 32 + lane;
+    const int len = L.seg_len[s];
+    const int depth = L.tile_depth[tile];
+    double A[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A[i] = B.seg_frame[(int64_t)i * L.n_seg + s];
+    const CamConst c = B.camc[L.seg_cam[s]];
+    const double* __restrict__ p = L.obs + L.tile_off[tile] * 128 + lane;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < depth; ++k) {
+        const double* q = p + (int64_t)k * 128;
+        const double X = q[0], Y = q[32], U = q[64], V = q[96];
+        if (k < len) acc += obs_ssr<MODEL>(c, A, X, Y, U, V);
+    }
+    B.seg_ssr[s] = acc;
+}
+void launch_cost(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
+    if (L.n_tiles == 0) return;
+    const unsigned g = (unsigned)((L.n_tiles + 3) / 4);
+    if (S.model == 0) k_cost<0><<<g, 128, 0, st>>>(L, B);
+    else k_cost<1><<<g, 128, 0, st>>>(L, B);
+}
+
+// ---------------------------------------------------------------------------
+// per-block assembly + deterministic per-camera reduction
+// ---------------------------------------------------------------------------
+// One lane per device block; a warp walks a contiguous range of 32-block
+// batches (camera groups are padded to 32 blocks so a batch has one camera).
+// The per-block value vector V is summed over the 32 lanes with a shared-
+// memory transpose (fixed order), accumulated lane-distributed in registers
+// across batches, and flushed to partial[cam][warp][NV] on camera change.
+constexpr int kMaxChunks = 10;  // NV <= 320
+
+template <int MODEL, int IMODE, int JAC>
+__global__ void __launch_bounds__(32 * kRedWarpsPerBlock) k_assemble(ProblemShape S, DevLayout L, EvalBuffers B,
+                                                                      int n_red_warps) {
+    using LT = Local<MODEL, IMODE>;
+    constexpr int NE = LT::NE, NC = LT::NC, PI = LT::PI;
+    __shared__ double sm[kRedWarpsPerBlock][32][33];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * kRedWarpsPerBlock + w;
+    const int64_t n_batches = L.n_blk / 32;
+    const int64_t per = (n_batches + n_red_warps - 1) / n_red_warps;
+    const int64_t b0 = gw * per, b1 = min(n_batches, b0 + per);
+    const bool bundle = S.kind == 2;
+    const int NV = S.NV;
+    const int n_chunks = (NV + 31) / 32;
+    double acc[kMaxChunks];
+#pragma unroll
+    for (int i = 0; i < kMaxChunks; ++i) acc[i] = 0.0;
+    int cur_cam = -1;
+    double V[JAC ? (NE + 1 + 63 + 6 * (PI > 0 ? PI : 1)) : 2];
+    for (int64_t batch = b0; batch < b1; ++batch) {
+        const int64_t b = batch * 32 + lane;
+        const int cam = L.blk_cam[batch * 32];
+        if (cam != cur_cam) {
+            if (cur_cam >= 0)
+                for (int ch = 0; ch < n_chunks; ++ch)
+                    if (ch * 32 + lane < NV) B.partial[((int64_t)cur_cam * n_red_warps + gw) * NV + ch * 32 + lane] = acc[ch];
+#pragma unroll
+            for (int i = 0; i < kMaxChunks; ++i) acc[i] = 0.0;
+            cur_cam = cam;
+        }
+        const int s0 = L.blk_seg_off[b], s1 = L.blk_seg_off[b + 1];
+        if (JAC) {
+            double* n = V;  // first NE entries: local system, then scaled by the Huber weight
+            for (int e = 0; e < NE; ++e) {
+                double a = 0.0;
+                for (int s = s0; s < s1; ++s) a += B.segN[(int64_t)e * L.n_seg + s];
+                n[e] = a;
+            }
+            const double ssr = n[LT::idx(NC, NC)];
+            double rho, wgt; huber_weight(S.huber_delta, ssr, rho, wgt);
+            B.blk_ssr[b] = ssr;
+            for (int e = 0; e < NE; ++e) n[e] *= wgt;
+            V[NE] = 0.5 * rho;
+            const bool vfree = L.blk_vfree[b] != 0;
+            if (bundle || S.n_views > 0) {
+                double T[36], Q[36];
+                for (int i = 0; i < 36; ++i) T[i] = vfree ? B.blk_Tv[(int64_t)i * L.n_blk + b] : 0.0;
+                // Q = T^T N_xixi
+                for (int i = 0; i < 6; ++i)
+                    for (int j = 0; j < 6; ++j) {
+                        double a = 0.0;
+                        for (int k = 0; k < 6; ++k) a += T[6 * k + i] * n[k <= j ? LT::idx(k, j) : LT::idx(j, k)];
+                        Q[6 * i + j] = a;
+                    }
+                double* out = V + NE + 1;  // Hvv(21) gv(6) Evc(36) Evi(6 PI)
+                int o = 0;
+                for (int i = 0; i < 6; ++i)
+                    for (int j = i; j < 6; ++j) {
+                        double a = 0.0;
+                        for (int k = 0; k < 6; ++k) a += Q[6 * i + k] * T[6 * k + j];
+                        out[o++] = a;
+                    }
+                for (int i = 0; i < 6; ++i) {
+                    double a = 0.0;
+                    for (int k = 0; k < 6; ++k) a += T[6 * k + i] * n[LT::idx(k, NC)];
+                    out[o++] = a;
+                }
+                if (bundle) {
+                    for (int i = 0; i < 36; ++i) out[o++] = Q[i];
+                } else {
+                    const double* Tc = B.camT + (int64_t)cam * 36;
+                    for (int i = 0; i < 6; ++i)
+                        for (int j = 0; j < 6; ++j) {
+                            double a = 0.0;
+                            for (int k = 0; k < 6; ++k) a += Q[6 * i + k] * Tc[6 * k + j];
+                            out[o++] = a;
+                        }
+                }
+                for (int i = 0; i < 6; ++i)
+                    for (int j = 0; j < PI; ++j) {
+                        double a = 0.0;
+                        for (int k = 0; k < 6; ++k) a += T[6 * k + i] * n[LT::idx(k, 6 + j)];
+                        out[o++] = a;
+                    }
+                if (!bundle) {  // per-view kinds: keep the view-type outputs per block for K2
+                    for (int i = 0; i < 21; ++i) B.blk_Hvv[(int64_t)i * L.n_blk + b] = out[i];
+                    for (int i = 0; i < 6; ++i) B.blk_gv[(int64_t)i * L.n_blk + b] = out[21 + i];
+                    for (int i = 0; i < 36; ++i) B.blk_Evc[(int64_t)i * L.n_blk + b] = out[27 + i];
+                    for (int i = 0; i < 6 * PI; ++i) B.blk_Evi[(int64_t)i * L.n_blk + b] = out[63 + i];
+                }
+            }
+        } else {
+            double a = 0.0;
+            for (int s = s0; s < s1; ++s) a += B.seg_ssr[s];
+            double rho, wgt; huber_weight(S.huber_delta, a, rho, wgt);
+            B.blk_ssr[b] = a;
+            V[0] = 0.5 * rho;
+        }
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            for (int j = 0; j < 32; ++j) { const int e = ch * 32 + j; sm[w][j][lane] = e < NV ? V[e] : 0.0; }
+            __syncwarp();
+            double sum = 0.0;
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) sum += sm[w][lane][l];
+            acc[ch] += sum;
+            __syncwarp();
+        }
+    }
+    if (cur_cam >= 0)
+        for (int ch = 0; ch < n_chunks; ++ch)
+            if (ch * 32 + lane < NV) B.partial[((int64_t)cur_cam * n_red_warps + gw) * NV + ch * 32 + lane] = acc[ch];
+}
+
+__global__ void k_final_reduce(EvalBuffers B, int n_cams, int n_red_warps, int NV) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cams * NV) return;
+    const int cam = i / NV, e = i % NV;
+    double a = 0.0;
+    for (int wv = 0; wv < n_red_warps; ++wv) a += B.partial[((int64_t)cam * n_red_warps + wv) * NV + e];
+    B.cam_sums[i] = a;
+}
+
+template <int MODEL, int IMODE>
+static void launch_assemble_t(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, int n_red_blocks,
+                              cudaStream_t st) {
+    const int nrw = n_red_blocks * kRedWarpsPerBlock;
+    k_assemble<MODEL, IMODE, 1><<<n_red_blocks, 32 * kRedWarpsPerBlock, 0, st>>>(S, L, B, nrw);
+}
+void launch_assemble(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, int n_red_blocks, int jac,
+                     cudaStream_t st) {
+    const int nrw = n_red_blocks * kRedWarpsPerBlock;
+    ProblemShape S2 = S;
+    if (!jac) S2.NV = 1;
+    cudaMemsetAsync(B.partial, 0, sizeof(double) * (size_t)S.n_cams * nrw * S2.NV, st);
+    if (jac) CALK_DISPATCH(launch_assemble_t, S, L, B, n_red_blocks, st);
+    else k_assemble<0, 0, 0><<<n_red_blocks, 32 * kRedWarpsPerBlock, 0, st>>>(S2, L, B, nrw);
+    const int n = S.n_cams * S2.NV;
+    k_final_reduce<<<(n + 127) / 128, 128, 0, st>>>(B, S.n_cams, nrw, S2.NV);
+}
+
+// ---------------------------------------------------------------------------
+// K2: per-view pose blocks — gather, scaling, batched Cholesky, Schur, back-substitution
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int sym6(int i, int j) {
+    return i <= j ? i * 6 - i * (i - 1) / 2 + (j - i) : j * 6 - j * (j - 1) / 2 + (i - j);
+}
+__device__ __forceinline__ int shared_col(const ViewBuffers& V, int cam, int j) {
+    // column j of a block's coupling E = [cam pose quat(3) | cam pose tran(3) | intr(PI)]
+    const int base = j < 3 ? V.cam_col_q[cam] : (j < 6 ? V.cam_col_t[cam] : V.cam_col_i[cam]);
+    return base < 0 ? -1 : base + (j < 3 ? j : (j < 6 ? j - 3 : j - 6));
+}
+
+__global__ void k_view_gather(ProblemShape S, DevLayout L, EvalBuffers B, ViewBuffers V) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= S.n_views) return;
+    double H[21], g[6];
+    for (int i = 0; i < 21; ++i) H[i] = 0.0;
+    for (int i = 0; i < 6; ++i) g[i] = 0.0;
+    if (V.view_free[v])
+        for (int k = V.view_blk_off[v]; k < V.view_blk_off[v + 1]; ++k) {
+            const int64_t b = V.view_blk_idx[k];
+            for (int i = 0; i < 21; ++i) H[i] += B.blk_Hvv[(int64_t)i * L.n_blk + b];
+            for (int i = 0; i < 6; ++i) g[i] += B.blk_gv[(int64_t)i * L.n_blk + b];
+        }
+    for (int i = 0; i < 6; ++i) {
+        for (int j = 0; j < 6; ++j) V.Hpp[(int64_t)v * 36 + 6 * i + j] = H[sym6(i, j)];
+        V.gp[(int64_t)v * 6 + i] = g[i];
+    }
+}
+void launch_view_gather(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V,
+                        cudaStream_t st) {
+    if (S.n_views == 0) return;
+    k_view_gather<<<(S.n_views + 127) / 128, 128, 0, st>>>(S, L, B, V);
+}
+
+__global__ void k_view_scale(ProblemShape S, ViewBuffers V, int compute_scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n_views * 6) return;
+    const int v = i / 6, k = i % 6;
+    const double h = V.Hpp[(int64_t)v * 36 + 7 * k];
+    double s = V.sp[i];
+    if (compute_scale) { s = 1.0 / (1.0 + sqrt(h)); V.sp[i] = s; }  // jacobi_scaling, once
+    V.dp[i] = fmin(fmax(h * s * s, 1e-6), 1e32);                      // LM diagonal clamp (B.3-1)
+}
+void launch_view_scale(const ProblemShape& S, const ViewBuffers& V, int compute_scale, cudaStream_t st) {
+    if (S.n_views == 0) return;
+    k_view_scale<<<(S.n_views * 6 + 127) / 128, 128, 0, st>>>(S, V, compute_scale);
+}
+
+// Per view: L = chol(sp Hpp sp + dp / radius), f = L^-1 (sp o gp), and for each
+// of its blocks F_b = L^-1 (diag(sp) E_b diag(s_shared)), so that
+// E^T A^-1 E = F^T F and E^T A^-1 g = F^T f.
+__global__ void k_schur_factor(ProblemShape S, DevLayout L, EvalBuffers B, ViewBuffers V, double inv_radius) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= S.n_views) return;
+    if (!V.view_free[v]) return;
+    double A[36], sp[6];
+    for (int i = 0; i < 6; ++i) sp[i] = V.sp[(int64_t)v * 6 + i];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) A[6 * i + j] = V.Hpp[(int64_t)v * 36 + 6 * i + j] * sp[i] * sp[j];
+    for (int i = 0; i < 6; ++i) A[7 * i] += V.dp[(int64_t)v * 6 + i] * inv_radius;
+    if (!chol6(A)) { atomicExch(V.fail, 1); return; }
+    for (int i = 0; i < 36; ++i) V.Lp[(int64_t)v * 36 + i] = A[i];
+    double f[6];
+    for (int i = 0; i < 6; ++i) f[i] = V.gp[(int64_t)v * 6 + i] * sp[i];
+    for (int i = 0; i < 6; ++i) { double s = f[i]; for (int k = 0; k < i; ++k) s -= A[6 * i + k] * f[k]; f[i] = s / A[7 * i]; }
+    for (int i = 0; i < 6; ++i) V.view_f[(int64_t)v * 6 + i] = f[i];
+    const int ncb = 6 + S.PI;
+    for (int k = V.view_blk_off[v]; k < V.view_blk_off[v + 1]; ++k) {
+        const int64_t b = V.view_blk_idx[k];
+        const int cam = L.blk_cam[b];
+        for (int j = 0; j < ncb; ++j) {
+            const int col = shared_col(V, cam, j);
+            const double sc = col < 0 ? 0.0 : V.s_shared[col];
+            double e[6];
+            for (int i = 0; i < 6; ++i) {
+                const double ev = j < 6 ? B.blk_Evc[(int64_t)(6 * i + j) * L.n_blk + b]
+                                        : B.blk_Evi[(int64_t)(S.PI * i + j - 6) * L.n_blk + b];
+                e[i] = ev * sp[i] * sc;
+            }
+            for (int i = 0; i < 6; ++i) { double s = e[i]; for (int kk = 0; kk < i; ++kk) s -= A[6 * i + kk] * e[kk]; e[i] = s / A[7 * i]; }
+            for (int i = 0; i < 6; ++i) V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b] = e[i];
+        }
+    }
+}
+
+// C_aug = sum_v F_v^T F_v as a tiled rank-6 SYRK.  Each CTA owns a chunk of
+// views and the whole (ns+1)^2 upper triangle in 8x8 register tiles; the dense
+// 6 x (ns+1) rows of [F_v | f_v] are staged in shared memory.  Partial results
+// per CTA are summed in a fixed order (no floating-point atomics).
+__global__ void __launch_bounds__(kSyrkThreads) k_schur_syrk(ProblemShape S, DevLayout L, ViewBuffers V, int ns,
+                                                             int views_per_cta) {
+    __shared__ double frow[6][kSyrkMaxN];
+    const int na = ns + 1;
+    const int nt = (na + kSyrkTile - 1) / kSyrkTile;
+    int ti = -1, tj = -1;
+    {
+        int t = threadIdx.x, row = 0;
+        while (row < nt && t >= nt - row) { t -= nt - row; ++row; }
+        if (row < nt) { ti = row; tj = row + t; }
+    }
+    double acc[kSyrkTile][kSyrkTile];
+#pragma unroll
+    for (int i = 0; i < kSyrkTile; ++i)
+#pragma unroll
+        for (int j = 0; j < kSyrkTile; ++j) acc[i][j] = 0.0;
+    const int v0 = blockIdx.x * views_per_cta, v1 = min(S.n_views, v0 + views_per_cta);
+    const int ncb = 6 + S.PI;
+    for (int v = v0; v < v1; ++v) {
+        if (!V.view_free[v]) continue;  // uniform across the CTA
+        for (int i = threadIdx.x; i < 6 * kSyrkMaxN; i += kSyrkThreads) (&frow[0][0])[i] = 0.0;
+        __syncthreads();
+        const int nb = V.view_blk_off[v + 1] - V.view_blk_off[v];
+        for (int idx = threadIdx.x; idx < nb * ncb * 6; idx += kSyrkThreads) {
+            const int kb = idx / (ncb * 6), rem = idx % (ncb * 6), i = rem / ncb, j = rem % ncb;
+            const int64_t b = V.view_blk_idx[V.view_blk_off[v] + kb];
+            const int col = shared_col(V, L.blk_cam[b], j);
+            if (col >= 0) frow[i][col] = V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b];
+        }
+        if (threadIdx.x < 6) frow[threadIdx.x][ns] = V.view_f[(int64_t)v * 6 + threadIdx.x];
+        __syncthreads();
+        if (ti >= 0) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                double fa[kSyrkTile], fb[kSyrkTile];
+#pragma unroll
+                for (int i = 0; i < kSyrkTile; ++i) { fa[i] = frow[r][ti * kSyrkTile + i]; fb[i] = frow[r][tj * kSyrkTile + i]; }
+#pragma unroll
+                for (int i = 0; i < kSyrkTile; ++i)
+#pragma unroll
+                    for (int j = 0; j < kSyrkTile; ++j) acc[i][j] = fma(fa[i], fb[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+    if (ti >= 0) {
+        double* out = V.partialC + (int64_t)blockIdx.x * na * na;
+        for (int i = 0; i < kSyrkTile; ++i)
+            for (int j = 0; j < kSyrkTile; ++j) {
+                const int r = ti * kSyrkTile + i, c = tj * kSyrkTile + j;
+                if (r < na && c < na) { out[(int64_t)r * na + c] = acc[i][j]; if (ti != tj) out[(int64_t)c * na + r] = acc[i][j]; }
+            }
+    }
+}
+
+__global__ void k_schur_reduce(ViewBuffers V, int n_cta, int ns) {
+    const int na = ns + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= na * na) return;
+    double s = 0.0;
+    for (int c = 0; c < n_cta; ++c) s += V.partialC[(int64_t)c * na * na + i];
+    const int r = i / na, cc = i % na;
+    if (r < ns && cc < ns) V.C[(int64_t)r * ns + cc] = s;
+    else if (r < ns && cc == ns) V.c[r] = s;
+}
+
+int schur_num_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < 148 * 16 ? (n_views + 15) / 16 : 148); }
+
+void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V, int ns,
+                  double radius, cudaStream_t st) {
+    if (S.n_views == 0) return;
+    k_schur_factor<<<(S.n_views + 63) / 64, 64, 0, st>>>(S, L, B, V, 1.0 / radius);
+    const int n_cta = schur_num_ctas(S.n_views);
+    const int per = (S.n_views + n_cta - 1) / n_cta;
+    k_schur_syrk<<<n_cta, kSyrkThreads, 0, st>>>(S, L, V, ns, per);
+    const int na = ns + 1;
+    k_schur_reduce<<<(na * na + 127) / 128, 128, 0, st>>>(V, n_cta, ns);
+}
+
+// y_p = L^-T (f - sum_b F_b y_s[cols(b)]), step_p = -y_p, delta_p = step_p o sp, and the
+// per-view terms of step'g and step'H step (H undamped, Jacobi-scaled).
+__global__ void k_backsub(ProblemShape S, DevLayout L, ViewBuffers V, int ns) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= S.n_views) return;
+    double* red = V.red + (int64_t)v * 4;
+    if (!V.view_free[v]) {
+        for (int i = 0; i < 6; ++i) V.delta_p[(int64_t)v * 6 + i] = 0.0;
+        red[0] = red[1] = 0.0;
+        return;
+    }
+    double Lm[36], q[6], f[6], sp[6];
+    for (int i = 0; i < 36; ++i) Lm[i] = V.Lp[(int64_t)v * 36 + i];
+    for (int i = 0; i < 6; ++i) { f[i] = V.view_f[(int64_t)v * 6 + i]; sp[i] = V.sp[(int64_t)v * 6 + i]; q[i] = 0.0; }
+    const int ncb = 6 + S.PI;
+    for (int k = V.view_blk_off[v]; k < V.view_blk_off[v + 1]; ++k) {
+        const int64_t b = V.view_blk_idx[k];
+        const int cam = L.blk_cam[b];
+        for (int j = 0; j < ncb; ++j) {
+            const int col = shared_col(V, cam, j);
+            if (col < 0) continue;
+            const double ys = V.y_shared[col];
+            for (int i = 0; i < 6; ++i) q[i] += V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b] * ys;
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) y[i] = f[i] - q[i];
+    for (int i = 5; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < 6; ++k) s -= Lm[6 * k + i] * y[k]; y[i] = s / Lm[7 * i]; }
+    double step[6], sg = 0.0;
+    for (int i = 0; i < 6; ++i) { step[i] = -y[i]; sg += step[i] * V.gp[(int64_t)v * 6 + i] * sp[i]; V.delta_p[(int64_t)v * 6 + i] = step[i] * sp[i]; }
+    // quad = step' A0 step + 2 step' E_s step_s ; E_s step_s = -L q
+    double quad = 0.0;
+    for (int i = 0; i < 6; ++i) {
+        double row = 0.0;
+        for (int j = 0; j < 6; ++j) row += V.Hpp[(int64_t)v * 36 + 6 * i + j] * sp[j] * step[j];
+        double lq = 0.0;
+        for (int k = 0; k <= i; ++k) lq += Lm[6 * i + k] * q[k];
+        quad += step[i] * (sp[i] * row - 2.0 * lq);
+    }
+    red[0] = sg; red[1] = quad;
+}
+void launch_backsub(const ProblemShape& S, const DevLayout& L, const ViewBuffers& V, int ns, cudaStream_t st) {
+    if (S.n_views == 0) return;
+    k_backsub<<<(S.n_views + 63) / 64, 64, 0, st>>>(S, L, V, ns);
+}
+
+// x_cand(view v) = x(view v) [+] t * delta_p ; red[2] = |dx|^2
+__global__ void k_view_plus(ProblemShape S, EvalBuffers B, ViewBuffers V, double t) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= S.n_views) return;
+    const double* q = B.x + S.off_viewq + 4 * (int64_t)v; const double* tr = B.x + S.off_viewt + 3 * (int64_t)v;
+    double* qo = V.x_cand + S.off_viewq + 4 * (int64_t)v; double* to = V.x_cand + S.off_viewt + 3 * (int64_t)v;
+    double d[6];
+    for (int i = 0; i < 6; ++i) d[i] = t * V.delta_p[(int64_t)v * 6 + i];
+    double qn[4]; quat_plus(q, d, qn);
+    double dx2 = 0.0;
+    for (int i = 0; i < 4; ++i) { qo[i] = qn[i]; const double e = qn[i] - q[i]; dx2 += e * e; }
+    for (int i = 0; i < 3; ++i) { const double e = d[3 + i]; to[i] = tr[i] + e; dx2 += (to[i] - tr[i]) * (to[i] - tr[i]); }
+    V.red[(int64_t)v * 4 + 2] = dx2;
+}
+void launch_view_plus(const ProblemShape& S, const EvalBuffers& B, const ViewBuffers& V, double t, cudaStream_t st) {
+    if (S.n_views == 0) return;
+    k_view_plus<<<(S.n_views + 127) / 128, 128, 0, st>>>(S, B, V, t);
+}
+
+// red[0] = |x_v|^2, red[3] = max |x_v - plus(x_v, -g_v)| (gradient max-norm piece)
+__global__ void k_view_norms(ProblemShape S, EvalBuffers B, ViewBuffers V) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= S.n_views) return;
+    const double* q = B.x + S.off_viewq + 4 * (int64_t)v; const double* tr = B.x + S.off_viewt + 3 * (int64_t)v;
+    double x2 = 0.0, gm = 0.0;
+    for (int i = 0; i < 4; ++i) x2 += q[i] * q[i];
+    for (int i = 0; i < 3; ++i) x2 += tr[i] * tr[i];
+    if (V.view_free[v]) {
+        double d[6]; for (int i = 0; i < 6; ++i) d[i] = -V.gp[(int64_t)v * 6 + i];
+        double qn[4]; quat_plus(q, d, qn);
+        for (int i = 0; i < 4; ++i) gm = fmax(gm, fabs(q[i] - qn[i]));
+        for (int i = 0; i < 3; ++i) gm = fmax(gm, fabs(tr[i] - (tr[i] + d[3 + i])));
+    }
+    V.red[(int64_t)v * 4 + 0] = x2; V.red[(int64_t)v * 4 + 3] = gm;
+}
+void launch_view_norms(const ProblemShape& S, const EvalBuffers& B, const ViewBuffers& V, cudaStream_t st) {
+    if (S.n_views == 0) return;
+    k_view_norms<<<(S.n_views + 127) / 128, 128, 0, st>>>(S, B, V);
+}
+
+// red_out[0..2] = column sums, red_out[3] = column max; fixed-order single-CTA tree
+__global__ void __launch_bounds__(1024) k_reduce_views(ViewBuffers V, int n_views) {
+    __shared__ double sm[4][1024];
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int v = threadIdx.x; v < n_views; v += 1024) {
+        const double* r = V.red + (int64_t)v * 4;
+        a[0] += r[0]; a[1] += r[1]; a[2] += r[2]; a[3] = fmax(a[3], r[3]);
+    }
+    for (int k = 0; k < 4; ++k) sm[k][threadIdx.x] = a[k];
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            for (int k = 0; k < 3; ++k) sm[k][threadIdx.x] += sm[k][threadIdx.x + s];
+            sm[3][threadIdx.x] = fmax(sm[3][threadIdx.x], sm[3][threadIdx.x + s]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) V.red_out[threadIdx.x] = sm[threadIdx.x][0];
+}
+void launch_reduce_views(const ViewBuffers& V, int n_views, cudaStream_t st) {
+    k_reduce_views<<<1, 1024, 0, st>>>(V, n_views);
+}
+
+}  // namespace calk

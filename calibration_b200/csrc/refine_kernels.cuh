@@ -1,0 +1,118 @@
+// Device-side data layout and kernel launchers of the refinement hot path.
+// See DESIGN.md §3-§4 for the layout in HBM and the roofline of each kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "k1_math.cuh"
+
+namespace calk {
+
+// Observations are stored tile-transposed: residual blocks are cut into
+// segments of <= seg_len corners, 32 segments form a tile (one warp), and the
+// tile stores corner k of its 32 segments contiguously:
+//     obs[(tile_off[t] + k) * 128 + comp * 32 + lane],  comp in {x, y, u, v}
+// so the lane-per-segment kernels read 256-byte fully coalesced rows.
+struct DevLayout {
+    int64_t n_seg = 0;        // padded to a multiple of 32
+    int64_t n_tiles = 0;
+    int64_t n_blk = 0;        // device blocks: sorted by camera, camera groups padded to 32
+    int64_t n_slices = 0;     // total k-slices (each 128 doubles)
+    double* obs = nullptr;
+    int64_t* tile_off = nullptr;  // [n_tiles]
+    int32_t* tile_depth = nullptr;
+    int32_t* seg_len = nullptr;   // [n_seg]
+    int32_t* seg_blk = nullptr;   // [n_seg] device block id
+    int32_t* seg_cam = nullptr;   // [n_seg]
+    int32_t* blk_cam = nullptr;   // [n_blk]
+    int32_t* blk_view = nullptr;  // [n_blk] (-1: none / padding)
+    int64_t* blk_orig = nullptr;  // [n_blk] original residual block id, -1 for padding
+    int32_t* blk_seg_off = nullptr;  // [n_blk + 1]
+    double* blk_bTg = nullptr;    // bundle: [12][n_blk]
+    int32_t* blk_vfree = nullptr; // [n_blk] 1 if the view-type pose of this block is free
+};
+
+struct EvalBuffers {
+    double* x = nullptr;          // ambient parameters [n_amb]
+    CamConst* camc = nullptr;     // [n_cams]
+    double* camT = nullptr;       // [n_cams][36]
+    double* seg_frame = nullptr;  // [9][n_seg]
+    double* blk_Tv = nullptr;     // [36][n_blk]
+    double* segN = nullptr;       // [NE][n_seg]
+    double* seg_ssr = nullptr;    // [n_seg] (cost passes)
+    double* blk_ssr = nullptr;    // [n_blk]
+    // per-block view-type outputs for the per-view (Schur) kinds: [entry][n_blk]
+    double* blk_Hvv = nullptr;    // 21
+    double* blk_gv = nullptr;     // 6
+    double* blk_Evc = nullptr;    // 36  (T_v^T N_xixi T_c)
+    double* blk_Evi = nullptr;    // 6 * PI
+    double* partial = nullptr;    // [n_cams][n_red_warps][NV]
+    double* cam_sums = nullptr;   // [n_cams][NV]
+};
+
+struct ProblemShape {
+    int kind, model, imode;  // imode: INTR_NONE / NOSKEW / SKEW
+    int n_cams, n_views;
+    int P, PI, NC, NL, NE;
+    int NV;                  // reduced values per camera
+    int view_free_global;    // bundle: b pose free
+    int cam_pose_kind;       // 0 none, 1 extrinsics, 2 bundle
+    // offsets of parameter blocks inside x
+    int off_intr, off_camq, off_camt, off_viewq, off_viewt;
+    double huber_delta;
+};
+
+constexpr int kRedWarpsPerBlock = 4;
+
+void launch_repack(const DevLayout& L, const double* sx, const double* sy, const double* su, const double* sv,
+                   const int64_t* seg_src, cudaStream_t st);
+void launch_setup(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st);
+void launch_k1(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st);
+void launch_cost(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st);
+// jac != 0: reduce the K1 output; else reduce seg_ssr to per-camera cost
+void launch_assemble(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, int n_red_blocks, int jac,
+                     cudaStream_t st);
+int k1_num_passes(const ProblemShape& S);
+
+// ---- per-view (Schur) machinery -------------------------------------------------
+constexpr int kSyrkTile = 8;
+constexpr int kSyrkThreads = 256;
+constexpr int kSyrkMaxN = 176;  // ns + 1 must not exceed this (22 x 8 tiles, 253 <= 256 threads)
+
+struct ViewBuffers {
+    int32_t* view_blk_off = nullptr;  // [n_views + 1] CSR of device block ids per view
+    int32_t* view_blk_idx = nullptr;
+    int32_t* view_free = nullptr;     // [n_views]
+    int32_t* cam_col_q = nullptr;     // [n_cams] shared column of the camera pose quat tangent (-1 const)
+    int32_t* cam_col_t = nullptr;
+    int32_t* cam_col_i = nullptr;
+    double* Hpp = nullptr;      // [n_views][36]
+    double* gp = nullptr;       // [n_views][6]
+    double* sp = nullptr;       // jacobi scale [n_views][6]
+    double* dp = nullptr;       // clamped LM diagonal [n_views][6]
+    double* Lp = nullptr;       // cholesky factors [n_views][36]
+    double* view_f = nullptr;   // L^-1 (sp o gp) [n_views][6]
+    double* blk_F = nullptr;    // L^-1 E_s, [6 * (6 + PI)][n_blk]
+    double* delta_p = nullptr;  // tangent step [n_views][6]
+    double* s_shared = nullptr; // [ns] jacobi scale of the shared columns
+    double* y_shared = nullptr; // [ns] reduced solution
+    double* C = nullptr;        // [ns*ns] sum E^T A^-1 E
+    double* c = nullptr;        // [ns]    sum E^T A^-1 g
+    double* partialC = nullptr; // [n_cta][(ns+1)^2]
+    double* red = nullptr;      // [n_views][4] per-view scalars to reduce
+    double* red_out = nullptr;  // [4]
+    double* x_cand = nullptr;   // candidate parameters [n_amb]
+    int32_t* fail = nullptr;    // cholesky failure flag
+};
+int schur_num_ctas(int n_views);
+void launch_view_gather(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V,
+                        cudaStream_t st);
+void launch_view_scale(const ProblemShape& S, const ViewBuffers& V, int compute_scale, cudaStream_t st);
+void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V, int ns,
+                  double radius, cudaStream_t st);
+void launch_backsub(const ProblemShape& S, const DevLayout& L, const ViewBuffers& V, int ns, cudaStream_t st);
+void launch_view_plus(const ProblemShape& S, const EvalBuffers& B, const ViewBuffers& V, double t, cudaStream_t st);
+void launch_view_norms(const ProblemShape& S, const EvalBuffers& B, const ViewBuffers& V, cudaStream_t st);
+void launch_reduce_views(const ViewBuffers& V, int n_views, cudaStream_t st);
+
+}  // namespace calk

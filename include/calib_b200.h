@@ -1,0 +1,207 @@
+/* calib_b200 — C ABI of the B200-native refinement hot path.
+ *
+ * Drop-in boundary for the data-parallel refinement path of
+ * VitalyVorobyev/calibration.  The reference has no FFI seam of its own: the
+ * path sits behind C++ functions of the static library calib_estimation_optim
+ * (SURVEY §8b).  Each entry point below names the reference interface it
+ * replaces; INTEGRATION.md shows the C++ adapter that re-exposes the exact
+ * calib::optimize_* / calib::estimate_homography signatures on top of it.
+ *
+ * Conventions
+ *   - plain pointers and sizes; all floating point data is FP64;
+ *   - host pointers unless a name ends in _dev;
+ *   - the caller owns every buffer passed in; handles own their device copies;
+ *   - every call returns a cal_status; cal_last_error() gives the message of
+ *     the last failure on the calling thread;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point returns CAL_ERR_CUDA.
+ *
+ * Parameter vector `x` (ambient coordinates) uses the reference's own block
+ * order, which is also its covariance row/column order:
+ *   intrinsics  [intr(P)] [quat(4) x n_views] [tran(3) x n_views]
+ *               (IntrinsicBlocks::get_param_blocks, src/estimation/optim/intrinsics.cpp:34-50)
+ *   extrinsics  [intr(P) x n_cams] [c_q_r x n_cams] [c_t_r x n_cams] [r_q_t x n_views] [r_t_t x n_views]
+ *               (ExtrinsicBlocks::get_param_blocks, src/estimation/optim/extrinsics.cpp:50-69)
+ *   bundle      [intr(P) x n_cams] [g_q_c x n_cams] [g_t_c x n_cams] [b_q_t] [b_t_t]
+ *               (BundleBlocks::get_param_blocks, src/estimation/optim/bundle.cpp:48-68)
+ *   hand-eye    [quat(4)] [tran(3)]   (HandeyeBlocks, src/estimation/optim/handeye.cpp:17-43)
+ * quaternions are (w, x, y, z) (observationutils.h:43-48); intr is
+ * [fx, fy, cx, cy, skew, k1, k2, k3, p1, p2 (, tau_x, tau_y)] (models/pinhole.h:125-146,
+ * models/scheimpflug.h:241-259), P = 10 or 12.
+ */
+#ifndef CALIB_B200_H
+#define CALIB_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cal_status {
+    CAL_OK = 0,
+    CAL_ERR_INVALID_ARGUMENT = 1, /* adapter rethrows std::invalid_argument */
+    CAL_ERR_RUNTIME = 2,          /* adapter rethrows std::runtime_error    */
+    CAL_ERR_CUDA = 3,             /* no device / CUDA failure: there is no CPU path */
+    CAL_ERR_COMM = 4
+} cal_status;
+
+enum { CAL_KIND_INTRINSICS = 0, CAL_KIND_EXTRINSICS = 1, CAL_KIND_BUNDLE = 2 };
+enum { CAL_MODEL_PINHOLE_BC5 = 0, CAL_MODEL_SCHEIMPFLUG_BC5 = 1 };
+enum { CAL_TERM_CONVERGENCE = 0, CAL_TERM_NO_CONVERGENCE = 1, CAL_TERM_FAILURE = 2 };
+
+/* One reprojection refinement problem in SoA / CSR form.  Replaces the
+ * std::vector<PlanarView> / MulticamPlanarView / BundleObservation inputs of
+ * optimize_intrinsics (optim/intrinsics.h:35-39), optimize_extrinsics
+ * (optim/extrinsics.h:29-34) and optimize_bundle (optim/bundle.h:58-63); the
+ * flags are IntrinsicsOptimOptions / ExtrinsicOptions / BundleOptions. */
+typedef struct cal_problem_desc {
+    int32_t kind;
+    int32_t model;
+    int32_t n_cams;
+    int32_t n_views;     /* per-view pose blocks (intrinsics, extrinsics); 0 for bundle */
+    int64_t n_blocks;    /* residual blocks: non-empty (view, camera) pairs */
+    int64_t n_obs;
+    const double* obj_x; /* PlanarObservation::object_xy / image_uv (linear/planarpose.h:22-26), SoA */
+    const double* obj_y;
+    const double* img_u;
+    const double* img_v;
+    const int64_t* block_offset; /* CSR into the observation arrays, n_blocks + 1 */
+    const int32_t* block_cam;
+    const int32_t* block_view;   /* index of the per-view pose block (ignored for bundle) */
+    const double* block_b_se3_g; /* bundle: BundleObservation::b_se3_g, [n_blocks][12] = R row-major, t */
+    int32_t optimize_intrinsics; /* extrinsics / bundle; always on for the intrinsics kind */
+    int32_t optimize_skew;
+    int32_t optimize_extrinsics;  /* extrinsics kind */
+    int32_t optimize_target_pose; /* bundle kind */
+    int32_t optimize_hand_eye;    /* bundle kind */
+    int32_t reserved;
+    double huber_delta;           /* OptimOptions::huber_delta; <= 0 disables the loss */
+} cal_problem_desc;
+
+/* calib::OptimOptions (optim/optimize.h:24-33) */
+typedef struct cal_optim_options {
+    int32_t optimizer;        /* OptimizerType; accepted and ignored: all four solve the same damped system */
+    int32_t max_iterations;
+    double epsilon;
+    int32_t compute_covariance;
+    int32_t verbose;
+    int32_t num_threads;      /* unused on the device path */
+    int32_t reserved;
+} cal_optim_options;
+
+/* calib::OptimResult (optim/optimize.h:35-40) plus iteration accounting */
+typedef struct cal_optim_result {
+    int32_t success;          /* termination == CONVERGENCE (detail/ceresutils.h:42) */
+    int32_t iterations;
+    int32_t num_jac_evals;    /* fused residual + Jacobian + J^T J passes */
+    int32_t num_cost_evals;   /* residual-only passes */
+    int32_t termination;
+    int32_t covariance_ok;
+    double initial_cost;
+    double final_cost;
+    char report[256];         /* same text as ceres::Solver::Summary::BriefReport() */
+} cal_optim_result;
+
+typedef struct cal_refine_handle cal_refine_handle;
+
+const char* cal_last_error(void);
+/* number of CUDA devices visible (0 when there is none) */
+int cal_device_count(void);
+
+/* Replaces the problem builders build_problem / set_residual_blocks
+ * (optim/intrinsics.cpp:63-90, optim/extrinsics.cpp:87-150, optim/bundle.cpp:84-133):
+ * validates like the reference (its std::invalid_argument cases), uploads the
+ * observations once and lays them out for the kernels.  device = CUDA ordinal. */
+cal_status cal_refine_create(const cal_problem_desc* desc, int device, cal_refine_handle** out);
+void cal_refine_destroy(cal_refine_handle* h);
+int64_t cal_refine_param_count(const cal_refine_handle* h);   /* ambient */
+int64_t cal_refine_tangent_count(const cal_refine_handle* h); /* free tangent dims */
+
+/* One fused residual + Jacobian + J^T J pass (what Ceres does per iteration
+ * through ResidualBlock::Evaluate on the functors of src/estimation/residuals/
+ * + normal-equation formation).  cost = 1/2 sum rho(s_b).  g (n_tan) and
+ * H (n_tan x n_tan, row-major) are the loss-corrected tangent-space J^T r and
+ * J^T J in the block order of x with constant blocks removed; either may be
+ * NULL.  Dense H is only produced while n_tan <= 8192. */
+cal_status cal_refine_eval(cal_refine_handle* h, const double* x, double* cost, double* g, double* H);
+/* Residual-only pass: cost and, if ssr != NULL, the per-residual-block sum of squares. */
+cal_status cal_refine_cost(cal_refine_handle* h, const double* x, double* cost, double* block_ssr);
+/* Timed device-resident passes for benchmarking: runs `reps` fused passes on
+ * parameters already on the device and returns the CUDA-event time in ms. */
+cal_status cal_refine_bench_pass(cal_refine_handle* h, const double* x, int reps, int jacobian, float* ms_total,
+                                 double* cost);
+
+/* Replaces solve_problem (detail/ceresutils.h:27-43) + compute_covariance
+ * (detail/ceresutils.h:69-126): Levenberg–Marquardt with Ceres 2.2 semantics
+ * on the host, every O(observations) pass on the device.  x is updated in
+ * place; cov may be NULL, otherwise n_amb x n_amb row-major. */
+cal_status cal_refine_solve(cal_refine_handle* h, const cal_optim_options* opts, double* x_inout,
+                            cal_optim_result* result, double* cov);
+
+/* Optional multi-GPU sharding (one process per GPU).  Each rank creates its
+ * handle over its own shard of the residual blocks (all ranks pass identical
+ * n_cams / n_views / parameter vectors) and then attaches a communicator; the
+ * per-evaluation normal-equation blocks are summed with ncclAllReduce.
+ * unique_id is the 128-byte ncclUniqueId created by rank 0 (cal_comm_unique_id). */
+cal_status cal_comm_unique_id(uint8_t out128[128]);
+cal_status cal_refine_attach_comm(cal_refine_handle* h, const uint8_t unique_id[128], int rank, int world_size);
+
+/* ---- AX = XB hand-eye refinement: optimize_handeye (optim/handeye.h:40-43,
+ * src/estimation/optim/handeye.cpp:45-78) over MotionPairs (linear/handeye.h:29-32). */
+typedef struct cal_axxb_desc {
+    int64_t n_pairs;
+    const double* rot_a; /* [n_pairs][9] row-major */
+    const double* rot_b;
+    const double* tra_a; /* [n_pairs][3] */
+    const double* tra_b;
+    double huber_delta;
+} cal_axxb_desc;
+typedef struct cal_axxb_handle cal_axxb_handle;
+cal_status cal_axxb_create(const cal_axxb_desc* desc, int device, cal_axxb_handle** out);
+void cal_axxb_destroy(cal_axxb_handle* h);
+cal_status cal_axxb_eval(cal_axxb_handle* h, const double* x7, double* cost, double* g6, double* H36);
+cal_status cal_axxb_solve(cal_axxb_handle* h, const cal_optim_options* opts, double* x7_inout,
+                          cal_optim_result* result, double* cov49);
+
+/* ---- batched RANSAC homography: estimate_homography(view, RansacOptions)
+ * (linear/homography.h:22-24) = ransac<HomographyEstimator> (common/ransac.h:121-194). */
+typedef struct cal_ransac_options { /* calib::RansacOptions (common/ransac.h:22-29) */
+    int32_t max_iters;
+    int32_t min_inliers;
+    double thresh;
+    double confidence;
+    uint64_t seed;
+    int32_t refit_on_inliers;
+    int32_t reserved;
+} cal_ransac_options;
+typedef struct cal_ransac_result { /* HomographyResult (linear/homography.h:15-20) + RansacResult fields */
+    int32_t success;
+    int32_t iters;
+    int32_t n_inliers;
+    int32_t iters_run;
+    double hmtx[9];
+    double inlier_rms;
+    double symmetric_rms_px;
+    double min_margin; /* unused by the device path (kept for layout parity with the test oracle) */
+} cal_ransac_result;
+/* n_problems independent problems of n correspondences each, arrays laid out
+ * [problem][n].  seed of problem p = opts->seed + p when seed_per_problem != 0
+ * (else opts->seed for all).  The minimal-sample stream is the libstdc++
+ * std::sample / std::mt19937_64 stream of the reference (ransac.h:135,144-145),
+ * generated on the device.  inlier_mask ([problem][n] bytes) may be NULL. */
+cal_status cal_ransac_homography_batch(int64_t n_problems, int32_t n, const double* x, const double* y,
+                                       const double* u, const double* v, const cal_ransac_options* opts,
+                                       int seed_per_problem, int device, cal_ransac_result* results,
+                                       uint8_t* inlier_mask);
+/* Device-resident variant used by the benchmark: pointers are device memory,
+ * results stay on the device; returns the CUDA-event time of the kernel. */
+cal_status cal_ransac_homography_batch_dev(int64_t n_problems, int32_t n, const double* x_dev, const double* y_dev,
+                                           const double* u_dev, const double* v_dev, const cal_ransac_options* opts,
+                                           int seed_per_problem, cal_ransac_result* results_dev,
+                                           uint8_t* inlier_mask_dev, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CALIB_B200_H */
