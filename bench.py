@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native refinement hot path.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm)
+  python bench.py --impl reference --gpus N --steps K ...  (CPU arm: the oracle port on host cores)
+For N > 1 launch through torch.distributed.run (one rank per GPU).
+
+A "step" is one fused residual + Jacobian + J^T J pass (set-up kernels, K1,
+assembly/reduction, and the NCCL allreduce of the per-camera blocks when N > 1)
+over the whole workload with the observations resident in HBM.  The workload is
+BASELINE.json configs[4]: optimize_bundle, 8 cameras x 100 000 views x 88 corners
+(70.4 M observations, 2.25 GB of SoA observations >> the 126 MB L2, so no L2
+flush is needed between steps); it is sharded by views across the N ranks
+(strong scaling).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_cams, n_poses, description)
+    "c5": (8, 100000, "optimize_bundle<pinhole+BC5>: 8 cameras x 100000 views x 88 corners (70.4M observations), joint intrinsics + hand-eye + target pose"),
+    "c4": (4, 5000, "optimize_bundle<pinhole+BC5>: 4 cameras x 5000 robot poses x 88 corners (1.76M observations)"),
+    "mini": (8, 2000, "optimize_bundle<pinhole+BC5>: 8 cameras x 2000 views x 88 corners (smoke size)"),
+}
+CHUNK = 12500  # robot poses per generation chunk (8 chunks for c5)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True); self._t.start(); return self
+
+    def __exit__(self, *a):
+        self._stop.set(); self._t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def shard_chunks(n_poses, rank, world):
+    n_chunks = (n_poses + CHUNK - 1) // CHUNK
+    if n_chunks % world != 0:
+        raise SystemExit(f"workload has {n_chunks} chunks, not divisible by {world} ranks")
+    per = n_chunks // world
+    return list(range(rank * per, (rank + 1) * per))
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    from calibration_b200 import abi, capi, synth
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_cams, n_poses, desc = WORKLOADS[args.workload]
+    chunks = shard_chunks(n_poses, rank, world)
+    t0 = time.time()
+    prob, x0, xgt = synth.make_bundle(seed=137, n_cams=n_cams, n_poses=n_poses, chunk=CHUNK, chunks=chunks, pinned=True,
+                                      optimize_intrinsics=not args.fixed_intrinsics)
+    gen_s = time.time() - t0
+    n_obs_local = int(prob.desc.n_obs)
+    n_obs_total = n_obs_local * world
+    obs_bytes_local = 32 * n_obs_local + 96 * int(prob.desc.n_blocks)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make_handle():
+        h = capi.RefineHandle(prob, device=local_rank)
+        if dist is not None:
+            uid = [capi.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            h.attach_comm(uid[0], rank, world)
+        return h
+
+    h = make_handle()
+    info = h.layout_info()
+    for _ in range(max(args.warmup, 3)):
+        h.bench_pass(x0, reps=1, jacobian=True)
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ms_total, ms_k1, cost = h.bench_pass(x0, reps=args.steps, jacobian=True)
+        barrier()
+    t = torch.tensor([ms_total, ms_k1], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_k1 = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    value = n_obs_total / (ms_step * 1e-3)
+    launches_timed = 6 * args.steps
+
+    # residual-only pass (the other per-iteration O(observations) kernel)
+    ms_c, ms_ck, _ = h.bench_pass(x0, reps=args.steps, jacobian=False)
+    fp64_peak = capi.fp64_peak_tflops(local_rank)
+
+    # ---- end to end through the C ABI from pinned HOST buffers: create (H2D of all observations +
+    # layout), LM solve with covariance, results back to the host, destroy ----
+    h.close()
+    opts = abi.OptimOptions.default(compute_covariance=1)
+    barrier()
+    t0 = time.perf_counter()
+    h2 = make_handle()
+    x_fin, res, cov = h2.solve(x0, opts)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te[0])
+    n_jac, n_cost = int(res.num_jac_evals) + 1, int(res.num_cost_evals)  # +1: the covariance pass
+    e2e_value = n_obs_total * n_jac / e2e_s
+    launches_e2e = h2.launch_count()
+    solve_err = float(np.abs(x_fin - xgt).max())
+    h2.close()
+
+    if rank != 0:
+        return
+    pk, pk_src = peaks()
+    hbm_peak = float(pk["hbm_gbs"])
+    k1_ms_launch = ms_k1 / args.steps
+    achieved_gbs = obs_bytes_local / (k1_ms_launch * 1e-3) / 1e9
+    # FP64 work of K1 per observation, from the SASS instruction mix of the committed ncu capture
+    # (profiles/): DFMA counts 2 flops, DMUL/DADD 1; see DESIGN.md §5.
+    flop_per_obs = args.k1_flop_per_obs
+    k1_tflops = flop_per_obs * n_obs_local / (k1_ms_launch * 1e-3) / 1e12
+    out = {
+        "metric": "observations/s in residual+Jacobian+JtJ pass",
+        "value": value, "unit": "observations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "baseline_config": "configs[4]" if args.workload == "c5" else args.workload,
+                   "observations_total": n_obs_total, "observations_per_gpu": n_obs_local,
+                   "optimize_intrinsics": not args.fixed_intrinsics, "huber_delta": 1.0, "noise_px": 0.2,
+                   "l2_policy": "inputs (2.25 GB SoA at c5) larger than the 126 MB L2; no flush",
+                   "sharding": f"views split contiguously over {world} rank(s); NCCL allreduce of per-camera blocks each pass" if world > 1 else "single GPU",
+                   "k1_segments": info["n_segments"], "k1_passes": info["k1_passes"], "local_entries": info["local_entries"]},
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e_value, "unit": "observations/s", "h2d_bytes_per_step": 32 * n_obs_local + 96 * int(prob.desc.n_blocks),
+                "d2h_bytes_per_step": int(8 * (len(x_fin) + len(x_fin) ** 2)),
+                "what": "cal_refine_create (H2D of all observations from pinned host memory + layout) + cal_refine_solve (LM, covariance) + destroy; "
+                        "value = observations x fused passes executed / wall time",
+                "wall_s": e2e_s, "lm_iterations": int(res.iterations), "jacobian_passes": n_jac, "cost_passes": n_cost,
+                "lm_iteration_ms": 1e3 * e2e_s / max(int(res.iterations), 1), "final_cost": float(res.final_cost),
+                "converged": bool(res.success), "max_abs_param_error_vs_ground_truth": solve_err, "gpu_launches": launches_e2e},
+        "gpu_launches": launches_timed,
+        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                     "traffic": None, "peak_source": pk_src, "kernel": "k1_kernel", "kernel_ms_per_launch": k1_ms_launch,
+                     "kernel_share_of_step": ms_k1 / ms_total,
+                     "algorithmic_bytes_per_launch": obs_bytes_local,
+                     "binding_roof": "fp64",
+                     "fp64": {"achieved": k1_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": k1_tflops / fp64_peak,
+                              "flop_per_observation": flop_per_obs, "peak_source": "DFMA-chain microbenchmark run in this process"}},
+        "cost_pass": {"ms_per_step": ms_c / args.steps, "kernel_ms": ms_ck / args.steps,
+                      "value": n_obs_total / (ms_c / args.steps * 1e-3),
+                      "hbm_frac": (obs_bytes_local / (ms_ck / args.steps * 1e-3) / 1e9) / hbm_peak},
+        "setup": {"generate_s": gen_s},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, steps=3)
+    print(json.dumps(out))
+
+
+def cpu_sample_problem(args):
+    """Bounded sample of the workload for the CPU arm: the first 1/SAMPLE of the views."""
+    from calibration_b200 import synth
+    n_cams, n_poses, _ = WORKLOADS[args.workload]
+    n_sample = max(64, n_poses // args.cpu_sample_div)
+    prob, x0, xgt = synth.make_bundle(seed=137, n_cams=n_cams, n_poses=n_poses, chunk=n_sample, chunks=[0],
+                                      optimize_intrinsics=not args.fixed_intrinsics)
+    return prob, x0, n_sample
+
+
+def cpu_baseline(args, steps):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    prob, x0, n_sample = cpu_sample_problem(args)
+    cores = os.cpu_count() or 1
+    O.refine_eval(prob, x0, jac=True, threads=cores)  # warm
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.refine_eval(prob, x0, jac=True, threads=cores)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": int(prob.desc.n_obs) / dt, "unit": "observations/s", "cores": cores, "kind": "port",
+            "sample": f"first {n_sample} views x {prob.desc.n_cams} cameras x 88 corners = {int(prob.desc.n_obs)} observations, "
+                      f"{steps} fused passes of the forward-mode (Jet-width-24) restatement, OpenMP over residual blocks",
+            "ms_per_pass": dt * 1e3}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference path on the host cores (Ceres cannot be built here)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    prob, x0, n_sample = cpu_sample_problem(args)
+    cores = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        O.refine_eval(prob, x0, jac=True, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.refine_eval(prob, x0, jac=True, threads=cores)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = int(prob.desc.n_obs) / dt
+    n_cams, n_poses, desc = WORKLOADS[args.workload]
+    cb = {"value": value, "unit": "observations/s", "cores": cores, "kind": "port",
+          "sample": f"first {n_sample} views x {n_cams} cameras x 88 corners = {int(prob.desc.n_obs)} observations per step"}
+    print(json.dumps({
+        "impl": "reference", "metric": "observations/s in residual+Jacobian+JtJ pass", "value": value, "unit": "observations/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "note": "CPU restatement (oracle) of the reference's Ceres path; Ceres/Eigen are absent from this image"},
+        "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": "observations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--fixed-intrinsics", action="store_true", help="BundleOptions default (optimize_intrinsics=false)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-div", type=int, default=64)
+    ap.add_argument("--k1-flop-per-obs", type=float, default=700.0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,7 +41,11 @@ def lib():
     L.cal_refine_tangent_count.argtypes = [hp]
     L.cal_refine_eval.argtypes = [hp, dp, dp, dp, dp]
     L.cal_refine_cost.argtypes = [hp, dp, dp, dp]
-    L.cal_refine_bench_pass.argtypes = [hp, dp, C.c_int, C.c_int, C.POINTER(C.c_float), dp]
+    L.cal_refine_bench_pass.argtypes = [hp, dp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), dp]
+    L.cal_refine_launch_count.restype = i64
+    L.cal_refine_launch_count.argtypes = [hp]
+    L.cal_refine_layout_info.argtypes = [hp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), ip, ip]
+    L.cal_fp64_peak_tflops.argtypes = [C.c_int, dp]
     L.cal_refine_solve.argtypes = [hp, C.POINTER(abi.OptimOptions), dp, C.POINTER(abi.OptimResult), dp]
     L.cal_comm_unique_id.argtypes = [u8p]
     L.cal_refine_attach_comm.argtypes = [hp, u8p, C.c_int, C.c_int]
@@ -75,6 +79,12 @@ def _check(rc):
 
 def device_count():
     return int(lib().cal_device_count())
+
+
+def fp64_peak_tflops(device=0):
+    v = C.c_double()
+    _check(lib().cal_fp64_peak_tflops(device, C.cast(C.byref(v), abi.c_double_p)))
+    return v.value
 
 
 class RefineHandle:
@@ -116,10 +126,18 @@ class RefineHandle:
 
     def bench_pass(self, x, reps=1, jacobian=True):
         x = abi.as_f64(x)
-        ms = C.c_float(); cost = C.c_double()
-        _check(lib().cal_refine_bench_pass(self._h, abi.dptr(x), reps, int(jacobian), C.byref(ms),
+        ms = C.c_float(); k1 = C.c_float(); cost = C.c_double()
+        _check(lib().cal_refine_bench_pass(self._h, abi.dptr(x), reps, int(jacobian), C.byref(ms), C.byref(k1),
                                            C.cast(C.byref(cost), abi.c_double_p)))
-        return ms.value, cost.value
+        return ms.value, k1.value, cost.value
+
+    def launch_count(self):
+        return int(lib().cal_refine_launch_count(self._h))
+
+    def layout_info(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64(); d, e = C.c_int32(), C.c_int32()
+        _check(lib().cal_refine_layout_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e)))
+        return dict(n_segments=a.value, n_tiles=b.value, obs_bytes=c.value, local_entries=d.value, k1_passes=e.value)
 
     def solve(self, x0, opts=None, want_cov=True):
         x = abi.as_f64(x0).copy()

@@ -553,26 +553,33 @@ extern "C" cal_status cal_refine_cost(cal_refine_handle* h, const double* x, dou
 }
 
 extern "C" cal_status cal_refine_bench_pass(cal_refine_handle* h, const double* x, int reps, int jacobian, float* ms_total,
-                                            double* cost) {
+                                            float* ms_k1, double* cost) {
     if (!h || !x || reps <= 0) return fail(CAL_ERR_INVALID_ARGUMENT, "bad argument");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaMemcpyAsync(h->B.x, x, sizeof(double) * h->n_amb, cudaMemcpyHostToDevice, h->st));
-    cudaEvent_t e0, e1; CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    std::vector<cudaEvent_t> ev(2 * (size_t)reps + 2);
+    for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaStreamSynchronize(h->st));
-    CUDA_TRY(cudaEventRecord(e0, h->st));
+    CUDA_TRY(cudaEventRecord(ev[0], h->st));
     for (int r = 0; r < reps; ++r) {
         launch_setup(h->S, h->L, h->B, h->st);
+        CUDA_TRY(cudaEventRecord(ev[2 + 2 * r], h->st));
         if (jacobian) launch_k1(h->S, h->L, h->B, h->st); else launch_cost(h->S, h->L, h->B, h->st);
+        CUDA_TRY(cudaEventRecord(ev[3 + 2 * r], h->st));
         launch_assemble(h->S, h->L, h->B, h->n_red_blocks, jacobian ? 1 : 0, h->st);
         if (h->comm && !h->comm->allreduce_sum(h->B.cam_sums, (size_t)h->S.n_cams * (jacobian ? h->S.NV : 1), h->st))
             return fail(CAL_ERR_COMM, h->comm->error());
         if (jacobian && h->S.n_views > 0) launch_view_gather(h->S, h->L, h->B, h->V, h->st);
+        h->launches += 6 + (jacobian && h->S.n_views > 0 ? 1 : 0);
     }
-    CUDA_TRY(cudaEventRecord(e1, h->st));
-    CUDA_TRY(cudaEventSynchronize(e1));
-    float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CUDA_TRY(cudaEventRecord(ev[1], h->st));
+    CUDA_TRY(cudaEventSynchronize(ev[1]));
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0, k1 = 0; CUDA_TRY(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+    for (int r = 0; r < reps; ++r) { float t = 0; CUDA_TRY(cudaEventElapsedTime(&t, ev[2 + 2 * r], ev[3 + 2 * r])); k1 += t; }
+    for (auto& e : ev) cudaEventDestroy(e);
     if (ms_total) *ms_total = ms;
+    if (ms_k1) *ms_k1 = k1;
     if (cost) {
         const int NV = jacobian ? h->S.NV : 1;
         std::vector<double> cs((size_t)h->S.n_cams * NV);
@@ -580,6 +587,34 @@ extern "C" cal_status cal_refine_bench_pass(cal_refine_handle* h, const double* 
         double c = 0; for (int k = 0; k < h->S.n_cams; ++k) c += cs[(size_t)k * NV + (jacobian ? h->S.NE : 0)];
         *cost = c;
     }
+    return CAL_OK;
+}
+
+extern "C" int64_t cal_refine_launch_count(const cal_refine_handle* h) { return h ? h->launches : 0; }
+
+extern "C" cal_status cal_refine_layout_info(const cal_refine_handle* h, int64_t* n_segments, int64_t* n_tiles,
+                                             int64_t* obs_bytes, int32_t* local_entries, int32_t* k1_passes) {
+    if (!h) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    if (n_segments) *n_segments = h->L.n_seg;
+    if (n_tiles) *n_tiles = h->L.n_tiles;
+    if (obs_bytes) *obs_bytes = h->L.n_slices * 128 * (int64_t)sizeof(double);
+    if (local_entries) *local_entries = h->S.NE;
+    if (k1_passes) *k1_passes = k1_num_passes(h->S);
+    return CAL_OK;
+}
+
+extern "C" cal_status cal_fp64_peak_tflops(int device, double* tflops) {
+    if (!tflops) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    if (cal_device_count() <= device) return fail(CAL_ERR_CUDA, "no CUDA device: calib_b200 has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    double* scratch; CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&scratch), sizeof(double) * blocks * threads));
+    cudaStream_t st; CUDA_TRY(cudaStreamCreate(&st));
+    const float ms = dfma_peak_ms(scratch, blocks, threads, iters, st);
+    cudaStreamDestroy(st); cudaFree(scratch);
+    CUDA_TRY(cudaGetLastError());
+    *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
     return CAL_OK;
 }
 

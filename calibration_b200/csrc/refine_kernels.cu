@@ -169,10 +169,11 @@ __device__ __forceinline__ void k1_body(const DevLayout& L, const EvalBuffers& B
 
 template <int MODEL, int IMODE, int NPASS>
 __global__ void __launch_bounds__(128) k1_kernel(DevLayout L, EvalBuffers B) {
-    const int64_t tile = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    // the passes of one tile group are adjacent CTAs, so the second pass finds the rows in L2
+    const int64_t tile = (int64_t)(blockIdx.x / NPASS) * 4 + (threadIdx.x >> 5);
     if (tile >= L.n_tiles) return;
     const int lane = threadIdx.x & 31;
-    const int pass = blockIdx.y;
+    const int pass = blockIdx.x % NPASS;
     if (pass == 0) k1_body<MODEL, IMODE, NPASS, 0>(L, B, tile, lane);
     if (NPASS > 1 && pass == 1) k1_body<MODEL, IMODE, NPASS, (NPASS > 1 ? 1 : 0)>(L, B, tile, lane);
     if (NPASS > 2 && pass == 2) k1_body<MODEL, IMODE, NPASS, (NPASS > 2 ? 2 : 0)>(L, B, tile, lane);
@@ -189,7 +190,7 @@ int k1_num_passes(const ProblemShape& S) {
 template <int MODEL, int IMODE>
 static void launch_k1_t(const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
     constexpr int NP = passes_for<MODEL, IMODE>();
-    dim3 grid((unsigned)((L.n_tiles + 3) / 4), NP);
+    const unsigned grid = (unsigned)((L.n_tiles + 3) / 4) * NP;
     k1_kernel<MODEL, IMODE, NP><<<grid, 128, 0, st>>>(L, B);
 }
 #define CALK_DISPATCH(FN, ...)                                                             \
@@ -663,6 +664,30 @@ __global__ void __launch_bounds__(1024) k_reduce_views(ViewBuffers V, int n_view
 }
 void launch_reduce_views(const ViewBuffers& V, int n_views, cudaStream_t st) {
     k_reduce_views<<<1, 1024, 0, st>>>(V, n_views);
+}
+
+
+// FP64 FMA-chain microbenchmark: the sustained DFMA rate of this GPU under its
+// actual clocks, used as the denominator of the FP64 roofline fraction.
+__global__ void k_dfma_peak(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+float dfma_peak_ms(double* scratch, int blocks, int threads, int iters, cudaStream_t st) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_dfma_peak<<<blocks, threads, 0, st>>>(scratch, iters / 8);
+    cudaEventRecord(e0, st);
+    k_dfma_peak<<<blocks, threads, 0, st>>>(scratch, iters);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ms;
 }
 
 }  // namespace calk

@@ -73,6 +73,7 @@ void launch_cost(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B
 void launch_assemble(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, int n_red_blocks, int jac,
                      cudaStream_t st);
 int k1_num_passes(const ProblemShape& S);
+float dfma_peak_ms(double* scratch, int blocks, int threads, int iters, cudaStream_t st);
 
 // ---- per-view (Schur) machinery -------------------------------------------------
 constexpr int kSyrkTile = 8;

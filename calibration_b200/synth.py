@@ -143,9 +143,15 @@ def rig(n_cams):
 
 def make_bundle(seed=137, n_cams=4, n_poses=5000, rows=8, cols=11, spacing=0.02, noise=0.2, huber_delta=1.0,
                 optimize_intrinsics=True, optimize_skew=False, optimize_target_pose=True, optimize_hand_eye=True,
-                model=abi.MODEL_PINHOLE_BC5, chunk=20000, pinned=False):
-    """C4 / C5: hand-eye bundle (one block per (robot pose, camera), blocks in pose-major order)."""
-    rng = np.random.default_rng(seed)
+                model=abi.MODEL_PINHOLE_BC5, chunk=12500, chunks=None, pinned=False):
+    """C4 / C5: hand-eye bundle (one block per (robot pose, camera), blocks in pose-major order).
+
+    Poses are generated in chunks of `chunk` robot poses, chunk c from its own
+    generator seeded by (seed, c), so a shard (`chunks` = iterable of chunk ids)
+    holds exactly the bytes the full problem holds for those poses; the
+    parameters (ground truth and start) depend on `seed` only.
+    """
+    prng = np.random.default_rng(seed)
     obj = grid(rows, cols, spacing)
     m = len(obj)
     g_gt = rig(n_cams)
@@ -156,43 +162,54 @@ def make_bundle(seed=137, n_cams=4, n_poses=5000, rows=8, cols=11, spacing=0.02,
         if model == abi.MODEL_SCHEIMPFLUG_BC5:
             k = np.concatenate([k, [0.02 - 0.004 * c, -0.015 + 0.003 * c]])
         intr_gt.append(k)
-    nb = n_cams * n_poses
-    n_obs = nb * m
-    if pinned:
-        import torch
-        bufs = [torch.empty(n_obs, dtype=torch.float64).pin_memory().numpy() for _ in range(4)]
-    else:
-        bufs = [np.empty(n_obs) for _ in range(4)]
-    xs, ys, us, vs = bufs
-    bTg = np.empty((nb, 12))
-    g_inv = np.stack([G.inv_pose(T) for T in g_gt])
-    for p0 in range(0, n_poses, chunk):
-        p1 = min(n_poses, p0 + chunk); n = p1 - p0
-        # camera 0 sees the board under a random pose; the robot pose follows from the chain
-        c0_t = random_poses(rng, n, 30.0, (0.8, 1.5), 0.12)
-        b_g = b_gt[None] @ inv_poses(c0_t) @ g_inv[0][None]       # b_se3_g = b_se3_t (c_se3_t)^-1 (g_se3_c)^-1
-        g_b = inv_poses(b_g)
-        for c in range(n_cams):
-            c_t = g_inv[c][None] @ g_b @ b_gt[None]
-            uv = render(intr_gt[c], c_t, obj, rng, noise)
-            blk = (np.arange(p0, p1) * n_cams + c)
-            idx = (blk[:, None] * m + np.arange(m)[None]).ravel()
-            xs[idx] = np.tile(obj[:, 0], n); ys[idx] = np.tile(obj[:, 1], n)
-            us[idx] = uv[..., 0].ravel(); vs[idx] = uv[..., 1].ravel()
-            bTg[blk] = G.pose_to_vec12(b_g)
-    bcam = np.tile(np.arange(n_cams, dtype=np.int32), n_poses)
-    off = np.arange(nb + 1, dtype=np.int64) * m
-    prob = abi.Problem(abi.KIND_BUNDLE, model, n_cams, 0, xs, ys, us, vs, off, bcam, block_b_se3_g=bTg,
-                       optimize_intrinsics=optimize_intrinsics, optimize_skew=optimize_skew,
-                       optimize_target_pose=optimize_target_pose, optimize_hand_eye=optimize_hand_eye, huber_delta=huber_delta)
     intr0 = [k.copy() for k in intr_gt]
     if optimize_intrinsics:
         for k in intr0:
             k[0] *= 0.99; k[1] *= 1.01; k[2] += 2.0; k[3] -= 1.5
             if model == abi.MODEL_SCHEIMPFLUG_BC5:
                 k[10] += 0.005; k[11] -= 0.005
-    g0 = [perturb_pose(rng, T, 1.0, 0.005) for T in g_gt] if optimize_hand_eye else g_gt
-    b0 = perturb_pose(rng, b_gt, 1.0, 0.005) if optimize_target_pose else b_gt
+    g0 = [perturb_pose(prng, T, 1.0, 0.005) for T in g_gt] if optimize_hand_eye else g_gt
+    b0 = perturb_pose(prng, b_gt, 1.0, 0.005) if optimize_target_pose else b_gt
+
+    n_chunks = (n_poses + chunk - 1) // chunk
+    chunk_ids = list(range(n_chunks)) if chunks is None else list(chunks)
+    sizes = [min(chunk, n_poses - c * chunk) for c in chunk_ids]
+    n_local = int(sum(sizes))
+    nb = n_cams * n_local
+    n_obs = nb * m
+    if pinned:
+        import torch
+        keep = [torch.empty(n_obs, dtype=torch.float64).pin_memory() for _ in range(4)]
+        bufs = [t.numpy() for t in keep]
+    else:
+        keep = None
+        bufs = [np.empty(n_obs) for _ in range(4)]
+    xs, ys, us, vs = bufs
+    bTg = np.empty((nb, 12))
+    g_inv = np.stack([G.inv_pose(T) for T in g_gt])
+    p0 = 0
+    for cid, n in zip(chunk_ids, sizes):
+        rng = np.random.default_rng([seed, cid])
+        # camera 0 sees the board under a random pose; the robot pose follows from the chain
+        c0_t = random_poses(rng, n, 30.0, (0.8, 1.5), 0.12)
+        b_g = b_gt[None] @ inv_poses(c0_t) @ g_inv[0][None]       # b_se3_g = b_se3_t (c_se3_t)^-1 (g_se3_c)^-1
+        g_b = inv_poses(b_g)
+        sl = slice(p0 * n_cams * m, (p0 + n) * n_cams * m)
+        X = xs[sl].reshape(n, n_cams, m); Y = ys[sl].reshape(n, n_cams, m)
+        U = us[sl].reshape(n, n_cams, m); V = vs[sl].reshape(n, n_cams, m)
+        X[:] = obj[:, 0]; Y[:] = obj[:, 1]
+        for c in range(n_cams):
+            c_t = g_inv[c][None] @ g_b @ b_gt[None]
+            uv = render(intr_gt[c], c_t, obj, rng, noise)
+            U[:, c, :] = uv[..., 0]; V[:, c, :] = uv[..., 1]
+        bTg[p0 * n_cams:(p0 + n) * n_cams] = np.repeat(G.pose_to_vec12(b_g), n_cams, axis=0)
+        p0 += n
+    bcam = np.tile(np.arange(n_cams, dtype=np.int32), n_local)
+    off = np.arange(nb + 1, dtype=np.int64) * m
+    prob = abi.Problem(abi.KIND_BUNDLE, model, n_cams, 0, xs, ys, us, vs, off, bcam, block_b_se3_g=bTg,
+                       optimize_intrinsics=optimize_intrinsics, optimize_skew=optimize_skew,
+                       optimize_target_pose=optimize_target_pose, optimize_hand_eye=optimize_hand_eye, huber_delta=huber_delta)
+    prob._pinned_keep = keep
     return prob, G.pack_bundle(intr0, g0, b0), G.pack_bundle(intr_gt, g_gt, b_gt)
 
 

@@ -128,9 +128,20 @@ cal_status cal_refine_eval(cal_refine_handle* h, const double* x, double* cost, 
 /* Residual-only pass: cost and, if ssr != NULL, the per-residual-block sum of squares. */
 cal_status cal_refine_cost(cal_refine_handle* h, const double* x, double* cost, double* block_ssr);
 /* Timed device-resident passes for benchmarking: runs `reps` fused passes on
- * parameters already on the device and returns the CUDA-event time in ms. */
+ * parameters already on the device.  ms_total is the CUDA-event time of the
+ * whole region on the handle's stream, ms_k1 the summed event time of the
+ * dominant kernel (K1, or the residual-only kernel when jacobian == 0). */
 cal_status cal_refine_bench_pass(cal_refine_handle* h, const double* x, int reps, int jacobian, float* ms_total,
-                                 double* cost);
+                                 float* ms_k1, double* cost);
+/* kernels launched through this handle so far */
+int64_t cal_refine_launch_count(const cal_refine_handle* h);
+/* layout facts for the roofline arithmetic: segments, 32-segment tiles, bytes of
+ * the tile-transposed observation store, entries of the per-segment local
+ * system and the number of K1 passes */
+cal_status cal_refine_layout_info(const cal_refine_handle* h, int64_t* n_segments, int64_t* n_tiles, int64_t* obs_bytes,
+                                  int32_t* local_entries, int32_t* k1_passes);
+/* sustained FP64 FMA rate of the device (FMA-chain microbenchmark), TFLOP/s */
+cal_status cal_fp64_peak_tflops(int device, double* tflops);
 
 /* Replaces solve_problem (detail/ceresutils.h:27-43) + compute_covariance
  * (detail/ceresutils.h:69-126): Levenberg–Marquardt with Ceres 2.2 semantics
