@@ -83,7 +83,7 @@ struct cal_refine_handle {
     int n_amb = 0, n_tan = 0, ns = 0;
     bool constrained = false;
     int64_t n_blocks = 0, n_obs = 0;
-    int n_red_blocks = 1;
+    ReduceDesc R{};
     int n_syrk_cta = 1;
     std::vector<int64_t> blk_orig_host;   // device block -> original block
     std::vector<int32_t> blk_cam_host, blk_view_host;
@@ -269,6 +269,8 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         blk_vfree[b] = d.kind == CAL_KIND_BUNDLE ? (d.optimize_target_pose != 0) : (bview[b] >= 0 && h.view_free_host[bview[b]]);
     }
     blk_seg_off[nblk] = (int32_t)seg_len.size();
+    h.L.one_seg_per_blk = 1;
+    for (int64_t b = 0; b < nblk; ++b) if (borig[b] >= 0 && blk_seg_off[b + 1] - blk_seg_off[b] != 1) { h.L.one_seg_per_blk = 0; break; }
     while (seg_len.size() % 32) { seg_len.push_back(0); seg_blk.push_back(0); seg_cam.push_back(0); seg_src.push_back(0); }
     const int64_t nseg = (int64_t)seg_len.size(), ntiles = nseg / 32;
     h.L.n_seg = nseg; h.L.n_tiles = ntiles;
@@ -314,12 +316,41 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     }
     // ---- evaluation buffers ----
     EvalBuffers& B = h.B;
-    h.n_red_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 2, (nblk / 32 + kRedWarpsPerBlock - 1) / kRedWarpsPerBlock));
-    const int nrw = h.n_red_blocks * kRedWarpsPerBlock;
+    {   // column chunks for the deterministic per-camera reductions (segments and blocks)
+        auto make_chunks = [&](const std::vector<int32_t>& cam_of, int64_t n, std::vector<ColChunk>& ch, std::vector<int32_t>& off) {
+            const int64_t kChunk = 8192;
+            off.assign(S.n_cams + 1, 0);
+            int64_t i = 0;
+            std::vector<std::vector<ColChunk>> per(S.n_cams);
+            while (i < n) {
+                const int cam = cam_of[i]; int64_t j = i;
+                while (j < n && cam_of[j] == cam) ++j;
+                for (int64_t k = i; k < j; k += kChunk) per[cam].push_back(ColChunk{cam, 0, k, std::min(j, k + kChunk)});
+                i = j;
+            }
+            for (int c = 0; c < S.n_cams; ++c) { off[c] = (int32_t)ch.size(); ch.insert(ch.end(), per[c].begin(), per[c].end()); }
+            off[S.n_cams] = (int32_t)ch.size();
+        };
+        std::vector<ColChunk> sc, bc; std::vector<int32_t> so, bo;
+        std::vector<int32_t> seg_cam_trim(seg_cam.begin(), seg_cam.begin() + blk_seg_off[nblk]);
+        make_chunks(seg_cam_trim, (int64_t)seg_cam_trim.size(), sc, so);
+        make_chunks(bcam, nblk, bc, bo);
+        h.R.n_seg_chunks = (int)sc.size(); h.R.n_blk_chunks = (int)bc.size();
+        CUDA_TRY(h.alloc(&h.R.seg_chunks, sc.size())); CUDA_TRY(h.alloc(&h.R.blk_chunks, bc.size()));
+        CUDA_TRY(h.alloc(&h.R.seg_cam_chunk_off, so.size())); CUDA_TRY(h.alloc(&h.R.blk_cam_chunk_off, bo.size()));
+        CUDA_TRY(upload(h.R.seg_chunks, sc, h.st)); CUDA_TRY(upload(h.R.blk_chunks, bc, h.st));
+        CUDA_TRY(upload(h.R.seg_cam_chunk_off, so, h.st)); CUDA_TRY(upload(h.R.blk_cam_chunk_off, bo, h.st));
+        CUDA_TRY(cudaStreamSynchronize(h.st));
+    }
+    const int n_brows = S.NV - S.NE;
     CUDA_TRY(h.alloc(&B.x, h.n_amb)); CUDA_TRY(h.alloc(&B.camc, S.n_cams)); CUDA_TRY(h.alloc(&B.camT, (size_t)S.n_cams * 36));
     CUDA_TRY(h.alloc(&B.seg_frame, (size_t)9 * nseg)); CUDA_TRY(h.alloc(&B.blk_Tv, (size_t)36 * nblk));
     CUDA_TRY(h.alloc(&B.segN, (size_t)S.NE * nseg)); CUDA_TRY(h.alloc(&B.seg_ssr, nseg)); CUDA_TRY(h.alloc(&B.blk_ssr, nblk));
-    CUDA_TRY(h.alloc(&B.partial, (size_t)S.n_cams * nrw * S.NV)); CUDA_TRY(h.alloc(&B.cam_sums, (size_t)S.n_cams * S.NV));
+    CUDA_TRY(h.alloc(&B.partial, (size_t)std::max(h.R.n_seg_chunks, 1) * S.NE)); CUDA_TRY(h.alloc(&B.partial_blk, (size_t)std::max(h.R.n_blk_chunks, 1) * n_brows));
+    CUDA_TRY(h.alloc(&B.cam_sums, (size_t)S.n_cams * S.NV));
+    CUDA_TRY(h.alloc(&B.blk_w, nblk)); CUDA_TRY(h.alloc(&B.seg_w, nseg)); CUDA_TRY(h.alloc(&B.blk_rows, (size_t)n_brows * nblk));
+    CUDA_TRY(cudaMemsetAsync(B.seg_w, 0, sizeof(double) * nseg, h.st));
+    CUDA_TRY(cudaMemsetAsync(B.blk_rows, 0, sizeof(double) * n_brows * nblk, h.st));
     CUDA_TRY(cudaMemsetAsync(B.seg_frame, 0, sizeof(double) * 9 * nseg, h.st));
     CUDA_TRY(cudaMemsetAsync(B.segN, 0, sizeof(double) * S.NE * nseg, h.st));
     CUDA_TRY(cudaMemsetAsync(B.seg_ssr, 0, sizeof(double) * nseg, h.st));
@@ -386,8 +417,7 @@ cal_status device_pass(cal_refine_handle& h, double* x_dev, bool jac, const doub
     const ProblemShape& S = h.S;
     launch_setup(S, h.L, B, h.st);
     if (jac) launch_k1(S, h.L, B, h.st); else launch_cost(S, h.L, B, h.st);
-    launch_assemble(S, h.L, B, h.n_red_blocks, jac ? 1 : 0, h.st);
-    h.launches += 5 + (jac ? k1_num_passes(S) - 1 : 0);
+    h.launches += 3 + launch_assemble(S, h.L, B, h.R, jac ? 1 : 0, h.st);
     const int NV = jac ? S.NV : 1;
     if (h.comm) {
         if (!h.comm->allreduce_sum(B.cam_sums, (size_t)S.n_cams * NV, h.st)) return fail(CAL_ERR_COMM, h.comm->error());
@@ -566,11 +596,10 @@ extern "C" cal_status cal_refine_bench_pass(cal_refine_handle* h, const double* 
         CUDA_TRY(cudaEventRecord(ev[2 + 2 * r], h->st));
         if (jacobian) launch_k1(h->S, h->L, h->B, h->st); else launch_cost(h->S, h->L, h->B, h->st);
         CUDA_TRY(cudaEventRecord(ev[3 + 2 * r], h->st));
-        launch_assemble(h->S, h->L, h->B, h->n_red_blocks, jacobian ? 1 : 0, h->st);
+        h->launches += 3 + launch_assemble(h->S, h->L, h->B, h->R, jacobian ? 1 : 0, h->st);
         if (h->comm && !h->comm->allreduce_sum(h->B.cam_sums, (size_t)h->S.n_cams * (jacobian ? h->S.NV : 1), h->st))
             return fail(CAL_ERR_COMM, h->comm->error());
-        if (jacobian && h->S.n_views > 0) launch_view_gather(h->S, h->L, h->B, h->V, h->st);
-        h->launches += 6 + (jacobian && h->S.n_views > 0 ? 1 : 0);
+        if (jacobian && h->S.n_views > 0) { launch_view_gather(h->S, h->L, h->B, h->V, h->st); h->launches++; }
     }
     CUDA_TRY(cudaEventRecord(ev[1], h->st));
     CUDA_TRY(cudaEventSynchronize(ev[1]));

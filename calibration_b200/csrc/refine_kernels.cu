@@ -241,151 +241,189 @@ void launch_cost(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B
 // ---------------------------------------------------------------------------
 // per-block assembly + deterministic per-camera reduction
 // ---------------------------------------------------------------------------
-// One lane per device block; a warp walks a contiguous range of 32-block
-// batches (camera groups are padded to 32 blocks so a batch has one camera).
-// The per-block value vector V is summed over the 32 lanes with a shared-
-// memory transpose (fixed order), accumulated lane-distributed in registers
-// across batches, and flushed to partial[cam][warp][NV] on camera change.
-constexpr int kMaxChunks = 10;  // NV <= 320
-
-template <int MODEL, int IMODE, int JAC>
-__global__ void __launch_bounds__(32 * kRedWarpsPerBlock) k_assemble(ProblemShape S, DevLayout L, EvalBuffers B,
-                                                                      int n_red_warps) {
-    using LT = Local<MODEL, IMODE>;
-    constexpr int NE = LT::NE, NC = LT::NC, PI = LT::PI;
-    __shared__ double sm[kRedWarpsPerBlock][32][33];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gw = blockIdx.x * kRedWarpsPerBlock + w;
-    const int64_t n_batches = L.n_blk / 32;
-    const int64_t per = (n_batches + n_red_warps - 1) / n_red_warps;
-    const int64_t b0 = gw * per, b1 = min(n_batches, b0 + per);
-    const bool bundle = S.kind == 2;
-    const int NV = S.NV;
-    const int n_chunks = (NV + 31) / 32;
-    double acc[kMaxChunks];
-#pragma unroll
-    for (int i = 0; i < kMaxChunks; ++i) acc[i] = 0.0;
-    int cur_cam = -1;
-    double V[JAC ? (NE + 1 + 63 + 6 * (PI > 0 ? PI : 1)) : 2];
-    for (int64_t batch = b0; batch < b1; ++batch) {
-        const int64_t b = batch * 32 + lane;
-        const int cam = L.blk_cam[batch * 32];
-        if (cam != cur_cam) {
-            if (cur_cam >= 0)
-                for (int ch = 0; ch < n_chunks; ++ch)
-                    if (ch * 32 + lane < NV) B.partial[((int64_t)cur_cam * n_red_warps + gw) * NV + ch * 32 + lane] = acc[ch];
-#pragma unroll
-            for (int i = 0; i < kMaxChunks; ++i) acc[i] = 0.0;
-            cur_cam = cam;
-        }
-        const int s0 = L.blk_seg_off[b], s1 = L.blk_seg_off[b + 1];
-        if (JAC) {
-            double* n = V;  // first NE entries: local system, then scaled by the Huber weight
-            for (int e = 0; e < NE; ++e) {
-                double a = 0.0;
-                for (int s = s0; s < s1; ++s) a += B.segN[(int64_t)e * L.n_seg + s];
-                n[e] = a;
-            }
-            const double ssr = n[LT::idx(NC, NC)];
-            double rho, wgt; huber_weight(S.huber_delta, ssr, rho, wgt);
-            B.blk_ssr[b] = ssr;
-            for (int e = 0; e < NE; ++e) n[e] *= wgt;
-            V[NE] = 0.5 * rho;
-            const bool vfree = L.blk_vfree[b] != 0;
-            if (bundle || S.n_views > 0) {
-                double T[36], Q[36];
-                for (int i = 0; i < 36; ++i) T[i] = vfree ? B.blk_Tv[(int64_t)i * L.n_blk + b] : 0.0;
-                // Q = T^T N_xixi
-                for (int i = 0; i < 6; ++i)
-                    for (int j = 0; j < 6; ++j) {
-                        double a = 0.0;
-                        for (int k = 0; k < 6; ++k) a += T[6 * k + i] * n[k <= j ? LT::idx(k, j) : LT::idx(j, k)];
-                        Q[6 * i + j] = a;
-                    }
-                double* out = V + NE + 1;  // Hvv(21) gv(6) Evc(36) Evi(6 PI)
-                int o = 0;
-                for (int i = 0; i < 6; ++i)
-                    for (int j = i; j < 6; ++j) {
-                        double a = 0.0;
-                        for (int k = 0; k < 6; ++k) a += Q[6 * i + k] * T[6 * k + j];
-                        out[o++] = a;
-                    }
-                for (int i = 0; i < 6; ++i) {
-                    double a = 0.0;
-                    for (int k = 0; k < 6; ++k) a += T[6 * k + i] * n[LT::idx(k, NC)];
-                    out[o++] = a;
-                }
-                if (bundle) {
-                    for (int i = 0; i < 36; ++i) out[o++] = Q[i];
-                } else {
-                    const double* Tc = B.camT + (int64_t)cam * 36;
-                    for (int i = 0; i < 6; ++i)
-                        for (int j = 0; j < 6; ++j) {
-                            double a = 0.0;
-                            for (int k = 0; k < 6; ++k) a += Q[6 * i + k] * Tc[6 * k + j];
-                            out[o++] = a;
-                        }
-                }
-                for (int i = 0; i < 6; ++i)
-                    for (int j = 0; j < PI; ++j) {
-                        double a = 0.0;
-                        for (int k = 0; k < 6; ++k) a += T[6 * k + i] * n[LT::idx(k, 6 + j)];
-                        out[o++] = a;
-                    }
-                if (!bundle) {  // per-view kinds: keep the view-type outputs per block for K2
-                    for (int i = 0; i < 21; ++i) B.blk_Hvv[(int64_t)i * L.n_blk + b] = out[i];
-                    for (int i = 0; i < 6; ++i) B.blk_gv[(int64_t)i * L.n_blk + b] = out[21 + i];
-                    for (int i = 0; i < 36; ++i) B.blk_Evc[(int64_t)i * L.n_blk + b] = out[27 + i];
-                    for (int i = 0; i < 6 * PI; ++i) B.blk_Evi[(int64_t)i * L.n_blk + b] = out[63 + i];
-                }
-            }
-        } else {
-            double a = 0.0;
-            for (int s = s0; s < s1; ++s) a += B.seg_ssr[s];
-            double rho, wgt; huber_weight(S.huber_delta, a, rho, wgt);
-            B.blk_ssr[b] = a;
-            V[0] = 0.5 * rho;
-        }
-        for (int ch = 0; ch < n_chunks; ++ch) {
-            for (int j = 0; j < 32; ++j) { const int e = ch * 32 + j; sm[w][j][lane] = e < NV ? V[e] : 0.0; }
-            __syncwarp();
-            double sum = 0.0;
-#pragma unroll 8
-            for (int l = 0; l < 32; ++l) sum += sm[w][lane][l];
-            acc[ch] += sum;
-            __syncwarp();
-        }
-    }
-    if (cur_cam >= 0)
-        for (int ch = 0; ch < n_chunks; ++ch)
-            if (ch * 32 + lane < NV) B.partial[((int64_t)cur_cam * n_red_warps + gw) * NV + ch * 32 + lane] = acc[ch];
+// k_block_weight   per block: s = sum of squared residuals (sum over its
+//                  segments), Huber rho / weight (per residual BLOCK),
+//                  cost row, and the weight copied to each of its segments
+// k_view_part      per block: chain rule of the view-type pose block,
+//                  Q = T^T N_xixi, H_vv = Q T, g_v = T^T N_xir, E_vi = T^T N_xii
+// k_colsum         per-camera weighted column sums of the [row][column]
+//                  matrices (segment- or block-indexed) in fixed order: strided
+//                  per-thread sums, shuffle tree, shared-memory tree — no
+//                  floating-point atomics, so results are run-to-run identical
+template <int JAC>
+__global__ void k_block_weight(ProblemShape S, DevLayout L, EvalBuffers B, int rr_row) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.n_blk) return;
+    const int s0 = L.blk_seg_off[b], s1 = L.blk_seg_off[b + 1];
+    double ssr = 0.0;
+    for (int s = s0; s < s1; ++s) ssr += JAC ? B.segN[(int64_t)rr_row * L.n_seg + s] : B.seg_ssr[s];
+    double rho, w; huber_weight(S.huber_delta, ssr, rho, w);
+    B.blk_ssr[b] = ssr;
+    B.blk_w[b] = w;
+    B.blk_rows[b] = 0.5 * rho;  // row 0 of the block-indexed matrix: cost
+    if (JAC) for (int s = s0; s < s1; ++s) B.seg_w[s] = w;
 }
 
-__global__ void k_final_reduce(EvalBuffers B, int n_cams, int n_red_warps, int NV) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cams * NV) return;
-    const int cam = i / NV, e = i % NV;
+// ONE = every block of the launch has exactly one segment (the large-problem case): all
+// input loads are then independent straight-line loads the compiler batches (memory-level
+// parallelism); otherwise the per-block segment loop is kept.
+template <int MODEL, int IMODE, bool ONE>
+__device__ __forceinline__ void view_part_body(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, int64_t b) {
+    using LT = Local<MODEL, IMODE>;
+    constexpr int PI = LT::PI, NC = LT::NC;
+    const int s0 = L.blk_seg_off[b], s1 = ONE ? s0 + 1 : L.blk_seg_off[b + 1];
+    const double w = B.blk_w[b];
+    const bool bundle = S.kind == 2;
+    const double* __restrict__ segN = B.segN;
+    auto load = [&](int a, int c) {
+        const double* __restrict__ p = segN + (int64_t)LT::idx(a, c) * L.n_seg;
+        double v = p[s0];
+        if (!ONE) for (int s = s0 + 1; s < s1; ++s) v += p[s];
+        return v;
+    };
+    double T[36], N[21], nr[6], ni[PI > 0 ? 6 * PI : 1];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) T[i] = B.blk_Tv[(int64_t)i * L.n_blk + b];
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int c = a; c < 6; ++c) N[a * 6 - a * (a - 1) / 2 + (c - a)] = load(a, c);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) nr[k] = load(k, NC);
+#pragma unroll
+    for (int j = 0; j < PI; ++j)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ni[6 * j + k] = load(k, 6 + j);
+    double Q[36];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a = fma(T[6 * k + i], N[k <= j ? k * 6 - k * (k - 1) / 2 + (j - k) : j * 6 - j * (j - 1) / 2 + (k - j)], a);
+            Q[6 * i + j] = a * w;
+        }
+    // rows of the block-indexed matrix: 0 cost | 1..21 Hvv | 22..27 gv | 28..63 Q or Evc | 64.. Evi
+    double* __restrict__ rows = B.blk_rows;
+    const int64_t nb = L.n_blk;
+    {
+        int o = 1;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j) {
+                double a = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) a = fma(Q[6 * i + k], T[6 * k + j], a);
+                if (bundle) rows[(int64_t)o * nb + b] = a; else B.blk_Hvv[(int64_t)(o - 1) * nb + b] = a;
+                ++o;
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a = fma(T[6 * k + i], nr[k], a);
+        a *= w;
+        if (bundle) rows[(int64_t)(22 + i) * nb + b] = a; else B.blk_gv[(int64_t)i * nb + b] = a;
+    }
+    if (bundle) {
+#pragma unroll
+        for (int i = 0; i < 36; ++i) rows[(int64_t)(28 + i) * nb + b] = Q[i];
+    } else {
+        const double* __restrict__ Tc = B.camT + (int64_t)L.blk_cam[b] * 36;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                double a = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) a = fma(Q[6 * i + k], Tc[6 * k + j], a);
+                B.blk_Evc[(int64_t)(6 * i + j) * nb + b] = a;
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < PI; ++j)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a = fma(T[6 * k + i], ni[6 * j + k], a);
+            a *= w;
+            if (bundle) rows[(int64_t)(64 + PI * i + j) * nb + b] = a; else B.blk_Evi[(int64_t)(PI * i + j) * nb + b] = a;
+        }
+}
+
+template <int MODEL, int IMODE, bool ONE>
+__global__ void __launch_bounds__(128) k_view_part(ProblemShape S, DevLayout L, EvalBuffers B) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.n_blk) return;
+    if (!L.blk_vfree[b]) return;  // outputs stay zero (buffers are cleared once at create)
+    view_part_body<MODEL, IMODE, ONE>(S, L, B, b);
+}
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(256) k_colsum(const double* __restrict__ M, int64_t ld, const double* __restrict__ w,
+                                                const ColChunk* __restrict__ chunks, double* __restrict__ partial,
+                                                int n_rows) {
+    __shared__ double sm[8];
+    const ColChunk c = chunks[blockIdx.x];
+    const int row = blockIdx.y;
+    const double* __restrict__ p = M + (int64_t)row * ld;
     double a = 0.0;
-    for (int wv = 0; wv < n_red_warps; ++wv) a += B.partial[((int64_t)cam * n_red_warps + wv) * NV + e];
-    B.cam_sums[i] = a;
+    for (int64_t i = c.begin + threadIdx.x; i < c.end; i += 256) a += WEIGHTED ? p[i] * w[i] : p[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k];
+        partial[(int64_t)blockIdx.x * n_rows + row] = t;
+    }
+}
+
+__global__ void k_final_reduce(const double* __restrict__ partial, const int32_t* __restrict__ cam_chunk_off, int n_cams,
+                               int n_rows, double* __restrict__ cam_sums, int NV, int row_base) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cams * n_rows) return;
+    const int cam = i / n_rows, row = i % n_rows;
+    double a = 0.0;
+    for (int c = cam_chunk_off[cam]; c < cam_chunk_off[cam + 1]; ++c) a += partial[(int64_t)c * n_rows + row];
+    cam_sums[(int64_t)cam * NV + row_base + row] = a;
 }
 
 template <int MODEL, int IMODE>
-static void launch_assemble_t(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, int n_red_blocks,
-                              cudaStream_t st) {
-    const int nrw = n_red_blocks * kRedWarpsPerBlock;
-    k_assemble<MODEL, IMODE, 1><<<n_red_blocks, 32 * kRedWarpsPerBlock, 0, st>>>(S, L, B, nrw);
+static void launch_view_part_t(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
+    const unsigned g = (unsigned)((L.n_blk + 127) / 128);
+    if (L.one_seg_per_blk) k_view_part<MODEL, IMODE, true><<<g, 128, 0, st>>>(S, L, B);
+    else k_view_part<MODEL, IMODE, false><<<g, 128, 0, st>>>(S, L, B);
 }
-void launch_assemble(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, int n_red_blocks, int jac,
-                     cudaStream_t st) {
-    const int nrw = n_red_blocks * kRedWarpsPerBlock;
-    ProblemShape S2 = S;
-    if (!jac) S2.NV = 1;
-    cudaMemsetAsync(B.partial, 0, sizeof(double) * (size_t)S.n_cams * nrw * S2.NV, st);
-    if (jac) CALK_DISPATCH(launch_assemble_t, S, L, B, n_red_blocks, st);
-    else k_assemble<0, 0, 0><<<n_red_blocks, 32 * kRedWarpsPerBlock, 0, st>>>(S2, L, B, nrw);
-    const int n = S.n_cams * S2.NV;
-    k_final_reduce<<<(n + 127) / 128, 128, 0, st>>>(B, S.n_cams, nrw, S2.NV);
+
+int launch_assemble(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ReduceDesc& R, int jac,
+                    cudaStream_t st) {
+    int launches = 0;
+    const unsigned gb = (unsigned)((L.n_blk + 127) / 128);
+    const int rr_row = S.NL * S.NC - S.NC * (S.NC - 1) / 2;  // idx(NC, NC)
+    if (jac) k_block_weight<1><<<gb, 128, 0, st>>>(S, L, B, rr_row); else k_block_weight<0><<<gb, 128, 0, st>>>(S, L, B, rr_row);
+    ++launches;
+    const int NV = jac ? S.NV : 1;
+    const bool view_part = jac && (S.kind == 2 ? S.view_free_global != 0 : S.n_views > 0);
+    if (view_part) { CALK_DISPATCH(launch_view_part_t, S, L, B, st); ++launches; }
+    if (jac) {
+        // segment-indexed rows: the local systems, weighted per segment
+        k_colsum<true><<<dim3(R.n_seg_chunks, S.NE), 256, 0, st>>>(B.segN, L.n_seg, B.seg_w, R.seg_chunks, B.partial, S.NE);
+        k_final_reduce<<<(S.n_cams * S.NE + 127) / 128, 128, 0, st>>>(B.partial, R.seg_cam_chunk_off, S.n_cams, S.NE, B.cam_sums, NV, 0);
+        launches += 2;
+    }
+    // block-indexed rows: cost (+ the view-type part of the bundle kind)
+    const int n_brows = jac ? NV - S.NE : 1;
+    k_colsum<false><<<dim3(R.n_blk_chunks, n_brows), 256, 0, st>>>(B.blk_rows, L.n_blk, nullptr, R.blk_chunks, B.partial_blk, n_brows);
+    k_final_reduce<<<(S.n_cams * n_brows + 127) / 128, 128, 0, st>>>(B.partial_blk, R.blk_cam_chunk_off, S.n_cams, n_brows, B.cam_sums, NV, jac ? S.NE : 0);
+    launches += 2;
+    return launches;
 }
 
 // ---------------------------------------------------------------------------

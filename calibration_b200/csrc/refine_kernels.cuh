@@ -18,6 +18,7 @@ struct DevLayout {
     int64_t n_tiles = 0;
     int64_t n_blk = 0;        // device blocks: sorted by camera, camera groups padded to 32
     int64_t n_slices = 0;     // total k-slices (each 128 doubles)
+    int32_t one_seg_per_blk = 0;  // every real block has exactly one segment
     double* obs = nullptr;
     int64_t* tile_off = nullptr;  // [n_tiles]
     int32_t* tile_depth = nullptr;
@@ -41,12 +42,16 @@ struct EvalBuffers {
     double* segN = nullptr;       // [NE][n_seg]
     double* seg_ssr = nullptr;    // [n_seg] (cost passes)
     double* blk_ssr = nullptr;    // [n_blk]
+    double* blk_w = nullptr;      // [n_blk] Huber weight rho'(s_b)
+    double* seg_w = nullptr;      // [n_seg] weight of the segment's block
+    double* blk_rows = nullptr;   // block-indexed rows [1 + 63 + 6 PI][n_blk]: cost | Hvv gv Q Evi (bundle)
     // per-block view-type outputs for the per-view (Schur) kinds: [entry][n_blk]
     double* blk_Hvv = nullptr;    // 21
     double* blk_gv = nullptr;     // 6
     double* blk_Evc = nullptr;    // 36  (T_v^T N_xixi T_c)
     double* blk_Evi = nullptr;    // 6 * PI
-    double* partial = nullptr;    // [n_cams][n_red_warps][NV]
+    double* partial = nullptr;    // [n_seg_chunks][NE]
+    double* partial_blk = nullptr;// [n_blk_chunks][NV - NE]
     double* cam_sums = nullptr;   // [n_cams][NV]
 };
 
@@ -62,16 +67,21 @@ struct ProblemShape {
     double huber_delta;
 };
 
-constexpr int kRedWarpsPerBlock = 4;
+// contiguous column ranges (within one camera group) reduced by one CTA of k_colsum
+struct ColChunk { int32_t cam; int32_t pad; int64_t begin, end; };
+struct ReduceDesc {
+    ColChunk* seg_chunks = nullptr; int n_seg_chunks = 0; int32_t* seg_cam_chunk_off = nullptr;  // [n_cams + 1]
+    ColChunk* blk_chunks = nullptr; int n_blk_chunks = 0; int32_t* blk_cam_chunk_off = nullptr;
+};
 
 void launch_repack(const DevLayout& L, const double* sx, const double* sy, const double* su, const double* sv,
                    const int64_t* seg_src, cudaStream_t st);
 void launch_setup(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st);
 void launch_k1(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st);
 void launch_cost(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st);
-// jac != 0: reduce the K1 output; else reduce seg_ssr to per-camera cost
-void launch_assemble(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, int n_red_blocks, int jac,
-                     cudaStream_t st);
+// jac != 0: reduce the K1 output; else reduce seg_ssr to per-camera cost.  Returns the number of launches.
+int launch_assemble(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ReduceDesc& R, int jac,
+                    cudaStream_t st);
 int k1_num_passes(const ProblemShape& S);
 float dfma_peak_ms(double* scratch, int blocks, int threads, int iters, cudaStream_t st);
 

@@ -1,0 +1,57 @@
+"""The C-ABI shared library loads and exports every symbol include/calib_b200.h declares
+(no compute calls: this runs without a GPU), and fails loudly without a device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from calibration_b200 import abi, build, capi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "calib_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cal_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_declared_symbols():
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    names = declared_symbols()
+    assert len(names) >= 15
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_struct_layouts_match_header_sizes():
+    assert ctypes.sizeof(abi.ProblemDesc) == 4 * 4 + 2 * 8 + 8 * 8 + 6 * 4 + 8
+    assert ctypes.sizeof(abi.OptimOptions) == 32
+    assert ctypes.sizeof(abi.OptimResult) == 6 * 4 + 2 * 8 + 256
+    assert ctypes.sizeof(abi.RansacOptions) == 40
+    assert ctypes.sizeof(abi.RansacResult) == 16 + 72 + 24
+
+
+@pytest.mark.skipif(capi.device_count() > 0, reason="needs a machine WITHOUT a GPU")
+def test_no_cpu_fallback():
+    prob, x0, _ = synth.make_bundle(n_cams=1, n_poses=8)
+    with pytest.raises(capi.CalibCudaError):
+        capi.RefineHandle(prob)
+
+
+def test_validation_errors_mirror_reference():
+    # std::invalid_argument cases (intrinsics.cpp:92-96, bundle.cpp:136-145, *residual.h create())
+    prob, x0, _ = synth.make_intrinsics(n_views=3)
+    with pytest.raises(ValueError, match="at least 4"):
+        capi.RefineHandle(prob)
+    prob, x0, _ = synth.make_bundle(n_cams=1, n_poses=4)
+    prob.desc.n_cams = 0
+    with pytest.raises(ValueError, match="No camera intrinsics"):
+        capi.RefineHandle(prob)
+    prob, x0, _ = synth.make_bundle(n_cams=1, n_poses=4)
+    prob.block_offset[2] = prob.block_offset[1]  # an empty view
+    with pytest.raises(ValueError, match="No observations"):
+        capi.RefineHandle(prob)
