@@ -1,0 +1,245 @@
+"""Parity of the CUDA refinement path (through the C ABI) with the CPU oracle.
+
+Tolerances: the fused pass (cost, J^T r, J^T J) must agree to 1e-10 relative
+(it agrees to ~1e-15 in practice: same math, different summation order);
+converged parameters within 1e-8 relative and final RMS reprojection error
+within 1e-10 px, the bars BASELINE.json's north star states.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import ref_scenarios as RS
+from calibration_b200 import abi, capi, synth
+from calibration_b200 import geometry as G
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300))
+
+
+def rms_px(prob, x):
+    ssr = O.block_ssr(prob, x)
+    return float(np.sqrt(ssr.sum() / (2.0 * prob.desc.n_obs)))
+
+
+def assert_eval_parity(prob, x, tol=1e-10):
+    h = capi.RefineHandle(prob)
+    try:
+        c_o, g_o, H_o = O.refine_eval(prob, x)
+        c_g, g_g, H_g = h.eval(x)
+        assert abs(c_g - c_o) <= tol * abs(c_o)
+        assert relerr(g_g, g_o) <= tol and relerr(H_g, H_o) <= tol
+        assert abs(h.cost(x) - c_o) <= tol * abs(c_o)
+        # determinism: no floating-point atomics anywhere on the path
+        c2, g2, H2 = h.eval(x)
+        assert c2 == c_g and np.array_equal(g2, g_g) and np.array_equal(H2, H_g)
+    finally:
+        h.close()
+
+
+def assert_solve_parity(prob, x0, opts=None):
+    opts = opts or abi.OptimOptions.default()
+    h = capi.RefineHandle(prob)
+    try:
+        x_o, r_o, cov_o = O.refine_solve(prob, x0, opts)
+        x_g, r_g, cov_g = h.solve(x0, opts)
+    finally:
+        h.close()
+    assert r_g.success == r_o.success and r_g.termination == r_o.termination
+    assert relerr(x_g, x_o) <= 1e-8
+    assert abs(rms_px(prob, x_g) - rms_px(prob, x_o)) <= 1e-10
+    assert abs(r_g.final_cost - r_o.final_cost) <= 1e-9 * max(abs(r_o.final_cost), 1e-12) + 1e-18
+    if r_o.covariance_ok:
+        assert r_g.covariance_ok and relerr(cov_g, cov_o) <= 1e-6
+    return x_g, r_g, cov_g
+
+
+EVAL_CASES = {
+    "intrinsics": lambda: synth.make_intrinsics()[:2],
+    "intrinsics_skew": lambda: synth.make_intrinsics(optimize_skew=True)[:2],
+    "intrinsics_no_loss": lambda: synth.make_intrinsics(huber_delta=-1.0)[:2],
+    "intrinsics_scheimpflug": lambda: synth.make_intrinsics(model=abi.MODEL_SCHEIMPFLUG_BC5)[:2],
+    "intrinsics_scheimpflug_skew": lambda: synth.make_intrinsics(model=abi.MODEL_SCHEIMPFLUG_BC5, optimize_skew=True)[:2],
+    "extrinsics": lambda: synth.make_extrinsics(n_views=40)[:2],
+    "extrinsics_missing_views": lambda: synth.make_extrinsics(n_cams=3, n_views=60, drop_fraction=0.3)[:2],
+    "extrinsics_fixed_intrinsics": lambda: synth.make_extrinsics(n_cams=3, n_views=30, optimize_intrinsics=False)[:2],
+    "extrinsics_fixed_extrinsics": lambda: synth.make_extrinsics(n_views=30, optimize_extrinsics=False)[:2],
+    "extrinsics_skew": lambda: synth.make_extrinsics(n_views=30, optimize_skew=True)[:2],
+    "bundle": lambda: synth.make_bundle(n_cams=4, n_poses=50)[:2],
+    "bundle_default_options": lambda: synth.make_bundle(n_cams=2, n_poses=50, optimize_intrinsics=False)[:2],
+    "bundle_skew": lambda: synth.make_bundle(n_cams=2, n_poses=50, optimize_skew=True)[:2],
+    "bundle_only_target": lambda: synth.make_bundle(n_cams=2, n_poses=50, optimize_intrinsics=False, optimize_hand_eye=False)[:2],
+    "bundle_only_handeye": lambda: synth.make_bundle(n_cams=2, n_poses=50, optimize_intrinsics=False, optimize_target_pose=False)[:2],
+    "bundle_only_intrinsics": lambda: synth.make_bundle(n_cams=2, n_poses=50, optimize_hand_eye=False, optimize_target_pose=False)[:2],
+    "bundle_scheimpflug": lambda: synth.make_bundle(n_cams=2, n_poses=50, model=abi.MODEL_SCHEIMPFLUG_BC5)[:2],
+    "bundle_scheimpflug_skew": lambda: synth.make_bundle(n_cams=2, n_poses=40, model=abi.MODEL_SCHEIMPFLUG_BC5, optimize_skew=True)[:2],
+    "bundle_no_loss": lambda: synth.make_bundle(n_cams=3, n_poses=40, huber_delta=-1.0)[:2],
+}
+
+
+@pytest.mark.parametrize("name", sorted(EVAL_CASES))
+def test_fused_pass_matches_oracle(name):
+    prob, x0 = EVAL_CASES[name]()
+    assert_eval_parity(prob, x0)
+
+
+def ragged_bundle(seed=11):
+    """Views of different lengths (culled corners), one with a single corner."""
+    prob, x0, _ = synth.make_bundle(n_cams=2, n_poses=37)
+    rng = np.random.default_rng(seed)
+    nb = prob.desc.n_blocks
+    keep_len = rng.integers(1, 89, size=nb); keep_len[0] = 1; keep_len[1] = 88
+    idx = np.concatenate([np.arange(prob.block_offset[b], prob.block_offset[b] + keep_len[b]) for b in range(nb)])
+    off = np.concatenate([[0], np.cumsum(keep_len)])
+    p2 = abi.Problem(abi.KIND_BUNDLE, abi.MODEL_PINHOLE_BC5, 2, 0, prob.x[idx], prob.y[idx], prob.u[idx], prob.v[idx], off,
+                     prob.block_cam, block_b_se3_g=prob.block_b_se3_g, optimize_intrinsics=True, huber_delta=1.0)
+    return p2, x0
+
+
+def test_ragged_views():
+    prob, x0 = ragged_bundle()
+    assert_eval_parity(prob, x0)
+
+
+def test_single_segment_layout_at_scale():
+    """8.8M observations: one segment per residual block, the layout the C5 benchmark runs."""
+    prob, x0, _ = synth.make_bundle(n_cams=8, n_poses=12500)
+    h = capi.RefineHandle(prob)
+    try:
+        assert h.layout_info()["n_segments"] == prob.desc.n_blocks == 100000
+        c_g, g_g, H_g = h.eval(x0)
+    finally:
+        h.close()
+    c_o, g_o, H_o = O.refine_eval(prob, x0)
+    assert abs(c_g - c_o) <= 1e-12 * c_o and relerr(g_g, g_o) <= 1e-11 and relerr(H_g, H_o) <= 1e-11
+
+
+def test_block_ssr_matches():
+    prob, x0, _ = synth.make_extrinsics(n_views=25)
+    h = capi.RefineHandle(prob)
+    try:
+        _, ssr = h.cost(x0, want_block_ssr=True)
+    finally:
+        h.close()
+    assert relerr(ssr, O.block_ssr(prob, x0)) <= 1e-12
+
+
+# ---- the reference's own tests through the CUDA path, with its tolerances ----
+@pytest.mark.parametrize("skew", [False, True])
+def test_reference_intrinsics_recovery(skew):
+    prob, x0, info = RS.intrinsics_scenario(skew)
+    x, res, cov = assert_solve_parity(prob, x0)
+    intr, _ = G.unpack_intrinsics(x, prob.desc.n_views)
+    assert np.abs(intr[:4] - info["intr_gt"][:4]).max() < 1e-6
+    assert abs(intr[4] - info["intr_gt"][4]) < (1e-8 if skew else 1e-9)
+
+
+@pytest.mark.parametrize("kind", ["nodist", "nodist_skew", "distortion"])
+def test_reference_bundle_recovery(kind):
+    prob, x0, info = RS.bundle_scenario(kind)
+    x, res, _ = assert_solve_parity(prob, x0)
+    intr, g, b = G.unpack_bundle(x, 1)
+    if kind == "distortion":
+        assert np.abs(intr[0][5:10] - info["intr_gt"][5:10]).max() < 1e-5
+    else:
+        assert np.degrees(G.rotation_angle(g[0][:3, :3].T @ info["g_gt"][:3, :3])) < 1e-6
+        assert np.linalg.norm(g[0][:3, 3] - info["g_gt"][:3, 3]) < 1e-6
+        assert np.abs(intr[0][:4] - info["intr_gt"][:4]).max() < 1e-6
+        assert np.linalg.norm(b[:3, 3] - info["b_gt"][:3, 3]) < 1e-6
+
+
+@pytest.mark.parametrize("which", ["intrinsics", "handeye"])
+def test_reference_scheimpflug_bundle(which):
+    prob, x0, info = RS.scheimpflug_scenario(which)
+    x, res, _ = assert_solve_parity(prob, x0)
+    intr, g, _ = G.unpack_bundle(x, 1, 12)
+    assert np.abs(intr[0][10:12] - info["intr_gt"][10:12]).max() < 1e-6
+    assert np.linalg.norm(g[0][:3, 3] - info["g_gt"][:3, 3]) < 1e-6
+
+
+@pytest.mark.parametrize("which", ["poses", "all", "first_fixed"])
+def test_reference_extrinsics(which):
+    prob, x0, info = RS.extrinsics_scenario(which)
+    x, res, cov = assert_solve_parity(prob, x0)
+    _, cams, tg = G.unpack_extrinsics(x, 2, prob.desc.n_views)
+    if which == "first_fixed":
+        assert np.abs(tg[0][:3, 3] - info["target_init"][0][:3, 3]).max() < 1e-12 and res.final_cost > 0.1
+    else:
+        assert res.final_cost < 1e-6
+        assert np.allclose(cams[1][:3, 3], info["cam_gt"][1][:3, 3], atol=1e-3)
+        if which == "all":
+            assert res.covariance_ok and np.trace(cov) > 0.0
+
+
+# ---- noisy BASELINE-shaped problems: converged parameters vs the oracle ----
+def test_c1_intrinsics_solve():
+    prob, x0, _ = synth.make_intrinsics()
+    assert_solve_parity(prob, x0)
+    prob, x0, _ = synth.make_intrinsics(huber_delta=-1.0)
+    assert_solve_parity(prob, x0)
+
+
+def test_c3_extrinsics_solve():
+    prob, x0, _ = synth.make_extrinsics(n_views=150)
+    assert_solve_parity(prob, x0, abi.OptimOptions.default(compute_covariance=0))
+
+
+def test_c4_bundle_solve_with_covariance():
+    prob, x0, xgt = synth.make_bundle(n_cams=4, n_poses=400)
+    x, res, cov = assert_solve_parity(prob, x0)
+    assert res.covariance_ok and cov.shape == (75, 75)
+    assert np.abs(x - xgt)[:40].max() < 3.0, np.abs(x - xgt)[:40].max()  # intrinsics near ground truth under 0.2 px noise
+
+
+def test_max_iterations_reports_no_convergence():
+    prob, x0, _ = synth.make_bundle(n_cams=2, n_poses=40)
+    h = capi.RefineHandle(prob)
+    try:
+        x, res, _ = h.solve(x0, abi.OptimOptions.default(max_iterations=2, compute_covariance=0))
+    finally:
+        h.close()
+    xo, ro, _ = O.refine_solve(prob, x0, abi.OptimOptions.default(max_iterations=2, compute_covariance=0))
+    assert not res.success and res.termination == 1 and res.iterations == 2  # ceresutils.h:42
+    assert relerr(x, xo) <= 1e-8
+
+
+# ---- size-independent properties at benchmark scale ----
+def test_additivity_over_shards_at_scale():
+    """J^T J, J^T r and the cost are sums over residual blocks: a pass over two shards equals a pass over their union."""
+    kw = dict(seed=137, n_cams=8, n_poses=20000, chunk=5000)
+    full, x0, _ = synth.make_bundle(**kw)
+    ha = capi.RefineHandle(full)
+    try:
+        c, g, H = ha.eval(x0)
+    finally:
+        ha.close()
+    cs, gs, Hs = 0.0, 0.0, 0.0
+    for chunks in ([0, 1], [2, 3]):
+        part, _, _ = synth.make_bundle(chunks=chunks, **kw)
+        hp = capi.RefineHandle(part)
+        try:
+            ci, gi, Hi = hp.eval(x0)
+        finally:
+            hp.close()
+        cs, gs, Hs = cs + ci, gs + gi, Hs + Hi
+    assert abs(c - cs) <= 1e-12 * c and relerr(g, gs) <= 1e-11 and relerr(H, Hs) <= 1e-11
+    assert np.allclose(H, H.T, rtol=0, atol=1e-9 * np.abs(H).max())
+
+
+def test_solve_reaches_stationary_point_at_scale():
+    prob, x0, xgt = synth.make_bundle(seed=137, n_cams=8, n_poses=10000)
+    h = capi.RefineHandle(prob)
+    try:
+        x, res, _ = h.solve(x0, abi.OptimOptions.default(compute_covariance=0))
+        c, g, H = h.eval(x)
+        c_gt = h.cost(xgt)
+    finally:
+        h.close()
+    assert res.success
+    # the LM minimum is at or below the cost of the ground truth, and the gradient is tiny relative to H's scale
+    assert c <= c_gt * (1 + 1e-9)
+    step = np.linalg.solve(H + 1e-9 * np.eye(len(g)) * np.trace(H) / len(g), g)
+    assert np.abs(step).max() < 1e-3  # function tolerance 1e-9 stops within ~1e-5 px of the stationary point
