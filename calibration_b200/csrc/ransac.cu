@@ -1,0 +1,577 @@
+// K3: batched RANSAC homography — estimate_homography(view, RansacOptions)
+// (reference include/calib/estimation/linear/homography.h:22-24) =
+// ransac<HomographyEstimator> (include/calib/estimation/common/ransac.h:121-194)
+// with the estimator of src/estimation/linear/homographyestimator.cpp:16-174 and
+// the wrapper / symmetric_rms_px of src/estimation/optim/homography.cpp:18-73.
+//
+// One warp per problem.  The problem's correspondences are read from HBM once
+// (coalesced) into shared memory and every hypothesis is scored from there.
+// The reference's sequential semantics are replayed exactly per problem:
+//   * the minimal-sample stream is the libstdc++ std::sample / std::mt19937_64
+//     stream (ransac.h:135,144-145), generated ON THE DEVICE: the 312-word
+//     twist and the tempering run lane-parallel, the selection-sampling walk
+//     takes 32 (index, index+1) pairs per step with one Lemire multiply per
+//     lane (integer arithmetic, bit-exact);
+//   * degeneracy test, 4-point Hartley-normalised DLT, inlier scoring, refit
+//     on the inliers, best-model update and the adaptive iteration bound
+//     follow ransac.h:140-190 statement by statement.
+// Numerical differences to the reference are confined to rounding: the DLT
+// null vector comes from Householder QR of A^T (4-point) / inverse iteration on
+// the 9x9 normal matrix (refit) instead of Eigen::JacobiSVD, and the inlier
+// test compares squared errors.  Inlier sets are therefore identical whenever
+// no residual lies within rounding distance of the threshold.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/calib_b200.h"
+
+extern "C" void cal_set_last_error_(const char* msg);
+
+namespace {
+
+cal_status rfail(cal_status s, const std::string& m) { cal_set_last_error_(m.c_str()); return s; }
+#define RCUDA(expr)                                                                                   \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) return rfail(CAL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+constexpr int kWarpsPerCta = 4;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct WarpMem {
+    double *x, *y, *u, *v;       // [n]
+    unsigned long long* mt;      // [312]
+    unsigned* cur;               // [nw] inlier bit mask of the current hypothesis
+    unsigned* ref;               // [nw] after refit
+    unsigned* best;              // [nw]
+};
+
+// ---- std::mt19937_64, state in shared memory, lane-parallel twist ----
+__device__ __forceinline__ unsigned long long mt_temper(unsigned long long z) {
+    z ^= (z >> 29) & 0x5555555555555555ULL;
+    z ^= (z << 17) & 0x71D67FFFEDA60000ULL;
+    z ^= (z << 37) & 0xFFF7EEE000000000ULL;
+    z ^= z >> 43;
+    return z;
+}
+__device__ void mt_seed(unsigned long long* mt, unsigned long long seed, int lane) {
+    unsigned long long xv = seed;
+    if (lane == 0) mt[0] = xv;
+    for (int i = 1; i < 312; ++i) {
+        xv = 6364136223846793005ULL * (xv ^ (xv >> 62)) + (unsigned long long)i;
+        if ((i & 31) == lane) mt[i] = xv;
+    }
+    __syncwarp();
+}
+__device__ void mt_twist(unsigned long long* mt, int lane) {
+    const unsigned long long UP = 0xFFFFFFFF80000000ULL, LO = 0x7FFFFFFFULL, A = 0xB5026F5AA96619E9ULL;
+    for (int base = 0; base < 312; base += 32) {
+        const int i = base + lane;
+        unsigned long long nv = 0;
+        if (i < 312) {
+            const unsigned long long yv = (mt[i] & UP) | (mt[(i + 1) % 312] & LO);
+            nv = mt[(i + 156) % 312] ^ (yv >> 1) ^ ((yv & 1ULL) ? A : 0ULL);
+        }
+        __syncwarp();
+        if (i < 312) mt[i] = nv;
+        __syncwarp();
+    }
+}
+// one engine output (warp-uniform)
+__device__ __forceinline__ unsigned long long mt_next(unsigned long long* mt, int& pos, int lane) {
+    if (pos >= 312) { mt_twist(mt, lane); pos = 0; }
+    return mt_temper(mt[pos++]);
+}
+// uniform_int_distribution<unsigned long>{0, range-1}: Lemire (uniform_int_dist.h:252-281), warp-uniform
+__device__ unsigned long long lemire_uniform(unsigned long long* mt, int& pos, int lane, unsigned long long range) {
+    unsigned long long r = mt_next(mt, pos, lane);
+    unsigned long long low = r * range, hi = __umul64hi(r, range);
+    if (low < range) {
+        const unsigned long long threshold = (0ULL - range) % range;
+        while (low < threshold) { r = mt_next(mt, pos, lane); low = r * range; hi = __umul64hi(r, range); }
+    }
+    return hi;
+}
+// std::sample(0..N-1, 4) — libstdc++ selection sampling (stl_algo.h:5841-5907).  Results are warp-uniform.
+__device__ void sample4(unsigned long long* mt, int& pos, int lane, int N, int* idx) {
+    unsigned long long uns = (unsigned long long)N;
+    int need = N < 4 ? N : 4, first = 0, o = 0;
+    bool slow = false;
+    while (need != 0 && uns >= 2 && !slow) {
+        if (pos >= 312) { mt_twist(mt, lane); pos = 0; }
+        const int avail = 312 - pos;
+        const unsigned long long pairs_left = uns / 2;
+        int B = 32; if (avail < B) B = avail; if (pairs_left < (unsigned long long)B) B = (int)pairs_left;
+        unsigned p0 = 0xffffffffu, p1 = 0xffffffffu; bool rej = false;
+        if (lane < B) {
+            const unsigned long long uj = uns - 2ULL * lane, b1 = uj - 1ULL, range = uj * b1;
+            const unsigned long long r = mt_temper(mt[pos + lane]);
+            const unsigned long long low = r * range, hi = __umul64hi(r, range);
+            rej = low < range && low < (0ULL - range) % range;   // would redraw: leave the fast path
+            if (N < 65536) { const unsigned h32 = (unsigned)hi, b32 = (unsigned)b1; p0 = h32 / b32; p1 = h32 - p0 * b32; }
+            else { p0 = (unsigned)(hi / b1); p1 = (unsigned)(hi % b1); }
+        }
+        if (__any_sync(kFull, rej)) { slow = true; break; }
+        unsigned m = __ballot_sync(kFull, lane < B && (p0 < (unsigned)need || p1 < (unsigned)need));
+        int consumed = B; bool done = false;
+        while (m) {
+            const int j = __ffs(m) - 1; m &= m - 1;
+            const unsigned a = __shfl_sync(kFull, p0, j), b = __shfl_sync(kFull, p1, j);
+            if (a < (unsigned)need) { idx[o++] = first + 2 * j; --need; }
+            if (need == 0) { consumed = j + 1; done = true; break; }
+            if (b < (unsigned)need) { idx[o++] = first + 2 * j + 1; --need; }
+            if (need == 0) { consumed = j + 1; done = true; break; }
+        }
+        pos += consumed;
+        if (!done) { uns -= 2ULL * B; first += 2 * B; }
+    }
+    if (slow) {  // exact sequential replay from the current state (a Lemire redraw occurred)
+        while (need != 0 && uns >= 2) {
+            const unsigned long long b1 = uns - 1ULL;
+            const unsigned long long xx = lemire_uniform(mt, pos, lane, uns * b1);
+            const unsigned long long q0 = xx / b1, q1 = xx % b1;
+            --uns;
+            if (q0 < (unsigned long long)need) { idx[o++] = first; --need; }
+            ++first;
+            if (need == 0) break;
+            --uns;
+            if (q1 < (unsigned long long)need) { idx[o++] = first; --need; }
+            ++first;
+        }
+    }
+    for (; need != 0; ++first) {  // one-at-a-time tail (stl_algo.h:5899-5905)
+        --uns;
+        if (lemire_uniform(mt, pos, lane, uns + 1ULL) < (unsigned long long)need) { idx[o++] = first; --need; }
+    }
+}
+
+// ---- small dense helpers (thread-redundant, fully unrolled) ----
+__device__ __forceinline__ void inv3(const double* M, double* I) {
+    const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+    const double id = 1.0 / (M[0] * c00 + M[1] * c01 + M[2] * c02);
+    I[0] = c00 * id; I[1] = (M[2] * M[7] - M[1] * M[8]) * id; I[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+    I[3] = c01 * id; I[4] = (M[0] * M[8] - M[2] * M[6]) * id; I[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+    I[6] = c02 * id; I[7] = (M[1] * M[6] - M[0] * M[7]) * id; I[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+}
+// H = Td^-1 * Hn * Ts for the Hartley similarity transforms T = [s 0 -s cx; 0 s -s cy; 0 0 1]
+__device__ __forceinline__ void denormalise(const double* hn, double ss, double scx, double scy, double ds, double dcx, double dcy,
+                                            double* H) {
+    // Hn * Ts
+    double M[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        M[3 * i] = hn[3 * i] * ss; M[3 * i + 1] = hn[3 * i + 1] * ss;
+        M[3 * i + 2] = hn[3 * i + 2] - ss * (hn[3 * i] * scx + hn[3 * i + 1] * scy);
+    }
+    // Td^-1 = [1/s 0 cx; 0 1/s cy; 0 0 1]
+    const double id = 1.0 / ds;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { H[j] = M[j] * id + dcx * M[6 + j]; H[3 + j] = M[3 + j] * id + dcy * M[6 + j]; H[6 + j] = M[6 + j]; }
+}
+
+// 4-point DLT (homographyestimator.cpp:45-78,123-143): null vector of the 8x9 matrix via Householder QR of A^T.
+__device__ bool dlt4(const double* px, const double* py, const double* pu, const double* pv, double* H) {
+    double scx = 0, scy = 0, dcx = 0, dcy = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { scx += px[i]; scy += py[i]; dcx += pu[i]; dcy += pv[i]; }
+    scx *= 0.25; scy *= 0.25; dcx *= 0.25; dcy *= 0.25;
+    double sm = 0, dm = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sm += sqrt((px[i] - scx) * (px[i] - scx) + (py[i] - scy) * (py[i] - scy));
+        dm += sqrt((pu[i] - dcx) * (pu[i] - dcx) + (pv[i] - dcy) * (pv[i] - dcy));
+    }
+    sm *= 0.25; dm *= 0.25;
+    const double ss = sm > 0 ? 1.4142135623730951 / sm : 1.0, ds = dm > 0 ? 1.4142135623730951 / dm : 1.0;
+    // M = A^T (9 x 8), column c = row c of A
+    double M[9][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double x = ss * (px[i] - scx), y = ss * (py[i] - scy), u = ds * (pu[i] - dcx), v = ds * (pv[i] - dcy);
+        const int c0 = 2 * i, c1 = 2 * i + 1;
+        M[0][c0] = -x; M[1][c0] = -y; M[2][c0] = -1.0; M[3][c0] = 0; M[4][c0] = 0; M[5][c0] = 0; M[6][c0] = u * x; M[7][c0] = u * y; M[8][c0] = u;
+        M[0][c1] = 0; M[1][c1] = 0; M[2][c1] = 0; M[3][c1] = -x; M[4][c1] = -y; M[5][c1] = -1.0; M[6][c1] = v * x; M[7][c1] = v * y; M[8][c1] = v;
+    }
+    double beta[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double nrm2 = 0;
+#pragma unroll
+        for (int i = k; i < 9; ++i) nrm2 = fma(M[i][k], M[i][k], nrm2);
+        const double nrm = sqrt(nrm2);
+        const double alpha = M[k][k] > 0 ? -nrm : nrm;
+        const double v0 = M[k][k] - alpha;
+        double vtv = v0 * v0;
+#pragma unroll
+        for (int i = k + 1; i < 9; ++i) vtv = fma(M[i][k], M[i][k], vtv);
+        beta[k] = vtv > 0 ? 2.0 / vtv : 0.0;
+        M[k][k] = v0;  // column k now holds the Householder vector v_k (rows k..8)
+#pragma unroll
+        for (int j = k + 1; j < 8; ++j) {
+            double d = 0;
+#pragma unroll
+            for (int i = k; i < 9; ++i) d = fma(M[i][k], M[i][j], d);
+            d *= beta[k];
+#pragma unroll
+            for (int i = k; i < 9; ++i) M[i][j] = fma(-d, M[i][k], M[i][j]);
+        }
+    }
+    // null vector = Q e9 = H_1 ... H_8 e9
+    double z[9] = {0, 0, 0, 0, 0, 0, 0, 0, 1.0};
+#pragma unroll
+    for (int k = 7; k >= 0; --k) {
+        double d = 0;
+#pragma unroll
+        for (int i = k; i < 9; ++i) d = fma(M[i][k], z[i], d);
+        d *= beta[k];
+#pragma unroll
+        for (int i = k; i < 9; ++i) z[i] = fma(-d, M[i][k], z[i]);
+    }
+    double hn[9];
+    const double ih = 1.0 / z[8];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) hn[i] = z[i] * ih;
+    denormalise(hn, ss, scx, scy, ds, dcx, dcy, H);
+    return isfinite(H[0]);
+}
+
+// smallest eigenvector of the symmetric 9x9 G (upper triangle given) by inverse iteration on G + mu I
+__device__ bool smallest_eigvec9(const double* Gu /*45*/, double* z) {
+    double L[9][9];
+    double tr = 0;
+    {
+        int o = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = i; j < 9; ++j) { L[j][i] = Gu[o]; if (i == j) tr += Gu[o]; ++o; }
+    }
+    const double mu = 1e-14 * tr + 1e-300;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        double s = L[j][j] + mu;
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-L[j][k], L[j][k], s);
+        if (!(s > 0.0)) return false;
+        const double l = sqrt(s), il = 1.0 / l;
+        L[j][j] = l;
+#pragma unroll
+        for (int i = j + 1; i < 9; ++i) {
+            double t = L[i][j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = fma(-L[i][k], L[j][k], t);
+            L[i][j] = t * il;
+        }
+    }
+    double w[9] = {1.0, 0.7, 0.3, -0.5, 0.9, 0.2, -0.8, 0.4, 1.0};
+    for (int it = 0; it < 16; ++it) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { double s = w[i];
+#pragma unroll
+            for (int k = 0; k < i; ++k) s = fma(-L[i][k], w[k], s); w[i] = s / L[i][i]; }
+#pragma unroll
+        for (int i = 8; i >= 0; --i) { double s = w[i];
+#pragma unroll
+            for (int k = i + 1; k < 9; ++k) s = fma(-L[k][i], w[k], s); w[i] = s / L[i][i]; }
+        double n2 = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) n2 = fma(w[i], w[i], n2);
+        const double in = rsqrt(n2);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) w[i] *= in;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) z[i] = w[i];
+    return true;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// Score H over all n correspondences (find_inliers, ransac.h:80-95 with the symmetric
+// transfer error of homographyestimator.cpp:80-93); writes the inlier bit mask, returns the
+// count and sum of squared residuals (warp-uniform).
+__device__ int score(const WarpMem& w, int n, int lane, const double* H, double thresh2, unsigned* mask, double& ssr) {
+    double Hi[9]; inv3(H, Hi);
+    int cnt = 0; double s = 0.0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        bool in = false; double r2 = 0.0;
+        if (i < n) {
+            const double x = w.x[i], y = w.y[i], u = w.u[i], v = w.v[i];
+            const double qx = H[0] * x + H[1] * y + H[2], qy = H[3] * x + H[4] * y + H[5], qz = H[6] * x + H[7] * y + H[8];
+            const double iq = 1.0 / qz;
+            const double du = u - qx * iq, dv = v - qy * iq;
+            const double px = Hi[0] * u + Hi[1] * v + Hi[2], py = Hi[3] * u + Hi[4] * v + Hi[5], pz = Hi[6] * u + Hi[7] * v + Hi[8];
+            const double ip = 1.0 / pz;
+            const double dx = x - px * ip, dy = y - py * ip;
+            r2 = 0.5 * (du * du + dv * dv + dx * dx + dy * dy);
+            in = r2 <= thresh2;  // false for NaN, like `r <= threshold`
+        }
+        const unsigned b = __ballot_sync(kFull, in);
+        if (lane == 0) mask[base >> 5] = b;
+        cnt += __popc(b);
+        if (in) s += r2;
+    }
+    __syncwarp();
+    ssr = warp_sum(s);
+    return cnt;
+}
+
+// refit: Hartley-normalised DLT over the inliers of `mask` (HomographyEstimator::refit :146-166)
+__device__ bool refit(const WarpMem& w, int n, int lane, const unsigned* mask, int cnt, double* H) {
+    if (cnt < 4) return false;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        if (i < n && ((mask[base >> 5] >> lane) & 1u)) { a0 += w.x[i]; a1 += w.y[i]; a2 += w.u[i]; a3 += w.v[i]; }
+    }
+    const double inv = 1.0 / (double)cnt;
+    const double scx = warp_sum(a0) * inv, scy = warp_sum(a1) * inv, dcx = warp_sum(a2) * inv, dcy = warp_sum(a3) * inv;
+    a0 = a1 = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        if (i < n && ((mask[base >> 5] >> lane) & 1u)) {
+            a0 += sqrt((w.x[i] - scx) * (w.x[i] - scx) + (w.y[i] - scy) * (w.y[i] - scy));
+            a1 += sqrt((w.u[i] - dcx) * (w.u[i] - dcx) + (w.v[i] - dcy) * (w.v[i] - dcy));
+        }
+    }
+    const double sm = warp_sum(a0) * inv, dm = warp_sum(a1) * inv;
+    const double ss = sm > 0 ? 1.4142135623730951 / sm : 1.0, ds = dm > 0 ? 1.4142135623730951 / dm : 1.0;
+    // A^T A from the monomials p p^T (p = (x, y, 1)) weighted by 1, u, v, u^2 + v^2
+    double m[4][6];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) m[k][e] = 0.0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        if (i < n && ((mask[base >> 5] >> lane) & 1u)) {
+            const double x = ss * (w.x[i] - scx), y = ss * (w.y[i] - scy), u = ds * (w.u[i] - dcx), v = ds * (w.v[i] - dcy);
+            const double pp[6] = {x * x, x * y, x, y * y, y, 1.0};
+            const double wt[4] = {1.0, u, v, u * u + v * v};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int e = 0; e < 6; ++e) m[k][e] = fma(wt[k], pp[e], m[k][e]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) m[k][e] = warp_sum(m[k][e]);
+    // G = [[S1, 0, -Su], [0, S1, -Sv], [-Su, -Sv, Sq]] with 3x3 symmetric blocks from the monomial sums
+    auto blk = [](const double* s, int i, int j) { const int a = i < j ? i : j, b = i < j ? j : i; return s[a == 0 ? b : (a == 1 ? 2 + b : 5)]; };
+    double Gu[45];
+    {
+        int o = 0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = i; j < 9; ++j) {
+                const int bi = i / 3, bj = j / 3, ii = i % 3, jj = j % 3;
+                double v = 0.0;
+                if (bi == bj) v = blk(bi == 2 ? m[3] : m[0], ii, jj);
+                else if (bj == 2) v = -blk(bi == 0 ? m[1] : m[2], ii, jj);
+                Gu[o++] = v;
+            }
+    }
+    double z[9];
+    if (!smallest_eigvec9(Gu, z)) return false;
+    double hn[9];
+    const double ih = 1.0 / z[8];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) hn[i] = z[i] * ih;
+    denormalise(hn, ss, scx, scy, ds, dcx, dcy, H);
+    return isfinite(H[0]);
+}
+
+__global__ void __launch_bounds__(32 * kWarpsPerCta) k_ransac(int64_t n_problems, int n, const double* __restrict__ gx,
+                                                              const double* __restrict__ gy, const double* __restrict__ gu,
+                                                              const double* __restrict__ gv, cal_ransac_options o,
+                                                              int seed_per_problem, const int* __restrict__ niter_table,
+                                                              cal_ransac_result* __restrict__ results, uint8_t* __restrict__ gmask) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t prob = (int64_t)blockIdx.x * kWarpsPerCta + wid;
+    if (prob >= n_problems) return;
+    const int nw = (n + 31) / 32;
+    const size_t per_warp = (size_t)4 * n * sizeof(double) + 312 * sizeof(unsigned long long) + (size_t)3 * nw * sizeof(unsigned);
+    unsigned char* base = smem_raw + (size_t)wid * ((per_warp + 15) / 16 * 16);
+    WarpMem w;
+    w.x = reinterpret_cast<double*>(base); w.y = w.x + n; w.u = w.y + n; w.v = w.u + n;
+    w.mt = reinterpret_cast<unsigned long long*>(w.v + n);
+    w.cur = reinterpret_cast<unsigned*>(w.mt + 312); w.ref = w.cur + nw; w.best = w.ref + nw;
+    for (int i = lane; i < n; i += 32) {
+        w.x[i] = gx[prob * n + i]; w.y[i] = gy[prob * n + i]; w.u[i] = gu[prob * n + i]; w.v[i] = gv[prob * n + i];
+    }
+    for (int i = lane; i < nw; i += 32) w.best[i] = 0u;
+    mt_seed(w.mt, o.seed + (seed_per_problem ? (unsigned long long)prob : 0ULL), lane);
+    int pos = 312;
+    const double thresh2 = o.thresh * o.thresh;
+    bool has_best = false; int best_cnt = 0, best_iters = 0; double best_rms = INFINITY;
+    double bestH[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    int dyn = o.max_iters, it = 0;
+    if (n >= 4) {
+        for (it = 0; it < dyn; ++it) {
+            int idx[4];
+            sample4(w.mt, pos, lane, n, idx);
+            double px[4], py[4], pu[4], pv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { px[k] = w.x[idx[k]]; py[k] = w.y[idx[k]]; pu[k] = w.u[idx[k]]; pv[k] = w.v[idx[k]]; }
+            // has_near_collinear_triplet (homographyestimator.cpp:100-119), object coordinates
+            bool degen = false;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = a + 1; b < 4; ++b)
+#pragma unroll
+                    for (int c = b + 1; c < 4; ++c)
+                        degen |= fabs((px[b] - px[a]) * (py[c] - py[a]) - (py[b] - py[a]) * (px[c] - px[a])) < 1e-6;
+            if (degen) continue;
+            double H[9];
+            if (!dlt4(px, py, pu, pv, H)) continue;
+            double ssr;
+            int cnt = score(w, n, lane, H, thresh2, w.cur, ssr);
+            if (cnt < o.min_inliers) continue;
+            const unsigned* fin = w.cur;
+            if (o.refit_on_inliers) {
+                double H2[9];
+                if (refit(w, n, lane, w.cur, cnt, H2)) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) H[k] = H2[k];
+                    cnt = score(w, n, lane, H, thresh2, w.ref, ssr);
+                    fin = w.ref;
+                }
+            }
+            const double frms = cnt > 0 ? sqrt(ssr / (double)cnt) : INFINITY;
+            if (!has_best || cnt > best_cnt || (cnt == best_cnt && frms < best_rms)) {  // is_better_model (ransac.h:113-117)
+                has_best = true; best_cnt = cnt; best_rms = frms; best_iters = it + 1;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) bestH[k] = H[k];
+                for (int i = lane; i < nw; i += 32) w.best[i] = fin[i];
+                __syncwarp();
+            }
+            // calculate_iterations (ransac.h:64-78) through the host-built table indexed by the inlier count
+            const int niter = niter_table[cnt];
+            int nd = niter == -1 ? o.max_iters : niter;  // -1: the function returns max_iters before the clamp
+            if (nd < it + 1) nd = it + 1;
+            if (nd > o.max_iters) nd = o.max_iters;
+            dyn = nd;
+        }
+    }
+    // symmetric_rms_px (optim/homography.cpp:18-28): sqrt(sum of the (root) residuals / (2 n_inl))
+    double sym = INFINITY;
+    if (has_best && best_cnt > 0) {
+        double Hi[9]; inv3(bestH, Hi);
+        double s = 0.0;
+        for (int basei = 0; basei < n; basei += 32) {
+            const int i = basei + lane;
+            if (i < n && ((w.best[basei >> 5] >> lane) & 1u)) {
+                const double x = w.x[i], y = w.y[i], u = w.u[i], v = w.v[i];
+                const double qz = bestH[6] * x + bestH[7] * y + bestH[8];
+                const double du = u - (bestH[0] * x + bestH[1] * y + bestH[2]) / qz, dv = v - (bestH[3] * x + bestH[4] * y + bestH[5]) / qz;
+                const double pz = Hi[6] * u + Hi[7] * v + Hi[8];
+                const double dx = x - (Hi[0] * u + Hi[1] * v + Hi[2]) / pz, dy = y - (Hi[3] * u + Hi[4] * v + Hi[5]) / pz;
+                s += sqrt(0.5 * (du * du + dv * dv + dx * dx + dy * dy));
+            }
+        }
+        sym = sqrt(warp_sum(s) / (2.0 * (double)best_cnt));
+    }
+    if (lane == 0) {
+        cal_ransac_result r;
+        r.success = has_best ? 1 : 0; r.iters = best_iters; r.n_inliers = has_best ? best_cnt : 0; r.iters_run = it;
+        for (int k = 0; k < 9; ++k) r.hmtx[k] = bestH[k];
+        r.inlier_rms = best_rms; r.symmetric_rms_px = has_best ? sym : 0.0; r.min_margin = 0.0;
+        results[prob] = r;
+    }
+    if (gmask) for (int i = lane; i < n; i += 32) gmask[prob * n + i] = has_best ? (uint8_t)((w.best[i >> 5] >> (i & 31)) & 1u) : 0;
+}
+
+// calculate_iterations (ransac.h:64-78) evaluated on the host for every possible inlier count;
+// -1 encodes "max_iters".  Same expression, same libm as the reference's own host code.
+std::vector<int> build_niter_table(int n, const cal_ransac_options& o) {
+    std::vector<int> t(n + 1, -1);
+    for (int k = 0; k <= n; ++k) {
+        const double w = (double)k / (double)n;
+        if (o.confidence <= 0.0 || w <= 0.0) continue;
+        const double denom = std::log(std::max(1e-12, 1.0 - std::pow(w, 4.0)));
+        if (denom >= 0.0) continue;
+        const double v = std::ceil(std::log(1.0 - o.confidence) / denom);
+        // static_cast<int> of an out-of-range double is what x86 cvttsd2si yields: INT_MIN,
+        // which std::clamp then lifts to iters_so_far
+        t[k] = (v >= 2147483648.0 || v < -2147483648.0 || v != v) ? INT32_MIN : (int)v;
+        if (t[k] == -1) t[k] = -2;  // keep -1 reserved for "max_iters" (cannot occur: the ratio is >= 0)
+    }
+    return t;
+}
+
+size_t smem_per_cta(int n) {
+    const int nw = (n + 31) / 32;
+    const size_t per_warp = (size_t)4 * n * sizeof(double) + 312 * sizeof(unsigned long long) + (size_t)3 * nw * sizeof(unsigned);
+    return kWarpsPerCta * ((per_warp + 15) / 16 * 16);
+}
+
+cal_status launch(int64_t n_problems, int n, const double* x, const double* y, const double* u, const double* v,
+                  const cal_ransac_options& o, int seed_per_problem, cal_ransac_result* res, uint8_t* mask, cudaStream_t st,
+                  float* ms) {
+    const size_t smem = smem_per_cta(n);
+    if (smem > 227 * 1024) return rfail(CAL_ERR_INVALID_ARGUMENT, "too many correspondences per problem for the shared-memory RANSAC kernel (n <= ~1700)");
+    RCUDA(cudaFuncSetAttribute(k_ransac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    std::vector<int> table = build_niter_table(n, o);
+    int* dtable; RCUDA(cudaMalloc(reinterpret_cast<void**>(&dtable), table.size() * sizeof(int)));
+    RCUDA(cudaMemcpyAsync(dtable, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    cudaEvent_t e0, e1; RCUDA(cudaEventCreate(&e0)); RCUDA(cudaEventCreate(&e1));
+    RCUDA(cudaEventRecord(e0, st));
+    const unsigned grid = (unsigned)((n_problems + kWarpsPerCta - 1) / kWarpsPerCta);
+    k_ransac<<<grid, 32 * kWarpsPerCta, smem, st>>>(n_problems, n, x, y, u, v, o, seed_per_problem, dtable, res, mask);
+    RCUDA(cudaEventRecord(e1, st));
+    RCUDA(cudaEventSynchronize(e1));
+    RCUDA(cudaGetLastError());
+    float t = 0; RCUDA(cudaEventElapsedTime(&t, e0, e1));
+    if (ms) *ms = t;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dtable);
+    return CAL_OK;
+}
+
+}  // namespace
+
+extern "C" int cal_device_count(void);
+
+extern "C" cal_status cal_ransac_homography_batch_dev(int64_t n_problems, int32_t n, const double* x_dev, const double* y_dev,
+                                                      const double* u_dev, const double* v_dev, const cal_ransac_options* opts,
+                                                      int seed_per_problem, cal_ransac_result* results_dev,
+                                                      uint8_t* inlier_mask_dev, float* ms) {
+    if (!opts || !results_dev || n_problems <= 0 || n <= 0) return rfail(CAL_ERR_INVALID_ARGUMENT, "bad argument");
+    return launch(n_problems, n, x_dev, y_dev, u_dev, v_dev, *opts, seed_per_problem, results_dev, inlier_mask_dev, nullptr, ms);
+}
+
+extern "C" cal_status cal_ransac_homography_batch(int64_t n_problems, int32_t n, const double* x, const double* y,
+                                                  const double* u, const double* v, const cal_ransac_options* opts,
+                                                  int seed_per_problem, int device, cal_ransac_result* results,
+                                                  uint8_t* inlier_mask) {
+    if (!opts || !results || !x || !y || !u || !v || n_problems <= 0 || n <= 0) return rfail(CAL_ERR_INVALID_ARGUMENT, "bad argument");
+    if (cal_device_count() <= device) return rfail(CAL_ERR_CUDA, "no CUDA device: calib_b200 has no CPU fallback");
+    RCUDA(cudaSetDevice(device));
+    const size_t nb = (size_t)n_problems * n * sizeof(double);
+    double *dx, *dy, *du, *dv; cal_ransac_result* dres; uint8_t* dmask = nullptr;
+    RCUDA(cudaMalloc(reinterpret_cast<void**>(&dx), nb)); RCUDA(cudaMalloc(reinterpret_cast<void**>(&dy), nb));
+    RCUDA(cudaMalloc(reinterpret_cast<void**>(&du), nb)); RCUDA(cudaMalloc(reinterpret_cast<void**>(&dv), nb));
+    RCUDA(cudaMalloc(reinterpret_cast<void**>(&dres), (size_t)n_problems * sizeof(cal_ransac_result)));
+    if (inlier_mask) RCUDA(cudaMalloc(reinterpret_cast<void**>(&dmask), (size_t)n_problems * n));
+    RCUDA(cudaMemcpy(dx, x, nb, cudaMemcpyHostToDevice)); RCUDA(cudaMemcpy(dy, y, nb, cudaMemcpyHostToDevice));
+    RCUDA(cudaMemcpy(du, u, nb, cudaMemcpyHostToDevice)); RCUDA(cudaMemcpy(dv, v, nb, cudaMemcpyHostToDevice));
+    cal_status s = launch(n_problems, n, dx, dy, du, dv, *opts, seed_per_problem, dres, dmask, nullptr, nullptr);
+    if (s == CAL_OK) {
+        RCUDA(cudaMemcpy(results, dres, (size_t)n_problems * sizeof(cal_ransac_result), cudaMemcpyDeviceToHost));
+        if (inlier_mask) RCUDA(cudaMemcpy(inlier_mask, dmask, (size_t)n_problems * n, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(dx); cudaFree(dy); cudaFree(du); cudaFree(dv); cudaFree(dres); cudaFree(dmask);
+    return s;
+}

@@ -185,6 +185,8 @@ cal_status validate(const cal_problem_desc& d) {
 }  // namespace
 
 extern "C" const char* cal_last_error(void) { return g_err.c_str(); }
+// internal: lets the other translation units of the library report through cal_last_error()
+extern "C" void cal_set_last_error_(const char* msg) { g_err = msg ? msg : ""; }
 
 extern "C" int cal_device_count(void) {
     int n = 0;
