@@ -24,8 +24,10 @@ def compare_ransac(x, y, u, v, opts, seed_per_problem=True, min_margin=1e-9):
         if ro[p].success:
             Ho, Hg = np.array(ro[p].hmtx), np.array(rg[p].hmtx)
             assert np.abs(Hg - Ho).max() <= 1e-7 * np.abs(Ho).max(), p
-            assert abs(rg[p].inlier_rms - ro[p].inlier_rms) <= 1e-8 * max(ro[p].inlier_rms, 1e-12) + 1e-12
-            assert abs(rg[p].symmetric_rms_px - ro[p].symmetric_rms_px) <= 1e-8 * max(ro[p].symmetric_rms_px, 1e-12) + 1e-12
+            # absolute floors: an exact fit leaves residuals at rounding level (1e-14), and symmetric_rms_px takes
+            # the square root of a SUM OF ROOTS, which turns 1e-12 into 1e-6
+            assert abs(rg[p].inlier_rms - ro[p].inlier_rms) <= 1e-8 * ro[p].inlier_rms + 1e-9
+            assert abs(rg[p].symmetric_rms_px - ro[p].symmetric_rms_px) <= 1e-8 * ro[p].symmetric_rms_px + 1e-5
     return n_checked, ro, rg
 
 
