@@ -1,0 +1,247 @@
+// Source-compatible C++20 adapter: re-exposes the reference's refinement entry
+// points on top of the C ABI of calib_b200.h, so the reference's callers
+// (facades, stages, tests) keep compiling unchanged.
+//
+//   calib::optimize_intrinsics<CameraT>   include/calib/estimation/optim/intrinsics.h:35-39
+//   calib::optimize_extrinsics<CameraT>   include/calib/estimation/optim/extrinsics.h:29-34
+//   calib::optimize_bundle<CameraT>       include/calib/estimation/optim/bundle.h:58-63
+//   calib::optimize_handeye               include/calib/estimation/optim/handeye.h:40-43
+//   calib::estimate_homography (RANSAC)   include/calib/estimation/linear/homography.h:22-24
+//
+// It needs the reference's own headers (Eigen types, camera models, option and
+// result structs) and is therefore only compiled inside the reference tree —
+// Eigen is not present in the image this library is developed in, so this file
+// is exercised there, not here.  It contains no arithmetic:
+// packing into SoA/CSR, the C call, unpacking, and the error mapping
+// (CAL_ERR_INVALID_ARGUMENT -> std::invalid_argument, CAL_ERR_RUNTIME ->
+// std::runtime_error, anything else -> std::runtime_error).
+#pragma once
+#if __has_include(<Eigen/Core>) && __has_include("calib/estimation/optim/bundle.h")
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "calib/estimation/linear/handeye.h"
+#include "calib/estimation/linear/homography.h"
+#include "calib/estimation/optim/bundle.h"
+#include "calib/estimation/optim/extrinsics.h"
+#include "calib/estimation/optim/handeye.h"
+#include "calib/estimation/optim/intrinsics.h"
+#include "calib/models/scheimpflug.h"
+#include "calib_b200.h"
+
+namespace calib::b200 {
+
+inline void check(cal_status s) {
+    if (s == CAL_OK) return;
+    const std::string msg = cal_last_error();
+    if (s == CAL_ERR_INVALID_ARGUMENT) throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);
+}
+
+template <class CameraT> constexpr int model_of() {
+    return CameraTraits<CameraT>::param_count == 12 ? CAL_MODEL_SCHEIMPFLUG_BC5 : CAL_MODEL_PINHOLE_BC5;
+}
+
+// populate_quat_tran (src/estimation/detail/observationutils.h:43-48)
+inline void push_pose(const Eigen::Isometry3d& T, double* q, double* t) {
+    Eigen::Quaterniond q0(T.linear());
+    q[0] = q0.w(); q[1] = q0.x(); q[2] = q0.y(); q[3] = q0.z();
+    t[0] = T.translation().x(); t[1] = T.translation().y(); t[2] = T.translation().z();
+}
+// restore_pose (observationutils.h:50-62)
+inline Eigen::Isometry3d pop_pose(const double* q, const double* t) {
+    Eigen::Quaterniond qq(q[0], q[1], q[2], q[3]);
+    qq.normalize();
+    Eigen::Isometry3d T = Eigen::Isometry3d::Identity();
+    T.linear() = qq.toRotationMatrix();
+    T.translation() << t[0], t[1], t[2];
+    return T;
+}
+
+struct Soa {
+    std::vector<double> x, y, u, v;
+    std::vector<int64_t> off{0};
+    std::vector<int32_t> cam, view;
+    std::vector<double> bTg;
+    void add(const PlanarView& pv, int c, int vw) {
+        for (const auto& ob : pv) { x.push_back(ob.object_xy.x()); y.push_back(ob.object_xy.y()); u.push_back(ob.image_uv.x()); v.push_back(ob.image_uv.y()); }
+        off.push_back(static_cast<int64_t>(x.size())); cam.push_back(c); view.push_back(vw);
+    }
+    void fill(cal_problem_desc& d) const {
+        d.n_blocks = static_cast<int64_t>(cam.size()); d.n_obs = static_cast<int64_t>(x.size());
+        d.obj_x = x.data(); d.obj_y = y.data(); d.img_u = u.data(); d.img_v = v.data();
+        d.block_offset = off.data(); d.block_cam = cam.data(); d.block_view = view.data();
+        d.block_b_se3_g = bTg.empty() ? nullptr : bTg.data();
+    }
+};
+
+inline cal_optim_options to_c(const OptimOptions& o) {
+    return cal_optim_options{static_cast<int32_t>(o.optimizer), o.max_iterations, o.epsilon, o.compute_covariance ? 1 : 0,
+                             o.verbose ? 1 : 0, 0, 0};
+}
+
+inline void run(const cal_problem_desc& d, const OptimOptions& core, std::vector<double>& x, OptimResult& out) {
+    cal_refine_handle* h = nullptr;
+    check(cal_refine_create(&d, /*device=*/0, &h));
+    const cal_optim_options co = to_c(core);
+    cal_optim_result r{};
+    std::vector<double> cov(core.compute_covariance ? x.size() * x.size() : 0);
+    const cal_status s = cal_refine_solve(h, &co, x.data(), &r, cov.empty() ? nullptr : cov.data());
+    cal_refine_destroy(h);
+    check(s);
+    out.success = r.success != 0; out.final_cost = r.final_cost; out.report = r.report;
+    if (r.covariance_ok) {
+        const auto n = static_cast<Eigen::Index>(x.size());
+        out.covariance = Eigen::Map<const Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor>>(cov.data(), n, n);
+    }
+}
+
+}  // namespace calib::b200
+
+namespace calib {
+
+template <camera_model CameraT>
+auto optimize_bundle(const std::vector<BundleObservation>& observations, const std::vector<CameraT>& initial_cameras,
+                     const std::vector<Eigen::Isometry3d>& init_g_se3_c, const Eigen::Isometry3d& init_b_se3_t,
+                     const BundleOptions& opts) -> BundleResult<CameraT> {
+    constexpr int P = CameraTraits<CameraT>::param_count;
+    b200::Soa s;
+    for (const auto& ob : observations) {
+        s.add(ob.view, static_cast<int>(ob.camera_index), -1);
+        const Eigen::Matrix3d R = ob.b_se3_g.linear(); const Eigen::Vector3d t = ob.b_se3_g.translation();
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) s.bTg.push_back(R(i, j));
+        for (int i = 0; i < 3; ++i) s.bTg.push_back(t(i));
+    }
+    cal_problem_desc d{};
+    d.kind = CAL_KIND_BUNDLE; d.model = b200::model_of<CameraT>(); d.n_cams = static_cast<int>(initial_cameras.size());
+    d.optimize_intrinsics = opts.optimize_intrinsics; d.optimize_skew = opts.optimize_skew;
+    d.optimize_target_pose = opts.optimize_target_pose; d.optimize_hand_eye = opts.optimize_hand_eye;
+    d.huber_delta = opts.core.huber_delta;
+    s.fill(d);
+    const size_t nc = initial_cameras.size();
+    std::vector<double> x(nc * (P + 7) + 7);
+    for (size_t c = 0; c < nc; ++c) {
+        std::array<double, P> a{}; CameraTraits<CameraT>::to_array(initial_cameras[c], a);
+        std::copy(a.begin(), a.end(), x.begin() + c * P);
+        b200::push_pose(init_g_se3_c[c], &x[nc * P + 4 * c], &x[nc * (P + 4) + 3 * c]);
+    }
+    b200::push_pose(init_b_se3_t, &x[nc * (P + 7)], &x[nc * (P + 7) + 4]);
+    BundleResult<CameraT> result;
+    b200::run(d, opts.core, x, result.core);
+    result.cameras.resize(nc); result.g_se3_c.resize(nc);
+    for (size_t c = 0; c < nc; ++c) {
+        result.cameras[c] = CameraTraits<CameraT>::template from_array<double>(&x[c * P]);
+        result.g_se3_c[c] = b200::pop_pose(&x[nc * P + 4 * c], &x[nc * (P + 4) + 3 * c]);
+    }
+    result.b_se3_t = b200::pop_pose(&x[nc * (P + 7)], &x[nc * (P + 7) + 4]);
+    return result;
+}
+
+template <camera_model CameraT>
+auto optimize_intrinsics(const std::vector<PlanarView>& views, const CameraT& init_camera,
+                         std::vector<Eigen::Isometry3d> init_c_se3_t, const IntrinsicsOptimOptions& opts)
+    -> IntrinsicsOptimizationResult<CameraT> {
+    constexpr int P = CameraTraits<CameraT>::param_count;
+    b200::Soa s;
+    for (size_t v = 0; v < views.size(); ++v) s.add(views[v], 0, static_cast<int>(v));
+    cal_problem_desc d{};
+    d.kind = CAL_KIND_INTRINSICS; d.model = b200::model_of<CameraT>(); d.n_cams = 1; d.n_views = static_cast<int>(views.size());
+    d.optimize_intrinsics = 1; d.optimize_skew = opts.optimize_skew; d.huber_delta = opts.core.huber_delta;
+    s.fill(d);
+    const size_t nv = views.size();
+    std::vector<double> x(P + 7 * nv);
+    std::array<double, P> a{}; CameraTraits<CameraT>::to_array(init_camera, a);
+    std::copy(a.begin(), a.end(), x.begin());
+    for (size_t v = 0; v < nv; ++v) b200::push_pose(init_c_se3_t[v], &x[P + 4 * v], &x[P + 4 * nv + 3 * v]);
+    IntrinsicsOptimizationResult<CameraT> result;
+    b200::run(d, opts.core, x, result.core);
+    result.camera = CameraTraits<CameraT>::template from_array<double>(x.data());
+    result.c_se3_t.resize(nv);
+    for (size_t v = 0; v < nv; ++v) result.c_se3_t[v] = b200::pop_pose(&x[P + 4 * v], &x[P + 4 * nv + 3 * v]);
+    return result;
+}
+
+template <camera_model CameraT>
+auto optimize_extrinsics(const std::vector<MulticamPlanarView>& views, const std::vector<CameraT>& init_cameras,
+                         const std::vector<Eigen::Isometry3d>& init_c_se3_r, const std::vector<Eigen::Isometry3d>& init_r_se3_t,
+                         const ExtrinsicOptions& opts) -> ExtrinsicOptimizationResult<CameraT> {
+    constexpr int P = CameraTraits<CameraT>::param_count;
+    const size_t nc = init_cameras.size(), nv = views.size();
+    if (init_c_se3_r.size() != nc || init_r_se3_t.size() != nv)  // extrinsics.cpp:163-171
+        throw std::invalid_argument("Incompatible pose vector sizes for joint optimization");
+    b200::Soa s;
+    for (size_t v = 0; v < nv; ++v)
+        for (size_t c = 0; c < nc; ++c)
+            if (!views[v][c].empty()) s.add(views[v][c], static_cast<int>(c), static_cast<int>(v));  // extrinsics.cpp:94-96
+    cal_problem_desc d{};
+    d.kind = CAL_KIND_EXTRINSICS; d.model = b200::model_of<CameraT>(); d.n_cams = static_cast<int>(nc); d.n_views = static_cast<int>(nv);
+    d.optimize_intrinsics = opts.optimize_intrinsics; d.optimize_skew = opts.optimize_skew;
+    d.optimize_extrinsics = opts.optimize_extrinsics; d.huber_delta = opts.core.huber_delta;
+    s.fill(d);
+    std::vector<double> x(nc * (P + 7) + 7 * nv);
+    const size_t oq = nc * P, ot = oq + 4 * nc, vq = ot + 3 * nc, vt = vq + 4 * nv;
+    for (size_t c = 0; c < nc; ++c) {
+        std::array<double, P> a{}; CameraTraits<CameraT>::to_array(init_cameras[c], a);
+        std::copy(a.begin(), a.end(), x.begin() + c * P);
+        b200::push_pose(init_c_se3_r[c], &x[oq + 4 * c], &x[ot + 3 * c]);
+    }
+    for (size_t v = 0; v < nv; ++v) b200::push_pose(init_r_se3_t[v], &x[vq + 4 * v], &x[vt + 3 * v]);
+    ExtrinsicOptimizationResult<CameraT> result;
+    b200::run(d, opts.core, x, result.core);
+    result.cameras.resize(nc); result.c_se3_r.resize(nc); result.r_se3_t.resize(nv);
+    for (size_t c = 0; c < nc; ++c) {
+        result.cameras[c] = CameraTraits<CameraT>::template from_array<double>(&x[c * P]);
+        result.c_se3_r[c] = b200::pop_pose(&x[oq + 4 * c], &x[ot + 3 * c]);
+    }
+    for (size_t v = 0; v < nv; ++v) result.r_se3_t[v] = b200::pop_pose(&x[vq + 4 * v], &x[vt + 3 * v]);
+    return result;
+}
+
+inline auto optimize_handeye(const std::vector<Eigen::Isometry3d>& base_se3_gripper,
+                             const std::vector<Eigen::Isometry3d>& camera_se3_target,
+                             const Eigen::Isometry3d& init_gripper_se3_ref, const OptimOptions& options) -> HandeyeResult {
+    // pair construction stays the reference's own host code (linear/handeyedlt.cpp:51-81)
+    const auto pairs = build_all_pairs(base_se3_gripper, camera_se3_target, 0.5);  // handeye.cpp:63-64
+    std::vector<double> ra, rb, ta, tb;
+    for (const auto& mp : pairs) {
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { ra.push_back(mp.rot_a(i, j)); rb.push_back(mp.rot_b(i, j)); }
+        for (int i = 0; i < 3; ++i) { ta.push_back(mp.tra_a(i)); tb.push_back(mp.tra_b(i)); }
+    }
+    cal_axxb_desc d{static_cast<int64_t>(pairs.size()), ra.data(), rb.data(), ta.data(), tb.data(), options.huber_delta};
+    cal_axxb_handle* h = nullptr;
+    b200::check(cal_axxb_create(&d, 0, &h));
+    double x[7]; b200::push_pose(init_gripper_se3_ref, x, x + 4);
+    const cal_optim_options co = b200::to_c(options);
+    cal_optim_result r{}; double cov[49];
+    const cal_status s = cal_axxb_solve(h, &co, x, &r, options.compute_covariance ? cov : nullptr);
+    cal_axxb_destroy(h);
+    b200::check(s);
+    HandeyeResult result;
+    result.core.success = r.success != 0; result.core.final_cost = r.final_cost; result.core.report = r.report;
+    if (r.covariance_ok) result.core.covariance = Eigen::Map<const Eigen::Matrix<double, 7, 7, Eigen::RowMajor>>(cov);
+    result.g_se3_c = b200::pop_pose(x, x + 4);
+    return result;
+}
+
+// RANSAC branch of estimate_homography (optim/homography.cpp:45-73); the plain DLT branch stays on the host.
+inline auto estimate_homography_ransac_b200(const PlanarView& data, const RansacOptions& ro) -> HomographyResult {
+    const auto n = static_cast<int32_t>(data.size());
+    std::vector<double> x(n), y(n), u(n), v(n);
+    for (int i = 0; i < n; ++i) { x[i] = data[i].object_xy.x(); y[i] = data[i].object_xy.y(); u[i] = data[i].image_uv.x(); v[i] = data[i].image_uv.y(); }
+    const cal_ransac_options co{ro.max_iters, ro.min_inliers, ro.thresh, ro.confidence, ro.seed, ro.refit_on_inliers ? 1 : 0, 0};
+    cal_ransac_result r{}; std::vector<uint8_t> mask(n);
+    b200::check(cal_ransac_homography_batch(1, n, x.data(), y.data(), u.data(), v.data(), &co, 0, 0, &r, mask.data()));
+    HomographyResult out;
+    out.success = r.success != 0;
+    if (out.success) {
+        out.hmtx = Eigen::Map<const Eigen::Matrix<double, 3, 3, Eigen::RowMajor>>(r.hmtx);
+        for (int i = 0; i < n; ++i) if (mask[i]) out.inliers.push_back(i);
+        out.symmetric_rms_px = r.symmetric_rms_px;
+    }
+    return out;
+}
+
+}  // namespace calib
+#endif

@@ -1,0 +1,59 @@
+"""Throughput probes for the secondary kernels (RANSAC K3, AX=XB) at BASELINE sizes; prints JSON lines."""
+import ctypes as C, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+from calibration_b200 import abi, capi, synth
+
+what = sys.argv[1] if len(sys.argv) > 1 else "ransac"
+if what == "ransac":
+    npb, n = int(sys.argv[2]) if len(sys.argv) > 2 else 100000, 500
+    t0 = time.time(); x, y, u, v, _ = synth.synth_ransac(seed=17, n_problems=npb, n=n); gen = time.time() - t0
+    dev = [torch.from_numpy(a).cuda() for a in (x, y, u, v)]
+    res = torch.empty(npb * C.sizeof(abi.RansacResult), dtype=torch.uint8, device="cuda")
+    mask = torch.empty(npb * n, dtype=torch.uint8, device="cuda")
+    opts = abi.RansacOptions.default()
+    ms = C.c_float()
+    L = capi.lib()
+    for rep in range(3):
+        rc = L.cal_ransac_homography_batch_dev(npb, n, *[C.c_void_p(d.data_ptr()) for d in dev], C.byref(opts), 1,
+                                               C.c_void_p(res.data_ptr()), C.c_void_p(mask.data_ptr()), C.byref(ms))
+        assert rc == 0, L.cal_last_error()
+    r = np.frombuffer(res.cpu().numpy().tobytes(), dtype=np.dtype([("success", "i4"), ("iters", "i4"), ("n_inliers", "i4"), ("iters_run", "i4"),
+                                                                    ("h", "f8", 9), ("rms", "f8"), ("sym", "f8"), ("mm", "f8")]))
+    hyp = int(r["iters_run"].sum())
+    t0 = time.perf_counter(); capi.ransac_homography_batch(x, y, u, v, opts, want_mask=True); e2e = time.perf_counter() - t0
+    out = {"kernel": "k_ransac", "problems": npb, "n": n, "ms": ms.value, "problems_per_s": npb / (ms.value * 1e-3),
+           "hypotheses": hyp, "mean_iters_run": hyp / npb, "hyp_point_scores_per_s": hyp * n * 2 / (ms.value * 1e-3),
+           "success": int(r["success"].sum()), "mean_inliers": float(r["n_inliers"].mean()),
+           "hbm_read_GBps": 32.0 * npb * n / (ms.value * 1e-3) / 1e9, "e2e_host_call_s": e2e, "gen_s": gen}
+    print(json.dumps(out))
+    if len(sys.argv) > 3 and sys.argv[3] == "cpu":
+        import oracle_lib as O
+        k = 2000
+        t0 = time.perf_counter(); O.ransac_batch(x[:k], y[:k], u[:k], v[:k], opts); dt = time.perf_counter() - t0
+        print(json.dumps({"cpu_oracle_problems_per_s": k / dt, "cores": os.cpu_count(), "sample": k}))
+else:
+    import oracle_lib as O
+    n_poses = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
+    rng = np.random.default_rng(1)
+    # synthetic motion pairs directly (pair construction is a host-side "next" row)
+    npairs = n_poses * (n_poses - 1) // 2
+    from calibration_b200 import geometry as G
+    X = G.make_pose([0.02, -0.01, 0.09], [0.2, 0.9, 0.1], 0.17)
+    A = synth.random_poses(rng, npairs, 25.0, (-0.1, 0.1), 0.1)
+    Xi = G.inv_pose(X)
+    B = Xi[None] @ A @ X[None]
+    ra = np.ascontiguousarray(A[:, :3, :3].reshape(npairs, 9)); rb = np.ascontiguousarray(B[:, :3, :3].reshape(npairs, 9))
+    ta = np.ascontiguousarray(A[:, :3, 3]) + rng.normal(scale=1e-3, size=(npairs, 3)); tb = np.ascontiguousarray(B[:, :3, 3])
+    t0 = time.perf_counter(); h = capi.AxxbHandle(ra, rb, ta, tb, 1.0); create = time.perf_counter() - t0
+    x0 = G.pack_handeye(synth.perturb_pose(rng, X, 2.0, 0.01))
+    h.eval(x0)
+    t0 = time.perf_counter()
+    for _ in range(5): h.eval(x0)
+    dt = (time.perf_counter() - t0) / 5
+    t0 = time.perf_counter(); xs, res, cov = h.solve(x0); ts = time.perf_counter() - t0
+    print(json.dumps({"kernel": "k_axxb", "pairs": npairs, "eval_ms_incl_sync": dt * 1e3, "pairs_per_s": npairs / dt,
+                      "hbm_GBps": 192.0 * npairs / dt / 1e9, "create_s": create, "solve_s": ts, "report": res.report.decode(),
+                      "param_err": float(np.abs(xs - G.pack_handeye(X)).max())}))
