@@ -48,7 +48,9 @@ def lib():
     L.cal_fp64_peak_tflops.argtypes = [C.c_int, dp]
     L.cal_refine_solve.argtypes = [hp, C.POINTER(abi.OptimOptions), dp, C.POINTER(abi.OptimResult), dp]
     L.cal_comm_unique_id.argtypes = [u8p]
-    L.cal_refine_attach_comm.argtypes = [hp, u8p, C.c_int, C.c_int]
+    L.cal_comm_create.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.POINTER(hp)]
+    L.cal_comm_destroy.argtypes = [hp]
+    L.cal_refine_attach_comm.argtypes = [hp, hp]
     for name, argt in (
         ("cal_axxb_create", [C.POINTER(abi.AxxbDesc), C.c_int, C.POINTER(hp)]),
         ("cal_axxb_destroy", [hp]),
@@ -148,15 +150,30 @@ class RefineHandle:
         _check(lib().cal_refine_solve(self._h, C.byref(opts), abi.dptr(x), C.byref(res), abi.dptr(cov)))
         return x, res, cov
 
-    def attach_comm(self, unique_id, rank, world):
-        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
-        _check(lib().cal_refine_attach_comm(self._h, buf, rank, world))
+    def attach_comm(self, comm):
+        self._comm = comm  # keep it alive
+        _check(lib().cal_refine_attach_comm(self._h, comm._c if comm is not None else None))
 
 
 def comm_unique_id():
     buf = (C.c_uint8 * 128)()
     _check(lib().cal_comm_unique_id(buf))
     return bytes(buf)
+
+
+class Comm:
+    """cal_comm: process-lifetime NCCL communicator (one process per GPU)."""
+
+    def __init__(self, unique_id, rank, world, device):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._c = C.c_void_p()
+        _check(lib().cal_comm_create(buf, rank, world, device, C.byref(self._c)))
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if self._c:
+            lib().cal_comm_destroy(self._c)
+            self._c = C.c_void_p()
 
 
 class AxxbHandle:

@@ -92,7 +92,7 @@ struct cal_refine_handle {
     // host mirrors of the last Jacobian evaluation (shared block)
     std::vector<double> Hss, gs, cam_sums;
     double cost = 0;
-    calcomm::Comm* comm = nullptr;
+    calcomm::Comm* comm = nullptr;  // not owned (cal_comm_create / cal_comm_destroy)
     // counters
     int64_t launches = 0;
 
@@ -112,7 +112,6 @@ struct cal_refine_handle {
     ~cal_refine_handle() {
         for (void* p : allocs) cudaFree(p);
         if (st) cudaStreamDestroy(st);
-        delete comm;
     }
 };
 
@@ -885,13 +884,23 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
     return CAL_OK;
 }
 
-extern "C" cal_status cal_refine_attach_comm(cal_refine_handle* h, const uint8_t unique_id[128], int rank, int world_size) {
-    if (!h || !unique_id) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
-    CUDA_TRY(cudaSetDevice(h->device));
-    delete h->comm; h->comm = nullptr;
+struct cal_comm { calcomm::Comm* c = nullptr; };
+
+extern "C" cal_status cal_comm_create(const uint8_t unique_id[128], int rank, int world_size, int device, cal_comm** out) {
+    if (!unique_id || !out) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (cal_device_count() <= device) return fail(CAL_ERR_CUDA, "no CUDA device: calib_b200 has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(device));
     std::string err;
-    h->comm = calcomm::Comm::create(unique_id, rank, world_size, &err);
-    if (!h->comm) return fail(CAL_ERR_COMM, err);
+    calcomm::Comm* c = calcomm::Comm::create(unique_id, rank, world_size, &err);
+    if (!c) return fail(CAL_ERR_COMM, err);
+    *out = new cal_comm{c};
+    return CAL_OK;
+}
+extern "C" void cal_comm_destroy(cal_comm* c) { if (c) { delete c->c; delete c; } }
+extern "C" cal_status cal_refine_attach_comm(cal_refine_handle* h, cal_comm* c) {
+    if (!h) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    h->comm = c ? c->c : nullptr;
     return CAL_OK;
 }
 extern "C" cal_status cal_comm_unique_id(uint8_t out128[128]) {

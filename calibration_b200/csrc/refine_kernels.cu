@@ -21,6 +21,9 @@
 //                   Schur complement onto the shared block as a tiled rank-6
 //                   SYRK, back-substitution
 #include <stdio.h>
+#include <stdlib.h>
+
+#include <type_traits>
 
 #include "refine_kernels.cuh"
 
@@ -179,11 +182,166 @@ __global__ void __launch_bounds__(128) k1_kernel(DevLayout L, EvalBuffers B) {
     if (NPASS > 2 && pass == 2) k1_body<MODEL, IMODE, NPASS, (NPASS > 2 ? 2 : 0)>(L, B, tile, lane);
 }
 
+// ---------------------------------------------------------------------------
+// K1 v2: producer / consumer warp pairs (pinhole model with free intrinsics)
+// ---------------------------------------------------------------------------
+// The 136/153 accumulators of the local system do not fit one thread.  v1 splits
+// them over passes that each recompute the projection and Jacobian.  v2 pairs two
+// warps on the same tile instead: warp A projects, forms the Jacobian rows once,
+// hands the 24 values warp B needs through a double-buffered shared-memory slot
+// (named barriers: A st.shared + bar.arrive, B bar.sync + ld.shared — the PTX
+// producer/consumer idiom) and accumulates the entries that involve a linear
+// intrinsic column (fx, fy, cx, cy, skew) plus |r|^2; warp B accumulates the
+// twist / distortion / residual block.  Both do ~155 FP64 instructions per
+// observation, nothing is computed twice, and B's stream of independent FMAs
+// fills the FP64 pipe while A sits in the dependent projection chain.
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
+}
+
+template <class LT>
+struct Split {
+    static constexpr bool is_lin(int c) {  // linear intrinsic columns
+        return c >= 6 && c < LT::NC && c - 6 < LT::c_d0;
+    }
+    static constexpr bool in_a(int a, int b) { return is_lin(a) || is_lin(b) || (a == LT::NC && b == LT::NC); }
+    static constexpr int slot(int a, int b) {  // index of (a,b) among the entries of its own role
+        const bool ra = in_a(a, b);
+        int n = 0;
+        for (int i = 0; i < LT::NL; ++i)
+            for (int j = i; j < LT::NL; ++j) {
+                if (i == a && j == b) return n;
+                if (in_a(i, j) == ra) ++n;
+            }
+        return n;
+    }
+    static constexpr int count(bool ra) {
+        int n = 0;
+        for (int i = 0; i < LT::NL; ++i) for (int j = i; j < LT::NL; ++j) if (in_a(i, j) == ra) ++n;
+        return n;
+    }
+    static constexpr int NA = count(true), NB = count(false);
+    // exchange slots: for every non-linear column c its u value at 2*x(c), v value at 2*x(c)+1
+    static constexpr int xcol(int c) { int n = 0; for (int i = 0; i < c; ++i) if (!is_lin(i)) ++n; return n; }
+    static constexpr int NX = 2 * (LT::NL - (LT::c_d0 < 0 ? 0 : LT::c_d0));
+};
+
+__device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+template <int MODEL, int IMODE>
+__global__ void __launch_bounds__(256, 1) k1v2_kernel(DevLayout L, EvalBuffers B) {
+    using LT = Local<MODEL, IMODE>;
+    using SP = Split<LT>;
+    constexpr int NX = SP::NX;
+    __shared__ double xbuf[4][2][NX][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = warp & 3;
+    const bool role_b = ((warp >> 2) ^ (warp & 1)) != 0;  // each SM sub-partition hosts one A and one B warp
+    const int64_t tile = (int64_t)blockIdx.x * 4 + pair;
+    if (tile >= L.n_tiles) return;  // both warps of the pair leave together
+    const int64_t s = tile * 32 + lane;
+    const int len = L.seg_len[s];
+    const int depth = L.tile_depth[tile];
+    const int bar_full = 4 * pair, bar_empty = 4 * pair + 2;
+    if (!role_b) {
+        double A[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) A[i] = B.seg_frame[(int64_t)i * L.n_seg + s];
+        const CamConst c = B.camc[L.seg_cam[s]];
+        const double* __restrict__ p = L.obs + L.tile_off[tile] * 128 + lane;
+        double acc[SP::NA];
+#pragma unroll
+        for (int i = 0; i < SP::NA; ++i) acc[i] = 0.0;
+        double X = 0, Y = 0, U = 0, V = 0;
+        if (depth > 0) { X = p[0]; Y = p[32]; U = p[64]; V = p[96]; }
+        for (int k = 0; k < depth; ++k) {
+            const int st = k & 1;
+            double Xn = 0, Yn = 0, Un = 0, Vn = 0;
+            if (k + 1 < depth) { const double* q = p + (int64_t)(k + 1) * 128; Xn = q[0]; Yn = q[32]; Un = q[64]; Vn = q[96]; }
+            double Ju[LT::NL], Jv[LT::NL];
+            const bool act = k < len;
+            if (act) obs_rows<MODEL, IMODE>(c, A, X, Y, U, V, Ju, Jv);
+            if (k >= 2) bar_sync64(bar_empty + st);  // B has drained this stage
+            if (act) {
+                static_for<0, LT::NL>([&](auto cc) {
+                    constexpr int col = decltype(cc)::value;
+                    if constexpr (!SP::is_lin(col)) {
+                        xbuf[pair][st][2 * SP::xcol(col)][lane] = Ju[col];
+                        xbuf[pair][st][2 * SP::xcol(col) + 1][lane] = Jv[col];
+                    }
+                });
+            }
+            bar_arrive64(bar_full + st);
+            if (act) {
+                static_for<0, LT::NL>([&](auto ca) {
+                    static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
+                        constexpr int a = decltype(ca)::value, b = decltype(cb)::value;
+                        if constexpr (SP::in_a(a, b)) {
+                            constexpr int sl = SP::slot(a, b);
+                            if constexpr (LT::has_u(a) && LT::has_u(b)) acc[sl] = fma(Ju[a], Ju[b], acc[sl]);
+                            if constexpr (LT::has_v(a) && LT::has_v(b)) acc[sl] = fma(Jv[a], Jv[b], acc[sl]);
+                        }
+                    });
+                });
+            }
+            X = Xn; Y = Yn; U = Un; V = Vn;
+        }
+        static_for<0, LT::NL>([&](auto ca) {
+            static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
+                constexpr int a = decltype(ca)::value, b = decltype(cb)::value;
+                if constexpr (SP::in_a(a, b)) B.segN[(int64_t)LT::idx(a, b) * L.n_seg + s] = acc[SP::slot(a, b)];
+            });
+        });
+    } else {
+        double acc[SP::NB];
+#pragma unroll
+        for (int i = 0; i < SP::NB; ++i) acc[i] = 0.0;
+        for (int k = 0; k < depth; ++k) {
+            const int st = k & 1;
+            const bool act = k < len;
+            bar_sync64(bar_full + st);
+            double Ju[LT::NL], Jv[LT::NL];
+            if (act) {
+                static_for<0, LT::NL>([&](auto cc) {
+                    constexpr int col = decltype(cc)::value;
+                    if constexpr (!SP::is_lin(col)) {
+                        Ju[col] = xbuf[pair][st][2 * SP::xcol(col)][lane];
+                        Jv[col] = xbuf[pair][st][2 * SP::xcol(col) + 1][lane];
+                    }
+                });
+            }
+            if (k + 2 < depth) bar_arrive64(bar_empty + st);
+            if (act) {
+                static_for<0, LT::NL>([&](auto ca) {
+                    static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
+                        constexpr int a = decltype(ca)::value, b = decltype(cb)::value;
+                        if constexpr (!SP::in_a(a, b)) {
+                            constexpr int sl = SP::slot(a, b);
+                            if constexpr (LT::has_u(a) && LT::has_u(b)) acc[sl] = fma(Ju[a], Ju[b], acc[sl]);
+                            if constexpr (LT::has_v(a) && LT::has_v(b)) acc[sl] = fma(Jv[a], Jv[b], acc[sl]);
+                        }
+                    });
+                });
+            }
+        }
+        static_for<0, LT::NL>([&](auto ca) {
+            static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
+                constexpr int a = decltype(ca)::value, b = decltype(cb)::value;
+                if constexpr (!SP::in_a(a, b)) B.segN[(int64_t)LT::idx(a, b) * L.n_seg + s] = acc[SP::slot(a, b)];
+            });
+        });
+    }
+}
+
 template <int MODEL, int IMODE>
 constexpr int passes_for() {
     return Local<MODEL, IMODE>::NE <= 72 ? 1 : (Local<MODEL, IMODE>::NE <= 144 ? 2 : 3);
 }
+bool k1_uses_pairs(const ProblemShape& S);
 int k1_num_passes(const ProblemShape& S) {
+    if (k1_uses_pairs(S)) return 1;
     return S.NE <= 72 ? 1 : (S.NE <= 144 ? 2 : 3);
 }
 
@@ -203,8 +361,20 @@ static void launch_k1_t(const DevLayout& L, const EvalBuffers& B, cudaStream_t s
         else FN<1, 2>(__VA_ARGS__);                                                        \
     } while (0)
 
+static int k1_variant() {  // CALIB_B200_K1=v1 forces the multi-pass kernel (A/B comparison while profiling)
+    static const int v = [] { const char* e = getenv("CALIB_B200_K1"); return (e && e[0] == 'v' && e[1] == '1') ? 1 : 2; }();
+    return v;
+}
+bool k1_uses_pairs(const ProblemShape& S) { return S.model == 0 && S.imode != 0 && k1_variant() == 2; }
+
 void launch_k1(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
     if (L.n_tiles == 0) return;
+    if (k1_uses_pairs(S)) {
+        const unsigned grid = (unsigned)((L.n_tiles + 3) / 4);
+        if (S.imode == 1) k1v2_kernel<0, 1><<<grid, 256, 0, st>>>(L, B);
+        else k1v2_kernel<0, 2><<<grid, 256, 0, st>>>(L, B);
+        return;
+    }
     CALK_DISPATCH(launch_k1_t, L, B, st);
 }
 

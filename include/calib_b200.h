@@ -152,11 +152,17 @@ cal_status cal_refine_solve(cal_refine_handle* h, const cal_optim_options* opts,
 
 /* Optional multi-GPU sharding (one process per GPU).  Each rank creates its
  * handle over its own shard of the residual blocks (all ranks pass identical
- * n_cams / n_views / parameter vectors) and then attaches a communicator; the
- * per-evaluation normal-equation blocks are summed with ncclAllReduce.
- * unique_id is the 128-byte ncclUniqueId created by rank 0 (cal_comm_unique_id). */
+ * n_cams and shared parameters) and attaches a communicator; the per-camera
+ * normal-equation blocks are then summed with ncclAllReduce (FP64) after the
+ * reductions of every pass, and the host LM runs replicated on all ranks.
+ * unique_id is the 128-byte ncclUniqueId created by rank 0 (cal_comm_unique_id)
+ * and distributed by the caller; the communicator is a process-lifetime object
+ * that can serve any number of handles. */
+typedef struct cal_comm cal_comm;
 cal_status cal_comm_unique_id(uint8_t out128[128]);
-cal_status cal_refine_attach_comm(cal_refine_handle* h, const uint8_t unique_id[128], int rank, int world_size);
+cal_status cal_comm_create(const uint8_t unique_id[128], int rank, int world_size, int device, cal_comm** out);
+void cal_comm_destroy(cal_comm* c);
+cal_status cal_refine_attach_comm(cal_refine_handle* h, cal_comm* c);
 
 /* ---- AX = XB hand-eye refinement: optimize_handeye (optim/handeye.h:40-43,
  * src/estimation/optim/handeye.cpp:45-78) over MotionPairs (linear/handeye.h:29-32). */
