@@ -6,8 +6,10 @@
 // here on the host; every O(observations) or O(views) pass is a kernel of
 // refine_kernels.cu.  There is no CPU fallback: a missing device is an error.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -104,13 +106,25 @@ struct cal_refine_handle {
     int pb_bq() const { return 3 * S.n_cams; }
     int pb_bt() const { return 3 * S.n_cams + 1; }
 
+    // all device buffers of a handle are carved from one arena (one cudaMalloc / cudaFree)
+    unsigned char* arena = nullptr; size_t arena_size = 0, arena_used = 0;
+    // stream-ordered allocation from the device's default memory pool (release threshold raised in
+    // cal_refine_create), so repeated create / destroy cycles reuse the same physical memory
+    cudaError_t arena_reserve(size_t bytes) {
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&arena), bytes, st);
+        if (e == cudaSuccess) { arena_size = bytes; arena_used = 0; }
+        return e;
+    }
     template <class T> cudaError_t alloc(T** p, size_t n) {
+        const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255) / 256 * 256;
+        if (arena && arena_used + bytes <= arena_size) { *p = reinterpret_cast<T*>(arena + arena_used); arena_used += bytes; return cudaSuccess; }
         cudaError_t e = dev_alloc(p, n);
         if (e == cudaSuccess) allocs.push_back(*p);
         return e;
     }
     ~cal_refine_handle() {
         for (void* p : allocs) cudaFree(p);
+        if (arena && st) { cudaFreeAsync(arena, st); cudaStreamSynchronize(st); }
         if (st) cudaStreamDestroy(st);
     }
 };
@@ -230,22 +244,46 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         S.off_viewq = S.off_camt + 3 * d.n_cams; S.off_viewt = S.off_viewq + 4;  // b_q_t, b_t_t
     }
 
-    // ---- device block order: by camera, camera groups padded to 32 ----
-    std::vector<int64_t> order(d.n_blocks);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return d.block_cam[a] < d.block_cam[b]; });
+    // ---- start the big copy first: raw SoA observations into one staging buffer on a copy
+    // stream, so the transfer overlaps the host-side layout construction below ----
+    const bool trace = getenv("CALIB_B200_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (trace) std::fprintf(stderr, "[calib_b200] create: %-28s %8.2f ms\n", what,
+                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    };
+    {   // keep freed blocks cached in the default pool instead of returning them to the OS at every sync
+        cudaMemPool_t pool; uint64_t thr = UINT64_MAX;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    double* raw = nullptr;
+    cudaStream_t cst = nullptr;
+    CUDA_TRY(cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&raw), sizeof(double) * 4 * (size_t)d.n_obs, cst));
+    {
+        const size_t nb = (size_t)d.n_obs * sizeof(double);
+        CUDA_TRY(cudaMemcpyAsync(raw, d.obj_x, nb, cudaMemcpyHostToDevice, cst));
+        CUDA_TRY(cudaMemcpyAsync(raw + d.n_obs, d.obj_y, nb, cudaMemcpyHostToDevice, cst));
+        CUDA_TRY(cudaMemcpyAsync(raw + 2 * d.n_obs, d.img_u, nb, cudaMemcpyHostToDevice, cst));
+        CUDA_TRY(cudaMemcpyAsync(raw + 3 * d.n_obs, d.img_v, nb, cudaMemcpyHostToDevice, cst));
+    }
+    lap("copies issued");
+    // ---- device block order: by camera (counting sort, stable), camera groups padded to 32 ----
     std::vector<int64_t>& borig = h.blk_orig_host;
     std::vector<int32_t>&bcam = h.blk_cam_host, &bview = h.blk_view_host;
     {
-        size_t i = 0;
-        while (i < order.size()) {
-            const int cam = d.block_cam[order[i]];
-            while (i < order.size() && d.block_cam[order[i]] == cam) {
-                borig.push_back(order[i]); bcam.push_back(cam);
-                bview.push_back(d.kind == CAL_KIND_INTRINSICS ? (int32_t)order[i] : (d.kind == CAL_KIND_EXTRINSICS ? d.block_view[order[i]] : -1));
-                ++i;
-            }
-            while (borig.size() % 32) { borig.push_back(-1); bcam.push_back(cam); bview.push_back(-1); }
+        std::vector<int64_t> cnt(d.n_cams + 1, 0);
+        for (int64_t b = 0; b < d.n_blocks; ++b) cnt[d.block_cam[b]]++;
+        std::vector<int64_t> start(d.n_cams + 1, 0);
+        for (int c = 0; c < d.n_cams; ++c) start[c + 1] = start[c] + (cnt[c] + 31) / 32 * 32;
+        const int64_t tot = start[d.n_cams];
+        borig.assign(tot, -1); bcam.assign(tot, 0); bview.assign(tot, -1);
+        for (int c = 0; c < d.n_cams; ++c) std::fill(bcam.begin() + start[c], bcam.begin() + start[c + 1], c);
+        std::vector<int64_t> cur(start.begin(), start.end() - 1);
+        for (int64_t b = 0; b < d.n_blocks; ++b) {
+            const int64_t pos = cur[d.block_cam[b]]++;
+            borig[pos] = b;
+            bview[pos] = d.kind == CAL_KIND_INTRINSICS ? (int32_t)b : (d.kind == CAL_KIND_EXTRINSICS ? d.block_view[b] : -1);
         }
     }
     const int64_t nblk = (int64_t)borig.size();
@@ -256,13 +294,19 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     const int64_t target = std::min<int64_t>(std::max<int64_t>(8, (d.n_obs + 65535) / 65536), std::max<int64_t>(max_len, 1));
     std::vector<int32_t> seg_len, seg_blk, seg_cam, blk_seg_off(nblk + 1, 0), blk_vfree(nblk, 0);
     std::vector<int64_t> seg_src;
+    {
+        const size_t guess = (size_t)(d.n_obs / target + nblk + 64);
+        seg_len.reserve(guess); seg_blk.reserve(guess); seg_cam.reserve(guess); seg_src.reserve(guess);
+    }
     h.view_free_host.assign(std::max(S.n_views, 0), 0);
     for (int v = 0; v < S.n_views; ++v) h.view_free_host[v] = !h.pbs[h.pb_viewq(v)].constant;
+    h.L.one_seg_per_blk = 1;
     for (int64_t b = 0; b < nblk; ++b) {
         blk_seg_off[b] = (int32_t)seg_len.size();
         if (borig[b] < 0) continue;
         const int64_t o0 = d.block_offset[borig[b]], len = d.block_offset[borig[b] + 1] - o0;
-        const int64_t nseg = (len + target - 1) / target, sl = (len + nseg - 1) / nseg;
+        const int64_t nsegb = (len + target - 1) / target, sl = (len + nsegb - 1) / nsegb;
+        if (nsegb != 1) h.L.one_seg_per_blk = 0;
         for (int64_t k = 0; k < len; k += sl) {
             seg_len.push_back((int32_t)std::min<int64_t>(sl, len - k)); seg_blk.push_back((int32_t)b);
             seg_cam.push_back(bcam[b]); seg_src.push_back(o0 + k);
@@ -270,8 +314,6 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         blk_vfree[b] = d.kind == CAL_KIND_BUNDLE ? (d.optimize_target_pose != 0) : (bview[b] >= 0 && h.view_free_host[bview[b]]);
     }
     blk_seg_off[nblk] = (int32_t)seg_len.size();
-    h.L.one_seg_per_blk = 1;
-    for (int64_t b = 0; b < nblk; ++b) if (borig[b] >= 0 && blk_seg_off[b + 1] - blk_seg_off[b] != 1) { h.L.one_seg_per_blk = 0; break; }
     while (seg_len.size() % 32) { seg_len.push_back(0); seg_blk.push_back(0); seg_cam.push_back(0); seg_src.push_back(0); }
     const int64_t nseg = (int64_t)seg_len.size(), ntiles = nseg / 32;
     h.L.n_seg = nseg; h.L.n_tiles = ntiles;
@@ -282,7 +324,19 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         tile_off[t] = slices; tile_depth[t] = dep; slices += dep;
     }
     h.L.n_slices = slices;
+    lap("host layout built");
 
+    // ---- one arena for every device buffer of the handle ----
+    {
+        const size_t nbr = (size_t)(S.NV - S.NE);
+        size_t bytes = (size_t)slices * 128 * 8 + (size_t)ntiles * 12 + (size_t)nseg * (12 + 8 * (9 + S.NE + 2)) +
+                       (size_t)nblk * (4 * 4 + 8 + 8 * (36 + 2 + nbr + 12)) + (size_t)h.n_amb * 16 + (1u << 20);
+        if (S.n_views > 0) bytes += (size_t)nblk * 8 * (21 + 6 + 36 + 6 * std::max(S.PI, 1) + 6 * (6 + S.PI)) + (size_t)S.n_views * 8 * 120 +
+                                    (size_t)schur_num_ctas(S.n_views) * (h.ns + 1) * (h.ns + 1) * 8 + (size_t)h.ns * h.ns * 8 + (1u << 20);
+        bytes += 256 * 64;  // alignment slack
+        CUDA_TRY(h.arena_reserve(bytes));
+    }
+    lap("arena allocated");
     // ---- uploads ----
     DevLayout& L = h.L;
     CUDA_TRY(h.alloc(&L.obs, (size_t)slices * 128));
@@ -294,25 +348,26 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     CUDA_TRY(upload(L.seg_len, seg_len, h.st)); CUDA_TRY(upload(L.seg_blk, seg_blk, h.st)); CUDA_TRY(upload(L.seg_cam, seg_cam, h.st));
     CUDA_TRY(upload(L.blk_cam, bcam, h.st)); CUDA_TRY(upload(L.blk_view, bview, h.st)); CUDA_TRY(upload(L.blk_orig, borig, h.st));
     CUDA_TRY(upload(L.blk_seg_off, blk_seg_off, h.st)); CUDA_TRY(upload(L.blk_vfree, blk_vfree, h.st));
-    if (d.kind == CAL_KIND_BUNDLE) {
-        std::vector<double> bTg((size_t)12 * nblk, 0.0);
-        for (int64_t b = 0; b < nblk; ++b)
-            for (int i = 0; i < 12; ++i) bTg[(size_t)i * nblk + b] = borig[b] >= 0 ? d.block_b_se3_g[12 * borig[b] + i] : (i % 4 == 0 && i < 9 ? 1.0 : 0.0);
-        CUDA_TRY(h.alloc(&L.blk_bTg, bTg.size())); CUDA_TRY(upload(L.blk_bTg, bTg, h.st));
+    double* raw_bTg = nullptr;
+    if (d.kind == CAL_KIND_BUNDLE) {  // robot poses: upload AoS, permute + transpose on the device
+        CUDA_TRY(h.alloc(&L.blk_bTg, (size_t)12 * nblk));
+        CUDA_TRY(dev_alloc(&raw_bTg, (size_t)12 * d.n_blocks));
+        CUDA_TRY(cudaMemcpyAsync(raw_bTg, d.block_b_se3_g, sizeof(double) * 12 * d.n_blocks, cudaMemcpyHostToDevice, h.st));
+        launch_btg_permute(L, raw_bTg, h.st);
     }
-    {   // raw SoA upload + one-time repack into the tile-transposed layout
-        double *rx, *ry, *ru, *rv; int64_t* dsrc;
-        CUDA_TRY(dev_alloc(&rx, d.n_obs)); CUDA_TRY(dev_alloc(&ry, d.n_obs)); CUDA_TRY(dev_alloc(&ru, d.n_obs)); CUDA_TRY(dev_alloc(&rv, d.n_obs));
+    {   // one-time repack into the tile-transposed layout (waits for the raw copy)
+        int64_t* dsrc;
         CUDA_TRY(dev_alloc(&dsrc, nseg));
-        const size_t nb = (size_t)d.n_obs * sizeof(double);
-        CUDA_TRY(cudaMemcpyAsync(rx, d.obj_x, nb, cudaMemcpyHostToDevice, h.st));
-        CUDA_TRY(cudaMemcpyAsync(ry, d.obj_y, nb, cudaMemcpyHostToDevice, h.st));
-        CUDA_TRY(cudaMemcpyAsync(ru, d.img_u, nb, cudaMemcpyHostToDevice, h.st));
-        CUDA_TRY(cudaMemcpyAsync(rv, d.img_v, nb, cudaMemcpyHostToDevice, h.st));
         CUDA_TRY(upload(dsrc, seg_src, h.st));
-        launch_repack(L, rx, ry, ru, rv, dsrc, h.st);
+        cudaEvent_t copied; CUDA_TRY(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(copied, cst));
+        CUDA_TRY(cudaStreamWaitEvent(h.st, copied, 0));
+        launch_repack(L, raw, raw + d.n_obs, raw + 2 * d.n_obs, raw + 3 * d.n_obs, dsrc, h.st);
         CUDA_TRY(cudaStreamSynchronize(h.st));
-        cudaFree(rx); cudaFree(ry); cudaFree(ru); cudaFree(rv); cudaFree(dsrc);
+        lap("copied + repacked");
+        cudaEventDestroy(copied);
+        cudaFreeAsync(raw, h.st); cudaStreamSynchronize(h.st); cudaStreamDestroy(cst);
+        cudaFree(dsrc); cudaFree(raw_bTg);
         CUDA_TRY(cudaGetLastError());
     }
     // ---- evaluation buffers ----
@@ -353,7 +408,6 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     CUDA_TRY(cudaMemsetAsync(B.seg_w, 0, sizeof(double) * nseg, h.st));
     CUDA_TRY(cudaMemsetAsync(B.blk_rows, 0, sizeof(double) * n_brows * nblk, h.st));
     CUDA_TRY(cudaMemsetAsync(B.seg_frame, 0, sizeof(double) * 9 * nseg, h.st));
-    CUDA_TRY(cudaMemsetAsync(B.segN, 0, sizeof(double) * S.NE * nseg, h.st));
     CUDA_TRY(cudaMemsetAsync(B.seg_ssr, 0, sizeof(double) * nseg, h.st));
     if (S.n_views > 0) {
         CUDA_TRY(h.alloc(&B.blk_Hvv, (size_t)21 * nblk)); CUDA_TRY(h.alloc(&B.blk_gv, (size_t)6 * nblk));
@@ -395,6 +449,9 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     }
     CUDA_TRY(h.alloc(&h.V.x_cand, h.n_amb));
     CUDA_TRY(cudaStreamSynchronize(h.st));
+    lap("done");
+    if (trace) std::fprintf(stderr, "[calib_b200] create: arena %.1f MB reserved, %.1f MB used, %zu extra allocations\n",
+                            h.arena_size / 1048576.0, h.arena_used / 1048576.0, h.allocs.size());
     *out = hp.release();
     return CAL_OK;
 }

@@ -56,6 +56,19 @@ void launch_repack(const DevLayout& L, const double* sx, const double* sy, const
     k_repack<<<(unsigned)L.n_tiles, 128, 0, st>>>(L, sx, sy, su, sv, seg_src);
 }
 
+// bundle: robot poses b_se3_g, AoS [orig block][12] -> device-block-ordered SoA [12][n_blk]
+__global__ void k_btg_permute(DevLayout L, const double* __restrict__ src) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.n_blk * 12) return;
+    const int64_t b = i / 12; const int k = (int)(i % 12);
+    const int64_t o = L.blk_orig[b];
+    L.blk_bTg[(int64_t)k * L.n_blk + b] = o >= 0 ? src[o * 12 + k] : ((k % 4 == 0 && k < 9) ? 1.0 : 0.0);
+}
+void launch_btg_permute(const DevLayout& L, const double* src, cudaStream_t st) {
+    const int64_t n = L.n_blk * 12;
+    if (n > 0) k_btg_permute<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L, src);
+}
+
 // ---------------------------------------------------------------------------
 // per-evaluation setup
 // ---------------------------------------------------------------------------
