@@ -132,7 +132,8 @@ def run_b200(args, rank, world, local_rank):
         launches_timed = h.launch_count() - l0
         barrier()
         ms_c, ms_ck, _ = h.bench_pass(x0, reps=args.steps, jacobian=False)
-        h.bench_pass(x0, reps=max(args.steps, 20), jacobian=True)  # keeps the GPU busy long enough for >= 2 clock samples
+        # keep the same kernels running ~1.5 s more so the 200 ms clock sampler sees the GPU under this load
+        h.bench_pass(x0, reps=max(args.steps, int(1500.0 / max(ms_total / args.steps, 0.05))), jacobian=True)
     t = torch.tensor([ms_total, ms_k1], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

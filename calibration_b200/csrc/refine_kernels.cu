@@ -128,6 +128,60 @@ void launch_setup(const ProblemShape& S, const DevLayout& L, const EvalBuffers& 
 }
 
 // ---------------------------------------------------------------------------
+// TMA staging of a warp's tile: bulk asynchronous copies (cp.async.bulk, SASS UBLKCP) of
+// kChunk k-slices (kChunk x 1 KB, contiguous in the tile-transposed layout) into a per-warp
+// two-stage shared-memory ring, completion signalled on an mbarrier.  One elected lane
+// issues; all lanes then read their column with conflict-free 8-byte shared loads.
+// ---------------------------------------------------------------------------
+constexpr int kChunk = 8;                       // k-slices per stage (8 KB)
+constexpr int kStageDoubles = kChunk * 128;
+constexpr int kWarpStageBytes = 2 * kStageDoubles * 8 + 16;  // two stages + two mbarriers
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+struct TileStage {
+    double* buf;                // [2][kChunk][4][32]
+    unsigned long long* bar;    // [2]
+    const double* src;          // tile base in global memory
+    int depth, n_chunks;
+
+    __device__ __forceinline__ void init(unsigned char* warp_smem, const double* tile_src, int tile_depth, int lane) {
+        buf = reinterpret_cast<double*>(warp_smem);
+        bar = reinterpret_cast<unsigned long long*>(warp_smem + 2 * kStageDoubles * 8);
+        src = tile_src; depth = tile_depth; n_chunks = (tile_depth + kChunk - 1) / kChunk;
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    // issue chunk c into stage c & 1 (lane 0 only)
+    __device__ __forceinline__ void issue(int c, int lane) {
+        if (lane == 0 && c < n_chunks) {
+            const int ks = min(kChunk, depth - c * kChunk);
+            const unsigned bytes = (unsigned)ks * 1024u;
+            const unsigned mb = smem_u32(&bar[c & 1]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(buf + (c & 1) * kStageDoubles)), "l"(src + (int64_t)c * kStageDoubles), "r"(bytes), "r"(mb)
+                         : "memory");
+        }
+    }
+    // wait until chunk c has landed
+    __device__ __forceinline__ void wait(int c) {
+        const unsigned mb = smem_u32(&bar[c & 1]);
+        const unsigned parity = (unsigned)(c >> 1) & 1u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@!p bra WAIT_%=;\n\t}" ::"r"(mb), "r"(parity) : "memory");
+    }
+    __device__ __forceinline__ const double* row(int c, int kk, int lane) const { return buf + (c & 1) * kStageDoubles + kk * 128 + lane; }
+};
+
+// ---------------------------------------------------------------------------
 // K1: fused residual + Jacobian + J^T J
 // ---------------------------------------------------------------------------
 template <class LT, int NPASS, int PASS>
@@ -149,34 +203,35 @@ __device__ __forceinline__ void k1_accumulate(const double* __restrict__ Ju, con
 }
 
 template <int MODEL, int IMODE, int NPASS, int PASS>
-__device__ __forceinline__ void k1_body(const DevLayout& L, const EvalBuffers& B, int64_t tile, int lane) {
+__device__ __forceinline__ void k1_body(const DevLayout& L, const EvalBuffers& B, int64_t tile, int lane, unsigned char* warp_smem) {
     using LT = Local<MODEL, IMODE>;
     constexpr int NA = (LT::NE + NPASS - 1) / NPASS;
     const int64_t s = tile * 32 + lane;
     const int len = L.seg_len[s];
     const int depth = L.tile_depth[tile];
+    TileStage ts; ts.init(warp_smem, L.obs + L.tile_off[tile] * 128, depth, lane);
+    ts.issue(0, lane); ts.issue(1, lane);
     double A[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) A[i] = B.seg_frame[(int64_t)i * L.n_seg + s];
     const CamConst c = B.camc[L.seg_cam[s]];
-    const double* __restrict__ p = L.obs + L.tile_off[tile] * 128 + lane;
     double acc[NA];
 #pragma unroll
     for (int i = 0; i < NA; ++i) acc[i] = 0.0;
-    double X = 0, Y = 0, U = 0, V = 0;
-    if (depth > 0) { X = p[0]; Y = p[32]; U = p[64]; V = p[96]; }
-    for (int k = 0; k < depth; ++k) {
-        double Xn = 0, Yn = 0, Un = 0, Vn = 0;
-        if (k + 1 < depth) {  // software prefetch of the next 256 B rows
-            const double* q = p + (int64_t)(k + 1) * 128;
-            Xn = q[0]; Yn = q[32]; Un = q[64]; Vn = q[96];
+    for (int ch = 0; ch < ts.n_chunks; ++ch) {
+        ts.wait(ch);
+        const int k0 = ch * kChunk, kn = min(kChunk, depth - k0);
+        for (int kk = 0; kk < kn; ++kk) {
+            const double* q = ts.row(ch, kk, lane);
+            const double X = q[0], Y = q[32], U = q[64], V = q[96];
+            if (k0 + kk < len) {
+                double Ju[LT::NL], Jv[LT::NL];
+                obs_rows<MODEL, IMODE>(c, A, X, Y, U, V, Ju, Jv);
+                k1_accumulate<LT, NPASS, PASS>(Ju, Jv, acc);
+            }
         }
-        if (k < len) {
-            double Ju[LT::NL], Jv[LT::NL];
-            obs_rows<MODEL, IMODE>(c, A, X, Y, U, V, Ju, Jv);
-            k1_accumulate<LT, NPASS, PASS>(Ju, Jv, acc);
-        }
-        X = Xn; Y = Yn; U = Un; V = Vn;
+        __syncwarp();               // every lane is done with this stage
+        ts.issue(ch + 2, lane);     // refill it
     }
 #pragma unroll
     for (int e = 0; e < LT::NE; ++e)
@@ -190,9 +245,11 @@ __global__ void __launch_bounds__(128) k1_kernel(DevLayout L, EvalBuffers B) {
     if (tile >= L.n_tiles) return;
     const int lane = threadIdx.x & 31;
     const int pass = blockIdx.x % NPASS;
-    if (pass == 0) k1_body<MODEL, IMODE, NPASS, 0>(L, B, tile, lane);
-    if (NPASS > 1 && pass == 1) k1_body<MODEL, IMODE, NPASS, (NPASS > 1 ? 1 : 0)>(L, B, tile, lane);
-    if (NPASS > 2 && pass == 2) k1_body<MODEL, IMODE, NPASS, (NPASS > 2 ? 2 : 0)>(L, B, tile, lane);
+    extern __shared__ __align__(128) unsigned char k1_smem[];
+    unsigned char* warp_smem = k1_smem + (threadIdx.x >> 5) * kWarpStageBytes;
+    if (pass == 0) k1_body<MODEL, IMODE, NPASS, 0>(L, B, tile, lane, warp_smem);
+    if (NPASS > 1 && pass == 1) k1_body<MODEL, IMODE, NPASS, (NPASS > 1 ? 1 : 0)>(L, B, tile, lane, warp_smem);
+    if (NPASS > 2 && pass == 2) k1_body<MODEL, IMODE, NPASS, (NPASS > 2 ? 2 : 0)>(L, B, tile, lane, warp_smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -243,12 +300,17 @@ struct Split {
 __device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
-template <int MODEL, int IMODE>
+// U observations of the lane's segment travel per exchange stage: warp A runs their U
+// independent projection chains interleaved (the chain, not the FP64 issue rate, bounds a
+// producer that handles one observation at a time) and both warps pay one barrier per U.
+template <int MODEL, int IMODE, int U>
 __global__ void __launch_bounds__(256, 1) k1v2_kernel(DevLayout L, EvalBuffers B) {
     using LT = Local<MODEL, IMODE>;
     using SP = Split<LT>;
     constexpr int NX = SP::NX;
-    __shared__ double xbuf[4][2][NX][32];
+    extern __shared__ __align__(16) double xbuf_raw[];
+    typedef double (*XBuf)[2][U][NX][32];
+    XBuf xbuf = reinterpret_cast<XBuf>(xbuf_raw);  // [pair][stage][u][value][lane]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pair = warp & 3;
     const bool role_b = ((warp >> 2) ^ (warp & 1)) != 0;  // each SM sub-partition hosts one A and one B warp
@@ -257,6 +319,7 @@ __global__ void __launch_bounds__(256, 1) k1v2_kernel(DevLayout L, EvalBuffers B
     const int64_t s = tile * 32 + lane;
     const int len = L.seg_len[s];
     const int depth = L.tile_depth[tile];
+    const int n_steps = (depth + U - 1) / U;
     const int bar_full = 4 * pair, bar_empty = 4 * pair + 2;
     if (!role_b) {
         double A[9];
@@ -267,39 +330,53 @@ __global__ void __launch_bounds__(256, 1) k1v2_kernel(DevLayout L, EvalBuffers B
         double acc[SP::NA];
 #pragma unroll
         for (int i = 0; i < SP::NA; ++i) acc[i] = 0.0;
-        double X = 0, Y = 0, U = 0, V = 0;
-        if (depth > 0) { X = p[0]; Y = p[32]; U = p[64]; V = p[96]; }
-        for (int k = 0; k < depth; ++k) {
-            const int st = k & 1;
-            double Xn = 0, Yn = 0, Un = 0, Vn = 0;
-            if (k + 1 < depth) { const double* q = p + (int64_t)(k + 1) * 128; Xn = q[0]; Yn = q[32]; Un = q[64]; Vn = q[96]; }
-            double Ju[LT::NL], Jv[LT::NL];
-            const bool act = k < len;
-            if (act) obs_rows<MODEL, IMODE>(c, A, X, Y, U, V, Ju, Jv);
-            if (k >= 2) bar_sync64(bar_empty + st);  // B has drained this stage
-            if (act) {
-                static_for<0, LT::NL>([&](auto cc) {
-                    constexpr int col = decltype(cc)::value;
-                    if constexpr (!SP::is_lin(col)) {
-                        xbuf[pair][st][2 * SP::xcol(col)][lane] = Ju[col];
-                        xbuf[pair][st][2 * SP::xcol(col) + 1][lane] = Jv[col];
-                    }
-                });
-            }
-            bar_arrive64(bar_full + st);
-            if (act) {
-                static_for<0, LT::NL>([&](auto ca) {
-                    static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
-                        constexpr int a = decltype(ca)::value, b = decltype(cb)::value;
-                        if constexpr (SP::in_a(a, b)) {
-                            constexpr int sl = SP::slot(a, b);
-                            if constexpr (LT::has_u(a) && LT::has_u(b)) acc[sl] = fma(Ju[a], Ju[b], acc[sl]);
-                            if constexpr (LT::has_v(a) && LT::has_v(b)) acc[sl] = fma(Jv[a], Jv[b], acc[sl]);
+        double ob[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ob[u][q] = (u < depth) ? p[(int64_t)u * 128 + 32 * q] : 0.0;
+        for (int t = 0; t < n_steps; ++t) {
+            const int st = t & 1, k0 = t * U;
+            double nx[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) nx[u][q] = (k0 + U + u < depth) ? p[(int64_t)(k0 + U + u) * 128 + 32 * q] : 0.0;
+            double Ju[U][LT::NL], Jv[U][LT::NL];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (k0 + u < len) obs_rows<MODEL, IMODE>(c, A, ob[u][0], ob[u][1], ob[u][2], ob[u][3], Ju[u], Jv[u]);
+            if (t >= 2) bar_sync64(bar_empty + st);  // B has drained this stage
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (k0 + u < len) {
+                    static_for<0, LT::NL>([&](auto cc) {
+                        constexpr int col = decltype(cc)::value;
+                        if constexpr (!SP::is_lin(col)) {
+                            xbuf[pair][st][u][2 * SP::xcol(col)][lane] = Ju[u][col];
+                            xbuf[pair][st][u][2 * SP::xcol(col) + 1][lane] = Jv[u][col];
                         }
                     });
-                });
-            }
-            X = Xn; Y = Yn; U = Un; V = Vn;
+                }
+            bar_arrive64(bar_full + st);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (k0 + u < len) {
+                    static_for<0, LT::NL>([&](auto ca) {
+                        static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
+                            constexpr int a = decltype(ca)::value, b = decltype(cb)::value;
+                            if constexpr (SP::in_a(a, b)) {
+                                constexpr int sl = SP::slot(a, b);
+                                if constexpr (LT::has_u(a) && LT::has_u(b)) acc[sl] = fma(Ju[u][a], Ju[u][b], acc[sl]);
+                                if constexpr (LT::has_v(a) && LT::has_v(b)) acc[sl] = fma(Jv[u][a], Jv[u][b], acc[sl]);
+                            }
+                        });
+                    });
+                }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ob[u][q] = nx[u][q];
         }
         static_for<0, LT::NL>([&](auto ca) {
             static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
@@ -311,32 +388,35 @@ __global__ void __launch_bounds__(256, 1) k1v2_kernel(DevLayout L, EvalBuffers B
         double acc[SP::NB];
 #pragma unroll
         for (int i = 0; i < SP::NB; ++i) acc[i] = 0.0;
-        for (int k = 0; k < depth; ++k) {
-            const int st = k & 1;
-            const bool act = k < len;
+        for (int t = 0; t < n_steps; ++t) {
+            const int st = t & 1, k0 = t * U;
             bar_sync64(bar_full + st);
-            double Ju[LT::NL], Jv[LT::NL];
-            if (act) {
-                static_for<0, LT::NL>([&](auto cc) {
-                    constexpr int col = decltype(cc)::value;
-                    if constexpr (!SP::is_lin(col)) {
-                        Ju[col] = xbuf[pair][st][2 * SP::xcol(col)][lane];
-                        Jv[col] = xbuf[pair][st][2 * SP::xcol(col) + 1][lane];
-                    }
-                });
-            }
-            if (k + 2 < depth) bar_arrive64(bar_empty + st);
-            if (act) {
-                static_for<0, LT::NL>([&](auto ca) {
-                    static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
-                        constexpr int a = decltype(ca)::value, b = decltype(cb)::value;
-                        if constexpr (!SP::in_a(a, b)) {
-                            constexpr int sl = SP::slot(a, b);
-                            if constexpr (LT::has_u(a) && LT::has_u(b)) acc[sl] = fma(Ju[a], Ju[b], acc[sl]);
-                            if constexpr (LT::has_v(a) && LT::has_v(b)) acc[sl] = fma(Jv[a], Jv[b], acc[sl]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool act = k0 + u < len;
+                double Ju[LT::NL], Jv[LT::NL];
+                if (act) {
+                    static_for<0, LT::NL>([&](auto cc) {
+                        constexpr int col = decltype(cc)::value;
+                        if constexpr (!SP::is_lin(col)) {
+                            Ju[col] = xbuf[pair][st][u][2 * SP::xcol(col)][lane];
+                            Jv[col] = xbuf[pair][st][u][2 * SP::xcol(col) + 1][lane];
                         }
                     });
-                });
+                }
+                if (u == U - 1 && t + 2 < n_steps) bar_arrive64(bar_empty + st);
+                if (act) {
+                    static_for<0, LT::NL>([&](auto ca) {
+                        static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
+                            constexpr int a = decltype(ca)::value, b = decltype(cb)::value;
+                            if constexpr (!SP::in_a(a, b)) {
+                                constexpr int sl = SP::slot(a, b);
+                                if constexpr (LT::has_u(a) && LT::has_u(b)) acc[sl] = fma(Ju[a], Ju[b], acc[sl]);
+                                if constexpr (LT::has_v(a) && LT::has_v(b)) acc[sl] = fma(Jv[a], Jv[b], acc[sl]);
+                            }
+                        });
+                    });
+                }
             }
         }
         static_for<0, LT::NL>([&](auto ca) {
@@ -346,6 +426,15 @@ __global__ void __launch_bounds__(256, 1) k1v2_kernel(DevLayout L, EvalBuffers B
             });
         });
     }
+}
+
+template <int IMODE, int U>
+static void launch_k1v2_t(const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
+    using SP = Split<Local<0, IMODE>>;
+    const size_t smem = sizeof(double) * 4 * 2 * U * SP::NX * 32;
+    static bool once = false;
+    if (!once) { cudaFuncSetAttribute(k1v2_kernel<0, IMODE, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once = true; }
+    k1v2_kernel<0, IMODE, U><<<(unsigned)((L.n_tiles + 3) / 4), 256, smem, st>>>(L, B);
 }
 
 template <int MODEL, int IMODE>
@@ -362,7 +451,10 @@ template <int MODEL, int IMODE>
 static void launch_k1_t(const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
     constexpr int NP = passes_for<MODEL, IMODE>();
     const unsigned grid = (unsigned)((L.n_tiles + 3) / 4) * NP;
-    k1_kernel<MODEL, IMODE, NP><<<grid, 128, 0, st>>>(L, B);
+    constexpr int smem = 4 * kWarpStageBytes;
+    static bool once = false;
+    if (!once) { cudaFuncSetAttribute(k1_kernel<MODEL, IMODE, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); once = true; }
+    k1_kernel<MODEL, IMODE, NP><<<grid, 128, smem, st>>>(L, B);
 }
 #define CALK_DISPATCH(FN, ...)                                                             \
     do {                                                                                   \
@@ -374,8 +466,8 @@ static void launch_k1_t(const DevLayout& L, const EvalBuffers& B, cudaStream_t s
         else FN<1, 2>(__VA_ARGS__);                                                        \
     } while (0)
 
-static int k1_variant() {  // CALIB_B200_K1=v1 forces the multi-pass kernel (A/B comparison while profiling)
-    static const int v = [] { const char* e = getenv("CALIB_B200_K1"); return (e && e[0] == 'v' && e[1] == '1') ? 1 : 2; }();
+static int k1_variant() {  // CALIB_B200_K1=v2 selects the experimental warp-pair kernel (A/B comparison while profiling)
+    static const int v = [] { const char* e = getenv("CALIB_B200_K1"); return (e && e[0] == 'v' && e[1] == '2') ? 2 : 1; }();
     return v;
 }
 bool k1_uses_pairs(const ProblemShape& S) { return S.model == 0 && S.imode != 0 && k1_variant() == 2; }
@@ -383,9 +475,9 @@ bool k1_uses_pairs(const ProblemShape& S) { return S.model == 0 && S.imode != 0 
 void launch_k1(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
     if (L.n_tiles == 0) return;
     if (k1_uses_pairs(S)) {
-        const unsigned grid = (unsigned)((L.n_tiles + 3) / 4);
-        if (S.imode == 1) k1v2_kernel<0, 1><<<grid, 256, 0, st>>>(L, B);
-        else k1v2_kernel<0, 2><<<grid, 256, 0, st>>>(L, B);
+        static const int U = [] { const char* e = getenv("CALIB_B200_K1_U"); return e ? atoi(e) : 1; }();
+        if (S.imode == 1) { if (U == 1) launch_k1v2_t<1, 1>(L, B, st); else if (U == 3) launch_k1v2_t<1, 3>(L, B, st); else launch_k1v2_t<1, 2>(L, B, st); }
+        else { if (U == 1) launch_k1v2_t<2, 1>(L, B, st); else launch_k1v2_t<2, 2>(L, B, st); }
         return;
     }
     CALK_DISPATCH(launch_k1_t, L, B, st);
@@ -397,28 +489,43 @@ __global__ void __launch_bounds__(128) k_cost(DevLayout L, EvalBuffers B) {
     const int64_t tile = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (tile >= L.n_tiles) return;
     const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(128) unsigned char k1_smem[];
     const int64_t s = tile * 32 + lane;
     const int len = L.seg_len[s];
     const int depth = L.tile_depth[tile];
+    TileStage ts; ts.init(k1_smem + (threadIdx.x >> 5) * kWarpStageBytes, L.obs + L.tile_off[tile] * 128, depth, lane);
+    ts.issue(0, lane); ts.issue(1, lane);
     double A[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) A[i] = B.seg_frame[(int64_t)i * L.n_seg + s];
     const CamConst c = B.camc[L.seg_cam[s]];
-    const double* __restrict__ p = L.obs + L.tile_off[tile] * 128 + lane;
     double acc = 0.0;
+    for (int ch = 0; ch < ts.n_chunks; ++ch) {
+        ts.wait(ch);
+        const int k0 = ch * kChunk, kn = min(kChunk, depth - k0);
 #pragma unroll 4
-    for (int k = 0; k < depth; ++k) {
-        const double* q = p + (int64_t)k * 128;
-        const double X = q[0], Y = q[32], U = q[64], V = q[96];
-        if (k < len) acc += obs_ssr<MODEL>(c, A, X, Y, U, V);
+        for (int kk = 0; kk < kn; ++kk) {
+            const double* q = ts.row(ch, kk, lane);
+            const double X = q[0], Y = q[32], U = q[64], V = q[96];
+            if (k0 + kk < len) acc += obs_ssr<MODEL>(c, A, X, Y, U, V);
+        }
+        __syncwarp();
+        ts.issue(ch + 2, lane);
     }
     B.seg_ssr[s] = acc;
 }
 void launch_cost(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
     if (L.n_tiles == 0) return;
     const unsigned g = (unsigned)((L.n_tiles + 3) / 4);
-    if (S.model == 0) k_cost<0><<<g, 128, 0, st>>>(L, B);
-    else k_cost<1><<<g, 128, 0, st>>>(L, B);
+    constexpr int smem = 4 * kWarpStageBytes;
+    static bool once = false;
+    if (!once) {
+        cudaFuncSetAttribute(k_cost<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(k_cost<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        once = true;
+    }
+    if (S.model == 0) k_cost<0><<<g, 128, smem, st>>>(L, B);
+    else k_cost<1><<<g, 128, smem, st>>>(L, B);
 }
 
 // ---------------------------------------------------------------------------
