@@ -79,11 +79,8 @@ class ClockSampler:
 
 
 def shard_chunks(n_poses, rank, world):
-    n_chunks = (n_poses + CHUNK - 1) // CHUNK
-    if n_chunks % world != 0:
-        raise SystemExit(f"workload has {n_chunks} chunks, not divisible by {world} ranks")
-    per = n_chunks // world
-    return list(range(rank * per, (rank + 1) * per))
+    from calibration_b200 import sharding
+    return sharding.chunk_shard(n_poses, CHUNK, rank, world)
 
 
 def run_b200(args, rank, world, local_rank):
