@@ -276,8 +276,9 @@ def main():
     ap.add_argument("--fixed-intrinsics", action="store_true", help="BundleOptions default (optimize_intrinsics=false)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-div", type=int, default=64)
-    ap.add_argument("--k1-flop-per-obs", type=float, default=672.0,
-                    help="FP64 flop per observation of K1 from the committed ncu capture (profiles/r1_k1_ncu_full_35M.csv)")
+    ap.add_argument("--k1-flop-per-obs", type=float, default=560.0,
+                    help="FP64 flop per observation of K1 from the committed ncu capture (profiles/r1_k1_fused_ncu_full_35M.csv: "
+                         "237 DFMA + 44 DMUL + 42 DADD per observation, epilogue included)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

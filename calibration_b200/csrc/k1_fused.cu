@@ -1,0 +1,531 @@
+// K1: fused project -> residual -> analytic Jacobian -> J^T J accumulation -> per-block
+// Huber weight and chain rule -> per-tile sums, in one kernel (sm_100a, FP64).
+//
+// Replaces, per Levenberg-Marquardt iteration, what the reference does with
+// ceres::AutoDiffCostFunction over src/estimation/residuals/{intrinsicresidual,
+// extrinsicsresidual,bundleresidual}.h plus Ceres' loss correction and normal-equation
+// formation (reached through solve_problem, src/estimation/detail/ceresutils.h:27-43).
+//
+// Work decomposition.  One lane owns one segment (in the fused mode: one residual block)
+// and keeps the upper triangle of [J | r]^T [J | r] of that segment in registers.  The
+// NE = 28 ... 190 entries do not fit one thread, so NROLE = 1 ... 3 warps ("roles") of the
+// same CTA work on the same tile of 32 segments and each accumulates its own subset of the
+// entries (K1Roles below).  The subsets are chosen so that every product the per-block
+// epilogue needs is role-local: role 0 holds the twist-twist and twist-residual entries,
+// and all six entries that couple the twist with one intrinsic column always sit in one role.
+//
+// Fused epilogue (one block per lane).  s_b = |r_b|^2 gives the Huber weight of the
+// residual BLOCK (rho is applied to the whole block, so it is only known after
+// the block's last corner); the role then forms w_b N_b for its entries, applies the 6x6
+// chain rule T_b of the view-type pose (k1_math.cuh) from registers, and reduces over the
+// 32 blocks of the tile through a padded shared-memory transpose in a fixed order (no
+// floating-point atomics: results are run-to-run identical).  Per tile one row of NVT
+// values is written; k_tile_colsum / k_tile_final add the rows per camera.  For the
+// kinds with per-view unknowns the per-block products (H_vv, g_v, E_vc, E_vi) are written
+// per block for the Schur kernels instead of being reduced.
+//
+// Without the fused epilogue (small problems, whose blocks are cut into several segments
+// to fill the machine) the roles store their entries to segN and the assembly kernels of
+// refine_kernels.cu take over.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <type_traits>
+#include <vector>
+
+#include "refine_kernels.cuh"
+#include "tile_stage.cuh"
+
+namespace calk {
+
+template <int I, int N, class F>
+__host__ __device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
+}
+
+// ---------------------------------------------------------------------------
+// entry -> (role, slot) tables
+// ---------------------------------------------------------------------------
+template <int MODEL, int IMODE>
+struct K1Roles {
+    using LT = Local<MODEL, IMODE>;
+    static constexpr int NE = LT::NE, NL = LT::NL, NC = LT::NC, PI = LT::PI;
+    static constexpr int NROLE = NE <= 72 ? 1 : (NE <= 144 ? 2 : 3);
+    static constexpr int RR = LT::idx(NC, NC);              // |r|^2: accumulated by every role, owned by none
+    struct Tbl {
+        int role[NE];
+        int slot[NE];
+        int count[3];
+        int col_role[PI > 0 ? PI : 1];  // role that owns the twist x intrinsic-column-j entries
+    };
+    static constexpr Tbl make() {
+        Tbl t{};
+        for (int e = 0; e < NE; ++e) { t.role[e] = -1; t.slot[e] = -1; }
+        for (int r = 0; r < 3; ++r) t.count[r] = 0;
+        const int cap = (NE - 1 + NROLE - 1) / NROLE;
+        // twist-twist and twist-residual: role 0
+        for (int a = 0; a < 6; ++a) {
+            for (int b = a; b < 6; ++b) { const int e = LT::idx(a, b); t.role[e] = 0; t.slot[e] = t.count[0]++; }
+            const int e = LT::idx(a, NC); t.role[e] = 0; t.slot[e] = t.count[0]++;
+        }
+        // twist x intrinsic column j: six entries, never split over roles
+        for (int j = 0; j < PI; ++j) {
+            int r = -1;
+            for (int k = 0; k < NROLE; ++k) if (r < 0 && t.count[k] + 6 <= cap) r = k;
+            if (r < 0) { r = 0; for (int k = 1; k < NROLE; ++k) if (t.count[k] < t.count[r]) r = k; }
+            t.col_role[j] = r;
+            for (int a = 0; a < 6; ++a) { const int e = LT::idx(a, 6 + j); t.role[e] = r; t.slot[e] = t.count[r]++; }
+        }
+        // everything else fills the roles up
+        for (int a = 6; a < NL; ++a)
+            for (int b = a; b < NL; ++b) {
+                const int e = LT::idx(a, b);
+                if (e == RR) continue;
+                int r = -1;
+                for (int k = 0; k < NROLE; ++k) if (r < 0 && t.count[k] < cap) r = k;
+                if (r < 0) { r = 0; for (int k = 1; k < NROLE; ++k) if (t.count[k] < t.count[r]) r = k; }
+                t.role[e] = r; t.slot[e] = t.count[r]++;
+            }
+        return t;
+    }
+    static constexpr Tbl tbl = make();
+    static constexpr int count(int r) { return tbl.count[r]; }
+    static constexpr int n_owned_cols(int r) { int n = 0; for (int j = 0; j < PI; ++j) if (tbl.col_role[j] == r) ++n; return n; }
+    static constexpr int col_rank(int j) { int n = 0; for (int k = 0; k < j; ++k) if (tbl.col_role[k] == tbl.col_role[j]) ++n; return n; }
+    static constexpr bool owns_cols(int r) { for (int j = 0; j < PI; ++j) if (tbl.col_role[j] == r) return true; return false; }
+
+    // ---- order in which a role emits its per-tile values (device epilogue and host map agree on it) ----
+    // cam part: the role's entries by slot; role 0 then rr and the cost; bundle view rows:
+    // the role's E_vi columns (i major within a column), role 0 then g_v, H_vv, Q.
+    static constexpr int n_vals(int r, bool view_rows) {
+        int n = tbl.count[r] + (r == 0 ? 2 : 0);
+        if (view_rows) {
+            for (int j = 0; j < PI; ++j) if (tbl.col_role[j] == r) n += 6;
+            if (r == 0) n += 6 + 21 + 36;
+        }
+        return n;
+    }
+    static constexpr int val_off(int r, bool view_rows) { int o = 0; for (int k = 0; k < r; ++k) o += n_vals(k, view_rows); return o; }
+    static constexpr int nvt(bool view_rows) { return val_off(NROLE, view_rows); }
+    // per-camera value index (cam_sums layout of refine_host.cu): [0, NE) local system | NE cost |
+    // NE+1.. H_vv(21) g_v(6) Q(36) E_vi(6 PI)
+    static void value_map(bool view_rows, std::vector<int32_t>& map) {
+        map.assign(nvt(view_rows), -1);
+        for (int r = 0; r < NROLE; ++r) {
+            int o = val_off(r, view_rows);
+            for (int sl = 0; sl < tbl.count[r]; ++sl)
+                for (int e = 0; e < NE; ++e) if (tbl.role[e] == r && tbl.slot[e] == sl) map[o++] = e;
+            if (r == 0) { map[o++] = RR; map[o++] = NE; }
+            if (view_rows) {
+                for (int j = 0; j < PI; ++j) if (tbl.col_role[j] == r) for (int i = 0; i < 6; ++i) map[o++] = NE + 64 + PI * i + j;
+                if (r == 0) {
+                    for (int i = 0; i < 6; ++i) map[o++] = NE + 22 + i;
+                    for (int i = 0; i < 21; ++i) map[o++] = NE + 1 + i;
+                    for (int i = 0; i < 36; ++i) map[o++] = NE + 28 + i;
+                }
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// streaming column sums over the 32 lanes of a warp through a padded [32][33] shared tile
+// ---------------------------------------------------------------------------
+struct LaneSum {
+    double* scratch;  // per warp, 32 * 33 doubles
+    double* out;      // global: this role's values of this tile
+    int lane;
+    // values [END - N, END) are complete in the tile: lane j adds the 32 lanes of value END - N + j
+    // in a fixed order (four interleaved partial sums, then a fixed tree)
+    template <int END, int N>
+    __device__ __forceinline__ void flush() {
+        __syncwarp();
+        if (lane < N) {
+            const double* row = scratch + lane * 33;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) { a0 += row[k]; a1 += row[k + 1]; a2 += row[k + 2]; a3 += row[k + 3]; }
+            out[END - N + lane] = (a0 + a1) + (a2 + a3);
+        }
+        __syncwarp();
+    }
+    template <int K>
+    __device__ __forceinline__ void push(double v) {
+        scratch[(K & 31) * 33 + lane] = v;
+        if constexpr ((K & 31) == 31) flush<K + 1, 32>();
+    }
+    template <int TOTAL>
+    __device__ __forceinline__ void finish() { if constexpr ((TOTAL & 31) != 0) flush<TOTAL, (TOTAL & 31)>(); }
+};
+
+struct K1Args {
+    DevLayout L;
+    EvalBuffers B;
+    double huber_delta;
+    int nvt;         // values per tile
+};
+
+// VIEW: what happens to the products with the view-type pose block (chain rule T_b):
+//   0 none (its pose is constant), 1 reduced per tile (bundle: one target pose for all blocks),
+//   2 stored per block (intrinsics / extrinsics: per-view unknowns, consumed by the Schur kernels)
+enum { VIEW_NONE = 0, VIEW_REDUCE = 1, VIEW_STORE = 2, NOT_FUSED = 3 };
+
+// CTA-shared staging of the tile's observation rows: thread 0 issues bulk asynchronous copies
+// (cp.async.bulk, SASS UBLKCP) of RC rows (RC x 1 KB, contiguous in the tile-transposed layout)
+// into a two-stage ring; completion is signalled on an mbarrier every thread waits on.  A stage
+// is refilled after the CTA barrier that ends its last step (all reads of a step precede it).
+template <int RC>
+struct CtaStage {
+    double* buf;              // [2][RC][4][32]
+    unsigned long long* bar;  // [2]
+    const double* src;
+    int depth, n_chunks;
+    static constexpr int kStage = RC * 128;
+    static constexpr int kBytes = 2 * kStage * 8 + 16;
+    __device__ __forceinline__ void init(unsigned char* smem, const double* tile_src, int tile_depth, bool leader, int n_threads) {
+        buf = reinterpret_cast<double*>(smem);
+        bar = reinterpret_cast<unsigned long long*>(smem + 2 * kStage * 8);
+        src = tile_src; depth = tile_depth; n_chunks = (tile_depth + RC - 1) / RC;
+        if (leader) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        if (n_threads > 32) asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory"); else __syncwarp();
+    }
+    __device__ __forceinline__ void issue(int c, bool leader) {
+        if (leader && c < n_chunks) {
+            const int ks = min(RC, depth - c * RC);
+            const unsigned bytes = (unsigned)ks * 1024u;
+            const unsigned mb = smem_u32(&bar[c & 1]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(buf + (c & 1) * kStage)), "l"(src + (int64_t)c * kStage), "r"(bytes), "r"(mb)
+                         : "memory");
+        }
+    }
+    __device__ __forceinline__ void wait(int c) {
+        const unsigned mb = smem_u32(&bar[c & 1]);
+        const unsigned parity = (unsigned)(c >> 1) & 1u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@!p bra WAIT_%=;\n\t}" ::"r"(mb), "r"(parity) : "memory");
+    }
+    __device__ __forceinline__ const double* row(int c, int kk, int lane) const { return buf + (c & 1) * kStage + kk * 128 + lane; }
+};
+
+// Values of one observation's Jacobian rows that travel between the roles of a tile: every
+// structurally non-zero entry except the constant 1 of the principal-point columns.
+template <int MODEL, int IMODE>
+struct K1Xchg {
+    using LT = Local<MODEL, IMODE>;
+    static constexpr bool is_one(int c) { return LT::PI > 0 && (c - 6 == LT::c_cx || c - 6 == LT::c_cy); }
+    static constexpr bool send_u(int c) { return LT::has_u(c) && !is_one(c); }
+    static constexpr bool send_v(int c) { return LT::has_v(c) && !is_one(c); }
+    static constexpr int pos_u(int c) { int n = 0; for (int i = 0; i < c; ++i) n += (send_u(i) ? 1 : 0) + (send_v(i) ? 1 : 0); return n; }
+    static constexpr int pos_v(int c) { return pos_u(c) + (send_u(c) ? 1 : 0); }
+    static constexpr int NX = pos_u(LT::NL);
+};
+
+template <int MODEL, int IMODE, int ROLE>
+__device__ __forceinline__ void k1_accumulate(const double* __restrict__ Ju, const double* __restrict__ Jv, double* __restrict__ acc,
+                                              double& ssr) {
+    using LT = Local<MODEL, IMODE>;
+    using RT = K1Roles<MODEL, IMODE>;
+    ssr = fma(Ju[LT::NC], Ju[LT::NC], ssr); ssr = fma(Jv[LT::NC], Jv[LT::NC], ssr);
+    static_for<0, LT::NL>([&](auto ca) {
+        static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
+            constexpr int a = decltype(ca)::value, b = decltype(cb)::value;
+            constexpr int e = LT::idx(a, b);
+            if constexpr (RT::tbl.role[e] == ROLE) {
+                constexpr int sl = RT::tbl.slot[e];
+                if constexpr (LT::has_u(a) && LT::has_u(b)) acc[sl] = fma(Ju[a], Ju[b], acc[sl]);
+                if constexpr (LT::has_v(a) && LT::has_v(b)) acc[sl] = fma(Jv[a], Jv[b], acc[sl]);
+            }
+        });
+    });
+}
+
+// Shared memory of one CTA (= one tile, NROLE warps):  [ stage ring | exchange slots ]
+template <int MODEL, int IMODE>
+struct K1Smem {
+    using RT = K1Roles<MODEL, IMODE>;
+    static constexpr int NROLE = RT::NROLE;
+    static constexpr int RC = NROLE == 3 ? 9 : 8;                 // rows per stage: a multiple of NROLE
+    static constexpr int kStageBytes = (CtaStage<RC>::kBytes + 127) / 128 * 128;
+    static constexpr int NX = K1Xchg<MODEL, IMODE>::NX;
+    static constexpr int kXchgBytes = NROLE > 1 ? 2 * NROLE * NX * 32 * 8 : 0;   // [stage][role][value][lane]
+    static constexpr int kScratch = 32 * 33 * 8;                  // epilogue transpose tile, per warp
+    static constexpr int kBytes = kStageBytes + (kXchgBytes > NROLE * kScratch ? kXchgBytes : NROLE * kScratch);
+};
+
+template <int MODEL, int IMODE, int ROLE, int VIEW>
+__device__ __forceinline__ void k1_role(const K1Args& P, int64_t tile, int lane, unsigned char* smem) {
+    using LT = Local<MODEL, IMODE>;
+    using RT = K1Roles<MODEL, IMODE>;
+    using XT = K1Xchg<MODEL, IMODE>;
+    using SM = K1Smem<MODEL, IMODE>;
+    constexpr int NROLE = RT::NROLE, RC = SM::RC, NX = XT::NX;
+    constexpr int NA = RT::count(ROLE);
+    constexpr int NL = LT::NL, NC = LT::NC, PI = LT::PI;
+    const DevLayout& L = P.L; const EvalBuffers& B = P.B;
+    const int64_t s = tile * 32 + lane;
+    const int len = L.seg_len[s];
+    const int depth = L.tile_depth[tile];
+    const bool leader = ROLE == 0 && lane == 0;
+    CtaStage<RC> ts; ts.init(smem, L.obs + L.tile_off[tile] * 128, depth, leader, NROLE * 32);
+    ts.issue(0, leader); ts.issue(1, leader);
+    double* xbuf = reinterpret_cast<double*>(smem + SM::kStageBytes);   // [2][NROLE][NX][32]
+    double A[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) A[i] = B.seg_frame[(int64_t)i * L.n_seg + s];
+    const CamConst c = B.camc[L.seg_cam[s]];
+    double acc[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) acc[i] = 0.0;
+    double ssr = 0.0;
+    int step = 0;
+    for (int ch = 0; ch < ts.n_chunks; ++ch) {
+        ts.wait(ch);
+        const int k0 = ch * RC, kn = min(RC, depth - k0);
+        for (int kk = 0; kk < kn; kk += NROLE, ++step) {
+            // each role projects one of the NROLE corners of this step ...
+            const int kmine = kk + ROLE;
+            const bool mine = k0 + kmine < len;
+            double Ju[NL], Jv[NL];
+            if (mine) {
+                const double* q = ts.row(ch, kmine, lane);
+                obs_rows<MODEL, IMODE>(c, A, q[0], q[32], q[64], q[96], Ju, Jv);
+            }
+            if constexpr (NROLE > 1) {
+                // ... hands the rows to the other roles through shared memory ...
+                double* xs = xbuf + ((step & 1) * NROLE + ROLE) * NX * 32 + lane;
+                if (mine) {
+                    static_for<0, NL>([&](auto cc) {
+                        constexpr int col = decltype(cc)::value;
+                        if constexpr (XT::send_u(col)) xs[XT::pos_u(col) * 32] = Ju[col];
+                        if constexpr (XT::send_v(col)) xs[XT::pos_v(col) * 32] = Jv[col];
+                    });
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(NROLE * 32) : "memory");
+            }
+            // ... and accumulates ITS entries of the local system for all NROLE corners
+            if (mine) k1_accumulate<MODEL, IMODE, ROLE>(Ju, Jv, acc, ssr);
+            if constexpr (NROLE > 1) {
+                static_for<1, NROLE>([&](auto cp) {
+                    constexpr int other = (ROLE + decltype(cp)::value) % NROLE;
+                    if (k0 + kk + other < len) {
+                        const double* xo = xbuf + ((step & 1) * NROLE + other) * NX * 32 + lane;
+                        double Pu[NL], Pv[NL];
+                        static_for<0, NL>([&](auto cc) {
+                            constexpr int col = decltype(cc)::value;
+                            Pu[col] = XT::send_u(col) ? xo[XT::pos_u(col) * 32] : (LT::has_u(col) ? 1.0 : 0.0);
+                            Pv[col] = XT::send_v(col) ? xo[XT::pos_v(col) * 32] : (LT::has_v(col) ? 1.0 : 0.0);
+                        });
+                        k1_accumulate<MODEL, IMODE, ROLE>(Pu, Pv, acc, ssr);
+                    }
+                });
+            }
+        }
+        if constexpr (NROLE == 1) __syncwarp();  // every lane is done with this stage (NROLE > 1: the step barrier)
+        ts.issue(ch + 2, leader);                // refill it
+    }
+    unsigned char* warp_smem = smem;             // NROLE == 1: the transpose tile aliases the idle staging ring
+    if constexpr (NROLE > 1) {
+        asm volatile("bar.sync 1, %0;" ::"n"(NROLE * 32) : "memory");  // the exchange slots are dead: they become the transpose tiles
+        warp_smem = smem + SM::kStageBytes + ROLE * SM::kScratch;
+    }
+    if constexpr (VIEW == NOT_FUSED) {
+        static_for<0, LT::NE>([&](auto ce) {
+            constexpr int e = decltype(ce)::value;
+            if constexpr (RT::tbl.role[e] == ROLE) { constexpr int sl = RT::tbl.slot[e]; B.segN[(int64_t)e * L.n_seg + s] = acc[sl]; }
+        });
+        if (ROLE == 0) B.segN[(int64_t)RT::RR * L.n_seg + s] = ssr;
+    } else {
+        // ---------------- fused epilogue: lane = residual block (s == device block id) ----------------
+        constexpr bool RED = VIEW == VIEW_REDUCE;
+        constexpr int K_RR = NA;                                    // role 0: rr, cost
+        constexpr int K_EVI = NA + (ROLE == 0 ? 2 : 0);             // owned E_vi columns, 6 values each
+        constexpr int K_GV = K_EVI + 6 * RT::n_owned_cols(ROLE);    // role 0: g_v(6) H_vv(21) Q(36)
+        constexpr int TOTAL = RT::n_vals(ROLE, RED);
+        double rho, w; huber_weight(P.huber_delta, ssr, rho, w);
+        LaneSum ls{reinterpret_cast<double*>(warp_smem), B.tile_vals + tile * P.nvt + RT::val_off(ROLE, RED), lane};
+        static_for<0, NA>([&](auto ci) { constexpr int i = decltype(ci)::value; ls.template push<i>(w * acc[i]); });
+        if constexpr (ROLE == 0) {
+            ls.template push<K_RR>(w * ssr); ls.template push<K_RR + 1>(0.5 * rho);
+            B.blk_ssr[s] = ssr;
+        }
+        if constexpr (VIEW != VIEW_NONE && (ROLE == 0 || RT::owns_cols(ROLE))) {
+            const int64_t nb = L.n_blk;
+            const bool vfree = RED ? true : (L.blk_vfree[s] != 0);
+            double T[36];
+#pragma unroll
+            for (int i = 0; i < 36; ++i) T[i] = B.blk_Tv[(int64_t)i * nb + s];
+            // E_vi columns of this role: w T^T N_xi,i[:, j]
+            static_for<0, PI>([&](auto cj) {
+                constexpr int j = decltype(cj)::value;
+                if constexpr (RT::tbl.col_role[j] == ROLE) {
+                    static_for<0, 6>([&](auto ci) {
+                        constexpr int i = decltype(ci)::value;
+                        double a = 0.0;
+                        static_for<0, 6>([&](auto ck) {
+                            constexpr int k = decltype(ck)::value;
+                            constexpr int sl = RT::tbl.slot[LT::idx(k, 6 + j)];
+                            a = fma(T[6 * k + i], acc[sl], a);
+                        });
+                        a *= w;
+                        if constexpr (RED) ls.template push<K_EVI + 6 * RT::col_rank(j) + i>(a);
+                        else if (vfree) B.blk_Evi[(int64_t)(PI * i + j) * nb + s] = a;
+                    });
+                }
+            });
+            if constexpr (ROLE == 0) {
+                static_for<0, 6>([&](auto ci) {
+                    constexpr int i = decltype(ci)::value;
+                    double a = 0.0;
+                    static_for<0, 6>([&](auto ck) {
+                        constexpr int k = decltype(ck)::value;
+                        constexpr int sl = RT::tbl.slot[LT::idx(k, NC)];
+                        a = fma(T[6 * k + i], acc[sl], a);
+                    });
+                    a *= w;
+                    if constexpr (RED) ls.template push<K_GV + i>(a);
+                    else if (vfree) B.blk_gv[(int64_t)i * nb + s] = a;
+                });
+                double Q[36];  // w T^T N_xixi
+                static_for<0, 6>([&](auto ci) {
+                    static_for<0, 6>([&](auto cjj) {
+                        constexpr int i = decltype(ci)::value, j = decltype(cjj)::value;
+                        double a = 0.0;
+                        static_for<0, 6>([&](auto ck) {
+                            constexpr int k = decltype(ck)::value;
+                            constexpr int sl = RT::tbl.slot[k <= j ? LT::idx(k, j) : LT::idx(j, k)];
+                            a = fma(T[6 * k + i], acc[sl], a);
+                        });
+                        Q[6 * i + j] = a * w;
+                    });
+                });
+                static_for<0, 6>([&](auto ci) {
+                    static_for<decltype(ci)::value, 6>([&](auto cjj) {
+                        constexpr int i = decltype(ci)::value, j = decltype(cjj)::value;
+                        constexpr int o = i * 6 - i * (i - 1) / 2 + (j - i);
+                        double a = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) a = fma(Q[6 * i + k], T[6 * k + j], a);
+                        if constexpr (RED) ls.template push<K_GV + 6 + o>(a);
+                        else if (vfree) B.blk_Hvv[(int64_t)o * nb + s] = a;
+                    });
+                });
+                if constexpr (RED) {
+                    static_for<0, 36>([&](auto ci) { constexpr int i = decltype(ci)::value; ls.template push<K_GV + 27 + i>(Q[i]); });
+                } else {
+                    const double* __restrict__ Tc = B.camT + (int64_t)L.seg_cam[s] * 36;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            double a = 0.0;
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) a = fma(Q[6 * i + k], Tc[6 * k + j], a);
+                            if (vfree) B.blk_Evc[(int64_t)(6 * i + j) * nb + s] = a;
+                        }
+                }
+            }
+        }
+        ls.template finish<TOTAL>();
+    }
+}
+
+template <int MODEL, int IMODE, int VIEW>
+__global__ void __launch_bounds__(K1Roles<MODEL, IMODE>::NROLE * 32) k1_kernel(const __grid_constant__ K1Args P) {
+    using RT = K1Roles<MODEL, IMODE>;
+    // one tile per CTA, one warp per role: small CTAs drift apart in time, so the epilogue of one
+    // overlaps the main loops of its neighbours on the SM
+    const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = blockIdx.x;
+    extern __shared__ __align__(128) unsigned char k1_smem[];
+    if (role == 0) k1_role<MODEL, IMODE, 0, VIEW>(P, tile, lane, k1_smem);
+    if constexpr (RT::NROLE > 1) { if (role == 1) k1_role<MODEL, IMODE, 1, VIEW>(P, tile, lane, k1_smem); }
+    if constexpr (RT::NROLE > 2) { if (role == 2) k1_role<MODEL, IMODE, 2, VIEW>(P, tile, lane, k1_smem); }
+}
+
+template <int MODEL, int IMODE, int VIEW>
+static void launch_k1_v(const K1Args& P, cudaStream_t st) {
+    using RT = K1Roles<MODEL, IMODE>;
+    constexpr int threads = RT::NROLE * 32;
+    constexpr int smem = K1Smem<MODEL, IMODE>::kBytes;
+    static bool once = false;
+    if (!once) { cudaFuncSetAttribute(k1_kernel<MODEL, IMODE, VIEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); once = true; }
+    k1_kernel<MODEL, IMODE, VIEW><<<(unsigned)P.L.n_tiles, threads, smem, st>>>(P);
+}
+
+template <int MODEL, int IMODE>
+static void launch_k1_t(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
+    using RT = K1Roles<MODEL, IMODE>;
+    K1Args P{L, B, S.huber_delta, 0};
+    if (!L.fused) { launch_k1_v<MODEL, IMODE, NOT_FUSED>(P, st); return; }
+    const bool reduce_rows = S.kind == 2 && S.view_free_global;
+    P.nvt = RT::nvt(reduce_rows);
+    if (S.kind != 2) launch_k1_v<MODEL, IMODE, VIEW_STORE>(P, st);
+    else if (reduce_rows) launch_k1_v<MODEL, IMODE, VIEW_REDUCE>(P, st);
+    else launch_k1_v<MODEL, IMODE, VIEW_NONE>(P, st);
+}
+
+#define CALK_K1_DISPATCH(FN, ...)                                                          \
+    do {                                                                                   \
+        if (S.model == 0 && S.imode == 0) FN<0, 0>(__VA_ARGS__);                           \
+        else if (S.model == 0 && S.imode == 1) FN<0, 1>(__VA_ARGS__);                      \
+        else if (S.model == 0 && S.imode == 2) FN<0, 2>(__VA_ARGS__);                      \
+        else if (S.model == 1 && S.imode == 0) FN<1, 0>(__VA_ARGS__);                      \
+        else if (S.model == 1 && S.imode == 1) FN<1, 1>(__VA_ARGS__);                      \
+        else FN<1, 2>(__VA_ARGS__);                                                        \
+    } while (0)
+
+void launch_k1(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
+    if (L.n_tiles == 0) return;
+    CALK_K1_DISPATCH(launch_k1_t, S, L, B, st);
+}
+
+template <int MODEL, int IMODE>
+static void roles_info_t(bool view_rows, int* n_roles, int* nvt, std::vector<int32_t>* map) {
+    using RT = K1Roles<MODEL, IMODE>;
+    if (n_roles) *n_roles = RT::NROLE;
+    if (nvt) *nvt = RT::nvt(view_rows);
+    if (map) RT::value_map(view_rows, *map);
+}
+void k1_tile_value_map(const ProblemShape& S, int* n_roles, int* nvt, std::vector<int32_t>* map) {
+    const bool view_rows = S.kind == 2 && S.view_free_global;
+    CALK_K1_DISPATCH(roles_info_t, view_rows, n_roles, nvt, map);
+}
+int k1_num_passes(const ProblemShape& S) { int r = 1; k1_tile_value_map(S, &r, nullptr, nullptr); return r; }
+
+// ---------------------------------------------------------------------------
+// per-camera sums of the per-tile rows (fixed order, no atomics)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tile_colsum(const double* __restrict__ tile_vals, int nvt,
+                                                     const ColChunk* __restrict__ chunks, double* __restrict__ partial) {
+    const ColChunk c = chunks[blockIdx.x];
+    for (int v = threadIdx.x; v < nvt; v += 256) {
+        double a = 0.0;
+        for (int64_t t = c.begin; t < c.end; ++t) a += tile_vals[t * nvt + v];
+        partial[(int64_t)blockIdx.x * nvt + v] = a;
+    }
+}
+__global__ void k_tile_final(const double* __restrict__ partial, const int32_t* __restrict__ cam_chunk_off, int n_cams, int nvt,
+                             const int32_t* __restrict__ vmap, double* __restrict__ cam_sums, int NV) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cams * nvt) return;
+    const int cam = i / nvt, v = i % nvt;
+    double a = 0.0;
+    for (int c = cam_chunk_off[cam]; c < cam_chunk_off[cam + 1]; ++c) a += partial[(int64_t)c * nvt + v];
+    cam_sums[(int64_t)cam * NV + vmap[v]] = a;
+}
+int launch_tile_reduce(const ProblemShape& S, const EvalBuffers& B, const ReduceDesc& R, int nvt, cudaStream_t st) {
+    k_tile_colsum<<<R.n_tile_chunks, 256, 0, st>>>(B.tile_vals, nvt, R.tile_chunks, B.partial_tile);
+    k_tile_final<<<(S.n_cams * nvt + 127) / 128, 128, 0, st>>>(B.partial_tile, R.tile_cam_chunk_off, S.n_cams, nvt, B.tile_vmap, B.cam_sums, S.NV);
+    return 2;
+}
+
+}  // namespace calk

@@ -291,7 +291,14 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     // ---- segments ----
     int64_t max_len = 0;
     for (int64_t b = 0; b < d.n_blocks; ++b) max_len = std::max<int64_t>(max_len, d.block_offset[b + 1] - d.block_offset[b]);
-    const int64_t target = std::min<int64_t>(std::max<int64_t>(8, (d.n_obs + 65535) / 65536), std::max<int64_t>(max_len, 1));
+    // Large problems: one segment per residual block and a (zero-length) segment for every padding
+    // block, so that segment s == device block s and K1 can finish each block in its epilogue.
+    // Small problems: blocks are cut into short segments so that they still fill the machine.
+    bool fused = d.n_blocks >= 16384;
+    if (const char* e = getenv("CALIB_B200_FUSED")) fused = e[0] == '1';
+    h.L.fused = fused ? 1 : 0;
+    const int64_t target = fused ? std::max<int64_t>(max_len, 1)
+                                 : std::min<int64_t>(std::max<int64_t>(8, (d.n_obs + 65535) / 65536), std::max<int64_t>(max_len, 1));
     std::vector<int32_t> seg_len, seg_blk, seg_cam, blk_seg_off(nblk + 1, 0), blk_vfree(nblk, 0);
     std::vector<int64_t> seg_src;
     {
@@ -303,7 +310,10 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     h.L.one_seg_per_blk = 1;
     for (int64_t b = 0; b < nblk; ++b) {
         blk_seg_off[b] = (int32_t)seg_len.size();
-        if (borig[b] < 0) continue;
+        if (borig[b] < 0) {
+            if (fused) { seg_len.push_back(0); seg_blk.push_back((int32_t)b); seg_cam.push_back(bcam[b]); seg_src.push_back(0); }
+            continue;
+        }
         const int64_t o0 = d.block_offset[borig[b]], len = d.block_offset[borig[b] + 1] - o0;
         const int64_t nsegb = (len + target - 1) / target, sl = (len + nsegb - 1) / nsegb;
         if (nsegb != 1) h.L.one_seg_per_blk = 0;
@@ -328,9 +338,13 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
 
     // ---- one arena for every device buffer of the handle ----
     {
-        const size_t nbr = (size_t)(S.NV - S.NE);
-        size_t bytes = (size_t)slices * 128 * 8 + (size_t)ntiles * 12 + (size_t)nseg * (12 + 8 * (9 + S.NE + 2)) +
+        // fused K1 keeps no per-segment local systems and no block-indexed rows (only the cost row)
+        int nvt = 0; k1_tile_value_map(S, nullptr, &nvt, nullptr);
+        const size_t nbr = fused ? 1 : (size_t)(S.NV - S.NE);
+        const size_t seg_doubles = fused ? 9 + 2 : 9 + S.NE + 2;
+        size_t bytes = (size_t)slices * 128 * 8 + (size_t)ntiles * 12 + (size_t)nseg * (12 + 8 * seg_doubles) +
                        (size_t)nblk * (4 * 4 + 8 + 8 * (36 + 2 + nbr + 12)) + (size_t)h.n_amb * 16 + (1u << 20);
+        if (fused) bytes += (size_t)ntiles * nvt * 8 + (size_t)(ntiles / 32 + S.n_cams + 1) * (nvt * 8 + 64);
         if (S.n_views > 0) bytes += (size_t)nblk * 8 * (21 + 6 + 36 + 6 * std::max(S.PI, 1) + 6 * (6 + S.PI)) + (size_t)S.n_views * 8 * 120 +
                                     (size_t)schur_num_ctas(S.n_views) * (h.ns + 1) * (h.ns + 1) * 8 + (size_t)h.ns * h.ns * 8 + (1u << 20);
         bytes += 256 * 64;  // alignment slack
@@ -373,8 +387,7 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     // ---- evaluation buffers ----
     EvalBuffers& B = h.B;
     {   // column chunks for the deterministic per-camera reductions (segments and blocks)
-        auto make_chunks = [&](const std::vector<int32_t>& cam_of, int64_t n, std::vector<ColChunk>& ch, std::vector<int32_t>& off) {
-            const int64_t kChunk = 8192;
+        auto make_chunks = [&](const std::vector<int32_t>& cam_of, int64_t n, std::vector<ColChunk>& ch, std::vector<int32_t>& off, int64_t kChunk) {
             off.assign(S.n_cams + 1, 0);
             int64_t i = 0;
             std::vector<std::vector<ColChunk>> per(S.n_cams);
@@ -389,8 +402,21 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         };
         std::vector<ColChunk> sc, bc; std::vector<int32_t> so, bo;
         std::vector<int32_t> seg_cam_trim(seg_cam.begin(), seg_cam.begin() + blk_seg_off[nblk]);
-        make_chunks(seg_cam_trim, (int64_t)seg_cam_trim.size(), sc, so);
-        make_chunks(bcam, nblk, bc, bo);
+        make_chunks(seg_cam_trim, (int64_t)seg_cam_trim.size(), sc, so, 8192);
+        make_chunks(bcam, nblk, bc, bo, 8192);
+        if (fused) {  // tiles are camera-pure (camera groups are padded to 32 blocks = one tile)
+            std::vector<int32_t> tile_cam(ntiles);
+            for (int64_t t = 0; t < ntiles; ++t) tile_cam[t] = bcam[t * 32];
+            std::vector<ColChunk> tc; std::vector<int32_t> to;
+            make_chunks(tile_cam, ntiles, tc, to, 32);
+            std::vector<int32_t> vmap; int nvt = 0; k1_tile_value_map(S, nullptr, &nvt, &vmap);
+            h.R.n_tile_chunks = (int)tc.size(); h.R.nvt = nvt;
+            CUDA_TRY(h.alloc(&h.R.tile_chunks, tc.size())); CUDA_TRY(h.alloc(&h.R.tile_cam_chunk_off, to.size()));
+            CUDA_TRY(upload(h.R.tile_chunks, tc, h.st)); CUDA_TRY(upload(h.R.tile_cam_chunk_off, to, h.st));
+            CUDA_TRY(h.alloc(&h.B.tile_vmap, vmap.size())); CUDA_TRY(upload(h.B.tile_vmap, vmap, h.st));
+            CUDA_TRY(h.alloc(&h.B.tile_vals, (size_t)ntiles * nvt)); CUDA_TRY(h.alloc(&h.B.partial_tile, tc.size() * (size_t)nvt));
+            CUDA_TRY(cudaStreamSynchronize(h.st));  // the staging vectors above go out of scope
+        }
         h.R.n_seg_chunks = (int)sc.size(); h.R.n_blk_chunks = (int)bc.size();
         CUDA_TRY(h.alloc(&h.R.seg_chunks, sc.size())); CUDA_TRY(h.alloc(&h.R.blk_chunks, bc.size()));
         CUDA_TRY(h.alloc(&h.R.seg_cam_chunk_off, so.size())); CUDA_TRY(h.alloc(&h.R.blk_cam_chunk_off, bo.size()));
@@ -398,12 +424,14 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         CUDA_TRY(upload(h.R.seg_cam_chunk_off, so, h.st)); CUDA_TRY(upload(h.R.blk_cam_chunk_off, bo, h.st));
         CUDA_TRY(cudaStreamSynchronize(h.st));
     }
-    const int n_brows = S.NV - S.NE;
+    const int n_brows = fused ? 1 : S.NV - S.NE;
     CUDA_TRY(h.alloc(&B.x, h.n_amb)); CUDA_TRY(h.alloc(&B.camc, S.n_cams)); CUDA_TRY(h.alloc(&B.camT, (size_t)S.n_cams * 36));
     CUDA_TRY(h.alloc(&B.seg_frame, (size_t)9 * nseg)); CUDA_TRY(h.alloc(&B.blk_Tv, (size_t)36 * nblk));
-    CUDA_TRY(h.alloc(&B.segN, (size_t)S.NE * nseg)); CUDA_TRY(h.alloc(&B.seg_ssr, nseg)); CUDA_TRY(h.alloc(&B.blk_ssr, nblk));
+    if (!fused) CUDA_TRY(h.alloc(&B.segN, (size_t)S.NE * nseg));
+    CUDA_TRY(h.alloc(&B.seg_ssr, nseg)); CUDA_TRY(h.alloc(&B.blk_ssr, nblk));
     CUDA_TRY(h.alloc(&B.partial, (size_t)std::max(h.R.n_seg_chunks, 1) * S.NE)); CUDA_TRY(h.alloc(&B.partial_blk, (size_t)std::max(h.R.n_blk_chunks, 1) * n_brows));
     CUDA_TRY(h.alloc(&B.cam_sums, (size_t)S.n_cams * S.NV));
+    CUDA_TRY(cudaMemsetAsync(B.cam_sums, 0, sizeof(double) * S.n_cams * S.NV, h.st));
     CUDA_TRY(h.alloc(&B.blk_w, nblk)); CUDA_TRY(h.alloc(&B.seg_w, nseg)); CUDA_TRY(h.alloc(&B.blk_rows, (size_t)n_brows * nblk));
     CUDA_TRY(cudaMemsetAsync(B.seg_w, 0, sizeof(double) * nseg, h.st));
     CUDA_TRY(cudaMemsetAsync(B.blk_rows, 0, sizeof(double) * n_brows * nblk, h.st));

@@ -9,9 +9,7 @@
 //                   per evaluation: camera constants, composite block poses
 //                   (pose chains of src/estimation/residuals/*.h), sensor-frame
 //                   frames and the 6x6 chain-rule transforms
-//   k1_kernel       K1: fused project -> residual -> analytic Jacobian ->
-//                   J^T J / J^T r accumulation, one lane per segment, lane-
-//                   private register accumulators, coalesced 256 B rows
+//   (K1 itself, the fused residual + Jacobian + J^T J + per-block epilogue kernel, is k1_fused.cu)
 //   k_cost          residual-only pass
 //   k_assemble      per block: Huber weight (per residual block),
 //                   chain rule, deterministic warp transpose-reductions into
@@ -26,6 +24,7 @@
 #include <type_traits>
 
 #include "refine_kernels.cuh"
+#include "tile_stage.cuh"
 
 namespace calk {
 
@@ -116,346 +115,11 @@ __global__ void k_block_setup(ProblemShape S, DevLayout L, EvalBuffers B) {
         for (int i = 0; i < 9; ++i) B.seg_frame[(int64_t)i * L.n_seg + s] = A[i];
 }
 
-__global__ void k_pad_frames(DevLayout L, EvalBuffers B, int64_t first_pad) {
-    const int64_t s = first_pad + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= L.n_seg) return;
-    for (int i = 0; i < 9; ++i) B.seg_frame[(int64_t)i * L.n_seg + s] = (i % 4 == 0) ? 1.0 : 0.0;
-}
-
 void launch_setup(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
     k_cam_setup<<<(S.n_cams + 63) / 64, 64, 0, st>>>(S, B);
     if (L.n_blk > 0) k_block_setup<<<(unsigned)((L.n_blk + 127) / 128), 128, 0, st>>>(S, L, B);
 }
 
-// ---------------------------------------------------------------------------
-// TMA staging of a warp's tile: bulk asynchronous copies (cp.async.bulk, SASS UBLKCP) of
-// kChunk k-slices (kChunk x 1 KB, contiguous in the tile-transposed layout) into a per-warp
-// two-stage shared-memory ring, completion signalled on an mbarrier.  One elected lane
-// issues; all lanes then read their column with conflict-free 8-byte shared loads.
-// ---------------------------------------------------------------------------
-constexpr int kChunk = 8;                       // k-slices per stage (8 KB)
-constexpr int kStageDoubles = kChunk * 128;
-constexpr int kWarpStageBytes = 2 * kStageDoubles * 8 + 16;  // two stages + two mbarriers
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-struct TileStage {
-    double* buf;                // [2][kChunk][4][32]
-    unsigned long long* bar;    // [2]
-    const double* src;          // tile base in global memory
-    int depth, n_chunks;
-
-    __device__ __forceinline__ void init(unsigned char* warp_smem, const double* tile_src, int tile_depth, int lane) {
-        buf = reinterpret_cast<double*>(warp_smem);
-        bar = reinterpret_cast<unsigned long long*>(warp_smem + 2 * kStageDoubles * 8);
-        src = tile_src; depth = tile_depth; n_chunks = (tile_depth + kChunk - 1) / kChunk;
-        if (lane == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
-        __syncwarp();
-    }
-    // issue chunk c into stage c & 1 (lane 0 only)
-    __device__ __forceinline__ void issue(int c, int lane) {
-        if (lane == 0 && c < n_chunks) {
-            const int ks = min(kChunk, depth - c * kChunk);
-            const unsigned bytes = (unsigned)ks * 1024u;
-            const unsigned mb = smem_u32(&bar[c & 1]);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(buf + (c & 1) * kStageDoubles)), "l"(src + (int64_t)c * kStageDoubles), "r"(bytes), "r"(mb)
-                         : "memory");
-        }
-    }
-    // wait until chunk c has landed
-    __device__ __forceinline__ void wait(int c) {
-        const unsigned mb = smem_u32(&bar[c & 1]);
-        const unsigned parity = (unsigned)(c >> 1) & 1u;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-            "@!p bra WAIT_%=;\n\t}" ::"r"(mb), "r"(parity) : "memory");
-    }
-    __device__ __forceinline__ const double* row(int c, int kk, int lane) const { return buf + (c & 1) * kStageDoubles + kk * 128 + lane; }
-};
-
-// ---------------------------------------------------------------------------
-// K1: fused residual + Jacobian + J^T J
-// ---------------------------------------------------------------------------
-template <class LT, int NPASS, int PASS>
-__device__ __forceinline__ void k1_accumulate(const double* __restrict__ Ju, const double* __restrict__ Jv,
-                                              double* __restrict__ acc) {
-#pragma unroll
-    for (int a = 0; a < LT::NL; ++a) {
-#pragma unroll
-        for (int b = a; b < LT::NL; ++b) {
-            const int e = LT::idx(a, b);
-            if (e % NPASS == PASS) {
-                double v = acc[e / NPASS];
-                if (LT::has_u(a) && LT::has_u(b)) v = fma(Ju[a], Ju[b], v);
-                if (LT::has_v(a) && LT::has_v(b)) v = fma(Jv[a], Jv[b], v);
-                acc[e / NPASS] = v;
-            }
-        }
-    }
-}
-
-template <int MODEL, int IMODE, int NPASS, int PASS>
-__device__ __forceinline__ void k1_body(const DevLayout& L, const EvalBuffers& B, int64_t tile, int lane, unsigned char* warp_smem) {
-    using LT = Local<MODEL, IMODE>;
-    constexpr int NA = (LT::NE + NPASS - 1) / NPASS;
-    const int64_t s = tile * 32 + lane;
-    const int len = L.seg_len[s];
-    const int depth = L.tile_depth[tile];
-    TileStage ts; ts.init(warp_smem, L.obs + L.tile_off[tile] * 128, depth, lane);
-    ts.issue(0, lane); ts.issue(1, lane);
-    double A[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) A[i] = B.seg_frame[(int64_t)i * L.n_seg + s];
-    const CamConst c = B.camc[L.seg_cam[s]];
-    double acc[NA];
-#pragma unroll
-    for (int i = 0; i < NA; ++i) acc[i] = 0.0;
-    for (int ch = 0; ch < ts.n_chunks; ++ch) {
-        ts.wait(ch);
-        const int k0 = ch * kChunk, kn = min(kChunk, depth - k0);
-        for (int kk = 0; kk < kn; ++kk) {
-            const double* q = ts.row(ch, kk, lane);
-            const double X = q[0], Y = q[32], U = q[64], V = q[96];
-            if (k0 + kk < len) {
-                double Ju[LT::NL], Jv[LT::NL];
-                obs_rows<MODEL, IMODE>(c, A, X, Y, U, V, Ju, Jv);
-                k1_accumulate<LT, NPASS, PASS>(Ju, Jv, acc);
-            }
-        }
-        __syncwarp();               // every lane is done with this stage
-        ts.issue(ch + 2, lane);     // refill it
-    }
-#pragma unroll
-    for (int e = 0; e < LT::NE; ++e)
-        if (e % NPASS == PASS) B.segN[(int64_t)e * L.n_seg + s] = acc[e / NPASS];
-}
-
-template <int MODEL, int IMODE, int NPASS>
-__global__ void __launch_bounds__(128) k1_kernel(DevLayout L, EvalBuffers B) {
-    // the passes of one tile group are adjacent CTAs, so the second pass finds the rows in L2
-    const int64_t tile = (int64_t)(blockIdx.x / NPASS) * 4 + (threadIdx.x >> 5);
-    if (tile >= L.n_tiles) return;
-    const int lane = threadIdx.x & 31;
-    const int pass = blockIdx.x % NPASS;
-    extern __shared__ __align__(128) unsigned char k1_smem[];
-    unsigned char* warp_smem = k1_smem + (threadIdx.x >> 5) * kWarpStageBytes;
-    if (pass == 0) k1_body<MODEL, IMODE, NPASS, 0>(L, B, tile, lane, warp_smem);
-    if (NPASS > 1 && pass == 1) k1_body<MODEL, IMODE, NPASS, (NPASS > 1 ? 1 : 0)>(L, B, tile, lane, warp_smem);
-    if (NPASS > 2 && pass == 2) k1_body<MODEL, IMODE, NPASS, (NPASS > 2 ? 2 : 0)>(L, B, tile, lane, warp_smem);
-}
-
-// ---------------------------------------------------------------------------
-// K1 v2: producer / consumer warp pairs (pinhole model with free intrinsics)
-// ---------------------------------------------------------------------------
-// The 136/153 accumulators of the local system do not fit one thread.  v1 splits
-// them over passes that each recompute the projection and Jacobian.  v2 pairs two
-// warps on the same tile instead: warp A projects, forms the Jacobian rows once,
-// hands the 24 values warp B needs through a double-buffered shared-memory slot
-// (named barriers: A st.shared + bar.arrive, B bar.sync + ld.shared — the PTX
-// producer/consumer idiom) and accumulates the entries that involve a linear
-// intrinsic column (fx, fy, cx, cy, skew) plus |r|^2; warp B accumulates the
-// twist / distortion / residual block.  Both do ~155 FP64 instructions per
-// observation, nothing is computed twice, and B's stream of independent FMAs
-// fills the FP64 pipe while A sits in the dependent projection chain.
-template <int I, int N, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-    if constexpr (I < N) { f(std::integral_constant<int, I>{}); static_for<I + 1, N>(f); }
-}
-
-template <class LT>
-struct Split {
-    static constexpr bool is_lin(int c) {  // linear intrinsic columns
-        return c >= 6 && c < LT::NC && c - 6 < LT::c_d0;
-    }
-    static constexpr bool in_a(int a, int b) { return is_lin(a) || is_lin(b) || (a == LT::NC && b == LT::NC); }
-    static constexpr int slot(int a, int b) {  // index of (a,b) among the entries of its own role
-        const bool ra = in_a(a, b);
-        int n = 0;
-        for (int i = 0; i < LT::NL; ++i)
-            for (int j = i; j < LT::NL; ++j) {
-                if (i == a && j == b) return n;
-                if (in_a(i, j) == ra) ++n;
-            }
-        return n;
-    }
-    static constexpr int count(bool ra) {
-        int n = 0;
-        for (int i = 0; i < LT::NL; ++i) for (int j = i; j < LT::NL; ++j) if (in_a(i, j) == ra) ++n;
-        return n;
-    }
-    static constexpr int NA = count(true), NB = count(false);
-    // exchange slots: for every non-linear column c its u value at 2*x(c), v value at 2*x(c)+1
-    static constexpr int xcol(int c) { int n = 0; for (int i = 0; i < c; ++i) if (!is_lin(i)) ++n; return n; }
-    static constexpr int NX = 2 * (LT::NL - (LT::c_d0 < 0 ? 0 : LT::c_d0));
-};
-
-__device__ __forceinline__ void bar_sync64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void bar_arrive64(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
-
-// U observations of the lane's segment travel per exchange stage: warp A runs their U
-// independent projection chains interleaved (the chain, not the FP64 issue rate, bounds a
-// producer that handles one observation at a time) and both warps pay one barrier per U.
-template <int MODEL, int IMODE, int U>
-__global__ void __launch_bounds__(256, 1) k1v2_kernel(DevLayout L, EvalBuffers B) {
-    using LT = Local<MODEL, IMODE>;
-    using SP = Split<LT>;
-    constexpr int NX = SP::NX;
-    extern __shared__ __align__(16) double xbuf_raw[];
-    typedef double (*XBuf)[2][U][NX][32];
-    XBuf xbuf = reinterpret_cast<XBuf>(xbuf_raw);  // [pair][stage][u][value][lane]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = warp & 3;
-    const bool role_b = ((warp >> 2) ^ (warp & 1)) != 0;  // each SM sub-partition hosts one A and one B warp
-    const int64_t tile = (int64_t)blockIdx.x * 4 + pair;
-    if (tile >= L.n_tiles) return;  // both warps of the pair leave together
-    const int64_t s = tile * 32 + lane;
-    const int len = L.seg_len[s];
-    const int depth = L.tile_depth[tile];
-    const int n_steps = (depth + U - 1) / U;
-    const int bar_full = 4 * pair, bar_empty = 4 * pair + 2;
-    if (!role_b) {
-        double A[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) A[i] = B.seg_frame[(int64_t)i * L.n_seg + s];
-        const CamConst c = B.camc[L.seg_cam[s]];
-        const double* __restrict__ p = L.obs + L.tile_off[tile] * 128 + lane;
-        double acc[SP::NA];
-#pragma unroll
-        for (int i = 0; i < SP::NA; ++i) acc[i] = 0.0;
-        double ob[U][4];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ob[u][q] = (u < depth) ? p[(int64_t)u * 128 + 32 * q] : 0.0;
-        for (int t = 0; t < n_steps; ++t) {
-            const int st = t & 1, k0 = t * U;
-            double nx[U][4];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) nx[u][q] = (k0 + U + u < depth) ? p[(int64_t)(k0 + U + u) * 128 + 32 * q] : 0.0;
-            double Ju[U][LT::NL], Jv[U][LT::NL];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (k0 + u < len) obs_rows<MODEL, IMODE>(c, A, ob[u][0], ob[u][1], ob[u][2], ob[u][3], Ju[u], Jv[u]);
-            if (t >= 2) bar_sync64(bar_empty + st);  // B has drained this stage
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (k0 + u < len) {
-                    static_for<0, LT::NL>([&](auto cc) {
-                        constexpr int col = decltype(cc)::value;
-                        if constexpr (!SP::is_lin(col)) {
-                            xbuf[pair][st][u][2 * SP::xcol(col)][lane] = Ju[u][col];
-                            xbuf[pair][st][u][2 * SP::xcol(col) + 1][lane] = Jv[u][col];
-                        }
-                    });
-                }
-            bar_arrive64(bar_full + st);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (k0 + u < len) {
-                    static_for<0, LT::NL>([&](auto ca) {
-                        static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
-                            constexpr int a = decltype(ca)::value, b = decltype(cb)::value;
-                            if constexpr (SP::in_a(a, b)) {
-                                constexpr int sl = SP::slot(a, b);
-                                if constexpr (LT::has_u(a) && LT::has_u(b)) acc[sl] = fma(Ju[u][a], Ju[u][b], acc[sl]);
-                                if constexpr (LT::has_v(a) && LT::has_v(b)) acc[sl] = fma(Jv[u][a], Jv[u][b], acc[sl]);
-                            }
-                        });
-                    });
-                }
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) ob[u][q] = nx[u][q];
-        }
-        static_for<0, LT::NL>([&](auto ca) {
-            static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
-                constexpr int a = decltype(ca)::value, b = decltype(cb)::value;
-                if constexpr (SP::in_a(a, b)) B.segN[(int64_t)LT::idx(a, b) * L.n_seg + s] = acc[SP::slot(a, b)];
-            });
-        });
-    } else {
-        double acc[SP::NB];
-#pragma unroll
-        for (int i = 0; i < SP::NB; ++i) acc[i] = 0.0;
-        for (int t = 0; t < n_steps; ++t) {
-            const int st = t & 1, k0 = t * U;
-            bar_sync64(bar_full + st);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const bool act = k0 + u < len;
-                double Ju[LT::NL], Jv[LT::NL];
-                if (act) {
-                    static_for<0, LT::NL>([&](auto cc) {
-                        constexpr int col = decltype(cc)::value;
-                        if constexpr (!SP::is_lin(col)) {
-                            Ju[col] = xbuf[pair][st][u][2 * SP::xcol(col)][lane];
-                            Jv[col] = xbuf[pair][st][u][2 * SP::xcol(col) + 1][lane];
-                        }
-                    });
-                }
-                if (u == U - 1 && t + 2 < n_steps) bar_arrive64(bar_empty + st);
-                if (act) {
-                    static_for<0, LT::NL>([&](auto ca) {
-                        static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
-                            constexpr int a = decltype(ca)::value, b = decltype(cb)::value;
-                            if constexpr (!SP::in_a(a, b)) {
-                                constexpr int sl = SP::slot(a, b);
-                                if constexpr (LT::has_u(a) && LT::has_u(b)) acc[sl] = fma(Ju[a], Ju[b], acc[sl]);
-                                if constexpr (LT::has_v(a) && LT::has_v(b)) acc[sl] = fma(Jv[a], Jv[b], acc[sl]);
-                            }
-                        });
-                    });
-                }
-            }
-        }
-        static_for<0, LT::NL>([&](auto ca) {
-            static_for<decltype(ca)::value, LT::NL>([&](auto cb) {
-                constexpr int a = decltype(ca)::value, b = decltype(cb)::value;
-                if constexpr (!SP::in_a(a, b)) B.segN[(int64_t)LT::idx(a, b) * L.n_seg + s] = acc[SP::slot(a, b)];
-            });
-        });
-    }
-}
-
-template <int IMODE, int U>
-static void launch_k1v2_t(const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
-    using SP = Split<Local<0, IMODE>>;
-    const size_t smem = sizeof(double) * 4 * 2 * U * SP::NX * 32;
-    static bool once = false;
-    if (!once) { cudaFuncSetAttribute(k1v2_kernel<0, IMODE, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); once = true; }
-    k1v2_kernel<0, IMODE, U><<<(unsigned)((L.n_tiles + 3) / 4), 256, smem, st>>>(L, B);
-}
-
-template <int MODEL, int IMODE>
-constexpr int passes_for() {
-    return Local<MODEL, IMODE>::NE <= 72 ? 1 : (Local<MODEL, IMODE>::NE <= 144 ? 2 : 3);
-}
-bool k1_uses_pairs(const ProblemShape& S);
-int k1_num_passes(const ProblemShape& S) {
-    if (k1_uses_pairs(S)) return 1;
-    return S.NE <= 72 ? 1 : (S.NE <= 144 ? 2 : 3);
-}
-
-template <int MODEL, int IMODE>
-static void launch_k1_t(const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
-    constexpr int NP = passes_for<MODEL, IMODE>();
-    const unsigned grid = (unsigned)((L.n_tiles + 3) / 4) * NP;
-    constexpr int smem = 4 * kWarpStageBytes;
-    static bool once = false;
-    if (!once) { cudaFuncSetAttribute(k1_kernel<MODEL, IMODE, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); once = true; }
-    k1_kernel<MODEL, IMODE, NP><<<grid, 128, smem, st>>>(L, B);
-}
 #define CALK_DISPATCH(FN, ...)                                                             \
     do {                                                                                   \
         if (S.model == 0 && S.imode == 0) FN<0, 0>(__VA_ARGS__);                           \
@@ -465,23 +129,6 @@ static void launch_k1_t(const DevLayout& L, const EvalBuffers& B, cudaStream_t s
         else if (S.model == 1 && S.imode == 1) FN<1, 1>(__VA_ARGS__);                      \
         else FN<1, 2>(__VA_ARGS__);                                                        \
     } while (0)
-
-static int k1_variant() {  // CALIB_B200_K1=v2 selects the experimental warp-pair kernel (A/B comparison while profiling)
-    static const int v = [] { const char* e = getenv("CALIB_B200_K1"); return (e && e[0] == 'v' && e[1] == '2') ? 2 : 1; }();
-    return v;
-}
-bool k1_uses_pairs(const ProblemShape& S) { return S.model == 0 && S.imode != 0 && k1_variant() == 2; }
-
-void launch_k1(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
-    if (L.n_tiles == 0) return;
-    if (k1_uses_pairs(S)) {
-        static const int U = [] { const char* e = getenv("CALIB_B200_K1_U"); return e ? atoi(e) : 1; }();
-        if (S.imode == 1) { if (U == 1) launch_k1v2_t<1, 1>(L, B, st); else if (U == 3) launch_k1v2_t<1, 3>(L, B, st); else launch_k1v2_t<1, 2>(L, B, st); }
-        else { if (U == 1) launch_k1v2_t<2, 1>(L, B, st); else launch_k1v2_t<2, 2>(L, B, st); }
-        return;
-    }
-    CALK_DISPATCH(launch_k1_t, L, B, st);
-}
 
 // residual-only pass
 template <int MODEL>
@@ -694,6 +341,7 @@ static void launch_view_part_t(const ProblemShape& S, const DevLayout& L, const 
 
 int launch_assemble(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ReduceDesc& R, int jac,
                     cudaStream_t st) {
+    if (jac && L.fused) return launch_tile_reduce(S, B, R, R.nvt, st);  // K1 already weighted, transformed and summed per tile
     int launches = 0;
     const unsigned gb = (unsigned)((L.n_blk + 127) / 128);
     const int rr_row = S.NL * S.NC - S.NC * (S.NC - 1) / 2;  // idx(NC, NC)

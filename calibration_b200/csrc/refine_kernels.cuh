@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "k1_math.cuh"
 
 namespace calk {
@@ -19,6 +21,7 @@ struct DevLayout {
     int64_t n_blk = 0;        // device blocks: sorted by camera, camera groups padded to 32
     int64_t n_slices = 0;     // total k-slices (each 128 doubles)
     int32_t one_seg_per_blk = 0;  // every real block has exactly one segment
+    int32_t fused = 0;            // segment s == device block s (padding blocks included): K1 runs its fused epilogue
     double* obs = nullptr;
     int64_t* tile_off = nullptr;  // [n_tiles]
     int32_t* tile_depth = nullptr;
@@ -53,6 +56,10 @@ struct EvalBuffers {
     double* partial = nullptr;    // [n_seg_chunks][NE]
     double* partial_blk = nullptr;// [n_blk_chunks][NV - NE]
     double* cam_sums = nullptr;   // [n_cams][NV]
+    // fused K1: one row of NVT values per tile, summed per camera by k_tile_colsum / k_tile_final
+    double* tile_vals = nullptr;  // [n_tiles][nvt]
+    double* partial_tile = nullptr;  // [n_tile_chunks][nvt]
+    int32_t* tile_vmap = nullptr; // [nvt] -> index into a camera's cam_sums row
 };
 
 struct ProblemShape {
@@ -72,6 +79,7 @@ struct ColChunk { int32_t cam; int32_t pad; int64_t begin, end; };
 struct ReduceDesc {
     ColChunk* seg_chunks = nullptr; int n_seg_chunks = 0; int32_t* seg_cam_chunk_off = nullptr;  // [n_cams + 1]
     ColChunk* blk_chunks = nullptr; int n_blk_chunks = 0; int32_t* blk_cam_chunk_off = nullptr;
+    ColChunk* tile_chunks = nullptr; int n_tile_chunks = 0; int32_t* tile_cam_chunk_off = nullptr; int nvt = 0;  // fused K1
 };
 
 void launch_repack(const DevLayout& L, const double* sx, const double* sy, const double* su, const double* sv,
@@ -83,7 +91,10 @@ void launch_cost(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B
 // jac != 0: reduce the K1 output; else reduce seg_ssr to per-camera cost.  Returns the number of launches.
 int launch_assemble(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ReduceDesc& R, int jac,
                     cudaStream_t st);
-int k1_num_passes(const ProblemShape& S);
+int k1_num_passes(const ProblemShape& S);  // roles (warps per tile) of K1
+// fused K1: number of roles, values per tile and their index in a camera's cam_sums row
+void k1_tile_value_map(const ProblemShape& S, int* n_roles, int* nvt, std::vector<int32_t>* map);
+int launch_tile_reduce(const ProblemShape& S, const EvalBuffers& B, const ReduceDesc& R, int nvt, cudaStream_t st);
 float dfma_peak_ms(double* scratch, int blocks, int threads, int iters, cudaStream_t st);
 
 // ---- per-view (Schur) machinery -------------------------------------------------

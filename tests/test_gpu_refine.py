@@ -80,8 +80,16 @@ EVAL_CASES = {
 }
 
 
+@pytest.fixture(params=["segments", "fused"])
+def k1_layout(request, monkeypatch):
+    """Both device layouts of K1: blocks cut into short segments + assembly kernels (small problems) and
+    one block per lane with the fused per-block epilogue (what problems of >= 16384 blocks get)."""
+    monkeypatch.setenv("CALIB_B200_FUSED", "1" if request.param == "fused" else "0")
+    return request.param
+
+
 @pytest.mark.parametrize("name", sorted(EVAL_CASES))
-def test_fused_pass_matches_oracle(name):
+def test_fused_pass_matches_oracle(name, k1_layout):
     prob, x0 = EVAL_CASES[name]()
     assert_eval_parity(prob, x0)
 
@@ -99,17 +107,18 @@ def ragged_bundle(seed=11):
     return p2, x0
 
 
-def test_ragged_views():
+def test_ragged_views(k1_layout):
     prob, x0 = ragged_bundle()
     assert_eval_parity(prob, x0)
 
 
 def test_single_segment_layout_at_scale():
-    """8.8M observations: one segment per residual block, the layout the C5 benchmark runs."""
+    """8.8M observations: one segment per residual block (camera groups padded to whole tiles of 32
+    blocks), K1 with its fused epilogue — the layout the C5 benchmark runs."""
     prob, x0, _ = synth.make_bundle(n_cams=8, n_poses=12500)
     h = capi.RefineHandle(prob)
     try:
-        assert h.layout_info()["n_segments"] == prob.desc.n_blocks == 100000
+        assert prob.desc.n_blocks == 100000 and h.layout_info()["n_segments"] == 8 * 12512
         c_g, g_g, H_g = h.eval(x0)
     finally:
         h.close()
@@ -175,23 +184,43 @@ def test_reference_extrinsics(which):
 
 
 # ---- noisy BASELINE-shaped problems: converged parameters vs the oracle ----
-def test_c1_intrinsics_solve():
+def test_c1_intrinsics_solve(k1_layout):
     prob, x0, _ = synth.make_intrinsics()
     assert_solve_parity(prob, x0)
     prob, x0, _ = synth.make_intrinsics(huber_delta=-1.0)
     assert_solve_parity(prob, x0)
 
 
-def test_c3_extrinsics_solve():
+def test_c3_extrinsics_solve(k1_layout):
     prob, x0, _ = synth.make_extrinsics(n_views=150)
     assert_solve_parity(prob, x0, abi.OptimOptions.default(compute_covariance=0))
 
 
-def test_c4_bundle_solve_with_covariance():
+def test_c4_bundle_solve_with_covariance(k1_layout):
     prob, x0, xgt = synth.make_bundle(n_cams=4, n_poses=400)
     x, res, cov = assert_solve_parity(prob, x0)
     assert res.covariance_ok and cov.shape == (75, 75)
     assert np.abs(x - xgt)[:40].max() < 3.0, np.abs(x - xgt)[:40].max()  # intrinsics near ground truth under 0.2 px noise
+
+
+def test_extrinsics_schur_path_at_scale():
+    """2 cameras x 9000 views (18 000 blocks, 1.58 M observations): the per-view kinds on the fused K1
+    layout — per-block H_vv / g_v / E_vc / E_vi come straight from K1's epilogue into the Schur kernels."""
+    prob, x0, _ = synth.make_extrinsics(n_views=9000)
+    h = capi.RefineHandle(prob)
+    try:
+        assert h.layout_info()["n_segments"] == h.layout_info()["n_tiles"] * 32 >= prob.desc.n_blocks >= 16384
+        c_g = h.cost(x0)
+        x, res, _ = h.solve(x0, abi.OptimOptions.default(compute_covariance=0))
+        c_fin = h.cost(x)
+    finally:
+        h.close()
+    ssr = O.block_ssr(prob, x0)
+    rho = np.where(ssr > 1.0, 2.0 * np.sqrt(ssr) - 1.0, ssr)
+    assert abs(c_g - 0.5 * rho.sum()) <= 1e-12 * c_g
+    assert res.success and c_fin < 0.05 * c_g
+    x_o, r_o, _ = O.refine_solve(prob, x0, abi.OptimOptions.default(compute_covariance=0))
+    assert r_o.success and relerr(x, x_o) <= 1e-8 and abs(rms_px(prob, x) - rms_px(prob, x_o)) <= 1e-10
 
 
 def test_max_iterations_reports_no_convergence():
