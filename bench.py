@@ -84,6 +84,20 @@ def shard_chunks(n_poses, rank, world):
 
 
 def run_b200(args, rank, world, local_rank):
+    # the contract is ONE JSON line on stdout: anything libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        out = _run_b200(args, rank, world, local_rank)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+def _run_b200(args, rank, world, local_rank):
     import torch
     from calibration_b200 import abi, capi, synth
     dist = None
@@ -167,7 +181,7 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
     if rank != 0:
-        return
+        return None
     pk, pk_src = peaks()
     hbm_peak = float(pk["hbm_gbs"])
     k1_ms_launch = ms_k1 / args.steps
@@ -210,7 +224,7 @@ def run_b200(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, steps=3)
-    print(json.dumps(out))
+    return out
 
 
 def cpu_sample_problem(args):

@@ -125,12 +125,36 @@ class RansacResult(C.Structure):
     ]
 
 
+class SeedOptions(C.Structure):
+    """cal_seed_options: IntrinsicsEstimOptions.bounds (optional CalibrationBounds)."""
+    _fields_ = [("use_bounds", C.c_int32), ("reserved", C.c_int32)] + [(n, C.c_double) for n in (
+        "fx_min", "fx_max", "fy_min", "fy_max", "cx_min", "cx_max", "cy_min", "cy_max", "skew_min", "skew_max")]
+
+    @classmethod
+    def from_bounds(cls, b):
+        """b = None (std::nullopt) or 10 values; the reference's defaults (camera_matrix.h:51-60) are
+        (0, 2000, 0, 2000, 0, 1280, 0, 720, -0.01, 0.01)."""
+        o = cls()
+        if b is not None:
+            o.use_bounds = 1
+            (o.fx_min, o.fx_max, o.fy_min, o.fy_max, o.cx_min, o.cx_max, o.cy_min, o.cy_max, o.skew_min, o.skew_max) = [float(t) for t in b]
+        return o
+
+
 def dptr(a):
     return a.ctypes.data_as(c_double_p) if a is not None else None
 
 
 def as_f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i64ptr(a):
+    return a.ctypes.data_as(c_int64_p) if a is not None else None
+
+
+def i32ptr(a):
+    return a.ctypes.data_as(c_int32_p) if a is not None else None
 
 
 class Problem:

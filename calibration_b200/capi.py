@@ -58,6 +58,9 @@ def lib():
         ("cal_axxb_solve", [hp, C.POINTER(abi.OptimOptions), dp, C.POINTER(abi.OptimResult), dp]),
         ("cal_ransac_homography_batch", [i64, C.c_int32, dp, dp, dp, dp, C.POINTER(abi.RansacOptions), C.c_int, C.c_int,
                                          C.POINTER(abi.RansacResult), u8p]),
+        ("cal_seed_intrinsics", [i64, abi.c_int64_p, ip, dp, dp, dp, dp, C.c_int32, C.POINTER(abi.SeedOptions), C.c_int, dp, ip,
+                                 ip, dp, dp, dp]),
+        ("cal_seed_planar_poses", [i64, abi.c_int64_p, ip, dp, dp, dp, dp, C.c_int32, dp, C.c_int, dp, ip]),
         ("cal_ransac_homography_batch_dev", [i64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(abi.RansacOptions), C.c_int, C.c_void_p, C.c_void_p,
                                              C.POINTER(C.c_float)]),
@@ -222,3 +225,34 @@ def ransac_homography_batch(x, y, u, v, opts=None, seed_per_problem=True, device
                                              int(seed_per_problem), device, res,
                                              mask.ctypes.data_as(abi.c_uint8_p) if want_mask else None))
     return res, mask
+
+
+def _views(x, y, u, v, view_offset, view_cam):
+    x, y, u, v = (abi.as_f64(a) for a in (x, y, u, v))
+    off = np.ascontiguousarray(view_offset, dtype=np.int64)
+    nv = len(off) - 1
+    cam = np.zeros(nv, dtype=np.int32) if view_cam is None else np.ascontiguousarray(view_cam, dtype=np.int32)
+    return x, y, u, v, off, cam, nv
+
+
+def seed_intrinsics(x, y, u, v, view_offset, view_cam=None, n_cams=1, bounds=None, device=0):
+    """estimate_intrinsics (linear/intrinsics.h:58-59) for every camera, batched on the GPU: Zhang's K,
+    per-view homographies, symmetric rms and poses from the homographies."""
+    x, y, u, v, off, cam, nv = _views(x, y, u, v, view_offset, view_cam)
+    opts = abi.SeedOptions.from_bounds(bounds)
+    kmtx = np.zeros((n_cams, 5)); cam_ok = np.zeros(n_cams, dtype=np.int32); ok = np.zeros(nv, dtype=np.int32)
+    H = np.zeros((nv, 9)); rms = np.zeros(nv); poses = np.zeros((nv, 12))
+    _check(lib().cal_seed_intrinsics(nv, abi.i64ptr(off), abi.i32ptr(cam), abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v),
+                                     n_cams, C.byref(opts), device, abi.dptr(kmtx), abi.i32ptr(cam_ok), abi.i32ptr(ok), abi.dptr(H),
+                                     abi.dptr(rms), abi.dptr(poses)))
+    return dict(kmtx=kmtx, cam_success=cam_ok, view_success=ok, hmtx=H.reshape(nv, 3, 3), sym_rms=rms, poses=poses)
+
+
+def seed_planar_poses(x, y, u, v, view_offset, kmtx, view_cam=None, device=0):
+    """estimate_planar_pose (linear/planarpose.h:34) for every view, batched on the GPU.  kmtx: (n_cams, 5)."""
+    x, y, u, v, off, cam, nv = _views(x, y, u, v, view_offset, view_cam)
+    k = abi.as_f64(np.asarray(kmtx).reshape(-1, 5))
+    poses = np.zeros((nv, 12)); ok = np.zeros(nv, dtype=np.int32)
+    _check(lib().cal_seed_planar_poses(nv, abi.i64ptr(off), abi.i32ptr(cam), abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v),
+                                       len(k), abi.dptr(k), device, abi.dptr(poses), abi.i32ptr(ok)))
+    return poses, ok

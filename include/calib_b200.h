@@ -218,6 +218,32 @@ cal_status cal_ransac_homography_batch_dev(int64_t n_problems, int32_t n, const 
                                            int seed_per_problem, cal_ransac_result* results_dev,
                                            uint8_t* inlier_mask_dev, float* ms);
 
+/* ---- linear seeding stage that feeds the refinement, batched over views.
+ * Views are given as SoA observations + CSR offsets, exactly like the residual blocks of
+ * cal_problem_desc (view k = observations [view_offset[k], view_offset[k+1]) seen by camera
+ * view_cam[k]).  The observation arrays may be host or device pointers. */
+typedef struct cal_seed_options { /* IntrinsicsEstimOptions.bounds (linear/intrinsics.h:26-30), CalibrationBounds (models/camera_matrix.h:50-72) */
+    int32_t use_bounds; /* 0: bounds = std::nullopt */
+    int32_t reserved;
+    double fx_min, fx_max, fy_min, fy_max, cx_min, cx_max, cy_min, cy_max, skew_min, skew_max;
+} cal_seed_options;
+/* estimate_intrinsics(views, opts) for every camera, homography_ransac = nullopt
+ * (src/estimation/linear/intrinsicsdlt.cpp:101-145): per-view DLT homography (h33 = 1) and
+ * symmetric_rms_px, Zhang's closed form for K (zhang.cpp:183-208), sanitize_intrinsics, and
+ * pose_from_homography (posefromhomography.cpp:12-67) per view.
+ * kmtx: [n_cams][5] = fx, fy, cx, cy, skew; cam_success[n_cams]; per view (any may be NULL):
+ * view_success, hmtx [9] row-major, sym_rms, poses [12] = R row-major then t (identity when failed). */
+cal_status cal_seed_intrinsics(int64_t n_views, const int64_t* view_offset, const int32_t* view_cam, const double* x,
+                               const double* y, const double* u, const double* v, int32_t n_cams,
+                               const cal_seed_options* opts, int device, double* kmtx, int32_t* cam_success,
+                               int32_t* view_success, double* hmtx, double* sym_rms, double* poses);
+/* estimate_planar_pose(view, CameraMatrix) for every view (src/estimation/linear/planarpose_linear.cpp:54-76
+ * with pose_from_homography_normalized :17-52); kmtx as above; identity for views with < 4 points
+ * or a failed DLT (view_success, optional, tells which). */
+cal_status cal_seed_planar_poses(int64_t n_views, const int64_t* view_offset, const int32_t* view_cam, const double* x,
+                                 const double* y, const double* u, const double* v, int32_t n_cams, const double* kmtx,
+                                 int device, double* poses, int32_t* view_success);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,11 @@ def lib():
         L.orc_ref_gauss_stream.argtypes = [C.c_uint32, C.c_int, C.c_double, i64, dp]
         L.orc_ref_homography_data.argtypes = [C.c_int, C.c_double, C.c_int, C.c_uint32, dp, dp]
         L.orc_ref_estimate_planar_pose.argtypes = [C.c_int32, dp, dp, dp, dp, dp, dp]
+        L.orc_zhang_rows.argtypes = [dp, dp]
+        L.orc_zhang_intrinsics.argtypes = [i64, dp, dp]
+        L.orc_sanitize_intrinsics.argtypes = [dp, dp]
+        L.orc_pose_from_homography.argtypes = [dp, dp, dp, dp, dp]
+        L.orc_estimate_intrinsics.argtypes = [i64, abi.c_int64_p, dp, dp, dp, dp, dp, dp, ip, dp, dp, dp]
         _lib = L
     return _lib
 
@@ -150,6 +155,45 @@ def ransac_batch(x, y, u, v, opts=None, seed_per_problem=True, threads=0):
     L.orc_ransac_homography_batch(npb, n, abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v), C.byref(opts),
                                   int(seed_per_problem), res, mask.ctypes.data_as(abi.c_uint8_p), threads)
     return res, mask
+
+
+def pose12_to_T(p):
+    T = np.eye(4); T[:3, :3] = np.asarray(p[:9]).reshape(3, 3); T[:3, 3] = p[9:12]
+    return T
+
+
+def zhang_intrinsics(hmtx):
+    """zhang_intrinsics_from_hs (zhang.cpp:183-208): (ok, K5 = fx, fy, cx, cy, skew)."""
+    H = abi.as_f64(np.asarray(hmtx).reshape(-1, 9))
+    k5 = np.zeros(5)
+    ok = lib().orc_zhang_intrinsics(len(H), abi.dptr(H), abi.dptr(k5))
+    return bool(ok), k5
+
+
+def sanitize_intrinsics(k5, bounds10):
+    k = abi.as_f64(k5).copy()
+    mod = lib().orc_sanitize_intrinsics(abi.dptr(k), abi.dptr(abi.as_f64(bounds10)))
+    return k, bool(mod)
+
+
+def pose_from_homography(k5, H):
+    """pose_from_homography (posefromhomography.cpp:12-67): (ok, T 4x4, scale, cond_check)."""
+    out = np.zeros(12); sc = np.zeros(1); cd = np.zeros(1)
+    ok = lib().orc_pose_from_homography(abi.dptr(abi.as_f64(k5)), abi.dptr(abi.as_f64(np.asarray(H).ravel())), abi.dptr(out),
+                                        abi.dptr(sc), abi.dptr(cd))
+    return bool(ok), pose12_to_T(out), float(sc[0]), float(cd[0])
+
+
+def estimate_intrinsics(x, y, u, v, view_offset, bounds10=None):
+    """estimate_intrinsics (intrinsicsdlt.cpp:101-145) of one camera, no RANSAC."""
+    x, y, u, v = (abi.as_f64(a) for a in (x, y, u, v))
+    off = np.ascontiguousarray(view_offset, dtype=np.int64)
+    nv = len(off) - 1
+    k5 = np.zeros(5); succ = np.zeros(nv, dtype=np.int32); H = np.zeros((nv, 9)); rms = np.zeros(nv); poses = np.zeros((nv, 12))
+    b = None if bounds10 is None else abi.as_f64(bounds10)
+    ok = lib().orc_estimate_intrinsics(nv, abi.i64ptr(off), abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v), abi.dptr(b),
+                                       abi.dptr(k5), abi.i32ptr(succ), abi.dptr(H), abi.dptr(rms), abi.dptr(poses))
+    return dict(success=bool(ok), kmtx=k5, view_success=succ, hmtx=H.reshape(nv, 3, 3), sym_rms=rms, poses=poses)
 
 
 def homography_dlt(x, y, u, v):
