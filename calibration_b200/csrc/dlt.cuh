@@ -49,8 +49,8 @@ __device__ bool smallest_eigvec9(const double* Gu /*45*/, double* z) {
 #pragma unroll
         for (int k = 0; k < j; ++k) s = fma(-L[j][k], L[j][k], s);
         if (!(s > 0.0)) return false;
-        const double l = sqrt(s), il = 1.0 / l;
-        L[j][j] = l;
+        const double il = rsqrt(s);  // the diagonal holds 1 / l_jj: the solves below multiply instead of dividing
+        L[j][j] = il;
 #pragma unroll
         for (int i = j + 1; i < 9; ++i) {
             double t = L[i][j];
@@ -60,21 +60,29 @@ __device__ bool smallest_eigvec9(const double* Gu /*45*/, double* z) {
         }
     }
     double w[9] = {1.0, 0.7, 0.3, -0.5, 0.9, 0.2, -0.8, 0.4, 1.0};
+    // (G + mu I)^-1 is positive definite, so the normalised iterates converge without sign flips; the
+    // iteration stops once they are stationary to rounding (a handful of steps: the smallest
+    // eigenvalue of a DLT normal matrix is separated from the next by orders of magnitude)
     for (int it = 0; it < 16; ++it) {
+        double prev[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) prev[i] = w[i];
 #pragma unroll
         for (int i = 0; i < 9; ++i) { double s = w[i];
 #pragma unroll
-            for (int k = 0; k < i; ++k) s = fma(-L[i][k], w[k], s); w[i] = s / L[i][i]; }
+            for (int k = 0; k < i; ++k) s = fma(-L[i][k], w[k], s); w[i] = s * L[i][i]; }
 #pragma unroll
         for (int i = 8; i >= 0; --i) { double s = w[i];
 #pragma unroll
-            for (int k = i + 1; k < 9; ++k) s = fma(-L[k][i], w[k], s); w[i] = s / L[i][i]; }
+            for (int k = i + 1; k < 9; ++k) s = fma(-L[k][i], w[k], s); w[i] = s * L[i][i]; }
         double n2 = 0;
 #pragma unroll
         for (int i = 0; i < 9; ++i) n2 = fma(w[i], w[i], n2);
         const double in = rsqrt(n2);
+        double d = 0.0;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) w[i] *= in;
+        for (int i = 0; i < 9; ++i) { w[i] *= in; d = fmax(d, fabs(w[i] - prev[i])); }
+        if (d < 4e-16) break;
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) z[i] = w[i];
