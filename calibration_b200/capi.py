@@ -53,6 +53,8 @@ def lib():
     L.cal_refine_attach_comm.argtypes = [hp, hp]
     for name, argt in (
         ("cal_axxb_create", [C.POINTER(abi.AxxbDesc), C.c_int, C.POINTER(hp)]),
+        ("cal_axxb_create_from_poses", [i64, dp, dp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(hp),
+                                        C.POINTER(i64)]),
         ("cal_axxb_destroy", [hp]),
         ("cal_axxb_eval", [hp, dp, dp, dp, dp]),
         ("cal_axxb_solve", [hp, C.POINTER(abi.OptimOptions), dp, C.POINTER(abi.OptimResult), dp]),
@@ -189,6 +191,26 @@ class AxxbHandle:
         self.desc = d
         self._h = C.c_void_p()
         _check(lib().cal_axxb_create(C.byref(d), device, C.byref(self._h)))
+
+    @classmethod
+    def from_poses(cls, base_se3_gripper, cam_se3_target, huber_delta=1.0, min_angle_deg=0.5, reject_axis_parallel=True,
+                   axis_parallel_eps=1e-3, device=0):
+        """optimize_handeye's inputs as they are (lists of 4x4 poses): build_all_pairs runs on the GPU and the
+        motion pairs are formed on the fly in every pass."""
+        def pack(poses):
+            P = np.asarray(poses, dtype=np.float64)
+            return abi.as_f64(np.concatenate([P[:, :3, :3].reshape(len(P), 9), P[:, :3, 3]], axis=1))
+        self = cls.__new__(cls)
+        g, c = pack(base_se3_gripper), pack(cam_se3_target)
+        if len(g) != len(c):
+            raise RuntimeError("Inconsistent hand-eye input sizes")   # handeyedlt.cpp:56-58
+        self._keep = [g, c]
+        self._h = C.c_void_p()
+        kept = C.c_int64()
+        _check(lib().cal_axxb_create_from_poses(len(g), abi.dptr(g), abi.dptr(c), min_angle_deg, int(reject_axis_parallel),
+                                                axis_parallel_eps, huber_delta, device, C.byref(self._h), C.byref(kept)))
+        self.n_pairs = kept.value
+        return self
 
     def close(self):
         if self._h:

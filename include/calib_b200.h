@@ -176,6 +176,15 @@ typedef struct cal_axxb_desc {
 } cal_axxb_desc;
 typedef struct cal_axxb_handle cal_axxb_handle;
 cal_status cal_axxb_create(const cal_axxb_desc* desc, int device, cal_axxb_handle** out);
+/* The same problem straight from the poses, as optimize_handeye(base_se3_gripper, camera_se3_target, ..)
+ * receives them ([n_poses][12] = R row-major then t, host or device memory): build_all_pairs
+ * (src/estimation/linear/handeyedlt.cpp:51-81; optimize_handeye uses min_angle_deg = 0.5,
+ * reject_axis_parallel = true, axis_parallel_eps = 1e-3) runs on the device and the n (n - 1) / 2
+ * motion pairs are formed on the fly in every pass instead of being materialised (192 B each).
+ * CAL_ERR_RUNTIME mirrors the std::runtime_error of inconsistent sizes / no valid pair. */
+cal_status cal_axxb_create_from_poses(int64_t n_poses, const double* base_se3_gripper, const double* cam_se3_target,
+                                      double min_angle_deg, int reject_axis_parallel, double axis_parallel_eps,
+                                      double huber_delta, int device, cal_axxb_handle** out, int64_t* n_pairs_kept);
 void cal_axxb_destroy(cal_axxb_handle* h);
 cal_status cal_axxb_eval(cal_axxb_handle* h, const double* x7, double* cost, double* g6, double* H36);
 cal_status cal_axxb_solve(cal_axxb_handle* h, const cal_optim_options* opts, double* x7_inout,

@@ -141,6 +141,60 @@ def test_axxb_noisy_pairs_at_scale():
     assert r_g.success and np.abs(x_g - x_o).max() <= 1e-8
 
 
+def test_axxb_pairs_on_the_fly_match_materialised_pairs():
+    """cal_axxb_create_from_poses: build_all_pairs (handeyedlt.cpp:51-81) on the device, pairs formed in every pass.
+    Same kept-pair count as the oracle's build_all_pairs, same normal equations and the same solution."""
+    bg, ct, X_gt, X0 = handeye_reference_scenario()
+    # a stationary robot step and a pure translation: is_good_pair must drop their pairs like the reference
+    bg = bg + [bg[-1].copy(), bg[3] @ G.make_pose([0.05, 0.0, 0.01])]
+    ct = ct + [ct[-1].copy(), G.inv_pose(X_gt) @ G.inv_pose(bg[-1]) @ (bg[3] @ X_gt @ ct[3])]
+    ra, rb, ta, tb = O.build_all_pairs(bg, ct, 0.5)
+    n_all = len(bg) * (len(bg) - 1) // 2
+    assert 100 < len(ta) < n_all
+    x0 = G.pack_handeye(X0)
+    h = capi.AxxbHandle.from_poses(bg, ct, 1.0)
+    assert h.n_pairs == len(ta)
+    d = O.axxb_desc(ra, rb, ta, tb, 1.0)
+    c_o, g_o, H_o = O.axxb_eval(d, x0)
+    c_g, g_g, H_g = h.eval(x0)
+    assert abs(c_g - c_o) <= 1e-12 * c_o
+    assert np.abs(g_g - g_o).max() <= 1e-10 * np.abs(g_o).max() and np.abs(H_g - H_o).max() <= 1e-10 * np.abs(H_o).max()
+    opts = abi.OptimOptions.default(max_iterations=60)
+    x_o, r_o, cov_o = O.axxb_solve(d, x0, opts)
+    x_g, r_g, cov_g = h.solve(x0, opts)
+    h.close()
+    assert r_g.success == r_o.success and np.abs(x_g - x_o).max() <= 1e-8
+    assert np.abs(cov_g - cov_o).max() <= 1e-6 * np.abs(cov_o).max()
+
+
+def test_axxb_pairs_on_the_fly_at_scale():
+    """1000 noisy poses (499 500 candidate pairs, several tiles incl. ragged edge tiles) against the materialised path."""
+    bg, ct, X_gt = synth.make_handeye_poses(seed=3, n=1000)
+    rng = np.random.default_rng(0)
+    ct = [synth.perturb_pose(rng, T, 0.3, 0.002) for T in ct]
+    ra, rb, ta, tb = O.build_all_pairs(bg, ct, 0.5)
+    x0 = G.pack_handeye(synth.perturb_pose(rng, X_gt, 2.0, 0.01))
+    hm = capi.AxxbHandle(ra, rb, ta, tb, 0.05)
+    hf = capi.AxxbHandle.from_poses(bg, ct, 0.05)
+    assert hf.n_pairs == len(ta)
+    c_m, g_m, H_m = hm.eval(x0)
+    c_f, g_f, H_f = hf.eval(x0)
+    assert abs(c_f - c_m) <= 1e-11 * c_m and np.abs(g_f - g_m).max() <= 1e-9 * np.abs(g_m).max() and np.abs(H_f - H_m).max() <= 1e-9 * np.abs(H_m).max()
+    c2, g2, H2 = hf.eval(x0)
+    assert c2 == c_f and np.array_equal(g2, g_f) and np.array_equal(H2, H_f)   # deterministic
+    x_m, r_m, _ = hm.solve(x0); x_f, r_f, _ = hf.solve(x0)
+    hm.close(); hf.close()
+    assert r_f.success and np.abs(x_f - x_m).max() <= 1e-9
+
+
+def test_axxb_from_poses_errors_mirror_reference():
+    I = [np.eye(4)] * 5
+    with pytest.raises(RuntimeError, match="No valid motion pairs"):     # handeyedlt.cpp:76-79
+        capi.AxxbHandle.from_poses(I, I)
+    with pytest.raises(RuntimeError, match="Inconsistent hand-eye input sizes"):   # handeyedlt.cpp:56-58
+        capi.AxxbHandle.from_poses(I[:1], I[:1])
+
+
 def test_axxb_no_pairs_is_runtime_error():
     with pytest.raises(RuntimeError, match="No valid motion pairs"):
         capi.AxxbHandle(np.zeros((0, 9)), np.zeros((0, 9)), np.zeros((0, 3)), np.zeros((0, 3)))

@@ -34,6 +34,23 @@ if what == "ransac":
         k = 2000
         t0 = time.perf_counter(); O.ransac_batch(x[:k], y[:k], u[:k], v[:k], opts); dt = time.perf_counter() - t0
         print(json.dumps({"cpu_oracle_problems_per_s": k / dt, "cores": os.cpu_count(), "sample": k}))
+elif what == "axxb_otf":
+    # optimize_handeye at C4 scale straight from the poses: pairs formed on the fly (cal_axxb_create_from_poses)
+    from calibration_b200 import geometry as G
+    n_poses = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
+    bg, ct, X_gt = synth.make_handeye_poses(seed=3, n=n_poses)
+    rng = np.random.default_rng(0)
+    ct = [synth.perturb_pose(rng, T, 0.3, 0.002) for T in ct]
+    t0 = time.perf_counter(); h = capi.AxxbHandle.from_poses(bg, ct, 0.05); create = time.perf_counter() - t0
+    x0 = G.pack_handeye(synth.perturb_pose(rng, X_gt, 2.0, 0.01))
+    h.eval(x0)
+    t0 = time.perf_counter()
+    for _ in range(5): h.eval(x0)
+    dt = (time.perf_counter() - t0) / 5
+    t0 = time.perf_counter(); xs, res, cov = h.solve(x0); ts = time.perf_counter() - t0
+    print(json.dumps({"kernel": "k_axxb_otf", "poses": n_poses, "pairs_kept": h.n_pairs, "eval_ms_incl_sync": dt * 1e3,
+                      "pairs_per_s": h.n_pairs / dt, "create_s": create, "solve_s": ts, "report": res.report.decode(),
+                      "param_err": float(np.abs(xs - G.pack_handeye(X_gt)).max())}))
 else:
     import oracle_lib as O
     n_poses = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
