@@ -141,6 +141,13 @@ class SeedOptions(C.Structure):
         return o
 
 
+class Dataset(C.Structure):
+    """cal_dataset: columnar observation store (mmap-ed)."""
+    _fields_ = [("n_views", C.c_int64), ("n_obs", C.c_int64), ("n_cams", C.c_int32), ("pinned", C.c_int32),
+                ("view_offset", c_int64_p), ("view_cam", c_int32_p), ("obj_x", c_double_p), ("obj_y", c_double_p),
+                ("img_u", c_double_p), ("img_v", c_double_p), ("impl", C.c_void_p)]
+
+
 def dptr(a):
     return a.ctypes.data_as(c_double_p) if a is not None else None
 

@@ -41,6 +41,7 @@ def lib():
     L.cal_refine_tangent_count.argtypes = [hp]
     L.cal_refine_eval.argtypes = [hp, dp, dp, dp, dp]
     L.cal_refine_cost.argtypes = [hp, dp, dp, dp]
+    L.cal_refine_view_errors.argtypes = [hp, dp, dp, dp]
     L.cal_refine_bench_pass.argtypes = [hp, dp, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), dp]
     L.cal_refine_launch_count.restype = i64
     L.cal_refine_launch_count.argtypes = [hp]
@@ -63,6 +64,10 @@ def lib():
         ("cal_seed_intrinsics", [i64, abi.c_int64_p, ip, dp, dp, dp, dp, C.c_int32, C.POINTER(abi.SeedOptions), C.c_int, dp, ip,
                                  ip, dp, dp, dp]),
         ("cal_seed_planar_poses", [i64, abi.c_int64_p, ip, dp, dp, dp, dp, C.c_int32, dp, C.c_int, dp, ip]),
+        ("cal_dataset_write", [C.c_char_p, i64, C.c_int32, abi.c_int64_p, ip, dp, dp, dp, dp]),
+        ("cal_dataset_open", [C.c_char_p, C.c_int, C.POINTER(abi.Dataset)]),
+        ("cal_dataset_close", [C.POINTER(abi.Dataset)]),
+        ("cal_dataset_from_planar_json", [C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]),
         ("cal_ransac_homography_batch_dev", [i64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(abi.RansacOptions), C.c_int, C.c_void_p, C.c_void_p,
                                              C.POINTER(C.c_float)]),
@@ -140,6 +145,12 @@ class RefineHandle:
 
     def launch_count(self):
         return int(lib().cal_refine_launch_count(self._h))
+
+    def view_errors(self, x):
+        """(per-block RMS reprojection error in px, global RMS) at x."""
+        rms = np.zeros(int(self.problem.desc.n_blocks)); g = C.c_double()
+        _check(lib().cal_refine_view_errors(self._h, abi.dptr(abi.as_f64(x)), abi.dptr(rms), C.cast(C.byref(g), abi.c_double_p)))
+        return rms, g.value
 
     def layout_info(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64(); d, e = C.c_int32(), C.c_int32()
@@ -278,3 +289,45 @@ def seed_planar_poses(x, y, u, v, view_offset, kmtx, view_cam=None, device=0):
     _check(lib().cal_seed_planar_poses(nv, abi.i64ptr(off), abi.i32ptr(cam), abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v),
                                        len(k), abi.dptr(k), device, abi.dptr(poses), abi.i32ptr(ok)))
     return poses, ok
+
+
+class Dataset:
+    """Columnar observation store (cal_dataset_*): numpy views straight onto the read-only mapping."""
+
+    def __init__(self, path, pin=False):
+        self._d = abi.Dataset()
+        _check(lib().cal_dataset_open(os.fsencode(path), int(pin), C.byref(self._d)))
+        d = self._d
+        self.n_views, self.n_obs, self.n_cams, self.pinned = int(d.n_views), int(d.n_obs), int(d.n_cams), bool(d.pinned)
+        as_np = lambda p, n, dt: np.ctypeslib.as_array(p, shape=(n,)) if n else np.zeros(0, dtype=dt)
+        self.view_offset = as_np(d.view_offset, self.n_views + 1, np.int64)
+        self.view_cam = as_np(d.view_cam, self.n_views, np.int32)
+        self.x, self.y = as_np(d.obj_x, self.n_obs, np.float64), as_np(d.obj_y, self.n_obs, np.float64)
+        self.u, self.v = as_np(d.img_u, self.n_obs, np.float64), as_np(d.img_v, self.n_obs, np.float64)
+
+    def close(self):
+        if self._d.impl:
+            self.view_offset = self.view_cam = self.x = self.y = self.u = self.v = None
+            lib().cal_dataset_close(C.byref(self._d))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @staticmethod
+    def write(path, view_offset, view_cam, x, y, u, v, n_cams=None):
+        off = np.ascontiguousarray(view_offset, dtype=np.int64); cam = np.ascontiguousarray(view_cam, dtype=np.int32)
+        x, y, u, v = (abi.as_f64(a) for a in (x, y, u, v))
+        n_cams = int(cam.max()) + 1 if n_cams is None else n_cams
+        _check(lib().cal_dataset_write(os.fsencode(path), len(off) - 1, n_cams, abi.i64ptr(off), abi.i32ptr(cam), abi.dptr(x), abi.dptr(y),
+                                       abi.dptr(u), abi.dptr(v)))
+
+    @staticmethod
+    def from_planar_json(json_paths, out_path, min_corners_per_view=0):
+        """One PlanarDetections JSON per camera (the reference's dataset schema) -> columnar file; returns (n_views, n_obs)."""
+        arr = (C.c_char_p * len(json_paths))(*[os.fsencode(p) for p in json_paths])
+        nv, no = C.c_int64(), C.c_int64()
+        _check(lib().cal_dataset_from_planar_json(arr, len(json_paths), int(min_corners_per_view), os.fsencode(out_path), C.byref(nv), C.byref(no)))
+        return nv.value, no.value

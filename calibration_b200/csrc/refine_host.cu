@@ -89,6 +89,7 @@ struct cal_refine_handle {
     int n_syrk_cta = 1;
     std::vector<int64_t> blk_orig_host;   // device block -> original block
     std::vector<int32_t> blk_cam_host, blk_view_host;
+    std::vector<int32_t> blk_len_host;    // observations per ORIGINAL residual block
     std::vector<char> view_free_host;
     std::vector<int32_t> view_blk_off_host, view_blk_idx_host;
     // host mirrors of the last Jacobian evaluation (shared block)
@@ -288,6 +289,8 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     }
     const int64_t nblk = (int64_t)borig.size();
     h.L.n_blk = nblk;
+    h.blk_len_host.resize(d.n_blocks);
+    for (int64_t b = 0; b < d.n_blocks; ++b) h.blk_len_host[b] = (int32_t)(d.block_offset[b + 1] - d.block_offset[b]);
     // ---- segments ----
     int64_t max_len = 0;
     for (int64_t b = 0; b < d.n_blocks; ++b) max_len = std::max<int64_t>(max_len, d.block_offset[b + 1] - d.block_offset[b]);
@@ -665,6 +668,30 @@ extern "C" cal_status cal_refine_cost(cal_refine_handle* h, const double* x, dou
         CUDA_TRY(cudaMemcpy(tmp.data(), h->B.blk_ssr, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
         for (int64_t b = 0; b < h->L.n_blk; ++b) if (h->blk_orig_host[b] >= 0) block_ssr[h->blk_orig_host[b]] = tmp[b];
     }
+    return CAL_OK;
+}
+
+// Per-view diagnostics after a solve: view_errors as compute_per_view_errors fills
+// them (src/estimation/optim/intrinsicssemidlt.cpp:137-151: sqrt(sum r^2 / (2 points)) per view) and the
+// global RMS of src/pipeline/reports/intrinsics.cpp:12-31, from one residual-only pass on the device.
+extern "C" cal_status cal_refine_view_errors(cal_refine_handle* h, const double* x, double* block_rms, double* global_rms) {
+    if (!h || !x) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(h->B.x, x, sizeof(double) * h->n_amb, cudaMemcpyHostToDevice, h->st));
+    if (cal_status s = device_pass(*h, h->B.x, false, x)) return s;
+    std::vector<double> ssr(h->L.n_blk);
+    std::vector<int32_t> len(h->L.n_blk + 1);
+    CUDA_TRY(cudaMemcpy(ssr.data(), h->B.blk_ssr, ssr.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    double sum_sq = 0.0, meas = 0.0;
+    for (int64_t b = 0; b < h->L.n_blk; ++b) {
+        const int64_t o = h->blk_orig_host[b];
+        if (o < 0) continue;
+        const double m = 2.0 * (double)h->blk_len_host[o];
+        const double rms = m > 0 ? std::sqrt(ssr[b] / m) : 0.0;
+        if (block_rms) block_rms[o] = rms;
+        sum_sq += rms * rms * m; meas += m;
+    }
+    if (global_rms) *global_rms = meas > 0 ? std::sqrt(sum_sq / meas) : 0.0;
     return CAL_OK;
 }
 

@@ -143,6 +143,11 @@ cal_status cal_refine_layout_info(const cal_refine_handle* h, int64_t* n_segment
 /* sustained FP64 FMA rate of the device (FMA-chain microbenchmark), TFLOP/s */
 cal_status cal_fp64_peak_tflops(int device, double* tflops);
 
+/* Per-view reprojection diagnostics at x: block_rms[b] = sqrt(sum r^2 / (2 points)) of residual block b
+ * (view_errors, src/estimation/optim/intrinsicssemidlt.cpp:137-151) and the measurement-weighted global
+ * RMS (src/pipeline/reports/intrinsics.cpp:12-31).  One residual-only pass; either output may be NULL. */
+cal_status cal_refine_view_errors(cal_refine_handle* h, const double* x, double* block_rms, double* global_rms);
+
 /* Replaces solve_problem (detail/ceresutils.h:27-43) + compute_covariance
  * (detail/ceresutils.h:69-126): Levenberg–Marquardt with Ceres 2.2 semantics
  * on the host, every O(observations) pass on the device.  x is updated in
@@ -252,6 +257,34 @@ cal_status cal_seed_intrinsics(int64_t n_views, const int64_t* view_offset, cons
 cal_status cal_seed_planar_poses(int64_t n_views, const int64_t* view_offset, const int32_t* view_cam, const double* x,
                                  const double* y, const double* u, const double* v, int32_t n_cams, const double* kmtx,
                                  int device, double* poses, int32_t* view_success);
+
+/* ---- columnar observation store: the SoA + CSR arrays of cal_problem_desc / cal_seed_*
+ * in one file, mmap-ed read-only (zero parsing, zero copies before the H2D transfer), and a streaming
+ * converter from the reference's PlanarDetections JSON (schemas/calib_dataset.schema.json,
+ * include/calib/pipeline/dataset.h:15-39) that replaces the nlohmann DOM + collect_planar_views /
+ * make_planar_view packing (src/pipeline/facades/intrinsics.cpp:38-59, detail/planar_utils.cpp:45-52). */
+typedef struct cal_dataset {
+    int64_t n_views;
+    int64_t n_obs;
+    int32_t n_cams;
+    int32_t pinned;             /* the mapping is page-locked (cudaHostRegister) */
+    const int64_t* view_offset; /* [n_views + 1] */
+    const int32_t* view_cam;    /* [n_views] */
+    const double* obj_x;        /* local_x */
+    const double* obj_y;        /* local_y */
+    const double* img_u;        /* x (pixels) */
+    const double* img_v;        /* y (pixels) */
+    void* impl;
+} cal_dataset;
+cal_status cal_dataset_write(const char* path, int64_t n_views, int32_t n_cams, const int64_t* view_offset,
+                             const int32_t* view_cam, const double* x, const double* y, const double* u, const double* v);
+cal_status cal_dataset_open(const char* path, int pin, cal_dataset* out);
+void cal_dataset_close(cal_dataset* d);
+/* One PlanarDetections JSON document per camera -> one columnar file.  Images with fewer than
+ * min_corners_per_view points are dropped (collect_planar_views, facades/intrinsics.cpp:45-47).
+ * CAL_ERR_INVALID_ARGUMENT with the byte offset for malformed documents. */
+cal_status cal_dataset_from_planar_json(const char* const* json_paths, int32_t n_cams, int32_t min_corners_per_view,
+                                        const char* out_path, int64_t* n_views_out, int64_t* n_obs_out);
 
 #ifdef __cplusplus
 }

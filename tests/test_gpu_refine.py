@@ -136,6 +136,19 @@ def test_block_ssr_matches():
     assert relerr(ssr, O.block_ssr(prob, x0)) <= 1e-12
 
 
+def test_view_errors_match_oracle(k1_layout):
+    prob, x0 = ragged_bundle()
+    h = capi.RefineHandle(prob)
+    try:
+        rms, g = h.view_errors(x0)
+    finally:
+        h.close()
+    ssr = O.block_ssr(prob, x0)
+    n = np.diff(np.asarray(prob.block_offset))
+    assert relerr(rms, np.sqrt(ssr / (2.0 * n))) <= 1e-12
+    assert abs(g - np.sqrt(ssr.sum() / (2.0 * n.sum()))) <= 1e-12 * g
+
+
 # ---- the reference's own tests through the CUDA path, with its tolerances ----
 @pytest.mark.parametrize("skew", [False, True])
 def test_reference_intrinsics_recovery(skew):

@@ -110,3 +110,33 @@ def test_device_resident_inputs_and_scale():
     k_gt = xgt[:80].reshape(8, 10)[:, :5]
     assert np.abs(host["kmtx"][:, :4] / k_gt[:, :4] - 1).max() < 0.05   # distortion + 0.2 px noise: a seed, not the answer
     assert (host["poses"][:, 11] > 0).all()
+
+
+def test_json_to_calibration_chain(tmp_path):
+    """The callers' path end to end (facades/intrinsics.cpp:80-135): PlanarDetections JSON -> columnar store ->
+    estimate_intrinsics on the GPU -> optimize_intrinsics on the GPU.  Noise-free views of a distortion-free
+    camera: the linear seed is already exact to 1e-6 and the refinement keeps it there (intrinsics_optimize_test
+    tolerances)."""
+    import json
+    from calibration_b200 import geometry as G
+    intr, c_se3_t, (xs, ys, us, vs, off) = intrinsics_estimate_scenario(n_frames=12, rows=7, cols=10)
+    doc = {"sensor_id": "cam0", "images": [
+        {"file": f"v{k}.png", "points": [{"x": float(us[i]), "y": float(vs[i]), "local_x": float(xs[i]), "local_y": float(ys[i])}
+                                         for i in range(off[k], off[k + 1])]} for k in range(len(off) - 1)]}
+    (tmp_path / "cam0.json").write_text(json.dumps(doc))
+    nv, no = capi.Dataset.from_planar_json([str(tmp_path / "cam0.json")], str(tmp_path / "obs.calobs"), min_corners_per_view=8)
+    assert (nv, no) == (int((np.diff(off) >= 8).sum()), len(xs))   # views the board left are dropped (collect_planar_views)
+    with capi.Dataset(str(tmp_path / "obs.calobs"), pin=True) as ds:
+        seed = capi.seed_intrinsics(ds.x, ds.y, ds.u, ds.v, ds.view_offset, view_cam=ds.view_cam, n_cams=ds.n_cams)
+        assert seed["cam_success"][0] and np.abs(seed["kmtx"][0, :4] - intr[:4]).max() < 1e-6
+        prob = abi.Problem(abi.KIND_INTRINSICS, abi.MODEL_PINHOLE_BC5, 1, ds.n_views, ds.x, ds.y, ds.u, ds.v, ds.view_offset,
+                           np.zeros(ds.n_views, dtype=np.int32), huber_delta=1.0)
+        intr0 = np.concatenate([seed["kmtx"][0], np.zeros(5)])
+        x0 = G.pack_intrinsics(intr0, [O.pose12_to_T(p) for p in seed["poses"]])
+        h = capi.RefineHandle(prob)
+        try:
+            x, res, _ = h.solve(x0)
+            rms, g = h.view_errors(x)
+        finally:
+            h.close()
+    assert res.success and np.abs(x[:4] - intr[:4]).max() < 1e-6 and np.abs(x[5:10]).max() < 1e-5 and g < 1e-6
