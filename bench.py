@@ -35,6 +35,23 @@ WORKLOADS = {
 CHUNK = 12500  # robot poses per generation chunk (8 chunks for c5)
 
 
+def k1_traffic_bytes(args, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch from the committed `ncu --set full` capture of this
+    very command (profiles/r1_k1_fused_ncu_full_bench_c5.csv: C5, one GPU, free intrinsics); None for any other shape."""
+    if args.workload != "c5" or world != 1 or args.fixed_intrinsics:
+        return None
+    path = os.path.join(ROOT, "profiles", "r1_k1_fused_ncu_full_bench_c5.csv")
+    if not os.path.exists(path):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for line in open(path):
+        parts = line.strip().split(",")
+        if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(parts[2]) * scale[parts[1]]
+    return tot or None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -211,7 +228,8 @@ def _run_b200(args, rank, world, local_rank):
                 "converged": bool(res.success), "max_abs_param_error_vs_ground_truth": solve_err, "gpu_launches": launches_e2e},
         "gpu_launches": launches_timed,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                     "traffic": None, "peak_source": pk_src, "kernel": "k1_kernel", "kernel_ms_per_launch": k1_ms_launch,
+                     "traffic": k1_traffic_bytes(args, world), "traffic_source": "profiles/r1_k1_fused_ncu_full_bench_c5.csv (ncu --set full of this command)",
+                     "peak_source": pk_src, "kernel": "k1_kernel", "kernel_ms_per_launch": k1_ms_launch,
                      "kernel_share_of_step": ms_k1 / ms_total,
                      "algorithmic_bytes_per_launch": obs_bytes_local,
                      "binding_roof": "fp64",

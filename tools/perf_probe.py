@@ -34,6 +34,51 @@ if what == "ransac":
         k = 2000
         t0 = time.perf_counter(); O.ransac_batch(x[:k], y[:k], u[:k], v[:k], opts); dt = time.perf_counter() - t0
         print(json.dumps({"cpu_oracle_problems_per_s": k / dt, "cores": os.cpu_count(), "sample": k}))
+elif what == "seed":
+    # seeding stage at C5 scale: estimate_intrinsics for 8 cameras x n_poses views, then estimate_planar_pose
+    n_poses = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
+    prob, _, xgt = synth.make_bundle(seed=137, n_cams=8, n_poses=n_poses)
+    off = np.asarray(prob.block_offset); cam = np.asarray(prob.block_cam)
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (prob.x, prob.y, prob.u, prob.v)]
+    nv = len(off) - 1
+    kmtx = np.zeros((8, 5)); cam_ok = np.zeros(8, dtype=np.int32); poses = np.zeros((nv, 12)); ok = np.zeros(nv, dtype=np.int32)
+    opts = abi.SeedOptions.from_bounds(None)
+    dptrs = [C.cast(C.c_void_p(d.data_ptr()), abi.c_double_p) for d in dev]
+    off64 = off.astype(np.int64); cam32 = cam.astype(np.int32)
+    L = capi.lib()
+    def run_intr():
+        rc = L.cal_seed_intrinsics(nv, abi.i64ptr(off64), abi.i32ptr(cam32), *dptrs, 8, C.byref(opts), 0, abi.dptr(kmtx), abi.i32ptr(cam_ok),
+                                   abi.i32ptr(ok), None, None, abi.dptr(poses))
+        assert rc == 0, L.cal_last_error()
+    def run_pose():
+        rc = L.cal_seed_planar_poses(nv, abi.i64ptr(off64), abi.i32ptr(cam32), *dptrs, 8, abi.dptr(kmtx), 0, abi.dptr(poses), abi.i32ptr(ok))
+        assert rc == 0, L.cal_last_error()
+    run_intr(); run_pose()
+    t0 = time.perf_counter(); run_intr(); ti = time.perf_counter() - t0
+    t0 = time.perf_counter(); run_pose(); tp = time.perf_counter() - t0
+    k_gt = xgt[:80].reshape(8, 10)[:, :5]
+    print(json.dumps({"stage": "seed", "views": nv, "observations": int(off[-1]), "estimate_intrinsics_ms": ti * 1e3,
+                      "estimate_planar_pose_ms": tp * 1e3, "views_per_s_intrinsics": nv / ti, "views_per_s_pose": nv / tp,
+                      "note": "observations resident on the device; includes D2H of 96 B/view poses and the host Zhang step",
+                      "max_rel_K_error_vs_gt": float(np.abs(kmtx[:, :4] / k_gt[:, :4] - 1).max())}))
+elif what == "solves":
+    # wall time of the full solves of the small BASELINE configs (latency-bound)
+    from calibration_b200 import geometry as G
+    capi.RefineHandle(synth.make_bundle(n_cams=2, n_poses=64)[0]).close()
+    out = {}
+    only = int(sys.argv[2]) if len(sys.argv) > 2 else -1
+    for idx, (name, mk) in enumerate((("C1 intrinsics 20 views x 54", lambda: synth.make_intrinsics()),
+                     ("C3 extrinsics 2 cams x 1000 views x 88", lambda: synth.make_extrinsics(n_cams=2, n_views=1000)),
+                     ("C4 bundle 4 cams x 5000 poses x 88", lambda: synth.make_bundle(n_cams=4, n_poses=5000)))):
+        if only >= 0 and idx != only:
+            continue
+        prob, x0, _ = mk()
+        print("running", name, flush=True)
+        h = capi.RefineHandle(prob); h.solve(x0); h.close()
+        t0 = time.perf_counter(); h = capi.RefineHandle(prob); t1 = time.perf_counter(); x, res, cov = h.solve(x0); t2 = time.perf_counter(); h.close()
+        out[name] = {"create_ms": 1e3 * (t1 - t0), "solve_ms": 1e3 * (t2 - t1), "iterations": int(res.iterations), "n_obs": int(prob.desc.n_obs),
+                     "ms_per_iteration": 1e3 * (t2 - t1) / max(int(res.iterations), 1)}
+    print(json.dumps(out))
 elif what == "axxb_otf":
     # optimize_handeye at C4 scale straight from the poses: pairs formed on the fly (cal_axxb_create_from_poses)
     from calibration_b200 import geometry as G
