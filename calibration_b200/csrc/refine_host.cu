@@ -960,8 +960,83 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
         if ((double)na * na * 8.0 > 8e9) return CAL_OK;  // would not fit; covariance_ok stays 0
         // the normal equations of the last accepted point are still on the device / host mirrors
         std::vector<double> xf(x_inout, x_inout + na);
-        EvalBuffers Bf = h.B; (void)Bf;
         if (cal_status st = device_pass(h, h.B.x, true, xf.data())) return st;
+        if (views && !h.comm) {
+            // ---- block-structured covariance (refine_kernels.cu, k_cov_*): shared block on the host, view blocks on the device ----
+            CUDA_TRY(cudaMemsetAsync(V.fail, 0, sizeof(int32_t), h.st));
+            launch_schur(S, h.L, h.B, V, ns, std::numeric_limits<double>::infinity(), h.st); h.launches += 3;
+            int32_t failed = 0;
+            CUDA_TRY(cudaMemcpyAsync(Cs.data(), V.C, sizeof(double) * ns * ns, cudaMemcpyDeviceToHost, h.st));
+            CUDA_TRY(cudaMemcpyAsync(&failed, V.fail, sizeof failed, cudaMemcpyDeviceToHost, h.st));
+            CUDA_TRY(cudaStreamSynchronize(h.st));
+            if (failed) return CAL_OK;  // a rank-deficient view block: covariance stays empty (ceresutils.h:86-88)
+            for (int i = 0; i < ns; ++i) for (int j = 0; j < ns; ++j) Sm[(size_t)i * ns + j] = h.Hss[(size_t)i * ns + j] * s[i] * s[j] - Cs[(size_t)i * ns + j];
+            if (ns > 0 && !chol_host(Sm, ns)) return CAL_OK;
+            std::vector<double> W((size_t)ns * ns), e(std::max(ns, 1));
+            for (int j = 0; j < ns; ++j) { std::fill(e.begin(), e.end(), 0.0); e[j] = 1.0; chol_solve_host(Sm, ns, e.data()); for (int i = 0; i < ns; ++i) W[(size_t)i * ns + j] = e[i]; }
+            double *dW = nullptr, *dZ = nullptr, *dG = nullptr, *dAinv = nullptr, *dcov = nullptr;
+            struct Free { std::vector<double**> p; ~Free() { for (auto q : p) cudaFree(*q); } } guard{{&dW, &dZ, &dG, &dAinv, &dcov}};
+            CUDA_TRY(dev_alloc(&dW, (size_t)ns * ns)); CUDA_TRY(dev_alloc(&dZ, (size_t)nv * 6 * ns)); CUDA_TRY(dev_alloc(&dG, (size_t)nv * 6 * ns));
+            CUDA_TRY(dev_alloc(&dAinv, (size_t)nv * 36)); CUDA_TRY(dev_alloc(&dcov, (size_t)na * na));
+            CUDA_TRY(cudaMemcpyAsync(dW, W.data(), sizeof(double) * ns * ns, cudaMemcpyHostToDevice, h.st));
+            CUDA_TRY(cudaMemsetAsync(dcov, 0, sizeof(double) * na * na, h.st));
+            CUDA_TRY(cudaMemsetAsync(dG, 0, sizeof(double) * nv * 6 * ns, h.st));
+            launch_cov_views(S, h.L, V, h.B.x, ns, dW, dZ, dG, dAinv, dcov, na, h.st); h.launches += 2;
+            std::vector<double> Gh((size_t)nv * 6 * ns), sph((size_t)nv * 6);
+            CUDA_TRY(cudaMemcpyAsync(cov, dcov, sizeof(double) * na * na, cudaMemcpyDeviceToHost, h.st));
+            CUDA_TRY(cudaMemcpyAsync(Gh.data(), dG, Gh.size() * sizeof(double), cudaMemcpyDeviceToHost, h.st));
+            CUDA_TRY(cudaMemcpyAsync(sph.data(), V.sp, sph.size() * sizeof(double), cudaMemcpyDeviceToHost, h.st));
+            CUDA_TRY(cudaStreamSynchronize(h.st));
+            CUDA_TRY(cudaGetLastError());
+            // plus-Jacobians of the shared blocks
+            const int n_shared_pb = h.pb_viewq(0);
+            std::vector<std::vector<double>> Pj(n_shared_pb);
+            for (int bi = 0; bi < n_shared_pb; ++bi) {
+                const PB& pb = h.pbs[bi]; if (pb.constant) continue;
+                std::vector<double>& Pm = Pj[bi]; Pm.assign((size_t)pb.size * pb.tsize, 0.0);
+                if (pb.type == PB_QUAT) quat_plus_jacobian(xf.data() + pb.off, Pm.data());
+                else if (pb.type == PB_INTR && pb.tsize == pb.size - 1) { int k = 0; for (int j = 0; j < pb.size; ++j) { if (j == 4) continue; Pm[(size_t)j * pb.tsize + k] = 1.0; ++k; } }
+                else for (int j = 0; j < pb.size; ++j) Pm[(size_t)j * pb.tsize + j] = 1.0;
+            }
+            for (int bi = 0; bi < n_shared_pb; ++bi) {
+                const PB& a = h.pbs[bi]; if (a.constant) continue;
+                // shared x shared: P_a (s s^T o W) P_b^T
+                for (int bj = 0; bj < n_shared_pb; ++bj) {
+                    const PB& b = h.pbs[bj]; if (b.constant) continue;
+                    for (int i = 0; i < a.size; ++i) for (int j = 0; j < b.size; ++j) {
+                        double acc = 0;
+                        for (int k = 0; k < a.tsize; ++k) { const double pik = Pj[bi][(size_t)i * a.tsize + k]; if (pik == 0.0) continue;
+                            for (int l = 0; l < b.tsize; ++l) acc += pik * s[a.toff + k] * s[b.toff + l] * W[(size_t)(a.toff + k) * ns + b.toff + l] * Pj[bj][(size_t)j * b.tsize + l]; }
+                        cov[(size_t)(a.off + i) * na + b.off + j] = acc;
+                    }
+                }
+                // shared x view: C_sv = -(Z_v W)^T, scaled and lifted on both sides
+                for (int v = 0; v < nv; ++v) {
+                    if (!h.view_free_host[v]) continue;
+                    const double* q = xf.data() + S.off_viewq + 4 * (size_t)v;
+                    double Pq[12]; quat_plus_jacobian(q, Pq);
+                    double LA[12][6];
+                    for (int i = 0; i < a.size; ++i) for (int m = 0; m < 6; ++m) {
+                        double acc = 0;
+                        for (int k = 0; k < a.tsize; ++k) acc -= Pj[bi][(size_t)i * a.tsize + k] * s[a.toff + k] * sph[(size_t)v * 6 + m] * Gh[((size_t)v * 6 + m) * ns + a.toff + k];
+                        LA[i][m] = acc;
+                    }
+                    for (int i = 0; i < a.size; ++i) {
+                        for (int bq = 0; bq < 4; ++bq) {
+                            const double val = LA[i][0] * Pq[3 * bq] + LA[i][1] * Pq[3 * bq + 1] + LA[i][2] * Pq[3 * bq + 2];
+                            cov[(size_t)(a.off + i) * na + S.off_viewq + 4 * (size_t)v + bq] = val;
+                            cov[(size_t)(S.off_viewq + 4 * (size_t)v + bq) * na + a.off + i] = val;
+                        }
+                        for (int bt = 0; bt < 3; ++bt) {
+                            cov[(size_t)(a.off + i) * na + S.off_viewt + 3 * (size_t)v + bt] = LA[i][3 + bt];
+                            cov[(size_t)(S.off_viewt + 3 * (size_t)v + bt) * na + a.off + i] = LA[i][3 + bt];
+                        }
+                    }
+                }
+            }
+            res->covariance_ok = 1;
+            return CAL_OK;
+        }
         std::vector<double> Hd, gd;
         if (n > 8192) return CAL_OK;
         if (cal_status st = dense_system(h, Hd, gd)) return st;

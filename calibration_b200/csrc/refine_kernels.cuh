@@ -137,5 +137,9 @@ void launch_backsub(const ProblemShape& S, const DevLayout& L, const ViewBuffers
 void launch_view_plus(const ProblemShape& S, const EvalBuffers& B, const ViewBuffers& V, double t, cudaStream_t st);
 void launch_view_norms(const ProblemShape& S, const EvalBuffers& B, const ViewBuffers& V, cudaStream_t st);
 void launch_reduce_views(const ViewBuffers& V, int n_views, cudaStream_t st);
+// block-structured covariance of the per-view kinds (after launch_schur with an infinite radius): W = inverse of the
+// reduced (scaled) shared block [ns][ns]; Z, G: [n_views][6][ns]; Ainv: [n_views][36]; cov: [na][na] zero-initialised
+void launch_cov_views(const ProblemShape& S, const DevLayout& L, const ViewBuffers& V, const double* x, int ns, const double* W,
+                      double* Z, double* G, double* Ainv, double* cov, int64_t na, cudaStream_t st);
 
 }  // namespace calk

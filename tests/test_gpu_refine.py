@@ -236,6 +236,25 @@ def test_extrinsics_schur_path_at_scale():
     assert r_o.success and relerr(x, x_o) <= 1e-8 and abs(rms_px(prob, x) - rms_px(prob, x_o)) <= 1e-10
 
 
+def test_c3_covariance_block_structured():
+    """Per-view kinds: the covariance comes from the block-structured inverse on the device (shared block S^-1,
+    view pairs A_v^-1 + Z_v S^-1 Z_w^T) — compared with the oracle's dense tangent inverse, lifted to ambient
+    coordinates in the reference's block order (ceresutils.h:90-115), incl. a constant view and camera block."""
+    for mk in (lambda: synth.make_extrinsics(n_cams=3, n_views=60, drop_fraction=0.2), lambda: synth.make_intrinsics(),
+               lambda: synth.make_extrinsics(n_views=40, optimize_intrinsics=False)):
+        prob, x0, _ = mk()
+        opts = abi.OptimOptions.default(compute_covariance=1)
+        x_o, r_o, cov_o = O.refine_solve(prob, x0, opts)
+        h = capi.RefineHandle(prob)
+        try:
+            x_g, r_g, cov_g = h.solve(x0, opts)
+        finally:
+            h.close()
+        assert r_o.covariance_ok and r_g.covariance_ok
+        assert relerr(cov_g, cov_o) <= 1e-6
+        assert np.allclose(cov_g, cov_g.T, rtol=0, atol=1e-12 * np.abs(cov_g).max())
+
+
 def test_max_iterations_reports_no_convergence():
     prob, x0, _ = synth.make_bundle(n_cams=2, n_poses=40)
     h = capi.RefineHandle(prob)
