@@ -114,8 +114,28 @@ def run_b200(args, rank, world, local_rank):
         print(json.dumps(out), flush=True)
 
 
+_STAGE = {"name": "start", "t0": time.time()}
+
+
+def stage(name, rank=0):
+    """Progress marker on stderr (one line per stage and rank) + what the watchdog reports if a stage never ends."""
+    _STAGE["name"] = name
+    sys.stderr.write(f"[bench r{rank} +{time.time() - _STAGE['t0']:.1f}s] {name}\n"); sys.stderr.flush()
+
+
+def start_watchdog(limit_s, rank):
+    """A multi-rank run must never hang the box: past the limit the process says where it was and exits non-zero."""
+    def run():
+        time.sleep(limit_s)
+        sys.stderr.write(f"[bench r{rank}] WATCHDOG: still in stage '{_STAGE['name']}' after {limit_s:.0f} s, aborting\n"); sys.stderr.flush()
+        os._exit(3)
+    threading.Thread(target=run, daemon=True).start()
+
+
 def _run_b200(args, rank, world, local_rank):
     import torch
+    start_watchdog(args.max_seconds, rank)
+    stage("import / init", rank)
     from calibration_b200 import abi, capi, synth
     dist = None
     if world > 1:
@@ -124,6 +144,7 @@ def _run_b200(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_cams, n_poses, desc = WORKLOADS[args.workload]
     chunks = shard_chunks(n_poses, rank, world)
+    stage("generate synthetic shard", rank)
     t0 = time.time()
     prob, x0, xgt = synth.make_bundle(seed=137, n_cams=n_cams, n_poses=n_poses, chunk=CHUNK, chunks=chunks, pinned=True,
                                       optimize_intrinsics=not args.fixed_intrinsics)
@@ -137,6 +158,7 @@ def _run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    stage("communicator", rank)
     comm = None
     if dist is not None:  # process-lifetime communicator, like the CUDA context: created once, outside every timed region
         uid = [capi.comm_unique_id() if rank == 0 else None]
@@ -149,8 +171,10 @@ def _run_b200(args, rank, world, local_rank):
             h.attach_comm(comm)
         return h
 
+    stage("create handle", rank)
     h = make_handle()
     info = h.layout_info()
+    stage("warm-up + timed passes", rank)
     with ClockSampler(local_rank) as clk:   # clocks are sampled under load: warm-up, timed region and the cost passes
         for _ in range(max(args.warmup, 3)):
             h.bench_pass(x0, reps=1, jacobian=True)
@@ -160,16 +184,19 @@ def _run_b200(args, rank, world, local_rank):
         launches_timed = h.launch_count() - l0
         barrier()
         ms_c, ms_ck, _ = h.bench_pass(x0, reps=args.steps, jacobian=False)
-        # keep the same kernels running ~1.5 s more so the 200 ms clock sampler sees the GPU under this load
+        t = torch.tensor([ms_total, ms_k1], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_k1 = float(t[0]), float(t[1])
+        # keep the same kernels running ~1.5 s more so the 200 ms clock sampler sees the GPU under this load; the
+        # repeat count comes from the all-reduced time, so every rank issues the same number of collectives
         h.bench_pass(x0, reps=max(args.steps, int(1500.0 / max(ms_total / args.steps, 0.05))), jacobian=True)
-    t = torch.tensor([ms_total, ms_k1], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_k1 = float(t[0]), float(t[1])
     ms_step = ms_total / args.steps
     value = n_obs_total / (ms_step * 1e-3)
 
+    stage("fp64 peak microbenchmark", rank)
     fp64_peak = capi.fp64_peak_tflops(local_rank)
+    stage("end-to-end solve", rank)
 
     # ---- end to end through the C ABI from pinned HOST buffers: create (H2D of all observations +
     # layout), LM solve with covariance, results back to the host, destroy ----
@@ -192,6 +219,7 @@ def _run_b200(args, rank, world, local_rank):
     launches_e2e = h2.launch_count()
     solve_err = float(np.abs(x_fin - xgt).max())
     h2.close()
+    stage("teardown", rank)
     if comm is not None:
         comm.close()
     if dist is not None:
@@ -307,6 +335,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--fixed-intrinsics", action="store_true", help="BundleOptions default (optimize_intrinsics=false)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-seconds", type=float, default=420.0, help="watchdog: abort (exit 3) instead of hanging past this many seconds")
     ap.add_argument("--cpu-sample-div", type=int, default=64)
     ap.add_argument("--k1-flop-per-obs", type=float, default=560.0,
                     help="FP64 flop per observation of K1 from the committed ncu capture (profiles/r1_k1_fused_ncu_full_35M.csv: "
