@@ -164,6 +164,14 @@ def _run_b200(args, rank, world, local_rank):
         uid = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         comm = capi.Comm(uid[0], rank, world, local_rank)
+        if not args.no_peer_allreduce:   # NVLink peer-memory all-reduce for the 16 KB blocks; falls back to NCCL by itself
+
+            def all_gather(b):
+                out = [None] * world
+                dist.all_gather_object(out, b)
+                return out
+            peer = comm.enable_peer(all_gather)
+            stage(f"peer all-reduce {'enabled' if peer else 'unavailable (' + comm.peer_error + '), NCCL in use'}", rank)
 
     def make_handle():
         h = capi.RefineHandle(prob, device=local_rank)
@@ -244,7 +252,8 @@ def _run_b200(args, rank, world, local_rank):
                    "observations_total": n_obs_total, "observations_per_gpu": n_obs_local,
                    "optimize_intrinsics": not args.fixed_intrinsics, "huber_delta": 1.0, "noise_px": 0.2,
                    "l2_policy": "inputs (2.25 GB SoA at c5) larger than the 126 MB L2; no flush",
-                   "sharding": f"views split contiguously over {world} rank(s); NCCL allreduce of per-camera blocks each pass" if world > 1 else "single GPU",
+                   "sharding": (f"views split contiguously over {world} rank(s); all-reduce of the per-camera blocks each pass: "
+                                + ("one NVLink peer-memory kernel" if (comm is not None and getattr(comm, "peer", False)) else "NCCL")) if world > 1 else "single GPU",
                    "k1_segments": info["n_segments"], "k1_passes": info["k1_passes"], "local_entries": info["local_entries"]},
         "clocks": clk.summary(),
         "e2e": {"value": e2e_value, "unit": "observations/s", "h2d_bytes_per_step": 32 * n_obs_local + 96 * int(prob.desc.n_blocks),
@@ -335,6 +344,7 @@ def main():
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--fixed-intrinsics", action="store_true", help="BundleOptions default (optimize_intrinsics=false)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer-allreduce", action="store_true", help="use NCCL for the per-pass all-reduce instead of the NVLink peer-memory kernel")
     ap.add_argument("--max-seconds", type=float, default=420.0, help="watchdog: abort (exit 3) instead of hanging past this many seconds")
     ap.add_argument("--cpu-sample-div", type=int, default=64)
     ap.add_argument("--k1-flop-per-obs", type=float, default=560.0,

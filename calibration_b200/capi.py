@@ -52,6 +52,10 @@ def lib():
     L.cal_comm_create.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.POINTER(hp)]
     L.cal_comm_destroy.argtypes = [hp]
     L.cal_refine_attach_comm.argtypes = [hp, hp]
+    L.cal_comm_peer_export.argtypes = [hp, u8p]
+    L.cal_comm_peer_enable.argtypes = [hp, u8p]
+    L.cal_comm_peer_disable.argtypes = [hp]
+    L.cal_comm_allreduce_test.argtypes = [hp, dp, C.c_int32, C.c_int]
     for name, argt in (
         ("cal_axxb_create", [C.POINTER(abi.AxxbDesc), C.c_int, C.POINTER(hp)]),
         ("cal_axxb_create_from_poses", [i64, dp, dp, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(hp),
@@ -185,6 +189,46 @@ class Comm:
         self._c = C.c_void_p()
         _check(lib().cal_comm_create(buf, rank, world, device, C.byref(self._c)))
         self.rank, self.world = rank, world
+
+    def enable_peer(self, all_gather):
+        """Switch the small all-reduces to the NVLink peer-memory kernel.  `all_gather(bytes) -> list of bytes in
+        rank order` is supplied by the caller (e.g. torch.distributed.all_gather_object).  Every rank takes part in
+        every exchange whatever happens locally, and the path is verified against NCCL on a rank-dependent vector
+        before it is trusted; returns False (NCCL stays in use on ALL ranks) if any rank fails any phase."""
+        L = lib()
+        self.peer, self.peer_error = False, ""
+
+        def agree(ok):
+            return all(o == b"1" for o in all_gather(b"1" if ok else b"0"))
+
+        buf = (C.c_uint8 * 64)()
+        ok = L.cal_comm_peer_export(self._c, buf) == CAL_OK
+        handles = all_gather(bytes(buf) if ok else b"")
+        ok = ok and all(len(h) == 64 for h in handles)
+        if ok:
+            blob = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(handles))
+            ok = L.cal_comm_peer_enable(self._c, blob) == CAL_OK
+        if not ok:
+            self.peer_error = L.cal_last_error().decode(errors="replace")
+        if not agree(ok):
+            L.cal_comm_peer_disable(self._c)
+            return False
+        n = 1000
+        ref = np.arange(n) * 0.25 + 1.0 / (self.rank + 3.0)
+        a = ref.copy()
+        for _ in range(3):   # several epochs: both parities of the double buffer
+            a = ref.copy()
+            ok = ok and L.cal_comm_allreduce_test(self._c, abi.dptr(a), n, 1) == CAL_OK
+        b = ref.copy()
+        ok = L.cal_comm_allreduce_test(self._c, abi.dptr(b), n, 0) == CAL_OK and ok
+        expect = sum(np.arange(n) * 0.25 + 1.0 / (r + 3.0) for r in range(self.world))
+        ok = ok and bool(np.allclose(a, expect, rtol=1e-14, atol=0) and np.array_equal(a, a) and np.allclose(a, b, rtol=1e-14, atol=0))
+        if not agree(ok):
+            self.peer_error = self.peer_error or "peer all-reduce self-test failed"
+            L.cal_comm_peer_disable(self._c)
+            return False
+        self.peer = True
+        return True
 
     def close(self):
         if self._c:

@@ -3,6 +3,7 @@
 #include <dlfcn.h>
 
 #include <cstring>
+#include <string>
 
 namespace calcomm {
 namespace {
@@ -79,7 +80,64 @@ Comm* Comm::create(const uint8_t id128[128], int rank, int world, std::string* e
     return c;
 }
 
+bool Comm::peer_export(uint8_t handle_out[kPeerHandleBytes]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == kPeerHandleBytes, "IPC handle size");
+    if (world_ > 64) { err_ = "peer path supports at most 64 ranks"; return false; }
+    if (!recv_) {
+        const size_t bytes = ((size_t)2 * world_ * kPeerMaxDoubles + (size_t)2 * world_) * sizeof(double);
+        if (cudaMalloc(reinterpret_cast<void**>(&recv_), bytes) != cudaSuccess || cudaMemset(recv_, 0, bytes) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&timed_out_), sizeof(int)) != cudaSuccess || cudaMemset(timed_out_, 0, sizeof(int)) != cudaSuccess) {
+            err_ = std::string("peer region allocation failed: ") + cudaGetErrorString(cudaGetLastError()); return false;
+        }
+        cudaDeviceSynchronize();
+    }
+    cudaIpcMemHandle_t hnd;
+    if (cudaIpcGetMemHandle(&hnd, recv_) != cudaSuccess) { err_ = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(cudaGetLastError()); return false; }
+    std::memcpy(handle_out, &hnd, kPeerHandleBytes);
+    return true;
+}
+
+bool Comm::peer_enable(const uint8_t* handles) {
+    if (!recv_) { err_ = "peer_export must be called first"; return false; }
+    double* host_ptrs[64];
+    for (int r = 0; r < world_; ++r) {
+        if (r == rank_) { host_ptrs[r] = recv_; continue; }
+        cudaIpcMemHandle_t hnd; std::memcpy(&hnd, handles + (size_t)r * kPeerHandleBytes, kPeerHandleBytes);
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            err_ = std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(cudaGetLastError());
+            return false;
+        }
+        opened_[r] = p; host_ptrs[r] = static_cast<double*>(p);
+    }
+    if (cudaMalloc(reinterpret_cast<void**>(&peers_dev_), sizeof(double*) * world_) != cudaSuccess ||
+        cudaMemcpy(peers_dev_, host_ptrs, sizeof(double*) * world_, cudaMemcpyHostToDevice) != cudaSuccess) {
+        err_ = "peer pointer table allocation failed"; return false;
+    }
+    peer_on_ = true;
+    return true;
+}
+
+bool Comm::allreduce_test(double* host_buf, size_t n, bool use_peer) {
+    if (n > (size_t)kPeerMaxDoubles) { err_ = "allreduce_test: too large"; return false; }
+    double* d = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&d), n * sizeof(double)) != cudaSuccess) { err_ = "allreduce_test: allocation failed"; return false; }
+    bool ok = cudaMemcpyAsync(d, host_buf, n * sizeof(double), cudaMemcpyHostToDevice, st_) == cudaSuccess;
+    const bool saved = peer_on_;
+    if (!use_peer) peer_on_ = false;
+    ok = ok && allreduce_sum(d, n, st_);
+    peer_on_ = saved;
+    ok = ok && cudaMemcpyAsync(host_buf, d, n * sizeof(double), cudaMemcpyDeviceToHost, st_) == cudaSuccess && cudaStreamSynchronize(st_) == cudaSuccess;
+    cudaFree(d);
+    if (!ok && err_.empty()) err_ = "allreduce_test failed";
+    return ok;
+}
+
 Comm::~Comm() {
+    for (int r = 0; r < 64; ++r) if (opened_[r]) cudaIpcCloseMemHandle(opened_[r]);
+    if (peers_dev_) cudaFree(peers_dev_);
+    if (recv_) cudaFree(recv_);
+    if (timed_out_) cudaFree(timed_out_);
     Api* a = api(nullptr);
     if (comm_ && a && a->CommDestroy) a->CommDestroy(comm_);
     if (stage_) cudaFree(stage_);
@@ -87,6 +145,11 @@ Comm::~Comm() {
 }
 
 bool Comm::allreduce_sum(double* dev_buf, size_t n, cudaStream_t st) {
+    if (peer_on_ && n <= (size_t)kPeerMaxDoubles) {
+        launch_peer_allreduce(dev_buf, (int)n, peers_dev_, rank_, world_, ++epoch_, timed_out_, st);
+        if (cudaGetLastError() != cudaSuccess) { err_ = "peer all-reduce launch failed"; return false; }
+        return true;
+    }
     Api* a = api(&err_);
     if (!a) return false;
     const int rc = a->AllReduce(dev_buf, dev_buf, n, kNcclFloat64, kNcclSum, comm_, st);

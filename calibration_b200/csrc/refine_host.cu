@@ -506,7 +506,7 @@ cal_status device_pass(cal_refine_handle& h, double* x_dev, bool jac, const doub
     const ProblemShape& S = h.S;
     launch_setup(S, h.L, B, h.st);
     if (jac) launch_k1(S, h.L, B, h.st); else launch_cost(S, h.L, B, h.st);
-    h.launches += 3 + launch_assemble(S, h.L, B, h.R, jac ? 1 : 0, h.st);
+    h.launches += 2 + launch_assemble(S, h.L, B, h.R, jac ? 1 : 0, h.st);
     const int NV = jac ? S.NV : 1;
     if (h.comm) {
         if (!h.comm->allreduce_sum(B.cam_sums, (size_t)S.n_cams * NV, h.st)) return fail(CAL_ERR_COMM, h.comm->error());
@@ -709,7 +709,7 @@ extern "C" cal_status cal_refine_bench_pass(cal_refine_handle* h, const double* 
         CUDA_TRY(cudaEventRecord(ev[2 + 2 * r], h->st));
         if (jacobian) launch_k1(h->S, h->L, h->B, h->st); else launch_cost(h->S, h->L, h->B, h->st);
         CUDA_TRY(cudaEventRecord(ev[3 + 2 * r], h->st));
-        h->launches += 3 + launch_assemble(h->S, h->L, h->B, h->R, jacobian ? 1 : 0, h->st);
+        h->launches += 2 + launch_assemble(h->S, h->L, h->B, h->R, jacobian ? 1 : 0, h->st);
         if (h->comm && !h->comm->allreduce_sum(h->B.cam_sums, (size_t)h->S.n_cams * (jacobian ? h->S.NV : 1), h->st))
             return fail(CAL_ERR_COMM, h->comm->error());
         if (jacobian && h->S.n_views > 0) { launch_view_gather(h->S, h->L, h->B, h->V, h->st); h->launches++; }
@@ -1089,6 +1089,19 @@ extern "C" cal_status cal_refine_attach_comm(cal_refine_handle* h, cal_comm* c) 
     if (!h) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
     h->comm = c ? c->c : nullptr;
     return CAL_OK;
+}
+extern "C" cal_status cal_comm_peer_export(cal_comm* c, uint8_t handle_out[64]) {
+    if (!c || !c->c || !handle_out) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    return c->c->peer_export(handle_out) ? CAL_OK : fail(CAL_ERR_COMM, c->c->error());
+}
+extern "C" cal_status cal_comm_peer_enable(cal_comm* c, const uint8_t* handles) {
+    if (!c || !c->c || !handles) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    return c->c->peer_enable(handles) ? CAL_OK : fail(CAL_ERR_COMM, c->c->error());
+}
+extern "C" void cal_comm_peer_disable(cal_comm* c) { if (c && c->c) c->c->peer_disable(); }
+extern "C" cal_status cal_comm_allreduce_test(cal_comm* c, double* host_inout, int32_t n, int use_peer) {
+    if (!c || !c->c || !host_inout || n <= 0) return fail(CAL_ERR_INVALID_ARGUMENT, "bad argument");
+    return c->c->allreduce_test(host_inout, (size_t)n, use_peer != 0) ? CAL_OK : fail(CAL_ERR_COMM, c->c->error());
 }
 extern "C" cal_status cal_comm_unique_id(uint8_t out128[128]) {
     std::string err;

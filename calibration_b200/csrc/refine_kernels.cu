@@ -5,7 +5,7 @@
 //
 //   k_repack        one-time gather of the uploaded SoA observations into the
 //                   tile-transposed layout (refine_kernels.cuh)
-//   k_cam_setup / k_block_setup
+//   k_block_setup
 //                   per evaluation: camera constants, composite block poses
 //                   (pose chains of src/estimation/residuals/*.h), sensor-frame
 //                   frames and the 6x6 chain-rule transforms
@@ -71,28 +71,35 @@ void launch_btg_permute(const DevLayout& L, const double* src, cudaStream_t st) 
 // ---------------------------------------------------------------------------
 // per-evaluation setup
 // ---------------------------------------------------------------------------
-__global__ void k_cam_setup(ProblemShape S, EvalBuffers B) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= S.n_cams) return;
-    const double* intr = B.x + S.off_intr + (S.kind == 0 ? 0 : c * S.P);
-    CamConst cc; cam_const_from_intr(intr, S.model, cc);
-    B.camc[c] = cc;
-    double T[36];
-    for (int i = 0; i < 36; ++i) T[i] = 0.0;
-    if (S.cam_pose_kind == 1) cam_transform_extrinsics(B.x + S.off_camt + 3 * c, cc.Rs, T);
-    else if (S.cam_pose_kind == 2) cam_transform_bundle(B.x + S.off_camq + 4 * c, cc.Rs, T);
-    for (int i = 0; i < 36; ++i) B.camT[c * 36 + i] = T[i];
-}
-
+// One launch per evaluation: threads c < n_cams additionally publish the camera constants and the
+// per-camera chain-rule transform T_c that K1 / k_cost read; every thread derives the sensor rotation
+// of ITS camera from the intrinsics itself (identity for the pinhole model), so no second launch and
+// no dependency between the two parts.
 __global__ void k_block_setup(ProblemShape S, DevLayout L, EvalBuffers B) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < S.n_cams) {
+        const int c = (int)b;
+        const double* intr = B.x + S.off_intr + (S.kind == 0 ? 0 : c * S.P);
+        CamConst cc; cam_const_from_intr(intr, S.model, cc);
+        B.camc[c] = cc;
+        double T[36];
+        for (int i = 0; i < 36; ++i) T[i] = 0.0;
+        if (S.cam_pose_kind == 1) cam_transform_extrinsics(B.x + S.off_camt + 3 * c, cc.Rs, T);
+        else if (S.cam_pose_kind == 2) cam_transform_bundle(B.x + S.off_camq + 4 * c, cc.Rs, T);
+        for (int i = 0; i < 36; ++i) B.camT[c * 36 + i] = T[i];
+    }
     if (b >= L.n_blk) return;
     double A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     double T[36];
     for (int i = 0; i < 36; ++i) T[i] = 0.0;
     if (L.blk_orig[b] >= 0) {
         const int cam = L.blk_cam[b];
-        const double* Rs = B.camc[cam].Rs;
+        double Rs[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (S.model == 1) {  // rot_sensor of this block's camera (scheimpflug.h:150-153)
+            const double* intr = B.x + S.off_intr + (S.kind == 0 ? 0 : cam * S.P);
+            CamConst cc; cam_const_from_intr(intr, S.model, cc);
+            for (int i = 0; i < 9; ++i) Rs[i] = cc.Rs[i];
+        }
         BlockPose bp;
         if (S.kind == 0) {
             const int v = L.blk_view[b];
@@ -116,8 +123,8 @@ __global__ void k_block_setup(ProblemShape S, DevLayout L, EvalBuffers B) {
 }
 
 void launch_setup(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
-    k_cam_setup<<<(S.n_cams + 63) / 64, 64, 0, st>>>(S, B);
-    if (L.n_blk > 0) k_block_setup<<<(unsigned)((L.n_blk + 127) / 128), 128, 0, st>>>(S, L, B);
+    const int64_t n = L.n_blk > S.n_cams ? L.n_blk : S.n_cams;
+    k_block_setup<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(S, L, B);
 }
 
 #define CALK_DISPATCH(FN, ...)                                                             \

@@ -168,6 +168,16 @@ cal_status cal_comm_unique_id(uint8_t out128[128]);
 cal_status cal_comm_create(const uint8_t unique_id[128], int rank, int world_size, int device, cal_comm** out);
 void cal_comm_destroy(cal_comm* c);
 cal_status cal_refine_attach_comm(cal_refine_handle* h, cal_comm* c);
+/* Optional NVLink peer-memory path for that all-reduce (blocks of <= 4096 doubles): every rank exports its
+ * receive region as a 64-byte CUDA IPC handle (cal_comm_peer_export), the caller all-gathers the handles in
+ * rank order and passes them to cal_comm_peer_enable.  The all-reduce then is ONE kernel — remote stores of
+ * the local block into every peer's slot over NVLink, a system-scope flag, a rank-ordered (bitwise
+ * reproducible) local sum — instead of an NCCL call; NCCL remains the path for larger payloads.
+ * cal_comm_allreduce_test all-reduces a host vector through either path (self-test). */
+cal_status cal_comm_peer_export(cal_comm* c, uint8_t handle_out[64]);
+cal_status cal_comm_peer_enable(cal_comm* c, const uint8_t* handles /* [world_size][64] */);
+void cal_comm_peer_disable(cal_comm* c); /* back to NCCL */
+cal_status cal_comm_allreduce_test(cal_comm* c, double* host_inout, int32_t n, int use_peer);
 
 /* ---- AX = XB hand-eye refinement: optimize_handeye (optim/handeye.h:40-43,
  * src/estimation/optim/handeye.cpp:45-78) over MotionPairs (linear/handeye.h:29-32). */
