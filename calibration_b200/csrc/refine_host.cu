@@ -263,10 +263,11 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&raw), sizeof(double) * 4 * (size_t)d.n_obs, cst));
     {
         const size_t nb = (size_t)d.n_obs * sizeof(double);
-        CUDA_TRY(cudaMemcpyAsync(raw, d.obj_x, nb, cudaMemcpyHostToDevice, cst));
-        CUDA_TRY(cudaMemcpyAsync(raw + d.n_obs, d.obj_y, nb, cudaMemcpyHostToDevice, cst));
-        CUDA_TRY(cudaMemcpyAsync(raw + 2 * d.n_obs, d.img_u, nb, cudaMemcpyHostToDevice, cst));
-        CUDA_TRY(cudaMemcpyAsync(raw + 3 * d.n_obs, d.img_v, nb, cudaMemcpyHostToDevice, cst));
+        // cudaMemcpyDefault: the observation arrays may be host memory or already on a device
+        CUDA_TRY(cudaMemcpyAsync(raw, d.obj_x, nb, cudaMemcpyDefault, cst));
+        CUDA_TRY(cudaMemcpyAsync(raw + d.n_obs, d.obj_y, nb, cudaMemcpyDefault, cst));
+        CUDA_TRY(cudaMemcpyAsync(raw + 2 * d.n_obs, d.img_u, nb, cudaMemcpyDefault, cst));
+        CUDA_TRY(cudaMemcpyAsync(raw + 3 * d.n_obs, d.img_v, nb, cudaMemcpyDefault, cst));
     }
     lap("copies issued");
     // ---- device block order: by camera (counting sort, stable), camera groups padded to 32 ----
@@ -368,24 +369,26 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     double* raw_bTg = nullptr;
     if (d.kind == CAL_KIND_BUNDLE) {  // robot poses: upload AoS, permute + transpose on the device
         CUDA_TRY(h.alloc(&L.blk_bTg, (size_t)12 * nblk));
-        CUDA_TRY(dev_alloc(&raw_bTg, (size_t)12 * d.n_blocks));
-        CUDA_TRY(cudaMemcpyAsync(raw_bTg, d.block_b_se3_g, sizeof(double) * 12 * d.n_blocks, cudaMemcpyHostToDevice, h.st));
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&raw_bTg), sizeof(double) * 12 * (size_t)d.n_blocks, h.st));
+        CUDA_TRY(cudaMemcpyAsync(raw_bTg, d.block_b_se3_g, sizeof(double) * 12 * d.n_blocks, cudaMemcpyDefault, h.st));
         launch_btg_permute(L, raw_bTg, h.st);
     }
-    {   // one-time repack into the tile-transposed layout (waits for the raw copy)
+    // one-time repack into the tile-transposed layout: queued behind the raw copy ON THE DEVICE (event), the
+    // host does not wait here — the rest of the set-up below (reduction chunk tables, buffer clears, view CSR)
+    // runs on a second stream and overlaps the H2D transfer; both streams are joined once at the end
+    cudaStream_t us = nullptr;
+    CUDA_TRY(cudaStreamCreateWithFlags(&us, cudaStreamNonBlocking));
+    cudaEvent_t copied; CUDA_TRY(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+    {
         int64_t* dsrc;
-        CUDA_TRY(dev_alloc(&dsrc, nseg));
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&dsrc), sizeof(int64_t) * std::max<size_t>(nseg, 1), h.st));
         CUDA_TRY(upload(dsrc, seg_src, h.st));
-        cudaEvent_t copied; CUDA_TRY(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
         CUDA_TRY(cudaEventRecord(copied, cst));
         CUDA_TRY(cudaStreamWaitEvent(h.st, copied, 0));
         launch_repack(L, raw, raw + d.n_obs, raw + 2 * d.n_obs, raw + 3 * d.n_obs, dsrc, h.st);
-        CUDA_TRY(cudaStreamSynchronize(h.st));
-        lap("copied + repacked");
-        cudaEventDestroy(copied);
-        cudaFreeAsync(raw, h.st); cudaStreamSynchronize(h.st); cudaStreamDestroy(cst);
-        cudaFree(dsrc); cudaFree(raw_bTg);
-        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaFreeAsync(raw, h.st)); CUDA_TRY(cudaFreeAsync(dsrc, h.st));
+        if (raw_bTg) CUDA_TRY(cudaFreeAsync(raw_bTg, h.st));
+        lap("repack queued");
     }
     // ---- evaluation buffers ----
     EvalBuffers& B = h.B;
@@ -415,17 +418,17 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
             std::vector<int32_t> vmap; int nvt = 0; k1_tile_value_map(S, nullptr, &nvt, &vmap);
             h.R.n_tile_chunks = (int)tc.size(); h.R.nvt = nvt;
             CUDA_TRY(h.alloc(&h.R.tile_chunks, tc.size())); CUDA_TRY(h.alloc(&h.R.tile_cam_chunk_off, to.size()));
-            CUDA_TRY(upload(h.R.tile_chunks, tc, h.st)); CUDA_TRY(upload(h.R.tile_cam_chunk_off, to, h.st));
-            CUDA_TRY(h.alloc(&h.B.tile_vmap, vmap.size())); CUDA_TRY(upload(h.B.tile_vmap, vmap, h.st));
+            CUDA_TRY(upload(h.R.tile_chunks, tc, us)); CUDA_TRY(upload(h.R.tile_cam_chunk_off, to, us));
+            CUDA_TRY(h.alloc(&h.B.tile_vmap, vmap.size())); CUDA_TRY(upload(h.B.tile_vmap, vmap, us));
             CUDA_TRY(h.alloc(&h.B.tile_vals, (size_t)ntiles * nvt)); CUDA_TRY(h.alloc(&h.B.partial_tile, tc.size() * (size_t)nvt));
-            CUDA_TRY(cudaStreamSynchronize(h.st));  // the staging vectors above go out of scope
+            CUDA_TRY(cudaStreamSynchronize(us));  // the staging vectors above go out of scope
         }
         h.R.n_seg_chunks = (int)sc.size(); h.R.n_blk_chunks = (int)bc.size();
         CUDA_TRY(h.alloc(&h.R.seg_chunks, sc.size())); CUDA_TRY(h.alloc(&h.R.blk_chunks, bc.size()));
         CUDA_TRY(h.alloc(&h.R.seg_cam_chunk_off, so.size())); CUDA_TRY(h.alloc(&h.R.blk_cam_chunk_off, bo.size()));
-        CUDA_TRY(upload(h.R.seg_chunks, sc, h.st)); CUDA_TRY(upload(h.R.blk_chunks, bc, h.st));
-        CUDA_TRY(upload(h.R.seg_cam_chunk_off, so, h.st)); CUDA_TRY(upload(h.R.blk_cam_chunk_off, bo, h.st));
-        CUDA_TRY(cudaStreamSynchronize(h.st));
+        CUDA_TRY(upload(h.R.seg_chunks, sc, us)); CUDA_TRY(upload(h.R.blk_chunks, bc, us));
+        CUDA_TRY(upload(h.R.seg_cam_chunk_off, so, us)); CUDA_TRY(upload(h.R.blk_cam_chunk_off, bo, us));
+        CUDA_TRY(cudaStreamSynchronize(us));
     }
     const int n_brows = fused ? 1 : S.NV - S.NE;
     CUDA_TRY(h.alloc(&B.x, h.n_amb)); CUDA_TRY(h.alloc(&B.camc, S.n_cams)); CUDA_TRY(h.alloc(&B.camT, (size_t)S.n_cams * 36));
@@ -434,18 +437,18 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     CUDA_TRY(h.alloc(&B.seg_ssr, nseg)); CUDA_TRY(h.alloc(&B.blk_ssr, nblk));
     CUDA_TRY(h.alloc(&B.partial, (size_t)std::max(h.R.n_seg_chunks, 1) * S.NE)); CUDA_TRY(h.alloc(&B.partial_blk, (size_t)std::max(h.R.n_blk_chunks, 1) * n_brows));
     CUDA_TRY(h.alloc(&B.cam_sums, (size_t)S.n_cams * S.NV));
-    CUDA_TRY(cudaMemsetAsync(B.cam_sums, 0, sizeof(double) * S.n_cams * S.NV, h.st));
+    CUDA_TRY(cudaMemsetAsync(B.cam_sums, 0, sizeof(double) * S.n_cams * S.NV, us));
     CUDA_TRY(h.alloc(&B.blk_w, nblk)); CUDA_TRY(h.alloc(&B.seg_w, nseg)); CUDA_TRY(h.alloc(&B.blk_rows, (size_t)n_brows * nblk));
-    CUDA_TRY(cudaMemsetAsync(B.seg_w, 0, sizeof(double) * nseg, h.st));
-    CUDA_TRY(cudaMemsetAsync(B.blk_rows, 0, sizeof(double) * n_brows * nblk, h.st));
-    CUDA_TRY(cudaMemsetAsync(B.seg_frame, 0, sizeof(double) * 9 * nseg, h.st));
-    CUDA_TRY(cudaMemsetAsync(B.seg_ssr, 0, sizeof(double) * nseg, h.st));
+    CUDA_TRY(cudaMemsetAsync(B.seg_w, 0, sizeof(double) * nseg, us));
+    CUDA_TRY(cudaMemsetAsync(B.blk_rows, 0, sizeof(double) * n_brows * nblk, us));
+    CUDA_TRY(cudaMemsetAsync(B.seg_frame, 0, sizeof(double) * 9 * nseg, us));
+    CUDA_TRY(cudaMemsetAsync(B.seg_ssr, 0, sizeof(double) * nseg, us));
     if (S.n_views > 0) {
         CUDA_TRY(h.alloc(&B.blk_Hvv, (size_t)21 * nblk)); CUDA_TRY(h.alloc(&B.blk_gv, (size_t)6 * nblk));
         CUDA_TRY(h.alloc(&B.blk_Evc, (size_t)36 * nblk)); CUDA_TRY(h.alloc(&B.blk_Evi, (size_t)6 * std::max(S.PI, 1) * nblk));
-        CUDA_TRY(cudaMemsetAsync(B.blk_Hvv, 0, sizeof(double) * 21 * nblk, h.st)); CUDA_TRY(cudaMemsetAsync(B.blk_gv, 0, sizeof(double) * 6 * nblk, h.st));
-        CUDA_TRY(cudaMemsetAsync(B.blk_Evc, 0, sizeof(double) * 36 * nblk, h.st));
-        CUDA_TRY(cudaMemsetAsync(B.blk_Evi, 0, sizeof(double) * 6 * std::max(S.PI, 1) * nblk, h.st));
+        CUDA_TRY(cudaMemsetAsync(B.blk_Hvv, 0, sizeof(double) * 21 * nblk, us)); CUDA_TRY(cudaMemsetAsync(B.blk_gv, 0, sizeof(double) * 6 * nblk, us));
+        CUDA_TRY(cudaMemsetAsync(B.blk_Evc, 0, sizeof(double) * 36 * nblk, us));
+        CUDA_TRY(cudaMemsetAsync(B.blk_Evi, 0, sizeof(double) * 6 * std::max(S.PI, 1) * nblk, us));
         // view CSR over device blocks
         ViewBuffers& V = h.V;
         std::vector<int32_t>& off = h.view_blk_off_host; std::vector<int32_t>& idx = h.view_blk_idx_host;
@@ -465,21 +468,25 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         h.n_syrk_cta = schur_num_ctas(nv);
         CUDA_TRY(h.alloc(&V.view_blk_off, nv + 1)); CUDA_TRY(h.alloc(&V.view_blk_idx, idx.size())); CUDA_TRY(h.alloc(&V.view_free, nv));
         CUDA_TRY(h.alloc(&V.cam_col_q, S.n_cams)); CUDA_TRY(h.alloc(&V.cam_col_t, S.n_cams)); CUDA_TRY(h.alloc(&V.cam_col_i, S.n_cams));
-        CUDA_TRY(upload(V.view_blk_off, off, h.st)); CUDA_TRY(upload(V.view_blk_idx, idx, h.st)); CUDA_TRY(upload(V.view_free, vfree, h.st));
-        CUDA_TRY(upload(V.cam_col_q, cq, h.st)); CUDA_TRY(upload(V.cam_col_t, ct, h.st)); CUDA_TRY(upload(V.cam_col_i, ci, h.st));
+        CUDA_TRY(upload(V.view_blk_off, off, us)); CUDA_TRY(upload(V.view_blk_idx, idx, us)); CUDA_TRY(upload(V.view_free, vfree, us));
+        CUDA_TRY(upload(V.cam_col_q, cq, us)); CUDA_TRY(upload(V.cam_col_t, ct, us)); CUDA_TRY(upload(V.cam_col_i, ci, us));
         CUDA_TRY(h.alloc(&V.Hpp, (size_t)nv * 36)); CUDA_TRY(h.alloc(&V.gp, (size_t)nv * 6)); CUDA_TRY(h.alloc(&V.sp, (size_t)nv * 6));
         CUDA_TRY(h.alloc(&V.dp, (size_t)nv * 6)); CUDA_TRY(h.alloc(&V.Lp, (size_t)nv * 36)); CUDA_TRY(h.alloc(&V.view_f, (size_t)nv * 6));
         CUDA_TRY(h.alloc(&V.blk_F, (size_t)6 * (6 + S.PI) * nblk)); CUDA_TRY(h.alloc(&V.delta_p, (size_t)nv * 6));
         CUDA_TRY(h.alloc(&V.s_shared, ns)); CUDA_TRY(h.alloc(&V.y_shared, ns)); CUDA_TRY(h.alloc(&V.C, (size_t)ns * ns)); CUDA_TRY(h.alloc(&V.c, ns));
         CUDA_TRY(h.alloc(&V.partialC, (size_t)h.n_syrk_cta * (ns + 1) * (ns + 1))); CUDA_TRY(h.alloc(&V.red, (size_t)nv * 4));
         CUDA_TRY(h.alloc(&V.red_out, 4)); CUDA_TRY(h.alloc(&V.fail, 1));
-        CUDA_TRY(cudaMemsetAsync(V.red, 0, sizeof(double) * nv * 4, h.st)); CUDA_TRY(cudaMemsetAsync(V.fail, 0, sizeof(int32_t), h.st));
-        CUDA_TRY(cudaMemsetAsync(V.blk_F, 0, sizeof(double) * 6 * (6 + S.PI) * nblk, h.st));
-        CUDA_TRY(cudaMemsetAsync(V.delta_p, 0, sizeof(double) * nv * 6, h.st));
-        CUDA_TRY(cudaMemsetAsync(V.sp, 0, sizeof(double) * nv * 6, h.st));
+        CUDA_TRY(cudaMemsetAsync(V.red, 0, sizeof(double) * nv * 4, us)); CUDA_TRY(cudaMemsetAsync(V.fail, 0, sizeof(int32_t), us));
+        CUDA_TRY(cudaMemsetAsync(V.blk_F, 0, sizeof(double) * 6 * (6 + S.PI) * nblk, us));
+        CUDA_TRY(cudaMemsetAsync(V.delta_p, 0, sizeof(double) * nv * 6, us));
+        CUDA_TRY(cudaMemsetAsync(V.sp, 0, sizeof(double) * nv * 6, us));
     }
     CUDA_TRY(h.alloc(&h.V.x_cand, h.n_amb));
+    lap("host set-up done");
+    CUDA_TRY(cudaStreamSynchronize(us));
     CUDA_TRY(cudaStreamSynchronize(h.st));
+    CUDA_TRY(cudaGetLastError());
+    cudaEventDestroy(copied); cudaStreamDestroy(us); cudaStreamDestroy(cst);
     lap("done");
     if (trace) std::fprintf(stderr, "[calib_b200] create: arena %.1f MB reserved, %.1f MB used, %zu extra allocations\n",
                             h.arena_size / 1048576.0, h.arena_used / 1048576.0, h.allocs.size());
@@ -958,9 +965,9 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
     if (cov && o->compute_covariance) {
         const int n = h.n_tan;
         if ((double)na * na * 8.0 > 8e9) return CAL_OK;  // would not fit; covariance_ok stays 0
-        // the normal equations of the last accepted point are still on the device / host mirrors
+        // The normal equations of the last accepted point are still on the device / in the host mirrors: the LM
+        // evaluates the Jacobian only at accepted points and x only moves on acceptance, so no extra pass.
         std::vector<double> xf(x_inout, x_inout + na);
-        if (cal_status st = device_pass(h, h.B.x, true, xf.data())) return st;
         if (views && !h.comm) {
             // ---- block-structured covariance (refine_kernels.cu, k_cov_*): shared block on the host, view blocks on the device ----
             CUDA_TRY(cudaMemsetAsync(V.fail, 0, sizeof(int32_t), h.st));
