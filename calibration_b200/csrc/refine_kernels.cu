@@ -457,15 +457,18 @@ __global__ void k_schur_factor(ProblemShape S, DevLayout L, EvalBuffers B, ViewB
     }
 }
 
-// C_aug = sum_v F_v^T F_v as a tiled rank-6 SYRK.  Each CTA owns a chunk of
-// views and the whole (ns+1)^2 upper triangle in 8x8 register tiles; the dense
-// 6 x (ns+1) rows of [F_v | f_v] are staged in shared memory.  Partial results
-// per CTA are summed in a fixed order (no floating-point atomics).
+// C_aug = sum_v F_v^T F_v as a tiled SYRK with a long inner dimension (6 rows per view).  The
+// (ns+1)^2 upper triangle is covered by 8x8 register tiles, one per thread; the CTA has exactly as many
+// warps as the tile count needs (120 tiles at ns = 114 -> 4 warps, three CTAs per SM), owns a chunk of
+// the views and stages the dense 6 x (ns+1) rows [F_v | f_v] of kSyrkViews views per barrier pair in
+// shared memory.  Per-CTA partial results are summed in a fixed order (no floating-point atomics).
+constexpr int kSyrkViews = 4;
 __global__ void __launch_bounds__(kSyrkThreads) k_schur_syrk(ProblemShape S, DevLayout L, ViewBuffers V, int ns,
                                                              int views_per_cta) {
-    __shared__ double frow[6][kSyrkMaxN];
+    __shared__ double frow[kSyrkViews * 6][kSyrkMaxN];
     const int na = ns + 1;
     const int nt = (na + kSyrkTile - 1) / kSyrkTile;
+    const int ncol = nt * kSyrkTile;  // columns actually read by the tiles
     int ti = -1, tj = -1;
     {
         int t = threadIdx.x, row = 0;
@@ -479,22 +482,25 @@ __global__ void __launch_bounds__(kSyrkThreads) k_schur_syrk(ProblemShape S, Dev
         for (int j = 0; j < kSyrkTile; ++j) acc[i][j] = 0.0;
     const int v0 = blockIdx.x * views_per_cta, v1 = min(S.n_views, v0 + views_per_cta);
     const int ncb = 6 + S.PI;
-    for (int v = v0; v < v1; ++v) {
-        if (!V.view_free[v]) continue;  // uniform across the CTA
-        for (int i = threadIdx.x; i < 6 * kSyrkMaxN; i += kSyrkThreads) (&frow[0][0])[i] = 0.0;
+    for (int vb = v0; vb < v1; vb += kSyrkViews) {
+        const int nvb = min(kSyrkViews, v1 - vb);
+        for (int i = threadIdx.x; i < nvb * 6 * ncol; i += blockDim.x) frow[i / ncol][i % ncol] = 0.0;
         __syncthreads();
-        const int nb = V.view_blk_off[v + 1] - V.view_blk_off[v];
-        for (int idx = threadIdx.x; idx < nb * ncb * 6; idx += kSyrkThreads) {
-            const int kb = idx / (ncb * 6), rem = idx % (ncb * 6), i = rem / ncb, j = rem % ncb;
-            const int64_t b = V.view_blk_idx[V.view_blk_off[v] + kb];
-            const int col = shared_col(V, L.blk_cam[b], j);
-            if (col >= 0) frow[i][col] = V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b];
+        for (int q = 0; q < nvb; ++q) {
+            const int v = vb + q;
+            if (!V.view_free[v]) continue;  // uniform across the CTA; its rows stay zero
+            const int nb = V.view_blk_off[v + 1] - V.view_blk_off[v];
+            for (int idx = threadIdx.x; idx < nb * ncb * 6; idx += blockDim.x) {
+                const int kb = idx / (ncb * 6), rem = idx % (ncb * 6), i = rem / ncb, j = rem % ncb;
+                const int64_t b = V.view_blk_idx[V.view_blk_off[v] + kb];
+                const int col = shared_col(V, L.blk_cam[b], j);
+                if (col >= 0) frow[q * 6 + i][col] = V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b];
+            }
+            if (threadIdx.x < 6) frow[q * 6 + threadIdx.x][ns] = V.view_f[(int64_t)v * 6 + threadIdx.x];
         }
-        if (threadIdx.x < 6) frow[threadIdx.x][ns] = V.view_f[(int64_t)v * 6 + threadIdx.x];
         __syncthreads();
         if (ti >= 0) {
-#pragma unroll
-            for (int r = 0; r < 6; ++r) {
+            for (int r = 0; r < nvb * 6; ++r) {
                 double fa[kSyrkTile], fb[kSyrkTile];
 #pragma unroll
                 for (int i = 0; i < kSyrkTile; ++i) { fa[i] = frow[r][ti * kSyrkTile + i]; fb[i] = frow[r][tj * kSyrkTile + i]; }
@@ -527,7 +533,8 @@ __global__ void k_schur_reduce(ViewBuffers V, int n_cta, int ns) {
     else if (r < ns && cc == ns) V.c[r] = s;
 }
 
-int schur_num_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < 148 * 16 ? (n_views + 15) / 16 : 148); }
+// up to three CTAs per SM (4-warp CTAs at the common shared-block widths), at least 16 views each
+int schur_num_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < 444 * 16 ? (n_views + 15) / 16 : 444); }
 
 void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V, int ns,
                   double radius, cudaStream_t st) {
@@ -535,7 +542,9 @@ void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& 
     k_schur_factor<<<(S.n_views + 63) / 64, 64, 0, st>>>(S, L, B, V, 1.0 / radius);
     const int n_cta = schur_num_ctas(S.n_views);
     const int per = (S.n_views + n_cta - 1) / n_cta;
-    k_schur_syrk<<<n_cta, kSyrkThreads, 0, st>>>(S, L, V, ns, per);
+    const int nt = (ns + 1 + kSyrkTile - 1) / kSyrkTile;
+    const int threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;  // one thread per 8x8 tile of the upper triangle
+    k_schur_syrk<<<n_cta, threads, 0, st>>>(S, L, V, ns, per);
     const int na = ns + 1;
     k_schur_reduce<<<(na * na + 127) / 128, 128, 0, st>>>(V, n_cta, ns);
 }
