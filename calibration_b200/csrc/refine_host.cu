@@ -20,6 +20,7 @@
 #include "../../include/calib_b200.h"
 #include "comm.h"
 #include "refine_kernels.cuh"
+#include "refine_model.hpp"
 
 using namespace calk;
 
@@ -33,9 +34,6 @@ cal_status fail(cal_status s, const std::string& m) { g_err = m; return s; }
         cudaError_t _e = (expr);                                                                \
         if (_e != cudaSuccess) return fail(CAL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
-
-enum PBType { PB_EUCLID = 0, PB_QUAT = 1, PB_INTR = 2 };
-struct PB { int off, size, tsize, type; bool constant; int toff; };
 
 template <class T> cudaError_t dev_alloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)); }
 template <class T> cudaError_t upload(T* dst, const std::vector<T>& src, cudaStream_t st) {
@@ -73,17 +71,13 @@ void quat_plus_jacobian(const double* q, double* J) {  // QuaternionManifold::Pl
 
 }  // namespace
 
-struct cal_refine_handle {
+struct cal_refine_handle : calk::HostModel {
     int device = 0;
     cudaStream_t st = nullptr;
-    ProblemShape S{};
     DevLayout L{};
     EvalBuffers B{};
     ViewBuffers V{};
     std::vector<void*> allocs;
-    std::vector<PB> pbs;
-    int n_amb = 0, n_tan = 0, ns = 0;
-    bool constrained = false;
     int64_t n_blocks = 0, n_obs = 0;
     ReduceDesc R{};
     int n_syrk_cta = 1;
@@ -98,14 +92,6 @@ struct cal_refine_handle {
     calcomm::Comm* comm = nullptr;  // not owned (cal_comm_create / cal_comm_destroy)
     // counters
     int64_t launches = 0;
-
-    int pb_intr(int c) const { return S.kind == CAL_KIND_INTRINSICS ? 0 : c; }
-    int pb_viewq(int v) const { return S.kind == CAL_KIND_INTRINSICS ? 1 + v : 3 * S.n_cams + v; }
-    int pb_viewt(int v) const { return S.kind == CAL_KIND_INTRINSICS ? 1 + S.n_views + v : 3 * S.n_cams + S.n_views + v; }
-    int pb_camq(int c) const { return S.n_cams + c; }
-    int pb_camt(int c) const { return 2 * S.n_cams + c; }
-    int pb_bq() const { return 3 * S.n_cams; }
-    int pb_bt() const { return 3 * S.n_cams + 1; }
 
     // all device buffers of a handle are carved from one arena (one cudaMalloc / cudaFree)
     unsigned char* arena = nullptr; size_t arena_size = 0, arena_used = 0;
@@ -131,47 +117,6 @@ struct cal_refine_handle {
 };
 
 namespace {
-
-void build_param_blocks(cal_refine_handle& h, const cal_problem_desc& d) {
-    const bool sk = d.optimize_skew != 0;
-    const int P = h.S.P;
-    auto add = [&](int size, int type, bool constant) {
-        PB b; b.off = h.n_amb; b.size = size; b.type = type; b.constant = constant;
-        b.tsize = type == PB_QUAT ? 3 : (type == PB_INTR && !sk ? size - 1 : size);
-        b.toff = -1; h.n_amb += size; h.pbs.push_back(b);
-    };
-    if (d.kind == CAL_KIND_INTRINSICS) {
-        add(P, PB_INTR, false);
-        for (int v = 0; v < d.n_views; ++v) add(4, PB_QUAT, false);
-        for (int v = 0; v < d.n_views; ++v) add(3, PB_EUCLID, false);
-        h.constrained = true;  // lower bounds on fx, fy (intrinsics.cpp:81-82)
-    } else if (d.kind == CAL_KIND_EXTRINSICS) {
-        const bool oi = d.optimize_intrinsics, oe = d.optimize_extrinsics;  // extrinsics.cpp:110-150
-        for (int c = 0; c < d.n_cams; ++c) add(P, PB_INTR, !oi);
-        for (int c = 0; c < d.n_cams; ++c) add(4, PB_QUAT, !oe || c == 0);
-        for (int c = 0; c < d.n_cams; ++c) add(3, PB_EUCLID, !oe || c == 0);
-        for (int v = 0; v < d.n_views; ++v) add(4, PB_QUAT, oi && v == 0);
-        for (int v = 0; v < d.n_views; ++v) add(3, PB_EUCLID, oi && v == 0);
-        h.constrained = oi;
-    } else {
-        const bool oi = d.optimize_intrinsics, oh = d.optimize_hand_eye, ot = d.optimize_target_pose;  // bundle.cpp:98-131
-        for (int c = 0; c < d.n_cams; ++c) add(P, PB_INTR, !oi);
-        for (int c = 0; c < d.n_cams; ++c) add(4, PB_QUAT, !oh);
-        for (int c = 0; c < d.n_cams; ++c) add(3, PB_EUCLID, !oh);
-        add(4, PB_QUAT, !ot);
-        add(3, PB_EUCLID, !ot);
-        h.constrained = oi;
-    }
-    for (auto& b : h.pbs) if (!b.constant) { b.toff = h.n_tan; h.n_tan += b.tsize; }
-    // shared block = everything that is not a per-view pose; for the per-view
-    // kinds the view blocks come last in x, so shared tangent indices are 0..ns-1
-    h.ns = h.n_tan;
-    if (d.kind != CAL_KIND_BUNDLE) {
-        h.ns = 0;
-        const int first_view_pb = h.pb_viewq(0);
-        for (int i = 0; i < first_view_pb; ++i) if (!h.pbs[i].constant) h.ns += h.pbs[i].tsize;
-    }
-}
 
 cal_status validate(const cal_problem_desc& d) {
     if (d.kind < 0 || d.kind > 2 || d.model < 0 || d.model > 1) return fail(CAL_ERR_INVALID_ARGUMENT, "unknown problem kind / camera model");
@@ -219,31 +164,11 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     cal_refine_handle& h = *hp;
     h.device = device;
     CUDA_TRY(cudaStreamCreateWithFlags(&h.st, cudaStreamNonBlocking));
+    h.init_model(d);
     ProblemShape& S = h.S;
-    S.kind = d.kind; S.model = d.model; S.n_cams = d.n_cams;
-    S.n_views = d.kind == CAL_KIND_BUNDLE ? 0 : d.n_views;
-    S.P = d.model == CAL_MODEL_SCHEIMPFLUG_BC5 ? 12 : 10;
-    const bool intr_free = d.kind == CAL_KIND_INTRINSICS || d.optimize_intrinsics;
-    S.imode = !intr_free ? INTR_NONE : (d.optimize_skew ? INTR_SKEW : INTR_NOSKEW);
-    S.PI = S.imode == INTR_NONE ? 0 : (S.imode == INTR_NOSKEW ? S.P - 1 : S.P);
-    S.NC = 6 + S.PI; S.NL = S.NC + 1; S.NE = S.NL * (S.NL + 1) / 2;
-    S.huber_delta = d.huber_delta;
-    S.cam_pose_kind = d.kind == CAL_KIND_EXTRINSICS ? 1 : (d.kind == CAL_KIND_BUNDLE ? 2 : 0);
-    S.view_free_global = d.kind == CAL_KIND_BUNDLE ? (d.optimize_target_pose != 0) : 1;
-    S.NV = S.NE + 1 + (d.kind == CAL_KIND_BUNDLE ? 63 + 6 * S.PI : 0);
     h.n_blocks = d.n_blocks; h.n_obs = d.n_obs;
-    build_param_blocks(h, d);
     if (d.kind != CAL_KIND_BUNDLE && h.ns + 1 > kSyrkMaxN)
         return fail(CAL_ERR_INVALID_ARGUMENT, "shared block too large for the Schur kernel (ns + 1 > 176)");
-    S.off_intr = 0;
-    if (d.kind == CAL_KIND_INTRINSICS) { S.off_camq = S.off_camt = 0; S.off_viewq = S.P; S.off_viewt = S.P + 4 * d.n_views; }
-    else if (d.kind == CAL_KIND_EXTRINSICS) {
-        S.off_camq = S.P * d.n_cams; S.off_camt = S.off_camq + 4 * d.n_cams;
-        S.off_viewq = S.off_camt + 3 * d.n_cams; S.off_viewt = S.off_viewq + 4 * d.n_views;
-    } else {
-        S.off_camq = S.P * d.n_cams; S.off_camt = S.off_camq + 4 * d.n_cams;
-        S.off_viewq = S.off_camt + 3 * d.n_cams; S.off_viewt = S.off_viewq + 4;  // b_q_t, b_t_t
-    }
 
     // ---- start the big copy first: raw SoA observations into one staging buffer on a copy
     // stream, so the transfer overlaps the host-side layout construction below ----
@@ -527,58 +452,7 @@ cal_status device_pass(cal_refine_handle& h, double* x_dev, bool jac, const doub
     for (int c = 0; c < S.n_cams; ++c) cost += h.cam_sums[(size_t)c * NV + (jac ? S.NE : 0)];
     h.cost = cost;
     if (!jac) return CAL_OK;
-    // ---- finish the shared block on the host (per-camera constant transforms) ----
-    const int ns = h.ns, NE = S.NE, NC = S.NC, PI = S.PI, NL = S.NL;
-    auto idx = [NL](int a, int b) { if (a > b) std::swap(a, b); return a * NL - a * (a - 1) / 2 + (b - a); };
-    h.Hss.assign((size_t)ns * ns, 0.0); h.gs.assign(ns, 0.0);
-    for (int c = 0; c < S.n_cams; ++c) {
-        const double* sums = &h.cam_sums[(size_t)c * S.NV];
-        const PB& pi = h.pbs[h.pb_intr(c)];
-        int pose_idx[6]; bool pose_free = false;
-        double Tc[36];
-        if (S.cam_pose_kind) {
-            const PB& pq = h.pbs[h.pb_camq(c)]; const PB& pt = h.pbs[h.pb_camt(c)];
-            pose_free = !pq.constant;
-            for (int k = 0; k < 3; ++k) { pose_idx[k] = pq.toff + k; pose_idx[3 + k] = pt.toff + k; }
-            CamConst cc; cam_const_from_intr(x_host + pi.off, S.model, cc);
-            if (S.cam_pose_kind == 1) cam_transform_extrinsics(x_host + pt.off, cc.Rs, Tc);
-            else cam_transform_bundle(x_host + pq.off, cc.Rs, Tc);
-        }
-        const bool intr_free = !pi.constant && PI > 0;
-        if (pose_free) {
-            double Q[36];  // T_c^T N_xixi
-            for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double a = 0; for (int k = 0; k < 6; ++k) a += Tc[6 * k + i] * sums[idx(k, j)]; Q[6 * i + j] = a; }
-            for (int i = 0; i < 6; ++i) {
-                for (int j = 0; j < 6; ++j) { double a = 0; for (int k = 0; k < 6; ++k) a += Q[6 * i + k] * Tc[6 * k + j]; h.Hss[(size_t)pose_idx[i] * ns + pose_idx[j]] += a; }
-                double g = 0; for (int k = 0; k < 6; ++k) g += Tc[6 * k + i] * sums[idx(k, NC)];
-                h.gs[pose_idx[i]] += g;
-                if (intr_free) for (int j = 0; j < PI; ++j) {
-                    double a = 0; for (int k = 0; k < 6; ++k) a += Tc[6 * k + i] * sums[idx(k, 6 + j)];
-                    h.Hss[(size_t)pose_idx[i] * ns + pi.toff + j] += a; h.Hss[(size_t)(pi.toff + j) * ns + pose_idx[i]] += a;
-                }
-            }
-        }
-        if (intr_free) for (int i = 0; i < PI; ++i) {
-            h.gs[pi.toff + i] += sums[idx(6 + i, NC)];
-            for (int j = 0; j < PI; ++j) h.Hss[(size_t)(pi.toff + i) * ns + pi.toff + j] += sums[idx(6 + i, 6 + j)];
-        }
-        if (S.kind == CAL_KIND_BUNDLE && S.view_free_global) {
-            const PB& bq = h.pbs[h.pb_bq()]; const PB& bt = h.pbs[h.pb_bt()];
-            int bidx[6]; for (int k = 0; k < 3; ++k) { bidx[k] = bq.toff + k; bidx[3 + k] = bt.toff + k; }
-            const double* Hvv = sums + NE + 1; const double* gv = Hvv + 21; const double* Qs = gv + 6; const double* Evi = Qs + 36;
-            int o = 0;
-            for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { const double a = Hvv[o++]; h.Hss[(size_t)bidx[i] * ns + bidx[j]] += a; if (i != j) h.Hss[(size_t)bidx[j] * ns + bidx[i]] += a; }
-            for (int i = 0; i < 6; ++i) h.gs[bidx[i]] += gv[i];
-            if (pose_free) for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) {
-                double a = 0; for (int k = 0; k < 6; ++k) a += Qs[6 * i + k] * Tc[6 * k + j];
-                h.Hss[(size_t)bidx[i] * ns + pose_idx[j]] += a; h.Hss[(size_t)pose_idx[j] * ns + bidx[i]] += a;
-            }
-            if (intr_free) for (int i = 0; i < 6; ++i) for (int j = 0; j < PI; ++j) {
-                const double a = Evi[PI * i + j];
-                h.Hss[(size_t)bidx[i] * ns + pi.toff + j] += a; h.Hss[(size_t)(pi.toff + j) * ns + bidx[i]] += a;
-            }
-        }
-    }
+    h.assemble_shared(h.cam_sums.data(), x_host, h.Hss, h.gs);
     return CAL_OK;
 }
 
