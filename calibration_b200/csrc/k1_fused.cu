@@ -286,52 +286,61 @@ __device__ __forceinline__ void k1_role(const K1Args& P, int64_t tile, int lane,
 #pragma unroll
     for (int i = 0; i < NA; ++i) acc[i] = 0.0;
     double ssr = 0.0;
-    int step = 0;
-    for (int ch = 0; ch < ts.n_chunks; ++ch) {
-        ts.wait(ch);
-        const int k0 = ch * RC, kn = min(RC, depth - k0);
-        for (int kk = 0; kk < kn; kk += NROLE, ++step) {
-            // each role projects one of the NROLE corners of this step ...
-            const int kmine = kk + ROLE;
-            const bool mine = k0 + kmine < len;
-            double Ju[NL], Jv[NL];
-            if (mine) {
-                const double* q = ts.row(ch, kmine, lane);
-                obs_rows<MODEL, IMODE>(c, A, q[0], q[32], q[64], q[96], Ju, Jv);
-            }
-            if constexpr (NROLE > 1) {
-                // ... hands the rows to the other roles through shared memory ...
-                double* xs = xbuf + ((step & 1) * NROLE + ROLE) * NX * 32 + lane;
+    // UNI: every lane of this warp has a full-depth segment and the depth is a multiple of NROLE (the
+    // benchmark's boards: 88 corners everywhere) — the step loop then carries no per-lane predicates at all.
+    // The barrier count per step is the same on both paths, so the roles of a tile may choose differently.
+    auto run = [&](auto uni_c) {
+        constexpr bool UNI = decltype(uni_c)::value;
+        int step = 0;
+        for (int ch = 0; ch < ts.n_chunks; ++ch) {
+            ts.wait(ch);
+            const int k0 = ch * RC, kn = min(RC, depth - k0);
+            for (int kk = 0; kk < kn; kk += NROLE, ++step) {
+                // each role projects one of the NROLE corners of this step ...
+                const int kmine = kk + ROLE;
+                const bool mine = UNI || k0 + kmine < len;
+                double Ju[NL], Jv[NL];
                 if (mine) {
-                    static_for<0, NL>([&](auto cc) {
-                        constexpr int col = decltype(cc)::value;
-                        if constexpr (XT::send_u(col)) xs[XT::pos_u(col) * 32] = Ju[col];
-                        if constexpr (XT::send_v(col)) xs[XT::pos_v(col) * 32] = Jv[col];
-                    });
+                    const double* q = ts.row(ch, kmine, lane);
+                    obs_rows<MODEL, IMODE>(c, A, q[0], q[32], q[64], q[96], Ju, Jv);
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(NROLE * 32) : "memory");
-            }
-            // ... and accumulates ITS entries of the local system for all NROLE corners
-            if (mine) k1_accumulate<MODEL, IMODE, ROLE>(Ju, Jv, acc, ssr);
-            if constexpr (NROLE > 1) {
-                static_for<1, NROLE>([&](auto cp) {
-                    constexpr int other = (ROLE + decltype(cp)::value) % NROLE;
-                    if (k0 + kk + other < len) {
-                        const double* xo = xbuf + ((step & 1) * NROLE + other) * NX * 32 + lane;
-                        double Pu[NL], Pv[NL];
+                if constexpr (NROLE > 1) {
+                    // ... hands the rows to the other roles through shared memory ...
+                    double* xs = xbuf + ((step & 1) * NROLE + ROLE) * NX * 32 + lane;
+                    if (mine) {
                         static_for<0, NL>([&](auto cc) {
                             constexpr int col = decltype(cc)::value;
-                            Pu[col] = XT::send_u(col) ? xo[XT::pos_u(col) * 32] : (LT::has_u(col) ? 1.0 : 0.0);
-                            Pv[col] = XT::send_v(col) ? xo[XT::pos_v(col) * 32] : (LT::has_v(col) ? 1.0 : 0.0);
+                            if constexpr (XT::send_u(col)) xs[XT::pos_u(col) * 32] = Ju[col];
+                            if constexpr (XT::send_v(col)) xs[XT::pos_v(col) * 32] = Jv[col];
                         });
-                        k1_accumulate<MODEL, IMODE, ROLE>(Pu, Pv, acc, ssr);
                     }
-                });
+                }
+                // ... accumulates ITS entries of the local system for its own corner (the published rows
+                // land in shared memory meanwhile, and the partner has time to arrive at the barrier) ...
+                if (mine) k1_accumulate<MODEL, IMODE, ROLE>(Ju, Jv, acc, ssr);
+                if constexpr (NROLE > 1) {
+                    asm volatile("bar.sync 1, %0;" ::"n"(NROLE * 32) : "memory");
+                    // ... and for the corners the other roles projected
+                    static_for<1, NROLE>([&](auto cp) {
+                        constexpr int other = (ROLE + decltype(cp)::value) % NROLE;
+                        if (UNI || k0 + kk + other < len) {
+                            const double* xo = xbuf + ((step & 1) * NROLE + other) * NX * 32 + lane;
+                            double Pu[NL], Pv[NL];
+                            static_for<0, NL>([&](auto cc) {
+                                constexpr int col = decltype(cc)::value;
+                                Pu[col] = XT::send_u(col) ? xo[XT::pos_u(col) * 32] : (LT::has_u(col) ? 1.0 : 0.0);
+                                Pv[col] = XT::send_v(col) ? xo[XT::pos_v(col) * 32] : (LT::has_v(col) ? 1.0 : 0.0);
+                            });
+                            k1_accumulate<MODEL, IMODE, ROLE>(Pu, Pv, acc, ssr);
+                        }
+                    });
+                }
             }
+            if constexpr (NROLE == 1) __syncwarp();  // every lane is done with this stage (NROLE > 1: the step barrier)
+            ts.issue(ch + 2, leader);                // refill it
         }
-        if constexpr (NROLE == 1) __syncwarp();  // every lane is done with this stage (NROLE > 1: the step barrier)
-        ts.issue(ch + 2, leader);                // refill it
-    }
+    };
+    if (__all_sync(0xffffffffu, len == depth) && depth % NROLE == 0) run(std::true_type{}); else run(std::false_type{});
     unsigned char* warp_smem = smem;             // NROLE == 1: the transpose tile aliases the idle staging ring
     if constexpr (NROLE > 1) {
         asm volatile("bar.sync 1, %0;" ::"n"(NROLE * 32) : "memory");  // the exchange slots are dead: they become the transpose tiles
