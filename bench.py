@@ -227,6 +227,20 @@ def _run_b200(args, rank, world, local_rank):
     launches_e2e = h2.launch_count()
     solve_err = float(np.abs(x_fin - xgt).max())
     h2.close()
+    # the strictest reading of "end to end": upload ALL inputs and run ONE fused pass, result (cost, g, H) back on the host
+    barrier()
+    t0 = time.perf_counter()
+    h3 = make_handle()
+    c1, g1, H1 = h3.eval(x0)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    one_pass_s = time.perf_counter() - t0
+    h3.close()
+    to = torch.tensor([one_pass_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(to, op=dist.ReduceOp.MAX)
+    one_pass_s = float(to[0])
     stage("teardown", rank)
     if comm is not None:
         comm.close()
@@ -262,7 +276,10 @@ def _run_b200(args, rank, world, local_rank):
                         "value = observations x fused passes executed / wall time",
                 "wall_s": e2e_s, "lm_iterations": int(res.iterations), "jacobian_passes": n_jac, "cost_passes": n_cost,
                 "lm_iteration_ms": 1e3 * e2e_s / max(int(res.iterations), 1), "final_cost": float(res.final_cost),
-                "converged": bool(res.success), "max_abs_param_error_vs_ground_truth": solve_err, "gpu_launches": launches_e2e},
+                "converged": bool(res.success), "max_abs_param_error_vs_ground_truth": solve_err, "gpu_launches": launches_e2e,
+                "upload_plus_one_pass": {"value": n_obs_total / one_pass_s, "unit": "observations/s", "wall_s": one_pass_s,
+                                         "what": "cal_refine_create (H2D of all observations) + ONE cal_refine_eval (fused pass, cost / g / H to the host) + destroy: "
+                                                 "PCIe-bound, the bound a caller pays who uploads for a single evaluation"}},
         "gpu_launches": launches_timed,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                      "traffic": k1_traffic_bytes(args, world), "traffic_source": "profiles/r1_k1_fused_ncu_full_bench_c5.csv (ncu --set full of this command)",

@@ -231,22 +231,27 @@ constexpr int kBatch = 16;
 // find_inliers (ransac.h:80-95) with the symmetric transfer error of homographyestimator.cpp:80-93,
 // written without divisions:  (e1 / qz^2 + e2 / pz^2) / 2 <= t^2  <=>  e1 pz^2 + e2 qz^2 <= 2 t^2 qz^2 pz^2.
 // Writes the inlier bit mask, returns the count (warp-uniform).
+__device__ __forceinline__ bool score_point(const WarpMem& w, int i, const double* H, const double* Hi, double two_thresh2) {
+    const double x = w.x[i], y = w.y[i], u = w.u[i], v = w.v[i];
+    const double qx = fma(H[0], x, fma(H[1], y, H[2])), qy = fma(H[3], x, fma(H[4], y, H[5])), qz = fma(H[6], x, fma(H[7], y, H[8]));
+    const double px = fma(Hi[0], u, fma(Hi[1], v, Hi[2])), py = fma(Hi[3], u, fma(Hi[4], v, Hi[5])), pz = fma(Hi[6], u, fma(Hi[7], v, Hi[8]));
+    const double a = fma(u, qz, -qx), b = fma(v, qz, -qy), c = fma(x, pz, -px), d = fma(y, pz, -py);
+    const double e1 = fma(a, a, b * b), e2 = fma(c, c, d * d), qq = qz * qz, pp = pz * pz;
+    return fma(e1, pp, e2 * qq) <= two_thresh2 * qq * pp && qq > 0.0 && pp > 0.0;  // false for NaN, like `r <= threshold`
+}
 __device__ int score_count(const WarpMem& w, int n, int lane, const double* H, double two_thresh2, unsigned* mask) {
     double Hi[9]; inv3(H, Hi);
     int cnt = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        bool in = false;
-        if (i < n) {
-            const double x = w.x[i], y = w.y[i], u = w.u[i], v = w.v[i];
-            const double qx = fma(H[0], x, fma(H[1], y, H[2])), qy = fma(H[3], x, fma(H[4], y, H[5])), qz = fma(H[6], x, fma(H[7], y, H[8]));
-            const double px = fma(Hi[0], u, fma(Hi[1], v, Hi[2])), py = fma(Hi[3], u, fma(Hi[4], v, Hi[5])), pz = fma(Hi[6], u, fma(Hi[7], v, Hi[8]));
-            const double a = fma(u, qz, -qx), b = fma(v, qz, -qy), c = fma(x, pz, -px), d = fma(y, pz, -py);
-            const double e1 = fma(a, a, b * b), e2 = fma(c, c, d * d), qq = qz * qz, pp = pz * pz;
-            in = fma(e1, pp, e2 * qq) <= two_thresh2 * qq * pp && qq > 0.0 && pp > 0.0;  // false for NaN, like `r <= threshold`
-        }
-        const unsigned bm = __ballot_sync(kFull, in);
+    const int nfull = n & ~31;
+    for (int base = 0; base < nfull; base += 32) {  // full rounds: no per-lane predicate
+        const unsigned bm = __ballot_sync(kFull, score_point(w, base + lane, H, Hi, two_thresh2));
         if (lane == 0) mask[base >> 5] = bm;
+        cnt += __popc(bm);
+    }
+    if (nfull < n) {
+        const int i = nfull + lane;
+        const unsigned bm = __ballot_sync(kFull, i < n && score_point(w, i < n ? i : n - 1, H, Hi, two_thresh2));
+        if (lane == 0) mask[nfull >> 5] = bm;
         cnt += __popc(bm);
     }
     __syncwarp();
