@@ -202,16 +202,20 @@ auto optimize_extrinsics(const std::vector<MulticamPlanarView>& views, const std
 inline auto optimize_handeye(const std::vector<Eigen::Isometry3d>& base_se3_gripper,
                              const std::vector<Eigen::Isometry3d>& camera_se3_target,
                              const Eigen::Isometry3d& init_gripper_se3_ref, const OptimOptions& options) -> HandeyeResult {
-    // pair construction stays the reference's own host code (linear/handeyedlt.cpp:51-81)
-    const auto pairs = build_all_pairs(base_se3_gripper, camera_se3_target, 0.5);  // handeye.cpp:63-64
-    std::vector<double> ra, rb, ta, tb;
-    for (const auto& mp : pairs) {
-        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { ra.push_back(mp.rot_a(i, j)); rb.push_back(mp.rot_b(i, j)); }
-        for (int i = 0; i < 3; ++i) { ta.push_back(mp.tra_a(i)); tb.push_back(mp.tra_b(i)); }
-    }
-    cal_axxb_desc d{static_cast<int64_t>(pairs.size()), ra.data(), rb.data(), ta.data(), tb.data(), options.huber_delta};
+    // build_all_pairs (linear/handeyedlt.cpp:51-81) runs on the device: the n (n - 1) / 2 motion pairs are
+    // formed on the fly in every pass (0.5 deg / reject-parallel / 1e-3 are optimize_handeye's own arguments,
+    // handeye.cpp:63-64 with the defaults of linear/handeye.h)
+    if (base_se3_gripper.size() != camera_se3_target.size()) throw std::runtime_error("Inconsistent hand-eye input sizes");
+    const auto np = static_cast<int64_t>(base_se3_gripper.size());
+    std::vector<double> g(12 * base_se3_gripper.size()), c(12 * camera_se3_target.size());
+    auto pack = [](const Eigen::Isometry3d& T, double* o) {
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) o[3 * i + j] = T.linear()(i, j);
+        for (int i = 0; i < 3; ++i) o[9 + i] = T.translation()(i);
+    };
+    for (int64_t i = 0; i < np; ++i) { pack(base_se3_gripper[i], &g[12 * i]); pack(camera_se3_target[i], &c[12 * i]); }
     cal_axxb_handle* h = nullptr;
-    b200::check(cal_axxb_create(&d, 0, &h));
+    int64_t kept = 0;
+    b200::check(cal_axxb_create_from_poses(np, g.data(), c.data(), 0.5, 1, 1e-3, options.huber_delta, 0, &h, &kept));
     double x[7]; b200::push_pose(init_gripper_se3_ref, x, x + 4);
     const cal_optim_options co = b200::to_c(options);
     cal_optim_result r{}; double cov[49];
@@ -222,6 +226,51 @@ inline auto optimize_handeye(const std::vector<Eigen::Isometry3d>& base_se3_grip
     result.core.success = r.success != 0; result.core.final_cost = r.final_cost; result.core.report = r.report;
     if (r.covariance_ok) result.core.covariance = Eigen::Map<const Eigen::Matrix<double, 7, 7, Eigen::RowMajor>>(cov);
     result.g_se3_c = b200::pop_pose(x, x + 4);
+    return result;
+}
+
+// estimate_intrinsics(views, opts) without homography RANSAC (linear/intrinsics.h:58-59,
+// src/estimation/linear/intrinsicsdlt.cpp:101-145): all views in one batched call.
+inline auto estimate_intrinsics_b200(const std::vector<PlanarView>& views, const IntrinsicsEstimOptions& opts) -> IntrinsicsEstimateResult {
+    IntrinsicsEstimateResult result;
+    if (views.empty()) return result;
+    std::vector<int64_t> off(views.size() + 1, 0);
+    for (size_t k = 0; k < views.size(); ++k) off[k + 1] = off[k] + static_cast<int64_t>(views[k].size());
+    std::vector<double> x(off.back()), y(off.back()), u(off.back()), v(off.back());
+    for (size_t k = 0; k < views.size(); ++k)
+        for (size_t i = 0; i < views[k].size(); ++i) {
+            const auto o = static_cast<size_t>(off[k]) + i;
+            x[o] = views[k][i].object_xy.x(); y[o] = views[k][i].object_xy.y(); u[o] = views[k][i].image_uv.x(); v[o] = views[k][i].image_uv.y();
+        }
+    std::vector<int32_t> cam(views.size(), 0), ok(views.size());
+    cal_seed_options so{};
+    if (opts.bounds) {
+        const auto& b = *opts.bounds;
+        so.use_bounds = 1; so.fx_min = b.fx_min; so.fx_max = b.fx_max; so.fy_min = b.fy_min; so.fy_max = b.fy_max;
+        so.cx_min = b.cx_min; so.cx_max = b.cx_max; so.cy_min = b.cy_min; so.cy_max = b.cy_max; so.skew_min = b.skew_min; so.skew_max = b.skew_max;
+    }
+    double k5[5]; int32_t cam_ok = 0;
+    std::vector<double> H(9 * views.size()), rms(views.size()), poses(12 * views.size());
+    b200::check(cal_seed_intrinsics(static_cast<int64_t>(views.size()), off.data(), cam.data(), x.data(), y.data(), u.data(), v.data(), 1, &so, 0,
+                                    k5, &cam_ok, ok.data(), H.data(), rms.data(), poses.data()));
+    if (!cam_ok) return result;
+    result.success = true;
+    result.kmtx = CameraMatrix{k5[0], k5[1], k5[2], k5[3], k5[4]};
+    for (size_t k = 0; k < views.size(); ++k) {
+        if (!ok[k]) continue;  // estimate_intrinsics keeps only the views whose homography succeeded (:109-113)
+        ViewEstimateData ved;
+        ved.view_index = k;
+        ved.forward_rms_px = rms[k];
+        ved.homography.success = true;
+        ved.homography.hmtx = Eigen::Map<const Eigen::Matrix<double, 3, 3, Eigen::RowMajor>>(&H[9 * k]);
+        ved.homography.symmetric_rms_px = rms[k];
+        ved.homography.inliers.resize(views[k].size());
+        for (size_t i = 0; i < views[k].size(); ++i) ved.homography.inliers[i] = static_cast<int>(i);
+        Eigen::Matrix3d R = Eigen::Map<const Eigen::Matrix<double, 3, 3, Eigen::RowMajor>>(&poses[12 * k]);
+        ved.c_se3_t.linear() = R;
+        ved.c_se3_t.translation() = Eigen::Vector3d(poses[12 * k + 9], poses[12 * k + 10], poses[12 * k + 11]);
+        result.views.push_back(std::move(ved));
+    }
     return result;
 }
 
