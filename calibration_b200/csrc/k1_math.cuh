@@ -27,6 +27,22 @@ namespace calk {
 
 enum { INTR_NONE = 0, INTR_NOSKEW = 1, INTR_SKEW = 2 };
 
+// 1 / x for the projection's depth: on the device the hardware seed (MUFU.RCP64H, ~20 bits) and two
+// Newton steps, straight-line code — the compiler's own division sequence carries a special-case branch
+// (a reconvergence point in the middle of K1's hot loop).  ~1 ulp; depths are O(1) metres, never denormal.
+CAL_HD double rcp_depth(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0); r = fma(r, e, r);
+    e = fma(-x, r, 1.0); r = fma(r, e, r);
+    e = fma(-x, r, 1.0); r = fma(r, e, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
 // Per-camera constants derived from the intrinsic block
 // [fx, fy, cx, cy, skew, k1, k2, k3, p1, p2 (, tau_x, tau_y)].
 struct CamConst {
@@ -92,7 +108,7 @@ CAL_HD void obs_rows(const CamConst& c, const double* A, double X, double Y, dou
     const double Px = fma(A[0], X, fma(A[1], Y, A[2]));
     const double Py = fma(A[3], X, fma(A[4], Y, A[5]));
     const double Pz = fma(A[6], X, fma(A[7], Y, A[8]));
-    const double iz = 1.0 / Pz;
+    const double iz = rcp_depth(Pz);
     const double mx = Px * iz, my = Py * iz;
     const double x = MODEL == 1 ? mx - c.mx0 : mx;
     const double y = MODEL == 1 ? my - c.my0 : my;
