@@ -40,7 +40,7 @@ class ProblemDesc(C.Structure):
         ("optimize_extrinsics", C.c_int32),
         ("optimize_target_pose", C.c_int32),
         ("optimize_hand_eye", C.c_int32),
-        ("reserved", C.c_int32),
+        ("view_base", C.c_int32),
         ("huber_delta", C.c_double),
     ]
 

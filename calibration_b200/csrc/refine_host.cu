@@ -682,6 +682,9 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
             launch_view_norms(S, Bx, V, h.st); launch_reduce_views(V, nv, h.st); h.launches += 2;
             CUDA_TRY(cudaMemcpyAsync(red, V.red_out, sizeof red, cudaMemcpyDeviceToHost, h.st));
             CUDA_TRY(cudaStreamSynchronize(h.st));
+            if (h.comm) {  // the views of the other ranks
+                if (!h.comm->allreduce_host(&red[0], 1, false) || !h.comm->allreduce_host(&red[3], 1, true)) return fail(CAL_ERR_COMM, h.comm->error());
+            }
             x2 += red[0]; gm = std::max(gm, red[3]);
         }
         x_norm = std::sqrt(x2); gmax = gm;
@@ -702,6 +705,7 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
             launch_view_plus(S, Bx, Vx, t, h.st); launch_reduce_views(V, nv, h.st); h.launches += 2;
             CUDA_TRY(cudaMemcpyAsync(red, V.red_out, sizeof red, cudaMemcpyDeviceToHost, h.st));
             CUDA_TRY(cudaStreamSynchronize(h.st));
+            if (h.comm && !h.comm->allreduce_host(&red[2], 1, false)) return fail(CAL_ERR_COMM, h.comm->error());
             sn += red[2];
         }
         step_norm2 = sn;
@@ -751,6 +755,11 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
             CUDA_TRY(cudaMemcpyAsync(cs.data(), V.c, sizeof(double) * ns, cudaMemcpyDeviceToHost, h.st));
             CUDA_TRY(cudaMemcpyAsync(&failed, V.fail, sizeof failed, cudaMemcpyDeviceToHost, h.st));
             CUDA_TRY(cudaStreamSynchronize(h.st));
+            if (h.comm) {  // a failed view factorisation on any rank invalidates the step on every rank
+                double f = failed ? 1.0 : 0.0;
+                if (!h.comm->allreduce_host(&f, 1, true)) return fail(CAL_ERR_COMM, h.comm->error());
+                failed = f != 0.0;
+            }
             if (failed) ok = false;
             for (int i = 0; i < ns; ++i) { y[i] -= cs[i]; for (int j = 0; j < ns; ++j) Sm[(size_t)i * ns + j] -= Cs[(size_t)i * ns + j]; }
         }
@@ -803,7 +812,6 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
             if (cal_status st = make_candidate(t, step_norm2)) return st;
             if (cal_status st = eval_cost_at(xc, xp.data(), cand_cost)) return st;
         }
-        if (h.comm && views) { double r1 = step_norm2; (void)r1; }
         // ParameterToleranceReached / FunctionToleranceReached: tested before acceptance (B.3-5)
         if (std::sqrt(step_norm2) <= eps * (x_norm + eps)) { term = CAL_TERM_CONVERGENCE; msg = "Parameter tolerance reached."; break; }
         const double cost_change = cost - cand_cost;
@@ -842,7 +850,8 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
         // The normal equations of the last accepted point are still on the device / in the host mirrors: the LM
         // evaluates the Jacobian only at accepted points and x only moves on acceptance, so no extra pass.
         std::vector<double> xf(x_inout, x_inout + na);
-        if (views && !h.comm) {
+        if (views && h.comm) return CAL_OK;  // sharded per-view kinds: the dense covariance would need every rank's views
+        if (views) {
             // ---- block-structured covariance (refine_kernels.cu, k_cov_*): shared block on the host, view blocks on the device ----
             CUDA_TRY(cudaMemsetAsync(V.fail, 0, sizeof(int32_t), h.st));
             launch_schur(S, h.L, h.B, V, ns, std::numeric_limits<double>::infinity(), h.st); h.launches += 3;

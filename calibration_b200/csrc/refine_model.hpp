@@ -51,8 +51,8 @@ struct HostModel {
             for (int c = 0; c < d.n_cams; ++c) add(P, PB_INTR, !oi);
             for (int c = 0; c < d.n_cams; ++c) add(4, PB_QUAT, !oe || c == 0);
             for (int c = 0; c < d.n_cams; ++c) add(3, PB_EUCLID, !oe || c == 0);
-            for (int v = 0; v < d.n_views; ++v) add(4, PB_QUAT, oi && v == 0);
-            for (int v = 0; v < d.n_views; ++v) add(3, PB_EUCLID, oi && v == 0);
+            for (int v = 0; v < d.n_views; ++v) add(4, PB_QUAT, oi && v + d.view_base == 0);
+            for (int v = 0; v < d.n_views; ++v) add(3, PB_EUCLID, oi && v + d.view_base == 0);
             constrained = oi;
         } else {
             const bool oi = d.optimize_intrinsics, oh = d.optimize_hand_eye, ot = d.optimize_target_pose;  // bundle.cpp:98-131

@@ -40,3 +40,51 @@ def shard_problem(problem, rank, world):
                        optimize_intrinsics=bool(d.optimize_intrinsics), optimize_skew=bool(d.optimize_skew),
                        optimize_target_pose=bool(d.optimize_target_pose), optimize_hand_eye=bool(d.optimize_hand_eye),
                        huber_delta=d.huber_delta)
+
+
+def shard_views(problem, x0, rank, world):
+    """Shard of a problem with per-view pose blocks (intrinsics / extrinsics kinds): a contiguous range of VIEWS
+    (balanced by observation count) with all their residual blocks, the shared parameter blocks replicated.
+    Returns (sub-problem, its start vector, (first view, one past the last view)).  The gauge of the extrinsics
+    kind fixes GLOBAL view 0 (extrinsics.cpp:133-139): the shard carries its view offset in desc.view_base."""
+    from . import abi
+    d = problem.desc
+    if d.kind == abi.KIND_BUNDLE:
+        raise ValueError("the bundle kind has no per-view unknowns: use shard_problem")
+    nv, nc = int(d.n_views), int(d.n_cams)
+    P = 12 if d.model == abi.MODEL_SCHEIMPFLUG_BC5 else 10
+    bview = np.arange(d.n_blocks, dtype=np.int32) if d.kind == abi.KIND_INTRINSICS else np.asarray(problem.block_view)
+    blen = np.diff(np.asarray(problem.block_offset))
+    per_view = np.bincount(bview, weights=blen, minlength=nv)
+    bounds = partition_blocks(np.concatenate([[0], np.cumsum(per_view)]).astype(np.int64), world)
+    v0, v1 = int(bounds[rank]), int(bounds[rank + 1])
+    sel = np.flatnonzero((bview >= v0) & (bview < v1))
+    off = np.asarray(problem.block_offset)
+    idx = np.concatenate([np.arange(off[b], off[b + 1]) for b in sel]).astype(np.int64) if len(sel) else np.zeros(0, dtype=np.int64)
+    new_off = np.concatenate([[0], np.cumsum(blen[sel])]).astype(np.int64)
+    sub = abi.Problem(d.kind, d.model, nc, v1 - v0, problem.x[idx], problem.y[idx], problem.u[idx], problem.v[idx], new_off,
+                      np.asarray(problem.block_cam)[sel], block_view=(bview[sel] - v0).astype(np.int32),
+                      optimize_intrinsics=bool(d.optimize_intrinsics), optimize_skew=bool(d.optimize_skew),
+                      optimize_extrinsics=bool(d.optimize_extrinsics), huber_delta=d.huber_delta)
+    sub.desc.view_base = v0
+    x0 = np.asarray(x0)
+    n_shared = P if d.kind == abi.KIND_INTRINSICS else (P + 7) * nc
+    q = x0[n_shared:n_shared + 4 * nv].reshape(nv, 4)[v0:v1]
+    t = x0[n_shared + 4 * nv:].reshape(nv, 3)[v0:v1]
+    return sub, np.concatenate([x0[:n_shared], q.ravel(), t.ravel()]), (v0, v1)
+
+
+def gather_views(x_local, x_full_like, problem, view_range):
+    """Writes a shard's converged view poses back into a full-size parameter vector (shared part from x_local)."""
+    from . import abi
+    d = problem.desc
+    nv, nc = int(d.n_views), int(d.n_cams)
+    P = 12 if d.model == abi.MODEL_SCHEIMPFLUG_BC5 else 10
+    n_shared = P if d.kind == abi.KIND_INTRINSICS else (P + 7) * nc
+    v0, v1 = view_range
+    out = np.array(x_full_like, dtype=np.float64)
+    out[:n_shared] = x_local[:n_shared]
+    nl = v1 - v0
+    out[n_shared + 4 * v0:n_shared + 4 * v1] = x_local[n_shared:n_shared + 4 * nl]
+    out[n_shared + 4 * nv + 3 * v0:n_shared + 4 * nv + 3 * v1] = x_local[n_shared + 4 * nl:]
+    return out

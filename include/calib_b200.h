@@ -75,7 +75,8 @@ typedef struct cal_problem_desc {
     int32_t optimize_extrinsics;  /* extrinsics kind */
     int32_t optimize_target_pose; /* bundle kind */
     int32_t optimize_hand_eye;    /* bundle kind */
-    int32_t reserved;
+    int32_t view_base;            /* multi-GPU shards of the per-view kinds: global index of this shard's view 0
+                                     (the gauge fixes GLOBAL view 0, extrinsics.cpp:133-139); 0 otherwise */
     double huber_delta;           /* OptimOptions::huber_delta; <= 0 disables the loss */
 } cal_problem_desc;
 

@@ -69,3 +69,33 @@ def test_partition_blocks_balanced_and_contiguous():
         assert per.sum() == off[-1] and per.max() - per.min() <= 2 * lens.max()
     with pytest.raises(ValueError):
         sharding.chunk_shard(100, 16, 0, 4)
+
+
+def test_view_shards_partition_the_per_view_kinds():
+    """shard_views: every residual block lands in exactly one shard together with its view's pose block, the shared
+    blocks are replicated, and the oracle's cost is additive over the shards (the per-view kinds' exchange step adds
+    the Schur complement on top, checked on two GPUs by tools/mgpu_views_check.py)."""
+    import sys
+    for p in (ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import oracle_lib as O
+    from calibration_b200 import sharding, synth
+    for mk, n_shared in ((lambda: synth.make_extrinsics(n_cams=3, n_views=41, drop_fraction=0.3), 3 * 17), (lambda: synth.make_intrinsics(n_views=23), 10)):
+        prob, x0, _ = mk()
+        c_full, _, _ = O.refine_eval(prob, x0)
+        for world in (2, 3):
+            tot, blocks, views = 0.0, 0, []
+            for r in range(world):
+                sub, xl, (v0, v1) = sharding.shard_views(prob, x0, r, world)
+                assert sub.desc.view_base == v0 and sub.desc.n_views == v1 - v0 and len(xl) == n_shared + 7 * (v1 - v0)
+                assert np.array_equal(xl[:n_shared], x0[:n_shared])
+                back = sharding.gather_views(xl, np.zeros_like(x0), prob, (v0, v1))
+                nv = prob.desc.n_views
+                assert np.array_equal(back[n_shared + 4 * v0:n_shared + 4 * v1], x0[n_shared + 4 * v0:n_shared + 4 * v1])
+                assert np.array_equal(back[n_shared + 4 * nv + 3 * v0:n_shared + 4 * nv + 3 * v1], x0[n_shared + 4 * nv + 3 * v0:n_shared + 4 * nv + 3 * v1])
+                c, _, _ = O.refine_eval(sub, xl)
+                tot += c; blocks += int(sub.desc.n_blocks); views.append((v0, v1))
+            assert blocks == prob.desc.n_blocks and views[0][0] == 0 and views[-1][1] == prob.desc.n_views
+            assert all(views[i][1] == views[i + 1][0] for i in range(world - 1))
+            assert abs(tot - c_full) <= 1e-12 * c_full
