@@ -484,38 +484,16 @@ struct LMState {
 
 // Build the dense tangent-space system (canonical order) from the last Jacobian pass.
 cal_status dense_system(cal_refine_handle& h, std::vector<double>& H, std::vector<double>& g) {
-    const int n = h.n_tan, ns = h.ns;
-    H.assign((size_t)n * n, 0.0); g.assign(n, 0.0);
-    for (int i = 0; i < ns; ++i) { g[i] = h.gs[i]; for (int j = 0; j < ns; ++j) H[(size_t)i * n + j] = h.Hss[(size_t)i * ns + j]; }
     const ProblemShape& S = h.S;
-    if (S.n_views == 0) return CAL_OK;
+    if (S.n_views == 0) { h.assemble_dense(h.Hss, h.gs, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, H, g); return CAL_OK; }
     const int nv = S.n_views, PI = S.PI; const int64_t nblk = h.L.n_blk;
     std::vector<double> Hpp((size_t)nv * 36), gp((size_t)nv * 6), Evc((size_t)36 * nblk), Evi((size_t)6 * std::max(PI, 1) * nblk);
     CUDA_TRY(cudaMemcpy(Hpp.data(), h.V.Hpp, Hpp.size() * sizeof(double), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(gp.data(), h.V.gp, gp.size() * sizeof(double), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(Evc.data(), h.B.blk_Evc, Evc.size() * sizeof(double), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(Evi.data(), h.B.blk_Evi, Evi.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int v = 0; v < nv; ++v) {
-        if (!h.view_free_host[v]) continue;
-        const PB& q = h.pbs[h.pb_viewq(v)]; const PB& t = h.pbs[h.pb_viewt(v)];
-        int vi[6]; for (int k = 0; k < 3; ++k) { vi[k] = q.toff + k; vi[3 + k] = t.toff + k; }
-        for (int i = 0; i < 6; ++i) { g[vi[i]] = gp[(size_t)v * 6 + i]; for (int j = 0; j < 6; ++j) H[(size_t)vi[i] * n + vi[j]] = Hpp[(size_t)v * 36 + 6 * i + j]; }
-        for (int k = h.view_blk_off_host[v]; k < h.view_blk_off_host[v + 1]; ++k) {
-            const int64_t b = h.view_blk_idx_host[k]; const int cam = h.blk_cam_host[b];
-            const PB& pi = h.pbs[h.pb_intr(cam)];
-            if (S.cam_pose_kind == 1 && !h.pbs[h.pb_camq(cam)].constant) {
-                const int cq = h.pbs[h.pb_camq(cam)].toff, ct = h.pbs[h.pb_camt(cam)].toff;
-                for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) {
-                    const int col = j < 3 ? cq + j : ct + j - 3; const double a = Evc[(size_t)(6 * i + j) * nblk + b];
-                    H[(size_t)vi[i] * n + col] += a; H[(size_t)col * n + vi[i]] += a;
-                }
-            }
-            if (!pi.constant && PI > 0) for (int i = 0; i < 6; ++i) for (int j = 0; j < PI; ++j) {
-                const double a = Evi[(size_t)(PI * i + j) * nblk + b];
-                H[(size_t)vi[i] * n + pi.toff + j] += a; H[(size_t)(pi.toff + j) * n + vi[i]] += a;
-            }
-        }
-    }
+    h.assemble_dense(h.Hss, h.gs, Hpp.data(), gp.data(), Evc.data(), Evi.data(), nblk, h.view_free_host.data(), h.view_blk_off_host.data(),
+                     h.view_blk_idx_host.data(), h.blk_cam_host.data(), H, g);
     return CAL_OK;
 }
 

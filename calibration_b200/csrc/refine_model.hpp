@@ -155,6 +155,39 @@ struct HostModel {
             }
         }
     }
+
+    // Dense tangent-space system (canonical order) = shared block + per-view 6x6 blocks + their couplings,
+    // from the per-view sums H_pp [n_views][36], g_p [n_views][6] and the per-block couplings
+    // E_vc [36][n_blk] (view x camera pose), E_vi [6 PI][n_blk] (view x intrinsics); views are given as a CSR
+    // of device block ids.  Only used for cal_refine_eval's dense output and the dense covariance path.
+    void assemble_dense(const std::vector<double>& Hss, const std::vector<double>& gs, const double* Hpp, const double* gp,
+                        const double* Evc, const double* Evi, int64_t nblk, const char* view_free, const int32_t* view_blk_off,
+                        const int32_t* view_blk_idx, const int32_t* blk_cam, std::vector<double>& H, std::vector<double>& g) const {
+        const int n = n_tan, PI = S.PI;
+        H.assign((size_t)n * n, 0.0); g.assign(n, 0.0);
+        for (int i = 0; i < ns; ++i) { g[i] = gs[i]; for (int j = 0; j < ns; ++j) H[(size_t)i * n + j] = Hss[(size_t)i * ns + j]; }
+        for (int v = 0; v < S.n_views; ++v) {
+            if (!view_free[v]) continue;
+            const PB& q = pbs[pb_viewq(v)]; const PB& t = pbs[pb_viewt(v)];
+            int vi[6]; for (int k = 0; k < 3; ++k) { vi[k] = q.toff + k; vi[3 + k] = t.toff + k; }
+            for (int i = 0; i < 6; ++i) { g[vi[i]] = gp[(size_t)v * 6 + i]; for (int j = 0; j < 6; ++j) H[(size_t)vi[i] * n + vi[j]] = Hpp[(size_t)v * 36 + 6 * i + j]; }
+            for (int k = view_blk_off[v]; k < view_blk_off[v + 1]; ++k) {
+                const int64_t b = view_blk_idx[k]; const int cam = blk_cam[b];
+                const PB& pi = pbs[pb_intr(cam)];
+                if (S.cam_pose_kind == 1 && !pbs[pb_camq(cam)].constant) {
+                    const int cq = pbs[pb_camq(cam)].toff, ct = pbs[pb_camt(cam)].toff;
+                    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) {
+                        const int col = j < 3 ? cq + j : ct + j - 3; const double a = Evc[(size_t)(6 * i + j) * nblk + b];
+                        H[(size_t)vi[i] * n + col] += a; H[(size_t)col * n + vi[i]] += a;
+                    }
+                }
+                if (!pi.constant && PI > 0) for (int i = 0; i < 6; ++i) for (int j = 0; j < PI; ++j) {
+                    const double a = Evi[(size_t)(PI * i + j) * nblk + b];
+                    H[(size_t)vi[i] * n + pi.toff + j] += a; H[(size_t)(pi.toff + j) * n + vi[i]] += a;
+                }
+            }
+        }
+    }
 };
 
 }  // namespace calk

@@ -26,6 +26,7 @@ def emul():
     L = C.CDLL(SO)
     L.emul_bundle_eval.argtypes = [C.POINTER(abi.ProblemDesc), abi.c_double_p, abi.c_double_p, abi.c_double_p, abi.c_double_p]
     L.emul_tangent_count.argtypes = [C.POINTER(abi.ProblemDesc)]
+    L.emul_views_eval.argtypes = L.emul_bundle_eval.argtypes
     return L
 
 
@@ -70,3 +71,31 @@ def test_emulated_pass_ragged_views(emul):
     cost = C.c_double(); g = np.zeros(n); H = np.zeros((n, n))
     assert emul.emul_bundle_eval(C.byref(p2.desc), abi.dptr(abi.as_f64(x0)), C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g), abi.dptr(H)) == 0
     assert abs(cost.value - c_o) <= 1e-12 * abs(c_o) and np.abs(H - H_o).max() <= 1e-10 * np.abs(H_o).max()
+
+
+VIEW_CASES = {
+    "intrinsics": lambda: synth.make_intrinsics(),
+    "intrinsics_skew": lambda: synth.make_intrinsics(optimize_skew=True),
+    "intrinsics_no_loss": lambda: synth.make_intrinsics(huber_delta=-1.0),
+    "intrinsics_scheimpflug_skew": lambda: synth.make_intrinsics(model=abi.MODEL_SCHEIMPFLUG_BC5, optimize_skew=True),
+    "extrinsics": lambda: synth.make_extrinsics(n_views=30),
+    "extrinsics_missing_views": lambda: synth.make_extrinsics(n_cams=3, n_views=40, drop_fraction=0.3),
+    "extrinsics_fixed_intrinsics": lambda: synth.make_extrinsics(n_cams=3, n_views=25, optimize_intrinsics=False),
+    "extrinsics_fixed_extrinsics": lambda: synth.make_extrinsics(n_views=25, optimize_extrinsics=False),
+    "extrinsics_skew": lambda: synth.make_extrinsics(n_views=25, optimize_skew=True),
+}
+
+
+@pytest.mark.parametrize("name", sorted(VIEW_CASES))
+def test_emulated_per_view_kinds_match_oracle(emul, name):
+    """compose_intrinsics / compose_extrinsics, the view- and camera-type chain-rule transforms and the dense
+    assembly (per-view 6x6 blocks + couplings) of the kinds the Schur kernels serve."""
+    prob, x0, _ = VIEW_CASES[name]()
+    n = emul.emul_tangent_count(C.byref(prob.desc))
+    c_o, g_o, H_o = O.refine_eval(prob, x0)
+    assert n == len(g_o)
+    cost = C.c_double(); g = np.zeros(n); H = np.zeros((n, n))
+    assert emul.emul_views_eval(C.byref(prob.desc), abi.dptr(abi.as_f64(x0)), C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g), abi.dptr(H)) == 0
+    assert abs(cost.value - c_o) <= 1e-12 * abs(c_o)
+    assert np.abs(g - g_o).max() <= 1e-10 * np.abs(g_o).max()
+    assert np.abs(H - H_o).max() <= 1e-10 * np.abs(H_o).max()
