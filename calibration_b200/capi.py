@@ -67,6 +67,8 @@ def lib():
                                          C.POINTER(abi.RansacResult), u8p]),
         ("cal_seed_intrinsics", [i64, abi.c_int64_p, ip, dp, dp, dp, dp, C.c_int32, C.POINTER(abi.SeedOptions), C.c_int, dp, ip,
                                  ip, dp, dp, dp]),
+        ("cal_seed_intrinsics_ransac", [i64, abi.c_int64_p, ip, dp, dp, dp, dp, C.c_int32, C.POINTER(abi.SeedOptions),
+                                        C.POINTER(abi.RansacOptions), C.c_int, dp, ip, ip, dp, dp, dp, u8p]),
         ("cal_seed_planar_poses", [i64, abi.c_int64_p, ip, dp, dp, dp, dp, C.c_int32, dp, C.c_int, dp, ip]),
         ("cal_dataset_write", [C.c_char_p, i64, C.c_int32, abi.c_int64_p, ip, dp, dp, dp, dp]),
         ("cal_dataset_open", [C.c_char_p, C.c_int, C.POINTER(abi.Dataset)]),
@@ -312,13 +314,20 @@ def _views(x, y, u, v, view_offset, view_cam):
     return x, y, u, v, off, cam, nv
 
 
-def seed_intrinsics(x, y, u, v, view_offset, view_cam=None, n_cams=1, bounds=None, device=0):
+def seed_intrinsics(x, y, u, v, view_offset, view_cam=None, n_cams=1, bounds=None, device=0, ransac=None):
     """estimate_intrinsics (linear/intrinsics.h:58-59) for every camera, batched on the GPU: Zhang's K,
-    per-view homographies, symmetric rms and poses from the homographies."""
+    per-view homographies, symmetric rms and poses from the homographies.  ransac = RansacOptions switches the
+    per-view homographies to ransac<HomographyEstimator> (IntrinsicsEstimOptions::homography_ransac)."""
     x, y, u, v, off, cam, nv = _views(x, y, u, v, view_offset, view_cam)
     opts = abi.SeedOptions.from_bounds(bounds)
     kmtx = np.zeros((n_cams, 5)); cam_ok = np.zeros(n_cams, dtype=np.int32); ok = np.zeros(nv, dtype=np.int32)
     H = np.zeros((nv, 9)); rms = np.zeros(nv); poses = np.zeros((nv, 12))
+    if ransac is not None:
+        mask = np.zeros(len(x), dtype=np.uint8)
+        _check(lib().cal_seed_intrinsics_ransac(nv, abi.i64ptr(off), abi.i32ptr(cam), abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v),
+                                                n_cams, C.byref(opts), C.byref(ransac), device, abi.dptr(kmtx), abi.i32ptr(cam_ok), abi.i32ptr(ok),
+                                                abi.dptr(H), abi.dptr(rms), abi.dptr(poses), mask.ctypes.data_as(abi.c_uint8_p)))
+        return dict(kmtx=kmtx, cam_success=cam_ok, view_success=ok, hmtx=H.reshape(nv, 3, 3), sym_rms=rms, poses=poses, inlier_mask=mask)
     _check(lib().cal_seed_intrinsics(nv, abi.i64ptr(off), abi.i32ptr(cam), abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v),
                                      n_cams, C.byref(opts), device, abi.dptr(kmtx), abi.i32ptr(cam_ok), abi.i32ptr(ok), abi.dptr(H),
                                      abi.dptr(rms), abi.dptr(poses)))

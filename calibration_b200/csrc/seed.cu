@@ -324,6 +324,31 @@ __global__ void __launch_bounds__(128) k_view_dlt(SeedArgs a) {
     }
 }
 
+// compute_planar_homographies, RANSAC branch (intrinsicsdlt.cpp:50-64): model / h33, symmetric rms over the
+// inliers (already evaluated by the RANSAC kernel; the residual does not depend on the scale of H)
+__global__ void k_seed_from_ransac(int64_t n_views, const cal_ransac_result* __restrict__ res, double* __restrict__ hmtx,
+                                   double* __restrict__ sym_rms, double* __restrict__ zrows, int32_t* __restrict__ success) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_views) return;
+    const cal_ransac_result r = res[v];
+    double H[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) H[i] = r.success ? r.hmtx[i] : ((i % 4 == 0) ? 1.0 : 0.0);
+    if (r.success && fabs(H[8]) > 1e-15) {
+        const double h = H[8];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) H[i] /= h;
+    }
+    double rows[12];
+    zhang_rows(H, rows);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) hmtx[v * 9 + i] = H[i];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) zrows[v * 12 + i] = r.success ? rows[i] : 0.0;
+    sym_rms[v] = r.success ? r.symmetric_rms_px : 0.0;
+    success[v] = r.success ? 1 : 0;
+}
+
 // Zhang's Gram matrix V^T V (upper triangle, 21) of one camera: one CTA per camera, strided
 // per-thread sums over the views, fixed-order shared-memory tree.
 __global__ void __launch_bounds__(256) k_zhang_gram(int64_t n_views, const int32_t* __restrict__ view_cam,
@@ -477,10 +502,16 @@ cal_status check_views(int64_t n_views, const int64_t* view_offset, const int32_
 
 }  // namespace
 
-extern "C" cal_status cal_seed_intrinsics(int64_t n_views, const int64_t* view_offset, const int32_t* view_cam, const double* x,
-                                          const double* y, const double* u, const double* v, int32_t n_cams,
-                                          const cal_seed_options* opts, int device, double* kmtx, int32_t* cam_success,
-                                          int32_t* view_success, double* hmtx, double* sym_rms, double* poses) {
+extern "C" cal_status cal_ransac_homography_batch_dev(int64_t n_problems, int32_t n, const double* x_dev, const double* y_dev,
+                                                      const double* u_dev, const double* v_dev, const cal_ransac_options* opts,
+                                                      int seed_per_problem, cal_ransac_result* results_dev,
+                                                      uint8_t* inlier_mask_dev, float* ms);
+
+extern "C" cal_status cal_seed_intrinsics_ransac(int64_t n_views, const int64_t* view_offset, const int32_t* view_cam, const double* x,
+                                                 const double* y, const double* u, const double* v, int32_t n_cams,
+                                                 const cal_seed_options* opts, const cal_ransac_options* ransac, int device, double* kmtx,
+                                                 int32_t* cam_success, int32_t* view_success, double* hmtx, double* sym_rms,
+                                                 double* poses, uint8_t* inlier_mask) {
     if (!x || !y || !u || !v || !kmtx || !cam_success) return sfail(CAL_ERR_INVALID_ARGUMENT, "null argument");
     int64_t n_obs = 0;
     if (cal_status s = check_views(n_views, view_offset, view_cam, n_cams, &n_obs)) return s;
@@ -494,9 +525,26 @@ extern "C" cal_status cal_seed_intrinsics(int64_t n_views, const int64_t* view_o
     DevBuf<double> dH, drms, drows, dgram, dk, dposes; DevBuf<int32_t> dsucc, dcamok;
     SCUDA(dH.alloc(9 * n_views)); SCUDA(drms.alloc(n_views)); SCUDA(drows.alloc(12 * n_views)); SCUDA(dsucc.alloc(n_views));
     SCUDA(dgram.alloc(22 * n_cams)); SCUDA(dk.alloc(5 * n_cams)); SCUDA(dcamok.alloc(n_cams)); SCUDA(dposes.alloc(12 * n_views));
-    SeedArgs a{n_views, in.off.p, in.cam.p, in.x.p, in.y.p, in.u.p, in.v.p, nullptr, dH.p, drms.p, drows.p, dsucc.p, nullptr};
     const unsigned groups = (unsigned)((n_views + 31) / 32);
-    k_view_dlt<false><<<(groups + 3) / 4, 128, 0, st>>>(a);
+    DevBuf<cal_ransac_result> dres; DevBuf<uint8_t> dmask;
+    if (ransac) {
+        // IntrinsicsEstimOptions::homography_ransac (intrinsicsdlt.cpp:50-64): every view is one problem of the batched
+        // RANSAC kernel, all with the seed of the options (each reference call constructs its own engine from opts.seed)
+        const int64_t n = view_offset[1] - view_offset[0];
+        for (int64_t k = 0; k < n_views; ++k)
+            if (view_offset[k + 1] - view_offset[k] != n)
+                return sfail(CAL_ERR_INVALID_ARGUMENT, "homography_ransac: the batched RANSAC kernel needs views of equal size");
+        if (n <= 0 || n > 0x7fffffff) return sfail(CAL_ERR_INVALID_ARGUMENT, "homography_ransac: empty views");
+        SCUDA(dres.alloc(n_views)); if (inlier_mask) SCUDA(dmask.alloc((size_t)n_views * n));
+        SCUDA(cudaStreamSynchronize(st));  // the inputs are in place before the RANSAC launch on the default stream
+        if (cal_status rs = cal_ransac_homography_batch_dev(n_views, (int32_t)n, in.x.p, in.y.p, in.u.p, in.v.p, ransac, 0, dres.p,
+                                                            inlier_mask ? dmask.p : nullptr, nullptr)) return rs;
+        k_seed_from_ransac<<<(unsigned)((n_views + 127) / 128), 128, 0, st>>>(n_views, dres.p, dH.p, drms.p, drows.p, dsucc.p);
+        if (inlier_mask) SCUDA(cudaMemcpyAsync(inlier_mask, dmask.p, (size_t)n_views * n, cudaMemcpyDeviceToHost, st));
+    } else {
+        SeedArgs a{n_views, in.off.p, in.cam.p, in.x.p, in.y.p, in.u.p, in.v.p, nullptr, dH.p, drms.p, drows.p, dsucc.p, nullptr};
+        k_view_dlt<false><<<(groups + 3) / 4, 128, 0, st>>>(a);
+    }
     k_zhang_gram<<<n_cams, 256, 0, st>>>(n_views, in.cam.p, dsucc.p, drows.p, dgram.p);
     std::vector<double> gram(22 * (size_t)n_cams);
     SCUDA(cudaMemcpyAsync(gram.data(), dgram.p, gram.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -530,6 +578,14 @@ extern "C" cal_status cal_seed_intrinsics(int64_t n_views, const int64_t* view_o
     SCUDA(cudaStreamSynchronize(st));
     SCUDA(cudaGetLastError());
     return CAL_OK;
+}
+
+extern "C" cal_status cal_seed_intrinsics(int64_t n_views, const int64_t* view_offset, const int32_t* view_cam, const double* x,
+                                          const double* y, const double* u, const double* v, int32_t n_cams,
+                                          const cal_seed_options* opts, int device, double* kmtx, int32_t* cam_success,
+                                          int32_t* view_success, double* hmtx, double* sym_rms, double* poses) {
+    return cal_seed_intrinsics_ransac(n_views, view_offset, view_cam, x, y, u, v, n_cams, opts, nullptr, device, kmtx, cam_success,
+                                      view_success, hmtx, sym_rms, poses, nullptr);
 }
 
 extern "C" cal_status cal_seed_planar_poses(int64_t n_views, const int64_t* view_offset, const int32_t* view_cam, const double* x,

@@ -262,6 +262,15 @@ cal_status cal_seed_intrinsics(int64_t n_views, const int64_t* view_offset, cons
                                const double* y, const double* u, const double* v, int32_t n_cams,
                                const cal_seed_options* opts, int device, double* kmtx, int32_t* cam_success,
                                int32_t* view_success, double* hmtx, double* sym_rms, double* poses);
+/* The same with IntrinsicsEstimOptions::homography_ransac set (intrinsicsdlt.cpp:50-64): every view's homography
+ * comes from ransac<HomographyEstimator> with the options' seed (the batched RANSAC kernel; views must have equal
+ * size), hmtx = model / h33, sym_rms over the inliers; inlier_mask ([n_views][n] bytes) may be NULL.
+ * ransac == NULL is cal_seed_intrinsics.  (cal_ransac_options is declared above.) */
+cal_status cal_seed_intrinsics_ransac(int64_t n_views, const int64_t* view_offset, const int32_t* view_cam, const double* x,
+                                      const double* y, const double* u, const double* v, int32_t n_cams,
+                                      const cal_seed_options* opts, const cal_ransac_options* ransac, int device, double* kmtx,
+                                      int32_t* cam_success, int32_t* view_success, double* hmtx, double* sym_rms, double* poses,
+                                      uint8_t* inlier_mask);
 /* estimate_planar_pose(view, CameraMatrix) for every view (src/estimation/linear/planarpose_linear.cpp:54-76
  * with pose_from_homography_normalized :17-52); kmtx as above; identity for views with < 4 points
  * or a failed DLT (view_success, optional, tells which). */

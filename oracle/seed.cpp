@@ -20,6 +20,8 @@
 #include "oracle_math.hpp"
 
 extern "C" int orc_homography_dlt(int32_t n, const double* x, const double* y, const double* u, const double* v, double* hmtx);
+extern "C" int orc_ransac_homography(int32_t n, const double* x, const double* y, const double* u, const double* v,
+                                     const orc_ransac_options* o, const int32_t* sample_idx, orc_ransac_result* res, uint8_t* inlier_mask);
 
 namespace {
 
@@ -204,6 +206,42 @@ int orc_estimate_intrinsics(int64_t n_views, const int64_t* view_offset, const d
         double Hi[9]; orc::mat3_inv(H, Hi);
         double s = 0; for (int i = 0; i < n; ++i) s += sym_residual(H, Hi, x[o + i], y[o + i], u[o + i], v[o + i]);
         sym_rms[k] = std::sqrt(s / (2.0 * n));
+        view_success[k] = 1;
+        valid.insert(valid.end(), H, H + 9);
+    }
+    if (n_views == 0) return 0;
+    if (!orc_zhang_intrinsics((int64_t)valid.size() / 9, valid.data(), kmtx5)) return 0;
+    if (bounds10) orc_sanitize_intrinsics(kmtx5, bounds10);
+    for (int64_t k = 0; k < n_views; ++k)
+        if (view_success[k]) orc_pose_from_homography(kmtx5, hmtx + 9 * k, poses + 12 * k, nullptr, nullptr);
+    return 1;
+}
+
+// estimate_intrinsics with IntrinsicsEstimOptions::homography_ransac (intrinsicsdlt.cpp:50-64): per view
+// ransac<HomographyEstimator>(view, opts), model / h33, symmetric rms over the inliers.
+int orc_estimate_intrinsics_ransac(int64_t n_views, const int64_t* view_offset, const double* x, const double* y, const double* u,
+                                   const double* v, const double* bounds10, const orc_ransac_options* ro, double* kmtx5,
+                                   int32_t* view_success, double* hmtx, double* sym_rms, double* poses, uint8_t* inlier_mask) {
+    const double I[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+    std::vector<double> valid;
+    for (int64_t k = 0; k < n_views; ++k) {
+        const int64_t o = view_offset[k]; const int n = (int)(view_offset[k + 1] - o);
+        double* H = hmtx + 9 * k;
+        view_success[k] = 0; sym_rms[k] = 0.0;
+        std::memcpy(poses + 12 * k, I, sizeof I);
+        for (int i = 0; i < 9; ++i) H[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        if (n < 4) continue;
+        orc_ransac_result r;
+        std::vector<uint8_t> mask(n);
+        orc_ransac_homography(n, x + o, y + o, u + o, v + o, ro, nullptr, &r, mask.data());
+        if (inlier_mask) std::memcpy(inlier_mask + o, mask.data(), n);
+        if (!r.success) continue;
+        std::memcpy(H, r.hmtx, sizeof r.hmtx);
+        if (std::fabs(H[8]) > 1e-15) { const double h = H[8]; for (int i = 0; i < 9; ++i) H[i] /= h; }
+        double Hi[9]; orc::mat3_inv(H, Hi);
+        double s = 0; int cnt = 0;
+        for (int i = 0; i < n; ++i) if (mask[i]) { s += sym_residual(H, Hi, x[o + i], y[o + i], u[o + i], v[o + i]); ++cnt; }
+        sym_rms[k] = cnt ? std::sqrt(s / (2.0 * cnt)) : INFINITY;
         view_success[k] = 1;
         valid.insert(valid.end(), H, H + 9);
     }

@@ -58,6 +58,8 @@ def lib():
         L.orc_sanitize_intrinsics.argtypes = [dp, dp]
         L.orc_pose_from_homography.argtypes = [dp, dp, dp, dp, dp]
         L.orc_estimate_intrinsics.argtypes = [i64, abi.c_int64_p, dp, dp, dp, dp, dp, dp, ip, dp, dp, dp]
+        L.orc_estimate_intrinsics_ransac.argtypes = [i64, abi.c_int64_p, dp, dp, dp, dp, dp, C.POINTER(abi.RansacOptions), dp, ip, dp, dp, dp,
+                                                     abi.c_uint8_p]
         _lib = L
     return _lib
 
@@ -182,6 +184,20 @@ def pose_from_homography(k5, H):
     ok = lib().orc_pose_from_homography(abi.dptr(abi.as_f64(k5)), abi.dptr(abi.as_f64(np.asarray(H).ravel())), abi.dptr(out),
                                         abi.dptr(sc), abi.dptr(cd))
     return bool(ok), pose12_to_T(out), float(sc[0]), float(cd[0])
+
+
+def estimate_intrinsics_ransac(x, y, u, v, view_offset, ransac_opts, bounds10=None):
+    """estimate_intrinsics with IntrinsicsEstimOptions::homography_ransac, one camera."""
+    x, y, u, v = (abi.as_f64(a) for a in (x, y, u, v))
+    off = np.ascontiguousarray(view_offset, dtype=np.int64)
+    nv = len(off) - 1
+    k5 = np.zeros(5); succ = np.zeros(nv, dtype=np.int32); H = np.zeros((nv, 9)); rms = np.zeros(nv); poses = np.zeros((nv, 12))
+    mask = np.zeros(len(x), dtype=np.uint8)
+    b = None if bounds10 is None else abi.as_f64(bounds10)
+    ok = lib().orc_estimate_intrinsics_ransac(nv, abi.i64ptr(off), abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v), abi.dptr(b),
+                                              C.byref(ransac_opts), abi.dptr(k5), abi.i32ptr(succ), abi.dptr(H), abi.dptr(rms), abi.dptr(poses),
+                                              mask.ctypes.data_as(abi.c_uint8_p))
+    return dict(success=bool(ok), kmtx=k5, view_success=succ, hmtx=H.reshape(nv, 3, 3), sym_rms=rms, poses=poses, inlier_mask=mask)
 
 
 def estimate_intrinsics(x, y, u, v, view_offset, bounds10=None):

@@ -78,6 +78,28 @@ def test_bounds_sanitize_like_reference():
     assert rel(g["kmtx"][0], o["kmtx"]) < 1e-7 and rel(g["poses"], o["poses"]) < 1e-7
 
 
+def test_intrinsics_with_homography_ransac_matches_oracle():
+    """IntrinsicsEstimOptions::homography_ransac: every view through the batched RANSAC kernel (10 % of the corners
+    of every view replaced by gross outliers), then Zhang and the pose decomposition — same inlier sets, K and poses
+    as the oracle's per-view ransac<HomographyEstimator>."""
+    prob, _, _ = synth.make_bundle(seed=5, n_cams=1, n_poses=40)
+    rng = np.random.default_rng(9)
+    off = np.asarray(prob.block_offset)
+    u, v = prob.u.copy(), prob.v.copy()
+    bad = rng.random(len(u)) < 0.10
+    u[bad] = rng.uniform(0, 1280, bad.sum()); v[bad] = rng.uniform(0, 720, bad.sum())
+    ro = abi.RansacOptions.default()
+    g = capi.seed_intrinsics(prob.x, prob.y, u, v, off, ransac=ro)
+    o = O.estimate_intrinsics_ransac(prob.x, prob.y, u, v, off, ro)
+    assert o["success"] and g["cam_success"][0] == 1 and np.array_equal(g["view_success"], o["view_success"])
+    assert np.array_equal(g["inlier_mask"], o["inlier_mask"])
+    assert (g["inlier_mask"][bad] == 0).mean() > 0.95 and (g["inlier_mask"][~bad] == 1).mean() > 0.95
+    assert rel(g["kmtx"][0], o["kmtx"]) < 1e-7 and rel(g["hmtx"], o["hmtx"]) < 1e-8
+    assert np.allclose(g["sym_rms"], o["sym_rms"], rtol=1e-8, atol=1e-9) and rel(g["poses"], o["poses"]) < 1e-7
+    with pytest.raises(ValueError, match="views of equal size"):
+        capi.seed_intrinsics(prob.x[:-1], prob.y[:-1], u[:-1], v[:-1], np.concatenate([off[:-1], [off[-1] - 1]]), ransac=ro)
+
+
 def test_planar_poses_match_oracle():
     xs, ys, us, vs, off, cam, n_cams = noisy_multicam()
     kmtx = np.array([[1000.0, 1005.0, 640.0, 360.0, 0.0], [1010.0, 1015.0, 640.0, 360.0, 0.5], [990.0, 1000.0, 630.0, 350.0, 0.0]])
