@@ -369,9 +369,16 @@ __device__ __forceinline__ void k1_role(const K1Args& P, int64_t tile, int lane,
         if constexpr (VIEW != VIEW_NONE && (ROLE == 0 || RT::owns_cols(ROLE))) {
             const int64_t nb = L.n_blk;
             const bool vfree = RED ? true : (L.blk_vfree[s] != 0);
+            // T = [[TL, 0], [BL, TL / 2]] (view_transform, k1_math.cuh): 18 loads, structural zeros known to the compiler
             double T[36];
 #pragma unroll
-            for (int i = 0; i < 36; ++i) T[i] = B.blk_Tv[(int64_t)i * nb + s];
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int cix = 0; cix < 3; ++cix) T[6 * r + cix] = B.blk_Tv[(int64_t)(6 * r + cix) * nb + s];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cix = 0; cix < 3; ++cix) { T[6 * r + 3 + cix] = 0.0; T[6 * (r + 3) + 3 + cix] = 0.5 * T[6 * r + cix]; }
             // E_vi columns of this role: w T^T N_xi,i[:, j]
             static_for<0, PI>([&](auto cj) {
                 constexpr int j = decltype(cj)::value;
@@ -522,18 +529,21 @@ __global__ void __launch_bounds__(256) k_tile_colsum(const double* __restrict__ 
         partial[(int64_t)blockIdx.x * nvt + v] = a;
     }
 }
-__global__ void k_tile_final(const double* __restrict__ partial, const int32_t* __restrict__ cam_chunk_off, int n_cams, int nvt,
-                             const int32_t* __restrict__ vmap, double* __restrict__ cam_sums, int NV) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_tile_final(const double* __restrict__ partial, const int32_t* __restrict__ cam_chunk_off, int n_cams,
+                                                    int nvt, const int32_t* __restrict__ vmap, double* __restrict__ cam_sums, int NV) {
+    // one warp per (camera, value): lanes stride over the camera's chunk partials, then a fixed shuffle tree
+    const int i = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (i >= n_cams * nvt) return;
     const int cam = i / nvt, v = i % nvt;
     double a = 0.0;
-    for (int c = cam_chunk_off[cam]; c < cam_chunk_off[cam + 1]; ++c) a += partial[(int64_t)c * nvt + v];
-    cam_sums[(int64_t)cam * NV + vmap[v]] = a;
+    for (int c = cam_chunk_off[cam] + lane; c < cam_chunk_off[cam + 1]; c += 32) a += partial[(int64_t)c * nvt + v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if (lane == 0) cam_sums[(int64_t)cam * NV + vmap[v]] = a;
 }
 int launch_tile_reduce(const ProblemShape& S, const EvalBuffers& B, const ReduceDesc& R, int nvt, cudaStream_t st) {
     k_tile_colsum<<<R.n_tile_chunks, 256, 0, st>>>(B.tile_vals, nvt, R.tile_chunks, B.partial_tile);
-    k_tile_final<<<(S.n_cams * nvt + 127) / 128, 128, 0, st>>>(B.partial_tile, R.tile_cam_chunk_off, S.n_cams, nvt, B.tile_vmap, B.cam_sums, S.NV);
+    k_tile_final<<<(S.n_cams * nvt + 7) / 8, 256, 0, st>>>(B.partial_tile, R.tile_cam_chunk_off, S.n_cams, nvt, B.tile_vmap, B.cam_sums, S.NV);
     return 2;
 }
 

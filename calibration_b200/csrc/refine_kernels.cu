@@ -117,7 +117,9 @@ __global__ void k_block_setup(ProblemShape S, DevLayout L, EvalBuffers B) {
         block_frame(bp, Rs, A);
         view_transform(bp, Rs, T);
     }
-    for (int i = 0; i < 36; ++i) B.blk_Tv[(int64_t)i * L.n_blk + b] = T[i];
+    // T = [[TL, 0], [BL, TL / 2]] (view_transform): the fused K1 reads only the 18 entries of TL and BL
+    for (int i = 0; i < 36; ++i)
+        if (!L.fused || i % 6 < 3) B.blk_Tv[(int64_t)i * L.n_blk + b] = T[i];
     for (int s = L.blk_seg_off[b]; s < L.blk_seg_off[b + 1]; ++s)
         for (int i = 0; i < 9; ++i) B.seg_frame[(int64_t)i * L.n_seg + s] = A[i];
 }
