@@ -99,3 +99,18 @@ def test_emulated_per_view_kinds_match_oracle(emul, name):
     assert abs(cost.value - c_o) <= 1e-12 * abs(c_o)
     assert np.abs(g - g_o).max() <= 1e-10 * np.abs(g_o).max()
     assert np.abs(H - H_o).max() <= 1e-10 * np.abs(H_o).max()
+
+
+def test_k1_role_tables_invariants():
+    """K1's compile-time split of the local system over roles and the per-tile value map (k1_roles.hpp): every entry
+    owned once, dense slots, the epilogue's role-locality, and a value map that is a bijection onto the camera row."""
+    src = os.path.join(ROOT, "tests", "host_emul", "roles_check.cpp")
+    so = os.path.join(ROOT, "tests", "host_emul", "_build", "libroles.so")
+    deps = [src] + [os.path.join(ROOT, "calibration_b200", "csrc", f) for f in ("k1_roles.hpp", "k1_math.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([cxx, "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, src], check=True)
+    L = C.CDLL(so)
+    assert L.roles_check() == 0
+    assert [L.roles_of(0, i) for i in range(3)] == [1, 2, 3] and [L.roles_of(1, i) for i in range(3)] == [1, 3, 3]
