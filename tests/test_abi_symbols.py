@@ -55,3 +55,20 @@ def test_validation_errors_mirror_reference():
     prob.block_offset[2] = prob.block_offset[1]  # an empty view
     with pytest.raises(ValueError, match="No observations"):
         capi.RefineHandle(prob)
+
+
+def test_header_is_plain_c_and_a_c_client_links(tmp_path):
+    """include/calib_b200.h is a C header (what cgo / JNI / ctypes bind to): it compiles as C99 and as C++17, and
+    the C example links against the shared library (running it needs a GPU: done in the gpu suite)."""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    (tmp_path / "t.c").write_text('#include "calib_b200.h"\nint main(void) { return (int)sizeof(cal_problem_desc) == 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", str(tmp_path / "t.c")], check=True)
+    (tmp_path / "t.cpp").write_text('#include "calib_b200.h"\nint main() { return 0; }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", str(tmp_path / "t.cpp")], check=True)
+    libdir = os.path.dirname(build.build())
+    exe = os.path.join(ROOT, "examples", "_build", "c_api_example")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I", inc, os.path.join(ROOT, "examples", "c_api_example.c"), "-L", libdir, "-lcalib_b200",
+                    "-lm", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    assert os.path.exists(exe)

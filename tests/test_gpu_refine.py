@@ -304,3 +304,20 @@ def test_solve_reaches_stationary_point_at_scale():
     assert c <= c_gt * (1 + 1e-9)
     step = np.linalg.solve(H + 1e-9 * np.eye(len(g)) * np.trace(H) / len(g), g)
     assert np.abs(step).max() < 1e-3  # function tolerance 1e-9 stops within ~1e-5 px of the stationary point
+
+
+def test_c_client_of_the_abi_runs():
+    """examples/c_api_example.c: a plain C99 program against include/calib_b200.h + libcalib_b200.so (no Python, no
+    torch in the process) recovers the ground truth of its noise-free hand-eye bundle."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from calibration_b200 import build
+    libdir = os.path.dirname(build.build())
+    exe = os.path.join(root, "examples", "_build", "c_api_example")
+    if not os.path.exists(exe):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "c_api_example.c"), "-L", libdir,
+                        "-lcalib_b200", "-lm", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=dict(os.environ, LD_LIBRARY_PATH=libdir))
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "CONVERGENCE" in out.stdout
