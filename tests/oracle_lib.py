@@ -23,7 +23,7 @@ def lib():
     global _lib
     if _lib is None:
         srcs = [os.path.join(_ROOT, "oracle", f) for f in os.listdir(os.path.join(_ROOT, "oracle"))
-                if f.endswith((".cpp", ".hpp", ".h"))]
+                if f.endswith((".cpp", ".hpp", ".h")) or f == "Makefile"]
         if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
             build()
         L = C.CDLL(_SO)
@@ -156,6 +156,49 @@ def ransac_batch(x, y, u, v, opts=None, seed_per_problem=True, threads=0):
     mask = np.zeros((npb, n), dtype=np.uint8)
     L.orc_ransac_homography_batch(npb, n, abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v), C.byref(opts),
                                   int(seed_per_problem), res, mask.ctypes.data_as(abi.c_uint8_p), threads)
+    return res, mask
+
+
+_REF_SO = os.path.join(_ROOT, "oracle", "_ref", "libref_ransac.so")
+_REF_TREE = "/root/reference"
+_ref = None
+
+
+def ref_lib():
+    """oracle/_ref/libref_ransac.so: the reference's own calib::ransac<> template (common/ransac.h:121-194)
+    compiled from where it lies in /root/reference, around the oracle's estimator hooks.  Built here when the
+    reference tree is present; on the GPU box only the prebuilt file is used.  None when neither exists."""
+    global _ref
+    if _ref is None:
+        if os.path.isdir(_REF_TREE):
+            subprocess.run(["make", "-s", "-C", os.path.join(_ROOT, "oracle"), "ref"], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        if not os.path.exists(_REF_SO):
+            return None
+        L = C.CDLL(_REF_SO)
+        dp = abi.c_double_p
+        L.ref_ransac_homography.argtypes = [C.c_int32, dp, dp, dp, dp, C.POINTER(abi.RansacOptions),
+                                            C.POINTER(abi.RansacResult), abi.c_uint8_p]
+        # the harness compiles oracle/ransac.cpp into the same library, with the same flags
+        L.orc_ransac_homography.argtypes = [C.c_int32, dp, dp, dp, dp, C.POINTER(abi.RansacOptions), abi.c_int32_p,
+                                            C.POINTER(abi.RansacResult), abi.c_uint8_p]
+        _ref = L
+    return _ref
+
+
+def ref_ransac(x, y, u, v, opts=None, oracle_twin=False):
+    """The reference's RANSAC loop itself (see ref_lib): (result, inlier mask).  oracle_twin=True runs the
+    oracle's ransac_one as compiled INTO the same library (same flags, no FMA contraction) instead."""
+    L = ref_lib()
+    x, y, u, v = (abi.as_f64(a) for a in (x, y, u, v))
+    opts = opts or abi.RansacOptions.default()
+    res = abi.RansacResult()
+    mask = np.zeros(len(x), dtype=np.uint8)
+    args = (len(x), abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v), C.byref(opts))
+    if oracle_twin:
+        L.orc_ransac_homography(*args, None, C.byref(res), mask.ctypes.data_as(abi.c_uint8_p))
+    else:
+        L.ref_ransac_homography(*args, C.byref(res), mask.ctypes.data_as(abi.c_uint8_p))
     return res, mask
 
 
