@@ -125,6 +125,19 @@ class RansacResult(C.Structure):
     ]
 
 
+class PlaneResult(C.Structure):
+    """cal_plane_ransac_result — PlaneRansacResult (linear/planefit.h:14-19) plus the loop counters."""
+    _fields_ = [
+        ("success", C.c_int32),
+        ("iters", C.c_int32),
+        ("n_inliers", C.c_int32),
+        ("iters_run", C.c_int32),
+        ("plane", C.c_double * 4),
+        ("inlier_rms", C.c_double),
+        ("min_margin", C.c_double),
+    ]
+
+
 class SeedOptions(C.Structure):
     """cal_seed_options: IntrinsicsEstimOptions.bounds (optional CalibrationBounds)."""
     _fields_ = [("use_bounds", C.c_int32), ("reserved", C.c_int32)] + [(n, C.c_double) for n in (

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OUT_DIR = os.path.join(_HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libcalib_b200.so")
-SOURCES = ["k1_fused.cu", "refine_kernels.cu", "refine_host.cu", "axxb.cu", "ransac.cu", "seed.cu", "comm.cpp", "comm_peer.cu", "dataset.cpp"]
+SOURCES = ["k1_fused.cu", "refine_kernels.cu", "refine_host.cu", "axxb.cu", "ransac.cu", "ransac_plane.cu", "seed.cu", "comm.cpp", "comm_peer.cu", "dataset.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",

@@ -74,6 +74,10 @@ def lib():
         ("cal_dataset_open", [C.c_char_p, C.c_int, C.POINTER(abi.Dataset)]),
         ("cal_dataset_close", [C.POINTER(abi.Dataset)]),
         ("cal_dataset_from_planar_json", [C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]),
+        ("cal_ransac_plane_batch", [i64, C.c_int32, dp, dp, dp, C.POINTER(abi.RansacOptions), C.c_int, C.c_int,
+                                    C.POINTER(abi.PlaneResult), u8p]),
+        ("cal_ransac_plane_batch_dev", [i64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(abi.RansacOptions), C.c_int,
+                                        C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
         ("cal_ransac_homography_batch_dev", [i64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(abi.RansacOptions), C.c_int, C.c_void_p, C.c_void_p,
                                              C.POINTER(C.c_float)]),
@@ -303,6 +307,19 @@ def ransac_homography_batch(x, y, u, v, opts=None, seed_per_problem=True, device
     _check(lib().cal_ransac_homography_batch(npb, n, abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v), C.byref(opts),
                                              int(seed_per_problem), device, res,
                                              mask.ctypes.data_as(abi.c_uint8_p) if want_mask else None))
+    return res, mask
+
+
+def ransac_plane_batch(x, y, z, opts=None, seed_per_problem=True, device=0, want_mask=True):
+    """fit_plane_ransac (linear/planefit.h:23-24) batched: x, y, z (n_problems, n) float64.
+    Returns (PlaneResult array, inlier mask)."""
+    x, y, z = (abi.as_f64(a) for a in (x, y, z))
+    npb, n = x.shape
+    opts = opts or abi.RansacOptions.default()
+    res = (abi.PlaneResult * npb)()
+    mask = np.zeros((npb, n), dtype=np.uint8) if want_mask else None
+    _check(lib().cal_ransac_plane_batch(npb, n, abi.dptr(x), abi.dptr(y), abi.dptr(z), C.byref(opts), int(seed_per_problem),
+                                        device, res, mask.ctypes.data_as(abi.c_uint8_p) if want_mask else None))
     return res, mask
 
 

@@ -29,6 +29,7 @@
 
 #include "../../include/calib_b200.h"
 #include "dlt.cuh"
+#include "ransac_sampler.cuh"
 
 extern "C" void cal_set_last_error_(const char* msg);
 
@@ -50,105 +51,6 @@ struct WarpMem {
     unsigned* ref;               // [kBatch][nw] after refit
     unsigned* best;              // [nw]
 };
-
-// ---- std::mt19937_64, state in shared memory, lane-parallel twist ----
-__device__ __forceinline__ unsigned long long mt_temper(unsigned long long z) {
-    z ^= (z >> 29) & 0x5555555555555555ULL;
-    z ^= (z << 17) & 0x71D67FFFEDA60000ULL;
-    z ^= (z << 37) & 0xFFF7EEE000000000ULL;
-    z ^= z >> 43;
-    return z;
-}
-__device__ void mt_seed(unsigned long long* mt, unsigned long long seed, int lane) {
-    unsigned long long xv = seed;
-    if (lane == 0) mt[0] = xv;
-    for (int i = 1; i < 312; ++i) {
-        xv = 6364136223846793005ULL * (xv ^ (xv >> 62)) + (unsigned long long)i;
-        if ((i & 31) == lane) mt[i] = xv;
-    }
-    __syncwarp();
-}
-__device__ void mt_twist(unsigned long long* mt, int lane) {
-    const unsigned long long UP = 0xFFFFFFFF80000000ULL, LO = 0x7FFFFFFFULL, A = 0xB5026F5AA96619E9ULL;
-    for (int base = 0; base < 312; base += 32) {
-        const int i = base + lane;
-        unsigned long long nv = 0;
-        if (i < 312) {
-            const unsigned long long yv = (mt[i] & UP) | (mt[(i + 1) % 312] & LO);
-            nv = mt[(i + 156) % 312] ^ (yv >> 1) ^ ((yv & 1ULL) ? A : 0ULL);
-        }
-        __syncwarp();
-        if (i < 312) mt[i] = nv;
-        __syncwarp();
-    }
-}
-// one engine output (warp-uniform)
-__device__ __forceinline__ unsigned long long mt_next(unsigned long long* mt, int& pos, int lane) {
-    if (pos >= 312) { mt_twist(mt, lane); pos = 0; }
-    return mt_temper(mt[pos++]);
-}
-// uniform_int_distribution<unsigned long>{0, range-1}: Lemire (uniform_int_dist.h:252-281), warp-uniform
-__device__ unsigned long long lemire_uniform(unsigned long long* mt, int& pos, int lane, unsigned long long range) {
-    unsigned long long r = mt_next(mt, pos, lane);
-    unsigned long long low = r * range, hi = __umul64hi(r, range);
-    if (low < range) {
-        const unsigned long long threshold = (0ULL - range) % range;
-        while (low < threshold) { r = mt_next(mt, pos, lane); low = r * range; hi = __umul64hi(r, range); }
-    }
-    return hi;
-}
-// std::sample(0..N-1, 4) — libstdc++ selection sampling (stl_algo.h:5841-5907).  Results are warp-uniform.
-__device__ void sample4(unsigned long long* mt, int& pos, int lane, int N, int* idx) {
-    unsigned long long uns = (unsigned long long)N;
-    int need = N < 4 ? N : 4, first = 0, o = 0;
-    bool slow = false;
-    while (need != 0 && uns >= 2 && !slow) {
-        if (pos >= 312) { mt_twist(mt, lane); pos = 0; }
-        const int avail = 312 - pos;
-        const unsigned long long pairs_left = uns / 2;
-        int B = 32; if (avail < B) B = avail; if (pairs_left < (unsigned long long)B) B = (int)pairs_left;
-        unsigned p0 = 0xffffffffu, p1 = 0xffffffffu; bool rej = false;
-        if (lane < B) {
-            const unsigned long long uj = uns - 2ULL * lane, b1 = uj - 1ULL, range = uj * b1;
-            const unsigned long long r = mt_temper(mt[pos + lane]);
-            const unsigned long long low = r * range, hi = __umul64hi(r, range);
-            rej = low < range && low < (0ULL - range) % range;   // would redraw: leave the fast path
-            if (N < 65536) { const unsigned h32 = (unsigned)hi, b32 = (unsigned)b1; p0 = h32 / b32; p1 = h32 - p0 * b32; }
-            else { p0 = (unsigned)(hi / b1); p1 = (unsigned)(hi % b1); }
-        }
-        if (__any_sync(kFull, rej)) { slow = true; break; }
-        unsigned m = __ballot_sync(kFull, lane < B && (p0 < (unsigned)need || p1 < (unsigned)need));
-        int consumed = B; bool done = false;
-        while (m) {
-            const int j = __ffs(m) - 1; m &= m - 1;
-            const unsigned a = __shfl_sync(kFull, p0, j), b = __shfl_sync(kFull, p1, j);
-            if (a < (unsigned)need) { idx[o++] = first + 2 * j; --need; }
-            if (need == 0) { consumed = j + 1; done = true; break; }
-            if (b < (unsigned)need) { idx[o++] = first + 2 * j + 1; --need; }
-            if (need == 0) { consumed = j + 1; done = true; break; }
-        }
-        pos += consumed;
-        if (!done) { uns -= 2ULL * B; first += 2 * B; }
-    }
-    if (slow) {  // exact sequential replay from the current state (a Lemire redraw occurred)
-        while (need != 0 && uns >= 2) {
-            const unsigned long long b1 = uns - 1ULL;
-            const unsigned long long xx = lemire_uniform(mt, pos, lane, uns * b1);
-            const unsigned long long q0 = xx / b1, q1 = xx % b1;
-            --uns;
-            if (q0 < (unsigned long long)need) { idx[o++] = first; --need; }
-            ++first;
-            if (need == 0) break;
-            --uns;
-            if (q1 < (unsigned long long)need) { idx[o++] = first; --need; }
-            ++first;
-        }
-    }
-    for (; need != 0; ++first) {  // one-at-a-time tail (stl_algo.h:5899-5905)
-        --uns;
-        if (lemire_uniform(mt, pos, lane, uns + 1ULL) < (unsigned long long)need) { idx[o++] = first; --need; }
-    }
-}
 
 // 4-point DLT (homographyestimator.cpp:45-78,123-143): null vector of the 8x9 matrix via Householder QR of A^T.
 __device__ bool dlt4(const double* px, const double* py, const double* pu, const double* pv, double* H) {
@@ -370,7 +272,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_ransac(int64_t n_problems
         int my_idx[4] = {0, 0, 0, 0};
         for (int h = 0; h < B; ++h) {
             int idx[4];
-            sample4(w.mt, pos, lane, n, idx);
+            sample_k<4>(w.mt, pos, lane, n, idx);
             if (lane == h) { my_idx[0] = idx[0]; my_idx[1] = idx[1]; my_idx[2] = idx[2]; my_idx[3] = idx[3]; }
         }
         // ---- 2. lane h: degeneracy test and 4-point DLT of hypothesis h ----
@@ -477,24 +379,6 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) k_ransac(int64_t n_problems
     if (gmask) for (int i = lane; i < n; i += 32) gmask[prob * n + i] = has_best ? (uint8_t)((w.best[i >> 5] >> (i & 31)) & 1u) : 0;
 }
 
-// calculate_iterations (ransac.h:64-78) evaluated on the host for every possible inlier count;
-// -1 encodes "max_iters".  Same expression, same libm as the reference's own host code.
-std::vector<int> build_niter_table(int n, const cal_ransac_options& o) {
-    std::vector<int> t(n + 1, -1);
-    for (int k = 0; k <= n; ++k) {
-        const double w = (double)k / (double)n;
-        if (o.confidence <= 0.0 || w <= 0.0) continue;
-        const double denom = std::log(std::max(1e-12, 1.0 - std::pow(w, 4.0)));
-        if (denom >= 0.0) continue;
-        const double v = std::ceil(std::log(1.0 - o.confidence) / denom);
-        // static_cast<int> of an out-of-range double is what x86 cvttsd2si yields: INT_MIN,
-        // which std::clamp then lifts to iters_so_far
-        t[k] = (v >= 2147483648.0 || v < -2147483648.0 || v != v) ? INT32_MIN : (int)v;
-        if (t[k] == -1) t[k] = -2;  // keep -1 reserved for "max_iters" (cannot occur: the ratio is >= 0)
-    }
-    return t;
-}
-
 size_t smem_per_cta(int n) {
     const int nw = (n + 31) / 32;
     const size_t per_warp = (size_t)4 * n * sizeof(double) + 312 * sizeof(unsigned long long) + (size_t)(1 + 2 * kBatch) * nw * sizeof(unsigned);
@@ -507,7 +391,7 @@ cal_status launch(int64_t n_problems, int n, const double* x, const double* y, c
     const size_t smem = smem_per_cta(n);
     if (smem > 227 * 1024) return rfail(CAL_ERR_INVALID_ARGUMENT, "too many correspondences per problem for the shared-memory RANSAC kernel (n <= ~1700)");
     RCUDA(cudaFuncSetAttribute(k_ransac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    std::vector<int> table = build_niter_table(n, o);
+    std::vector<int> table = build_niter_table(n, o, 4);
     int* dtable; RCUDA(cudaMalloc(reinterpret_cast<void**>(&dtable), table.size() * sizeof(int)));
     RCUDA(cudaMemcpyAsync(dtable, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     cudaEvent_t e0, e1; RCUDA(cudaEventCreate(&e0)); RCUDA(cudaEventCreate(&e1));

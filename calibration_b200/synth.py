@@ -240,3 +240,20 @@ def synth_ransac(seed=17, n_problems=1000, n=500, outlier_fraction=0.3, noise=0.
     u = np.where(out, rng.uniform(0, 1280, size=x.shape), u)
     v = np.where(out, rng.uniform(0, 720, size=x.shape), v)
     return x, y, u, v, H
+
+
+def synth_plane_ransac(seed=23, n_problems=1000, n=500, outlier_fraction=0.3, noise=0.002):
+    """Laser-plane style problems (fit_plane_ransac, linear/planefit.cpp:86-104): n points per problem near a
+    random plane (unit normal within 40 deg of +z, offset 0.5..2 m), Gaussian distance noise, a fraction of
+    gross outliers in the surrounding box.  Arrays of shape (n_problems, n) and the planes (n_problems, 4)."""
+    rng = np.random.default_rng(seed)
+    tilt = np.deg2rad(rng.uniform(0, 40, n_problems)); az = rng.uniform(0, 2 * np.pi, n_problems)
+    nrm = np.stack([np.sin(tilt) * np.cos(az), np.sin(tilt) * np.sin(az), np.cos(tilt)], axis=1)
+    d = -rng.uniform(0.5, 2.0, n_problems)
+    x = rng.uniform(-0.5, 0.5, size=(n_problems, n)); y = rng.uniform(-0.5, 0.5, size=(n_problems, n))
+    z = (-d[:, None] - nrm[:, :1] * x - nrm[:, 1:2] * y) / nrm[:, 2:3]
+    e = rng.normal(scale=noise, size=x.shape)
+    x = x + e * nrm[:, :1]; y = y + e * nrm[:, 1:2]; z = z + e * nrm[:, 2:3]
+    out = rng.uniform(size=x.shape) < outlier_fraction
+    z = np.where(out, rng.uniform(0.0, 3.0, size=x.shape), z)
+    return x, y, z, np.concatenate([nrm, d[:, None]], axis=1)

@@ -243,6 +243,32 @@ cal_status cal_ransac_homography_batch_dev(int64_t n_problems, int32_t n, const 
                                            int seed_per_problem, cal_ransac_result* results_dev,
                                            uint8_t* inlier_mask_dev, float* ms);
 
+/* ---- batched RANSAC plane fit: fit_plane_ransac(pts, RansacOptions) (linear/planefit.h:23-24,
+ * src/estimation/linear/planefit.cpp:86-104) = ransac<PlaneRansacEstimator> (planefit.cpp:9-62) with
+ * fit_plane_svd (:66-84) as the refit — the batched RANSAC kernel generalised to the reference's second
+ * estimator. */
+typedef struct cal_plane_ransac_result { /* PlaneRansacResult (linear/planefit.h:14-19) + RansacResult fields */
+    int32_t success;
+    int32_t iters;
+    int32_t n_inliers;
+    int32_t iters_run;
+    double plane[4];   /* (n, d): n . p + d = 0, |n| = 1; all zero when !success (planefit.h:16) */
+    double inlier_rms;
+    double min_margin; /* unused by the device path (layout parity with the test oracle) */
+} cal_plane_ransac_result;
+/* n_problems independent point sets of n points each, arrays laid out [problem][n]; seeds, sample stream
+ * and inlier_mask as cal_ransac_homography_batch (k_min_samples = 3).  A plane that comes from the refit
+ * (fit_plane_svd) has the sign that makes its largest normal component positive — the reference leaves
+ * that sign to Eigen::JacobiSVD and its tests align it (tests/unit/planefit_test.cpp:18-20). */
+cal_status cal_ransac_plane_batch(int64_t n_problems, int32_t n, const double* x, const double* y, const double* z,
+                                  const cal_ransac_options* opts, int seed_per_problem, int device,
+                                  cal_plane_ransac_result* results, uint8_t* inlier_mask);
+/* Device-resident variant: pointers are device memory, results stay on the device; returns the
+ * CUDA-event time of the kernel. */
+cal_status cal_ransac_plane_batch_dev(int64_t n_problems, int32_t n, const double* x_dev, const double* y_dev,
+                                      const double* z_dev, const cal_ransac_options* opts, int seed_per_problem,
+                                      cal_plane_ransac_result* results_dev, uint8_t* inlier_mask_dev, float* ms);
+
 /* ---- linear seeding stage that feeds the refinement, batched over views.
  * Views are given as SoA observations + CSR offsets, exactly like the residual blocks of
  * cal_problem_desc (view k = observations [view_offset[k], view_offset[k+1]) seen by camera

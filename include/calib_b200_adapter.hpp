@@ -7,6 +7,7 @@
 //   calib::optimize_bundle<CameraT>       include/calib/estimation/optim/bundle.h:58-63
 //   calib::optimize_handeye               include/calib/estimation/optim/handeye.h:40-43
 //   calib::estimate_homography (RANSAC)   include/calib/estimation/linear/homography.h:22-24
+//   calib::fit_plane_ransac               include/calib/estimation/linear/planefit.h:23-24
 //
 // It needs the reference's own headers (Eigen types, camera models, option and
 // result structs) and is therefore only compiled inside the reference tree —
@@ -24,6 +25,7 @@
 
 #include "calib/estimation/linear/handeye.h"
 #include "calib/estimation/linear/homography.h"
+#include "calib/estimation/linear/planefit.h"
 #include "calib/estimation/optim/bundle.h"
 #include "calib/estimation/optim/extrinsics.h"
 #include "calib/estimation/optim/handeye.h"
@@ -290,6 +292,37 @@ inline auto estimate_homography_ransac_b200(const PlanarView& data, const Ransac
         out.symmetric_rms_px = r.symmetric_rms_px;
     }
     return out;
+}
+
+// fit_plane_ransac (src/estimation/linear/planefit.cpp:86-104) for one point set, and for a batch of point
+// sets of equal size in one kernel launch (seed of set p = opts.seed + p when seed_per_problem).
+inline auto fit_plane_ransac_b200(const std::vector<std::vector<Eigen::Vector3d>>& sets, const RansacOptions& ro,
+                                  bool seed_per_problem = false) -> std::vector<PlaneRansacResult> {
+    std::vector<PlaneRansacResult> out(sets.size());
+    if (sets.empty()) return out;
+    const auto n = static_cast<int32_t>(sets.front().size());
+    for (const auto& s : sets)
+        if (static_cast<int32_t>(s.size()) != n) throw std::invalid_argument("fit_plane_ransac_b200: point sets must have equal size");
+    if (n < 3) return out;  // planefit.cpp:88-90
+    const size_t np = sets.size();
+    std::vector<double> x(np * n), y(np * n), z(np * n);
+    for (size_t p = 0; p < np; ++p)
+        for (int i = 0; i < n; ++i) { x[p * n + i] = sets[p][i].x(); y[p * n + i] = sets[p][i].y(); z[p * n + i] = sets[p][i].z(); }
+    const cal_ransac_options co{ro.max_iters, ro.min_inliers, ro.thresh, ro.confidence, ro.seed, ro.refit_on_inliers ? 1 : 0, 0};
+    std::vector<cal_plane_ransac_result> r(np); std::vector<uint8_t> mask(np * n);
+    b200::check(cal_ransac_plane_batch(static_cast<int64_t>(np), n, x.data(), y.data(), z.data(), &co, seed_per_problem ? 1 : 0, 0,
+                                       r.data(), mask.data()));
+    for (size_t p = 0; p < np; ++p) {
+        if (!r[p].success) continue;
+        out[p].success = true;
+        out[p].plane = Eigen::Vector4d(r[p].plane[0], r[p].plane[1], r[p].plane[2], r[p].plane[3]);
+        for (int i = 0; i < n; ++i) if (mask[p * n + i]) out[p].inliers.push_back(i);
+        out[p].inlier_rms = r[p].inlier_rms;
+    }
+    return out;
+}
+inline auto fit_plane_ransac_b200(const std::vector<Eigen::Vector3d>& pts, const RansacOptions& ro) -> PlaneRansacResult {
+    return fit_plane_ransac_b200(std::vector<std::vector<Eigen::Vector3d>>{pts}, ro).front();
 }
 
 }  // namespace calib

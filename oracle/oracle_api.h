@@ -138,6 +138,28 @@ int orc_ransac_homography_batch(int64_t n_problems, int32_t n, const double* x, 
 int orc_homography_dlt(int32_t n, const double* x, const double* y, const double* u,
                        const double* v, double* hmtx);
 
+
+/* RANSAC plane fit (fit_plane_ransac, src/estimation/linear/planefit.cpp:9-104): the same loop, k = 3 */
+typedef struct orc_plane_result {
+    int32_t success;
+    int32_t iters;
+    int32_t n_inliers;
+    int32_t iters_run;
+    double plane[4];     /* (n, d), |n| = 1; Zero when !success (planefit.h:16) */
+    double inlier_rms;
+    double min_margin;
+} orc_plane_result;
+void orc_ref_plane_data(double* plane, double* xyz /* [140][3] */);
+void orc_sample_stream_k(uint64_t seed, int32_t n, int32_t k, int32_t iters, int32_t* out);
+void orc_sample_stream_k_libstdcxx(uint64_t seed, int32_t n, int32_t k, int32_t iters, int32_t* out);
+/* fit_plane_svd (planefit.cpp:66-84); returns 1 for n < 3 (the reference throws) */
+int orc_fit_plane_svd(int32_t n, const double* x, const double* y, const double* z, double* plane);
+int orc_ransac_plane(int32_t n, const double* x, const double* y, const double* z, const orc_ransac_options* o,
+                     orc_plane_result* res, uint8_t* inlier_mask);
+int orc_ransac_plane_batch(int64_t n_problems, int32_t n, const double* x, const double* y, const double* z,
+                           const orc_ransac_options* o, int seed_per_problem, orc_plane_result* res,
+                           uint8_t* inlier_mask, int num_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -285,3 +285,155 @@ int orc_homography_dlt(int32_t n, const double* x, const double* y, const double
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// fit_plane_ransac (src/estimation/linear/planefit.cpp:9-62,86-104): the same ransac<> loop with the
+// three-point plane estimator; refit = fit_plane_svd (:66-84).
+// ---------------------------------------------------------------------------
+namespace orc {
+
+// the smallest right singular vector of the centred point matrix has no defined sign (the reference
+// takes whatever Eigen::JacobiSVD's V holds, and its tests align signs before comparing,
+// planefit_test.cpp:18-20).  Restatement and product both return the sign that makes the normal
+// component of largest magnitude positive.  UNPINNED against Eigen.
+static void canonical_sign(double* plane) {
+    int k = 0;
+    for (int i = 1; i < 3; ++i) if (std::fabs(plane[i]) > std::fabs(plane[k])) k = i;
+    if (plane[k] < 0.0) for (int i = 0; i < 4; ++i) plane[i] = -plane[i];
+}
+
+// fit_plane_svd (planefit.cpp:66-84)
+static bool fit_plane_svd(const std::vector<double>& px, const std::vector<double>& py, const std::vector<double>& pz, double* plane) {
+    const size_t n = px.size();
+    if (n < 3) return false;  // the reference throws std::invalid_argument
+    double cx = 0, cy = 0, cz = 0;
+    for (size_t i = 0; i < n; ++i) { cx += px[i]; cy += py[i]; cz += pz[i]; }
+    const double dn = static_cast<double>(n);
+    cx /= dn; cy /= dn; cz /= dn;
+    std::vector<double> A(3 * n), V, sv;
+    for (size_t i = 0; i < n; ++i) { A[3 * i] = px[i] - cx; A[3 * i + 1] = py[i] - cy; A[3 * i + 2] = pz[i] - cz; }
+    jacobi_svd(A, static_cast<int>(n), 3, V, sv);
+    int k = 0;  // JacobiSVD sorts descending: V.col(2) belongs to the smallest singular value
+    for (int j = 1; j < 3; ++j) if (sv[j] < sv[k]) k = j;
+    const double nx = V[0 * 3 + k], ny = V[1 * 3 + k], nz = V[2 * 3 + k];
+    const double d = -(nx * cx + ny * cy + nz * cz);
+    const double nrm = std::sqrt(nx * nx + ny * ny + nz * nz);
+    plane[0] = nx / nrm; plane[1] = ny / nrm; plane[2] = nz / nrm; plane[3] = d / nrm;
+    canonical_sign(plane);
+    return true;
+}
+
+// PlaneRansacEstimator::fit / is_degenerate (planefit.cpp:14-33,52-62): both test the same cross product
+static bool plane_from_sample(const double* x, const double* y, const double* z, const int* s, double* plane) {
+    const double v1x = x[s[1]] - x[s[0]], v1y = y[s[1]] - y[s[0]], v1z = z[s[1]] - z[s[0]];
+    const double v2x = x[s[2]] - x[s[0]], v2y = y[s[2]] - y[s[0]], v2z = z[s[2]] - z[s[0]];
+    double nx = v1y * v2z - v1z * v2y, ny = v1z * v2x - v1x * v2z, nz = v1x * v2y - v1y * v2x;
+    const double norm = std::sqrt(nx * nx + ny * ny + nz * nz);
+    if (norm < 1e-12) return false;
+    nx /= norm; ny /= norm; nz /= norm;
+    plane[0] = nx; plane[1] = ny; plane[2] = nz; plane[3] = -(nx * x[s[0]] + ny * y[s[0]] + nz * z[s[0]]);
+    return true;
+}
+// PlaneRansacEstimator::residual (planefit.cpp:35-38)
+static inline double plane_residual(const double* pl, double x, double y, double z) {
+    return std::fabs(pl[0] * x + pl[1] * y + pl[2] * z + pl[3]);
+}
+static void plane_inliers(int n, const double* x, const double* y, const double* z, const double* pl, double thresh, Scored& out,
+                          double& margin) {
+    out.idx.clear(); out.res.clear();
+    for (int i = 0; i < n; ++i) {
+        const double r = plane_residual(pl, x[i], y[i], z[i]);
+        if (std::isfinite(r)) margin = std::min(margin, std::fabs(r - thresh));
+        if (r <= thresh) { out.idx.push_back(i); out.res.push_back(r); }
+    }
+}
+
+static void ransac_plane_one(int n, const double* x, const double* y, const double* z, const orc_ransac_options& o,
+                             orc_plane_result* res, uint8_t* mask) {
+    std::memset(res, 0, sizeof *res);  // PlaneRansacResult: plane = Zero (planefit.h:16)
+    res->inlier_rms = std::numeric_limits<double>::infinity();
+    res->min_margin = std::numeric_limits<double>::infinity();
+    if (mask) std::memset(mask, 0, n);
+    if (n < 3) return;
+    MT64 rng(o.seed);
+    int dyn = o.max_iters, it = 0;
+    std::vector<int> best_inl; bool has_best = false; double best_rms = std::numeric_limits<double>::infinity();
+    Scored a, b; int idxs[3];
+    for (it = 0; it < dyn; ++it) {
+        sample_indices(rng, n, 3, idxs);
+        double P[4];
+        if (!plane_from_sample(x, y, z, idxs, P)) continue;  // is_degenerate, and fit's own test
+        plane_inliers(n, x, y, z, P, o.thresh, a, res->min_margin);
+        if (static_cast<int>(a.idx.size()) < o.min_inliers) continue;
+        double Pf[4]; std::memcpy(Pf, P, sizeof Pf);
+        const Scored* fin = &a;
+        if (o.refit_on_inliers) {
+            b = a;
+            if (a.idx.size() >= 3) {  // PlaneRansacEstimator::refit (planefit.cpp:40-50)
+                std::vector<double> rx, ry, rz;
+                for (int id : a.idx) { rx.push_back(x[id]); ry.push_back(y[id]); rz.push_back(z[id]); }
+                double P2[4];
+                if (fit_plane_svd(rx, ry, rz, P2)) { std::memcpy(Pf, P2, sizeof Pf); plane_inliers(n, x, y, z, Pf, o.thresh, b, res->min_margin); }
+            }
+            fin = &b;
+        }
+        const double frms = rms(fin->res);
+        if (!has_best || fin->idx.size() > best_inl.size() || (fin->idx.size() == best_inl.size() && frms < best_rms)) {
+            has_best = true; best_inl = fin->idx; best_rms = frms;
+            std::memcpy(res->plane, Pf, sizeof Pf); res->iters = it + 1;
+        }
+        const double ratio = static_cast<double>(fin->idx.size()) / static_cast<double>(n);
+        dyn = calc_iters(o.confidence, ratio, 3, it + 1, o.max_iters);
+    }
+    res->iters_run = it;
+    res->success = has_best ? 1 : 0;
+    if (has_best) {
+        res->n_inliers = static_cast<int>(best_inl.size());
+        res->inlier_rms = best_rms;
+        if (mask) for (int id : best_inl) mask[id] = 1;
+    }
+}
+
+}  // namespace orc
+
+extern "C" {
+
+void orc_sample_stream_k(uint64_t seed, int32_t n, int32_t k, int32_t iters, int32_t* out) {
+    MT64 g(seed);
+    for (int it = 0; it < iters; ++it) sample_indices(g, n, k, out + static_cast<size_t>(k) * it);
+}
+void orc_sample_stream_k_libstdcxx(uint64_t seed, int32_t n, int32_t k, int32_t iters, int32_t* out) {
+    std::vector<int> all(n), idxs(k);
+    std::iota(all.begin(), all.end(), 0);
+    std::mt19937_64 rng(seed);
+    for (int it = 0; it < iters; ++it) {
+        std::sample(all.begin(), all.end(), idxs.begin(), static_cast<size_t>(k), rng);
+        for (int j = 0; j < k; ++j) out[static_cast<size_t>(k) * it + j] = idxs[j];
+    }
+}
+
+int orc_fit_plane_svd(int32_t n, const double* x, const double* y, const double* z, double* plane) {
+    std::vector<double> px(x, x + n), py(y, y + n), pz(z, z + n);
+    return fit_plane_svd(px, py, pz, plane) ? 0 : 1;
+}
+
+int orc_ransac_plane(int32_t n, const double* x, const double* y, const double* z, const orc_ransac_options* o,
+                     orc_plane_result* res, uint8_t* inlier_mask) {
+    ransac_plane_one(n, x, y, z, *o, res, inlier_mask);
+    return 0;
+}
+
+int orc_ransac_plane_batch(int64_t n_problems, int32_t n, const double* x, const double* y, const double* z,
+                           const orc_ransac_options* o, int seed_per_problem, orc_plane_result* res, uint8_t* inlier_mask,
+                           int num_threads) {
+    const int nt = num_threads > 0 ? num_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nt)
+    for (int64_t p = 0; p < n_problems; ++p) {
+        orc_ransac_options op = *o;
+        if (seed_per_problem) op.seed = o->seed + static_cast<uint64_t>(p);
+        ransac_plane_one(n, x + p * n, y + p * n, z + p * n, op, res + p, inlier_mask ? inlier_mask + p * n : nullptr);
+    }
+    return 0;
+}
+
+}  // extern "C"

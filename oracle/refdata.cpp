@@ -116,6 +116,27 @@ void orc_ref_homography_data(int n_points, double noise, int n_out, uint32_t see
 
 int orc_homography_dlt(int32_t n, const double* x, const double* y, const double* u, const double* v, double* hmtx);
 
+// PlaneFit.RansacRejectsOutliers data (planefit_test.cpp:24-46): std::mt19937(1337), 100 points on the
+// plane through (0,0,1) with normal (0.2,-0.3,1), then 40 outliers in [5,10]^3.  xyz: [140][3]; plane: 4.
+void orc_ref_plane_data(double* plane, double* xyz) {
+    std::mt19937 rng(1337);
+    std::uniform_real_distribution<double> dist_xy(-1.0, 1.0);
+    const double nn = std::sqrt(0.2 * 0.2 + 0.3 * 0.3 + 1.0);
+    const double gt[4] = {0.2 / nn, -0.3 / nn, 1.0 / nn, -(0.2 / nn * 0.0 + -0.3 / nn * 0.0 + 1.0 / nn * 1.0)};
+    std::memcpy(plane, gt, sizeof gt);
+    for (int i = 0; i < 100; ++i) {
+        const double x = dist_xy(rng);
+        const double y = dist_xy(rng);
+        xyz[3 * i] = x; xyz[3 * i + 1] = y; xyz[3 * i + 2] = (-gt[3] - gt[0] * x - gt[1] * y) / gt[2];
+    }
+    std::uniform_real_distribution<double> dist_out(5.0, 10.0);
+    for (int i = 0; i < 40; ++i) {
+        // emplace_back(dist_out(rng), dist_out(rng), dist_out(rng)): GCC evaluates the arguments right to left
+        const double z = dist_out(rng), y = dist_out(rng), x = dist_out(rng);
+        xyz[3 * (100 + i)] = x; xyz[3 * (100 + i) + 1] = y; xyz[3 * (100 + i) + 2] = z;
+    }
+}
+
 // estimate_planar_pose(view, CameraMatrix) — planarpose_linear.cpp:54-76 with
 // pose_from_homography_normalized :17-52.  K5 = fx, fy, cx, cy, skew.
 void orc_ref_estimate_planar_pose(int32_t n, const double* x, const double* y, const double* u, const double* v,

@@ -60,6 +60,13 @@ def lib():
         L.orc_estimate_intrinsics.argtypes = [i64, abi.c_int64_p, dp, dp, dp, dp, dp, dp, ip, dp, dp, dp]
         L.orc_estimate_intrinsics_ransac.argtypes = [i64, abi.c_int64_p, dp, dp, dp, dp, dp, C.POINTER(abi.RansacOptions), dp, ip, dp, dp, dp,
                                                      abi.c_uint8_p]
+        L.orc_sample_stream_k.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_int32, ip]
+        L.orc_sample_stream_k_libstdcxx.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_int32, ip]
+        L.orc_ref_plane_data.argtypes = [dp, dp]
+        L.orc_fit_plane_svd.argtypes = [C.c_int32, dp, dp, dp, dp]
+        L.orc_ransac_plane.argtypes = [C.c_int32, dp, dp, dp, C.POINTER(abi.RansacOptions), C.POINTER(abi.PlaneResult), abi.c_uint8_p]
+        L.orc_ransac_plane_batch.argtypes = [i64, C.c_int32, dp, dp, dp, C.POINTER(abi.RansacOptions), C.c_int,
+                                             C.POINTER(abi.PlaneResult), abi.c_uint8_p, C.c_int]
         _lib = L
     return _lib
 
@@ -179,6 +186,9 @@ def ref_lib():
         dp = abi.c_double_p
         L.ref_ransac_homography.argtypes = [C.c_int32, dp, dp, dp, dp, C.POINTER(abi.RansacOptions),
                                             C.POINTER(abi.RansacResult), abi.c_uint8_p]
+        L.ref_ransac_plane.argtypes = [C.c_int32, dp, dp, dp, C.POINTER(abi.RansacOptions), C.POINTER(abi.PlaneResult),
+                                       abi.c_uint8_p]
+        L.orc_ransac_plane.argtypes = L.ref_ransac_plane.argtypes
         # the harness compiles oracle/ransac.cpp into the same library, with the same flags
         L.orc_ransac_homography.argtypes = [C.c_int32, dp, dp, dp, dp, C.POINTER(abi.RansacOptions), abi.c_int32_p,
                                             C.POINTER(abi.RansacResult), abi.c_uint8_p]
@@ -199,6 +209,61 @@ def ref_ransac(x, y, u, v, opts=None, oracle_twin=False):
         L.orc_ransac_homography(*args, None, C.byref(res), mask.ctypes.data_as(abi.c_uint8_p))
     else:
         L.ref_ransac_homography(*args, C.byref(res), mask.ctypes.data_as(abi.c_uint8_p))
+    return res, mask
+
+
+def ref_ransac_plane(x, y, z, opts=None, oracle_twin=False):
+    """fit_plane_ransac through the reference's loop (see ref_lib); oracle_twin as in ref_ransac."""
+    L = ref_lib()
+    x, y, z = (abi.as_f64(a) for a in (x, y, z))
+    opts = opts or abi.RansacOptions.default()
+    res = abi.PlaneResult()
+    mask = np.zeros(len(x), dtype=np.uint8)
+    fn = L.orc_ransac_plane if oracle_twin else L.ref_ransac_plane
+    fn(len(x), abi.dptr(x), abi.dptr(y), abi.dptr(z), C.byref(opts), C.byref(res), mask.ctypes.data_as(abi.c_uint8_p))
+    return res, mask
+
+
+def sample_stream_k(seed, n, k, iters, real=False):
+    out = np.zeros((iters, k), dtype=np.int32)
+    fn = lib().orc_sample_stream_k_libstdcxx if real else lib().orc_sample_stream_k
+    fn(seed, n, k, iters, out.ctypes.data_as(abi.c_int32_p))
+    return out
+
+
+def plane_testdata():
+    """planefit_test.cpp:24-46: (ground-truth plane, 140 x 3 points)."""
+    plane = np.zeros(4); xyz = np.zeros((140, 3))
+    lib().orc_ref_plane_data(abi.dptr(plane), abi.dptr(xyz))
+    return plane, xyz
+
+
+def fit_plane_svd(x, y, z):
+    x, y, z = (abi.as_f64(a) for a in (x, y, z))
+    plane = np.zeros(4)
+    rc = lib().orc_fit_plane_svd(len(x), abi.dptr(x), abi.dptr(y), abi.dptr(z), abi.dptr(plane))
+    return rc, plane
+
+
+def ransac_plane(x, y, z, opts=None):
+    x, y, z = (abi.as_f64(a) for a in (x, y, z))
+    opts = opts or abi.RansacOptions.default()
+    res = abi.PlaneResult()
+    mask = np.zeros(len(x), dtype=np.uint8)
+    lib().orc_ransac_plane(len(x), abi.dptr(x), abi.dptr(y), abi.dptr(z), C.byref(opts), C.byref(res),
+                           mask.ctypes.data_as(abi.c_uint8_p))
+    return res, mask
+
+
+def ransac_plane_batch(x, y, z, opts=None, seed_per_problem=True, threads=0):
+    """x, y, z: (n_problems, n) arrays."""
+    x, y, z = (abi.as_f64(a) for a in (x, y, z))
+    npb, n = x.shape
+    opts = opts or abi.RansacOptions.default()
+    res = (abi.PlaneResult * npb)()
+    mask = np.zeros((npb, n), dtype=np.uint8)
+    lib().orc_ransac_plane_batch(npb, n, abi.dptr(x), abi.dptr(y), abi.dptr(z), C.byref(opts), int(seed_per_problem), res,
+                                 mask.ctypes.data_as(abi.c_uint8_p), threads)
     return res, mask
 
 

@@ -114,3 +114,68 @@ def test_k1_role_tables_invariants():
     L = C.CDLL(so)
     assert L.roles_check() == 0
     assert [L.roles_of(0, i) for i in range(3)] == [1, 2, 3] and [L.roles_of(1, i) for i in range(3)] == [1, 3, 3]
+
+
+# ---- plane RANSAC: the product's per-hypothesis math (plane_math.cuh) in the kernel's batch order ----
+PLANE_SRC = os.path.join(ROOT, "tests", "host_emul", "plane_emul.cpp")
+PLANE_SO = os.path.join(ROOT, "tests", "host_emul", "_build", "libplane_emul.so")
+
+
+@pytest.fixture(scope="module")
+def plane_emul():
+    deps = [PLANE_SRC] + [os.path.join(ROOT, "calibration_b200", "csrc", f) for f in ("plane_math.cuh", "ransac_iters.hpp")]
+    if not os.path.exists(PLANE_SO) or any(os.path.getmtime(d) > os.path.getmtime(PLANE_SO) for d in deps):
+        os.makedirs(os.path.dirname(PLANE_SO), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", PLANE_SO, PLANE_SRC], check=True)
+    L = C.CDLL(PLANE_SO)
+    L.emul_ransac_plane.argtypes = [C.c_int32, abi.c_double_p, abi.c_double_p, abi.c_double_p, C.POINTER(abi.RansacOptions),
+                                    abi.c_int32_p, C.POINTER(abi.PlaneResult), abi.c_uint8_p]
+    return L
+
+
+def run_plane_emul(L, x, y, z, opts):
+    x, y, z = (abi.as_f64(a) for a in (x, y, z))
+    idx = O.sample_stream_k(opts.seed, len(x), 3, max(opts.max_iters, 1))
+    res = abi.PlaneResult(); mask = np.zeros(len(x), dtype=np.uint8)
+    L.emul_ransac_plane(len(x), abi.dptr(x), abi.dptr(y), abi.dptr(z), C.byref(opts), idx.ctypes.data_as(abi.c_int32_p),
+                        C.byref(res), mask.ctypes.data_as(abi.c_uint8_p))
+    return res, mask
+
+
+def check_plane(L, x, y, z, opts, margin=1e-10):
+    ro, mo = O.ransac_plane(x, y, z, opts)
+    re_, me = run_plane_emul(L, x, y, z, opts)
+    if ro.min_margin <= margin:
+        return False
+    assert bool(re_.success) == bool(ro.success)
+    assert np.array_equal(me, mo) and re_.n_inliers == ro.n_inliers
+    assert re_.iters == ro.iters and re_.iters_run == ro.iters_run
+    if ro.success:
+        assert np.abs(np.array(re_.plane) - np.array(ro.plane)).max() <= 1e-9
+        assert abs(re_.inlier_rms - ro.inlier_rms) <= 1e-9 * ro.inlier_rms + 1e-13
+    else:
+        assert list(re_.plane) == [0.0] * 4
+    return True
+
+
+def test_plane_math_replays_oracle_loop(plane_emul):
+    x, y, z, _ = synth.synth_plane_ransac(seed=12, n_problems=48, n=200)
+    n_ok = 0
+    for p in range(48):
+        for kw in (dict(), dict(refit_on_inliers=0), dict(confidence=0.0, max_iters=70), dict(min_inliers=190, max_iters=90)):
+            n_ok += check_plane(plane_emul, x[p], y[p], z[p], abi.RansacOptions.default(seed=1234567 + p, thresh=0.006, **kw))
+    assert n_ok >= 0.97 * 48 * 4
+
+
+def test_plane_math_reference_scenario_and_edges(plane_emul):
+    gt, xyz = O.plane_testdata()     # planefit_test.cpp:22-75 (noise-free plane: the scatter matrix is singular)
+    assert check_plane(plane_emul, *xyz.T, abi.RansacOptions.default(max_iters=2000, thresh=0.01, min_inliers=80, confidence=0.999))
+    t = np.linspace(0, 1, 40)
+    assert check_plane(plane_emul, t, 2 * t, -t, abi.RansacOptions.default(min_inliers=3, max_iters=40))      # all samples degenerate
+    assert check_plane(plane_emul, [0.0, 1.0], [0.0, 0.0], [0.0, 0.0], abi.RansacOptions.default(min_inliers=1))
+    q = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0.3, 0.3, 0.5]], float)
+    assert check_plane(plane_emul, *q.T, abi.RansacOptions.default(min_inliers=3, thresh=1e-6, max_iters=30))
+    for n in (3, 31, 33, 65):
+        x, y, z, _ = synth.synth_plane_ransac(seed=n, n_problems=1, n=n, outlier_fraction=0.2)
+        check_plane(plane_emul, x[0], y[0], z[0], abi.RansacOptions.default(thresh=0.006, min_inliers=min(12, n), max_iters=150))
