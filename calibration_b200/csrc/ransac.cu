@@ -427,18 +427,23 @@ extern "C" cal_status cal_ransac_homography_batch(int64_t n_problems, int32_t n,
     if (cal_device_count() <= device) return rfail(CAL_ERR_CUDA, "no CUDA device: calib_b200 has no CPU fallback");
     RCUDA(cudaSetDevice(device));
     const size_t nb = (size_t)n_problems * n * sizeof(double);
-    double *dx, *dy, *du, *dv; cal_ransac_result* dres; uint8_t* dmask = nullptr;
-    RCUDA(cudaMalloc(reinterpret_cast<void**>(&dx), nb)); RCUDA(cudaMalloc(reinterpret_cast<void**>(&dy), nb));
-    RCUDA(cudaMalloc(reinterpret_cast<void**>(&du), nb)); RCUDA(cudaMalloc(reinterpret_cast<void**>(&dv), nb));
-    RCUDA(cudaMalloc(reinterpret_cast<void**>(&dres), (size_t)n_problems * sizeof(cal_ransac_result)));
-    if (inlier_mask) RCUDA(cudaMalloc(reinterpret_cast<void**>(&dmask), (size_t)n_problems * n));
-    RCUDA(cudaMemcpy(dx, x, nb, cudaMemcpyHostToDevice)); RCUDA(cudaMemcpy(dy, y, nb, cudaMemcpyHostToDevice));
-    RCUDA(cudaMemcpy(du, u, nb, cudaMemcpyHostToDevice)); RCUDA(cudaMemcpy(dv, v, nb, cudaMemcpyHostToDevice));
+    // every exit releases the device buffers (cudaFree(nullptr) is a no-op)
+    double* dxyuv = nullptr; cal_ransac_result* dres = nullptr; uint8_t* dmask = nullptr;
+    auto done = [&](cal_status rc) { cudaFree(dxyuv); cudaFree(dres); cudaFree(dmask); return rc; };
+    if (cudaMalloc(reinterpret_cast<void**>(&dxyuv), 4 * nb) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&dres), (size_t)n_problems * sizeof(cal_ransac_result)) != cudaSuccess ||
+        (inlier_mask && cudaMalloc(reinterpret_cast<void**>(&dmask), (size_t)n_problems * n) != cudaSuccess))
+        return done(rfail(CAL_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(cudaGetLastError())));
+    const size_t ne = (size_t)n_problems * n;
+    double *dx = dxyuv, *dy = dx + ne, *du = dy + ne, *dv = du + ne;
+    if (cudaMemcpy(dx, x, nb, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(dy, y, nb, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(du, u, nb, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(dv, v, nb, cudaMemcpyHostToDevice) != cudaSuccess)
+        return done(rfail(CAL_ERR_CUDA, std::string("host to device copy: ") + cudaGetErrorString(cudaGetLastError())));
     cal_status s = launch(n_problems, n, dx, dy, du, dv, *opts, seed_per_problem, dres, dmask, nullptr, nullptr);
     if (s == CAL_OK) {
-        RCUDA(cudaMemcpy(results, dres, (size_t)n_problems * sizeof(cal_ransac_result), cudaMemcpyDeviceToHost));
-        if (inlier_mask) RCUDA(cudaMemcpy(inlier_mask, dmask, (size_t)n_problems * n, cudaMemcpyDeviceToHost));
+        if (cudaMemcpy(results, dres, (size_t)n_problems * sizeof(cal_ransac_result), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            (inlier_mask && cudaMemcpy(inlier_mask, dmask, (size_t)n_problems * n, cudaMemcpyDeviceToHost) != cudaSuccess))
+            s = rfail(CAL_ERR_CUDA, std::string("device to host copy: ") + cudaGetErrorString(cudaGetLastError()));
     }
-    cudaFree(dx); cudaFree(dy); cudaFree(du); cudaFree(dv); cudaFree(dres); cudaFree(dmask);
-    return s;
+    return done(s);
 }

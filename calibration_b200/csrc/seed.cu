@@ -26,6 +26,7 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../../include/calib_b200.h"
@@ -349,6 +350,30 @@ __global__ void k_seed_from_ransac(int64_t n_views, const cal_ransac_result* __r
     success[v] = r.success ? 1 : 0;
 }
 
+// ragged views through the equal-size RANSAC kernel: gather the views `ids` (all of n points) into a dense
+// [group][n] batch, and scatter the batch's results / inlier masks back to their views
+__global__ void k_gather_views(int64_t cnt, int n, const int64_t* __restrict__ ids, const int64_t* __restrict__ off,
+                               const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ u,
+                               const double* __restrict__ v, double* __restrict__ gx, double* __restrict__ gy, double* __restrict__ gu,
+                               double* __restrict__ gv) {
+    const int64_t total = cnt * n;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = t / n; const int i = (int)(t - p * n);
+        const int64_t s = off[ids[p]] + i;
+        gx[t] = x[s]; gy[t] = y[s]; gu[t] = u[s]; gv[t] = v[s];
+    }
+}
+__global__ void k_scatter_views(int64_t cnt, int n, const int64_t* __restrict__ ids, const int64_t* __restrict__ off,
+                                const cal_ransac_result* __restrict__ gres, const uint8_t* __restrict__ gmask,
+                                cal_ransac_result* __restrict__ res, uint8_t* __restrict__ mask) {
+    const int64_t total = cnt * n;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = t / n; const int i = (int)(t - p * n);
+        if (i == 0) res[ids[p]] = gres[p];
+        if (mask) mask[off[ids[p]] + i] = gmask[t];
+    }
+}
+
 // Zhang's Gram matrix V^T V (upper triangle, 21) of one camera: one CTA per camera, strided
 // per-thread sums over the views, fixed-order shared-memory tree.
 __global__ void __launch_bounds__(256) k_zhang_gram(int64_t n_views, const int32_t* __restrict__ view_cam,
@@ -531,16 +556,47 @@ extern "C" cal_status cal_seed_intrinsics_ransac(int64_t n_views, const int64_t*
         // IntrinsicsEstimOptions::homography_ransac (intrinsicsdlt.cpp:50-64): every view is one problem of the batched
         // RANSAC kernel, all with the seed of the options (each reference call constructs its own engine from opts.seed)
         const int64_t n = view_offset[1] - view_offset[0];
-        for (int64_t k = 0; k < n_views; ++k)
-            if (view_offset[k + 1] - view_offset[k] != n)
-                return sfail(CAL_ERR_INVALID_ARGUMENT, "homography_ransac: the batched RANSAC kernel needs views of equal size");
-        if (n <= 0 || n > 0x7fffffff) return sfail(CAL_ERR_INVALID_ARGUMENT, "homography_ransac: empty views");
-        SCUDA(dres.alloc(n_views)); if (inlier_mask) SCUDA(dmask.alloc((size_t)n_views * n));
-        SCUDA(cudaStreamSynchronize(st));  // the inputs are in place before the RANSAC launch on the default stream
-        if (cal_status rs = cal_ransac_homography_batch_dev(n_views, (int32_t)n, in.x.p, in.y.p, in.u.p, in.v.p, ransac, 0, dres.p,
-                                                            inlier_mask ? dmask.p : nullptr, nullptr)) return rs;
+        bool equal = true;
+        for (int64_t k = 0; k < n_views; ++k) {
+            const int64_t nk = view_offset[k + 1] - view_offset[k];
+            if (nk > 0x7fffffff) return sfail(CAL_ERR_INVALID_ARGUMENT, "homography_ransac: view too large");
+            equal = equal && nk == n;
+        }
+        SCUDA(dres.alloc(n_views)); if (inlier_mask) SCUDA(dmask.alloc((size_t)n_obs));
+        if (equal) {
+            if (n <= 0) return sfail(CAL_ERR_INVALID_ARGUMENT, "homography_ransac: empty views");
+            SCUDA(cudaStreamSynchronize(st));  // the inputs are in place before the RANSAC launch on the default stream
+            if (cal_status rs = cal_ransac_homography_batch_dev(n_views, (int32_t)n, in.x.p, in.y.p, in.u.p, in.v.p, ransac, 0, dres.p,
+                                                                inlier_mask ? dmask.p : nullptr, nullptr)) return rs;
+        } else {
+            // ragged views: the batched kernel takes problems of one size, so the views are grouped by size; each
+            // group is gathered into a dense [group][n] batch, solved by one launch and scattered back (results per
+            // view, inlier mask in the observations' own CSR layout).  Views with fewer than four points stay
+            // unsuccessful (intrinsicsdlt.cpp:41-45).
+            std::map<int64_t, std::vector<int64_t>> by_size;
+            for (int64_t k = 0; k < n_views; ++k) by_size[view_offset[k + 1] - view_offset[k]].push_back(k);
+            SCUDA(cudaMemsetAsync(dres.p, 0, (size_t)n_views * sizeof(cal_ransac_result), st));
+            if (inlier_mask) SCUDA(cudaMemsetAsync(dmask.p, 0, (size_t)n_obs, st));
+            for (const auto& [ng, ids] : by_size) {
+                if (ng < 4) continue;
+                const int64_t cnt = (int64_t)ids.size();
+                DevBuf<int64_t> dids; DevBuf<double> g; DevBuf<cal_ransac_result> gres; DevBuf<uint8_t> gmask;
+                SCUDA(dids.alloc(cnt)); SCUDA(g.alloc((size_t)4 * cnt * ng)); SCUDA(gres.alloc(cnt));
+                if (inlier_mask) SCUDA(gmask.alloc((size_t)cnt * ng));
+                SCUDA(cudaMemcpyAsync(dids.p, ids.data(), (size_t)cnt * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+                double *gx = g.p, *gy = gx + cnt * ng, *gu = gy + cnt * ng, *gv = gu + cnt * ng;
+                const unsigned gb = (unsigned)std::min<int64_t>((cnt * ng + 255) / 256, 148 * 8);
+                k_gather_views<<<gb, 256, 0, st>>>(cnt, (int)ng, dids.p, in.off.p, in.x.p, in.y.p, in.u.p, in.v.p, gx, gy, gu, gv);
+                SCUDA(cudaStreamSynchronize(st));  // ids (a host vector) consumed; inputs in place before the default-stream launch
+                if (cal_status rs = cal_ransac_homography_batch_dev(cnt, (int32_t)ng, gx, gy, gu, gv, ransac, 0, gres.p,
+                                                                    inlier_mask ? gmask.p : nullptr, nullptr)) return rs;
+                k_scatter_views<<<gb, 256, 0, st>>>(cnt, (int)ng, dids.p, in.off.p, gres.p, inlier_mask ? gmask.p : nullptr, dres.p,
+                                                    inlier_mask ? dmask.p : nullptr);
+                SCUDA(cudaStreamSynchronize(st));  // the group's buffers are released at the end of this iteration
+            }
+        }
         k_seed_from_ransac<<<(unsigned)((n_views + 127) / 128), 128, 0, st>>>(n_views, dres.p, dH.p, drms.p, drows.p, dsucc.p);
-        if (inlier_mask) SCUDA(cudaMemcpyAsync(inlier_mask, dmask.p, (size_t)n_views * n, cudaMemcpyDeviceToHost, st));
+        if (inlier_mask) SCUDA(cudaMemcpyAsync(inlier_mask, dmask.p, (size_t)n_obs, cudaMemcpyDeviceToHost, st));
     } else {
         SeedArgs a{n_views, in.off.p, in.cam.p, in.x.p, in.y.p, in.u.p, in.v.p, nullptr, dH.p, drms.p, drows.p, dsucc.p, nullptr};
         k_view_dlt<false><<<(groups + 3) / 4, 128, 0, st>>>(a);

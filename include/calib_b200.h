@@ -289,8 +289,9 @@ cal_status cal_seed_intrinsics(int64_t n_views, const int64_t* view_offset, cons
                                const cal_seed_options* opts, int device, double* kmtx, int32_t* cam_success,
                                int32_t* view_success, double* hmtx, double* sym_rms, double* poses);
 /* The same with IntrinsicsEstimOptions::homography_ransac set (intrinsicsdlt.cpp:50-64): every view's homography
- * comes from ransac<HomographyEstimator> with the options' seed (the batched RANSAC kernel; views must have equal
- * size), hmtx = model / h33, sym_rms over the inliers; inlier_mask ([n_views][n] bytes) may be NULL.
+ * comes from ransac<HomographyEstimator> with the options' seed (the batched RANSAC kernel: one launch when the
+ * views have equal size, else one launch per distinct view size), hmtx = model / h33, sym_rms over the inliers;
+ * inlier_mask (one byte per observation, in the observations' own order) may be NULL.
  * ransac == NULL is cal_seed_intrinsics.  (cal_ransac_options is declared above.) */
 cal_status cal_seed_intrinsics_ransac(int64_t n_views, const int64_t* view_offset, const int32_t* view_cam, const double* x,
                                       const double* y, const double* u, const double* v, int32_t n_cams,

@@ -96,8 +96,35 @@ def test_intrinsics_with_homography_ransac_matches_oracle():
     assert (g["inlier_mask"][bad] == 0).mean() > 0.95 and (g["inlier_mask"][~bad] == 1).mean() > 0.95
     assert rel(g["kmtx"][0], o["kmtx"]) < 1e-7 and rel(g["hmtx"], o["hmtx"]) < 1e-8
     assert np.allclose(g["sym_rms"], o["sym_rms"], rtol=1e-8, atol=1e-9) and rel(g["poses"], o["poses"]) < 1e-7
-    with pytest.raises(ValueError, match="views of equal size"):
-        capi.seed_intrinsics(prob.x[:-1], prob.y[:-1], u[:-1], v[:-1], np.concatenate([off[:-1], [off[-1] - 1]]), ransac=ro)
+
+
+def test_homography_ransac_with_ragged_views_matches_oracle():
+    """Views of different sizes (partly detected boards): grouped by size, one launch of the batched kernel per
+    group, results and inlier masks scattered back to the views' own CSR layout.  A view of three points stays
+    unsuccessful (intrinsicsdlt.cpp:41-45)."""
+    prob, _, _ = synth.make_bundle(seed=6, n_cams=2, n_poses=30)
+    rng = np.random.default_rng(10)
+    off0 = np.asarray(prob.block_offset); cam0 = np.asarray(prob.block_cam)
+    keep_n = rng.choice([88, 88, 80, 61, 40, 33, 3], size=len(off0) - 1)
+    keep_n[5] = 3
+    sel = np.concatenate([off0[k] + np.sort(rng.choice(off0[k + 1] - off0[k], keep_n[k], replace=False)) for k in range(len(keep_n))])
+    off = np.concatenate([[0], np.cumsum(keep_n)]).astype(np.int64)
+    x, y, u, v = prob.x[sel], prob.y[sel], prob.u[sel].copy(), prob.v[sel].copy()
+    bad = rng.random(len(u)) < 0.08
+    u[bad] = rng.uniform(0, 1280, bad.sum()); v[bad] = rng.uniform(0, 720, bad.sum())
+    ro = abi.RansacOptions.default()
+    g = capi.seed_intrinsics(x, y, u, v, off, view_cam=cam0, n_cams=2, ransac=ro)
+    for c in range(2):
+        vs = np.flatnonzero(cam0 == c)
+        idx = np.concatenate([np.arange(off[k], off[k + 1]) for k in vs])
+        offc = np.concatenate([[0], np.cumsum(keep_n[vs])]).astype(np.int64)
+        o = O.estimate_intrinsics_ransac(x[idx], y[idx], u[idx], v[idx], offc, ro)
+        assert o["success"] and g["cam_success"][c] == 1
+        assert np.array_equal(g["view_success"][vs], o["view_success"])
+        assert np.array_equal(g["inlier_mask"][idx], o["inlier_mask"])
+        assert rel(g["kmtx"][c], o["kmtx"]) < 1e-7 and rel(g["hmtx"][vs], o["hmtx"]) < 1e-8
+        assert np.allclose(g["sym_rms"][vs], o["sym_rms"], rtol=1e-8, atol=1e-9) and rel(g["poses"][vs], o["poses"]) < 1e-7
+    assert g["view_success"][5] == 0 and g["view_success"].sum() >= len(keep_n) - (keep_n < 4).sum() - 2
 
 
 def test_planar_poses_match_oracle():
