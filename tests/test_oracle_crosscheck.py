@@ -1,0 +1,132 @@
+"""Independent cross-checks of the oracle ("sanity cross-checks available in the image").
+
+The reference's Ceres cannot run here, so its converged parameters on NOISY data are not recorded anywhere; what
+can be checked is that the oracle's LM lands on the minimiser of the reference's objective, found by solvers that
+share no code with it:
+  * OpenCV's calibrateCamera — the same pinhole + Brown-Conrady model (k1 k2 p1 p2 k3, no skew) and the same
+    sum of squared reprojection errors as optimize_intrinsics without a loss (optim/intrinsics.cpp:63-90);
+  * scipy.optimize.least_squares on a numpy restatement of the residuals (geometry.project, written to
+    SYNTHESISE the pixels) with the per-block Huber loss folded into the residuals: r_b * sqrt(rho(s_b) / s_b)
+    has exactly the robustified cost as its sum of squares, whatever Gauss-Newton model a solver builds on it.
+Neither is parity with the reference; both pin the objective (models, pose chains, loss per residual block) and
+the minimiser the restated LM converges to."""
+import numpy as np
+import pytest
+from scipy.optimize import least_squares
+from scipy.spatial.transform import Rotation
+
+import oracle_lib as O
+from calibration_b200 import abi, synth
+from calibration_b200 import geometry as G
+
+
+def huber_scale(s, delta):
+    """sqrt(rho(s) / s) for ceres::HuberLoss(delta): rho(s) = s for s <= delta^2, else 2 delta sqrt(s) - delta^2."""
+    if delta <= 0 or s <= delta * delta:
+        return 1.0
+    return np.sqrt((2.0 * delta * np.sqrt(s) - delta * delta) / s)
+
+
+def to_rt(T):
+    return np.concatenate([Rotation.from_matrix(T[:3, :3]).as_rotvec(), T[:3, 3]])
+
+
+def from_rt(p):
+    T = np.eye(4); T[:3, :3] = Rotation.from_rotvec(p[:3]).as_matrix(); T[:3, 3] = p[3:6]
+    return T
+
+
+def test_intrinsics_minimiser_equals_opencv_calibrate_camera():
+    cv2 = pytest.importorskip("cv2")
+    prob, x0, _ = synth.make_intrinsics(seed=7, noise=0.2, huber_delta=-1.0)
+    for name in ("x", "y", "u", "v"):   # calibrateCamera takes float32 points: give both solvers the same numbers
+        a = getattr(prob, name); a[:] = a.astype(np.float32).astype(np.float64)
+    off = np.asarray(prob.block_offset); nv = len(off) - 1
+    x_o, res, _ = O.refine_solve(prob, x0, abi.OptimOptions.default(compute_covariance=0))
+    assert res.success
+    objp = [np.stack([prob.x[off[k]:off[k + 1]], prob.y[off[k]:off[k + 1]], np.zeros(off[k + 1] - off[k])], 1).astype(np.float32) for k in range(nv)]
+    imgp = [np.stack([prob.u[off[k]:off[k + 1]], prob.v[off[k]:off[k + 1]]], 1).astype(np.float32).reshape(-1, 1, 2) for k in range(nv)]
+    K0 = np.array([[x0[0], 0, x0[2]], [0, x0[1], x0[3]], [0, 0, 1.0]])
+    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 2000, 1e-16)
+    rms, K, dist, rv, tv = cv2.calibrateCamera(objp, imgp, (1280, 720), K0.copy(), np.zeros(5), flags=cv2.CALIB_USE_INTRINSIC_GUESS, criteria=crit)
+    rms_o = np.sqrt(2.0 * res.final_cost / len(prob.u))          # cost = 1/2 sum r^2 over 2 n_obs residuals; OpenCV: per point
+    assert abs(rms - rms_o) <= 1e-9 * rms                         # same minimum of the same objective
+    assert abs(K[0, 0] - x_o[0]) <= 1e-6 * x_o[0] and abs(K[1, 1] - x_o[1]) <= 1e-6 * x_o[1]
+    assert abs(K[0, 2] - x_o[2]) <= 1e-3 and abs(K[1, 2] - x_o[3]) <= 1e-3 and x_o[4] == 0.0
+    d = dist.ravel()                                              # OpenCV order k1 k2 p1 p2 k3; ours k1 k2 k3 p1 p2
+    assert abs(d[0] - x_o[5]) <= 1e-4 * abs(x_o[5]) and abs(d[1] - x_o[6]) <= 1e-3 * abs(x_o[6]) and abs(d[4] - x_o[7]) <= 1e-3 * abs(x_o[7])
+    assert abs(d[2] - x_o[8]) <= 1e-6 and abs(d[3] - x_o[9]) <= 1e-6
+    _, poses = G.unpack_intrinsics(x_o, nv)
+    for k in range(nv):
+        R, _ = cv2.Rodrigues(rv[k])
+        assert np.abs(R - poses[k][:3, :3]).max() <= 1e-5 and np.abs(tv[k].ravel() - poses[k][:3, 3]).max() <= 1e-5
+
+
+def intrinsics_residuals(p, prob, off, delta):
+    nv = len(off) - 1
+    intr = np.concatenate([p[:4], [0.0], p[4:9]])
+    out = []
+    for k in range(nv):
+        T = from_rt(p[9 + 6 * k:15 + 6 * k])
+        s = slice(off[k], off[k + 1])
+        P = np.stack([prob.x[s], prob.y[s], np.zeros(off[k + 1] - off[k])], 1) @ T[:3, :3].T + T[:3, 3]
+        r = (G.project(intr, P) - np.stack([prob.u[s], prob.v[s]], 1)).ravel()
+        out.append(r * huber_scale(r @ r, delta))
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("delta", [1.0, -1.0])
+def test_intrinsics_minimiser_equals_scipy_with_per_block_huber(delta):
+    prob, x0, _ = synth.make_intrinsics(seed=11, n_views=12, noise=0.3, huber_delta=delta)
+    off = np.asarray(prob.block_offset); nv = len(off) - 1
+    x_o, res, _ = O.refine_solve(prob, x0, abi.OptimOptions.default(compute_covariance=0, epsilon=1e-13))
+    assert res.success
+    intr0, poses0 = G.unpack_intrinsics(x0, nv)
+    p0 = np.concatenate([intr0[:4], intr0[5:10]] + [to_rt(T) for T in poses0])
+    sol = least_squares(intrinsics_residuals, p0, args=(prob, off, delta), method="trf", jac="3-point", x_scale="jac", xtol=1e-15, ftol=1e-15,
+                        gtol=1e-15, max_nfev=400)
+    assert abs(sol.cost - res.final_cost) <= 1e-8 * res.final_cost       # scipy's cost is 1/2 sum f^2 as well
+    intr_o, poses_o = G.unpack_intrinsics(x_o, nv)
+    assert np.allclose(sol.x[:4], intr_o[:4], rtol=2e-5, atol=2e-3)
+    assert np.allclose(sol.x[4:9], intr_o[5:10], rtol=5e-3, atol=2e-5)
+    for k in range(nv):
+        assert np.abs(from_rt(sol.x[9 + 6 * k:15 + 6 * k]) - poses_o[k])[:3].max() <= 2e-5
+    if delta > 0:   # every block of 54 corners with 0.3 px noise is beyond delta = 1: the loss really acts
+        r = intrinsics_residuals(sol.x, prob, off, -1.0)
+        assert all((r[2 * off[k]:2 * off[k + 1]] ** 2).sum() > 1.0 for k in range(nv))
+
+
+def bundle_residuals(p, prob, off, cam, bTg, n_cams, delta):
+    out = []
+    b_T_t = from_rt(p[9 * n_cams + 6 * n_cams:9 * n_cams + 6 * n_cams + 6])
+    g_T_c = [from_rt(p[9 * n_cams + 6 * c:9 * n_cams + 6 * c + 6]) for c in range(n_cams)]
+    for b in range(len(off) - 1):
+        c = cam[b]
+        q = p[9 * c:9 * c + 9]
+        intr = np.concatenate([q[:4], [0.0], q[4:9]])
+        T = np.linalg.inv(g_T_c[c]) @ np.linalg.inv(bTg[b]) @ b_T_t        # bundleresidual.h:15-27
+        s = slice(off[b], off[b + 1])
+        P = np.stack([prob.x[s], prob.y[s], np.zeros(off[b + 1] - off[b])], 1) @ T[:3, :3].T + T[:3, 3]
+        r = (G.project(intr, P) - np.stack([prob.u[s], prob.v[s]], 1)).ravel()
+        out.append(r * huber_scale(r @ r, delta))
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("delta", [1.0, -1.0])
+def test_bundle_minimiser_equals_scipy(delta):
+    n_cams = 2
+    prob, x0, _ = synth.make_bundle(seed=3, n_cams=n_cams, n_poses=14, noise=0.25, huber_delta=delta)
+    off = np.asarray(prob.block_offset); cam = np.asarray(prob.block_cam)
+    bTg = [O.pose12_to_T(p) for p in np.asarray(prob.block_b_se3_g).reshape(-1, 12)]
+    x_o, res, _ = O.refine_solve(prob, x0, abi.OptimOptions.default(compute_covariance=0, epsilon=1e-13))
+    assert res.success
+    intr0, g0, b0 = G.unpack_bundle(x0, n_cams)
+    p0 = np.concatenate([np.concatenate([k[:4], k[5:10]]) for k in intr0] + [to_rt(T) for T in g0] + [to_rt(b0)])
+    sol = least_squares(bundle_residuals, p0, args=(prob, off, cam, bTg, n_cams, delta), method="trf", jac="3-point", x_scale="jac",
+                        xtol=1e-15, ftol=1e-15, gtol=1e-15, max_nfev=400)
+    assert abs(sol.cost - res.final_cost) <= 1e-8 * res.final_cost
+    intr_o, g_o, b_o = G.unpack_bundle(x_o, n_cams)
+    for c in range(n_cams):
+        assert np.allclose(sol.x[9 * c:9 * c + 4], intr_o[c][:4], rtol=2e-5, atol=2e-3)
+        assert np.abs(from_rt(sol.x[9 * n_cams + 6 * c:9 * n_cams + 6 * c + 6]) - g_o[c])[:3].max() <= 2e-5
+    assert np.abs(from_rt(sol.x[15 * n_cams:15 * n_cams + 6]) - b_o)[:3].max() <= 2e-5
