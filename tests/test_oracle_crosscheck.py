@@ -130,3 +130,29 @@ def test_bundle_minimiser_equals_scipy(delta):
         assert np.allclose(sol.x[9 * c:9 * c + 4], intr_o[c][:4], rtol=2e-5, atol=2e-3)
         assert np.abs(from_rt(sol.x[9 * n_cams + 6 * c:9 * n_cams + 6 * c + 6]) - g_o[c])[:3].max() <= 2e-5
     assert np.abs(from_rt(sol.x[15 * n_cams:15 * n_cams + 6]) - b_o)[:3].max() <= 2e-5
+
+
+def test_covariance_blocks_equal_independent_inverse_normal_matrix():
+    """compute_covariance (ceresutils.h:69-126) without a loss is (J^T J)^-1 lifted to the ambient blocks.  Its
+    intrinsics block and its translation blocks do not depend on how rotations are parametrised, so they must equal
+    the same blocks of inv(J^T J) for the numpy residuals above (rotation-vector poses, numeric Jacobian)."""
+    from scipy.optimize._numdiff import approx_derivative
+    prob, x0, _ = synth.make_intrinsics(seed=11, n_views=12, noise=0.3, huber_delta=-1.0)
+    off = np.asarray(prob.block_offset); nv = len(off) - 1
+    x_o, res, cov = O.refine_solve(prob, x0, abi.OptimOptions.default(compute_covariance=1, epsilon=1e-13))
+    assert res.success and res.covariance_ok and cov.shape == (10 + 7 * nv, 10 + 7 * nv)
+    intr_o, poses_o = G.unpack_intrinsics(x_o, nv)
+    p = np.concatenate([intr_o[:4], intr_o[5:10]] + [to_rt(T) for T in poses_o])
+    J = approx_derivative(intrinsics_residuals, p, method="3-point", args=(prob, off, -1.0))
+    Cn = np.linalg.inv(J.T @ J)
+    idx = [0, 1, 2, 3, 5, 6, 7, 8, 9]
+    Co = cov[np.ix_(idx, idx)]
+    assert np.abs(Cn[:9, :9] - Co).max() <= 1e-7 * np.abs(Co).max()
+    assert not cov[4].any() and not cov[:, 4].any()                  # the constant skew has zero rows and columns
+    t0 = 10 + 4 * nv                                                 # block order [intr, all quats, all trans] (intrinsics.cpp:14-61)
+    for k in range(nv):
+        Ct = Cn[9 + 6 * k + 3:9 + 6 * k + 6, 9 + 6 * k + 3:9 + 6 * k + 6]
+        assert np.abs(Ct - cov[t0 + 3 * k:t0 + 3 * k + 3, t0 + 3 * k:t0 + 3 * k + 3]).max() <= 1e-7 * np.abs(Ct).max()
+        # intrinsics x translation cross block
+        Cx = Cn[:9, 9 + 6 * k + 3:9 + 6 * k + 6]
+        assert np.abs(Cx - cov[np.ix_(idx, range(t0 + 3 * k, t0 + 3 * k + 3))]).max() <= 1e-7 * np.abs(Cx).max()
