@@ -156,3 +156,74 @@ def test_covariance_blocks_equal_independent_inverse_normal_matrix():
         # intrinsics x translation cross block
         Cx = Cn[:9, 9 + 6 * k + 3:9 + 6 * k + 6]
         assert np.abs(Cx - cov[np.ix_(idx, range(t0 + 3 * k, t0 + 3 * k + 3))]).max() <= 1e-7 * np.abs(Cx).max()
+
+
+def extrinsics_residuals(p, prob, off, cam, view, n_cams, n_views, cam0, tgt0, delta):
+    """Free parameters only: cameras 1.., views 1.. (camera 0 and view 0 are held at their start values,
+    optim/extrinsics.cpp:122-139)."""
+    o = 9 * n_cams
+    c_T_r = [cam0] + [from_rt(p[o + 6 * (c - 1):o + 6 * c]) for c in range(1, n_cams)]
+    o += 6 * (n_cams - 1)
+    r_T_t = [tgt0] + [from_rt(p[o + 6 * (v - 1):o + 6 * v]) for v in range(1, n_views)]
+    out = []
+    for b in range(len(off) - 1):
+        c = cam[b]
+        q = p[9 * c:9 * c + 9]
+        T = c_T_r[c] @ r_T_t[view[b]]                                   # extrinsicsresidual.h:14-20
+        s = slice(off[b], off[b + 1])
+        P = np.stack([prob.x[s], prob.y[s], np.zeros(off[b + 1] - off[b])], 1) @ T[:3, :3].T + T[:3, 3]
+        r = (G.project(np.concatenate([q[:4], [0.0], q[4:9]]), P) - np.stack([prob.u[s], prob.v[s]], 1)).ravel()
+        out.append(r * huber_scale(r @ r, delta))
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("delta", [1.0, -1.0])
+def test_extrinsics_minimiser_equals_scipy(delta):
+    n_cams, n_views = 2, 10
+    prob, x0, _ = synth.make_extrinsics(seed=5, n_cams=n_cams, n_views=n_views, noise=0.25, huber_delta=delta)
+    off = np.asarray(prob.block_offset); cam = np.asarray(prob.block_cam); view = np.asarray(prob.block_view)
+    x_o, res, _ = O.refine_solve(prob, x0, abi.OptimOptions.default(compute_covariance=0, epsilon=1e-13))
+    assert res.success
+    intr0, c0, t0 = G.unpack_extrinsics(x0, n_cams, n_views)
+    p0 = np.concatenate([np.concatenate([k[:4], k[5:10]]) for k in intr0] + [to_rt(T) for T in c0[1:]] + [to_rt(T) for T in t0[1:]])
+    sol = least_squares(extrinsics_residuals, p0, args=(prob, off, cam, view, n_cams, n_views, c0[0], t0[0], delta), method="trf",
+                        jac="3-point", x_scale="jac", xtol=1e-15, ftol=1e-15, gtol=1e-15, max_nfev=400)
+    assert abs(sol.cost - res.final_cost) <= 1e-8 * res.final_cost
+    intr_o, c_o, t_o = G.unpack_extrinsics(x_o, n_cams, n_views)
+    assert np.abs(c_o[0] - c0[0]).max() == 0.0 and np.abs(t_o[0] - t0[0]).max() == 0.0    # the held blocks did not move
+    for c in range(n_cams):
+        assert np.allclose(sol.x[9 * c:9 * c + 4], intr_o[c][:4], rtol=5e-5, atol=5e-3)
+    assert np.abs(from_rt(sol.x[9 * n_cams:9 * n_cams + 6]) - c_o[1])[:3].max() <= 5e-5
+
+
+def axxb_residuals(p, ra, rb, ta, tb, delta):
+    """AxXbResidual (residuals/handeyeresidual.h:25-49): [Log(R_A R_X R_B^T R_X^T); (R_A - I) t_X - (R_X t_B - t_A)]."""
+    RX = Rotation.from_rotvec(p[:3]).as_matrix(); tX = p[3:6]
+    RA = ra.reshape(-1, 3, 3); RB = rb.reshape(-1, 3, 3)
+    S = RA @ RX @ np.transpose(RB, (0, 2, 1)) @ RX.T
+    rot = Rotation.from_matrix(S).as_rotvec()
+    tra = np.einsum("nij,j->ni", RA - np.eye(3), tX) - (tb @ RX.T - ta)
+    r = np.concatenate([rot, tra], axis=1)
+    s = (r * r).sum(axis=1)
+    return (r * np.array([huber_scale(v, delta) for v in s])[:, None]).ravel()
+
+
+@pytest.mark.parametrize("delta", [1.0, 0.002])
+def test_axxb_minimiser_equals_scipy(delta):
+    bg, ct, X_gt = synth.make_handeye_poses(seed=2024, n=16)
+    rng = np.random.default_rng(1)
+    ct = [synth.perturb_pose(rng, T, 0.3, 0.002) for T in ct]            # noisy camera poses: the minimum is not X_gt
+    ra, rb, ta, tb = O.build_all_pairs(bg, ct, 1.0)
+    assert len(ta) > 60
+    d = O.axxb_desc(ra, rb, ta, tb, huber_delta=delta)
+    X0 = synth.perturb_pose(rng, X_gt, 3.0, 0.01)
+    q0, t0 = G.pose_to_qt(X0)
+    x_o, res, _ = O.axxb_solve(d, np.concatenate([q0, t0]), abi.OptimOptions.default(epsilon=1e-14))
+    assert res.success
+    sol = least_squares(axxb_residuals, to_rt(X0), args=(ra, rb, ta, tb, delta), method="trf", jac="3-point", x_scale="jac", xtol=1e-15,
+                        ftol=1e-15, gtol=1e-15, max_nfev=300)
+    assert abs(sol.cost - res.final_cost) <= 1e-8 * res.final_cost
+    assert np.abs(from_rt(sol.x) - G.qt_to_pose(x_o[:4], x_o[4:7]))[:3].max() <= 1e-6
+    if delta < 1.0:   # the small delta puts pairs beyond it: the per-pair loss acts
+        r = axxb_residuals(sol.x, ra, rb, ta, tb, -1.0).reshape(-1, 6)
+        assert ((r * r).sum(axis=1) > delta * delta).mean() > 0.2
