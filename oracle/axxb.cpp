@@ -165,6 +165,10 @@ using namespace orc;
 
 extern "C" {
 
+// known-answer hooks for tests/unit/se3_utils_test.cpp:10-30
+void orc_project_to_so3(const double* R9, double* out9) { project_to_so3(R9, out9); }
+void orc_log_so3(const double* R9, double* w3) { log_so3(R9, w3); }
+
 int orc_axxb_eval(const orc_axxb_desc* d, const double* x7, double* cost, double* g6, double* H36, int num_threads) {
     AxxbLM lm; lm.d = d; lm.threads = num_threads;
     double c; const bool ok = lm.eval(x7, &c, g6 || H36);

@@ -149,6 +149,9 @@ typedef struct orc_plane_result {
     double inlier_rms;
     double min_margin;
 } orc_plane_result;
+/* project_to_so3 / log_so3 (common/se3_utils.h:10-42), used by the pair filter of build_all_pairs */
+void orc_project_to_so3(const double* R9, double* out9);
+void orc_log_so3(const double* R9, double* w3);
 void orc_ref_plane_data(double* plane, double* xyz /* [140][3] */);
 void orc_sample_stream_k(uint64_t seed, int32_t n, int32_t k, int32_t iters, int32_t* out);
 void orc_sample_stream_k_libstdcxx(uint64_t seed, int32_t n, int32_t k, int32_t iters, int32_t* out);

@@ -60,6 +60,8 @@ def lib():
         L.orc_estimate_intrinsics.argtypes = [i64, abi.c_int64_p, dp, dp, dp, dp, dp, dp, ip, dp, dp, dp]
         L.orc_estimate_intrinsics_ransac.argtypes = [i64, abi.c_int64_p, dp, dp, dp, dp, dp, C.POINTER(abi.RansacOptions), dp, ip, dp, dp, dp,
                                                      abi.c_uint8_p]
+        L.orc_project_to_so3.argtypes = [dp, dp]
+        L.orc_log_so3.argtypes = [dp, dp]
         L.orc_sample_stream_k.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_int32, ip]
         L.orc_sample_stream_k_libstdcxx.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_int32, ip]
         L.orc_ref_plane_data.argtypes = [dp, dp]
@@ -343,6 +345,16 @@ def axxb_desc(rot_a, rot_b, tra_a, tra_b, huber_delta=1.0):
     d.huber_delta = huber_delta
     d._keep = keep
     return d
+
+
+def project_to_so3(R):
+    out = np.zeros(9); lib().orc_project_to_so3(abi.dptr(abi.as_f64(np.asarray(R).reshape(9))), abi.dptr(out))
+    return out.reshape(3, 3)
+
+
+def log_so3(R):
+    out = np.zeros(3); lib().orc_log_so3(abi.dptr(abi.as_f64(np.asarray(R).reshape(9))), abi.dptr(out))
+    return out
 
 
 def build_all_pairs(base_se3_gripper, cam_se3_target, min_angle_deg):
