@@ -1,6 +1,7 @@
 """The CUDA RANSAC kernels against outputs of the REFERENCE's own calib::ransac<> loop (tests/golden/ransac_ref.npz,
 generated in the build container from /root/reference through oracle/_ref; see tests/golden/make_golden.py):
-same inlier set, same best.iters, model to 1e-9.  Cases whose oracle run reports a residual within 1e-10 of the
+same inlier set, same best.iters, model to 1e-7 relative (the tolerance of the GPU-vs-oracle RANSAC tests: the DLT null
+vector comes from a different factorisation).  Cases whose oracle run reports a residual within 1e-10 of the
 threshold are skipped (rounding could move a point across it)."""
 import numpy as np
 import pytest
@@ -25,5 +26,5 @@ def test_cuda_ransac_reproduces_reference_loop_outputs():
             model = np.array(res[0].plane)
             if res[0].success and np.dot(model[:3], ref["model"][:3]) < 0:
                 model = -model                                           # refit sign: see ransac_plane.cu header
-        n_ok += check_against_reference_loop(key, res[0], mask[0], model, margin > 1e-10, ref)
+        n_ok += check_against_reference_loop(key, res[0], mask[0], model, margin > 1e-10, ref, model_rtol=1e-7, rms_atol=1e-9)
     assert n_ok >= 11
