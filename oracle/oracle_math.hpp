@@ -15,9 +15,14 @@
 //     for the Eigen/Ceres calls (Eigen and Ceres are absent from this image).
 //
 // Parity status: pinned against the reference's own synthetic-recovery tests
-// (tests/unit/*_test.cpp re-expressed in oracle/refdata.cpp) and against this
-// image's libstdc++ std::sample; parity against real Ceres iterates on noisy
-// data is UNPINNED (Ceres cannot be built here) — see DESIGN.md.
+// (tests/unit/*_test.cpp re-expressed in oracle/refdata.cpp), against this
+// image's libstdc++ std::sample, and — for the RANSAC loop — bit for bit against
+// the reference's own ransac<> template compiled from /root/reference
+// (oracle/_ref, ref_ransac_harness.cpp; outputs frozen in tests/golden/).  The
+// minimisers on noisy data are cross-checked against OpenCV and scipy
+// (tests/test_oracle_crosscheck.py).  Parity against real Ceres ITERATES
+// (iteration counts, covariance digits) is UNPINNED: Ceres cannot be built here
+// — see DESIGN.md.
 #pragma once
 #include <algorithm>
 #include <cfloat>
