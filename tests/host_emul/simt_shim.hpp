@@ -25,7 +25,12 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __shared__
+// static __shared__ arrays become function-local statics (one CTA runs at a time); a translation unit whose kernels
+// declare dynamic shared memory (`extern __shared__`) leaves SIMT_SHARED_STORAGE empty instead
+#ifndef SIMT_SHARED_STORAGE
+#define SIMT_SHARED_STORAGE
+#endif
+#define __shared__ SIMT_SHARED_STORAGE
 #define __align__(n) __attribute__((aligned(n)))
 #define __launch_bounds__(...)
 #define __grid_constant__

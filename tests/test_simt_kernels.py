@@ -145,3 +145,125 @@ def test_plane_kernel_degenerate_inputs(simt):
     assert not any(r.success for r in rg) and all(r.iters_run == 40 for r in rg)
     _, rg = compare_p(simt, np.zeros((2, 2)), np.ones((2, 2)), np.zeros((2, 2)), abi.RansacOptions.default(min_inliers=1))
     assert not any(r.success for r in rg) and all(r.iters_run == 0 for r in rg)
+
+
+# ---------------------------------------------------------------------------
+# seeding kernels (csrc/seed_kernels.cuh + seed_host.hpp) under the same shim
+# ---------------------------------------------------------------------------
+SEED_SRC = os.path.join(ROOT, "tests", "host_emul", "seed_simt.cpp")
+SEED_SO = os.path.join(ROOT, "tests", "host_emul", "_build", "libseed_simt.so")
+
+
+@pytest.fixture(scope="module")
+def seed_simt():
+    deps = [SEED_SRC, os.path.join(ROOT, "tests", "host_emul", "simt_shim.hpp")] + [
+        os.path.join(CSRC, f) for f in ("seed_kernels.cuh", "seed_host.hpp", "dlt.cuh")]
+    if not os.path.exists(SEED_SO) or any(os.path.getmtime(d) > os.path.getmtime(SEED_SO) for d in deps):
+        os.makedirs(os.path.dirname(SEED_SO), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([cxx, "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-o", SEED_SO, SEED_SRC], check=True)
+    L = C.CDLL(SEED_SO)
+    dp, ip = abi.c_double_p, abi.c_int32_p
+    L.simt_seed_intrinsics.argtypes = [C.c_int64, abi.c_int64_p, ip, dp, dp, dp, dp, C.c_int32, C.POINTER(abi.SeedOptions), dp, ip, ip, dp, dp, dp]
+    L.simt_seed_planar_poses.argtypes = [C.c_int64, abi.c_int64_p, ip, dp, dp, dp, dp, dp, dp, ip]
+    L.simt_gather_scatter_roundtrip.argtypes = [C.c_int64, C.c_int32, abi.c_int64_p, abi.c_int64_p, dp, dp, dp, dp, dp, dp, dp, dp,
+                                                C.POINTER(abi.RansacResult), abi.c_uint8_p, C.POINTER(abi.RansacResult), abi.c_uint8_p]
+    return L
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300))
+
+
+def simt_seed_intrinsics(L, x, y, u, v, off, cam=None, n_cams=1, bounds=None):
+    x, y, u, v = (abi.as_f64(a) for a in (x, y, u, v))
+    off = np.ascontiguousarray(off, dtype=np.int64); nv = len(off) - 1
+    cam = np.zeros(nv, dtype=np.int32) if cam is None else np.ascontiguousarray(cam, dtype=np.int32)
+    opts = abi.SeedOptions.from_bounds(bounds)
+    kmtx = np.zeros((n_cams, 5)); cam_ok = np.zeros(n_cams, dtype=np.int32); ok = np.zeros(nv, dtype=np.int32)
+    H = np.zeros((nv, 9)); rms = np.zeros(nv); poses = np.zeros((nv, 12))
+    assert L.simt_seed_intrinsics(nv, abi.i64ptr(off), abi.i32ptr(cam), abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v), n_cams, C.byref(opts),
+                                  abi.dptr(kmtx), abi.i32ptr(cam_ok), abi.i32ptr(ok), abi.dptr(H), abi.dptr(rms), abi.dptr(poses)) == 0
+    return dict(kmtx=kmtx, cam_success=cam_ok, view_success=ok, hmtx=H.reshape(nv, 3, 3), sym_rms=rms, poses=poses)
+
+
+def noisy_multicam(n_cams=2, n_poses=60, seed=3):
+    prob, _, _ = synth.make_bundle(seed=seed, n_cams=n_cams, n_poses=n_poses)
+    rng = np.random.default_rng(seed)
+    nb = prob.desc.n_blocks
+    keep = rng.integers(20, 89, size=nb); keep[5] = 3; keep[17] = 4; keep[40] = 0   # < 4 points: failed views
+    pick = lambda b: np.array([0, 7, 40, 85]) if keep[b] == 4 else np.arange(keep[b])
+    idx = np.concatenate([prob.block_offset[b] + pick(b) for b in range(nb)]).astype(np.int64)
+    off = np.concatenate([[0], np.cumsum(keep)])
+    return prob.x[idx], prob.y[idx], prob.u[idx], prob.v[idx], off, np.asarray(prob.block_cam), n_cams
+
+
+def test_seed_kernels_reference_scenario(seed_simt):
+    from test_oracle_seed import intrinsics_estimate_scenario
+    intr, c_se3_t, (xs, ys, us, vs, off) = intrinsics_estimate_scenario()
+    g = simt_seed_intrinsics(seed_simt, xs, ys, us, vs, off)
+    o = O.estimate_intrinsics(xs, ys, us, vs, off)
+    assert g["cam_success"][0] == 1 and g["view_success"].all()
+    assert np.abs(g["kmtx"][0, :4] - intr[:4]).max() < 1e-6 and abs(g["kmtx"][0, 4]) < 1e-9   # intrinsics_estimate_test.cpp:39-44
+    assert rel(g["kmtx"][0, :4], o["kmtx"][:4]) < 1e-9 and rel(g["hmtx"], o["hmtx"]) < 1e-9 and rel(g["poses"], o["poses"]) < 1e-8
+    _, _, (xs, ys, us, vs, off) = intrinsics_estimate_scenario(seed=5, n_frames=3, rows=5, cols=7, spacing=0.04, k=(800.0, 805.0, 320.0, 240.0))
+    g = simt_seed_intrinsics(seed_simt, xs, ys, us, vs, off)
+    assert g["cam_success"][0] == 0 and np.allclose(g["poses"][:, :9], np.eye(3).ravel())       # too few views
+
+
+def test_seed_kernels_noisy_ragged_multicamera(seed_simt):
+    xs, ys, us, vs, off, cam, n_cams = noisy_multicam()
+    g = simt_seed_intrinsics(seed_simt, xs, ys, us, vs, off, cam=cam, n_cams=n_cams)
+    for c in range(n_cams):
+        sel = np.flatnonzero(cam == c)
+        pieces = [np.arange(off[k], off[k + 1]) for k in sel]
+        idx = np.concatenate(pieces).astype(np.int64)
+        o = O.estimate_intrinsics(xs[idx], ys[idx], us[idx], vs[idx], np.concatenate([[0], np.cumsum([len(p) for p in pieces])]))
+        assert o["success"] and g["cam_success"][c] == 1 and np.array_equal(g["view_success"][sel], o["view_success"])
+        assert rel(g["kmtx"][c], o["kmtx"]) < 1e-7
+        ok = o["view_success"] == 1
+        assert rel(g["hmtx"][sel][ok], o["hmtx"][ok]) < 1e-8
+        assert np.allclose(g["sym_rms"][sel][ok], o["sym_rms"][ok], rtol=1e-8, atol=1e-6)
+        assert rel(g["poses"][sel], o["poses"]) < 1e-7
+    assert (g["view_success"] == 0).sum() == 2
+    bounds = [200.0, 2000.0, 150.0, 2000.0, 100.0, 200.0, 50.0, 75.0, -1.0, 1.0]
+    xs, ys, us, vs, off, cam, _ = noisy_multicam(n_cams=1, n_poses=60)
+    g = simt_seed_intrinsics(seed_simt, xs, ys, us, vs, off, bounds=bounds)
+    o = O.estimate_intrinsics(xs, ys, us, vs, off, bounds10=bounds)
+    assert g["kmtx"][0, 2] == 150.0 and g["kmtx"][0, 3] == 62.5 and rel(g["kmtx"][0], o["kmtx"]) < 1e-7
+
+
+def test_planar_pose_kernel(seed_simt):
+    xs, ys, us, vs, off, cam, n_cams = noisy_multicam()
+    kmtx = np.array([[1000.0, 1005.0, 640.0, 360.0, 0.0], [1010.0, 1015.0, 640.0, 360.0, 0.5]])
+    off = np.ascontiguousarray(off, dtype=np.int64); nv = len(off) - 1
+    poses = np.zeros((nv, 12)); ok = np.zeros(nv, dtype=np.int32)
+    xs, ys, us, vs = (abi.as_f64(a) for a in (xs, ys, us, vs)); cam = np.ascontiguousarray(cam, dtype=np.int32)
+    assert seed_simt.simt_seed_planar_poses(nv, abi.i64ptr(off), abi.i32ptr(cam), abi.dptr(xs), abi.dptr(ys), abi.dptr(us), abi.dptr(vs),
+                                            abi.dptr(kmtx), abi.dptr(poses), abi.i32ptr(ok)) == 0
+    for k in range(nv):
+        s = slice(off[k], off[k + 1])
+        T = O.estimate_planar_pose(xs[s], ys[s], us[s], vs[s], kmtx[cam[k]])
+        assert rel(poses[k], np.concatenate([T[:3, :3].ravel(), T[:3, 3]])) < 1e-8, k
+        assert ok[k] == (off[k + 1] - off[k] >= 4)
+
+
+def test_gather_scatter_kernels_for_ragged_ransac_views(seed_simt):
+    rng = np.random.default_rng(0)
+    sizes = rng.choice([5, 9, 9, 12], size=11); sizes[3] = 9; sizes[7] = 9
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    x, y, u, v = rng.normal(size=(4, off[-1]))
+    ids = np.flatnonzero(sizes == 9).astype(np.int64); cnt, n = len(ids), 9
+    g = np.zeros((4, cnt * n)); gres = (abi.RansacResult * cnt)(); gmask = rng.integers(0, 2, cnt * n).astype(np.uint8)
+    for p in range(cnt):
+        gres[p].iters = 100 + p; gres[p].success = 1
+    res = (abi.RansacResult * len(sizes))(); mask = np.zeros(off[-1], dtype=np.uint8)
+    assert seed_simt.simt_gather_scatter_roundtrip(cnt, n, abi.i64ptr(ids), abi.i64ptr(off), abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v),
+                                                   abi.dptr(g[0]), abi.dptr(g[1]), abi.dptr(g[2]), abi.dptr(g[3]), gres,
+                                                   gmask.ctypes.data_as(abi.c_uint8_p), res, mask.ctypes.data_as(abi.c_uint8_p)) == 0
+    for p, k in enumerate(ids):
+        s = slice(off[k], off[k + 1])
+        assert np.array_equal(g[0, p * n:(p + 1) * n], x[s]) and np.array_equal(g[3, p * n:(p + 1) * n], v[s])
+        assert res[k].iters == 100 + p and np.array_equal(mask[s], gmask[p * n:(p + 1) * n])
+    others = np.setdiff1d(np.arange(len(sizes)), ids)
+    assert all(res[k].success == 0 for k in others) and not any(mask[off[k]:off[k + 1]].any() for k in others)
