@@ -109,6 +109,10 @@ template <class T>
 inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
     return simt::exchange(v, [&](const uint64_t* s) { return simt::from_bits<T>(s[(simt::tl_lane ^ lane_mask) & 31]); });
 }
+template <class T>
+inline T __shfl_down_sync(unsigned, T v, int delta) {   // lanes whose source is out of range keep their own value
+    return simt::exchange(v, [&](const uint64_t* s) { const int src = simt::tl_lane + delta; return src < 32 ? simt::from_bits<T>(s[src]) : v; });
+}
 inline unsigned __ballot_sync(unsigned, int pred) {
     return simt::exchange<uint64_t>(pred ? 1u : 0u, [&](const uint64_t* s) { unsigned m = 0; for (int i = 0; i < 32; ++i) m |= (unsigned)(s[i] & 1u) << i; return m; });
 }
@@ -116,6 +120,7 @@ inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0
 inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 
 // ---- device intrinsics ----
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }

@@ -267,3 +267,69 @@ def test_gather_scatter_kernels_for_ragged_ransac_views(seed_simt):
         assert res[k].iters == 100 + p and np.array_equal(mask[s], gmask[p * n:(p + 1) * n])
     others = np.setdiff1d(np.arange(len(sizes)), ids)
     assert all(res[k].success == 0 for k in others) and not any(mask[off[k]:off[k + 1]].any() for k in others)
+
+
+# ---------------------------------------------------------------------------
+# AX = XB kernels (csrc/axxb_kernels.cuh) under the same shim
+# ---------------------------------------------------------------------------
+AXXB_SRC = os.path.join(ROOT, "tests", "host_emul", "axxb_simt.cpp")
+AXXB_SO = os.path.join(ROOT, "tests", "host_emul", "_build", "libaxxb_simt.so")
+
+
+@pytest.fixture(scope="module")
+def axxb_simt():
+    deps = [AXXB_SRC, os.path.join(ROOT, "tests", "host_emul", "simt_shim.hpp")] + [os.path.join(CSRC, f) for f in ("axxb_kernels.cuh", "k1_math.cuh")]
+    if not os.path.exists(AXXB_SO) or any(os.path.getmtime(d) > os.path.getmtime(AXXB_SO) for d in deps):
+        os.makedirs(os.path.dirname(AXXB_SO), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([cxx, "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-o", AXXB_SO, AXXB_SRC], check=True)
+    L = C.CDLL(AXXB_SO)
+    dp = abi.c_double_p
+    L.simt_axxb_eval.argtypes = [C.c_int64, dp, dp, dp, dp, C.c_double, dp, C.c_int, dp, dp, dp]
+    L.simt_axxb_eval_from_poses.restype = C.c_int64
+    L.simt_axxb_eval_from_poses.argtypes = [C.c_int64, dp, dp, C.c_double, C.c_int, C.c_double, C.c_double, dp, C.c_int, dp, dp, dp]
+    return L
+
+
+def handeye_case(n, seed=2024, noise=True):
+    from calibration_b200 import geometry as G
+    bg, ct, X_gt = synth.make_handeye_poses(seed=seed, n=n)
+    rng = np.random.default_rng(seed + 1)
+    if noise:
+        ct = [synth.perturb_pose(rng, T, 0.3, 0.002) for T in ct]
+    X0 = synth.perturb_pose(rng, X_gt, 3.0, 0.01)
+    return bg, ct, G.pack_handeye(X0)
+
+
+@pytest.mark.parametrize("huber", [1.0, 0.002, -1.0])
+def test_axxb_kernels_materialised_pairs(axxb_simt, huber):
+    bg, ct, x7 = handeye_case(30)
+    ra, rb, ta, tb = O.build_all_pairs(bg, ct, 1.0)
+    n = len(ta)
+    assert n > 300                                   # more than one CTA of 256 pairs
+    c_o, g_o, H_o = O.axxb_eval(O.axxb_desc(ra, rb, ta, tb, huber), x7)
+    cost = C.c_double(); g = np.zeros(6); H = np.zeros((6, 6))
+    ra, rb, ta, tb = (abi.as_f64(a) for a in (ra, rb, ta, tb))
+    assert axxb_simt.simt_axxb_eval(n, abi.dptr(ra), abi.dptr(rb), abi.dptr(ta), abi.dptr(tb), huber, abi.dptr(abi.as_f64(x7)), 1,
+                                    C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g), abi.dptr(H)) == 0
+    assert abs(cost.value - c_o) <= 1e-12 * c_o
+    assert np.abs(g - g_o).max() <= 1e-10 * np.abs(g_o).max() and np.abs(H - H_o).max() <= 1e-10 * np.abs(H_o).max()
+    c2 = C.c_double()
+    assert axxb_simt.simt_axxb_eval(n, abi.dptr(ra), abi.dptr(rb), abi.dptr(ta), abi.dptr(tb), huber, abi.dptr(abi.as_f64(x7)), 0,
+                                    C.cast(C.byref(c2), abi.c_double_p), None, None) == 0
+    assert abs(c2.value - c_o) <= 1e-12 * c_o       # the residual-only instantiation
+
+
+@pytest.mark.parametrize("n_poses,min_angle", [(20, 0.5), (45, 8.0), (70, 1.0)])
+def test_axxb_kernels_pairs_on_the_fly(axxb_simt, n_poses, min_angle):
+    from calibration_b200 import geometry as G
+    bg, ct, x7 = handeye_case(n_poses, seed=7)
+    ra, rb, ta, tb = O.build_all_pairs(bg, ct, min_angle)
+    c_o, g_o, H_o = O.axxb_eval(O.axxb_desc(ra, rb, ta, tb, 1.0), x7)
+    bg12 = abi.as_f64(np.stack([G.pose_to_vec12(T) for T in bg])); ct12 = abi.as_f64(np.stack([G.pose_to_vec12(T) for T in ct]))
+    cost = C.c_double(); g = np.zeros(6); H = np.zeros((6, 6))
+    kept = axxb_simt.simt_axxb_eval_from_poses(n_poses, abi.dptr(bg12), abi.dptr(ct12), min_angle, 1, 1e-3, 1.0, abi.dptr(abi.as_f64(x7)), 1,
+                                               C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g), abi.dptr(H))
+    assert kept == len(ta) and 0 < kept <= n_poses * (n_poses - 1) // 2          # is_good_pair keeps the same pairs
+    assert abs(cost.value - c_o) <= 1e-11 * c_o
+    assert np.abs(g - g_o).max() <= 1e-9 * np.abs(g_o).max() and np.abs(H - H_o).max() <= 1e-9 * np.abs(H_o).max()
