@@ -21,6 +21,19 @@
 #include <thread>
 #include <vector>
 
+// the CUDA runtime header (pulled in by some product headers for cudaStream_t) defines the same decorations for a
+// host compiler: take it first where it exists, then impose the shim's meanings
+#if __has_include(<cuda_runtime.h>)
+#include <cuda_runtime.h>
+#endif
+#undef __global__
+#undef __device__
+#undef __host__
+#undef __forceinline__
+#undef __shared__
+#undef __align__
+#undef __launch_bounds__
+#undef __grid_constant__
 #define __global__
 #define __device__
 #define __host__
@@ -74,6 +87,19 @@ inline auto exchange(T mine, F&& read) {
     w.bar.arrive_and_wait();
     return r;
 }
+
+// ---- stand-ins for the asynchronous-copy machinery of the kernels that stage tiles with TMA (CALIB_SIMT_SHIM
+// branches of k1_kernel.cuh): the bulk copy is a memcpy by the issuing thread, the mbarrier a completion counter
+// every thread polls, the named barrier `bar.sync 1, n` (n = the whole CTA in those kernels) the CTA rendezvous ----
+inline void mbar_init(unsigned long long* b) { __atomic_store_n(b, 0ULL, __ATOMIC_RELEASE); }
+inline void bulk_copy_and_complete(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
+    std::memcpy(dst, src, bytes);
+    __atomic_fetch_add(b, 1ULL, __ATOMIC_RELEASE);
+}
+inline void mbar_wait(const unsigned long long* b, unsigned long long completions) {
+    while (__atomic_load_n(b, __ATOMIC_ACQUIRE) < completions) std::this_thread::yield();
+}
+inline void named_barrier(int /*n_threads: the whole CTA*/) { tl_cta->bar.arrive_and_wait(); }
 
 // Runs `kernel()` for every thread of every CTA of the grid.  The CTA size must be a multiple of 32.
 inline void launch(unsigned grid, unsigned block, const std::function<void()>& kernel);

@@ -333,3 +333,80 @@ def test_axxb_kernels_pairs_on_the_fly(axxb_simt, n_poses, min_angle):
     assert kept == len(ta) and 0 < kept <= n_poses * (n_poses - 1) // 2          # is_good_pair keeps the same pairs
     assert abs(cost.value - c_o) <= 1e-11 * c_o
     assert np.abs(g - g_o).max() <= 1e-9 * np.abs(g_o).max() and np.abs(H - H_o).max() <= 1e-9 * np.abs(H_o).max()
+
+
+# ---------------------------------------------------------------------------
+# K1 itself (csrc/k1_kernel.cuh) with the layout / setup kernels, bundle kind, fused epilogue
+# ---------------------------------------------------------------------------
+K1_SRC = os.path.join(ROOT, "tests", "host_emul", "k1_simt.cpp")
+K1_SO = os.path.join(ROOT, "tests", "host_emul", "_build", "libk1_simt.so")
+
+
+@pytest.fixture(scope="module")
+def k1_simt():
+    deps = [K1_SRC, os.path.join(ROOT, "tests", "host_emul", "simt_shim.hpp")] + [
+        os.path.join(CSRC, f) for f in ("k1_kernel.cuh", "k1_roles.hpp", "k1_math.cuh", "refine_kernels.cuh", "refine_setup_kernels.cuh", "refine_model.hpp")]
+    if not os.path.exists(K1_SO) or any(os.path.getmtime(d) > os.path.getmtime(K1_SO) for d in deps):
+        os.makedirs(os.path.dirname(K1_SO), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([cxx, "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I/usr/local/cuda/include", "-o", K1_SO, K1_SRC],
+                       check=True)
+    L = C.CDLL(K1_SO)
+    dp = abi.c_double_p
+    L.simt_bundle_eval.argtypes = [C.POINTER(abi.ProblemDesc), dp, dp, dp, dp, abi.c_int32_p, abi.c_int32_p]
+    L.simt_tangent_count.restype = C.c_int64
+    L.simt_tangent_count.argtypes = [C.POINTER(abi.ProblemDesc)]
+    return L
+
+
+def k1_eval(L, prob, x0):
+    n = L.simt_tangent_count(C.byref(prob.desc))
+    cost = C.c_double(); g = np.zeros(n); H = np.zeros((n, n)); roles = C.c_int32(); uni = C.c_int32()
+    assert L.simt_bundle_eval(C.byref(prob.desc), abi.dptr(abi.as_f64(x0)), C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g), abi.dptr(H),
+                              C.byref(roles), C.byref(uni)) == 0
+    return cost.value, g, H, roles.value, uni.value
+
+
+K1_CASES = {   # n_poses = 32: whole tiles of full-depth blocks, the predicate-free loop; 21 / 37: padded tiles, the predicated loop
+    "default_uniform": (dict(n_cams=3, n_poses=32), 2),
+    "default_padded": (dict(n_cams=3, n_poses=21), 2),
+    "fixed_intrinsics": (dict(n_cams=2, n_poses=32, optimize_intrinsics=False), 1),
+    "skew": (dict(n_cams=2, n_poses=32, optimize_skew=True), 3),
+    "skew_padded": (dict(n_cams=2, n_poses=37, optimize_skew=True), 3),
+    "only_target": (dict(n_cams=2, n_poses=32, optimize_intrinsics=False, optimize_hand_eye=False), 1),
+    "only_handeye": (dict(n_cams=2, n_poses=21, optimize_intrinsics=False, optimize_target_pose=False), 1),
+    "only_intrinsics": (dict(n_cams=2, n_poses=32, optimize_hand_eye=False, optimize_target_pose=False), 2),
+    "scheimpflug": (dict(n_cams=2, n_poses=32, model=abi.MODEL_SCHEIMPFLUG_BC5), 3),
+    "scheimpflug_skew": (dict(n_cams=2, n_poses=21, model=abi.MODEL_SCHEIMPFLUG_BC5, optimize_skew=True), 3),
+    "scheimpflug_fixed_intrinsics": (dict(n_cams=2, n_poses=32, model=abi.MODEL_SCHEIMPFLUG_BC5, optimize_intrinsics=False), 1),
+    "no_loss": (dict(n_cams=3, n_poses=32, huber_delta=-1.0), 2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(K1_CASES))
+def test_k1_source_matches_oracle(k1_simt, name):
+    kw, n_roles = K1_CASES[name]
+    prob, x0, _ = synth.make_bundle(**kw)
+    c_o, g_o, H_o = O.refine_eval(prob, x0)
+    c, g, H, roles, uni = k1_eval(k1_simt, prob, x0)
+    assert roles == n_roles                                       # 1, 2 and 3 role warps per tile are all exercised
+    assert uni == kw["n_cams"] * (kw["n_poses"] // 32)             # whole tiles of full-depth blocks take the predicate-free loop
+    assert len(g) == len(g_o)
+    assert abs(c - c_o) <= 1e-12 * abs(c_o)
+    assert np.abs(g - g_o).max() <= 1e-10 * np.abs(g_o).max()
+    assert np.abs(H - H_o).max() <= 1e-10 * np.abs(H_o).max()
+
+
+def test_k1_source_ragged_blocks(k1_simt):
+    prob, x0, _ = synth.make_bundle(n_cams=2, n_poses=37)
+    rng = np.random.default_rng(11)
+    nb = prob.desc.n_blocks
+    keep = rng.integers(1, 89, size=nb); keep[0] = 1
+    idx = np.concatenate([np.arange(prob.block_offset[b], prob.block_offset[b] + keep[b]) for b in range(nb)])
+    off = np.concatenate([[0], np.cumsum(keep)])
+    p2 = abi.Problem(abi.KIND_BUNDLE, abi.MODEL_PINHOLE_BC5, 2, 0, prob.x[idx], prob.y[idx], prob.u[idx], prob.v[idx], off,
+                     prob.block_cam, block_b_se3_g=prob.block_b_se3_g, optimize_intrinsics=True, huber_delta=1.0)
+    c_o, g_o, H_o = O.refine_eval(p2, x0)
+    c, g, H, roles, uni = k1_eval(k1_simt, p2, x0)
+    assert uni == 0 and abs(c - c_o) <= 1e-12 * abs(c_o)
+    assert np.abs(g - g_o).max() <= 1e-10 * np.abs(g_o).max() and np.abs(H - H_o).max() <= 1e-10 * np.abs(H_o).max()
