@@ -9,20 +9,27 @@
 //   calib::estimate_homography (RANSAC)   include/calib/estimation/linear/homography.h:22-24
 //   calib::fit_plane_ransac               include/calib/estimation/linear/planefit.h:23-24
 //
-// It needs the reference's own headers (Eigen types, camera models, option and
-// result structs) and is therefore only compiled inside the reference tree —
-// Eigen is not present in the image this library is developed in, so this file
-// is exercised there, not here.  It contains no arithmetic:
-// packing into SoA/CSR, the C call, unpacking, and the error mapping
-// (CAL_ERR_INVALID_ARGUMENT -> std::invalid_argument, CAL_ERR_RUNTIME ->
+// Two build modes, one source:
+//   * inside the reference tree (Eigen and the calib/ headers are on the include path) the option,
+//     result and camera-model types are the reference's own;
+//   * stand-alone (this repository's image has neither Eigen nor Ceres) the same names come from
+//     calib_b200_mini.hpp, and the linear-stage entry points that the reference defines in
+//     calib_estimation_linear (estimate_homography, estimate_planar_pose, estimate_intrinsics,
+//     fit_plane_ransac) are provided here under their reference names as well.  This is the mode the
+//     C++ host tests of this repository compile (tests/cpp/reference_tests.cpp).
+// It contains no arithmetic of the hot path: packing into SoA/CSR, the C call, unpacking, and the
+// error mapping (CAL_ERR_INVALID_ARGUMENT -> std::invalid_argument, CAL_ERR_RUNTIME ->
 // std::runtime_error, anything else -> std::runtime_error).
 #pragma once
-#if __has_include(<Eigen/Core>) && __has_include("calib/estimation/optim/bundle.h")
 
+#include <array>
+#include <optional>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
+#if __has_include(<Eigen/Core>) && __has_include("calib/estimation/optim/bundle.h")
+#define CALIB_B200_REFERENCE_TREE 1
 #include "calib/estimation/linear/handeye.h"
 #include "calib/estimation/linear/homography.h"
 #include "calib/estimation/linear/planefit.h"
@@ -31,7 +38,18 @@
 #include "calib/estimation/optim/handeye.h"
 #include "calib/estimation/optim/intrinsics.h"
 #include "calib/models/scheimpflug.h"
+#else
+#define CALIB_B200_REFERENCE_TREE 0
+#include "calib_b200_mini.hpp"
+#endif
 #include "calib_b200.h"
+
+// default arguments live on the reference's own declarations inside its tree
+#if CALIB_B200_REFERENCE_TREE
+#define CALIB_B200_DEFAULT(x)
+#else
+#define CALIB_B200_DEFAULT(x) = x
+#endif
 
 namespace calib::b200 {
 
@@ -40,6 +58,19 @@ inline void check(cal_status s) {
     const std::string msg = cal_last_error();
     if (s == CAL_ERR_INVALID_ARGUMENT) throw std::invalid_argument(msg);
     throw std::runtime_error(msg);
+}
+
+// row-major C buffers -> the matrix types of the result structs (element-wise: no Eigen::Map, so the same
+// lines compile against Eigen and against calib_b200_mini.hpp)
+inline Eigen::Matrix3d mat3_from_rowmajor(const double* p) {
+    Eigen::Matrix3d m;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m(i, j) = p[3 * i + j];
+    return m;
+}
+inline Eigen::MatrixXd dense_from_rowmajor(const double* p, Eigen::Index n) {
+    Eigen::MatrixXd m(n, n);
+    for (Eigen::Index i = 0; i < n; ++i) for (Eigen::Index j = 0; j < n; ++j) m(i, j) = p[i * n + j];
+    return m;
 }
 
 template <class CameraT> constexpr int model_of() {
@@ -58,7 +89,7 @@ inline Eigen::Isometry3d pop_pose(const double* q, const double* t) {
     qq.normalize();
     Eigen::Isometry3d T = Eigen::Isometry3d::Identity();
     T.linear() = qq.toRotationMatrix();
-    T.translation() << t[0], t[1], t[2];
+    T.translation() = Eigen::Vector3d(t[0], t[1], t[2]);
     return T;
 }
 
@@ -95,8 +126,7 @@ inline void run(const cal_problem_desc& d, const OptimOptions& core, std::vector
     check(s);
     out.success = r.success != 0; out.final_cost = r.final_cost; out.report = r.report;
     if (r.covariance_ok) {
-        const auto n = static_cast<Eigen::Index>(x.size());
-        out.covariance = Eigen::Map<const Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor>>(cov.data(), n, n);
+        out.covariance = dense_from_rowmajor(cov.data(), static_cast<Eigen::Index>(x.size()));
     }
 }
 
@@ -107,8 +137,12 @@ namespace calib {
 template <camera_model CameraT>
 auto optimize_bundle(const std::vector<BundleObservation>& observations, const std::vector<CameraT>& initial_cameras,
                      const std::vector<Eigen::Isometry3d>& init_g_se3_c, const Eigen::Isometry3d& init_b_se3_t,
-                     const BundleOptions& opts) -> BundleResult<CameraT> {
+                     const BundleOptions& opts CALIB_B200_DEFAULT({})) -> BundleResult<CameraT> {
     constexpr int P = CameraTraits<CameraT>::param_count;
+    if (initial_cameras.empty()) throw std::invalid_argument("No camera intrinsics provided");  // bundle.cpp:139-141
+    if (observations.empty()) throw std::invalid_argument("No observations provided");            // bundle.cpp:142-144
+    if (init_g_se3_c.size() != initial_cameras.size())
+        throw std::invalid_argument("optimize_bundle: one initial hand-eye pose per camera required");
     b200::Soa s;
     for (const auto& ob : observations) {
         s.add(ob.view, static_cast<int>(ob.camera_index), -1);
@@ -143,9 +177,13 @@ auto optimize_bundle(const std::vector<BundleObservation>& observations, const s
 
 template <camera_model CameraT>
 auto optimize_intrinsics(const std::vector<PlanarView>& views, const CameraT& init_camera,
-                         std::vector<Eigen::Isometry3d> init_c_se3_t, const IntrinsicsOptimOptions& opts)
+                         std::vector<Eigen::Isometry3d> init_c_se3_t, const IntrinsicsOptimOptions& opts CALIB_B200_DEFAULT({}))
     -> IntrinsicsOptimizationResult<CameraT> {
     constexpr int P = CameraTraits<CameraT>::param_count;
+    if (views.size() < 4)  // validate_input, intrinsics.cpp:92-96 (before the start poses are touched)
+        throw std::invalid_argument("Insufficient views for calibration (at least 4 required).");
+    if (init_c_se3_t.size() != views.size())  // the reference indexes one pose block per view (intrinsics.cpp:68-75)
+        throw std::invalid_argument("optimize_intrinsics: one initial pose per view required");
     b200::Soa s;
     for (size_t v = 0; v < views.size(); ++v) s.add(views[v], 0, static_cast<int>(v));
     cal_problem_desc d{};
@@ -168,7 +206,7 @@ auto optimize_intrinsics(const std::vector<PlanarView>& views, const CameraT& in
 template <camera_model CameraT>
 auto optimize_extrinsics(const std::vector<MulticamPlanarView>& views, const std::vector<CameraT>& init_cameras,
                          const std::vector<Eigen::Isometry3d>& init_c_se3_r, const std::vector<Eigen::Isometry3d>& init_r_se3_t,
-                         const ExtrinsicOptions& opts) -> ExtrinsicOptimizationResult<CameraT> {
+                         const ExtrinsicOptions& opts CALIB_B200_DEFAULT({})) -> ExtrinsicOptimizationResult<CameraT> {
     constexpr int P = CameraTraits<CameraT>::param_count;
     const size_t nc = init_cameras.size(), nv = views.size();
     if (init_c_se3_r.size() != nc || init_r_se3_t.size() != nv)  // extrinsics.cpp:163-171
@@ -203,7 +241,7 @@ auto optimize_extrinsics(const std::vector<MulticamPlanarView>& views, const std
 
 inline auto optimize_handeye(const std::vector<Eigen::Isometry3d>& base_se3_gripper,
                              const std::vector<Eigen::Isometry3d>& camera_se3_target,
-                             const Eigen::Isometry3d& init_gripper_se3_ref, const OptimOptions& options) -> HandeyeResult {
+                             const Eigen::Isometry3d& init_gripper_se3_ref, const OptimOptions& options CALIB_B200_DEFAULT({})) -> HandeyeResult {
     // build_all_pairs (linear/handeyedlt.cpp:51-81) runs on the device: the n (n - 1) / 2 motion pairs are
     // formed on the fly in every pass (0.5 deg / reject-parallel / 1e-3 are optimize_handeye's own arguments,
     // handeye.cpp:63-64 with the defaults of linear/handeye.h)
@@ -226,19 +264,22 @@ inline auto optimize_handeye(const std::vector<Eigen::Isometry3d>& base_se3_grip
     b200::check(s);
     HandeyeResult result;
     result.core.success = r.success != 0; result.core.final_cost = r.final_cost; result.core.report = r.report;
-    if (r.covariance_ok) result.core.covariance = Eigen::Map<const Eigen::Matrix<double, 7, 7, Eigen::RowMajor>>(cov);
+    if (r.covariance_ok) result.core.covariance = b200::dense_from_rowmajor(cov, 7);
     result.g_se3_c = b200::pop_pose(x, x + 4);
     return result;
 }
 
-// estimate_intrinsics(views, opts) without homography RANSAC (linear/intrinsics.h:58-59,
-// src/estimation/linear/intrinsicsdlt.cpp:101-145): all views in one batched call.
+// estimate_intrinsics(views, opts) (linear/intrinsics.h:58-59, src/estimation/linear/intrinsicsdlt.cpp:101-145):
+// all views in one batched call; with opts.homography_ransac every view's homography comes from the batched
+// RANSAC kernel (intrinsicsdlt.cpp:50-64), else from the DLT over all its points.
 inline auto estimate_intrinsics_b200(const std::vector<PlanarView>& views, const IntrinsicsEstimOptions& opts) -> IntrinsicsEstimateResult {
     IntrinsicsEstimateResult result;
     if (views.empty()) return result;
     std::vector<int64_t> off(views.size() + 1, 0);
     for (size_t k = 0; k < views.size(); ++k) off[k + 1] = off[k] + static_cast<int64_t>(views[k].size());
-    std::vector<double> x(off.back()), y(off.back()), u(off.back()), v(off.back());
+    const auto n_obs = static_cast<size_t>(off.back());
+    if (n_obs == 0) return result;  // no view has a homography: Zhang fails (intrinsicsdlt.cpp:116-120)
+    std::vector<double> x(n_obs), y(n_obs), u(n_obs), v(n_obs);
     for (size_t k = 0; k < views.size(); ++k)
         for (size_t i = 0; i < views[k].size(); ++i) {
             const auto o = static_cast<size_t>(off[k]) + i;
@@ -251,10 +292,18 @@ inline auto estimate_intrinsics_b200(const std::vector<PlanarView>& views, const
         so.use_bounds = 1; so.fx_min = b.fx_min; so.fx_max = b.fx_max; so.fy_min = b.fy_min; so.fy_max = b.fy_max;
         so.cx_min = b.cx_min; so.cx_max = b.cx_max; so.cy_min = b.cy_min; so.cy_max = b.cy_max; so.skew_min = b.skew_min; so.skew_max = b.skew_max;
     }
+    cal_ransac_options ro{};
+    std::vector<uint8_t> mask;
+    if (opts.homography_ransac) {
+        const auto& r = *opts.homography_ransac;
+        ro = cal_ransac_options{r.max_iters, r.min_inliers, r.thresh, r.confidence, r.seed, r.refit_on_inliers ? 1 : 0, 0};
+        mask.resize(n_obs);
+    }
     double k5[5]; int32_t cam_ok = 0;
     std::vector<double> H(9 * views.size()), rms(views.size()), poses(12 * views.size());
-    b200::check(cal_seed_intrinsics(static_cast<int64_t>(views.size()), off.data(), cam.data(), x.data(), y.data(), u.data(), v.data(), 1, &so, 0,
-                                    k5, &cam_ok, ok.data(), H.data(), rms.data(), poses.data()));
+    b200::check(cal_seed_intrinsics_ransac(static_cast<int64_t>(views.size()), off.data(), cam.data(), x.data(), y.data(), u.data(), v.data(), 1,
+                                           &so, opts.homography_ransac ? &ro : nullptr, 0, k5, &cam_ok, ok.data(), H.data(), rms.data(),
+                                           poses.data(), mask.empty() ? nullptr : mask.data()));
     if (!cam_ok) return result;
     result.success = true;
     result.kmtx = CameraMatrix{k5[0], k5[1], k5[2], k5[3], k5[4]};
@@ -264,21 +313,43 @@ inline auto estimate_intrinsics_b200(const std::vector<PlanarView>& views, const
         ved.view_index = k;
         ved.forward_rms_px = rms[k];
         ved.homography.success = true;
-        ved.homography.hmtx = Eigen::Map<const Eigen::Matrix<double, 3, 3, Eigen::RowMajor>>(&H[9 * k]);
+        ved.homography.hmtx = b200::mat3_from_rowmajor(&H[9 * k]);
         ved.homography.symmetric_rms_px = rms[k];
-        ved.homography.inliers.resize(views[k].size());
-        for (size_t i = 0; i < views[k].size(); ++i) ved.homography.inliers[i] = static_cast<int>(i);
-        Eigen::Matrix3d R = Eigen::Map<const Eigen::Matrix<double, 3, 3, Eigen::RowMajor>>(&poses[12 * k]);
-        ved.c_se3_t.linear() = R;
+        for (size_t i = 0; i < views[k].size(); ++i)
+            if (mask.empty() || mask[static_cast<size_t>(off[k]) + i]) ved.homography.inliers.push_back(static_cast<int>(i));
+        ved.c_se3_t.linear() = b200::mat3_from_rowmajor(&poses[12 * k]);
         ved.c_se3_t.translation() = Eigen::Vector3d(poses[12 * k + 9], poses[12 * k + 10], poses[12 * k + 11]);
         result.views.push_back(std::move(ved));
     }
     return result;
 }
 
+// estimate_planar_pose(view, CameraMatrix) (src/estimation/linear/planarpose_linear.cpp:54-76) for many views in one call
+inline auto estimate_planar_poses_b200(const std::vector<PlanarView>& views, const CameraMatrix& k) -> std::vector<Eigen::Isometry3d> {
+    std::vector<Eigen::Isometry3d> out(views.size(), Eigen::Isometry3d::Identity());
+    std::vector<int64_t> off(views.size() + 1, 0);
+    for (size_t i = 0; i < views.size(); ++i) off[i + 1] = off[i] + static_cast<int64_t>(views[i].size());
+    const auto n_obs = static_cast<size_t>(off.back());
+    if (n_obs == 0) return out;  // fewer than 4 points: identity (planarpose_linear.cpp:55-57)
+    std::vector<double> x(n_obs), y(n_obs), u(n_obs), v(n_obs);
+    for (size_t i = 0, o = 0; i < views.size(); ++i)
+        for (const auto& ob : views[i]) { x[o] = ob.object_xy.x(); y[o] = ob.object_xy.y(); u[o] = ob.image_uv.x(); v[o] = ob.image_uv.y(); ++o; }
+    std::vector<int32_t> cam(views.size(), 0);
+    const double k5[5] = {k.fx, k.fy, k.cx, k.cy, k.skew};
+    std::vector<double> poses(12 * views.size());
+    b200::check(cal_seed_planar_poses(static_cast<int64_t>(views.size()), off.data(), cam.data(), x.data(), y.data(), u.data(), v.data(), 1, k5, 0,
+                                      poses.data(), nullptr));
+    for (size_t i = 0; i < views.size(); ++i) {
+        out[i].linear() = b200::mat3_from_rowmajor(&poses[12 * i]);
+        out[i].translation() = Eigen::Vector3d(poses[12 * i + 9], poses[12 * i + 10], poses[12 * i + 11]);
+    }
+    return out;
+}
+
 // RANSAC branch of estimate_homography (optim/homography.cpp:45-73); the plain DLT branch stays on the host.
 inline auto estimate_homography_ransac_b200(const PlanarView& data, const RansacOptions& ro) -> HomographyResult {
     const auto n = static_cast<int32_t>(data.size());
+    if (n < 4) return HomographyResult{};  // ransac<> returns an unsuccessful result below k_min_samples (common/ransac.h:126-128)
     std::vector<double> x(n), y(n), u(n), v(n);
     for (int i = 0; i < n; ++i) { x[i] = data[i].object_xy.x(); y[i] = data[i].object_xy.y(); u[i] = data[i].image_uv.x(); v[i] = data[i].image_uv.y(); }
     const cal_ransac_options co{ro.max_iters, ro.min_inliers, ro.thresh, ro.confidence, ro.seed, ro.refit_on_inliers ? 1 : 0, 0};
@@ -287,7 +358,7 @@ inline auto estimate_homography_ransac_b200(const PlanarView& data, const Ransac
     HomographyResult out;
     out.success = r.success != 0;
     if (out.success) {
-        out.hmtx = Eigen::Map<const Eigen::Matrix<double, 3, 3, Eigen::RowMajor>>(r.hmtx);
+        out.hmtx = b200::mat3_from_rowmajor(r.hmtx);
         for (int i = 0; i < n; ++i) if (mask[i]) out.inliers.push_back(i);
         out.symmetric_rms_px = r.symmetric_rms_px;
     }
@@ -325,5 +396,45 @@ inline auto fit_plane_ransac_b200(const std::vector<Eigen::Vector3d>& pts, const
     return fit_plane_ransac_b200(std::vector<std::vector<Eigen::Vector3d>>{pts}, ro).front();
 }
 
-}  // namespace calib
+#if !CALIB_B200_REFERENCE_TREE
+// Stand-alone mode only: the linear-stage entry points under their reference names (inside the reference tree
+// these are defined by calib_estimation_linear / optim/homography.cpp, whose bodies call the *_b200 functions above).
+
+// estimate_homography (include/calib/estimation/linear/homography.h:22-24, src/estimation/optim/homography.cpp:62-73)
+inline auto estimate_homography(const PlanarView& data, std::optional<RansacOptions> ransac_opts = std::nullopt) -> HomographyResult {
+    if (ransac_opts.has_value()) return estimate_homography_ransac_b200(data, *ransac_opts);
+    // estimate_homography_dlt (homography.cpp:30-43): HomographyEstimator::fit over all points = the per-view DLT of the seeding kernel
+    HomographyResult out;
+    const auto n = static_cast<int64_t>(data.size());
+    if (n < 4) return out;  // HomographyEstimator::fit -> nullopt (homographyestimator.cpp:126-128)
+    std::vector<double> x(n), y(n), u(n), v(n);
+    for (int64_t i = 0; i < n; ++i) { x[i] = data[i].object_xy.x(); y[i] = data[i].object_xy.y(); u[i] = data[i].image_uv.x(); v[i] = data[i].image_uv.y(); }
+    const int64_t off[2] = {0, n};
+    const int32_t cam = 0;
+    double k5[5], H[9], rms = 0.0;
+    int32_t cam_ok = 0, ok = 0;
+    b200::check(cal_seed_intrinsics(1, off, &cam, x.data(), y.data(), u.data(), v.data(), 1, nullptr, 0, k5, &cam_ok, &ok, H, &rms, nullptr));
+    if (!ok) return out;
+    out.success = true;
+    out.hmtx = b200::mat3_from_rowmajor(H);
+    out.symmetric_rms_px = rms;
+    out.inliers.resize(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) out.inliers[static_cast<size_t>(i)] = static_cast<int>(i);
+    return out;
+}
+// estimate_planar_pose (include/calib/estimation/linear/planarpose.h:33, src/estimation/linear/planarpose_linear.cpp:54-76)
+inline auto estimate_planar_pose(PlanarView view, const CameraMatrix& intrinsics) -> Eigen::Isometry3d {
+    if (view.size() < 4) return Eigen::Isometry3d::Identity();
+    return estimate_planar_poses_b200(std::vector<PlanarView>{std::move(view)}, intrinsics).front();
+}
+// estimate_intrinsics (include/calib/estimation/linear/intrinsics.h:58-59)
+inline auto estimate_intrinsics(const std::vector<PlanarView>& views, const IntrinsicsEstimOptions& opts = {}) -> IntrinsicsEstimateResult {
+    return estimate_intrinsics_b200(views, opts);
+}
+// fit_plane_ransac (include/calib/estimation/linear/planefit.h:23-24)
+inline auto fit_plane_ransac(const std::vector<Eigen::Vector3d>& pts, const RansacOptions& opts = {}) -> PlaneRansacResult {
+    return fit_plane_ransac_b200(pts, opts);
+}
 #endif
+
+}  // namespace calib

@@ -1,0 +1,45 @@
+"""The C++ host layer (include/calib_b200_adapter.hpp, stand-alone mode) on the CPU: it compiles as C++20 with
+-Wall -Wextra -Werror, the reference's unit tests re-expressed on it (tests/cpp/reference_tests.cpp) pass when the
+C ABI underneath is answered by the CPU stand-in (packing, block order, unpacking, error mapping), and against the
+REAL library its argument validation maps to the reference's exception types while every computing call fails
+loudly without a device.  The parity run of the same binary is tests/test_gpu_zzz_cpp_host.py."""
+import re
+
+import cpp_host_build as B
+
+VALIDATION = ["InsufficientViewsThrow", "InputValidation", "MismatchedPoseVectorsThrow", "InsufficientPoints", "TooFewPointsFail"]
+
+
+def _summary(out):
+    m = re.search(r"(\d+) tests ran, (\d+) failed", out.stdout)
+    assert m, out.stdout + out.stderr
+    return int(m.group(1)), int(m.group(2))
+
+
+def test_reference_unit_tests_pass_on_the_adapter_over_the_cpu_standin():
+    exe, env = B.build_standin()
+    out = B.run(exe, env)
+    ran, failed = _summary(out)
+    assert out.returncode == 0 and failed == 0, out.stdout[-4000:]
+    assert ran >= 29
+
+
+def test_argument_validation_through_the_real_library_without_a_device():
+    exe, env = B.build_real()
+    out = B.run(exe, env, *VALIDATION)
+    ran, failed = _summary(out)
+    assert out.returncode == 0 and failed == 0 and ran == len(VALIDATION), out.stdout[-4000:]
+
+
+def test_computing_calls_fail_loudly_without_a_device():
+    from calibration_b200 import capi
+    if capi.device_count() > 0:
+        import pytest
+        pytest.skip("a CUDA device is present")
+    exe, env = B.build_real()
+    for name in ("OptimizeBundle.SingleCameraHandEye", "OptimizeIntrinsics.RecoversSkew", "CeresAXXBRefine.ImprovesOverInitializer",
+                 "HomographyTest.RansacRecoversHomographyWithOutliers", "PlaneFit.RansacRejectsOutliers",
+                 "EstimateIntrinsics.RecoversCameraMatrix", "PlanarPoseTest.DLTEstimation"):
+        out = B.run(exe, env, name)
+        assert out.returncode != 0, name
+        assert "no CUDA device: calib_b200 has no CPU fallback" in out.stdout, out.stdout[-2000:]
