@@ -35,6 +35,22 @@ cal_status fail(cal_status s, const std::string& m) { g_err = m; return s; }
         if (_e != cudaSuccess) return fail(CAL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
+// set-up temporaries of cal_refine_create: released on every exit, also the CUDA_TRY ones
+struct ScopedStream {
+    cudaStream_t s = nullptr;
+    ~ScopedStream() { if (s) cudaStreamDestroy(s); }   // pending work still completes (CUDA defers the release)
+};
+struct ScopedEvent {
+    cudaEvent_t e = nullptr;
+    ~ScopedEvent() { if (e) cudaEventDestroy(e); }
+};
+template <class T> struct ScopedAsyncBuf {   // cudaMallocAsync'ed staging buffer, freed in stream order
+    T* p = nullptr;
+    cudaStream_t st = nullptr;               // stream the failure-path free is ordered on
+    ~ScopedAsyncBuf() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t free_on(cudaStream_t s) { cudaError_t e = p ? cudaFreeAsync(p, s) : cudaSuccess; p = nullptr; return e; }
+};
+
 template <class T> cudaError_t dev_alloc(T** p, size_t n) { return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)); }
 template <class T> cudaError_t upload(T* dst, const std::vector<T>& src, cudaStream_t st) {
     if (src.empty()) return cudaSuccess;
@@ -182,10 +198,15 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         cudaMemPool_t pool; uint64_t thr = UINT64_MAX;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
-    double* raw = nullptr;
-    cudaStream_t cst = nullptr;
-    CUDA_TRY(cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking));
-    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&raw), sizeof(double) * 4 * (size_t)d.n_obs, cst));
+    ScopedStream cst_guard, us_guard;
+    ScopedEvent copied_guard;
+    ScopedAsyncBuf<double> raw_guard, raw_bTg_guard;
+    ScopedAsyncBuf<int64_t> dsrc_guard;
+    CUDA_TRY(cudaStreamCreateWithFlags(&cst_guard.s, cudaStreamNonBlocking));
+    const cudaStream_t cst = cst_guard.s;
+    raw_guard.st = cst; raw_bTg_guard.st = h.st; dsrc_guard.st = h.st;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&raw_guard.p), sizeof(double) * 4 * (size_t)d.n_obs, cst));
+    double* const raw = raw_guard.p;
     {
         const size_t nb = (size_t)d.n_obs * sizeof(double);
         // cudaMemcpyDefault: the observation arrays may be host memory or already on a device
@@ -291,7 +312,7 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     CUDA_TRY(upload(L.seg_len, seg_len, h.st)); CUDA_TRY(upload(L.seg_blk, seg_blk, h.st)); CUDA_TRY(upload(L.seg_cam, seg_cam, h.st));
     CUDA_TRY(upload(L.blk_cam, bcam, h.st)); CUDA_TRY(upload(L.blk_view, bview, h.st)); CUDA_TRY(upload(L.blk_orig, borig, h.st));
     CUDA_TRY(upload(L.blk_seg_off, blk_seg_off, h.st)); CUDA_TRY(upload(L.blk_vfree, blk_vfree, h.st));
-    double* raw_bTg = nullptr;
+    double*& raw_bTg = raw_bTg_guard.p;
     if (d.kind == CAL_KIND_BUNDLE) {  // robot poses: upload AoS, permute + transpose on the device
         CUDA_TRY(h.alloc(&L.blk_bTg, (size_t)12 * nblk));
         CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&raw_bTg), sizeof(double) * 12 * (size_t)d.n_blocks, h.st));
@@ -301,18 +322,19 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     // one-time repack into the tile-transposed layout: queued behind the raw copy ON THE DEVICE (event), the
     // host does not wait here — the rest of the set-up below (reduction chunk tables, buffer clears, view CSR)
     // runs on a second stream and overlaps the H2D transfer; both streams are joined once at the end
-    cudaStream_t us = nullptr;
-    CUDA_TRY(cudaStreamCreateWithFlags(&us, cudaStreamNonBlocking));
-    cudaEvent_t copied; CUDA_TRY(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&us_guard.s, cudaStreamNonBlocking));
+    const cudaStream_t us = us_guard.s;
+    CUDA_TRY(cudaEventCreateWithFlags(&copied_guard.e, cudaEventDisableTiming));
+    const cudaEvent_t copied = copied_guard.e;
     {
-        int64_t* dsrc;
-        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&dsrc), sizeof(int64_t) * std::max<size_t>(nseg, 1), h.st));
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&dsrc_guard.p), sizeof(int64_t) * std::max<size_t>(nseg, 1), h.st));
+        int64_t* const dsrc = dsrc_guard.p;
         CUDA_TRY(upload(dsrc, seg_src, h.st));
         CUDA_TRY(cudaEventRecord(copied, cst));
         CUDA_TRY(cudaStreamWaitEvent(h.st, copied, 0));
         launch_repack(L, raw, raw + d.n_obs, raw + 2 * d.n_obs, raw + 3 * d.n_obs, dsrc, h.st);
-        CUDA_TRY(cudaFreeAsync(raw, h.st)); CUDA_TRY(cudaFreeAsync(dsrc, h.st));
-        if (raw_bTg) CUDA_TRY(cudaFreeAsync(raw_bTg, h.st));
+        CUDA_TRY(raw_guard.free_on(h.st)); CUDA_TRY(dsrc_guard.free_on(h.st));
+        CUDA_TRY(raw_bTg_guard.free_on(h.st));
         lap("repack queued");
     }
     // ---- evaluation buffers ----
@@ -411,8 +433,7 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     CUDA_TRY(cudaStreamSynchronize(us));
     CUDA_TRY(cudaStreamSynchronize(h.st));
     CUDA_TRY(cudaGetLastError());
-    cudaEventDestroy(copied); cudaStreamDestroy(us); cudaStreamDestroy(cst);
-    lap("done");
+    lap("done");   // the scoped streams / event are released on return
     if (trace) std::fprintf(stderr, "[calib_b200] create: arena %.1f MB reserved, %.1f MB used, %zu extra allocations\n",
                             h.arena_size / 1048576.0, h.arena_used / 1048576.0, h.allocs.size());
     *out = hp.release();
