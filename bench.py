@@ -296,7 +296,78 @@ def _run_b200(args, rank, world, local_rank):
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, steps=3)
+    if world == 1 and not args.no_board_probe:
+        stage("shared-board probe (child process)", rank)
+        out["e2e"]["shared_board"] = shared_board_probe(args)
     return out
+
+
+def run_board_probe(args):
+    """Child process of the N = 1 run (`--probe-shared-board`): the same end-to-end solve with the observations in the
+    shared-board form of cal_problem_desc (one board of 88 points + u, v per observation: 16 instead of 32 bytes per
+    observation over PCIe), next to the per-observation form in the same process, and whether the two solves are
+    bitwise identical.  A separate process so that nothing here can disturb the main record."""
+    import torch
+    from calibration_b200 import abi, capi, synth
+    n_cams, n_poses, _ = WORKLOADS[args.workload]
+    prob, x0, _ = synth.make_bundle(seed=137, n_cams=n_cams, n_poses=n_poses, chunk=CHUNK, chunks=shard_chunks(n_poses, 0, 1), pinned=True,
+                                    optimize_intrinsics=not args.fixed_intrinsics)
+    pb = prob.with_shared_board()
+    opts = abi.OptimOptions.default(compute_covariance=1)
+    n_obs = int(prob.desc.n_obs)
+
+    def solve(p):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h = capi.RefineHandle(p)
+        x, res, cov = h.solve(x0, opts)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        h.close()
+        return dt, x, res, cov
+
+    def one_pass(p):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h = capi.RefineHandle(p)
+        c, g, H = h.eval(x0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        h.close()
+        return dt, c
+
+    solve(prob)                                  # warm-up: context, module load, memory-pool growth
+    t_o, x_o, r_o, cov_o = solve(prob)
+    t_b, x_b, r_b, cov_b = solve(pb)
+    p_o, c_o = one_pass(prob)
+    p_b, c_b = one_pass(pb)
+    same = bool(np.array_equal(x_o, x_b) and np.array_equal(cov_o, cov_b) and r_o.iterations == r_b.iterations
+                and r_o.final_cost == r_b.final_cost and c_o == c_b)
+    n_jac = int(r_b.num_jac_evals)
+    print(json.dumps({
+        "what": "the e2e solve of this record with the observations in the shared-board form (cal_problem_desc.board_n = 88): "
+                "create (H2D of one board + u, v) + LM solve with covariance + destroy; per_observation is the default form timed in the same process",
+        "h2d_bytes": 16 * n_obs + 16 * int(pb.desc.board_n) + 96 * int(pb.desc.n_blocks),
+        "wall_s": t_b, "value": n_obs * n_jac / t_b, "unit": "observations/s", "jacobian_passes": n_jac, "converged": bool(r_b.success),
+        "upload_plus_one_pass_wall_s": p_b, "upload_plus_one_pass_value": n_obs / p_b,
+        "per_observation": {"wall_s": t_o, "value": n_obs * int(r_o.num_jac_evals) / t_o, "upload_plus_one_pass_wall_s": p_o},
+        "bitwise_identical_to_per_observation_form": same}), flush=True)
+
+
+def shared_board_probe(args):
+    """Runs run_board_probe in a child process and returns its record (or why there is none)."""
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--probe-shared-board", "--workload", args.workload]
+    if args.fixed_intrinsics:
+        cmd.append("--fixed-intrinsics")
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=150)
+        lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        if p.returncode != 0 or not lines:
+            return {"error": f"exit {p.returncode}: {p.stderr.strip()[-300:]}"}
+        return json.loads(lines[-1])
+    except Exception as e:  # noqa: BLE001 - a probe: its failure is recorded, never raised
+        return {"error": repr(e)}
 
 
 def cpu_sample_problem(args):
@@ -364,6 +435,8 @@ def main():
     ap.add_argument("--no-peer-allreduce", action="store_true", help="use NCCL for the per-pass all-reduce instead of the NVLink peer-memory kernel")
     ap.add_argument("--max-seconds", type=float, default=420.0, help="watchdog: abort (exit 3) instead of hanging past this many seconds")
     ap.add_argument("--cpu-sample-div", type=int, default=64)
+    ap.add_argument("--no-board-probe", action="store_true", help="skip the shared-board e2e probe (N = 1 only; runs in a child process)")
+    ap.add_argument("--probe-shared-board", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--k1-flop-per-obs", type=float, default=560.0,
                     help="FP64 flop per observation of K1 from the committed ncu capture (profiles/r1_k1_fused_ncu_full_35M.csv: "
                          "237 DFMA + 44 DMUL + 42 DADD per observation, epilogue included)")
@@ -372,7 +445,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if args.impl == "reference":
+    if args.probe_shared_board:
+        run_board_probe(args)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_b200(args, rank, world, local_rank)

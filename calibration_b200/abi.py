@@ -42,6 +42,10 @@ class ProblemDesc(C.Structure):
         ("optimize_hand_eye", C.c_int32),
         ("view_base", C.c_int32),
         ("huber_delta", C.c_double),
+        ("board_x", c_double_p),
+        ("board_y", c_double_p),
+        ("board_n", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -206,6 +210,27 @@ class Problem:
         d.optimize_hand_eye = int(optimize_hand_eye)
         d.huber_delta = float(huber_delta)
         self.desc = d
+
+    def with_shared_board(self):
+        """The same problem in the shared-board form of cal_problem_desc (board_n > 0): every residual block must
+        observe the same object points in the same order; obj_x / obj_y are then NULL in the descriptor and only
+        one board crosses PCIe.  Raises ValueError when the views do not share one board."""
+        import copy
+        off = self.block_offset
+        n = int(off[1] - off[0])
+        if not np.all(np.diff(off) == n):
+            raise ValueError("views of different sizes cannot share a board")
+        bx, by = self.x[:n].copy(), self.y[:n].copy()
+        if not (np.array_equal(self.x.reshape(-1, n), np.broadcast_to(bx, (len(off) - 1, n)))
+                and np.array_equal(self.y.reshape(-1, n), np.broadcast_to(by, (len(off) - 1, n)))):
+            raise ValueError("object points differ between views")
+        p = copy.copy(self)
+        p.board_x, p.board_y = bx, by
+        d = ProblemDesc.from_buffer_copy(self.desc)
+        d.obj_x, d.obj_y = None, None
+        d.board_x, d.board_y, d.board_n = dptr(bx), dptr(by), n
+        p.desc = d
+        return p
 
     @property
     def intr_size(self):

@@ -140,7 +140,9 @@ cal_status validate(const cal_problem_desc& d) {
     if (d.kind == CAL_KIND_INTRINSICS && d.n_views < 4)
         return fail(CAL_ERR_INVALID_ARGUMENT, "Insufficient views for calibration (at least 4 required).");  // intrinsics.cpp:92-96
     if (d.n_blocks <= 0 || d.n_obs <= 0) return fail(CAL_ERR_INVALID_ARGUMENT, "No observations provided");    // bundle.cpp:142-144
-    if (!d.obj_x || !d.obj_y || !d.img_u || !d.img_v || !d.block_offset || !d.block_cam)
+    if (d.board_n < 0) return fail(CAL_ERR_INVALID_ARGUMENT, "board_n < 0");
+    const bool board = d.board_n > 0;   // shared-board form: obj_x / obj_y come from one board of board_n points
+    if ((board ? (!d.board_x || !d.board_y) : (!d.obj_x || !d.obj_y)) || !d.img_u || !d.img_v || !d.block_offset || !d.block_cam)
         return fail(CAL_ERR_INVALID_ARGUMENT, "null observation arrays");
     if (d.kind == CAL_KIND_INTRINSICS && (d.n_cams != 1 || d.n_blocks != d.n_views))
         return fail(CAL_ERR_INVALID_ARGUMENT, "intrinsics: one camera and one residual block per view expected");
@@ -150,6 +152,8 @@ cal_status validate(const cal_problem_desc& d) {
     for (int64_t b = 0; b < d.n_blocks; ++b) {
         // *Residual::create throws on an empty view (intrinsicresidual.h:38-40, bundleresidual.h:59-61)
         if (d.block_offset[b + 1] <= d.block_offset[b]) return fail(CAL_ERR_INVALID_ARGUMENT, "No observations provided");
+        if (board && d.block_offset[b + 1] - d.block_offset[b] != d.board_n)
+            return fail(CAL_ERR_INVALID_ARGUMENT, "shared-board form: every residual block must hold exactly board_n observations");
         if (d.block_cam[b] < 0 || d.block_cam[b] >= d.n_cams) return fail(CAL_ERR_INVALID_ARGUMENT, "block_cam out of range");
         if (d.kind == CAL_KIND_EXTRINSICS && (d.block_view[b] < 0 || d.block_view[b] >= d.n_views))
             return fail(CAL_ERR_INVALID_ARGUMENT, "Incompatible pose vector sizes for joint optimization");  // extrinsics.cpp:163-171
@@ -205,15 +209,19 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     CUDA_TRY(cudaStreamCreateWithFlags(&cst_guard.s, cudaStreamNonBlocking));
     const cudaStream_t cst = cst_guard.s;
     raw_guard.st = cst; raw_bTg_guard.st = h.st; dsrc_guard.st = h.st;
-    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&raw_guard.p), sizeof(double) * 4 * (size_t)d.n_obs, cst));
+    // staging buffer: [obj_x | obj_y | img_u | img_v], n_obs each; in the shared-board form the two object
+    // arrays shrink to the board_n points of the one board (half the PCIe traffic)
+    const size_t n_objpts = d.board_n > 0 ? (size_t)d.board_n : (size_t)d.n_obs;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&raw_guard.p), sizeof(double) * (2 * n_objpts + 2 * (size_t)d.n_obs), cst));
     double* const raw = raw_guard.p;
+    double* const raw_x = raw, *const raw_y = raw + n_objpts, *const raw_u = raw + 2 * n_objpts, *const raw_v = raw_u + d.n_obs;
     {
-        const size_t nb = (size_t)d.n_obs * sizeof(double);
+        const size_t nb = (size_t)d.n_obs * sizeof(double), nbo = n_objpts * sizeof(double);
         // cudaMemcpyDefault: the observation arrays may be host memory or already on a device
-        CUDA_TRY(cudaMemcpyAsync(raw, d.obj_x, nb, cudaMemcpyDefault, cst));
-        CUDA_TRY(cudaMemcpyAsync(raw + d.n_obs, d.obj_y, nb, cudaMemcpyDefault, cst));
-        CUDA_TRY(cudaMemcpyAsync(raw + 2 * d.n_obs, d.img_u, nb, cudaMemcpyDefault, cst));
-        CUDA_TRY(cudaMemcpyAsync(raw + 3 * d.n_obs, d.img_v, nb, cudaMemcpyDefault, cst));
+        CUDA_TRY(cudaMemcpyAsync(raw_x, d.board_n > 0 ? d.board_x : d.obj_x, nbo, cudaMemcpyDefault, cst));
+        CUDA_TRY(cudaMemcpyAsync(raw_y, d.board_n > 0 ? d.board_y : d.obj_y, nbo, cudaMemcpyDefault, cst));
+        CUDA_TRY(cudaMemcpyAsync(raw_u, d.img_u, nb, cudaMemcpyDefault, cst));
+        CUDA_TRY(cudaMemcpyAsync(raw_v, d.img_v, nb, cudaMemcpyDefault, cst));
     }
     lap("copies issued");
     // ---- device block order: by camera (counting sort, stable), camera groups padded to 32 ----
@@ -332,7 +340,7 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         CUDA_TRY(upload(dsrc, seg_src, h.st));
         CUDA_TRY(cudaEventRecord(copied, cst));
         CUDA_TRY(cudaStreamWaitEvent(h.st, copied, 0));
-        launch_repack(L, raw, raw + d.n_obs, raw + 2 * d.n_obs, raw + 3 * d.n_obs, dsrc, h.st);
+        launch_repack(L, raw_x, raw_y, raw_u, raw_v, dsrc, d.board_n, h.st);
         CUDA_TRY(raw_guard.free_on(h.st)); CUDA_TRY(dsrc_guard.free_on(h.st));
         CUDA_TRY(raw_bTg_guard.free_on(h.st));
         lap("repack queued");

@@ -33,9 +33,9 @@ namespace calk {
 // layout
 // ---------------------------------------------------------------------------
 void launch_repack(const DevLayout& L, const double* sx, const double* sy, const double* su, const double* sv,
-                   const int64_t* seg_src, cudaStream_t st) {
+                   const int64_t* seg_src, int board_n, cudaStream_t st) {
     if (L.n_tiles == 0) return;
-    k_repack<<<(unsigned)L.n_tiles, 128, 0, st>>>(L, sx, sy, su, sv, seg_src);
+    k_repack<<<(unsigned)L.n_tiles, 128, 0, st>>>(L, sx, sy, su, sv, seg_src, board_n);
 }
 
 void launch_btg_permute(const DevLayout& L, const double* src, cudaStream_t st) {

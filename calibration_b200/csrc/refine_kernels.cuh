@@ -83,7 +83,7 @@ struct ReduceDesc {
 };
 
 void launch_repack(const DevLayout& L, const double* sx, const double* sy, const double* su, const double* sv,
-                   const int64_t* seg_src, cudaStream_t st);
+                   const int64_t* seg_src, int board_n, cudaStream_t st);
 void launch_btg_permute(const DevLayout& L, const double* src, cudaStream_t st);
 void launch_setup(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st);
 void launch_k1(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st);

@@ -5,21 +5,25 @@
 
 namespace calk {
 
-// layout: SoA observations of the caller -> tile-transposed device layout (refine_kernels.cuh)
+// layout: SoA observations of the caller -> tile-transposed device layout (refine_kernels.cuh).
+// board_n > 0 (shared-board form of cal_problem_desc): sx / sy hold ONE board of board_n points and every block
+// has board_n observations in board order, so observation i reads board point i % board_n; a segment never leaves
+// its block, hence one modulo per thread.
 __global__ void k_repack(DevLayout L, const double* __restrict__ sx, const double* __restrict__ sy,
                          const double* __restrict__ su, const double* __restrict__ sv,
-                         const int64_t* __restrict__ seg_src) {
+                         const int64_t* __restrict__ seg_src, int board_n) {
     const int64_t tile = blockIdx.x;
     const int lane = threadIdx.x & 31;
     const int64_t s = tile * 32 + lane;
     const int len = L.seg_len[s];
     const int depth = L.tile_depth[tile];
     const int64_t src = seg_src[s];
+    const int64_t osrc = board_n > 0 ? src % board_n : src;   // where this segment's object points start
     double* dst = L.obs + L.tile_off[tile] * 128 + lane;
     for (int k = threadIdx.x >> 5; k < depth; k += blockDim.x >> 5) {
         const bool ok = k < len;
-        dst[(int64_t)k * 128 + 0] = ok ? sx[src + k] : 0.0;
-        dst[(int64_t)k * 128 + 32] = ok ? sy[src + k] : 0.0;
+        dst[(int64_t)k * 128 + 0] = ok ? sx[osrc + k] : 0.0;
+        dst[(int64_t)k * 128 + 32] = ok ? sy[osrc + k] : 0.0;
         dst[(int64_t)k * 128 + 64] = ok ? su[src + k] : 0.0;
         dst[(int64_t)k * 128 + 96] = ok ? sv[src + k] : 0.0;
     }

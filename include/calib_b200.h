@@ -78,6 +78,15 @@ typedef struct cal_problem_desc {
     int32_t view_base;            /* multi-GPU shards of the per-view kinds: global index of this shard's view 0
                                      (the gauge fixes GLOBAL view 0, extrinsics.cpp:133-139); 0 otherwise */
     double huber_delta;           /* OptimOptions::huber_delta; <= 0 disables the loss */
+    /* Optional shared-board form (board_n > 0): every view of a calibration observes the same planar target, so
+     * object_xy repeats from view to view.  Every residual block then has exactly board_n observations, in board
+     * order; observation k of a block has object_xy = (board_x[k], board_y[k]); obj_x / obj_y are ignored and may
+     * be NULL.  Halves the bytes that cross PCIe at create (16 instead of 32 per observation); the device layout
+     * and every result are identical to the per-observation form.  board_n = 0: per-observation obj_x / obj_y. */
+    const double* board_x;
+    const double* board_y;
+    int32_t board_n;
+    int32_t reserved;
 } cal_problem_desc;
 
 /* calib::OptimOptions (optim/optimize.h:24-33) */

@@ -93,18 +93,46 @@ inline Eigen::Isometry3d pop_pose(const double* q, const double* t) {
     return T;
 }
 
+// SoA / CSR packing of the caller's views.  Every view of a calibration usually observes the same board, so
+// object_xy repeats from view to view: while that holds only ONE board is kept (the shared-board form of
+// cal_problem_desc, half the bytes to the GPU); the first view that differs expands what was packed so far to
+// the per-observation form.  Exact comparison — a board with one corner missing in some view is not shared.
 struct Soa {
-    std::vector<double> x, y, u, v;
+    std::vector<double> x, y, u, v;   // x, y stay empty while the views share a board
+    std::vector<double> board_x, board_y;
+    bool shared = true;
     std::vector<int64_t> off{0};
     std::vector<int32_t> cam, view;
     std::vector<double> bTg;
+    bool on_board(const PlanarView& pv) const {
+        if (pv.size() != board_x.size()) return false;
+        for (size_t i = 0; i < pv.size(); ++i)
+            if (pv[i].object_xy.x() != board_x[i] || pv[i].object_xy.y() != board_y[i]) return false;
+        return true;
+    }
     void add(const PlanarView& pv, int c, int vw) {
-        for (const auto& ob : pv) { x.push_back(ob.object_xy.x()); y.push_back(ob.object_xy.y()); u.push_back(ob.image_uv.x()); v.push_back(ob.image_uv.y()); }
-        off.push_back(static_cast<int64_t>(x.size())); cam.push_back(c); view.push_back(vw);
+        if (shared) {
+            if (cam.empty()) {
+                for (const auto& ob : pv) { board_x.push_back(ob.object_xy.x()); board_y.push_back(ob.object_xy.y()); }
+            } else if (!on_board(pv)) {
+                shared = false;
+                for (size_t b = 0; b < cam.size(); ++b) { x.insert(x.end(), board_x.begin(), board_x.end()); y.insert(y.end(), board_y.begin(), board_y.end()); }
+            }
+        }
+        for (const auto& ob : pv) {
+            if (!shared) { x.push_back(ob.object_xy.x()); y.push_back(ob.object_xy.y()); }
+            u.push_back(ob.image_uv.x()); v.push_back(ob.image_uv.y());
+        }
+        off.push_back(static_cast<int64_t>(u.size())); cam.push_back(c); view.push_back(vw);
     }
     void fill(cal_problem_desc& d) const {
-        d.n_blocks = static_cast<int64_t>(cam.size()); d.n_obs = static_cast<int64_t>(x.size());
-        d.obj_x = x.data(); d.obj_y = y.data(); d.img_u = u.data(); d.img_v = v.data();
+        d.n_blocks = static_cast<int64_t>(cam.size()); d.n_obs = static_cast<int64_t>(u.size());
+        if (shared && !board_x.empty()) {
+            d.board_x = board_x.data(); d.board_y = board_y.data(); d.board_n = static_cast<int32_t>(board_x.size());
+        } else {
+            d.obj_x = x.data(); d.obj_y = y.data();
+        }
+        d.img_u = u.data(); d.img_v = v.data();
         d.block_offset = off.data(); d.block_cam = cam.data(); d.block_view = view.data();
         d.block_b_se3_g = bTg.empty() ? nullptr : bTg.data();
     }

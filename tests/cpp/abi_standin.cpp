@@ -40,7 +40,9 @@ int simt_seed_planar_poses(int64_t, const int64_t*, const int32_t*, const double
 }
 #endif
 
-static_assert(sizeof(cal_problem_desc) == sizeof(orc_problem_desc));
+#include <cstddef>
+// the oracle's descriptor is the prefix of the product's (which adds the optional shared-board fields)
+static_assert(offsetof(cal_problem_desc, board_x) == sizeof(orc_problem_desc));
 static_assert(sizeof(cal_optim_options) == sizeof(orc_optim_options));
 static_assert(sizeof(cal_optim_result) == sizeof(orc_optim_result));
 static_assert(sizeof(cal_ransac_options) == sizeof(orc_ransac_options));
@@ -77,7 +79,18 @@ cal_status cal_refine_create(const cal_problem_desc* desc, int, cal_refine_handl
     if (d.n_blocks <= 0 || d.n_obs <= 0) return fail(CAL_ERR_INVALID_ARGUMENT, "No observations provided");
     auto* h = new cal_refine_handle;
     h->d = d;
-    h->x.assign(d.obj_x, d.obj_x + d.n_obs); h->y.assign(d.obj_y, d.obj_y + d.n_obs);
+    if (d.board_n > 0) {  // shared-board form: the oracle wants per-observation object points
+        if (!d.board_x || !d.board_y) { delete h; return fail(CAL_ERR_INVALID_ARGUMENT, "null observation arrays"); }
+        for (int64_t b = 0; b < d.n_blocks; ++b) {
+            if (d.block_offset[b + 1] - d.block_offset[b] != d.board_n) {
+                delete h;
+                return fail(CAL_ERR_INVALID_ARGUMENT, "shared-board form: every residual block must hold exactly board_n observations");
+            }
+            h->x.insert(h->x.end(), d.board_x, d.board_x + d.board_n); h->y.insert(h->y.end(), d.board_y, d.board_y + d.board_n);
+        }
+    } else {
+        h->x.assign(d.obj_x, d.obj_x + d.n_obs); h->y.assign(d.obj_y, d.obj_y + d.n_obs);
+    }
     h->u.assign(d.img_u, d.img_u + d.n_obs); h->v.assign(d.img_v, d.img_v + d.n_obs);
     h->off.assign(d.block_offset, d.block_offset + d.n_blocks + 1);
     h->cam.assign(d.block_cam, d.block_cam + d.n_blocks);

@@ -110,6 +110,44 @@ TEST(OptimizeIntrinsics, RecoversSkew) {  // :64-113
     EXPECT_NEAR(k_final.skew, k_gt.skew, 1e-8);
 }
 
+// The adapter keeps ONE board while the views share it (shared-board form of cal_problem_desc) and expands to
+// per-observation object points at the first view that differs: a view with corners missing must give the same
+// calibration as the reference's per-observation packing would.
+TEST(OptimizeIntrinsics, ViewsWithMissingCornersLeaveTheSharedBoardForm) {
+    RNG rng(7);
+    const auto cam_gt = pinhole(1000, 1005, 640, 360);
+    SimulatedHandEye sim{Eigen::Isometry3d::Identity(), Eigen::Translation3d(0.0, 0.0, 2.0) * Eigen::Isometry3d::Identity(), cam_gt};
+    sim.make_sequence(15, rng);
+    sim.make_target_grid(8, 11, 0.02);
+    sim.render_pixels();
+    auto views = views_of(sim);
+    views[4].erase(views[4].begin() + 10, views[4].begin() + 17);  // seven corners undetected in view 4
+    views[9].resize(60);
+    auto guess_cam = cam_gt;
+    guess_cam.kmtx.fx *= 0.97;
+    guess_cam.kmtx.cy -= 4.0;
+    std::vector<Eigen::Isometry3d> init_poses;
+    for (const auto& view : views) init_poses.push_back(estimate_planar_pose(view, guess_cam.kmtx));
+    auto res = optimize_intrinsics(views, guess_cam, init_poses);
+    EXPECT_NEAR(res.camera.kmtx.fx, cam_gt.kmtx.fx, 1e-6);
+    EXPECT_NEAR(res.camera.kmtx.fy, cam_gt.kmtx.fy, 1e-6);
+    EXPECT_NEAR(res.camera.kmtx.cx, cam_gt.kmtx.cx, 1e-6);
+    EXPECT_NEAR(res.camera.kmtx.cy, cam_gt.kmtx.cy, 1e-6);
+    for (size_t v = 0; v < views.size(); ++v) EXPECT_LT((res.c_se3_t[v].translation() - sim.c_se3_t[v].translation()).norm(), 1e-8);
+    // the packing itself: shared while the boards agree, per-observation from the first view that differs
+    b200::Soa s;
+    for (size_t v = 0; v < 4; ++v) s.add(views[v], 0, static_cast<int>(v));
+    EXPECT_TRUE(s.shared && s.x.empty() && s.board_x.size() == 88);
+    s.add(views[4], 0, 4);
+    EXPECT_FALSE(s.shared);
+    EXPECT_EQ(s.x.size(), static_cast<size_t>(4 * 88 + 81));
+    EXPECT_EQ(s.x.size(), s.u.size());
+    for (size_t i = 0; i < s.x.size(); ++i) {
+        const auto& ob = views[i / 88 < 4 ? i / 88 : 4][i / 88 < 4 ? i % 88 : i - 4 * 88];
+        EXPECT_TRUE(s.x[i] == ob.object_xy.x() && s.y[i] == ob.object_xy.y() && s.u[i] == ob.image_uv.x());
+    }
+}
+
 TEST(OptimizeIntrinsics, InsufficientViewsThrow) {  // validate_input, src/estimation/optim/intrinsics.cpp:92-96
     const auto cam = pinhole(1000, 1000, 640, 360);
     std::vector<PlanarView> views(3, PlanarView(12));

@@ -86,7 +86,10 @@ extern "C" int simt_bundle_eval(const cal_problem_desc* dp, const double* x, dou
     L.obs = obs.data(); L.tile_off = tile_off.data(); L.tile_depth = tile_depth.data(); L.seg_len = seg_len.data(); L.seg_blk = seg_blk.data();
     L.seg_cam = blk_cam.data(); L.blk_cam = blk_cam.data(); L.blk_view = blk_view.data(); L.blk_orig = blk_orig.data();
     L.blk_seg_off = blk_seg_off.data(); L.blk_bTg = bTg.data(); L.blk_vfree = blk_vfree.data();
-    simt::launch((unsigned)nt, 128, [&] { k_repack(L, d.obj_x, d.obj_y, d.img_u, d.img_v, seg_src.data()); });
+    // shared-board form of the descriptor (board_n > 0): the object points come from the one board
+    const double* ox = d.board_n > 0 ? d.board_x : d.obj_x;
+    const double* oy = d.board_n > 0 ? d.board_y : d.obj_y;
+    simt::launch((unsigned)nt, 128, [&] { k_repack(L, ox, oy, d.img_u, d.img_v, seg_src.data(), d.board_n); });
     simt::launch((unsigned)((nb * 12 + 255) / 256), 256, [&] { k_btg_permute(L, d.block_b_se3_g); });
     // ---- setup, K1, per-camera sums, host assembly ----
     std::vector<double> cam_sums((size_t)S.n_cams * S.NV, 0.0);

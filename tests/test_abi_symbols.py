@@ -28,7 +28,7 @@ def test_library_builds_and_exports_declared_symbols():
 
 
 def test_struct_layouts_match_header_sizes():
-    assert ctypes.sizeof(abi.ProblemDesc) == 4 * 4 + 2 * 8 + 8 * 8 + 6 * 4 + 8
+    assert ctypes.sizeof(abi.ProblemDesc) == 4 * 4 + 2 * 8 + 8 * 8 + 6 * 4 + 8 + 2 * 8 + 2 * 4
     assert ctypes.sizeof(abi.OptimOptions) == 32
     assert ctypes.sizeof(abi.OptimResult) == 6 * 4 + 2 * 8 + 256
     assert ctypes.sizeof(abi.RansacOptions) == 40
@@ -55,6 +55,26 @@ def test_validation_errors_mirror_reference():
     prob.block_offset[2] = prob.block_offset[1]  # an empty view
     with pytest.raises(ValueError, match="No observations"):
         capi.RefineHandle(prob)
+
+
+def test_shared_board_form_is_validated_before_the_device_is_touched():
+    """cal_problem_desc.board_n > 0: one board instead of object points per observation.  Its argument checks run
+    before the device check, so they are testable here; a valid descriptor then fails with 'no CUDA device'."""
+    prob, x0, _ = synth.make_bundle(n_cams=1, n_poses=8)
+    pb = prob.with_shared_board()
+    if capi.device_count() == 0:
+        with pytest.raises(capi.CalibCudaError):
+            capi.RefineHandle(pb)
+    pb.desc.board_n = 80          # blocks hold 88 observations
+    with pytest.raises(ValueError, match="exactly board_n"):
+        capi.RefineHandle(pb)
+    pb.desc.board_n = 88
+    pb.desc.board_y = None
+    with pytest.raises(ValueError, match="null observation arrays"):
+        capi.RefineHandle(pb)
+    pb.desc.board_n = -1
+    with pytest.raises(ValueError, match="board_n"):
+        capi.RefineHandle(pb)
 
 
 def test_header_is_plain_c_and_a_c_client_links(tmp_path):

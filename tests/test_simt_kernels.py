@@ -345,7 +345,8 @@ K1_SO = os.path.join(ROOT, "tests", "host_emul", "_build", "libk1_simt.so")
 @pytest.fixture(scope="module")
 def k1_simt():
     deps = [K1_SRC, os.path.join(ROOT, "tests", "host_emul", "simt_shim.hpp")] + [
-        os.path.join(CSRC, f) for f in ("k1_kernel.cuh", "k1_roles.hpp", "k1_math.cuh", "refine_kernels.cuh", "refine_setup_kernels.cuh", "refine_model.hpp")]
+        os.path.join(CSRC, f) for f in ("k1_kernel.cuh", "k1_roles.hpp", "k1_math.cuh", "refine_kernels.cuh", "refine_setup_kernels.cuh", "refine_model.hpp")] + [
+        os.path.join(ROOT, "include", "calib_b200.h")]
     if not os.path.exists(K1_SO) or any(os.path.getmtime(d) > os.path.getmtime(K1_SO) for d in deps):
         os.makedirs(os.path.dirname(K1_SO), exist_ok=True)
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -395,6 +396,23 @@ def test_k1_source_matches_oracle(k1_simt, name):
     assert abs(c - c_o) <= 1e-12 * abs(c_o)
     assert np.abs(g - g_o).max() <= 1e-10 * np.abs(g_o).max()
     assert np.abs(H - H_o).max() <= 1e-10 * np.abs(H_o).max()
+
+
+@pytest.mark.parametrize("n_poses", [21, 32])
+def test_repack_kernel_shared_board_form_is_bitwise_the_per_observation_form(k1_simt, n_poses):
+    """cal_problem_desc with board_n > 0 (one board instead of object points per observation): k_repack reads the
+    board modulo the block length and must lay out exactly the same device observations, so the pass over them
+    returns bit-identical cost, gradient and Hessian."""
+    prob, x0, _ = synth.make_bundle(n_cams=2, n_poses=n_poses)
+    pb = prob.with_shared_board()
+    assert pb.desc.board_n == 88 and not pb.desc.obj_x and not pb.desc.obj_y
+    c, g, H, _, _ = k1_eval(k1_simt, prob, x0)
+    cb, gb, Hb, _, _ = k1_eval(k1_simt, pb, x0)
+    assert c == cb and np.array_equal(g, gb) and np.array_equal(H, Hb)
+    # views that do not share a board are refused by the helper (the descriptor form requires equal blocks)
+    prob.x[100] += 1e-9
+    with pytest.raises(ValueError):
+        prob.with_shared_board()
 
 
 def test_k1_source_ragged_blocks(k1_simt):
