@@ -23,6 +23,7 @@
 #pragma once
 
 #include <array>
+#include <cstdlib>
 #include <optional>
 #include <stdexcept>
 #include <string>
@@ -100,7 +101,7 @@ inline Eigen::Isometry3d pop_pose(const double* q, const double* t) {
 struct Soa {
     std::vector<double> x, y, u, v;   // x, y stay empty while the views share a board
     std::vector<double> board_x, board_y;
-    bool shared = true;
+    bool shared = std::getenv("CALIB_B200_PER_OBSERVATION") == nullptr;   // set to force the per-observation form
     std::vector<int64_t> off{0};
     std::vector<int32_t> cam, view;
     std::vector<double> bTg;
@@ -112,7 +113,7 @@ struct Soa {
     }
     void add(const PlanarView& pv, int c, int vw) {
         if (shared) {
-            if (cam.empty()) {
+            if (cam.empty() && board_x.empty()) {
                 for (const auto& ob : pv) { board_x.push_back(ob.object_xy.x()); board_y.push_back(ob.object_xy.y()); }
             } else if (!on_board(pv)) {
                 shared = false;

@@ -7,6 +7,7 @@
 // Linked against libcalib_b200.so this is a parity run on the GPU (tests/test_gpu_zzz_cpp_host.py);
 // linked against tests/cpp/abi_standin.cpp (CPU oracle behind the same C symbols) it checks the
 // adapter's packing, block order, unpacking and error mapping in the CPU suite.  TEST INFRASTRUCTURE.
+#include <cstdlib>
 #include <numeric>
 
 #include "mini_gtest.hpp"
@@ -137,7 +138,8 @@ TEST(OptimizeIntrinsics, ViewsWithMissingCornersLeaveTheSharedBoardForm) {
     // the packing itself: shared while the boards agree, per-observation from the first view that differs
     b200::Soa s;
     for (size_t v = 0; v < 4; ++v) s.add(views[v], 0, static_cast<int>(v));
-    EXPECT_TRUE(s.shared && s.x.empty() && s.board_x.size() == 88);
+    if (std::getenv("CALIB_B200_PER_OBSERVATION") == nullptr) EXPECT_TRUE(s.shared && s.x.empty() && s.board_x.size() == 88);
+    else EXPECT_TRUE(!s.shared && s.x.size() == 4 * 88);   // the switch forces object points per observation from the start
     s.add(views[4], 0, 4);
     EXPECT_FALSE(s.shared);
     EXPECT_EQ(s.x.size(), static_cast<size_t>(4 * 88 + 81));

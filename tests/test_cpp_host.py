@@ -16,12 +16,19 @@ def _summary(out):
     return int(m.group(1)), int(m.group(2))
 
 
-def test_reference_unit_tests_pass_on_the_adapter_over_the_cpu_standin():
+import pytest
+
+
+@pytest.mark.parametrize("per_observation", [False, True])
+def test_reference_unit_tests_pass_on_the_adapter_over_the_cpu_standin(per_observation):
+    """both descriptor forms the adapter can emit: one shared board (default) and object_xy per observation"""
     exe, env = B.build_standin()
+    if per_observation:
+        env = dict(env, CALIB_B200_PER_OBSERVATION="1")
     out = B.run(exe, env)
     ran, failed = _summary(out)
     assert out.returncode == 0 and failed == 0, out.stdout[-4000:]
-    assert ran >= 29
+    assert ran >= 30
 
 
 def test_argument_validation_through_the_real_library_without_a_device():

@@ -12,9 +12,19 @@ import cpp_host_build as B
 pytestmark = pytest.mark.gpu
 
 
-def test_reference_unit_tests_pass_on_the_adapter_over_the_cuda_library():
-    exe, env = B.build_real()
-    out = B.run(exe, env, timeout=900)
+def _run(env):
+    exe, base = B.build_real()
+    out = B.run(exe, dict(base, **env), timeout=900)
     m = re.search(r"(\d+) tests ran, (\d+) failed", out.stdout)
     assert m, out.stdout[-4000:] + out.stderr[-2000:]
-    assert out.returncode == 0 and int(m.group(2)) == 0 and int(m.group(1)) >= 29, out.stdout[-6000:]
+    assert out.returncode == 0 and int(m.group(2)) == 0 and int(m.group(1)) >= 30, out.stdout[-6000:]
+
+
+def test_reference_unit_tests_pass_on_the_adapter_over_the_cuda_library():
+    """per-observation form of cal_problem_desc (object_xy uploaded for every observation)"""
+    _run({"CALIB_B200_PER_OBSERVATION": "1"})
+
+
+def test_reference_unit_tests_pass_with_the_shared_board_form():
+    """the adapter's default: one board while the views share it (cal_problem_desc.board_n > 0)"""
+    _run({})
