@@ -393,7 +393,19 @@ def cpu_baseline(args, steps):
     return {"value": int(prob.desc.n_obs) / dt, "unit": "observations/s", "cores": cores, "kind": "port",
             "sample": f"first {n_sample} views x {prob.desc.n_cams} cameras x 88 corners = {int(prob.desc.n_obs)} observations, "
                       f"{steps} fused passes of the forward-mode (Jet-width-24) restatement, OpenMP over residual blocks",
-            "ms_per_pass": dt * 1e3}
+            "ms_per_pass": dt * 1e3, "lm_solve": cpu_lm_solve(O, prob, x0)}
+
+
+def cpu_lm_solve(O, prob, x0):
+    """The whole LM solve (with covariance) of the CPU restatement on the same bounded sample: the counterpart of the
+    GPU arm's e2e.wall_s / lm_iteration_ms (SURVEY 8d asks for per-iteration and total solve time of the CPU path)."""
+    t0 = time.perf_counter()
+    _, r, _ = O.refine_solve(prob, x0)
+    dt = time.perf_counter() - t0
+    n_jac = int(r.num_jac_evals)
+    return {"wall_s": dt, "iterations": int(r.iterations), "jacobian_passes": n_jac, "cost_passes": int(r.num_cost_evals),
+            "ms_per_iteration": 1e3 * dt / max(int(r.iterations), 1), "converged": bool(r.success),
+            "value": int(prob.desc.n_obs) * n_jac / dt, "unit": "observations/s (observations x fused passes / solve wall time, as e2e.value)"}
 
 
 def run_reference(args, rank, world):
@@ -413,7 +425,8 @@ def run_reference(args, rank, world):
     value = int(prob.desc.n_obs) / dt
     n_cams, n_poses, desc = WORKLOADS[args.workload]
     cb = {"value": value, "unit": "observations/s", "cores": cores, "kind": "port",
-          "sample": f"first {n_sample} views x {n_cams} cameras x 88 corners = {int(prob.desc.n_obs)} observations per step"}
+          "sample": f"first {n_sample} views x {n_cams} cameras x 88 corners = {int(prob.desc.n_obs)} observations per step",
+          "lm_solve": cpu_lm_solve(O, prob, x0)}
     print(json.dumps({
         "impl": "reference", "metric": "observations/s in residual+Jacobian+JtJ pass", "value": value, "unit": "observations/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
