@@ -385,6 +385,9 @@ struct PinholeCamera final {
     PinholeCamera(const CameraMatrixT<Scalar>& m, const Eigen::VectorXd& coeffs) : kmtx(m), distortion(coeffs) {}
     auto apply_intrinsics(const Eigen::Vector2d& px) const -> Eigen::Vector2d { return normalize(kmtx, px); }
     auto remove_intrinsics(const Eigen::Vector2d& n) const -> Eigen::Vector2d { return denormalize(kmtx, n); }
+    auto project(const Eigen::Vector2d& norm_xy) const -> Eigen::Vector2d {  // pinhole.h:96-100
+        return denormalize(kmtx, distortion.distort(norm_xy));
+    }
     auto project(const Eigen::Vector3d& xyz) const -> Eigen::Vector2d {  // pinhole.h:102-107
         return denormalize(kmtx, distortion.distort(xyz.hnormalized()));
     }

@@ -379,6 +379,26 @@ TEST(ScheimpflugBundle, HandeyeWithFixedIntrinsics) {  // :58-94
     EXPECT_NEAR(res.cameras[0].tau_y, tauy, 1e-6);
 }
 
+// ---- tests/unit/scheimpflug_test.cpp: the model that renders the scenes above (calib_b200_mini.hpp) ----
+
+TEST(ScheimpflugCamera, ZeroTiltMatchesPinhole) {  // :11-29
+    const auto cam = pinhole(800, 820, 320, 240);
+    ScheimpflugCamera<PinholeCamera<BrownConradyd>> sc(cam, {0.0, 0.0});
+    const Eigen::Vector3d Xc(0.2, -0.1, 1.0);
+    EXPECT_NEAR(sc.project(Xc).x(), cam.project(Xc).x(), 1e-9);
+    EXPECT_NEAR(sc.project(Xc).y(), cam.project(Xc).y(), 1e-9);
+}
+
+TEST(ScheimpflugCamera, PrincipalRay) {  // :31-51
+    const auto cam = pinhole(600, 600, 400, 300);
+    const double taux = 0.1, tauy = -0.2;
+    ScheimpflugCamera<PinholeCamera<BrownConradyd>> sc(cam, {taux, tauy});
+    const Eigen::Vector2d uv = sc.project(Eigen::Vector3d(0.0, 0.0, 1.0));
+    const Eigen::Vector2d expected_uv = cam.project(Eigen::Vector2d(-std::tan(tauy) / std::cos(taux), std::tan(taux)));
+    EXPECT_NEAR(uv.x(), expected_uv.x(), 1e-9);
+    EXPECT_NEAR(uv.y(), expected_uv.y(), 1e-9);
+}
+
 // ---- tests/unit/extrinsics_test.cpp ---------------------------------------------------------------
 
 namespace {

@@ -63,5 +63,29 @@ def build_standin():
     return exe, dict(os.environ, LD_LIBRARY_PATH=os.pathsep.join([odir, sdir, os.environ.get("LD_LIBRARY_PATH", "")]))
 
 
+EXAMPLE = os.path.join(ROOT, "examples", "cpp_adapter_example.cpp")
+
+
+def build_example(real):
+    """examples/cpp_adapter_example.cpp against the product library (real) or the CPU stand-in."""
+    if real:
+        from calibration_b200 import build
+        lib = build.build()
+        libdir = os.path.dirname(lib)
+        exe = os.path.join(ROOT, "examples", "_build", "cpp_adapter_example")
+        if _stale(exe, [EXAMPLE, lib] + SOURCES[3:]):
+            os.makedirs(os.path.dirname(exe), exist_ok=True)
+            subprocess.run([CXX, *FLAGS, EXAMPLE, "-o", exe, "-L", libdir, "-lcalib_b200", "-Wl,-rpath," + libdir], check=True)
+        return exe, dict(os.environ, LD_LIBRARY_PATH=libdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    _, env = build_standin()
+    odir, sdir = os.path.join(ROOT, "oracle", "_build"), os.path.join(EMUL, "_build")
+    exe = os.path.join(OUT, "cpp_adapter_example_standin")
+    standin = os.path.join(CPP, "abi_standin.cpp")
+    if _stale(exe, [EXAMPLE, standin] + SOURCES[3:]):
+        subprocess.run([CXX, *FLAGS, "-DSTANDIN_SIMT", "-I", os.path.join(ROOT, "oracle"), EXAMPLE, standin, "-o", exe, "-L", odir, "-loracle",
+                        "-L", sdir, "-lransac_simt", "-lseed_simt", "-pthread", "-Wl,-rpath," + odir, "-Wl,-rpath," + sdir], check=True)
+    return exe, env
+
+
 def run(exe, env, *filters, timeout=600):
     return subprocess.run([exe, *filters], capture_output=True, text=True, timeout=timeout, env=env)

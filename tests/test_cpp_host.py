@@ -50,3 +50,16 @@ def test_computing_calls_fail_loudly_without_a_device():
         out = B.run(exe, env, name)
         assert out.returncode != 0, name
         assert "no CUDA device: calib_b200 has no CPU fallback" in out.stdout, out.stdout[-2000:]
+
+
+def test_cpp_example_of_the_adapter_builds_and_runs_over_the_standin():
+    """examples/cpp_adapter_example.cpp: estimate_intrinsics -> estimate_planar_pose -> optimize_intrinsics on noisy
+    data, the way a user of the reference writes it"""
+    exe, env = B.build_example(real=False)
+    out = B.run(exe, env)
+    assert out.returncode == 0 and "CONVERGENCE" in out.stdout, out.stdout + out.stderr
+    exe, env = B.build_example(real=True)     # links against the product; without a device it reports the error and exits 2
+    from calibration_b200 import capi
+    if capi.device_count() == 0:
+        out = B.run(exe, env)
+        assert out.returncode == 2 and "no CUDA device" in out.stdout

@@ -28,3 +28,9 @@ def test_reference_unit_tests_pass_on_the_adapter_over_the_cuda_library():
 def test_reference_unit_tests_pass_with_the_shared_board_form():
     """the adapter's default: one board while the views share it (cal_problem_desc.board_n > 0)"""
     _run({})
+
+
+def test_cpp_example_of_the_adapter_runs():
+    exe, env = B.build_example(real=True)
+    out = B.run(exe, env, timeout=300)
+    assert out.returncode == 0 and "CONVERGENCE" in out.stdout, out.stdout + out.stderr
