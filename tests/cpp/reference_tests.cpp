@@ -150,6 +150,33 @@ TEST(OptimizeIntrinsics, ViewsWithMissingCornersLeaveTheSharedBoardForm) {
     }
 }
 
+// Non-convergence is not an error (solve_problem, src/estimation/detail/ceresutils.h:40-42): success = false, the
+// parameters reached so far are returned; compute_covariance = false leaves OptimResult::covariance empty (:109-118 of intrinsics.cpp).
+TEST(OptimizeIntrinsics, NonConvergenceStaysInBand) {
+    RNG rng(7);
+    const auto cam_gt = pinhole(1000, 1005, 640, 360);
+    SimulatedHandEye sim{Eigen::Isometry3d::Identity(), Eigen::Translation3d(0.0, 0.0, 2.0) * Eigen::Isometry3d::Identity(), cam_gt};
+    sim.make_sequence(15, rng);
+    sim.make_target_grid(8, 11, 0.02);
+    sim.render_pixels();
+    const auto views = views_of(sim);
+    auto guess_cam = cam_gt;
+    guess_cam.kmtx.fx *= 0.97;
+    guess_cam.kmtx.fy *= 1.03;
+    std::vector<Eigen::Isometry3d> init_poses;
+    for (const auto& view : views) init_poses.push_back(estimate_planar_pose(view, guess_cam.kmtx));
+    IntrinsicsOptimOptions opts;
+    opts.core.max_iterations = 2;
+    opts.core.compute_covariance = false;
+    const auto res = optimize_intrinsics(views, guess_cam, init_poses, opts);
+    EXPECT_FALSE(res.core.success);
+    EXPECT_TRUE(res.core.report.find("NO_CONVERGENCE") != std::string::npos);
+    EXPECT_EQ(res.core.covariance.rows(), static_cast<Eigen::Index>(0));
+    EXPECT_GT(res.core.final_cost, 0.0);
+    EXPECT_LT(std::abs(res.camera.kmtx.fx - 1000.0), 30.0);   // two iterations in: better than the start, not yet there
+    ASSERT_EQ(res.c_se3_t.size(), views.size());
+}
+
 TEST(OptimizeIntrinsics, InsufficientViewsThrow) {  // validate_input, src/estimation/optim/intrinsics.cpp:92-96
     const auto cam = pinhole(1000, 1000, 640, 360);
     std::vector<PlanarView> views(3, PlanarView(12));
