@@ -1,0 +1,257 @@
+// Device code of K2 — the per-view pose blocks of the intrinsics / extrinsics kinds: gather, Jacobi scaling, batched
+// 6x6 Cholesky, Schur complement as a tiled SYRK, back-substitution, per-view plus / norms / reductions (see
+// refine_kernels.cu for the launchers).  Kept in a header so that tests/host_emul can run this very source on the
+// CPU under the lock-step SIMT shim (test-only); nothing here differs between the two builds.
+#pragma once
+#include "refine_kernels.cuh"
+
+namespace calk {
+
+// ---------------------------------------------------------------------------
+// K2: per-view pose blocks — gather, scaling, batched Cholesky, Schur, back-substitution
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int sym6(int i, int j) {
+    return i <= j ? i * 6 - i * (i - 1) / 2 + (j - i) : j * 6 - j * (j - 1) / 2 + (i - j);
+}
+__device__ __forceinline__ int shared_col(const ViewBuffers& V, int cam, int j) {
+    // column j of a block's coupling E = [cam pose quat(3) | cam pose tran(3) | intr(PI)]
+    const int base = j < 3 ? V.cam_col_q[cam] : (j < 6 ? V.cam_col_t[cam] : V.cam_col_i[cam]);
+    return base < 0 ? -1 : base + (j < 3 ? j : (j < 6 ? j - 3 : j - 6));
+}
+
+__global__ void k_view_gather(ProblemShape S, DevLayout L, EvalBuffers B, ViewBuffers V) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= S.n_views) return;
+    double H[21], g[6];
+    for (int i = 0; i < 21; ++i) H[i] = 0.0;
+    for (int i = 0; i < 6; ++i) g[i] = 0.0;
+    if (V.view_free[v])
+        for (int k = V.view_blk_off[v]; k < V.view_blk_off[v + 1]; ++k) {
+            const int64_t b = V.view_blk_idx[k];
+            for (int i = 0; i < 21; ++i) H[i] += B.blk_Hvv[(int64_t)i * L.n_blk + b];
+            for (int i = 0; i < 6; ++i) g[i] += B.blk_gv[(int64_t)i * L.n_blk + b];
+        }
+    for (int i = 0; i < 6; ++i) {
+        for (int j = 0; j < 6; ++j) V.Hpp[(int64_t)v * 36 + 6 * i + j] = H[sym6(i, j)];
+        V.gp[(int64_t)v * 6 + i] = g[i];
+    }
+}
+
+__global__ void k_view_scale(ProblemShape S, ViewBuffers V, int compute_scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.n_views * 6) return;
+    const int v = i / 6, k = i % 6;
+    const double h = V.Hpp[(int64_t)v * 36 + 7 * k];
+    double s = V.sp[i];
+    if (compute_scale) { s = 1.0 / (1.0 + sqrt(h)); V.sp[i] = s; }  // jacobi_scaling, once
+    V.dp[i] = fmin(fmax(h * s * s, 1e-6), 1e32);                      // LM diagonal clamp (B.3-1)
+}
+
+// Per view: L = chol(sp Hpp sp + dp / radius), f = L^-1 (sp o gp), and for each
+// of its blocks F_b = L^-1 (diag(sp) E_b diag(s_shared)), so that
+// E^T A^-1 E = F^T F and E^T A^-1 g = F^T f.
+__global__ void k_schur_factor(ProblemShape S, DevLayout L, EvalBuffers B, ViewBuffers V, double inv_radius) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= S.n_views) return;
+    if (!V.view_free[v]) return;
+    double A[36], sp[6];
+    for (int i = 0; i < 6; ++i) sp[i] = V.sp[(int64_t)v * 6 + i];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) A[6 * i + j] = V.Hpp[(int64_t)v * 36 + 6 * i + j] * sp[i] * sp[j];
+    for (int i = 0; i < 6; ++i) A[7 * i] += V.dp[(int64_t)v * 6 + i] * inv_radius;
+    if (!chol6(A)) { atomicExch(V.fail, 1); return; }
+    for (int i = 0; i < 36; ++i) V.Lp[(int64_t)v * 36 + i] = A[i];
+    double f[6];
+    for (int i = 0; i < 6; ++i) f[i] = V.gp[(int64_t)v * 6 + i] * sp[i];
+    for (int i = 0; i < 6; ++i) { double s = f[i]; for (int k = 0; k < i; ++k) s -= A[6 * i + k] * f[k]; f[i] = s / A[7 * i]; }
+    for (int i = 0; i < 6; ++i) V.view_f[(int64_t)v * 6 + i] = f[i];
+    const int ncb = 6 + S.PI;
+    for (int k = V.view_blk_off[v]; k < V.view_blk_off[v + 1]; ++k) {
+        const int64_t b = V.view_blk_idx[k];
+        const int cam = L.blk_cam[b];
+        for (int j = 0; j < ncb; ++j) {
+            const int col = shared_col(V, cam, j);
+            const double sc = col < 0 ? 0.0 : V.s_shared[col];
+            double e[6];
+            for (int i = 0; i < 6; ++i) {
+                const double ev = j < 6 ? B.blk_Evc[(int64_t)(6 * i + j) * L.n_blk + b]
+                                        : B.blk_Evi[(int64_t)(S.PI * i + j - 6) * L.n_blk + b];
+                e[i] = ev * sp[i] * sc;
+            }
+            for (int i = 0; i < 6; ++i) { double s = e[i]; for (int kk = 0; kk < i; ++kk) s -= A[6 * i + kk] * e[kk]; e[i] = s / A[7 * i]; }
+            for (int i = 0; i < 6; ++i) V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b] = e[i];
+        }
+    }
+}
+
+// C_aug = sum_v F_v^T F_v as a tiled SYRK with a long inner dimension (6 rows per view).  The
+// (ns+1)^2 upper triangle is covered by 8x8 register tiles, one per thread; the CTA has exactly as many
+// warps as the tile count needs (120 tiles at ns = 114 -> 4 warps, three CTAs per SM), owns a chunk of
+// the views and stages the dense 6 x (ns+1) rows [F_v | f_v] of kSyrkViews views per barrier pair in
+// shared memory.  Per-CTA partial results are summed in a fixed order (no floating-point atomics).
+constexpr int kSyrkViews = 4;
+__global__ void __launch_bounds__(kSyrkThreads) k_schur_syrk(ProblemShape S, DevLayout L, ViewBuffers V, int ns,
+                                                             int views_per_cta) {
+    __shared__ double frow[kSyrkViews * 6][kSyrkMaxN];
+    const int na = ns + 1;
+    const int nt = (na + kSyrkTile - 1) / kSyrkTile;
+    const int ncol = nt * kSyrkTile;  // columns actually read by the tiles
+    int ti = -1, tj = -1;
+    {
+        int t = threadIdx.x, row = 0;
+        while (row < nt && t >= nt - row) { t -= nt - row; ++row; }
+        if (row < nt) { ti = row; tj = row + t; }
+    }
+    double acc[kSyrkTile][kSyrkTile];
+#pragma unroll
+    for (int i = 0; i < kSyrkTile; ++i)
+#pragma unroll
+        for (int j = 0; j < kSyrkTile; ++j) acc[i][j] = 0.0;
+    const int v0 = blockIdx.x * views_per_cta, v1 = min(S.n_views, v0 + views_per_cta);
+    const int ncb = 6 + S.PI;
+    for (int vb = v0; vb < v1; vb += kSyrkViews) {
+        const int nvb = min(kSyrkViews, v1 - vb);
+        for (int i = threadIdx.x; i < nvb * 6 * ncol; i += blockDim.x) frow[i / ncol][i % ncol] = 0.0;
+        __syncthreads();
+        for (int q = 0; q < nvb; ++q) {
+            const int v = vb + q;
+            if (!V.view_free[v]) continue;  // uniform across the CTA; its rows stay zero
+            const int nb = V.view_blk_off[v + 1] - V.view_blk_off[v];
+            for (int idx = threadIdx.x; idx < nb * ncb * 6; idx += blockDim.x) {
+                const int kb = idx / (ncb * 6), rem = idx % (ncb * 6), i = rem / ncb, j = rem % ncb;
+                const int64_t b = V.view_blk_idx[V.view_blk_off[v] + kb];
+                const int col = shared_col(V, L.blk_cam[b], j);
+                if (col >= 0) frow[q * 6 + i][col] = V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b];
+            }
+            if (threadIdx.x < 6) frow[q * 6 + threadIdx.x][ns] = V.view_f[(int64_t)v * 6 + threadIdx.x];
+        }
+        __syncthreads();
+        if (ti >= 0) {
+            for (int r = 0; r < nvb * 6; ++r) {
+                double fa[kSyrkTile], fb[kSyrkTile];
+#pragma unroll
+                for (int i = 0; i < kSyrkTile; ++i) { fa[i] = frow[r][ti * kSyrkTile + i]; fb[i] = frow[r][tj * kSyrkTile + i]; }
+#pragma unroll
+                for (int i = 0; i < kSyrkTile; ++i)
+#pragma unroll
+                    for (int j = 0; j < kSyrkTile; ++j) acc[i][j] = fma(fa[i], fb[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+    if (ti >= 0) {
+        double* out = V.partialC + (int64_t)blockIdx.x * na * na;
+        for (int i = 0; i < kSyrkTile; ++i)
+            for (int j = 0; j < kSyrkTile; ++j) {
+                const int r = ti * kSyrkTile + i, c = tj * kSyrkTile + j;
+                if (r < na && c < na) { out[(int64_t)r * na + c] = acc[i][j]; if (ti != tj) out[(int64_t)c * na + r] = acc[i][j]; }
+            }
+    }
+}
+
+__global__ void k_schur_reduce(ViewBuffers V, int n_cta, int ns) {
+    const int na = ns + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= na * na) return;
+    double s = 0.0;
+    for (int c = 0; c < n_cta; ++c) s += V.partialC[(int64_t)c * na * na + i];
+    const int r = i / na, cc = i % na;
+    if (r < ns && cc < ns) V.C[(int64_t)r * ns + cc] = s;
+    else if (r < ns && cc == ns) V.c[r] = s;
+}
+
+// y_p = L^-T (f - sum_b F_b y_s[cols(b)]), step_p = -y_p, delta_p = step_p o sp, and the
+// per-view terms of step'g and step'H step (H undamped, Jacobi-scaled).
+__global__ void k_backsub(ProblemShape S, DevLayout L, ViewBuffers V, int ns) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= S.n_views) return;
+    double* red = V.red + (int64_t)v * 4;
+    if (!V.view_free[v]) {
+        for (int i = 0; i < 6; ++i) V.delta_p[(int64_t)v * 6 + i] = 0.0;
+        red[0] = red[1] = 0.0;
+        return;
+    }
+    double Lm[36], q[6], f[6], sp[6];
+    for (int i = 0; i < 36; ++i) Lm[i] = V.Lp[(int64_t)v * 36 + i];
+    for (int i = 0; i < 6; ++i) { f[i] = V.view_f[(int64_t)v * 6 + i]; sp[i] = V.sp[(int64_t)v * 6 + i]; q[i] = 0.0; }
+    const int ncb = 6 + S.PI;
+    for (int k = V.view_blk_off[v]; k < V.view_blk_off[v + 1]; ++k) {
+        const int64_t b = V.view_blk_idx[k];
+        const int cam = L.blk_cam[b];
+        for (int j = 0; j < ncb; ++j) {
+            const int col = shared_col(V, cam, j);
+            if (col < 0) continue;
+            const double ys = V.y_shared[col];
+            for (int i = 0; i < 6; ++i) q[i] += V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b] * ys;
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) y[i] = f[i] - q[i];
+    for (int i = 5; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < 6; ++k) s -= Lm[6 * k + i] * y[k]; y[i] = s / Lm[7 * i]; }
+    double step[6], sg = 0.0;
+    for (int i = 0; i < 6; ++i) { step[i] = -y[i]; sg += step[i] * V.gp[(int64_t)v * 6 + i] * sp[i]; V.delta_p[(int64_t)v * 6 + i] = step[i] * sp[i]; }
+    // quad = step' A0 step + 2 step' E_s step_s ; E_s step_s = -L q
+    double quad = 0.0;
+    for (int i = 0; i < 6; ++i) {
+        double row = 0.0;
+        for (int j = 0; j < 6; ++j) row += V.Hpp[(int64_t)v * 36 + 6 * i + j] * sp[j] * step[j];
+        double lq = 0.0;
+        for (int k = 0; k <= i; ++k) lq += Lm[6 * i + k] * q[k];
+        quad += step[i] * (sp[i] * row - 2.0 * lq);
+    }
+    red[0] = sg; red[1] = quad;
+}
+
+// x_cand(view v) = x(view v) [+] t * delta_p ; red[2] = |dx|^2
+__global__ void k_view_plus(ProblemShape S, EvalBuffers B, ViewBuffers V, double t) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= S.n_views) return;
+    const double* q = B.x + S.off_viewq + 4 * (int64_t)v; const double* tr = B.x + S.off_viewt + 3 * (int64_t)v;
+    double* qo = V.x_cand + S.off_viewq + 4 * (int64_t)v; double* to = V.x_cand + S.off_viewt + 3 * (int64_t)v;
+    double d[6];
+    for (int i = 0; i < 6; ++i) d[i] = t * V.delta_p[(int64_t)v * 6 + i];
+    double qn[4]; quat_plus(q, d, qn);
+    double dx2 = 0.0;
+    for (int i = 0; i < 4; ++i) { qo[i] = qn[i]; const double e = qn[i] - q[i]; dx2 += e * e; }
+    for (int i = 0; i < 3; ++i) { const double e = d[3 + i]; to[i] = tr[i] + e; dx2 += (to[i] - tr[i]) * (to[i] - tr[i]); }
+    V.red[(int64_t)v * 4 + 2] = dx2;
+}
+
+// red[0] = |x_v|^2, red[3] = max |x_v - plus(x_v, -g_v)| (gradient max-norm piece)
+__global__ void k_view_norms(ProblemShape S, EvalBuffers B, ViewBuffers V) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= S.n_views) return;
+    const double* q = B.x + S.off_viewq + 4 * (int64_t)v; const double* tr = B.x + S.off_viewt + 3 * (int64_t)v;
+    double x2 = 0.0, gm = 0.0;
+    for (int i = 0; i < 4; ++i) x2 += q[i] * q[i];
+    for (int i = 0; i < 3; ++i) x2 += tr[i] * tr[i];
+    if (V.view_free[v]) {
+        double d[6]; for (int i = 0; i < 6; ++i) d[i] = -V.gp[(int64_t)v * 6 + i];
+        double qn[4]; quat_plus(q, d, qn);
+        for (int i = 0; i < 4; ++i) gm = fmax(gm, fabs(q[i] - qn[i]));
+        for (int i = 0; i < 3; ++i) gm = fmax(gm, fabs(tr[i] - (tr[i] + d[3 + i])));
+    }
+    V.red[(int64_t)v * 4 + 0] = x2; V.red[(int64_t)v * 4 + 3] = gm;
+}
+
+// red_out[0..2] = column sums, red_out[3] = column max; fixed-order single-CTA tree
+__global__ void __launch_bounds__(1024) k_reduce_views(ViewBuffers V, int n_views) {
+    __shared__ double sm[4][1024];
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int v = threadIdx.x; v < n_views; v += 1024) {
+        const double* r = V.red + (int64_t)v * 4;
+        a[0] += r[0]; a[1] += r[1]; a[2] += r[2]; a[3] = fmax(a[3], r[3]);
+    }
+    for (int k = 0; k < 4; ++k) sm[k][threadIdx.x] = a[k];
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            for (int k = 0; k < 3; ++k) sm[k][threadIdx.x] += sm[k][threadIdx.x + s];
+            sm[3][threadIdx.x] = fmax(sm[3][threadIdx.x], sm[3][threadIdx.x + s]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 4) V.red_out[threadIdx.x] = sm[threadIdx.x][0];
+}
+
+}  // namespace calk

@@ -1,0 +1,94 @@
+// TEST INFRASTRUCTURE — the PRODUCT's K2 kernels (calibration_b200/csrc/refine_schur_kernels.cuh: k_view_gather,
+// k_view_scale, k_schur_factor, k_schur_syrk, k_schur_reduce, k_backsub, k_reduce_views) compiled by g++ and run on
+// the CPU under the lock-step SIMT shim, launched in the order and with the grids of one LM iteration of
+// cal_refine_solve (refine_host.cu) / launch_schur (refine_kernels.cu).  Input: the per-residual-block products K1's
+// epilogue stores for the per-view kinds (H_vv, g_v, E_vc, E_vi) and the damped, Jacobi-scaled shared block; output:
+// the Schur complement, the reduced solution, the per-view steps and the per-view terms of the model cost change.
+#define SIMT_SHARED_STORAGE static
+#include "simt_shim.hpp"
+
+inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+
+#include "../../calibration_b200/csrc/refine_schur_kernels.cuh"
+
+using namespace calk;
+
+namespace {
+// launch_schur's grid (refine_kernels.cu: schur_num_ctas): up to 444 CTAs, at least 16 views each
+int schur_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < 444 * 16 ? (n_views + 15) / 16 : 444); }
+
+// dense SPD solve (the product factorises the reduced system on the host with chol_host; any exact solver checks it)
+bool solve_spd(std::vector<double> A, int n, double* b) {
+    for (int j = 0; j < n; ++j) {
+        double d = A[(size_t)j * n + j];
+        for (int k = 0; k < j; ++k) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+        if (!(d > 0)) return false;
+        d = std::sqrt(d); A[(size_t)j * n + j] = d;
+        for (int i = j + 1; i < n; ++i) {
+            double s = A[(size_t)i * n + j];
+            for (int k = 0; k < j; ++k) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+            A[(size_t)i * n + j] = s / d;
+        }
+    }
+    for (int i = 0; i < n; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= A[(size_t)i * n + k] * b[k]; b[i] = s / A[(size_t)i * n + i]; }
+    for (int i = n - 1; i >= 0; --i) { double s = b[i]; for (int k = i + 1; k < n; ++k) s -= A[(size_t)k * n + i] * b[k]; b[i] = s / A[(size_t)i * n + i]; }
+    return true;
+}
+}  // namespace
+
+extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, const int32_t* blk_cam, const int32_t* blk_view,
+                            const int32_t* view_free, const int32_t* cam_col_q, const int32_t* cam_col_t, const int32_t* cam_col_i,
+                            const double* blk_Hvv, const double* blk_gv, const double* blk_Evc, const double* blk_Evi, int ns,
+                            const double* s_shared, const double* Hss_scaled_damped, const double* gs_scaled, double radius,
+                            double* C, double* c, double* y_shared, double* delta_p, double* red_out4, int32_t* fail, double* sp_out) {
+    if (ns + 1 > kSyrkMaxN) return 2;
+    ProblemShape S{};
+    S.n_views = n_views; S.n_cams = n_cams; S.PI = PI;
+    DevLayout L;
+    L.n_blk = n_blk;
+    std::vector<int32_t> bcam(blk_cam, blk_cam + n_blk);
+    L.blk_cam = bcam.data();
+    EvalBuffers B;
+    B.blk_Hvv = const_cast<double*>(blk_Hvv); B.blk_gv = const_cast<double*>(blk_gv);
+    B.blk_Evc = const_cast<double*>(blk_Evc); B.blk_Evi = const_cast<double*>(blk_Evi);
+    // view -> blocks CSR (cal_refine_create builds the same)
+    std::vector<int32_t> off(n_views + 1, 0), idx(n_blk), vfree(view_free, view_free + n_views), cq(cam_col_q, cam_col_q + n_cams),
+        ct(cam_col_t, cam_col_t + n_cams), ci(cam_col_i, cam_col_i + n_cams);
+    for (int64_t b = 0; b < n_blk; ++b) off[blk_view[b] + 1]++;
+    for (int v = 0; v < n_views; ++v) off[v + 1] += off[v];
+    { std::vector<int32_t> cur(off.begin(), off.end() - 1); for (int64_t b = 0; b < n_blk; ++b) idx[cur[blk_view[b]]++] = (int32_t)b; }
+    const int n_cta = schur_ctas(n_views), na = ns + 1, ncb = 6 + PI;
+    std::vector<double> Hpp((size_t)n_views * 36), gp((size_t)n_views * 6), sp((size_t)n_views * 6, 0.0), dp((size_t)n_views * 6), Lp((size_t)n_views * 36),
+        view_f((size_t)n_views * 6), blk_F((size_t)6 * ncb * n_blk, 0.0), dlt((size_t)n_views * 6, 0.0), ss(s_shared, s_shared + ns), ys(std::max(ns, 1)),
+        Cm((size_t)ns * ns), cv(std::max(ns, 1)), partialC((size_t)n_cta * na * na), red((size_t)n_views * 4, 0.0), ro(4, 0.0);
+    int32_t failed = 0;
+    ViewBuffers V;
+    V.view_blk_off = off.data(); V.view_blk_idx = idx.data(); V.view_free = vfree.data();
+    V.cam_col_q = cq.data(); V.cam_col_t = ct.data(); V.cam_col_i = ci.data();
+    V.Hpp = Hpp.data(); V.gp = gp.data(); V.sp = sp.data(); V.dp = dp.data(); V.Lp = Lp.data(); V.view_f = view_f.data(); V.blk_F = blk_F.data();
+    V.delta_p = dlt.data(); V.s_shared = ss.data(); V.y_shared = ys.data(); V.C = Cm.data(); V.c = cv.data(); V.partialC = partialC.data();
+    V.red = red.data(); V.red_out = ro.data(); V.fail = &failed;
+    // after the Jacobian pass: gather, Jacobi scaling once (compute_scale = 1); first LM iteration: the diagonal clamp
+    simt::launch((unsigned)((n_views + 127) / 128), 128, [&] { k_view_gather(S, L, B, V); });
+    simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 1); });
+    simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 0); });
+    // launch_schur
+    simt::launch((unsigned)((n_views + 63) / 64), 64, [&] { k_schur_factor(S, L, B, V, 1.0 / radius); });
+    const int per = (n_views + n_cta - 1) / n_cta, nt = (na + kSyrkTile - 1) / kSyrkTile, threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
+    simt::launch((unsigned)n_cta, (unsigned)threads, [&] { k_schur_syrk(S, L, V, ns, per); });
+    simt::launch((unsigned)((na * na + 127) / 128), 128, [&] { k_schur_reduce(V, n_cta, ns); });
+    *fail = failed;
+    std::memcpy(C, Cm.data(), sizeof(double) * ns * ns); std::memcpy(c, cv.data(), sizeof(double) * ns);
+    std::memcpy(sp_out, sp.data(), sizeof(double) * 6 * n_views);
+    if (failed) return 0;
+    // host: (S Hss S + D / radius - C) y = S gs - c
+    std::vector<double> Sm((size_t)ns * ns);
+    for (int i = 0; i < ns; ++i) { ys[i] = gs_scaled[i] - cv[i]; for (int j = 0; j < ns; ++j) Sm[(size_t)i * ns + j] = Hss_scaled_damped[(size_t)i * ns + j] - Cm[(size_t)i * ns + j]; }
+    if (ns > 0 && !solve_spd(Sm, ns, ys.data())) return 3;
+    std::memcpy(y_shared, ys.data(), sizeof(double) * ns);
+    simt::launch((unsigned)((n_views + 63) / 64), 64, [&] { k_backsub(S, L, V, ns); });
+    simt::launch(1, 1024, [&] { k_reduce_views(V, n_views); });
+    std::memcpy(delta_p, dlt.data(), sizeof(double) * 6 * n_views);
+    std::memcpy(red_out4, ro.data(), sizeof(double) * 4);
+    return 0;
+}

@@ -428,3 +428,127 @@ def test_k1_source_ragged_blocks(k1_simt):
     c, g, H, roles, uni = k1_eval(k1_simt, p2, x0)
     assert uni == 0 and abs(c - c_o) <= 1e-12 * abs(c_o)
     assert np.abs(g - g_o).max() <= 1e-10 * np.abs(g_o).max() and np.abs(H - H_o).max() <= 1e-10 * np.abs(H_o).max()
+
+
+# K2 kernels (csrc/refine_schur_kernels.cuh) under the same shim
+# ---------------------------------------------------------------------------
+K2_SRC = os.path.join(ROOT, "tests", "host_emul", "k2_simt.cpp")
+K2_SO = os.path.join(ROOT, "tests", "host_emul", "_build", "libk2_simt.so")
+
+
+@pytest.fixture(scope="module")
+def k2_simt():
+    deps = [K2_SRC, os.path.join(ROOT, "tests", "host_emul", "simt_shim.hpp")] + [
+        os.path.join(CSRC, f) for f in ("refine_schur_kernels.cuh", "refine_kernels.cuh", "k1_math.cuh")]
+    if not os.path.exists(K2_SO) or any(os.path.getmtime(d) > os.path.getmtime(K2_SO) for d in deps):
+        os.makedirs(os.path.dirname(K2_SO), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([cxx, "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I/usr/local/cuda/include", "-o", K2_SO, K2_SRC],
+                       check=True)
+    L = C.CDLL(K2_SO)
+    dp, ip = abi.c_double_p, abi.c_int32_p
+    L.simt_k2_step.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, ip, ip, ip, ip, ip, ip, dp, dp, dp, dp, C.c_int, dp, dp, dp, C.c_double,
+                               dp, dp, dp, dp, dp, ip, dp]
+    return L
+
+
+def _k2_problem(seed, n_views, PI, radius, fixed_views=(0,), drop=0.15):
+    """A random normal-equation system with the block structure of the per-view kinds: per view a 6-dof pose block,
+    two cameras (camera 0's pose is the gauge, camera 1's is free), PI free intrinsics per camera; every residual
+    block couples ONE view with ONE camera.  Returns the per-block products K1's epilogue stores and the dense system."""
+    rng = np.random.default_rng(seed)
+    n_cams = 2
+    cq = np.array([-1, PI], dtype=np.int32); ct = np.array([-1, PI + 3], dtype=np.int32); ci = np.array([0, PI + 6], dtype=np.int32)
+    ns = 2 * PI + 6
+    blocks = [(v, c) for v in range(n_views) for c in range(n_cams) if c == v % 2 or rng.random() > drop]
+    nb = len(blocks)
+    view_free = np.ones(n_views, dtype=np.int32); view_free[list(fixed_views)] = 0
+    Hvv = np.zeros((21, nb)); gv = np.zeros((6, nb)); Evc = np.zeros((36, nb)); Evi = np.zeros((6 * max(PI, 1), nb))
+    pcol = {v: 6 * k for k, v in enumerate(np.flatnonzero(view_free))}           # dense column of a free view's block
+    n_free = len(pcol)
+    N = 6 * n_free + ns
+    H = np.zeros((N, N)); g = np.zeros(N)
+    iu = [(i, j) for i in range(6) for j in range(i, 6)]
+    for b, (v, c) in enumerate(blocks):
+        m = 24
+        J = rng.normal(size=(m, 12 + PI)) * rng.uniform(0.5, 30.0, size=12 + PI)     # [view twist | camera pose | intrinsics], graded columns
+        r = rng.normal(size=m)
+        scols = np.array([-1 if cq[c] < 0 else cq[c] + j for j in range(3)] + [-1 if ct[c] < 0 else ct[c] + j for j in range(3)]
+                         + [ci[c] + j for j in range(PI)])
+        keep = scols >= 0
+        Js = J[:, 6:][:, keep]; sc = 6 * n_free + scols[keep]
+        H[np.ix_(sc, sc)] += Js.T @ Js; g[sc] += Js.T @ r
+        if view_free[v]:
+            Jv = J[:, :6]; pc = pcol[v] + np.arange(6)
+            A = Jv.T @ Jv
+            Hvv[:, b] = [A[i, j] for i, j in iu]; gv[:, b] = Jv.T @ r
+            E = Jv.T @ J[:, 6:]
+            Evc[:, b] = E[:, :6].reshape(-1)                       # garbage in the columns of a constant camera pose is ignored
+            if PI: Evi[:, b] = E[:, 6:].reshape(-1)
+            H[np.ix_(pc, pc)] += A; g[pc] += Jv.T @ r
+            H[np.ix_(pc, sc)] += Jv.T @ Js; H[np.ix_(sc, pc)] += Js.T @ Jv
+        else:
+            Evc[:, b] = rng.normal(size=36)                        # never read for a held view
+    return dict(n_views=n_views, n_cams=n_cams, PI=PI, ns=ns, blocks=blocks, view_free=view_free, cq=cq, ct=ct, ci=ci, Hvv=Hvv, gv=gv, Evc=Evc,
+                Evi=Evi, H=H, g=g, pcol=pcol, n_free=n_free, radius=radius)
+
+
+@pytest.mark.parametrize("case", [dict(seed=1, n_views=37, PI=9, radius=1e4), dict(seed=2, n_views=90, PI=10, radius=3.0),
+                                  dict(seed=3, n_views=21, PI=0, radius=1e2), dict(seed=4, n_views=70, PI=11, radius=1e-2, fixed_views=(0, 5, 69))])
+def test_k2_source_matches_a_dense_solve(k2_simt, case):
+    """One LM iteration of the per-view kinds through the product's K2 kernels — Jacobi scaling, clamped LM diagonal,
+    per-view Cholesky, Schur complement (tiled SYRK over several CTAs), back-substitution, the per-view terms of the model
+    cost change — against numpy's dense solve of the same damped, scaled normal equations."""
+    P = _k2_problem(**case)
+    nv, ns, nf, rad = P["n_views"], P["ns"], P["n_free"], P["radius"]
+    H, g = P["H"], P["g"]
+    s = 1.0 / (1.0 + np.sqrt(np.diag(H)))
+    Hs = H * np.outer(s, s)
+    D = np.clip(np.diag(Hs), 1e-6, 1e32)
+    y = np.linalg.solve(Hs + np.diag(D / rad), g * s)
+    step = -y
+    sh = slice(6 * nf, 6 * nf + ns)
+    ss = np.ascontiguousarray(s[sh]); Hsd = np.ascontiguousarray((Hs + np.diag(D / rad))[sh, sh]); gss = np.ascontiguousarray((g * s)[sh])
+    bcam = np.array([c for _, c in P["blocks"]], dtype=np.int32); bview = np.array([v for v, _ in P["blocks"]], dtype=np.int32)
+    Cm = np.zeros((ns, ns)); c = np.zeros(ns); ys = np.zeros(ns); dlt = np.zeros((nv, 6)); red = np.zeros(4); fail = np.zeros(1, dtype=np.int32); sp = np.zeros((nv, 6))
+    arrs = [np.ascontiguousarray(P[k]) for k in ("Hvv", "gv", "Evc", "Evi")]
+    rc = k2_simt.simt_k2_step(nv, P["n_cams"], P["PI"], len(bcam), abi.i32ptr(bcam), abi.i32ptr(bview), abi.i32ptr(P["view_free"]), abi.i32ptr(P["cq"]),
+                              abi.i32ptr(P["ct"]), abi.i32ptr(P["ci"]), *[abi.dptr(a) for a in arrs], ns, abi.dptr(ss), abi.dptr(Hsd), abi.dptr(gss), rad,
+                              abi.dptr(Cm), abi.dptr(c), abi.dptr(ys), abi.dptr(dlt), abi.dptr(red), abi.i32ptr(fail), abi.dptr(sp))
+    assert rc == 0 and fail[0] == 0
+    # Schur complement of the view blocks: E_s^T (A + D_p / radius)^-1 E_s and E_s^T (..)^-1 g_p, scaled
+    pv = slice(0, 6 * nf)
+    App = (Hs + np.diag(D / rad))[pv, pv]; Eps = Hs[pv, sh]
+    C_ref = Eps.T @ np.linalg.solve(App, Eps) if nf else np.zeros((ns, ns))
+    c_ref = Eps.T @ np.linalg.solve(App, (g * s)[pv]) if nf else np.zeros(ns)
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    if ns:
+        assert rel(Cm, C_ref) < 1e-11 and rel(c, c_ref) < 1e-11
+        assert rel(ys, y[sh]) < 1e-9
+    for v, col in P["pcol"].items():
+        assert rel(sp[v], s[col:col + 6]) < 1e-15
+    d_ref = np.zeros((nv, 6))
+    for v, col in P["pcol"].items():
+        d_ref[v] = step[col:col + 6] * s[col:col + 6]
+    assert rel(dlt, d_ref) < 1e-9
+    assert np.all(dlt[P["view_free"] == 0] == 0.0)
+    sg_ref = float(step[pv] @ (g * s)[pv])
+    quad_ref = float(step[pv] @ Hs[pv, pv] @ step[pv] + 2.0 * step[pv] @ Hs[pv, sh] @ step[sh])
+    assert abs(red[0] - sg_ref) <= 1e-9 * abs(sg_ref) and abs(red[1] - quad_ref) <= 1e-8 * max(abs(quad_ref), abs(sg_ref))
+
+
+def test_k2_source_flags_a_rank_deficient_view(k2_simt):
+    """a view block that is not positive definite raises the failure flag (the LM then treats the step as invalid)"""
+    P = _k2_problem(seed=5, n_views=12, PI=9, radius=1e4)
+    b0 = [b for b, (v, _) in enumerate(P["blocks"]) if v == 3]
+    P["Hvv"][:, b0] = 0.0
+    P["Hvv"][0, b0[0]] = -1.0
+    nv, ns = P["n_views"], P["ns"]
+    bcam = np.array([c for _, c in P["blocks"]], dtype=np.int32); bview = np.array([v for v, _ in P["blocks"]], dtype=np.int32)
+    Cm = np.zeros((ns, ns)); c = np.zeros(ns); ys = np.zeros(ns); dlt = np.zeros((nv, 6)); red = np.zeros(4); fail = np.zeros(1, dtype=np.int32); sp = np.zeros((nv, 6))
+    arrs = [np.ascontiguousarray(P[k]) for k in ("Hvv", "gv", "Evc", "Evi")]
+    ss = np.ones(ns); Hsd = np.eye(ns); gss = np.zeros(ns)
+    rc = k2_simt.simt_k2_step(nv, P["n_cams"], P["PI"], len(bcam), abi.i32ptr(bcam), abi.i32ptr(bview), abi.i32ptr(P["view_free"]), abi.i32ptr(P["cq"]),
+                              abi.i32ptr(P["ct"]), abi.i32ptr(P["ci"]), *[abi.dptr(a) for a in arrs], ns, abi.dptr(ss), abi.dptr(Hsd), abi.dptr(gss), 1e4,
+                              abi.dptr(Cm), abi.dptr(c), abi.dptr(ys), abi.dptr(dlt), abi.dptr(red), abi.i32ptr(fail), abi.dptr(sp))
+    assert rc == 0 and fail[0] == 1
