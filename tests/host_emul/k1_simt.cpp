@@ -112,3 +112,108 @@ extern "C" int simt_bundle_eval(const cal_problem_desc* dp, const double* x, dou
 }
 
 extern "C" int64_t simt_tangent_count(const cal_problem_desc* dp) { HostModel M; M.init_model(*dp); return M.n_tan; }
+
+// ---- kinds with per-view pose blocks (intrinsics, extrinsics): K1 with the VIEW_STORE epilogue (per-block H_vv, g_v,
+// E_vc = Q T_c, E_vi written for the Schur kernels) + k_view_gather, then the product's dense host assembly ----
+#include "../../calibration_b200/csrc/refine_schur_kernels.cuh"
+
+namespace {
+template <int MODEL, int IMODE>
+void views_pass_t(const ProblemShape& S, const DevLayout& L, const double* x, int n_amb, std::vector<double>& cam_sums, EvalBuffers& B, int* n_roles) {
+    using RT = K1Roles<MODEL, IMODE>;
+    const int64_t nb = L.n_blk;
+    const int nvt = RT::nvt(false);
+    std::vector<int32_t> vmap; RT::value_map(false, vmap);
+    std::vector<CamConst> camc(S.n_cams);
+    std::vector<double> xs(x, x + n_amb), camT((size_t)36 * S.n_cams), seg_frame((size_t)9 * nb), blk_Tv((size_t)36 * nb, 0.0), blk_ssr(nb),
+        tile_vals((size_t)L.n_tiles * nvt, 0.0);
+    B.x = xs.data(); B.camc = camc.data(); B.camT = camT.data(); B.seg_frame = seg_frame.data(); B.blk_Tv = blk_Tv.data();
+    B.blk_ssr = blk_ssr.data(); B.tile_vals = tile_vals.data();
+    const int64_t n = std::max<int64_t>(nb, S.n_cams);
+    simt::launch((unsigned)((n + 127) / 128), 128, [&] { k_block_setup(S, L, B); });
+    K1Args P{L, B, S.huber_delta, nvt};
+    if (K1Smem<MODEL, IMODE>::kBytes > (int)sizeof k1_smem) std::abort();
+    simt::launch((unsigned)L.n_tiles, RT::NROLE * 32, [&] { k1_kernel<MODEL, IMODE, VIEW_STORE>(P); });
+    for (int64_t t = 0; t < L.n_tiles; ++t) {
+        double* sums = &cam_sums[(size_t)L.seg_cam[t * 32] * S.NV];
+        for (int j = 0; j < nvt; ++j) sums[vmap[j]] += tile_vals[(size_t)t * nvt + j];
+    }
+    B.x = nullptr; B.camc = nullptr; B.camT = nullptr; B.seg_frame = nullptr; B.blk_Tv = nullptr; B.blk_ssr = nullptr; B.tile_vals = nullptr;
+    *n_roles = RT::NROLE;
+}
+}  // namespace
+
+extern "C" int simt_views_eval(const cal_problem_desc* dp, const double* x, double* cost, double* g, double* H, int32_t* n_roles_out) {
+    const cal_problem_desc& d = *dp;
+    if (d.kind == CAL_KIND_BUNDLE) return 1;
+    HostModel M; M.init_model(d);
+    const ProblemShape& S = M.S;
+    const int nv = S.n_views;
+    auto view_of = [&](int64_t b) { return S.kind == CAL_KIND_INTRINSICS ? (int32_t)b : d.block_view[b]; };
+    // fused layout as cal_refine_create builds it: device blocks sorted by camera, camera groups padded to whole tiles
+    std::vector<int64_t> blk_orig; std::vector<int32_t> blk_cam, blk_view;
+    for (int c = 0; c < S.n_cams; ++c) {
+        for (int64_t b = 0; b < d.n_blocks; ++b) if (d.block_cam[b] == c) { blk_orig.push_back(b); blk_cam.push_back(c); blk_view.push_back(view_of(b)); }
+        while (blk_orig.size() % 32) { blk_orig.push_back(-1); blk_cam.push_back(c); blk_view.push_back(-1); }
+    }
+    const int64_t nb = (int64_t)blk_orig.size(), nt = nb / 32;
+    std::vector<int32_t> seg_len(nb), seg_blk(nb), blk_seg_off(nb + 1), blk_vfree(nb, 0), tile_depth(nt), vfree(nv);
+    std::vector<int64_t> seg_src(nb, 0), tile_off(nt);
+    for (int v = 0; v < nv; ++v) vfree[v] = !M.pbs[M.pb_viewq(v)].constant;
+    for (int64_t b = 0; b < nb; ++b) {
+        const int64_t o = blk_orig[b];
+        seg_len[b] = o >= 0 ? (int32_t)(d.block_offset[o + 1] - d.block_offset[o]) : 0;
+        seg_src[b] = o >= 0 ? d.block_offset[o] : 0;
+        seg_blk[b] = (int32_t)b; blk_seg_off[b] = (int32_t)b;
+        blk_vfree[b] = o >= 0 && vfree[blk_view[b]];
+    }
+    blk_seg_off[nb] = (int32_t)nb;
+    int64_t slices = 0;
+    for (int64_t t = 0; t < nt; ++t) {
+        int dep = 0;
+        for (int l = 0; l < 32; ++l) dep = std::max(dep, seg_len[t * 32 + l]);
+        tile_depth[t] = dep; tile_off[t] = slices; slices += dep;
+    }
+    std::vector<double> obs((size_t)slices * 128);
+    DevLayout L;
+    L.n_seg = nb; L.n_tiles = nt; L.n_blk = nb; L.n_slices = slices; L.one_seg_per_blk = 1; L.fused = 1;
+    L.obs = obs.data(); L.tile_off = tile_off.data(); L.tile_depth = tile_depth.data(); L.seg_len = seg_len.data(); L.seg_blk = seg_blk.data();
+    L.seg_cam = blk_cam.data(); L.blk_cam = blk_cam.data(); L.blk_view = blk_view.data(); L.blk_orig = blk_orig.data();
+    L.blk_seg_off = blk_seg_off.data(); L.blk_vfree = blk_vfree.data();
+    const double* ox = d.board_n > 0 ? d.board_x : d.obj_x;
+    const double* oy = d.board_n > 0 ? d.board_y : d.obj_y;
+    simt::launch((unsigned)nt, 128, [&] { k_repack(L, ox, oy, d.img_u, d.img_v, seg_src.data(), d.board_n); });
+    // K1 with per-block outputs (zero-initialised, as cal_refine_create leaves them: held views and padding stay zero)
+    const int PIe = std::max(S.PI, 1);
+    std::vector<double> cam_sums((size_t)S.n_cams * S.NV, 0.0), bHvv((size_t)21 * nb, 0.0), bgv((size_t)6 * nb, 0.0), bEvc((size_t)36 * nb, 0.0),
+        bEvi((size_t)6 * PIe * nb, 0.0);
+    EvalBuffers B;
+    B.blk_Hvv = bHvv.data(); B.blk_gv = bgv.data(); B.blk_Evc = bEvc.data(); B.blk_Evi = bEvi.data();
+    int n_roles = 0;
+    if (S.model == 0 && S.imode == 0) views_pass_t<0, 0>(S, L, x, M.n_amb, cam_sums, B, &n_roles);
+    else if (S.model == 0 && S.imode == 1) views_pass_t<0, 1>(S, L, x, M.n_amb, cam_sums, B, &n_roles);
+    else if (S.model == 0 && S.imode == 2) views_pass_t<0, 2>(S, L, x, M.n_amb, cam_sums, B, &n_roles);
+    else if (S.model == 1 && S.imode == 0) views_pass_t<1, 0>(S, L, x, M.n_amb, cam_sums, B, &n_roles);
+    else if (S.model == 1 && S.imode == 1) views_pass_t<1, 1>(S, L, x, M.n_amb, cam_sums, B, &n_roles);
+    else views_pass_t<1, 2>(S, L, x, M.n_amb, cam_sums, B, &n_roles);
+    double c = 0; for (int k = 0; k < S.n_cams; ++k) c += cam_sums[(size_t)k * S.NV + S.NE];
+    *cost = c;
+    // k_view_gather over the view -> device-block CSR
+    std::vector<int32_t> off(nv + 1, 0), idx;
+    for (int64_t b = 0; b < nb; ++b) if (blk_orig[b] >= 0) off[blk_view[b] + 1]++;
+    for (int v = 0; v < nv; ++v) off[v + 1] += off[v];
+    idx.resize(off[nv]);
+    { std::vector<int32_t> cur(off.begin(), off.end() - 1); for (int64_t b = 0; b < nb; ++b) if (blk_orig[b] >= 0) idx[cur[blk_view[b]]++] = (int32_t)b; }
+    std::vector<double> Hpp((size_t)nv * 36, 0.0), gp((size_t)nv * 6, 0.0);
+    ViewBuffers V;
+    V.view_blk_off = off.data(); V.view_blk_idx = idx.data(); V.view_free = vfree.data(); V.Hpp = Hpp.data(); V.gp = gp.data();
+    simt::launch((unsigned)((nv + 127) / 128), 128, [&] { k_view_gather(S, L, B, V); });
+    std::vector<double> Hss, gs, Hd, gd;
+    M.assemble_shared(cam_sums.data(), x, Hss, gs);
+    std::vector<char> vf(vfree.begin(), vfree.end());
+    M.assemble_dense(Hss, gs, Hpp.data(), gp.data(), bEvc.data(), bEvi.data(), nb, vf.data(), off.data(), idx.data(), blk_cam.data(), Hd, gd);
+    std::memcpy(g, gd.data(), gd.size() * sizeof(double));
+    std::memcpy(H, Hd.data(), Hd.size() * sizeof(double));
+    if (n_roles_out) *n_roles_out = n_roles;
+    return 0;
+}

@@ -7,8 +7,6 @@
 #define SIMT_SHARED_STORAGE static
 #include "simt_shim.hpp"
 
-inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
-
 #include "../../calibration_b200/csrc/refine_schur_kernels.cuh"
 
 using namespace calk;

@@ -345,8 +345,8 @@ K1_SO = os.path.join(ROOT, "tests", "host_emul", "_build", "libk1_simt.so")
 @pytest.fixture(scope="module")
 def k1_simt():
     deps = [K1_SRC, os.path.join(ROOT, "tests", "host_emul", "simt_shim.hpp")] + [
-        os.path.join(CSRC, f) for f in ("k1_kernel.cuh", "k1_roles.hpp", "k1_math.cuh", "refine_kernels.cuh", "refine_setup_kernels.cuh", "refine_model.hpp")] + [
-        os.path.join(ROOT, "include", "calib_b200.h")]
+        os.path.join(CSRC, f) for f in ("k1_kernel.cuh", "k1_roles.hpp", "k1_math.cuh", "refine_kernels.cuh", "refine_setup_kernels.cuh", "refine_schur_kernels.cuh",
+                                       "refine_model.hpp")] + [os.path.join(ROOT, "include", "calib_b200.h")]
     if not os.path.exists(K1_SO) or any(os.path.getmtime(d) > os.path.getmtime(K1_SO) for d in deps):
         os.makedirs(os.path.dirname(K1_SO), exist_ok=True)
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -357,6 +357,7 @@ def k1_simt():
     L.simt_bundle_eval.argtypes = [C.POINTER(abi.ProblemDesc), dp, dp, dp, dp, abi.c_int32_p, abi.c_int32_p]
     L.simt_tangent_count.restype = C.c_int64
     L.simt_tangent_count.argtypes = [C.POINTER(abi.ProblemDesc)]
+    L.simt_views_eval.argtypes = [C.POINTER(abi.ProblemDesc), dp, dp, dp, dp, abi.c_int32_p]
     return L
 
 
@@ -413,6 +414,35 @@ def test_repack_kernel_shared_board_form_is_bitwise_the_per_observation_form(k1_
     prob.x[100] += 1e-9
     with pytest.raises(ValueError):
         prob.with_shared_board()
+
+
+VIEW_CASES = {
+    "intrinsics": lambda: synth.make_intrinsics()[:2],                                   # C1: 20 views, 9 x 6 board, one role pair
+    "intrinsics_skew": lambda: synth.make_intrinsics(optimize_skew=True)[:2],
+    "intrinsics_no_loss": lambda: synth.make_intrinsics(huber_delta=-1.0)[:2],
+    "intrinsics_scheimpflug": lambda: synth.make_intrinsics(model=abi.MODEL_SCHEIMPFLUG_BC5)[:2],   # three roles; the pass itself is well defined
+    "extrinsics": lambda: synth.make_extrinsics(n_views=24)[:2],                          # 2 cameras: camera 0 and view 0 are the gauge
+    "extrinsics_ragged": lambda: synth.make_extrinsics(n_views=21, drop_fraction=0.3)[:2],
+    "extrinsics_fixed_intrinsics": lambda: synth.make_extrinsics(n_views=20, optimize_intrinsics=False)[:2],
+    "extrinsics_poses_only_three_cams": lambda: synth.make_extrinsics(n_cams=3, n_views=16, optimize_intrinsics=False)[:2],
+}
+
+
+@pytest.mark.parametrize("name", sorted(VIEW_CASES))
+def test_k1_view_store_epilogue_and_gather_match_oracle(k1_simt, name):
+    """The kinds with per-view pose blocks: K1's VIEW_STORE epilogue (per-block H_vv, g_v, E_vc = Q T_c, E_vi through the
+    chain rule T_b) and k_view_gather under the shim, assembled densely by the product's host model — cost, gradient and
+    the full tangent-space normal matrix against the oracle's forward-mode evaluation."""
+    prob, x0 = VIEW_CASES[name]()
+    c_o, g_o, H_o = O.refine_eval(prob, x0)
+    n = k1_simt.simt_tangent_count(C.byref(prob.desc))
+    assert n == len(g_o)
+    cost = C.c_double(); g = np.zeros(n); H = np.zeros((n, n)); roles = C.c_int32()
+    assert k1_simt.simt_views_eval(C.byref(prob.desc), abi.dptr(abi.as_f64(x0)), C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g), abi.dptr(H),
+                                   C.byref(roles)) == 0
+    assert abs(cost.value - c_o) <= 1e-12 * abs(c_o)
+    assert np.abs(g - g_o).max() <= 1e-10 * np.abs(g_o).max()
+    assert np.abs(H - H_o).max() <= 1e-10 * np.abs(H_o).max()
 
 
 def test_k1_source_ragged_blocks(k1_simt):
