@@ -102,19 +102,20 @@ inline void mbar_wait(const unsigned long long* b, unsigned long long completion
 inline void named_barrier(int /*n_threads: the whole CTA*/) { tl_cta->bar.arrive_and_wait(); }
 
 // Runs `kernel()` for every thread of every CTA of the grid.  The CTA size must be a multiple of 32.
-inline void launch(unsigned grid, unsigned block, const std::function<void()>& kernel);
+inline void launch(unsigned grid, unsigned block, const std::function<void()>& kernel, unsigned grid_y = 1);
 
 }  // namespace simt
 
 inline thread_local simt::Dim3 threadIdx, blockIdx, blockDim, gridDim;
 
-inline void simt::launch(unsigned grid, unsigned block, const std::function<void()>& kernel) {
+inline void simt::launch(unsigned grid, unsigned block, const std::function<void()>& kernel, unsigned grid_y) {
+    for (unsigned by = 0; by < grid_y; ++by)
     for (unsigned b = 0; b < grid; ++b) {
         Cta cta((int)block);
         std::vector<std::thread> th;
         for (unsigned t = 0; t < block; ++t)
             th.emplace_back([&, t] {
-                threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
+                threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid; blockIdx.y = by; gridDim.y = grid_y;
                 tl_cta = &cta; tl_warp = cta.warps[t / 32].get(); tl_lane = (int)(t % 32);
                 kernel();
                 tl_warp->bar.arrive_and_drop();   // a lane that has left the kernel no longer takes part in rendezvous

@@ -582,3 +582,57 @@ def test_k2_source_flags_a_rank_deficient_view(k2_simt):
                               abi.i32ptr(P["ct"]), abi.i32ptr(P["ci"]), *[abi.dptr(a) for a in arrs], ns, abi.dptr(ss), abi.dptr(Hsd), abi.dptr(gss), 1e4,
                               abi.dptr(Cm), abi.dptr(c), abi.dptr(ys), abi.dptr(dlt), abi.dptr(red), abi.i32ptr(fail), abi.dptr(sp))
     assert rc == 0 and fail[0] == 1
+
+
+# segment layout (small problems) under the same shim
+# ---------------------------------------------------------------------------
+SEG_SRC = os.path.join(ROOT, "tests", "host_emul", "seg_simt.cpp")
+SEG_SO = os.path.join(ROOT, "tests", "host_emul", "_build", "libseg_simt.so")
+
+
+@pytest.fixture(scope="module")
+def seg_simt():
+    deps = [SEG_SRC, os.path.join(ROOT, "tests", "host_emul", "simt_shim.hpp"), os.path.join(ROOT, "include", "calib_b200.h")] + [
+        os.path.join(CSRC, f) for f in ("k1_kernel.cuh", "k1_roles.hpp", "k1_math.cuh", "refine_kernels.cuh", "refine_setup_kernels.cuh",
+                                       "refine_schur_kernels.cuh", "refine_assemble_kernels.cuh", "refine_model.hpp")]
+    if not os.path.exists(SEG_SO) or any(os.path.getmtime(d) > os.path.getmtime(SEG_SO) for d in deps):
+        os.makedirs(os.path.dirname(SEG_SO), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([cxx, "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-I/usr/local/cuda/include", "-o", SEG_SO, SEG_SRC],
+                       check=True)
+    L = C.CDLL(SEG_SO)
+    dp = abi.c_double_p
+    L.simt_segment_eval.argtypes = [C.POINTER(abi.ProblemDesc), dp, C.c_int, C.c_int, dp, dp, dp, abi.c_int32_p]
+    L.simt_seg_tangent_count.restype = C.c_int64
+    L.simt_seg_tangent_count.argtypes = [C.POINTER(abi.ProblemDesc)]
+    return L
+
+
+SEG_CASES = {   # (problem, corners per segment, columns per reduction chunk)
+    "c1_intrinsics": (lambda: synth.make_intrinsics()[:2], 8, 8192),                       # BASELINE configs[0]: 54 corners -> 7 segments per view
+    "c1_intrinsics_skew_small_chunks": (lambda: synth.make_intrinsics(n_views=12, optimize_skew=True)[:2], 8, 48),
+    "c3_extrinsics": (lambda: synth.make_extrinsics(n_views=24)[:2], 8, 8192),              # configs[2] shape: 88 corners -> 11 segments
+    "extrinsics_ragged_one_segment": (lambda: synth.make_extrinsics(n_views=21, drop_fraction=0.3)[:2], 88, 64),
+    "extrinsics_fixed_intrinsics": (lambda: synth.make_extrinsics(n_views=20, optimize_intrinsics=False)[:2], 8, 100),
+    "bundle": (lambda: synth.make_bundle(n_cams=2, n_poses=12)[:2], 8, 8192),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SEG_CASES))
+def test_segment_layout_source_matches_oracle(seg_simt, name):
+    """The layout small problems run (residual blocks cut into segments of 8-27 corners): K1's NOT_FUSED epilogue, the
+    per-block Huber weight over a block's segments, k_view_part's chain rule, and the chunked fixed-order column sums,
+    in the launch order of device_pass / launch_assemble — cost, gradient and normal matrix against the oracle."""
+    mk, target, chunk = SEG_CASES[name]
+    prob, x0 = mk()
+    c_o, g_o, H_o = O.refine_eval(prob, x0)
+    n = seg_simt.simt_seg_tangent_count(C.byref(prob.desc))
+    assert n == len(g_o)
+    cost = C.c_double(); g = np.zeros(n); H = np.zeros((n, n)); nseg = C.c_int32()
+    assert seg_simt.simt_segment_eval(C.byref(prob.desc), abi.dptr(abi.as_f64(x0)), target, chunk, C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g),
+                                      abi.dptr(H), C.byref(nseg)) == 0
+    if target < 54:
+        assert nseg.value > prob.desc.n_blocks          # blocks really are cut into several segments
+    assert abs(cost.value - c_o) <= 1e-12 * abs(c_o)
+    assert np.abs(g - g_o).max() <= 1e-10 * np.abs(g_o).max()
+    assert np.abs(H - H_o).max() <= 1e-10 * np.abs(H_o).max()
