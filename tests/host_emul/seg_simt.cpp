@@ -16,6 +16,7 @@ __attribute__((aligned(128))) unsigned char k1_smem[232448];
 #include "../../calibration_b200/csrc/refine_model.hpp"
 #include "../../calibration_b200/csrc/refine_setup_kernels.cuh"
 #include "../../calibration_b200/csrc/refine_schur_kernels.cuh"
+#include "../../calibration_b200/csrc/refine_cost_kernel.cuh"   // k_cost with the per-warp TMA ring of tile_stage.cuh
 // k_colsum's 8-double scratch is the only static shared array used here: one CTA runs at a time, so a plain static serves
 #undef __shared__
 #define __shared__ static
@@ -64,8 +65,9 @@ void view_part(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B) 
 
 // target_len: corners per segment (cal_refine_create uses min(max(8, n_obs / 65536), longest block)); chunk: columns per
 // k_colsum CTA (8192 in the product; small values exercise several chunks per camera)
-extern "C" int simt_segment_eval(const cal_problem_desc* dp, const double* x, int target_len, int chunk, double* cost, double* g, double* H,
-                                 int32_t* n_segments_out) {
+// cost_only != 0: the residual-only pass (k_cost); g then receives the per-block sums of squared residuals (n_blocks values)
+extern "C" int simt_segment_eval(const cal_problem_desc* dp, const double* x, int target_len, int chunk, int cost_only, double* cost, double* g,
+                                 double* H, int32_t* n_segments_out) {
     const cal_problem_desc& d = *dp;
     HostModel M; M.init_model(d);
     const ProblemShape& S = M.S;
@@ -128,17 +130,32 @@ extern "C" int simt_segment_eval(const cal_problem_desc* dp, const double* x, in
     B.seg_ssr = seg_ssr.data(); B.blk_ssr = blk_ssr.data(); B.partial = partial.data(); B.partial_blk = partial_blk.data(); B.cam_sums = cam_sums.data();
     B.blk_w = blk_w.data(); B.seg_w = seg_w.data(); B.blk_rows = blk_rows.data(); B.blk_Hvv = bHvv.data(); B.blk_gv = bgv.data(); B.blk_Evc = bEvc.data();
     B.blk_Evi = bEvi.data();
-    // device_pass(jacobian): setup, K1, launch_assemble
     const int64_t n = std::max<int64_t>(nb, S.n_cams);
     simt::launch((unsigned)((n + 127) / 128), 128, [&] { k_block_setup(S, L, B); });
-    K1Args P{L, B, S.huber_delta, 0};
-    DISPATCH(k1_not_fused, P);
     const unsigned gb = (unsigned)((nb + 127) / 128);
     const int rr_row = S.NL * S.NC - S.NC * (S.NC - 1) / 2;
+    const ColChunk* scp = sc.data(); const ColChunk* bcp = bc.data();
+    if (cost_only) {
+        // device_pass(residual only): k_cost, then launch_assemble(jac = 0): block weight from seg_ssr, one block-indexed row
+        if (4 * kWarpStageBytes > (int)sizeof k1_smem) std::abort();
+        if (S.model == 0) simt::launch((unsigned)((nt + 3) / 4), 128, [&] { k_cost<0>(L, B); });
+        else simt::launch((unsigned)((nt + 3) / 4), 128, [&] { k_cost<1>(L, B); });
+        simt::launch(gb, 128, [&] { k_block_weight<0>(S, L, B, rr_row); });
+        std::vector<double> pb((size_t)std::max<size_t>(bc.size(), 1)), cs((size_t)S.n_cams, 0.0);
+        simt::launch((unsigned)bc.size(), 256, [&] { k_colsum<false>(B.blk_rows, L.n_blk, nullptr, bcp, pb.data(), 1); }, 1u);
+        simt::launch((unsigned)((S.n_cams + 127) / 128), 128, [&] { k_final_reduce(pb.data(), bo.data(), S.n_cams, 1, cs.data(), 1, 0); });
+        double c = 0; for (int k = 0; k < S.n_cams; ++k) c += cs[k];
+        *cost = c;
+        for (int64_t b = 0; b < nb; ++b) if (blk_orig[b] >= 0) g[blk_orig[b]] = blk_ssr[b];   // per-block sum of squares, in the caller's block order
+        if (n_segments_out) *n_segments_out = (int32_t)nseg_used;
+        return 0;
+    }
+    // device_pass(jacobian): setup, K1, launch_assemble
+    K1Args P{L, B, S.huber_delta, 0};
+    DISPATCH(k1_not_fused, P);
     simt::launch(gb, 128, [&] { k_block_weight<1>(S, L, B, rr_row); });
     const bool has_view_part = bundle ? S.view_free_global != 0 : S.n_views > 0;
     if (has_view_part) DISPATCH(view_part, S, L, B);
-    const ColChunk* scp = sc.data(); const ColChunk* bcp = bc.data();
     simt::launch((unsigned)sc.size(), 256, [&] { k_colsum<true>(B.segN, L.n_seg, B.seg_w, scp, B.partial, S.NE); }, (unsigned)S.NE);
     simt::launch((unsigned)((S.n_cams * S.NE + 127) / 128), 128, [&] { k_final_reduce(B.partial, so.data(), S.n_cams, S.NE, B.cam_sums, S.NV, 0); });
     simt::launch((unsigned)bc.size(), 256, [&] { k_colsum<false>(B.blk_rows, L.n_blk, nullptr, bcp, B.partial_blk, n_brows); }, (unsigned)n_brows);

@@ -594,7 +594,7 @@ SEG_SO = os.path.join(ROOT, "tests", "host_emul", "_build", "libseg_simt.so")
 def seg_simt():
     deps = [SEG_SRC, os.path.join(ROOT, "tests", "host_emul", "simt_shim.hpp"), os.path.join(ROOT, "include", "calib_b200.h")] + [
         os.path.join(CSRC, f) for f in ("k1_kernel.cuh", "k1_roles.hpp", "k1_math.cuh", "refine_kernels.cuh", "refine_setup_kernels.cuh",
-                                       "refine_schur_kernels.cuh", "refine_assemble_kernels.cuh", "refine_model.hpp")]
+                                       "refine_schur_kernels.cuh", "refine_assemble_kernels.cuh", "refine_cost_kernel.cuh", "tile_stage.cuh", "refine_model.hpp")]
     if not os.path.exists(SEG_SO) or any(os.path.getmtime(d) > os.path.getmtime(SEG_SO) for d in deps):
         os.makedirs(os.path.dirname(SEG_SO), exist_ok=True)
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -602,7 +602,7 @@ def seg_simt():
                        check=True)
     L = C.CDLL(SEG_SO)
     dp = abi.c_double_p
-    L.simt_segment_eval.argtypes = [C.POINTER(abi.ProblemDesc), dp, C.c_int, C.c_int, dp, dp, dp, abi.c_int32_p]
+    L.simt_segment_eval.argtypes = [C.POINTER(abi.ProblemDesc), dp, C.c_int, C.c_int, C.c_int, dp, dp, dp, abi.c_int32_p]
     L.simt_seg_tangent_count.restype = C.c_int64
     L.simt_seg_tangent_count.argtypes = [C.POINTER(abi.ProblemDesc)]
     return L
@@ -629,10 +629,34 @@ def test_segment_layout_source_matches_oracle(seg_simt, name):
     n = seg_simt.simt_seg_tangent_count(C.byref(prob.desc))
     assert n == len(g_o)
     cost = C.c_double(); g = np.zeros(n); H = np.zeros((n, n)); nseg = C.c_int32()
-    assert seg_simt.simt_segment_eval(C.byref(prob.desc), abi.dptr(abi.as_f64(x0)), target, chunk, C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g),
+    assert seg_simt.simt_segment_eval(C.byref(prob.desc), abi.dptr(abi.as_f64(x0)), target, chunk, 0, C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g),
                                       abi.dptr(H), C.byref(nseg)) == 0
     if target < 54:
         assert nseg.value > prob.desc.n_blocks          # blocks really are cut into several segments
     assert abs(cost.value - c_o) <= 1e-12 * abs(c_o)
     assert np.abs(g - g_o).max() <= 1e-10 * np.abs(g_o).max()
     assert np.abs(H - H_o).max() <= 1e-10 * np.abs(H_o).max()
+
+
+COST_CASES = {
+    "intrinsics_segments": (lambda: synth.make_intrinsics()[:2], 8),
+    "extrinsics_ragged": (lambda: synth.make_extrinsics(n_views=21, drop_fraction=0.3)[:2], 27),
+    "bundle_whole_blocks": (lambda: synth.make_bundle(n_cams=2, n_poses=24)[:2], 88),          # one segment per block: the fused layout's tiles, 11 chunks deep
+    "bundle_scheimpflug_no_loss": (lambda: synth.make_bundle(n_cams=2, n_poses=10, model=abi.MODEL_SCHEIMPFLUG_BC5, huber_delta=-1.0)[:2], 20),
+}
+
+
+@pytest.mark.parametrize("name", sorted(COST_CASES))
+def test_residual_only_pass_source_matches_oracle(seg_simt, name):
+    """k_cost — the pass every candidate step of the LM runs: the per-warp two-stage TMA ring of tile_stage.cuh (as a
+    memcpy plus completion counter here), projection and squared residual per corner, then the per-block Huber weight
+    from the segments' sums and the fixed-order cost reduction: cost and per-block sums of squares against the oracle."""
+    mk, target = COST_CASES[name]
+    prob, x0 = mk()
+    c_o, _, _ = O.refine_eval(prob, x0)
+    ssr_o = O.block_ssr(prob, x0)
+    cost = C.c_double(); ssr = np.zeros(prob.desc.n_blocks); nseg = C.c_int32()
+    assert seg_simt.simt_segment_eval(C.byref(prob.desc), abi.dptr(abi.as_f64(x0)), target, 8192, 1, C.cast(C.byref(cost), abi.c_double_p), abi.dptr(ssr),
+                                      None, C.byref(nseg)) == 0
+    assert abs(cost.value - c_o) <= 1e-12 * abs(c_o)
+    assert np.abs(ssr - ssr_o).max() <= 1e-12 * np.abs(ssr_o).max()
