@@ -242,6 +242,9 @@ auto optimize_extrinsics(const std::vector<MulticamPlanarView>& views, const std
         throw std::invalid_argument("Incompatible pose vector sizes for joint optimization");
     b200::Soa s;
     for (size_t v = 0; v < nv; ++v)
+        if (views[v].size() < nc)  // the reference indexes views[v][cam] for every camera (extrinsics.cpp:91-96)
+            throw std::invalid_argument("optimize_extrinsics: every MulticamPlanarView needs one PlanarView per camera");
+    for (size_t v = 0; v < nv; ++v)
         for (size_t c = 0; c < nc; ++c)
             if (!views[v][c].empty()) s.add(views[v][c], static_cast<int>(c), static_cast<int>(v));  // extrinsics.cpp:94-96
     cal_problem_desc d{};

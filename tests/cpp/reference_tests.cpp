@@ -528,6 +528,9 @@ TEST(Extrinsics, MismatchedPoseVectorsThrow) {  // src/estimation/optim/extrinsi
     StereoScene s({Eigen::Translation3d(0.0, 0.0, 5.0) * Eigen::Isometry3d::Identity()}, k_eight_points);
     EXPECT_THROW(optimize_extrinsics(s.views, s.cameras_gt, {Eigen::Isometry3d::Identity()}, s.target_gt), std::invalid_argument);
     EXPECT_THROW(optimize_extrinsics(s.views, s.cameras_gt, s.cam_gt, {}), std::invalid_argument);
+    auto short_views = s.views;
+    short_views[0].pop_back();  // a view that lists one camera only
+    EXPECT_THROW(optimize_extrinsics(short_views, s.cameras_gt, s.cam_gt, s.target_gt), std::invalid_argument);
 }
 
 // ---- tests/unit/handeye_test.cpp ------------------------------------------------------------------
