@@ -180,131 +180,7 @@ void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& 
 // ambient coordinates with the quaternion plus-Jacobians and un-scaled, straight into the dense
 // covariance in the reference's block order.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_cov_view_prep(ProblemShape S, DevLayout L, ViewBuffers V, int ns, const double* __restrict__ W,
-                                                      double* __restrict__ Z, double* __restrict__ G, double* __restrict__ Ainv) {
-    __shared__ double Y[6][kSyrkMaxN];
-    __shared__ double Lm[36];
-    const int v = blockIdx.x;
-    if (!V.view_free[v]) return;  // uniform
-    for (int i = threadIdx.x; i < 6 * kSyrkMaxN; i += 64) (&Y[0][0])[i] = 0.0;
-    if (threadIdx.x < 36) Lm[threadIdx.x] = V.Lp[(int64_t)v * 36 + threadIdx.x];
-    __syncthreads();
-    const int ncb = 6 + S.PI;
-    const int nb = V.view_blk_off[v + 1] - V.view_blk_off[v];
-    for (int idx = threadIdx.x; idx < nb * ncb * 6; idx += 64) {
-        const int kb = idx / (ncb * 6), rem = idx % (ncb * 6), i = rem / ncb, j = rem % ncb;
-        const int64_t b = V.view_blk_idx[V.view_blk_off[v] + kb];
-        const int col = shared_col(V, L.blk_cam[b], j);
-        if (col >= 0) Y[i][col] = V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b];  // each (view, camera) pair has one block: no collisions
-    }
-    __syncthreads();
-    // Z = L^-T Y, column by column
-    for (int c = threadIdx.x; c < ns; c += 64) {
-        double z[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) z[i] = Y[i][c];
-#pragma unroll
-        for (int i = 5; i >= 0; --i) { double s = z[i];
-#pragma unroll
-            for (int k = i + 1; k < 6; ++k) s -= Lm[6 * k + i] * z[k]; z[i] = s / Lm[7 * i]; }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { Y[i][c] = z[i]; Z[((int64_t)v * 6 + i) * ns + c] = z[i]; }
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < ns; c += 64) {
-        double g[6] = {0, 0, 0, 0, 0, 0};
-        for (int k = 0; k < ns; ++k) {
-            const double w = W[(int64_t)k * ns + c];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) g[i] = fma(Y[i][k], w, g[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) G[((int64_t)v * 6 + i) * ns + c] = g[i];
-    }
-    if (threadIdx.x < 6) {  // column j of A^-1 = L^-T L^-1 e_j
-        const int j = threadIdx.x;
-        double e[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) e[i] = i == j ? 1.0 : 0.0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { double s = e[i];
-#pragma unroll
-            for (int k = 0; k < i; ++k) s -= Lm[6 * i + k] * e[k]; e[i] = s / Lm[7 * i]; }
-#pragma unroll
-        for (int i = 5; i >= 0; --i) { double s = e[i];
-#pragma unroll
-            for (int k = i + 1; k < 6; ++k) s -= Lm[6 * k + i] * e[k]; e[i] = s / Lm[7 * i]; }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) Ainv[(int64_t)v * 36 + 6 * i + j] = e[i];
-    }
-}
-
-constexpr int kCovTile = 16, kCovK = 16;
-__global__ void __launch_bounds__(kCovTile * kCovTile) k_cov_vv(ProblemShape S, ViewBuffers V, const double* __restrict__ x, int ns,
-                                                                  const double* __restrict__ Z, const double* __restrict__ G,
-                                                                  const double* __restrict__ Ainv, double* __restrict__ cov, int64_t na) {
-    __shared__ double sG[kCovTile][6][kCovK + 1], sZ[kCovTile][6][kCovK + 1];
-    const int tv = threadIdx.x / kCovTile, tw = threadIdx.x % kCovTile;
-    const int v = blockIdx.y * kCovTile + tv, w = blockIdx.x * kCovTile + tw;
-    double c[36];
-#pragma unroll
-    for (int i = 0; i < 36; ++i) c[i] = 0.0;
-    for (int k0 = 0; k0 < ns; k0 += kCovK) {
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < kCovTile * 6 * kCovK; idx += kCovTile * kCovTile) {
-            const int t = idx / (6 * kCovK), rem = idx % (6 * kCovK), i = rem / kCovK, k = rem % kCovK;
-            const int vv = blockIdx.y * kCovTile + t, ww = blockIdx.x * kCovTile + t;
-            sG[t][i][k] = (vv < S.n_views && k0 + k < ns && V.view_free[vv]) ? G[((int64_t)vv * 6 + i) * ns + k0 + k] : 0.0;
-            sZ[t][i][k] = (ww < S.n_views && k0 + k < ns && V.view_free[ww]) ? Z[((int64_t)ww * 6 + i) * ns + k0 + k] : 0.0;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int k = 0; k < kCovK; ++k) {
-            double g[6], z[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) { g[i] = sG[tv][i][k]; z[i] = sZ[tw][i][k]; }
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-#pragma unroll
-                for (int j = 0; j < 6; ++j) c[6 * i + j] = fma(g[i], z[j], c[6 * i + j]);
-        }
-    }
-    if (v >= S.n_views || w >= S.n_views || !V.view_free[v] || !V.view_free[w]) return;  // constant blocks: zero rows / columns
-    if (v == w) {
-#pragma unroll
-        for (int i = 0; i < 36; ++i) c[i] += Ainv[(int64_t)v * 36 + i];
-    }
-    double sv[6], sw[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { sv[i] = V.sp[(int64_t)v * 6 + i]; sw[i] = V.sp[(int64_t)w * 6 + i]; }
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) c[6 * i + j] *= sv[i] * sw[j];
-    // ambient lift: rows / columns 0..2 through the quaternion plus-Jacobian (4x3), 3..5 unchanged
-    const double* qv = x + S.off_viewq + 4 * (int64_t)v; const double* qw = x + S.off_viewq + 4 * (int64_t)w;
-    const double Pv[12] = {-qv[1], -qv[2], -qv[3], qv[0], qv[3], -qv[2], -qv[3], qv[0], qv[1], qv[2], -qv[1], qv[0]};
-    const double Pw[12] = {-qw[1], -qw[2], -qw[3], qw[0], qw[3], -qw[2], -qw[3], qw[0], qw[1], qw[2], -qw[1], qw[0]};
-    double R[7][6];  // rows lifted: [quat(4); tran(3)] x tangent columns(6)
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a) R[a][j] = Pv[3 * a] * c[j] + Pv[3 * a + 1] * c[6 + j] + Pv[3 * a + 2] * c[12 + j];
-#pragma unroll
-        for (int a = 0; a < 3; ++a) R[4 + a][j] = c[6 * (3 + a) + j];
-    }
-    const int64_t rq = S.off_viewq + 4 * (int64_t)v, rt = S.off_viewt + 3 * (int64_t)v;
-    const int64_t cq = S.off_viewq + 4 * (int64_t)w, ct = S.off_viewt + 3 * (int64_t)w;
-#pragma unroll
-    for (int a = 0; a < 7; ++a) {
-        double* row = cov + (a < 4 ? rq + a : rt + a - 4) * na;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) row[cq + b] = R[a][0] * Pw[3 * b] + R[a][1] * Pw[3 * b + 1] + R[a][2] * Pw[3 * b + 2];
-#pragma unroll
-        for (int b = 0; b < 3; ++b) row[ct + b] = R[a][3 + b];
-    }
-}
-
+// (device code of k_cov_view_prep / k_cov_vv: refine_schur_kernels.cuh)
 void launch_cov_views(const ProblemShape& S, const DevLayout& L, const ViewBuffers& V, const double* x, int ns, const double* W,
                       double* Z, double* G, double* Ainv, double* cov, int64_t na, cudaStream_t st) {
     if (S.n_views == 0) return;

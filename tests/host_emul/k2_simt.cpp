@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE — the PRODUCT's K2 kernels (calibration_b200/csrc/refine_schur_kernels.cuh: k_view_gather,
-// k_view_scale, k_schur_factor, k_schur_syrk, k_schur_reduce, k_backsub, k_reduce_views) compiled by g++ and run on
+// k_view_scale, k_schur_factor, k_schur_syrk, k_schur_reduce, k_backsub, k_reduce_views, and the covariance pair
+// k_cov_view_prep / k_cov_vv) compiled by g++ and run on
 // the CPU under the lock-step SIMT shim, launched in the order and with the grids of one LM iteration of
 // cal_refine_solve (refine_host.cu) / launch_schur (refine_kernels.cu).  Input: the per-residual-block products K1's
 // epilogue stores for the per-view kinds (H_vv, g_v, E_vc, E_vi) and the damped, Jacobi-scaled shared block; output:
@@ -88,5 +89,70 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
     simt::launch(1, 1024, [&] { k_reduce_views(V, n_views); });
     std::memcpy(delta_p, dlt.data(), sizeof(double) * 6 * n_views);
     std::memcpy(red_out4, ro.data(), sizeof(double) * 4);
+    return 0;
+}
+
+// Block-structured covariance of the per-view kinds (cal_refine_solve's covariance branch): launch_schur with an
+// infinite radius, W = (S Hss S - C)^-1 on the host, k_cov_view_prep, k_cov_vv.  The parameter vector of this harness
+// holds the view blocks only: x = [quat(4) x n_views | tran(3) x n_views], so cov_vv is (7 n_views)^2.
+// Hss_scaled: the UNDAMPED scaled shared block.  Outputs: W [ns][ns], Z and G [n_views][6][ns], Ainv [n_views][36].
+extern "C" int simt_k2_cov(int n_views, int n_cams, int PI, int64_t n_blk, const int32_t* blk_cam, const int32_t* blk_view,
+                           const int32_t* view_free, const int32_t* cam_col_q, const int32_t* cam_col_t, const int32_t* cam_col_i,
+                           const double* blk_Hvv, const double* blk_gv, const double* blk_Evc, const double* blk_Evi, int ns,
+                           const double* s_shared, const double* Hss_scaled, const double* view_quats, double* W_out, double* Z_out,
+                           double* G_out, double* Ainv_out, double* cov_vv) {
+    if (ns + 1 > kSyrkMaxN) return 2;
+    ProblemShape S{};
+    S.n_views = n_views; S.n_cams = n_cams; S.PI = PI; S.off_viewq = 0; S.off_viewt = 4 * n_views;
+    const int64_t na_amb = 7 * (int64_t)n_views;
+    DevLayout L;
+    L.n_blk = n_blk;
+    std::vector<int32_t> bcam(blk_cam, blk_cam + n_blk);
+    L.blk_cam = bcam.data();
+    EvalBuffers B;
+    B.blk_Hvv = const_cast<double*>(blk_Hvv); B.blk_gv = const_cast<double*>(blk_gv);
+    B.blk_Evc = const_cast<double*>(blk_Evc); B.blk_Evi = const_cast<double*>(blk_Evi);
+    std::vector<int32_t> off(n_views + 1, 0), idx(n_blk), vfree(view_free, view_free + n_views), cq(cam_col_q, cam_col_q + n_cams),
+        ct(cam_col_t, cam_col_t + n_cams), ci(cam_col_i, cam_col_i + n_cams);
+    for (int64_t b = 0; b < n_blk; ++b) off[blk_view[b] + 1]++;
+    for (int v = 0; v < n_views; ++v) off[v + 1] += off[v];
+    { std::vector<int32_t> cur(off.begin(), off.end() - 1); for (int64_t b = 0; b < n_blk; ++b) idx[cur[blk_view[b]]++] = (int32_t)b; }
+    const int n_cta = schur_ctas(n_views), na = ns + 1, ncb = 6 + PI;
+    std::vector<double> Hpp((size_t)n_views * 36), gp((size_t)n_views * 6), sp((size_t)n_views * 6, 0.0), dp((size_t)n_views * 6), Lp((size_t)n_views * 36),
+        view_f((size_t)n_views * 6), blk_F((size_t)6 * ncb * n_blk, 0.0), ss(s_shared, s_shared + ns), Cm((size_t)ns * ns), cv(std::max(ns, 1)),
+        partialC((size_t)n_cta * na * na), x(na_amb, 0.0);
+    std::memcpy(x.data(), view_quats, sizeof(double) * 4 * n_views);
+    int32_t failed = 0;
+    ViewBuffers V;
+    V.view_blk_off = off.data(); V.view_blk_idx = idx.data(); V.view_free = vfree.data();
+    V.cam_col_q = cq.data(); V.cam_col_t = ct.data(); V.cam_col_i = ci.data();
+    V.Hpp = Hpp.data(); V.gp = gp.data(); V.sp = sp.data(); V.dp = dp.data(); V.Lp = Lp.data(); V.view_f = view_f.data(); V.blk_F = blk_F.data();
+    V.s_shared = ss.data(); V.C = Cm.data(); V.c = cv.data(); V.partialC = partialC.data(); V.fail = &failed;
+    simt::launch((unsigned)((n_views + 127) / 128), 128, [&] { k_view_gather(S, L, B, V); });
+    simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 1); });
+    // launch_schur(radius = infinity): undamped factors L_v and F_b = L_v^-1 E_b stay in V
+    simt::launch((unsigned)((n_views + 63) / 64), 64, [&] { k_schur_factor(S, L, B, V, 0.0); });
+    const int per = (n_views + n_cta - 1) / n_cta, nt = (na + kSyrkTile - 1) / kSyrkTile, threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
+    simt::launch((unsigned)n_cta, (unsigned)threads, [&] { k_schur_syrk(S, L, V, ns, per); });
+    simt::launch((unsigned)((na * na + 127) / 128), 128, [&] { k_schur_reduce(V, n_cta, ns); });
+    if (failed) return 4;
+    // host: W = (S Hss S - C)^-1, column by column (cal_refine_solve does the same with chol_host / chol_solve_host)
+    std::vector<double> Sm((size_t)ns * ns), W((size_t)ns * ns), e(std::max(ns, 1));
+    for (int i = 0; i < ns; ++i) for (int j = 0; j < ns; ++j) Sm[(size_t)i * ns + j] = Hss_scaled[(size_t)i * ns + j] - Cm[(size_t)i * ns + j];
+    for (int j = 0; j < ns; ++j) {
+        std::fill(e.begin(), e.end(), 0.0); e[j] = 1.0;
+        if (!solve_spd(Sm, ns, e.data())) return 3;
+        for (int i = 0; i < ns; ++i) W[(size_t)i * ns + j] = e[i];
+    }
+    std::vector<double> Z((size_t)n_views * 6 * std::max(ns, 1), 0.0), G((size_t)n_views * 6 * std::max(ns, 1), 0.0), Ainv((size_t)n_views * 36, 0.0),
+        cov((size_t)na_amb * na_amb, 0.0);
+    simt::launch((unsigned)n_views, 64, [&] { k_cov_view_prep(S, L, V, ns, W.data(), Z.data(), G.data(), Ainv.data()); });
+    const unsigned t = (unsigned)((n_views + kCovTile - 1) / kCovTile);
+    simt::launch(t, kCovTile * kCovTile, [&] { k_cov_vv(S, V, x.data(), ns, Z.data(), G.data(), Ainv.data(), cov.data(), na_amb); }, t);
+    std::memcpy(W_out, W.data(), sizeof(double) * ns * ns);
+    std::memcpy(Z_out, Z.data(), sizeof(double) * (size_t)n_views * 6 * ns);
+    std::memcpy(G_out, G.data(), sizeof(double) * (size_t)n_views * 6 * ns);
+    std::memcpy(Ainv_out, Ainv.data(), sizeof(double) * (size_t)n_views * 36);
+    std::memcpy(cov_vv, cov.data(), sizeof(double) * na_amb * na_amb);
     return 0;
 }

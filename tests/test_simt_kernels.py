@@ -479,6 +479,7 @@ def k2_simt():
     dp, ip = abi.c_double_p, abi.c_int32_p
     L.simt_k2_step.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, ip, ip, ip, ip, ip, ip, dp, dp, dp, dp, C.c_int, dp, dp, dp, C.c_double,
                                dp, dp, dp, dp, dp, ip, dp]
+    L.simt_k2_cov.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, ip, ip, ip, ip, ip, ip, dp, dp, dp, dp, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
     return L
 
 
@@ -660,3 +661,47 @@ def test_residual_only_pass_source_matches_oracle(seg_simt, name):
                                       None, C.byref(nseg)) == 0
     assert abs(cost.value - c_o) <= 1e-12 * abs(c_o)
     assert np.abs(ssr - ssr_o).max() <= 1e-12 * np.abs(ssr_o).max()
+
+
+@pytest.mark.parametrize("case", [dict(seed=11, n_views=19, PI=9, radius=1.0), dict(seed=12, n_views=40, PI=10, radius=1.0, fixed_views=(0, 7))])
+def test_covariance_kernels_source_matches_the_dense_inverse(k2_simt, case):
+    """Block-structured covariance of the per-view kinds (k_cov_view_prep, k_cov_vv after launch_schur with an infinite
+    radius): the view x view blocks of the inverse normal matrix, un-scaled and lifted to ambient coordinates with the
+    quaternion plus-Jacobian, against numpy's inverse of the whole dense system."""
+    P = _k2_problem(**case)
+    nv, ns, nf = P["n_views"], P["ns"], P["n_free"]
+    H = P["H"]
+    s = 1.0 / (1.0 + np.sqrt(np.diag(H)))
+    Hs = H * np.outer(s, s)
+    sh = slice(6 * nf, 6 * nf + ns)
+    ss = np.ascontiguousarray(s[sh]); Hss = np.ascontiguousarray(Hs[sh, sh])
+    rng = np.random.default_rng(case["seed"])
+    q = rng.normal(size=(nv, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    bcam = np.array([c for _, c in P["blocks"]], dtype=np.int32); bview = np.array([v for v, _ in P["blocks"]], dtype=np.int32)
+    W = np.zeros((ns, ns)); Z = np.zeros((nv, 6, ns)); G = np.zeros((nv, 6, ns)); Ainv = np.zeros((nv, 6, 6)); cov = np.zeros((7 * nv, 7 * nv))
+    arrs = [np.ascontiguousarray(P[k]) for k in ("Hvv", "gv", "Evc", "Evi")]
+    rc = k2_simt.simt_k2_cov(nv, P["n_cams"], P["PI"], len(bcam), abi.i32ptr(bcam), abi.i32ptr(bview), abi.i32ptr(P["view_free"]), abi.i32ptr(P["cq"]),
+                             abi.i32ptr(P["ct"]), abi.i32ptr(P["ci"]), *[abi.dptr(a) for a in arrs], ns, abi.dptr(ss), abi.dptr(Hss), abi.dptr(q),
+                             abi.dptr(W), abi.dptr(Z), abi.dptr(G), abi.dptr(Ainv), abi.dptr(cov))
+    assert rc == 0
+    Cs = np.linalg.inv(Hs)                       # scaled covariance; tangent covariance = s C s = inv(H)
+    Ct = np.linalg.inv(H)
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    assert rel(W, Cs[sh, sh]) < 1e-9
+    def plus_jacobian(qq):                        # d (dq * q) / d delta at delta = 0, dq = [1, delta] (Ceres QuaternionManifold)
+        w, x, y, z = qq
+        return np.array([[-x, -y, -z], [w, z, -y], [-z, w, x], [y, -x, w]])
+    exp = np.zeros_like(cov)
+    for v, cv in P["pcol"].items():
+        assert rel(Z[v], -Cs[cv:cv + 6, sh] @ np.linalg.inv(Cs[sh, sh])) < 1e-8      # C_vs = -Z_v W
+        Jv = np.zeros((7, 6)); Jv[:4, :3] = plus_jacobian(q[v]); Jv[4:, 3:] = np.eye(3)
+        rows = np.r_[4 * v + np.arange(4), 4 * nv + 3 * v + np.arange(3)]
+        for w_, cw in P["pcol"].items():
+            Jw = np.zeros((7, 6)); Jw[:4, :3] = plus_jacobian(q[w_]); Jw[4:, 3:] = np.eye(3)
+            cols = np.r_[4 * w_ + np.arange(4), 4 * nv + 3 * w_ + np.arange(3)]
+            exp[np.ix_(rows, cols)] = Jv @ Ct[cv:cv + 6, cw:cw + 6] @ Jw.T
+    assert rel(cov, exp) < 1e-8
+    held = np.flatnonzero(P["view_free"] == 0)
+    for v in held:                                 # held views: zero rows and columns
+        rows = np.r_[4 * v + np.arange(4), 4 * nv + 3 * v + np.arange(3)]
+        assert np.all(cov[rows] == 0.0) and np.all(cov[:, rows] == 0.0)
