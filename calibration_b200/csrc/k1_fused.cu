@@ -93,27 +93,7 @@ int k1_num_passes(const ProblemShape& S) { int r = 1; k1_tile_value_map(S, &r, n
 // ---------------------------------------------------------------------------
 // per-camera sums of the per-tile rows (fixed order, no atomics)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_tile_colsum(const double* __restrict__ tile_vals, int nvt,
-                                                     const ColChunk* __restrict__ chunks, double* __restrict__ partial) {
-    const ColChunk c = chunks[blockIdx.x];
-    for (int v = threadIdx.x; v < nvt; v += 256) {
-        double a = 0.0;
-        for (int64_t t = c.begin; t < c.end; ++t) a += tile_vals[t * nvt + v];
-        partial[(int64_t)blockIdx.x * nvt + v] = a;
-    }
-}
-__global__ void __launch_bounds__(256) k_tile_final(const double* __restrict__ partial, const int32_t* __restrict__ cam_chunk_off, int n_cams,
-                                                    int nvt, const int32_t* __restrict__ vmap, double* __restrict__ cam_sums, int NV) {
-    // one warp per (camera, value): lanes stride over the camera's chunk partials, then a fixed shuffle tree
-    const int i = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (i >= n_cams * nvt) return;
-    const int cam = i / nvt, v = i % nvt;
-    double a = 0.0;
-    for (int c = cam_chunk_off[cam] + lane; c < cam_chunk_off[cam + 1]; c += 32) a += partial[(int64_t)c * nvt + v];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
-    if (lane == 0) cam_sums[(int64_t)cam * NV + vmap[v]] = a;
-}
+// (device code of k_tile_colsum / k_tile_final: k1_kernel.cuh)
 int launch_tile_reduce(const ProblemShape& S, const EvalBuffers& B, const ReduceDesc& R, int nvt, cudaStream_t st) {
     k_tile_colsum<<<R.n_tile_chunks, 256, 0, st>>>(B.tile_vals, nvt, R.tile_chunks, B.partial_tile);
     k_tile_final<<<(S.n_cams * nvt + 7) / 8, 256, 0, st>>>(B.partial_tile, R.tile_cam_chunk_off, S.n_cams, nvt, B.tile_vmap, B.cam_sums, S.NV);

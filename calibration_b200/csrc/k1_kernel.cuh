@@ -374,4 +374,29 @@ __global__ void __launch_bounds__(K1Roles<MODEL, IMODE>::NROLE * 32) k1_kernel(c
     if constexpr (RT::NROLE > 2) { if (role == 2) k1_role<MODEL, IMODE, 2, VIEW>(P, tile, lane, k1_smem); }
 }
 
+// ---------------------------------------------------------------------------
+// per-camera sums of the per-tile rows (fixed order, no atomics); launcher: k1_fused.cu
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tile_colsum(const double* __restrict__ tile_vals, int nvt,
+                                                     const ColChunk* __restrict__ chunks, double* __restrict__ partial) {
+    const ColChunk c = chunks[blockIdx.x];
+    for (int v = threadIdx.x; v < nvt; v += 256) {
+        double a = 0.0;
+        for (int64_t t = c.begin; t < c.end; ++t) a += tile_vals[t * nvt + v];
+        partial[(int64_t)blockIdx.x * nvt + v] = a;
+    }
+}
+__global__ void __launch_bounds__(256) k_tile_final(const double* __restrict__ partial, const int32_t* __restrict__ cam_chunk_off, int n_cams,
+                                                    int nvt, const int32_t* __restrict__ vmap, double* __restrict__ cam_sums, int NV) {
+    // one warp per (camera, value): lanes stride over the camera's chunk partials, then a fixed shuffle tree
+    const int i = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (i >= n_cams * nvt) return;
+    const int cam = i / nvt, v = i % nvt;
+    double a = 0.0;
+    for (int c = cam_chunk_off[cam] + lane; c < cam_chunk_off[cam + 1]; c += 32) a += partial[(int64_t)c * nvt + v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if (lane == 0) cam_sums[(int64_t)cam * NV + vmap[v]] = a;
+}
+
 }  // namespace calk

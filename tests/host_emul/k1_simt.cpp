@@ -4,8 +4,7 @@
 // fused epilogue with its padded transposes) compiled by g++ and run under the lock-step SIMT shim, followed by the
 // product's host assembly (refine_model.hpp).  The integer layout tables (device blocks sorted by camera, camera
 // groups padded to whole tiles of 32, tile depths and offsets) are built here the way cal_refine_create builds them
-// for the fused layout; the per-camera sums of the tile rows are taken directly instead of through
-// k_tile_colsum / k_tile_final.
+// for the fused layout; the per-camera sums of the tile rows go through k_tile_colsum / k_tile_final.
 #define CALIB_SIMT_SHIM 1
 #include "simt_shim.hpp"
 
@@ -20,6 +19,22 @@ __attribute__((aligned(128))) unsigned char k1_smem[232448];
 using namespace calk;
 
 namespace {
+
+// k_tile_colsum + k_tile_final (launch_tile_reduce, k1_fused.cu).  The product groups 32 tiles per chunk; one tile per
+// chunk here, so that k_tile_final's lane-strided sum over a camera's chunks and its shuffle tree see several chunks
+// per camera at test sizes.
+void tile_reduce(const ProblemShape& S, const DevLayout& L, const std::vector<double>& tile_vals, int nvt, const std::vector<int32_t>& vmap,
+                 std::vector<double>& cam_sums) {
+    std::vector<ColChunk> tc; std::vector<int32_t> to(S.n_cams + 1, 0);
+    for (int c = 0; c < S.n_cams; ++c) {
+        to[c] = (int32_t)tc.size();
+        for (int64_t t = 0; t < L.n_tiles; ++t) if (L.seg_cam[t * 32] == c) tc.push_back(ColChunk{c, 0, t, t + 1});
+    }
+    to[S.n_cams] = (int32_t)tc.size();
+    std::vector<double> partial(tc.size() * (size_t)nvt);
+    simt::launch((unsigned)tc.size(), 256, [&] { k_tile_colsum(tile_vals.data(), nvt, tc.data(), partial.data()); });
+    simt::launch((unsigned)((S.n_cams * nvt + 7) / 8), 256, [&] { k_tile_final(partial.data(), to.data(), S.n_cams, nvt, vmap.data(), cam_sums.data(), S.NV); });
+}
 
 // setup + K1 + per-camera sums of the tile rows for one (model, intrinsics mode) instantiation
 template <int MODEL, int IMODE>
@@ -41,10 +56,7 @@ void pass_t(const ProblemShape& S, const DevLayout& L, const double* x, int n_am
     if (K1Smem<MODEL, IMODE>::kBytes > (int)sizeof k1_smem) std::abort();
     if (reduce_rows) simt::launch((unsigned)L.n_tiles, RT::NROLE * 32, [&] { k1_kernel<MODEL, IMODE, VIEW_REDUCE>(P); });
     else simt::launch((unsigned)L.n_tiles, RT::NROLE * 32, [&] { k1_kernel<MODEL, IMODE, VIEW_NONE>(P); });
-    for (int64_t t = 0; t < L.n_tiles; ++t) {
-        double* sums = &cam_sums[(size_t)L.seg_cam[t * 32] * S.NV];
-        for (int j = 0; j < nvt; ++j) sums[vmap[j]] += tile_vals[(size_t)t * nvt + j];
-    }
+    tile_reduce(S, L, tile_vals, nvt, vmap, cam_sums);
     *n_roles = RT::NROLE;
 }
 
@@ -134,10 +146,7 @@ void views_pass_t(const ProblemShape& S, const DevLayout& L, const double* x, in
     K1Args P{L, B, S.huber_delta, nvt};
     if (K1Smem<MODEL, IMODE>::kBytes > (int)sizeof k1_smem) std::abort();
     simt::launch((unsigned)L.n_tiles, RT::NROLE * 32, [&] { k1_kernel<MODEL, IMODE, VIEW_STORE>(P); });
-    for (int64_t t = 0; t < L.n_tiles; ++t) {
-        double* sums = &cam_sums[(size_t)L.seg_cam[t * 32] * S.NV];
-        for (int j = 0; j < nvt; ++j) sums[vmap[j]] += tile_vals[(size_t)t * nvt + j];
-    }
+    tile_reduce(S, L, tile_vals, nvt, vmap, cam_sums);
     B.x = nullptr; B.camc = nullptr; B.camT = nullptr; B.seg_frame = nullptr; B.blk_Tv = nullptr; B.blk_ssr = nullptr; B.tile_vals = nullptr;
     *n_roles = RT::NROLE;
 }
