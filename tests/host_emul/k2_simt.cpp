@@ -156,3 +156,26 @@ extern "C" int simt_k2_cov(int n_views, int n_cams, int PI, int64_t n_blk, const
     std::memcpy(cov_vv, cov.data(), sizeof(double) * na_amb * na_amb);
     return 0;
 }
+
+// k_view_plus (candidate x [+] t delta_p per view, |dx|^2) and k_view_norms (|x_v|^2, max |x_v - plus(x_v, -g_v)|) with
+// k_reduce_views, as make_candidate / norms of cal_refine_solve launch them.  x = [quat(4) x n_views | tran(3) x n_views].
+extern "C" int simt_k2_plus_norms(int n_views, const double* x, const double* delta_p, const double* gp, const int32_t* view_free, double t,
+                                  double* x_cand, double* red_plus4, double* red_norms4) {
+    ProblemShape S{};
+    S.n_views = n_views; S.off_viewq = 0; S.off_viewt = 4 * n_views;
+    std::vector<double> xs(x, x + 7 * (size_t)n_views), xc(7 * (size_t)n_views, 0.0), dl(delta_p, delta_p + 6 * (size_t)n_views),
+        g(gp, gp + 6 * (size_t)n_views), red((size_t)n_views * 4, 0.0), ro(4, 0.0);
+    std::vector<int32_t> vfree(view_free, view_free + n_views);
+    EvalBuffers B; B.x = xs.data();
+    ViewBuffers V;
+    V.x_cand = xc.data(); V.delta_p = dl.data(); V.gp = g.data(); V.view_free = vfree.data(); V.red = red.data(); V.red_out = ro.data();
+    simt::launch((unsigned)((n_views + 127) / 128), 128, [&] { k_view_plus(S, B, V, t); });
+    simt::launch(1, 1024, [&] { k_reduce_views(V, n_views); });
+    std::memcpy(red_plus4, ro.data(), 4 * sizeof(double));
+    std::memcpy(x_cand, xc.data(), sizeof(double) * 7 * n_views);
+    std::fill(red.begin(), red.end(), 0.0);
+    simt::launch((unsigned)((n_views + 127) / 128), 128, [&] { k_view_norms(S, B, V); });
+    simt::launch(1, 1024, [&] { k_reduce_views(V, n_views); });
+    std::memcpy(red_norms4, ro.data(), 4 * sizeof(double));
+    return 0;
+}

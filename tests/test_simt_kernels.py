@@ -479,6 +479,7 @@ def k2_simt():
     dp, ip = abi.c_double_p, abi.c_int32_p
     L.simt_k2_step.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, ip, ip, ip, ip, ip, ip, dp, dp, dp, dp, C.c_int, dp, dp, dp, C.c_double,
                                dp, dp, dp, dp, dp, ip, dp]
+    L.simt_k2_plus_norms.argtypes = [C.c_int, dp, dp, dp, ip, C.c_double, dp, dp, dp]
     L.simt_k2_cov.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, ip, ip, ip, ip, ip, ip, dp, dp, dp, dp, C.c_int, dp, dp, dp, dp, dp, dp, dp, dp]
     return L
 
@@ -705,3 +706,37 @@ def test_covariance_kernels_source_matches_the_dense_inverse(k2_simt, case):
     for v in held:                                 # held views: zero rows and columns
         rows = np.r_[4 * v + np.arange(4), 4 * nv + 3 * v + np.arange(3)]
         assert np.all(cov[rows] == 0.0) and np.all(cov[:, rows] == 0.0)
+
+
+def _ceres_quaternion_plus(q, d):
+    """ceres::QuaternionManifold::Plus: x_plus = [cos|d|, sin|d| / |d| d] * x (Hamilton product, w first)"""
+    n = np.linalg.norm(d)
+    dq = np.array([1.0, 0, 0, 0]) if n == 0 else np.r_[np.cos(n), np.sin(n) / n * d]
+    w1, x1, y1, z1 = dq; w2, x2, y2, z2 = q
+    return np.array([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
+                     w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2])
+
+
+def test_view_plus_and_norms_kernels_match_the_ceres_manifold(k2_simt):
+    """k_view_plus / k_view_norms / k_reduce_views: the per-view part of the candidate point, of the step norm, of |x| and
+    of the projected-gradient max norm, against the QuaternionManifold formulas (un-normalised quaternions, as the LM keeps them)."""
+    rng = np.random.default_rng(21)
+    nv, t = 1100, 0.7                                   # more views than the 1024 threads of the reduction
+    q = rng.normal(size=(nv, 4)) * rng.uniform(0.8, 1.2, size=(nv, 1)); tr = rng.normal(size=(nv, 3))
+    x = np.r_[q.reshape(-1), tr.reshape(-1)]
+    delta = rng.normal(size=(nv, 6)) * 0.05; delta[3] = 0.0
+    gp = rng.normal(size=(nv, 6)) * 1e-3
+    vfree = np.ones(nv, dtype=np.int32); vfree[[0, 17]] = 0
+    xc = np.zeros(7 * nv); rp = np.zeros(4); rn = np.zeros(4)
+    assert k2_simt.simt_k2_plus_norms(nv, abi.dptr(x), abi.dptr(np.ascontiguousarray(delta)), abi.dptr(np.ascontiguousarray(gp)), abi.i32ptr(vfree), t,
+                                      abi.dptr(xc), abi.dptr(rp), abi.dptr(rn)) == 0
+    q_ref = np.array([_ceres_quaternion_plus(q[v], t * delta[v, :3]) for v in range(nv)])
+    t_ref = tr + t * delta[:, 3:]
+    assert np.abs(xc[:4 * nv].reshape(nv, 4) - q_ref).max() < 1e-15 and np.abs(xc[4 * nv:].reshape(nv, 3) - t_ref).max() < 1e-15
+    dx2 = ((q_ref - q) ** 2).sum() + ((t_ref - tr) ** 2).sum()
+    assert abs(rp[2] - dx2) <= 1e-12 * dx2
+    assert abs(rn[0] - (x ** 2).sum()) <= 1e-12 * (x ** 2).sum()
+    gm = 0.0
+    for v in np.flatnonzero(vfree):
+        gm = max(gm, np.abs(q[v] - _ceres_quaternion_plus(q[v], -gp[v, :3])).max(), np.abs(gp[v, 3:]).max())
+    assert abs(rn[3] - gm) <= 1e-12 * gm
