@@ -109,3 +109,37 @@ def test_the_real_library_is_back_afterwards():
         prob, _, _ = synth.make_bundle(n_cams=1, n_poses=8)
         with pytest.raises(capi.CalibCudaError):
             capi.RefineHandle(prob)
+
+
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_shared_board_form_through_the_product_host_code(product_on_cpu, monkeypatch, fused):
+    """cal_problem_desc.board_n > 0 through cal_refine_create itself — the staging-buffer arithmetic and copies of the
+    shared-board form, then k_repack — must give bit-identical passes to the per-observation form in both layouts."""
+    monkeypatch.setenv("CALIB_B200_FUSED", fused)
+    prob, x0, _ = synth.make_bundle(n_cams=2, n_poses=6)
+    out = []
+    for p in (prob, prob.with_shared_board()):
+        h = product_on_cpu.RefineHandle(p)
+        out.append(h.eval(x0) + (h.cost(x0),))
+        h.close()
+    (c, g, H, c1), (cb, gb, Hb, c1b) = out
+    assert c == cb and c1 == c1b and np.array_equal(g, gb) and np.array_equal(H, Hb)
+    pb = prob.with_shared_board()
+    pb.desc.board_n = 80
+    with pytest.raises(ValueError, match="exactly board_n"):
+        product_on_cpu.RefineHandle(pb)
+
+
+def test_every_parameter_block_frozen(product_on_cpu, monkeypatch):
+    """optimize_bundle with all three optimize_* flags false — Ceres finds no free parameter block and
+    returns CONVERGENCE after 0 iterations with final_cost = the fixed cost; the product's LM must do the same."""
+    monkeypatch.setenv("CALIB_B200_FUSED", "1")
+    prob, x0, _ = synth.make_bundle(n_cams=1, n_poses=8, optimize_intrinsics=False, optimize_hand_eye=False, optimize_target_pose=False)
+    h = product_on_cpu.RefineHandle(prob)
+    assert h.n_tan == 0
+    x, r, cov = h.solve(x0)
+    h.close()
+    x_o, r_o, _ = O.refine_solve(prob, x0)
+    assert r.success and r.iterations == 0 == r_o.iterations
+    assert abs(r.final_cost - r_o.final_cost) <= 1e-12 * r_o.final_cost and r.final_cost == r.initial_cost
+    assert np.array_equal(x, x0)
