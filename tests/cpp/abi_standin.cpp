@@ -49,17 +49,29 @@ static_assert(sizeof(cal_ransac_options) == sizeof(orc_ransac_options));
 static_assert(sizeof(cal_ransac_result) == sizeof(orc_ransac_result));
 static_assert(sizeof(cal_plane_ransac_result) == sizeof(orc_plane_result));
 
+// -DSTANDIN_NO_REFINE: the refinement entry points (and cal_last_error / cal_device_count) come from the CPU build of
+// the product's own host code and kernels (tests/host_emul/_build/libcalib_b200_simt.so, tests/test_product_on_cpu.py)
+// instead of the oracle; this file then only answers the linear stage and AX = XB.
+#ifdef STANDIN_NO_REFINE
+extern "C" void cal_set_last_error_(const char* msg);
+namespace {
+cal_status fail(cal_status s, const char* m) { cal_set_last_error_(m); return s; }
+}  // namespace
+#else
 namespace {
 thread_local std::string g_err;
 cal_status fail(cal_status s, const char* m) { g_err = m; return s; }
 }  // namespace
+#endif
 
+#ifndef STANDIN_NO_REFINE
 struct cal_refine_handle {
     cal_problem_desc d;
     std::vector<double> x, y, u, v, bTg;
     std::vector<int64_t> off;
     std::vector<int32_t> cam, view;
 };
+#endif
 struct cal_axxb_handle {
     std::vector<double> ra, rb, ta, tb;
     double huber;
@@ -67,6 +79,7 @@ struct cal_axxb_handle {
 
 extern "C" {
 
+#ifndef STANDIN_NO_REFINE
 const char* cal_last_error(void) { return g_err.c_str(); }
 int cal_device_count(void) { return 0; }
 
@@ -111,6 +124,8 @@ cal_status cal_refine_solve(cal_refine_handle* h, const cal_optim_options* o, do
     std::memcpy(r, &rr, sizeof rr);
     return rc == 0 ? CAL_OK : fail(CAL_ERR_RUNTIME, "oracle solve failed");
 }
+
+#endif  // STANDIN_NO_REFINE
 
 cal_status cal_axxb_create_from_poses(int64_t n, const double* bg, const double* ct, double min_angle_deg, int, double, double huber, int,
                                       cal_axxb_handle** out, int64_t* kept) {

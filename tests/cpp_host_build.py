@@ -63,6 +63,22 @@ def build_standin():
     return exe, dict(os.environ, LD_LIBRARY_PATH=os.pathsep.join([odir, sdir, os.environ.get("LD_LIBRARY_PATH", "")]))
 
 
+def build_product_on_cpu():
+    """reference_tests.cpp over the CPU build of the product's own refinement sources (tests/test_product_on_cpu.py):
+    cal_refine_* = refine_host.cu + the kernels under the shim; the linear stage as in build_standin; AX = XB from the oracle"""
+    import test_product_on_cpu
+    so = test_product_on_cpu._build()
+    _, env = build_standin()
+    odir, sdir = os.path.join(ROOT, "oracle", "_build"), os.path.join(EMUL, "_build")
+    exe = os.path.join(OUT, "host_tests_product")
+    standin = os.path.join(CPP, "abi_standin.cpp")
+    if _stale(exe, SOURCES + [standin, so]):
+        subprocess.run([CXX, *FLAGS, "-DSTANDIN_SIMT", "-DSTANDIN_NO_REFINE", "-I", os.path.join(ROOT, "oracle"), os.path.join(CPP, "reference_tests.cpp"),
+                        standin, "-o", exe, "-L", odir, "-loracle", "-L", sdir, "-lransac_simt", "-lseed_simt", "-lcalib_b200_simt", "-pthread",
+                        "-Wl,-rpath," + odir, "-Wl,-rpath," + sdir], check=True)
+    return exe, env
+
+
 EXAMPLE = os.path.join(ROOT, "examples", "cpp_adapter_example.cpp")
 
 

@@ -63,3 +63,15 @@ def test_cpp_example_of_the_adapter_builds_and_runs_over_the_standin():
     if capi.device_count() == 0:
         out = B.run(exe, env)
         assert out.returncode == 2 and "no CUDA device" in out.stdout
+
+
+def test_reference_unit_tests_on_the_adapter_over_the_products_own_host_code_and_kernels():
+    """A subset of the C++ tests with cal_refine_* answered by the product itself on the CPU — refine_host.cu compiled
+    against the host-only CUDA runtime stand-in, kernels under the SIMT shim (tests/test_product_on_cpu.py) — in the
+    adapter's default shared-board form: one test per refinement kind and model, plus the validation paths."""
+    exe, env = B.build_product_on_cpu()
+    names = ["RecoversIntrinsicsNoSkew", "SingleCameraHandEye", "RecoverAllParameters", "HandeyeWithFixedIntrinsics", "InputValidation",
+             "InsufficientViewsThrow", "MismatchedPoseVectorsThrow"]
+    out = B.run(exe, dict(env, CALIB_B200_FUSED="1"), *names, timeout=900)
+    ran, failed = _summary(out)
+    assert out.returncode == 0 and failed == 0 and ran == len(names), out.stdout[-4000:]
