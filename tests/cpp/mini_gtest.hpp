@@ -38,6 +38,7 @@ inline int run(int argc, char** argv) {
         else inc.emplace_back(argv[i]);
     }
     int ran = 0, failed = 0;
+    std::string failed_names;
     for (auto& c : cases()) {
         const std::string full = c.suite + "." + c.name;
         bool sel = inc.empty();
@@ -52,8 +53,9 @@ inline int run(int argc, char** argv) {
         std::printf("%s %s\n", ok ? "[       OK ]" : "[  FAILED  ]", full.c_str());
         std::fflush(stdout);
         ++ran; failed += ok ? 0 : 1;
+        if (!ok) failed_names += " " + full;
     }
-    if (!list) std::printf("[==========] %d tests ran, %d failed\n", ran, failed);
+    if (!list) std::printf("[==========] %d tests ran, %d failed%s%s\n", ran, failed, failed ? ":" : "", failed_names.c_str());
     return failed ? 1 : 0;
 }
 }  // namespace mini_gtest

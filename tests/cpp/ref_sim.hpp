@@ -25,6 +25,13 @@ inline double rotation_angle(const Eigen::Matrix3d& R) {
     return std::acos(c);
 }
 
+// The acos form above (the reference's, tests/unit/utils.h:29-32) cannot resolve angles below sqrt(2 eps) = 2.1e-8 rad:
+// a trace one ulp short of 3 already reads as 2.1e-8.  Assertions tighter than that use the atan2 form.
+inline double rotation_angle_small(const Eigen::Matrix3d& R) {
+    const double ax = R(2, 1) - R(1, 2), ay = R(0, 2) - R(2, 0), az = R(1, 0) - R(0, 1);
+    return std::atan2(0.5 * std::sqrt(ax * ax + ay * ay + az * az), (R.trace() - 1.0) * 0.5);
+}
+
 inline PlanarView make_view(const std::vector<Eigen::Vector2d>& obj, const std::vector<Eigen::Vector2d>& img) {
     PlanarView view(obj.size());
     for (size_t i = 0; i < obj.size(); ++i) view[i] = {obj[i], img[i]};

@@ -72,7 +72,7 @@ TEST(OptimizeIntrinsics, RecoversIntrinsicsNoSkew) {  // :8-62
     EXPECT_TRUE(res.core.success);
     ASSERT_EQ(res.c_se3_t.size(), views.size());
     for (size_t v = 0; v < views.size(); ++v) {
-        EXPECT_LT(rotation_angle(res.c_se3_t[v].linear().transpose() * sim.c_se3_t[v].linear()), 1e-8);
+        EXPECT_LT(rotation_angle_small(res.c_se3_t[v].linear().transpose() * sim.c_se3_t[v].linear()), 1e-8);
         EXPECT_LT((res.c_se3_t[v].translation() - sim.c_se3_t[v].translation()).norm(), 1e-8);
     }
     EXPECT_EQ(res.core.covariance.rows(), static_cast<Eigen::Index>(10 + 7 * views.size()));
@@ -795,7 +795,7 @@ TEST(PlanarPoseTest, DLTEstimation) {  // planarpose_test.cpp:60-94 with the dat
     EXPECT_TRUE(true_pose.linear().isApprox(estimated_pose.linear(), 1e-1) || true_pose.linear().isApprox(-estimated_pose.linear(), 1e-1));
     EXPECT_GT(std::abs(true_pose.translation().normalized().dot(estimated_pose.translation().normalized())), 0.9);
     // noise-free data: the DLT pose is exact
-    EXPECT_LT(rotation_angle(true_pose.linear().transpose() * estimated_pose.linear()), 1e-9);
+    EXPECT_LT(rotation_angle_small(true_pose.linear().transpose() * estimated_pose.linear()), 1e-9);
     EXPECT_LT((true_pose.translation() - estimated_pose.translation()).norm(), 1e-9);
     // fewer than four points: identity (planarpose_linear.cpp:55-57)
     view.resize(3);
