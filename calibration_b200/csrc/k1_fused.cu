@@ -45,8 +45,8 @@ static void launch_k1_v(const K1Args& P, cudaStream_t st) {
     using RT = K1Roles<MODEL, IMODE>;
     constexpr int threads = RT::NROLE * 32;
     constexpr int smem = K1Smem<MODEL, IMODE>::kBytes;
-    static bool once = false;
-    if (!once) { cudaFuncSetAttribute(k1_kernel<MODEL, IMODE, VIEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); once = true; }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(k1_kernel<MODEL, IMODE, VIEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     k1_kernel<MODEL, IMODE, VIEW><<<(unsigned)P.L.n_tiles, threads, smem, st>>>(P);
 }
 

@@ -69,11 +69,10 @@ void launch_cost(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B
     if (L.n_tiles == 0) return;
     const unsigned g = (unsigned)((L.n_tiles + 3) / 4);
     constexpr int smem = 4 * kWarpStageBytes;
-    static bool once = false;
-    if (!once) {
+    static PerDeviceOnce once;
+    if (once.first()) {
         cudaFuncSetAttribute(k_cost<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(k_cost<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        once = true;
     }
     if (S.model == 0) k_cost<0><<<g, 128, smem, st>>>(L, B);
     else k_cost<1><<<g, 128, smem, st>>>(L, B);

@@ -4,11 +4,26 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <vector>
 
 #include "k1_math.cuh"
 
 namespace calk {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (function, device) pair: a handle on a second device
+// of the same process must set it again.  One bit per device ordinal; setting it twice from two threads is harmless.
+struct PerDeviceOnce {
+    std::atomic<uint64_t> mask{0};
+    bool first() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return true;
+        const uint64_t bit = 1ull << (dev & 63);
+        if (mask.load(std::memory_order_acquire) & bit) return false;
+        mask.fetch_or(bit, std::memory_order_acq_rel);
+        return true;
+    }
+};
 
 // Observations are stored tile-transposed: residual blocks are cut into
 // segments of <= seg_len corners, 32 segments form a tile (one warp), and the
