@@ -70,13 +70,30 @@ struct Scanner {
     }
     bool number(double* out) {
         ws();
+        // RFC 8259 grammar first (strtod alone would also take nan, inf, hex floats and a leading '+'):
+        //   -? (0 | [1-9][0-9]*) (. [0-9]+)? ([eE] [+-]? [0-9]+)?
+        const char* q = p;
+        if (q < end && *q == '-') ++q;
+        if (q >= end || *q < '0' || *q > '9') return fail("expected a number");
+        if (*q == '0') ++q; else while (q < end && *q >= '0' && *q <= '9') ++q;
+        if (q < end && *q == '.') { ++q; if (q >= end || *q < '0' || *q > '9') return fail("malformed number"); while (q < end && *q >= '0' && *q <= '9') ++q; }
+        if (q < end && (*q == 'e' || *q == 'E')) {
+            ++q; if (q < end && (*q == '+' || *q == '-')) ++q;
+            if (q >= end || *q < '0' || *q > '9') return fail("malformed number");
+            while (q < end && *q >= '0' && *q <= '9') ++q;
+        }
         char* e = nullptr;
-        const double v = std::strtod(p, &e);
-        if (e == p) return fail("expected a number");
-        p = e; if (out) *out = v;
+        const double v = std::strtod(p, &e);   // the buffer is NUL-terminated; the grammar above bounds what it reads
+        if (e != q) return fail("malformed number");
+        if (!std::isfinite(v)) return fail("number out of range");
+        p = q; if (out) *out = v;
         return true;
     }
+    static constexpr int kMaxDepth = 64;   // nesting of skipped values: bounded recursion on hostile input
+    int depth = 0;
     bool skip_value() {  // any JSON value
+        if (depth >= kMaxDepth) return fail("nesting too deep");
+        struct Level { int& d; explicit Level(int& x) : d(x) { ++d; } ~Level() { --d; } } level(depth);
         ws();
         if (p >= end) return fail("unexpected end of input");
         if (*p == '"') return string(nullptr);
@@ -189,11 +206,31 @@ extern "C" cal_status cal_dataset_open(const char* path, int pin, cal_dataset* o
     ::close(fd);
     if (map == MAP_FAILED) return dfail(CAL_ERR_RUNTIME, std::string("mmap failed for ") + path);
     const Header* h = static_cast<const Header*>(map);
-    const bool sane = !std::memcmp(h->magic, kMagic, 8) && h->n_views >= 0 && h->n_obs >= 0 && h->n_cams > 0 &&
-                      h->off_view_offset == 64 && h->off_view_cam >= 64 && h->off_x >= h->off_view_cam && h->stride_obs >= h->n_obs * 8 &&
-                      h->off_x + 4 * h->stride_obs <= (int64_t)st.st_size;
+    // every section is checked against the file size with arithmetic that cannot overflow: counts are bounded by
+    // the size before they are multiplied, sections must be ordered, aligned and non-overlapping
+    const int64_t size = (int64_t)st.st_size;
+    bool sane = !std::memcmp(h->magic, kMagic, 8) && h->n_cams > 0 && h->off_view_offset == 64 &&
+                h->n_views >= 0 && h->n_views <= (size - 64) / 8 - 1 &&       // (n_views + 1) * 8 fits behind the header
+                h->n_obs >= 0 && h->n_obs <= size / 32 &&                     // four columns of n_obs doubles fit
+                h->stride_obs >= 0 && h->stride_obs <= size / 4 && h->stride_obs % 8 == 0 && h->stride_obs >= h->n_obs * 8;
+    if (sane) {
+        const int64_t end_off = h->off_view_offset + (h->n_views + 1) * 8, cam_bytes = h->n_views * 4;
+        sane = h->off_view_cam >= end_off && h->off_view_cam % 4 == 0 && h->off_view_cam <= size - cam_bytes &&
+               h->off_x >= h->off_view_cam + cam_bytes && h->off_x % 8 == 0 && h->off_x <= size - 4 * h->stride_obs &&
+               3 * h->stride_obs + h->n_obs * 8 <= size - h->off_x;
+    }
     if (!sane) { munmap(map, (size_t)st.st_size); return dfail(CAL_ERR_RUNTIME, std::string(path) + ": not a CALOBS01 file"); }
     const char* base = static_cast<const char*>(map);
+    {   // the CSR offsets and camera ids are what the kernels index with: a corrupt file must not get past here
+        const int64_t* vo = reinterpret_cast<const int64_t*>(base + h->off_view_offset);
+        const int32_t* vc = reinterpret_cast<const int32_t*>(base + h->off_view_cam);
+        bool ok = vo[0] == 0 && vo[h->n_views] == h->n_obs;
+        for (int64_t v = 0; ok && v < h->n_views; ++v) ok = vo[v + 1] >= vo[v] && vc[v] >= 0 && vc[v] < h->n_cams;
+        if (!ok) {
+            munmap(map, (size_t)st.st_size);
+            return dfail(CAL_ERR_RUNTIME, std::string(path) + ": view_offset does not span the observations monotonically or view_cam is out of range");
+        }
+    }
     out->n_views = h->n_views; out->n_obs = h->n_obs; out->n_cams = h->n_cams;
     out->view_offset = reinterpret_cast<const int64_t*>(base + h->off_view_offset);
     out->view_cam = reinterpret_cast<const int32_t*>(base + h->off_view_cam);
@@ -201,10 +238,6 @@ extern "C" cal_status cal_dataset_open(const char* path, int pin, cal_dataset* o
     out->obj_y = reinterpret_cast<const double*>(base + h->off_x + h->stride_obs);
     out->img_u = reinterpret_cast<const double*>(base + h->off_x + 2 * h->stride_obs);
     out->img_v = reinterpret_cast<const double*>(base + h->off_x + 3 * h->stride_obs);
-    if (out->view_offset[0] != 0 || out->view_offset[h->n_views] != h->n_obs) {
-        munmap(map, (size_t)st.st_size); std::memset(out, 0, sizeof *out);
-        return dfail(CAL_ERR_RUNTIME, std::string(path) + ": view_offset does not span the observations");
-    }
     Impl* im = new Impl; im->map = map; im->size = (size_t)st.st_size;
     if (pin) {  // page-lock the mapping so cudaMemcpyAsync runs at full PCIe speed; optional (needs a CUDA device)
         if (cudaHostRegister(map, im->size, cudaHostRegisterReadOnly) == cudaSuccess) im->pinned = true;

@@ -88,3 +88,61 @@ def test_open_rejects_foreign_files(tmp_path):
         capi.Dataset(str(p))
     with pytest.raises(RuntimeError, match="cannot open"):
         capi.Dataset(str(tmp_path / "missing.calobs"))
+
+
+def _header(n_views, n_obs, n_cams, off_view_offset, off_view_cam, off_x, stride_obs):
+    import struct
+    return b"CALOBS01" + struct.pack("<qqiiqqqq", n_views, n_obs, n_cams, 0, off_view_offset, off_view_cam, off_x, stride_obs)
+
+
+def test_open_rejects_crafted_and_truncated_headers(tmp_path):
+    """cal_dataset_open validates every section against the file size before it dereferences anything: a header whose
+    counts or offsets point outside the file, a truncated file, non-monotone CSR offsets and camera ids out of range
+    are all reported, never dereferenced."""
+    rng = np.random.default_rng(2)
+    off = np.array([0, 3, 7])
+    cols = [rng.normal(size=7) for _ in range(4)]
+    good = tmp_path / "g.calobs"
+    capi.Dataset.write(str(good), off, [0, 1], *cols, n_cams=2)
+    blob = bytearray(good.read_bytes())
+    with capi.Dataset(str(good)) as ds:
+        assert ds.n_views == 2
+
+    def opens(data, name):
+        p = tmp_path / name; p.write_bytes(bytes(data)); return capi.Dataset(str(p))
+
+    crafted = {
+        "huge_n_views": _header(2 ** 40, 0, 1, 64, 64, 64, 0) + bytes(64),                     # the 128-byte reproducer
+        "n_views_past_eof": _header(1000, 7, 2, 64, 128, 192, 64) + bytes(blob[64:]),
+        "stride_overflow": _header(2, 7, 2, 64, 128, 192, 2 ** 62) + bytes(blob[64:]),
+        "off_x_past_eof": _header(2, 7, 2, 64, 128, 2 ** 40, 64) + bytes(blob[64:]),
+        "cam_overlaps_offsets": _header(2, 7, 2, 64, 72, 192, 64) + bytes(blob[64:]),
+        "negative_obs": _header(2, -7, 2, 64, 128, 192, 64) + bytes(blob[64:]),
+        "truncated": bytes(blob[:len(blob) - 40]),
+    }
+    for name, data in crafted.items():
+        with pytest.raises(RuntimeError, match="not a CALOBS01 file"):
+            opens(data, name)
+    import struct
+    bad = bytearray(blob); struct.pack_into("<q", bad, 64 + 8, 9)                               # view_offset = [0, 9, 7]
+    with pytest.raises(RuntimeError, match="monotonically"):
+        opens(bad, "non_monotone")
+    hdr = struct.unpack_from("<qqiiqqqq", blob, 8)
+    bad = bytearray(blob); struct.pack_into("<i", bad, hdr[5], 5)                               # view_cam[0] = 5 >= n_cams
+    with pytest.raises(RuntimeError, match="out of range"):
+        opens(bad, "cam_range")
+
+
+@pytest.mark.parametrize("text, msg", [
+    ('{"images": [{"points": [{"x": nan, "y": 2, "local_x": 3, "local_y": 4}]}]}', "expected a number"),
+    ('{"images": [{"points": [{"x": inf, "y": 2, "local_x": 3, "local_y": 4}]}]}', "expected a number"),
+    ('{"images": [{"points": [{"x": 0x10, "y": 2, "local_x": 3, "local_y": 4}]}]}', "malformed number"),
+    ('{"images": [{"points": [{"x": +1, "y": 2, "local_x": 3, "local_y": 4}]}]}', "expected a number"),
+    ('{"images": [{"points": [{"x": 1e999, "y": 2, "local_x": 3, "local_y": 4}]}]}', "out of range"),
+    ('{"images": [{"points": [{"x": 1., "y": 2, "local_x": 3, "local_y": 4}]}]}', "malformed number"),
+    ('{"meta": ' + "[" * 100000 + "]" * 100000 + ', "images": []}', "nesting too deep"),
+])
+def test_numbers_follow_the_json_grammar_and_nesting_is_bounded(tmp_path, text, msg):
+    p = tmp_path / "bad.json"; p.write_text(text)
+    with pytest.raises(ValueError, match=msg):
+        capi.Dataset.from_planar_json([str(p)], str(tmp_path / "o.calobs"))
