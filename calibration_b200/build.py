@@ -9,8 +9,11 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-OUT_DIR = os.path.join(_HERE, "_build")
+# CALIB_B200_BUILD_DIR / CALIB_B200_NVCC_EXTRA: a second build of the library beside the default one (kernel experiments
+# are compared in ONE process sequence on the same GPU box: tools/k1_probe.py); the default build ignores both
+OUT_DIR = os.path.join(_HERE, os.environ.get("CALIB_B200_BUILD_DIR", "_build"))
 LIB = os.path.join(OUT_DIR, "libcalib_b200.so")
+NVCC_EXTRA = os.environ.get("CALIB_B200_NVCC_EXTRA", "").split()
 SOURCES = ["k1_fused.cu", "refine_kernels.cu", "refine_host.cu", "axxb.cu", "ransac.cu", "ransac_plane.cu", "seed.cu", "comm.cpp", "comm_peer.cu", "dataset.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -48,7 +51,7 @@ def build(force=False, verbose=False):
         if not os.path.exists(path):
             continue
         obj = os.path.join(OUT_DIR, src.rsplit(".", 1)[0] + ".o")
-        cmd = [_nvcc(), *ccbin, *NVCC_FLAGS, "-c", path, "-o", obj]
+        cmd = [_nvcc(), *ccbin, *NVCC_FLAGS, *NVCC_EXTRA, "-c", path, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas"); cmd.insert(2, "-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)))

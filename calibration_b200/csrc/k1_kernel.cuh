@@ -125,13 +125,6 @@ struct K1Xchg {
     static constexpr int pos_u(int c) { int n = 0; for (int i = 0; i < c; ++i) n += (send_u(i) ? 1 : 0) + (send_v(i) ? 1 : 0); return n; }
     static constexpr int pos_v(int c) { return pos_u(c) + (send_u(c) ? 1 : 0); }
     static constexpr int NX = pos_u(LT::NL);
-    // what one corner adds to entry (a, b) when every exchanged value reads as zero (an all-zero exchange slot): only
-    // the products of two constant ones survive.  The pipelined step loop consumes one such slot per foreign role
-    // before the first real corner and starts the accumulator at minus this count (small integers: exact).
-    static constexpr int ones(int a, int b) {
-        return ((LT::has_u(a) && !send_u(a) && LT::has_u(b) && !send_u(b)) ? 1 : 0) +
-               ((LT::has_v(a) && !send_v(a) && LT::has_v(b) && !send_v(b)) ? 1 : 0);
-    }
 };
 
 template <int MODEL, int IMODE, int ROLE>
@@ -180,13 +173,9 @@ __device__ __forceinline__ void k1_role(const K1Args& P, int64_t tile, int lane,
     const int len = L.seg_len[s];
     const int depth = L.tile_depth[tile];
     const bool leader = ROLE == 0 && lane == 0;
-    double* xbuf = reinterpret_cast<double*>(smem + SM::kStageBytes);   // [2][NROLE][NX][32]
-    if constexpr (NROLE == 2) {   // the pipelined loop reads the parity-1 slots once before anything was published
-#pragma unroll
-        for (int i = 0; i < NX; ++i) xbuf[(NROLE + ROLE) * NX * 32 + i * 32 + lane] = 0.0;
-    }
-    CtaStage<RC> ts; ts.init(smem, L.obs + L.tile_off[tile] * 128, depth, leader, NROLE * 32);   // (CTA barrier inside)
+    CtaStage<RC> ts; ts.init(smem, L.obs + L.tile_off[tile] * 128, depth, leader, NROLE * 32);
     ts.issue(0, leader); ts.issue(1, leader);
+    double* xbuf = reinterpret_cast<double*>(smem + SM::kStageBytes);   // [2][NROLE][NX][32]
     double A[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) A[i] = B.seg_frame[(int64_t)i * L.n_seg + s];
@@ -253,73 +242,7 @@ __device__ __forceinline__ void k1_role(const K1Args& P, int64_t tile, int lane,
             ts.issue(ch + 2, leader);                // refill it
         }
     };
-    // PIPE (NROLE == 2, full-depth tile, depth a multiple of 2 NROLE): the same work, software-pipelined.  Step s projects
-    // its corner and accumulates it from registers WHILE it accumulates the corners the other roles projected in step
-    // s - 1, read from the exchange slot of the opposite parity.  The two streams share one basic block (the loop is
-    // unrolled over the slot parity, so every shared-memory address is base + constant and the compiler can tell the
-    // slots apart): the long dependent chain of the projection hides under the independent FMAs of the foreign corners.
-    // One barrier per step, as before.  Before step 0 the parity-1 slots are zero-filled; what an all-zero corner adds
-    // (products of two constant ones) is taken off the accumulators up front.
-    auto run_pipelined = [&](auto) {   // (generic: only instantiated for the role counts that call it)
-        double* const xb0 = xbuf;
-        double* const xb1 = xbuf + NROLE * NX * 32;
-        auto consume = [&](const double* xb) {
-            static_for<1, NROLE>([&](auto cp) {
-                constexpr int other = (ROLE + decltype(cp)::value) % NROLE;
-                const double* xo = xb + other * NX * 32 + lane;
-                double Pu[NL], Pv[NL];
-                static_for<0, NL>([&](auto cc) {
-                    constexpr int col = decltype(cc)::value;
-                    Pu[col] = XT::send_u(col) ? xo[XT::pos_u(col) * 32] : (LT::has_u(col) ? 1.0 : 0.0);
-                    Pv[col] = XT::send_v(col) ? xo[XT::pos_v(col) * 32] : (LT::has_v(col) ? 1.0 : 0.0);
-                });
-                k1_accumulate<MODEL, IMODE, ROLE>(Pu, Pv, acc, ssr);
-            });
-        };
-        auto step = [&](int ch, int kk, const double* xprev, double* xcur) {
-            consume(xprev);
-            double Ju[NL], Jv[NL];
-            const double* q = ts.row(ch, kk + ROLE, lane);
-            obs_rows<MODEL, IMODE>(c, A, q[0], q[32], q[64], q[96], Ju, Jv);
-            double* xs = xcur + ROLE * NX * 32 + lane;
-            static_for<0, NL>([&](auto cc) {
-                constexpr int col = decltype(cc)::value;
-                if constexpr (XT::send_u(col)) xs[XT::pos_u(col) * 32] = Ju[col];
-                if constexpr (XT::send_v(col)) xs[XT::pos_v(col) * 32] = Jv[col];
-            });
-            k1_accumulate<MODEL, IMODE, ROLE>(Ju, Jv, acc, ssr);
-#if defined(CALIB_SIMT_SHIM)
-            simt::named_barrier(NROLE * 32);
-#else
-            asm volatile("bar.sync 1, %0;" ::"n"(NROLE * 32) : "memory");
-#endif
-        };
-        static_for<0, LT::NE>([&](auto ce) {
-            constexpr int e = decltype(ce)::value;
-            if constexpr (RT::tbl.role[e] == ROLE) {
-                constexpr int a = LT::row_of(e), b = LT::col_of(e), sl = RT::tbl.slot[e];
-                acc[sl] = -(double)((NROLE - 1) * XT::ones(a, b));
-            }
-        });
-        for (int ch = 0; ch < ts.n_chunks; ++ch) {
-            ts.wait(ch);
-            const int kn = min(RC, depth - ch * RC);
-            for (int kk = 0; kk < kn; kk += 2 * NROLE) {
-                step(ch, kk, xb1, xb0);
-                step(ch, kk + NROLE, xb0, xb1);
-            }
-            ts.issue(ch + 2, leader);
-        }
-        consume(xb1);
-    };
-    const bool full = __all_sync(0xffffffffu, len == depth);
-    if constexpr (NROLE == 2 && RC % (2 * NROLE) == 0) {
-        if (full && depth % (2 * NROLE) == 0) run_pipelined(0);
-        else if (full && depth % NROLE == 0) run(std::true_type{});
-        else run(std::false_type{});
-    } else {
-        if (full && depth % NROLE == 0) run(std::true_type{}); else run(std::false_type{});
-    }
+    if (__all_sync(0xffffffffu, len == depth) && depth % NROLE == 0) run(std::true_type{}); else run(std::false_type{});
     unsigned char* warp_smem = smem;             // NROLE == 1: the transpose tile aliases the idle staging ring
     if constexpr (NROLE > 1) {
         // the exchange slots are dead: they become the transpose tiles

@@ -97,8 +97,6 @@ struct Local {
         return c < 6 || c == NC || (c - 6 != c_fx && c - 6 != c_cx && c - 6 != c_sk);
     }
     static constexpr int idx(int a, int b) { return a * NL - a * (a - 1) / 2 + (b - a); }  // a <= b
-    static constexpr int row_of(int e) { int a = 0; while (idx(a + 1, a + 1) <= e) ++a; return a; }
-    static constexpr int col_of(int e) { const int a = row_of(e); return a + (e - idx(a, a)); }
 };
 
 // Residual + local Jacobian rows of one observation.  Ju/Jv have NL entries;
