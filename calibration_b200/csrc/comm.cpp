@@ -85,10 +85,13 @@ bool Comm::peer_export(uint8_t handle_out[kPeerHandleBytes]) {
     if (world_ > 64) { err_ = "peer path supports at most 64 ranks"; return false; }
     if (!recv_) {
         const size_t bytes = ((size_t)2 * world_ * kPeerMaxDoubles + (size_t)2 * world_) * sizeof(double);
+        int* flag = nullptr;
         if (cudaMalloc(reinterpret_cast<void**>(&recv_), bytes) != cudaSuccess || cudaMemset(recv_, 0, bytes) != cudaSuccess ||
-            cudaMalloc(reinterpret_cast<void**>(&timed_out_), sizeof(int)) != cudaSuccess || cudaMemset(timed_out_, 0, sizeof(int)) != cudaSuccess) {
+            cudaHostAlloc(reinterpret_cast<void**>(&flag), sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(reinterpret_cast<void**>(&timed_out_dev_), flag, 0) != cudaSuccess) {
             err_ = std::string("peer region allocation failed: ") + cudaGetErrorString(cudaGetLastError()); return false;
         }
+        *flag = 0; timed_out_ = flag;
         cudaDeviceSynchronize();
     }
     cudaIpcMemHandle_t hnd;
@@ -128,6 +131,7 @@ bool Comm::allreduce_test(double* host_buf, size_t n, bool use_peer) {
     ok = ok && allreduce_sum(d, n, st_);
     peer_on_ = saved;
     ok = ok && cudaMemcpyAsync(host_buf, d, n * sizeof(double), cudaMemcpyDeviceToHost, st_) == cudaSuccess && cudaStreamSynchronize(st_) == cudaSuccess;
+    ok = ok && check_timeout();
     cudaFree(d);
     if (!ok && err_.empty()) err_ = "allreduce_test failed";
     return ok;
@@ -137,7 +141,7 @@ Comm::~Comm() {
     for (int r = 0; r < 64; ++r) if (opened_[r]) cudaIpcCloseMemHandle(opened_[r]);
     if (peers_dev_) cudaFree(peers_dev_);
     if (recv_) cudaFree(recv_);
-    if (timed_out_) cudaFree(timed_out_);
+    if (timed_out_) cudaFreeHost(const_cast<int*>(timed_out_));
     Api* a = api(nullptr);
     if (comm_ && a && a->CommDestroy) a->CommDestroy(comm_);
     if (stage_) cudaFree(stage_);
@@ -146,7 +150,8 @@ Comm::~Comm() {
 
 bool Comm::allreduce_sum(double* dev_buf, size_t n, cudaStream_t st) {
     if (peer_on_ && n <= (size_t)kPeerMaxDoubles) {
-        launch_peer_allreduce(dev_buf, (int)n, peers_dev_, rank_, world_, ++epoch_, timed_out_, st);
+        PeerArgs a; peer_args(n, &a);
+        launch_peer_allreduce(dev_buf, (int)n, a, st);
         if (cudaGetLastError() != cudaSuccess) { err_ = "peer all-reduce launch failed"; return false; }
         return true;
     }

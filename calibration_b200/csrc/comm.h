@@ -9,12 +9,12 @@
 
 #include <string>
 
+#include "comm_peer.cuh"
+
 namespace calcomm {
 
-constexpr int kPeerMaxDoubles = 4096;   // largest block the peer-memory all-reduce takes (32 KB)
 constexpr int kPeerHandleBytes = 64;    // sizeof(cudaIpcMemHandle_t)
-void launch_peer_allreduce(double* buf, int n, double* const* peers_dev, int rank, int world, unsigned long long epoch, int* timed_out,
-                           cudaStream_t st);
+void launch_peer_allreduce(double* buf, int n, const PeerArgs& a, cudaStream_t st);
 
 class Comm {
   public:
@@ -28,6 +28,16 @@ class Comm {
     bool peer_export(uint8_t handle_out[kPeerHandleBytes]);
     bool peer_enable(const uint8_t* handles /*[world][kPeerHandleBytes]*/);
     bool peer_enabled() const { return peer_on_; }
+    // arguments of the NEXT peer all-reduce of n doubles for a kernel that performs it inline (k_tile_reduce); false
+    // when the peer path is off or the block too large — the caller then uses allreduce_sum.  Every rank must make
+    // the same sequence of peer_args / allreduce_sum calls (one epoch each).
+    bool peer_args(size_t n, PeerArgs* out) {
+        if (!peer_on_ || n > (size_t)kPeerMaxDoubles) return false;
+        *out = PeerArgs{peers_dev_, rank_, world_, ++epoch_, timed_out_dev_};
+        return true;
+    }
+    // after a stream synchronisation: did a peer all-reduce give up waiting?  (then its result is NaN-poisoned)
+    bool check_timeout() { if (timed_out_ && *timed_out_) { err_ = "peer all-reduce timed out waiting for another rank"; return false; } return true; }
     void peer_disable() { peer_on_ = false; }
     // test hook: all-reduce a host vector through the device (peer path if enabled and use_peer, else NCCL)
     bool allreduce_test(double* host_buf, size_t n, bool use_peer);
@@ -46,7 +56,8 @@ class Comm {
     double* recv_ = nullptr;            // my region: slots [2][world][kPeerMaxDoubles] + flags [2][world]
     double** peers_dev_ = nullptr;      // device array [world] of region base pointers
     void* opened_[64] = {nullptr};      // cudaIpcOpenMemHandle results to close
-    int* timed_out_ = nullptr;          // device flag set by the kernel's bounded wait
+    volatile int* timed_out_ = nullptr; // pinned host flag set by the kernel's bounded wait (mapped: no copy needed to read it)
+    int* timed_out_dev_ = nullptr;      // its device address
     unsigned long long epoch_ = 0;
     bool peer_on_ = false;
 };

@@ -20,7 +20,7 @@
 // chain rule T_b of the view-type pose (k1_math.cuh) from registers, and reduces over the
 // 32 blocks of the tile through a padded shared-memory transpose in a fixed order (no
 // floating-point atomics: results are run-to-run identical).  Per tile one row of NVT
-// values is written; k_tile_colsum / k_tile_final add the rows per camera.  For the
+// values is written; k_tile_reduce adds the rows per camera (and all-reduces them over NVLink).  For the
 // kinds with per-view unknowns the per-block products (H_vv, g_v, E_vc, E_vi) are written
 // per block for the Schur kernels instead of being reduced.
 //
@@ -62,6 +62,9 @@ static void launch_k1_t(const ProblemShape& S, const DevLayout& L, const EvalBuf
     else launch_k1_v<MODEL, IMODE, VIEW_NONE>(P, st);
 }
 
+#if defined(CALK_K1_ONLY_PINHOLE_NOSKEW)   // kernel experiments: compile the benchmark's instance only (never the shipped build)
+#define CALK_K1_DISPATCH(FN, ...) FN<0, 1>(__VA_ARGS__)
+#else
 #define CALK_K1_DISPATCH(FN, ...)                                                          \
     do {                                                                                   \
         if (S.model == 0 && S.imode == 0) FN<0, 0>(__VA_ARGS__);                           \
@@ -71,6 +74,7 @@ static void launch_k1_t(const ProblemShape& S, const DevLayout& L, const EvalBuf
         else if (S.model == 1 && S.imode == 1) FN<1, 1>(__VA_ARGS__);                      \
         else FN<1, 2>(__VA_ARGS__);                                                        \
     } while (0)
+#endif
 
 void launch_k1(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st) {
     if (L.n_tiles == 0) return;
@@ -93,11 +97,11 @@ int k1_num_passes(const ProblemShape& S) { int r = 1; k1_tile_value_map(S, &r, n
 // ---------------------------------------------------------------------------
 // per-camera sums of the per-tile rows (fixed order, no atomics)
 // ---------------------------------------------------------------------------
-// (device code of k_tile_colsum / k_tile_final: k1_kernel.cuh)
-int launch_tile_reduce(const ProblemShape& S, const EvalBuffers& B, const ReduceDesc& R, int nvt, cudaStream_t st) {
-    k_tile_colsum<<<R.n_tile_chunks, 256, 0, st>>>(B.tile_vals, nvt, R.tile_chunks, B.partial_tile);
-    k_tile_final<<<(S.n_cams * nvt + 7) / 8, 256, 0, st>>>(B.partial_tile, R.tile_cam_chunk_off, S.n_cams, nvt, B.tile_vmap, B.cam_sums, S.NV);
-    return 2;
+// (device code of k_tile_reduce: k1_kernel.cuh)
+int launch_tile_reduce(const ProblemShape& S, const EvalBuffers& B, const ReduceDesc& R, int nvt, const calcomm::PeerArgs& peer, cudaStream_t st) {
+    const TileReduceArgs A{B.tile_vals, nvt, R.tile_chunks, B.partial_tile, R.tile_cam_chunk_off, S.n_cams, B.tile_vmap, B.cam_sums, S.NV, R.tile_tickets, R.n_active_cams};
+    k_tile_reduce<<<R.n_tile_chunks, 256, 0, st>>>(A, peer);
+    return 1;
 }
 
 }  // namespace calk

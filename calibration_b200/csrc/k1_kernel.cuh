@@ -7,6 +7,7 @@
 
 #include "k1_roles.hpp"
 #include "refine_kernels.cuh"
+#include "comm_peer.cuh"
 #if !defined(CALIB_SIMT_SHIM)
 #include "tile_stage.cuh"
 #endif
@@ -375,28 +376,62 @@ __global__ void __launch_bounds__(K1Roles<MODEL, IMODE>::NROLE * 32) k1_kernel(c
 }
 
 // ---------------------------------------------------------------------------
-// per-camera sums of the per-tile rows (fixed order, no atomics); launcher: k1_fused.cu
+// per-camera sums of the per-tile rows, fixed order, no floating-point atomics; launcher: k1_fused.cu.
+// ONE launch: every CTA sums the rows of its chunk (32 tiles of one camera); the CTA that finishes a camera's last
+// chunk (an integer ticket per camera) adds that camera's chunk partials in chunk order; the CTA that finishes the
+// last camera resets the tickets and, on several GPUs, runs the NVLink peer-memory all-reduce of cam_sums itself
+// (comm_peer.cuh) — the reduction and the collective that follows it are one kernel.  Which CTA happens to be last
+// does not matter: every sum is formed by one thread in a fixed order, so results are run-to-run identical.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_tile_colsum(const double* __restrict__ tile_vals, int nvt,
-                                                     const ColChunk* __restrict__ chunks, double* __restrict__ partial) {
-    const ColChunk c = chunks[blockIdx.x];
+struct TileReduceArgs {
+    const double* tile_vals; int nvt;
+    const ColChunk* chunks; double* partial;          // [n_chunks][nvt]
+    const int32_t* cam_chunk_off; int n_cams;         // [n_cams + 1]
+    const int32_t* vmap; double* cam_sums; int NV;    // value v of a row -> cam_sums[cam * NV + vmap[v]]
+    unsigned* tickets;                                // [n_cams + 1], zero between launches
+    int n_active_cams;                                // cameras that own at least one chunk on this GPU
+};
+__global__ void __launch_bounds__(256) k_tile_reduce(const TileReduceArgs A, const calcomm::PeerArgs peer) {
+#if defined(CALIB_SIMT_SHIM)
+    static int s_last, s_bad;   // tests/host_emul runs one CTA at a time
+#else
+    __shared__ int s_last, s_bad;
+#endif
+    const ColChunk c = A.chunks[blockIdx.x];
+    const int nvt = A.nvt;
     for (int v = threadIdx.x; v < nvt; v += 256) {
         double a = 0.0;
-        for (int64_t t = c.begin; t < c.end; ++t) a += tile_vals[t * nvt + v];
-        partial[(int64_t)blockIdx.x * nvt + v] = a;
+        for (int64_t t = c.begin; t < c.end; ++t) a += A.tile_vals[t * nvt + v];
+        A.partial[(int64_t)blockIdx.x * nvt + v] = a;
     }
-}
-__global__ void __launch_bounds__(256) k_tile_final(const double* __restrict__ partial, const int32_t* __restrict__ cam_chunk_off, int n_cams,
-                                                    int nvt, const int32_t* __restrict__ vmap, double* __restrict__ cam_sums, int NV) {
-    // one warp per (camera, value): lanes stride over the camera's chunk partials, then a fixed shuffle tree
-    const int i = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (i >= n_cams * nvt) return;
-    const int cam = i / nvt, v = i % nvt;
-    double a = 0.0;
-    for (int c = cam_chunk_off[cam] + lane; c < cam_chunk_off[cam + 1]; c += 32) a += partial[(int64_t)c * nvt + v];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
-    if (lane == 0) cam_sums[(int64_t)cam * NV + vmap[v]] = a;
+    __threadfence();
+    __syncthreads();
+    const int cam = c.cam, c0 = A.cam_chunk_off[cam], c1 = A.cam_chunk_off[cam + 1];
+    if (threadIdx.x == 0) s_last = atomicAdd(&A.tickets[cam], 1u) == (unsigned)(c1 - c0 - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int v = threadIdx.x; v < nvt; v += 256) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // four interleaved partial sums over the chunks, fixed order
+        int k = c0;
+        for (; k + 3 < c1; k += 4) {
+            a0 += __ldcg(A.partial + (int64_t)k * nvt + v); a1 += __ldcg(A.partial + (int64_t)(k + 1) * nvt + v);
+            a2 += __ldcg(A.partial + (int64_t)(k + 2) * nvt + v); a3 += __ldcg(A.partial + (int64_t)(k + 3) * nvt + v);
+        }
+        for (; k < c1; ++k) a0 += __ldcg(A.partial + (int64_t)k * nvt + v);
+        A.cam_sums[(int64_t)cam * A.NV + A.vmap[v]] = (a0 + a1) + (a2 + a3);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&A.tickets[A.n_cams], 1u) == (unsigned)(A.n_active_cams - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i <= A.n_cams; i += 256) A.tickets[i] = 0u;   // ready for the next launch
+#if !defined(CALIB_SIMT_SHIM)
+    if (peer.world > 1) calcomm::peer_allreduce_cta(A.cam_sums, A.n_cams * A.NV, peer, &s_bad);
+#endif
+    (void)s_bad;
 }
 
 }  // namespace calk

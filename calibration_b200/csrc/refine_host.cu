@@ -374,6 +374,9 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
             h.R.n_tile_chunks = (int)tc.size(); h.R.nvt = nvt;
             CUDA_TRY(h.alloc(&h.R.tile_chunks, tc.size())); CUDA_TRY(h.alloc(&h.R.tile_cam_chunk_off, to.size()));
             CUDA_TRY(upload(h.R.tile_chunks, tc, us)); CUDA_TRY(upload(h.R.tile_cam_chunk_off, to, us));
+            CUDA_TRY(h.alloc(&h.R.tile_tickets, S.n_cams + 1)); CUDA_TRY(cudaMemsetAsync(h.R.tile_tickets, 0, sizeof(unsigned) * (S.n_cams + 1), us));
+            h.R.n_active_cams = 0;
+            for (int c = 0; c < S.n_cams; ++c) h.R.n_active_cams += to[c + 1] > to[c] ? 1 : 0;
             CUDA_TRY(h.alloc(&h.B.tile_vmap, vmap.size())); CUDA_TRY(upload(h.B.tile_vmap, vmap, us));
             CUDA_TRY(h.alloc(&h.B.tile_vals, (size_t)ntiles * nvt)); CUDA_TRY(h.alloc(&h.B.partial_tile, tc.size() * (size_t)nvt));
             CUDA_TRY(cudaStreamSynchronize(us));  // the staging vectors above go out of scope
@@ -459,6 +462,19 @@ extern "C" int64_t cal_refine_tangent_count(const cal_refine_handle* h) { return
 namespace {
 
 // ---- device passes -----------------------------------------------------------
+// Per-camera sums of a pass and, with a communicator, their all-reduce over the ranks.  In the fused layout the
+// all-reduce runs inside the reduction kernel over NVLink peer memory (k_tile_reduce); otherwise it is its own call.
+cal_status reduce_pass(cal_refine_handle& h, const EvalBuffers& B, bool jac) {
+    const ProblemShape& S = h.S;
+    const size_t n = (size_t)S.n_cams * (jac ? S.NV : 1);
+    calcomm::PeerArgs pa;
+    const bool inline_peer = h.comm && jac && h.L.fused && h.R.n_tile_chunks > 0 && h.comm->peer_args(n, &pa);
+    bool done = false;
+    h.launches += 2 + launch_assemble(S, h.L, B, h.R, jac ? 1 : 0, inline_peer ? &pa : nullptr, &done, h.st);
+    if (h.comm && !done && !h.comm->allreduce_sum(B.cam_sums, n, h.st)) return fail(CAL_ERR_COMM, h.comm->error());
+    return CAL_OK;
+}
+
 // x_dev must already hold the parameters.  After a Jacobian pass the host
 // mirrors h.Hss / h.gs / h.cost describe the shared block; per-view blocks stay
 // on the device (h.V.Hpp, h.V.gp, B.blk_E*).
@@ -467,16 +483,14 @@ cal_status device_pass(cal_refine_handle& h, double* x_dev, bool jac, const doub
     const ProblemShape& S = h.S;
     launch_setup(S, h.L, B, h.st);
     if (jac) launch_k1(S, h.L, B, h.st); else launch_cost(S, h.L, B, h.st);
-    h.launches += 2 + launch_assemble(S, h.L, B, h.R, jac ? 1 : 0, h.st);
     const int NV = jac ? S.NV : 1;
-    if (h.comm) {
-        if (!h.comm->allreduce_sum(B.cam_sums, (size_t)S.n_cams * NV, h.st)) return fail(CAL_ERR_COMM, h.comm->error());
-    }
+    if (cal_status st = reduce_pass(h, B, jac)) return st;
     h.cam_sums.resize((size_t)S.n_cams * NV);
     CUDA_TRY(cudaMemcpyAsync(h.cam_sums.data(), B.cam_sums, h.cam_sums.size() * sizeof(double), cudaMemcpyDeviceToHost, h.st));
     if (jac && S.n_views > 0) { launch_view_gather(S, h.L, B, h.V, h.st); h.launches++; }
     CUDA_TRY(cudaStreamSynchronize(h.st));
     CUDA_TRY(cudaGetLastError());
+    if (h.comm && !h.comm->check_timeout()) return fail(CAL_ERR_COMM, h.comm->error());
     double cost = 0;
     for (int c = 0; c < S.n_cams; ++c) cost += h.cam_sums[(size_t)c * NV + (jac ? S.NE : 0)];
     h.cost = cost;
@@ -597,9 +611,7 @@ extern "C" cal_status cal_refine_bench_pass(cal_refine_handle* h, const double* 
         CUDA_TRY(cudaEventRecord(ev[2 + 2 * r], h->st));
         if (jacobian) launch_k1(h->S, h->L, h->B, h->st); else launch_cost(h->S, h->L, h->B, h->st);
         CUDA_TRY(cudaEventRecord(ev[3 + 2 * r], h->st));
-        h->launches += 2 + launch_assemble(h->S, h->L, h->B, h->R, jacobian ? 1 : 0, h->st);
-        if (h->comm && !h->comm->allreduce_sum(h->B.cam_sums, (size_t)h->S.n_cams * (jacobian ? h->S.NV : 1), h->st))
-            return fail(CAL_ERR_COMM, h->comm->error());
+        if (cal_status st = reduce_pass(*h, h->B, jacobian != 0)) return st;
         if (jacobian && h->S.n_views > 0) { launch_view_gather(h->S, h->L, h->B, h->V, h->st); h->launches++; }
     }
     CUDA_TRY(cudaEventRecord(ev[1], h->st));
@@ -762,6 +774,7 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
             CUDA_TRY(cudaMemcpyAsync(cs.data(), V.c, sizeof(double) * ns, cudaMemcpyDeviceToHost, h.st));
             CUDA_TRY(cudaMemcpyAsync(&failed, V.fail, sizeof failed, cudaMemcpyDeviceToHost, h.st));
             CUDA_TRY(cudaStreamSynchronize(h.st));
+            if (h.comm && !h.comm->check_timeout()) return fail(CAL_ERR_COMM, h.comm->error());
             if (h.comm) {  // a failed view factorisation on any rank invalidates the step on every rank
                 double f = failed ? 1.0 : 0.0;
                 if (!h.comm->allreduce_host(&f, 1, true)) return fail(CAL_ERR_COMM, h.comm->error());

@@ -99,8 +99,12 @@ static void launch_view_part_t(const ProblemShape& S, const DevLayout& L, const 
 }
 
 int launch_assemble(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ReduceDesc& R, int jac,
-                    cudaStream_t st) {
-    if (jac && L.fused) return launch_tile_reduce(S, B, R, R.nvt, st);  // K1 already weighted, transformed and summed per tile
+                    const calcomm::PeerArgs* peer, bool* peer_done, cudaStream_t st) {
+    if (peer_done) *peer_done = false;
+    if (jac && L.fused) {   // K1 already weighted, transformed and summed per tile
+        if (peer_done) *peer_done = peer != nullptr;
+        return launch_tile_reduce(S, B, R, R.nvt, peer ? *peer : calcomm::PeerArgs{}, st);
+    }
     int launches = 0;
     const unsigned gb = (unsigned)((L.n_blk + 127) / 128);
     const int rr_row = S.NL * S.NC - S.NC * (S.NC - 1) / 2;  // idx(NC, NC)

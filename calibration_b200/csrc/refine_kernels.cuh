@@ -7,6 +7,7 @@
 #include <atomic>
 #include <vector>
 
+#include "comm_peer.cuh"
 #include "k1_math.cuh"
 
 namespace calk {
@@ -71,7 +72,7 @@ struct EvalBuffers {
     double* partial = nullptr;    // [n_seg_chunks][NE]
     double* partial_blk = nullptr;// [n_blk_chunks][NV - NE]
     double* cam_sums = nullptr;   // [n_cams][NV]
-    // fused K1: one row of NVT values per tile, summed per camera by k_tile_colsum / k_tile_final
+    // fused K1: one row of NVT values per tile, summed per camera by k_tile_reduce
     double* tile_vals = nullptr;  // [n_tiles][nvt]
     double* partial_tile = nullptr;  // [n_tile_chunks][nvt]
     int32_t* tile_vmap = nullptr; // [nvt] -> index into a camera's cam_sums row
@@ -89,12 +90,36 @@ struct ProblemShape {
     double huber_delta;
 };
 
+// Composite pose c_se3_t of device block b (the pose chains of src/estimation/residuals/{intrinsic,extrinsics,bundle}residual.h)
+// from the parameters x (k_block_setup).  Deriving it inside K1 per block instead of through the set-up kernel was measured
+// on B200 and is slower (the dependent chain is not hidden with two warps per sub-partition): +6.5 % on K1 against the 46 us launch.
+// real == false (padding block of a camera group): the identity, so nothing downstream sees garbage.
+CAL_HD void block_pose(const ProblemShape& S, const DevLayout& L, const double* __restrict__ x, int64_t b, int cam, bool real, BlockPose& bp) {
+    if (!real) {
+        for (int i = 0; i < 9; ++i) bp.R[i] = bp.M[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        bp.t[0] = bp.t[1] = bp.t[2] = 0.0;
+    } else if (S.kind == 0) {
+        const int v = L.blk_view[b];
+        compose_intrinsics(x + S.off_viewq + 4 * v, x + S.off_viewt + 3 * v, bp);
+    } else if (S.kind == 1) {
+        const int v = L.blk_view[b];
+        compose_extrinsics(x + S.off_camq + 4 * cam, x + S.off_camt + 3 * cam, x + S.off_viewq + 4 * v, x + S.off_viewt + 3 * v, bp);
+    } else {
+        double bTg[12];
+        for (int i = 0; i < 12; ++i) bTg[i] = L.blk_bTg[(int64_t)i * L.n_blk + b];
+        compose_bundle(x + S.off_viewq, x + S.off_viewt, x + S.off_camq + 4 * cam, x + S.off_camt + 3 * cam, bTg, bp);
+    }
+}
+CAL_HD const double* cam_intrinsics(const ProblemShape& S, const double* __restrict__ x, int cam) { return x + S.off_intr + (S.kind == 0 ? 0 : cam * S.P); }
+
 // contiguous column ranges (within one camera group) reduced by one CTA of k_colsum
 struct ColChunk { int32_t cam; int32_t pad; int64_t begin, end; };
 struct ReduceDesc {
     ColChunk* seg_chunks = nullptr; int n_seg_chunks = 0; int32_t* seg_cam_chunk_off = nullptr;  // [n_cams + 1]
     ColChunk* blk_chunks = nullptr; int n_blk_chunks = 0; int32_t* blk_cam_chunk_off = nullptr;
     ColChunk* tile_chunks = nullptr; int n_tile_chunks = 0; int32_t* tile_cam_chunk_off = nullptr; int nvt = 0;  // fused K1
+    unsigned* tile_tickets = nullptr;   // [n_cams + 1] arrival counters of k_tile_reduce (zero between launches)
+    int n_active_cams = 0;              // cameras with at least one tile on this GPU
 };
 
 void launch_repack(const DevLayout& L, const double* sx, const double* sy, const double* su, const double* sv,
@@ -104,12 +129,13 @@ void launch_setup(const ProblemShape& S, const DevLayout& L, const EvalBuffers& 
 void launch_k1(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st);
 void launch_cost(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, cudaStream_t st);
 // jac != 0: reduce the K1 output; else reduce seg_ssr to per-camera cost.  Returns the number of launches.
+// peer (world > 1): the fused layout's reduction all-reduces cam_sums over NVLink itself; *peer_done says whether it did.
 int launch_assemble(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ReduceDesc& R, int jac,
-                    cudaStream_t st);
+                    const calcomm::PeerArgs* peer, bool* peer_done, cudaStream_t st);
 int k1_num_passes(const ProblemShape& S);  // roles (warps per tile) of K1
 // fused K1: number of roles, values per tile and their index in a camera's cam_sums row
 void k1_tile_value_map(const ProblemShape& S, int* n_roles, int* nvt, std::vector<int32_t>* map);
-int launch_tile_reduce(const ProblemShape& S, const EvalBuffers& B, const ReduceDesc& R, int nvt, cudaStream_t st);
+int launch_tile_reduce(const ProblemShape& S, const EvalBuffers& B, const ReduceDesc& R, int nvt, const calcomm::PeerArgs& peer, cudaStream_t st);
 float dfma_peak_ms(double* scratch, int blocks, int threads, int iters, cudaStream_t st);
 
 // ---- per-view (Schur) machinery -------------------------------------------------

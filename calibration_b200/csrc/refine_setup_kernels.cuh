@@ -68,19 +68,7 @@ __global__ void k_block_setup(ProblemShape S, DevLayout L, EvalBuffers B) {
             for (int i = 0; i < 9; ++i) Rs[i] = cc.Rs[i];
         }
         BlockPose bp;
-        if (S.kind == 0) {
-            const int v = L.blk_view[b];
-            compose_intrinsics(B.x + S.off_viewq + 4 * v, B.x + S.off_viewt + 3 * v, bp);
-        } else if (S.kind == 1) {
-            const int v = L.blk_view[b];
-            compose_extrinsics(B.x + S.off_camq + 4 * cam, B.x + S.off_camt + 3 * cam, B.x + S.off_viewq + 4 * v,
-                               B.x + S.off_viewt + 3 * v, bp);
-        } else {
-            double bTg[12];
-            for (int i = 0; i < 12; ++i) bTg[i] = L.blk_bTg[(int64_t)i * L.n_blk + b];
-            compose_bundle(B.x + S.off_viewq, B.x + S.off_viewt, B.x + S.off_camq + 4 * cam, B.x + S.off_camt + 3 * cam,
-                           bTg, bp);
-        }
+        block_pose(S, L, B.x, b, cam, true, bp);
         block_frame(bp, Rs, A);
         view_transform(bp, Rs, T);
     }

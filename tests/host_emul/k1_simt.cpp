@@ -20,9 +20,8 @@ using namespace calk;
 
 namespace {
 
-// k_tile_colsum + k_tile_final (launch_tile_reduce, k1_fused.cu).  The product groups 32 tiles per chunk; one tile per
-// chunk here, so that k_tile_final's lane-strided sum over a camera's chunks and its shuffle tree see several chunks
-// per camera at test sizes.
+// k_tile_reduce (launch_tile_reduce, k1_fused.cu).  The product groups 32 tiles per chunk; one tile per chunk here, so
+// that the last-arriving CTA's sum over a camera's chunks sees several chunks per camera at test sizes.
 void tile_reduce(const ProblemShape& S, const DevLayout& L, const std::vector<double>& tile_vals, int nvt, const std::vector<int32_t>& vmap,
                  std::vector<double>& cam_sums) {
     std::vector<ColChunk> tc; std::vector<int32_t> to(S.n_cams + 1, 0);
@@ -32,8 +31,12 @@ void tile_reduce(const ProblemShape& S, const DevLayout& L, const std::vector<do
     }
     to[S.n_cams] = (int32_t)tc.size();
     std::vector<double> partial(tc.size() * (size_t)nvt);
-    simt::launch((unsigned)tc.size(), 256, [&] { k_tile_colsum(tile_vals.data(), nvt, tc.data(), partial.data()); });
-    simt::launch((unsigned)((S.n_cams * nvt + 7) / 8), 256, [&] { k_tile_final(partial.data(), to.data(), S.n_cams, nvt, vmap.data(), cam_sums.data(), S.NV); });
+    std::vector<unsigned> tickets(S.n_cams + 1, 0u);
+    int active = 0;
+    for (int c = 0; c < S.n_cams; ++c) active += to[c + 1] > to[c] ? 1 : 0;
+    const TileReduceArgs A{tile_vals.data(), nvt, tc.data(), partial.data(), to.data(), S.n_cams, vmap.data(), cam_sums.data(), S.NV, tickets.data(), active};
+    simt::launch((unsigned)tc.size(), 256, [&] { k_tile_reduce(A, calcomm::PeerArgs{}); });
+    for (unsigned t : tickets) if (t != 0u) std::abort();   // the last CTA leaves the tickets ready for the next launch
 }
 
 // setup + K1 + per-camera sums of the tile rows for one (model, intrinsics mode) instantiation

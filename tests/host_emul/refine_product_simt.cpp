@@ -87,10 +87,10 @@ void k1_tile_value_map(const ProblemShape& S, int* n_roles, int* nvt, std::vecto
     SIMT_DISPATCH(roles_info_t, view_rows, n_roles, nvt, map);
 }
 int k1_num_passes(const ProblemShape& S) { int r = 1; k1_tile_value_map(S, &r, nullptr, nullptr); return r; }
-int launch_tile_reduce(const ProblemShape& S, const EvalBuffers& B, const ReduceDesc& R, int nvt, cudaStream_t) {
-    simt::launch((unsigned)R.n_tile_chunks, 256, [&] { k_tile_colsum(B.tile_vals, nvt, R.tile_chunks, B.partial_tile); });
-    simt::launch((unsigned)((S.n_cams * nvt + 7) / 8), 256, [&] { k_tile_final(B.partial_tile, R.tile_cam_chunk_off, S.n_cams, nvt, B.tile_vmap, B.cam_sums, S.NV); });
-    return 2;
+int launch_tile_reduce(const ProblemShape& S, const EvalBuffers& B, const ReduceDesc& R, int nvt, const calcomm::PeerArgs& peer, cudaStream_t) {
+    const TileReduceArgs A{B.tile_vals, nvt, R.tile_chunks, B.partial_tile, R.tile_cam_chunk_off, S.n_cams, B.tile_vmap, B.cam_sums, S.NV, R.tile_tickets, R.n_active_cams};
+    simt::launch((unsigned)R.n_tile_chunks, 256, [&] { k_tile_reduce(A, peer); });
+    return 1;
 }
 float dfma_peak_ms(double*, int, int, int, cudaStream_t) { return 1.0f; }   // a benchmark utility: no meaning on the CPU
 
@@ -101,8 +101,10 @@ static void launch_view_part_t(const ProblemShape& S, const DevLayout& L, const 
     if (L.one_seg_per_blk) simt::launch(g, 128, [&] { k_view_part<MODEL, IMODE, true>(S, L, B); });
     else simt::launch(g, 128, [&] { k_view_part<MODEL, IMODE, false>(S, L, B); });
 }
-int launch_assemble(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ReduceDesc& R, int jac, cudaStream_t st) {
-    if (jac && L.fused) return launch_tile_reduce(S, B, R, R.nvt, st);
+int launch_assemble(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ReduceDesc& R, int jac, const calcomm::PeerArgs*, bool* peer_done,
+                    cudaStream_t st) {
+    if (peer_done) *peer_done = false;
+    if (jac && L.fused) return launch_tile_reduce(S, B, R, R.nvt, calcomm::PeerArgs{}, st);
     int launches = 0;
     const unsigned gb = (unsigned)((L.n_blk + 127) / 128);
     const int rr_row = S.NL * S.NC - S.NC * (S.NC - 1) / 2;
