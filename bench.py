@@ -32,6 +32,7 @@ WORKLOADS = {
     "c4": (4, 5000, "optimize_bundle<pinhole+BC5>: 4 cameras x 5000 robot poses x 88 corners (1.76M observations)"),
     "mini": (8, 2000, "optimize_bundle<pinhole+BC5>: 8 cameras x 2000 views x 88 corners (smoke size)"),
 }
+OTHER_WORKLOADS = ("c1", "c2", "c3", "c4", "c4-axxb")   # BASELINE configs[0]-[3]: bench_workloads.py (single GPU)
 CHUNK = 12500  # robot poses per generation chunk (8 chunks for c5)
 
 
@@ -442,7 +443,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c5", choices=sorted(set(WORKLOADS) | set(OTHER_WORKLOADS) | {"c4-pass"}),
+                    help="c5 (default, BASELINE configs[4]); c1 / c2 / c3 / c4 / c4-axxb: the other named shapes, single GPU")
+    ap.add_argument("--ransac-problems", type=int, default=100000)
+    ap.add_argument("--axxb-poses", type=int, default=5000)
     ap.add_argument("--fixed-intrinsics", action="store_true", help="BundleOptions default (optimize_intrinsics=false)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peer-allreduce", action="store_true", help="use NCCL for the per-pass all-reduce instead of the NVLink peer-memory kernel")
@@ -458,6 +462,25 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.workload == "c4-pass":   # the bundle pass alone at C4 size through the C5 code path (strong-scaling runs)
+        args.workload = "c4"
+    elif args.workload in OTHER_WORKLOADS:
+        if rank != 0:
+            return
+        import bench_workloads as W
+        if args.impl == "reference":
+            print(json.dumps(W.run_reference(args)), flush=True)
+            return
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)   # one JSON line on stdout: library chatter goes to stderr
+        try:
+            out = W.run(args, ClockSampler)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
+        return
     if args.probe_shared_board:
         run_board_probe(args)
     elif args.impl == "reference":

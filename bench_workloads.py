@@ -1,0 +1,345 @@
+"""The other named shapes of BASELINE.json (configs[0]-[3]) behind `bench.py --workload c1|c2|c3|c4|c4-axxb`.
+
+Same JSON contract as the default workload (bench.py): `value` is device-timed with the inputs resident in HBM (CUDA
+events on the launching stream inside the library), `e2e` is the same metric through the C ABI from HOST buffers with
+the copies inside the timed region, `roofline` describes the dominant kernel, `cpu_baseline` is the oracle port timed
+on the host cores.  Inputs of c1 / c3 / c4 / c4-axxb are smaller than the 126 MB L2, so L2 is flushed between timed
+iterations (a 512 MB device buffer is rewritten); c2 (1.6 GB) is larger than L2.
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+DESCR = {
+    "c1": ("configs[0]", "optimize_intrinsics<pinhole+BC5>: 20 views of a 9x6 checkerboard (1 080 observations), per-view poses (Schur path)"),
+    "c2": ("configs[1]", "batched RANSAC DLT homography: 100 000 image pairs x 500 correspondences, 30 % outliers, seed list = problem index"),
+    "c3": ("configs[2]", "optimize_extrinsics: 2 cameras x 1 000 views x 88 corners (176 000 observations), joint intrinsics + camera pose + per-view target poses (Schur path)"),
+    "c4": ("configs[3]", "optimize_bundle<pinhole+BC5>: 4 cameras x 5 000 robot poses x 88 corners (1.76 M observations), hand-eye + intrinsics + target pose, with covariance"),
+    "c4-axxb": ("configs[3]", "optimize_handeye (AX = XB): 5 000 robot poses, all 12.5 M motion pairs formed on the fly, with covariance"),
+}
+
+
+class L2Flush:
+    """Rewrites a buffer four times the size of the L2 so that the next timed pass starts cold."""
+
+    def __init__(self, device):
+        import torch
+        self.torch = torch
+        self.buf = torch.empty(512 << 20, dtype=torch.uint8, device=f"cuda:{device}")
+        self.k = 0
+
+    def __call__(self):
+        self.k = (self.k + 1) & 0x7f
+        self.buf.fill_(self.k)
+        self.torch.cuda.synchronize()
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def _base(args, metric, unit, value, ms_step, workload, extra_cfg):
+    return {"metric": metric, "value": value, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict({"workload": DESCR[workload][1], "baseline_config": DESCR[workload][0]}, **extra_cfg)}
+
+
+def _roofline(alg_bytes, kernel_ms, kernel, share, note, fp64=None):
+    pk, src = _peaks()
+    ach = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": ach, "peak": float(pk["hbm_gbs"]), "unit": "GB/s", "frac": ach / float(pk["hbm_gbs"]), "traffic": None,
+         "peak_source": src, "kernel": kernel, "kernel_ms_per_launch": kernel_ms, "kernel_share_of_step": share,
+         "algorithmic_bytes_per_launch": alg_bytes, "note": note}
+    if fp64:
+        r["fp64"] = fp64
+    return r
+
+
+def _oracle():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    return O
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# c1 / c3 / c4: refinement of the small named shapes
+# ----------------------------------------------------------------------------------------------------------------
+def _make_refine(workload, pinned):
+    from calibration_b200 import synth
+    if workload == "c1":
+        return synth.make_intrinsics()
+    if workload == "c3":
+        return synth.make_extrinsics(n_cams=2, n_views=1000)
+    return synth.make_bundle(seed=137, n_cams=4, n_poses=5000, pinned=pinned)
+
+
+def run_refine(args, clock_sampler_cls):
+    import torch
+    from calibration_b200 import abi, capi
+    prob, x0, xgt = _make_refine(args.workload, pinned=True)
+    n_obs = int(prob.desc.n_obs)
+    h = capi.RefineHandle(prob, device=0)
+    info = h.layout_info()
+    flush = L2Flush(0)
+    with clock_sampler_cls(0) as clk:
+        for _ in range(max(args.warmup, 3)):
+            h.bench_pass(x0, reps=1, jacobian=True)
+        ms_total = ms_k1 = 0.0
+        l0 = h.launch_count()
+        for _ in range(args.steps):
+            flush()
+            a, b, _ = h.bench_pass(x0, reps=1, jacobian=True)
+            ms_total += a; ms_k1 += b
+        launches = h.launch_count() - l0
+        # the same passes back to back (inputs L2-resident), as the LM sees them; also keeps the GPU busy for the clock sampler
+        ms_hot, _, _ = h.bench_pass(x0, reps=max(200, args.steps), jacobian=True)
+        ms_hot /= max(200, args.steps)
+        for _ in range(3):
+            h.bench_pass(x0, reps=400, jacobian=True)
+    h.close()
+    ms_step = ms_total / args.steps
+    opts = abi.OptimOptions.default(compute_covariance=1)
+    capi.RefineHandle(prob).solve(x0, opts)   # warm-up of the solve path (module load, pool growth)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    h2 = capi.RefineHandle(prob, device=0)
+    t1 = time.perf_counter()
+    x_fin, res, cov = h2.solve(x0, opts)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    launches_e2e = h2.launch_count()
+    h2.close()
+    e2e_s = time.perf_counter() - t0
+    n_jac = int(res.num_jac_evals)
+    blocks = int(prob.desc.n_blocks)
+    alg = 32 * n_obs + (96 * blocks if args.workload == "c4" else 0)
+    out = _base(args, "observations/s in residual+Jacobian+JtJ pass", "observations/s", n_obs / (ms_step * 1e-3), ms_step, args.workload,
+                {"observations_total": n_obs, "residual_blocks": blocks, "huber_delta": 1.0, "noise_px": 0.2,
+                 "l2_policy": "L2 flushed (512 MB rewritten) before every timed pass; ms_per_step_l2_resident is the back-to-back figure the LM sees",
+                 "k1_segments": info["n_segments"], "k1_passes": info["k1_passes"], "local_entries": info["local_entries"],
+                 "layout": "fused (one block per lane)" if blocks >= 16384 else "segment (blocks cut into short segments to fill the machine)"})
+    out["ms_per_step_l2_resident"] = ms_hot
+    out["clocks"] = clk.summary()
+    out["gpu_launches"] = launches
+    out["e2e"] = {"value": n_obs * n_jac / e2e_s, "unit": "observations/s", "h2d_bytes_per_step": alg, "d2h_bytes_per_step": int(8 * (len(x_fin) + cov.size)),
+                  "what": "cal_refine_create (H2D of all observations from host memory + layout) + cal_refine_solve (LM, covariance) + destroy; "
+                          "value = observations x Jacobian passes / wall time",
+                  "wall_s": e2e_s, "create_ms": 1e3 * (t1 - t0), "solve_ms": 1e3 * (t2 - t1), "lm_iterations": int(res.iterations), "jacobian_passes": n_jac,
+                  "cost_passes": int(res.num_cost_evals), "lm_iteration_ms": 1e3 * (t2 - t1) / max(int(res.iterations), 1), "converged": bool(res.success),
+                  "covariance": bool(res.covariance_ok), "final_cost": float(res.final_cost), "gpu_launches": launches_e2e,
+                  "max_abs_param_error_vs_ground_truth": float(np.abs(x_fin - xgt).max())}
+    out["roofline"] = _roofline(alg, ms_k1 / args.steps, "k1_kernel", ms_k1 / ms_total,
+                                "a problem of this size occupies a fraction of the 148 SMs for a few microseconds: the pass is bound by launch "
+                                "latency and the dependent chain of one tile, not by HBM or the FP64 pipe")
+    if not args.no_cpu_baseline:
+        O = _oracle()
+        cores = os.cpu_count() or 1
+        O.refine_eval(prob, x0, jac=True, threads=cores)
+        t0 = time.perf_counter()
+        reps = 3 if n_obs > 500000 else 20
+        for _ in range(reps):
+            O.refine_eval(prob, x0, jac=True, threads=cores)
+        dt = (time.perf_counter() - t0) / reps
+        # the restatement assembles the covariance densely (n^3): affordable for the bundle kinds, not for c3's 7 034 unknowns
+        want_cov = args.workload != "c3"
+        t0 = time.perf_counter()
+        _, r, _ = O.refine_solve(prob, x0, want_cov=want_cov)
+        ds = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_obs / dt, "unit": "observations/s", "cores": cores, "kind": "port",
+                               "sample": f"the whole workload ({n_obs} observations), {reps} fused passes of the forward-mode restatement, OpenMP over residual blocks",
+                               "ms_per_pass": dt * 1e3,
+                               "lm_solve": {"wall_s": ds, "iterations": int(r.iterations), "ms_per_iteration": 1e3 * ds / max(int(r.iterations), 1),
+                                            "converged": bool(r.success), "with_covariance": want_cov}}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# c2: batched RANSAC homography
+# ----------------------------------------------------------------------------------------------------------------
+def run_ransac(args, clock_sampler_cls):
+    import torch
+    from calibration_b200 import abi, capi, synth
+    npb, n = args.ransac_problems, 500
+    x, y, u, v, _ = synth.synth_ransac(seed=17, n_problems=npb, n=n)
+    pin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (x, y, u, v)]
+    dev = [p.cuda() for p in pin]
+    res = torch.empty(npb * C.sizeof(abi.RansacResult), dtype=torch.uint8, device="cuda")
+    mask = torch.empty(npb * n, dtype=torch.uint8, device="cuda")
+    opts = abi.RansacOptions.default()
+    L = capi.lib()
+    ms = C.c_float()
+
+    def launch():
+        rc = L.cal_ransac_homography_batch_dev(npb, n, *[C.c_void_p(d.data_ptr()) for d in dev], C.byref(opts), 1, C.c_void_p(res.data_ptr()),
+                                               C.c_void_p(mask.data_ptr()), C.byref(ms))
+        assert rc == 0, L.cal_last_error()
+        return ms.value
+    with clock_sampler_cls(0) as clk:
+        for _ in range(max(args.warmup, 3)):
+            launch()
+        tot = sum(launch() for _ in range(args.steps))
+        for _ in range(max(10, int(1500.0 / max(tot / args.steps, 0.05)))):
+            launch()
+    ms_step = tot / args.steps
+    r = np.frombuffer(res.cpu().numpy().tobytes(), dtype=np.dtype([("success", "i4"), ("iters", "i4"), ("n_inliers", "i4"), ("iters_run", "i4"),
+                                                                    ("h", "f8", 9), ("rms", "f8"), ("sym", "f8"), ("mm", "f8")]))
+    hyp = int(r["iters_run"].sum())
+    hx = [p.numpy() for p in pin]
+    capi.ransac_homography_batch(*hx, opts, want_mask=True)
+    t0 = time.perf_counter()
+    capi.ransac_homography_batch(*hx, opts, want_mask=True)
+    e2e_s = time.perf_counter() - t0
+    alg = 32 * npb * n
+    out = _base(args, "image pairs/s in batched RANSAC homography (DLT hypotheses, inlier scoring, refit)", "problems/s", npb / (ms_step * 1e-3), ms_step, "c2",
+                {"problems": npb, "correspondences": n, "outlier_fraction": 0.3, "max_iters": int(opts.max_iters), "thresh": float(opts.thresh),
+                 "l2_policy": f"inputs ({alg / 1e9:.2f} GB) larger than the 126 MB L2; no flush", "hypotheses_evaluated": hyp, "mean_hypotheses_per_problem": hyp / npb,
+                 "success": int(r["success"].sum()), "mean_inliers": float(r["n_inliers"].mean())})
+    out["clocks"] = clk.summary()
+    out["gpu_launches"] = args.steps
+    out["e2e"] = {"value": npb / e2e_s, "unit": "problems/s", "h2d_bytes_per_step": alg, "d2h_bytes_per_step": int(npb * (C.sizeof(abi.RansacResult) + n)),
+                  "what": "cal_ransac_homography_batch from pinned host arrays: H2D of the correspondences, the kernel, results and inlier masks back to the host",
+                  "wall_s": e2e_s}
+    out["roofline"] = _roofline(alg, ms_step, "k_ransac", 1.0,
+                                "correspondences are read once into shared memory; the kernel is bound by FP64 latency (4-point DLT by Householder QR, "
+                                "refit null vector by inverse iteration, one hypothesis per lane) and by the exact device-side replay of std::sample")
+    out["roofline"]["hypothesis_point_scores_per_s"] = hyp * n / (ms_step * 1e-3)
+    if not args.no_cpu_baseline:
+        O = _oracle()
+        k = min(npb, 4000)
+        cores = os.cpu_count() or 1
+        O.ransac_batch(x[:256], y[:256], u[:256], v[:256], opts)
+        t0 = time.perf_counter(); O.ransac_batch(x[:k], y[:k], u[:k], v[:k], opts); dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": k / dt, "unit": "problems/s", "cores": cores, "kind": "port",
+                               "sample": f"the first {k} problems, restatement of ransac<HomographyEstimator> (bit-equal to the reference's own loop template), OpenMP over problems"}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# c4-axxb: hand-eye AX = XB refinement from the pose lists
+# ----------------------------------------------------------------------------------------------------------------
+def run_axxb(args, clock_sampler_cls):
+    import torch
+    from calibration_b200 import abi, capi, geometry as G, synth
+    n = args.axxb_poses
+    bg, ct, X_gt = synth.make_handeye_poses(seed=3, n=n)
+    rng = np.random.default_rng(0)
+    ct = [synth.perturb_pose(rng, T, 0.3, 0.002) for T in ct]
+    x0 = G.pack_handeye(synth.perturb_pose(rng, X_gt, 2.0, 0.01))
+    h = capi.AxxbHandle.from_poses(bg, ct, 0.05)
+    n_pairs = int(h.n_pairs)
+    flush = L2Flush(0)
+    with clock_sampler_cls(0) as clk:
+        for _ in range(max(args.warmup, 3)):
+            h.bench_pass(x0, 1)
+        tot = 0.0
+        for _ in range(args.steps):
+            flush()
+            tot += h.bench_pass(x0, 1)
+        for _ in range(3):
+            h.bench_pass(x0, 300)
+    h.close()
+    ms_step = tot / args.steps
+    opts = abi.OptimOptions.default(compute_covariance=1)
+    capi.AxxbHandle.from_poses(bg, ct, 0.05).solve(x0, opts)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    h2 = capi.AxxbHandle.from_poses(bg, ct, 0.05)
+    t1 = time.perf_counter()
+    x_fin, res, cov = h2.solve(x0, opts)
+    t2 = time.perf_counter()
+    h2.close()
+    e2e_s = time.perf_counter() - t0
+    n_jac = int(res.num_jac_evals)
+    alg = 2 * 96 * n   # the two pose lists, read per tile from L2; pairs are never materialised
+    out = _base(args, "motion pairs/s in AX=XB residual+Jacobian+JtJ pass", "pairs/s", n_pairs / (ms_step * 1e-3), ms_step, "c4-axxb",
+                {"poses": n, "pairs_kept": n_pairs, "pairs_candidate": n * (n - 1) // 2, "huber_delta": 0.05,
+                 "l2_policy": "L2 flushed (512 MB rewritten) before every timed pass (the inputs are 2 x 96 B per pose)"})
+    out["clocks"] = clk.summary()
+    out["gpu_launches"] = 2 * args.steps
+    out["e2e"] = {"value": n_pairs * n_jac / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": alg, "d2h_bytes_per_step": 8 * (7 + 49),
+                  "what": "cal_axxb_create_from_poses (H2D of the pose lists, build_all_pairs mask on the device) + cal_axxb_solve (LM, covariance) + destroy; "
+                          "value = pairs x Jacobian passes / wall time",
+                  "wall_s": e2e_s, "create_ms": 1e3 * (t1 - t0), "solve_ms": 1e3 * (t2 - t1), "lm_iterations": int(res.iterations), "jacobian_passes": n_jac,
+                  "lm_iteration_ms": 1e3 * (t2 - t1) / max(int(res.iterations), 1), "converged": bool(res.success),
+                  "rotation_error_deg_vs_ground_truth": float(np.rad2deg(G.rotation_angle(G.quat_to_rotmat(x_fin[:4]).T @ X_gt[:3, :3])))}
+    out["roofline"] = _roofline(alg, ms_step, "k_axxb_otf", 1.0,
+                                "pairs are formed from 2 x 32 poses staged in shared memory per tile: the pass touches 1 MB of HBM and is bound by FP64 "
+                                "(SO(3) projection by a Newton polar iteration, rotation log, analytic 6x6 Jacobian per pair)")
+    if not args.no_cpu_baseline:
+        O = _oracle()
+        k = min(n, 600)   # bounded sample: all pairs of the first k poses
+        cores = os.cpu_count() or 1
+        ra, rb, ta, tb = O.build_all_pairs(bg[:k], ct[:k], 0.5)
+        d = O.axxb_desc(ra, rb, ta, tb, 0.05)
+        O.axxb_eval(d, x0, threads=cores)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            O.axxb_eval(d, x0, threads=cores)
+        dt = (time.perf_counter() - t0) / 5
+        out["cpu_baseline"] = {"value": len(ta) / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                               "sample": f"all {len(ta)} kept pairs of the first {k} poses (materialised by the restatement of build_all_pairs), 5 passes of the "
+                                         "dual-number restatement of AxXbResidual, OpenMP over pairs"}
+    return out
+
+
+def run(args, clock_sampler_cls):
+    if args.workload in ("c1", "c3", "c4"):
+        return run_refine(args, clock_sampler_cls)
+    if args.workload == "c2":
+        return run_ransac(args, clock_sampler_cls)
+    return run_axxb(args, clock_sampler_cls)
+
+
+def run_reference(args):
+    """CPU arm of the same workloads: the oracle port on all host cores, bounded samples (see cpu_baseline above)."""
+    O = _oracle()
+    cores = os.cpu_count() or 1
+    if args.workload in ("c1", "c3", "c4"):
+        prob, x0, _ = _make_refine(args.workload, pinned=False)
+        n = int(prob.desc.n_obs)
+        for _ in range(min(args.warmup, 1)):
+            O.refine_eval(prob, x0, jac=True, threads=cores)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.refine_eval(prob, x0, jac=True, threads=cores)
+        dt = (time.perf_counter() - t0) / args.steps
+        metric, unit, value, sample = "observations/s in residual+Jacobian+JtJ pass", "observations/s", n / dt, f"the whole workload ({n} observations) per step"
+    elif args.workload == "c2":
+        from calibration_b200 import abi, synth
+        k = min(args.ransac_problems, 4000)
+        x, y, u, v, _ = synth.synth_ransac(seed=17, n_problems=k, n=500)
+        opts = abi.RansacOptions.default()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.ransac_batch(x, y, u, v, opts)
+        dt = (time.perf_counter() - t0) / args.steps
+        metric, unit, value, sample = "image pairs/s in batched RANSAC homography (DLT hypotheses, inlier scoring, refit)", "problems/s", k / dt, f"the first {k} problems per step"
+    else:
+        from calibration_b200 import geometry as G, synth
+        k = min(args.axxb_poses, 600)
+        bg, ct, X_gt = synth.make_handeye_poses(seed=3, n=k)
+        rng = np.random.default_rng(0)
+        ct = [synth.perturb_pose(rng, T, 0.3, 0.002) for T in ct]
+        x0 = G.pack_handeye(synth.perturb_pose(rng, X_gt, 2.0, 0.01))
+        ra, rb, ta, tb = O.build_all_pairs(bg, ct, 0.5)
+        d = O.axxb_desc(ra, rb, ta, tb, 0.05)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.axxb_eval(d, x0, threads=cores)
+        dt = (time.perf_counter() - t0) / args.steps
+        metric, unit, value, sample = "motion pairs/s in AX=XB residual+Jacobian+JtJ pass", "pairs/s", len(ta) / dt, f"all {len(ta)} kept pairs of the first {k} poses per step"
+    return {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": DESCR[args.workload][1], "note": "CPU restatement (oracle) of the reference's path; Ceres/Eigen are absent from this image"},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

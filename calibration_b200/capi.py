@@ -63,6 +63,7 @@ def lib():
         ("cal_axxb_destroy", [hp]),
         ("cal_axxb_eval", [hp, dp, dp, dp, dp]),
         ("cal_axxb_solve", [hp, C.POINTER(abi.OptimOptions), dp, C.POINTER(abi.OptimResult), dp]),
+        ("cal_axxb_bench_pass", [hp, dp, C.c_int, C.POINTER(C.c_float)]),
         ("cal_ransac_homography_batch", [i64, C.c_int32, dp, dp, dp, dp, C.POINTER(abi.RansacOptions), C.c_int, C.c_int,
                                          C.POINTER(abi.RansacResult), u8p]),
         ("cal_seed_intrinsics", [i64, abi.c_int64_p, ip, dp, dp, dp, dp, C.c_int32, C.POINTER(abi.SeedOptions), C.c_int, dp, ip,
@@ -288,6 +289,12 @@ class AxxbHandle:
         cost = C.c_double(); g = np.zeros(6); H = np.zeros((6, 6))
         _check(lib().cal_axxb_eval(self._h, abi.dptr(abi.as_f64(x7)), C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g), abi.dptr(H)))
         return cost.value, g, H
+
+    def bench_pass(self, x7, reps=1):
+        """device time (ms, CUDA events on the handle's stream) of `reps` residual + Jacobian passes"""
+        ms = C.c_float()
+        _check(lib().cal_axxb_bench_pass(self._h, abi.dptr(abi.as_f64(x7)), reps, C.byref(ms)))
+        return ms.value
 
     def solve(self, x7, opts=None):
         x = abi.as_f64(x7).copy()

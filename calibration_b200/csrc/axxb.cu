@@ -170,6 +170,29 @@ extern "C" cal_status cal_axxb_eval(cal_axxb_handle* h, const double* x7, double
     return axxb_pass(*h, x7, g6 || H36, cost, g6, H36);
 }
 
+// benchmark hook: `reps` Jacobian passes back to back on the handle's stream, timed with CUDA events on that stream
+extern "C" cal_status cal_axxb_bench_pass(cal_axxb_handle* h, const double* x7, int reps, float* ms_total) {
+    if (!h || !x7 || reps <= 0 || !ms_total) return afail(CAL_ERR_INVALID_ARGUMENT, "bad argument");
+    ACUDA(cudaSetDevice(h->device));
+    ACUDA(cudaMemcpyAsync(h->x, x7, 7 * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    cudaEvent_t e0, e1; ACUDA(cudaEventCreate(&e0)); ACUDA(cudaEventCreate(&e1));
+    ACUDA(cudaStreamSynchronize(h->st));
+    ACUDA(cudaEventRecord(e0, h->st));
+    for (int r = 0; r < reps; ++r) {
+        if (h->from_poses) k_axxb_otf<1><<<h->n_cta, 256, 0, h->st>>>(h->tiles, h->x, h->huber, h->partial);
+        else k_axxb<1><<<h->n_cta, 256, 0, h->st>>>(h->pairs, h->n, h->x, h->huber, h->partial);
+        k_axxb_final<<<1, 32 * kAcc, 0, h->st>>>(h->partial, h->n_cta, h->out);
+        h->launches += 2;
+    }
+    ACUDA(cudaEventRecord(e1, h->st));
+    ACUDA(cudaEventSynchronize(e1));
+    ACUDA(cudaGetLastError());
+    ACUDA(cudaEventElapsedTime(ms_total, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return CAL_OK;
+}
+extern "C" int64_t cal_axxb_launch_count(const cal_axxb_handle* h) { return h ? h->launches : 0; }
+
 // LM with Ceres 2.2 trust-region semantics on the dense 6x6 system.
 extern "C" cal_status cal_axxb_solve(cal_axxb_handle* hp, const cal_optim_options* o, double* x7, cal_optim_result* res,
                                      double* cov49) {

@@ -392,10 +392,10 @@ struct TileReduceArgs {
     int n_active_cams;                                // cameras that own at least one chunk on this GPU
 };
 __global__ void __launch_bounds__(256) k_tile_reduce(const TileReduceArgs A, const calcomm::PeerArgs peer) {
-#if defined(CALIB_SIMT_SHIM)
-    static int s_last, s_bad;   // tests/host_emul runs one CTA at a time
-#else
+#if defined(__CUDACC__)
     __shared__ int s_last, s_bad;
+#else
+    static int s_last, s_bad;   // host build of this source (tests/host_emul): one CTA runs at a time
 #endif
     const ColChunk c = A.chunks[blockIdx.x];
     const int nvt = A.nvt;

@@ -106,6 +106,16 @@ struct cal_refine_handle : calk::HostModel {
     std::vector<double> Hss, gs, cam_sums;
     double cost = 0;
     calcomm::Comm* comm = nullptr;  // not owned (cal_comm_create / cal_comm_destroy)
+    // Small results come back through ONE page-locked block, so that their device-to-host copies are truly
+    // asynchronous (a copy into pageable memory blocks the host like a synchronisation):
+    //   [0, 4) red of the step  | [4, 8) red of the candidate | [8, 12) red of the norms | [12, 16) flags (int32 pairs)
+    //   [16, 16 + ns) y of the reduced solve | then cam_sums [n_cams * NV]
+    double* pin = nullptr; size_t pin_doubles = 0;
+    double* dSm = nullptr; double* dgss = nullptr; int32_t* dinfo = nullptr;   // reduced system of one LM iteration (device)
+    double* pin_red(int k) const { return pin + 4 * k; }
+    int32_t* pin_flags() const { return reinterpret_cast<int32_t*>(pin + 12); }
+    double* pin_y() const { return pin + 16; }
+    double* pin_sums() const { return pin + 16 + std::max(ns, 1); }
     // counters
     int64_t launches = 0;
 
@@ -128,6 +138,7 @@ struct cal_refine_handle : calk::HostModel {
     ~cal_refine_handle() {
         for (void* p : allocs) cudaFree(p);
         if (arena && st) { cudaFreeAsync(arena, st); cudaStreamSynchronize(st); }
+        if (pin) cudaFreeHost(pin);
         if (st) cudaStreamDestroy(st);
     }
 };
@@ -440,6 +451,10 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         CUDA_TRY(cudaMemsetAsync(V.sp, 0, sizeof(double) * nv * 6, us));
     }
     CUDA_TRY(h.alloc(&h.V.x_cand, h.n_amb));
+    CUDA_TRY(h.alloc(&h.dSm, (size_t)std::max(h.ns, 1) * std::max(h.ns, 1))); CUDA_TRY(h.alloc(&h.dgss, std::max(h.ns, 1))); CUDA_TRY(h.alloc(&h.dinfo, 2));
+    h.pin_doubles = 16 + (size_t)std::max(h.ns, 1) + (size_t)S.n_cams * S.NV;
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h.pin), h.pin_doubles * sizeof(double), cudaHostAllocDefault));
+    std::memset(h.pin, 0, h.pin_doubles * sizeof(double));
     lap("host set-up done");
     CUDA_TRY(cudaStreamSynchronize(us));
     CUDA_TRY(cudaStreamSynchronize(h.st));
@@ -478,19 +493,26 @@ cal_status reduce_pass(cal_refine_handle& h, const EvalBuffers& B, bool jac) {
 // x_dev must already hold the parameters.  After a Jacobian pass the host
 // mirrors h.Hss / h.gs / h.cost describe the shared block; per-view blocks stay
 // on the device (h.V.Hpp, h.V.gp, B.blk_E*).
-cal_status device_pass(cal_refine_handle& h, double* x_dev, bool jac, const double* x_host) {
+cal_status device_pass(cal_refine_handle& h, double* x_dev, bool jac, const double* x_host, bool with_norms = false) {
     EvalBuffers B = h.B; B.x = x_dev;
     const ProblemShape& S = h.S;
     launch_setup(S, h.L, B, h.st);
     if (jac) launch_k1(S, h.L, B, h.st); else launch_cost(S, h.L, B, h.st);
     const int NV = jac ? S.NV : 1;
     if (cal_status st = reduce_pass(h, B, jac)) return st;
-    h.cam_sums.resize((size_t)S.n_cams * NV);
-    CUDA_TRY(cudaMemcpyAsync(h.cam_sums.data(), B.cam_sums, h.cam_sums.size() * sizeof(double), cudaMemcpyDeviceToHost, h.st));
-    if (jac && S.n_views > 0) { launch_view_gather(S, h.L, B, h.V, h.st); h.launches++; }
+    const size_t n_sums = (size_t)S.n_cams * NV;
+    CUDA_TRY(cudaMemcpyAsync(h.pin_sums(), B.cam_sums, n_sums * sizeof(double), cudaMemcpyDeviceToHost, h.st));
+    if (jac && S.n_views > 0) {
+        launch_view_gather(S, h.L, B, h.V, h.st); h.launches++;
+        if (with_norms) {   // |x|^2 and the gradient max-norm of the per-view blocks at this point (red slot 2), same synchronisation
+            launch_view_norms(S, B, h.V, h.st); launch_reduce_views(h.V, S.n_views, h.st); h.launches += 2;
+            CUDA_TRY(cudaMemcpyAsync(h.pin_red(2), h.V.red_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, h.st));
+        }
+    }
     CUDA_TRY(cudaStreamSynchronize(h.st));
     CUDA_TRY(cudaGetLastError());
     if (h.comm && !h.comm->check_timeout()) return fail(CAL_ERR_COMM, h.comm->error());
+    h.cam_sums.assign(h.pin_sums(), h.pin_sums() + n_sums);
     double cost = 0;
     for (int c = 0; c < S.n_cams; ++c) cost += h.cam_sums[(size_t)c * NV + (jac ? S.NE : 0)];
     h.cost = cost;
@@ -667,6 +689,7 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
                                        cal_optim_result* res, double* cov) {
     if (!hp || !o || !x_inout || !res) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
     cal_refine_handle& h = *hp;
+    const auto t_solve_start = std::chrono::steady_clock::now();
     CUDA_TRY(cudaSetDevice(h.device));
     std::memset(res, 0, sizeof *res);
     const ProblemShape& S = h.S;
@@ -690,17 +713,15 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
     int term = CAL_TERM_NO_CONVERGENCE, iter = 0, n_invalid = 0, jev = 0, cev = 0;
     std::string msg;
 
+    // the Jacobian passes of this solve carry the per-view norms along (device_pass(..., with_norms)): one synchronisation
     auto norms = [&](double& x_norm, double& gmax) -> cal_status {
-        // |x|_2 and |x - Plus(x, -g)|_inf (ambient), shared part on the host, view part on the device
+        // |x|_2 and |x - Plus(x, -g)|_inf (ambient), shared part on the host, view part from the pass (red slot 2)
         double x2 = 0, gm = 0;
         std::vector<double> ng(std::max(ns, 1)); for (int i = 0; i < ns; ++i) ng[i] = -h.gs[i];
         plus_shared(h, x.data(), ng.data(), 1.0, xp.data());
         for (int i = 0; i < n_shared_amb; ++i) { x2 += x[i] * x[i]; gm = std::max(gm, std::fabs(x[i] - xp[i])); }
         if (views) {
-            EvalBuffers Bx = B; Bx.x = xd;
-            launch_view_norms(S, Bx, V, h.st); launch_reduce_views(V, nv, h.st); h.launches += 2;
-            CUDA_TRY(cudaMemcpyAsync(red, V.red_out, sizeof red, cudaMemcpyDeviceToHost, h.st));
-            CUDA_TRY(cudaStreamSynchronize(h.st));
+            std::memcpy(red, h.pin_red(2), sizeof red);
             if (h.comm) {  // the views of the other ranks
                 if (!h.comm->allreduce_host(&red[0], 1, false) || !h.comm->allreduce_host(&red[3], 1, true)) return fail(CAL_ERR_COMM, h.comm->error());
             }
@@ -715,26 +736,49 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
         return CAL_OK;
     };
     // candidate x [+] t*delta: shared part on the host (uploaded), view part on the device
-    auto make_candidate = [&](double t, double& step_norm2) -> cal_status {
+    // (queued only: the evaluation of the candidate that follows synchronises once for both; finish_candidate then adds
+    // the per-view part of |dx|^2 from red slot 1)
+    double cand_shared_norm2 = 0;
+    auto make_candidate = [&](double t) -> cal_status {
         plus_shared(h, x.data(), delta.data(), t, xp.data());
         double sn = 0; for (int i = 0; i < n_shared_amb; ++i) { const double dd = x[i] - xp[i]; sn += dd * dd; }
+        cand_shared_norm2 = sn;
         CUDA_TRY(cudaMemcpyAsync(xc, xp.data(), sizeof(double) * n_shared_amb, cudaMemcpyHostToDevice, h.st));
         if (views) {
             EvalBuffers Bx = B; Bx.x = xd; ViewBuffers Vx = V; Vx.x_cand = xc;
             launch_view_plus(S, Bx, Vx, t, h.st); launch_reduce_views(V, nv, h.st); h.launches += 2;
-            CUDA_TRY(cudaMemcpyAsync(red, V.red_out, sizeof red, cudaMemcpyDeviceToHost, h.st));
-            CUDA_TRY(cudaStreamSynchronize(h.st));
-            if (h.comm && !h.comm->allreduce_host(&red[2], 1, false)) return fail(CAL_ERR_COMM, h.comm->error());
-            sn += red[2];
+            CUDA_TRY(cudaMemcpyAsync(h.pin_red(1), V.red_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, h.st));
+        }
+        return CAL_OK;
+    };
+    auto finish_candidate = [&](double& step_norm2) -> cal_status {   // after the synchronisation of the candidate's pass
+        double sn = cand_shared_norm2;
+        if (views) {
+            double r2 = h.pin_red(1)[2];
+            if (h.comm && !h.comm->allreduce_host(&r2, 1, false)) return fail(CAL_ERR_COMM, h.comm->error());
+            sn += r2;
         }
         step_norm2 = sn;
         return CAL_OK;
     };
 
-    if (cal_status st = device_pass(h, xd, true, x.data())) return st;
+    if (cal_status st = device_pass(h, xd, true, x.data(), true)) return st;
     ++jev;
     double cost = h.cost;
     res->initial_cost = cost;
+    // Speculative Jacobian (kinds without per-view unknowns): a candidate that follows an accepted step is evaluated with
+    // the FULL fused pass — K1 yields the cost as well — so an accepted step costs one pass over the observations, not a
+    // residual-only pass plus a Jacobian pass at the same point.  The accepted point's system (host mirrors) is kept
+    // aside and comes back when the candidate is rejected or the solve stops on it; after a rejection the next
+    // candidate is evaluated cost-only (rejections cluster).  Counters keep the reference's meaning: one cost
+    // evaluation per candidate, one Jacobian evaluation per accepted point.
+    bool speculate = !views && getenv("CALIB_B200_NO_SPECULATION") == nullptr;
+    bool spec_live = false;                       // the host mirrors describe the candidate, not the accepted point
+    std::vector<double> keep_H, keep_g, keep_sums; double keep_cost = 0;
+    auto spec_restore = [&]() {
+        if (!spec_live) return;
+        h.Hss.swap(keep_H); h.gs.swap(keep_g); h.cam_sums.swap(keep_sums); h.cost = keep_cost; spec_live = false;
+    };
     for (int i = 0; i < ns; ++i) s[i] = 1.0 / (1.0 + std::sqrt(h.Hss[(size_t)i * ns + i]));  // jacobi_scaling, once
     if (views) {
         CUDA_TRY(cudaMemcpyAsync(V.s_shared, s.data(), sizeof(double) * ns, cudaMemcpyHostToDevice, h.st));
@@ -763,27 +807,46 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
         }
         std::vector<double> Hs_scaled = Sm;  // undamped, for the model cost change
         for (int i = 0; i < ns; ++i) Sm[(size_t)i * ns + i] += diag[i] / radius;
+        bool solved_on_device = false;   // per-view kinds: y of the reduced system and the per-view scalars are already here
         if (views) {
             CUDA_TRY(cudaMemsetAsync(V.fail, 0, sizeof(int32_t), h.st));
             launch_schur(S, h.L, B, V, ns, radius, h.st); h.launches += 3;
             if (h.comm) {
                 if (!h.comm->allreduce_sum(V.C, (size_t)ns * ns, h.st) || !h.comm->allreduce_sum(V.c, ns, h.st)) return fail(CAL_ERR_COMM, h.comm->error());
             }
-            int32_t failed = 0;
-            CUDA_TRY(cudaMemcpyAsync(Cs.data(), V.C, sizeof(double) * ns * ns, cudaMemcpyDeviceToHost, h.st));
-            CUDA_TRY(cudaMemcpyAsync(cs.data(), V.c, sizeof(double) * ns, cudaMemcpyDeviceToHost, h.st));
-            CUDA_TRY(cudaMemcpyAsync(&failed, V.fail, sizeof failed, cudaMemcpyDeviceToHost, h.st));
+            int32_t* flags = h.pin_flags();
+            if (ns > 0 && ns <= kReducedMaxN) {
+                // the reduced system is solved where the Schur complement lies and the back-substitution follows in
+                // stream order: ONE synchronisation per solve (y, the per-view scalars and the two flags come back together)
+                CUDA_TRY(cudaMemcpyAsync(h.dSm, Sm.data(), sizeof(double) * ns * ns, cudaMemcpyHostToDevice, h.st));
+                CUDA_TRY(cudaMemcpyAsync(h.dgss, gss.data(), sizeof(double) * ns, cudaMemcpyHostToDevice, h.st));
+                launch_reduced_solve(h.dSm, h.dgss, V, ns, h.dinfo, h.st);
+                launch_backsub(S, h.L, V, ns, h.st); launch_reduce_views(V, nv, h.st); h.launches += 3;
+                CUDA_TRY(cudaMemcpyAsync(h.pin_y(), V.y_shared, sizeof(double) * ns, cudaMemcpyDeviceToHost, h.st));
+                CUDA_TRY(cudaMemcpyAsync(h.pin_red(0), V.red_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, h.st));
+                CUDA_TRY(cudaMemcpyAsync(&flags[0], V.fail, sizeof(int32_t), cudaMemcpyDeviceToHost, h.st));
+                CUDA_TRY(cudaMemcpyAsync(&flags[1], h.dinfo, sizeof(int32_t), cudaMemcpyDeviceToHost, h.st));
+                solved_on_device = true;
+            } else {   // a shared block too wide for one CTA's shared memory: the Schur complement comes to the host
+                CUDA_TRY(cudaMemcpyAsync(Cs.data(), V.C, sizeof(double) * ns * ns, cudaMemcpyDeviceToHost, h.st));
+                CUDA_TRY(cudaMemcpyAsync(cs.data(), V.c, sizeof(double) * ns, cudaMemcpyDeviceToHost, h.st));
+                CUDA_TRY(cudaMemcpyAsync(&flags[0], V.fail, sizeof(int32_t), cudaMemcpyDeviceToHost, h.st));
+                flags[1] = 0;
+            }
             CUDA_TRY(cudaStreamSynchronize(h.st));
+            CUDA_TRY(cudaGetLastError());
             if (h.comm && !h.comm->check_timeout()) return fail(CAL_ERR_COMM, h.comm->error());
+            int32_t failed = flags[0];
             if (h.comm) {  // a failed view factorisation on any rank invalidates the step on every rank
                 double f = failed ? 1.0 : 0.0;
                 if (!h.comm->allreduce_host(&f, 1, true)) return fail(CAL_ERR_COMM, h.comm->error());
                 failed = f != 0.0;
             }
             if (failed) ok = false;
-            for (int i = 0; i < ns; ++i) { y[i] -= cs[i]; for (int j = 0; j < ns; ++j) Sm[(size_t)i * ns + j] -= Cs[(size_t)i * ns + j]; }
+            if (solved_on_device) { if (flags[1]) ok = false; for (int i = 0; i < ns; ++i) y[i] = h.pin_y()[i]; }
+            else for (int i = 0; i < ns; ++i) { y[i] -= cs[i]; for (int j = 0; j < ns; ++j) Sm[(size_t)i * ns + j] -= Cs[(size_t)i * ns + j]; }
         }
-        if (ok && ns > 0) { ok = chol_host(Sm, ns); if (ok) chol_solve_host(Sm, ns, y.data()); }
+        if (ok && ns > 0 && !solved_on_device) { ok = chol_host(Sm, ns); if (ok) chol_solve_host(Sm, ns, y.data()); }
         reuse_diag = true;
         double model_cost_change = 0;
         if (ok) {
@@ -791,10 +854,14 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
             for (int i = 0; i < ns; ++i) { if (!std::isfinite(y[i])) ok = false; step[i] = -y[i]; sg += step[i] * gss[i]; }
             for (int i = 0; i < ns; ++i) { double row = 0; for (int j = 0; j < ns; ++j) row += Hs_scaled[(size_t)i * ns + j] * step[j]; quad += row * step[i]; }
             if (views && ok) {
-                CUDA_TRY(cudaMemcpyAsync(V.y_shared, y.data(), sizeof(double) * ns, cudaMemcpyHostToDevice, h.st));
-                launch_backsub(S, h.L, V, ns, h.st); launch_reduce_views(V, nv, h.st); h.launches += 2;
-                CUDA_TRY(cudaMemcpyAsync(red, V.red_out, sizeof red, cudaMemcpyDeviceToHost, h.st));
-                CUDA_TRY(cudaStreamSynchronize(h.st));
+                if (solved_on_device) std::memcpy(red, h.pin_red(0), sizeof red);
+                else {
+                    CUDA_TRY(cudaMemcpyAsync(V.y_shared, y.data(), sizeof(double) * ns, cudaMemcpyHostToDevice, h.st));
+                    launch_backsub(S, h.L, V, ns, h.st); launch_reduce_views(V, nv, h.st); h.launches += 2;
+                    CUDA_TRY(cudaMemcpyAsync(h.pin_red(0), V.red_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, h.st));
+                    CUDA_TRY(cudaStreamSynchronize(h.st));
+                    std::memcpy(red, h.pin_red(0), sizeof red);
+                }
                 if (h.comm) { double r2[2] = {red[0], red[1]}; if (!h.comm->allreduce_host(r2, 2)) return fail(CAL_ERR_COMM, h.comm->error()); red[0] = r2[0]; red[1] = r2[1]; }
                 sg += red[0]; quad += red[1];
                 if (!std::isfinite(sg) || !std::isfinite(quad)) ok = false;
@@ -818,10 +885,18 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
                 g0 += red[0];
             }
             for (int ls = 0; ls < 20; ++ls) {
-                if (cal_status st = make_candidate(t, step_norm2)) return st;
-                double c; if (cal_status st = eval_cost_at(xc, xp.data(), c)) return st;
+                if (cal_status st = make_candidate(t)) return st;
+                double c;
+                if (speculate && ls == 0) {   // the full step: almost always accepted, so take the Jacobian along
+                    keep_H = h.Hss; keep_g = h.gs; keep_sums = h.cam_sums; keep_cost = h.cost;
+                    if (cal_status st = device_pass(h, xc, true, xp.data())) return st;
+                    spec_live = true; ++cev;
+                    c = std::isfinite(h.cost) ? h.cost : std::numeric_limits<double>::max();
+                } else if (cal_status st = eval_cost_at(xc, xp.data(), c)) return st;
+                if (cal_status st = finish_candidate(step_norm2)) return st;
                 const bool v = c < std::numeric_limits<double>::max();
                 if (v && c <= cost + 1e-4 * g0 * t) { cand_cost = c; have_cand = true; break; }
+                spec_restore();   // the search goes on with shorter steps, cost only
                 double tn = 0.5 * t;
                 if (v) { const double denom = 2.0 * (c - cost - g0 * t); if (denom > 0) tn = -g0 * t * t / denom; }
                 t = std::min(std::max(tn, 1e-3 * t), 0.6 * t);
@@ -829,27 +904,40 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
             if (!have_cand) t = 1.0;
         }
         if (!have_cand) {
-            if (cal_status st = make_candidate(t, step_norm2)) return st;
-            if (cal_status st = eval_cost_at(xc, xp.data(), cand_cost)) return st;
+            if (cal_status st = make_candidate(t)) return st;
+            if (speculate && !h.constrained) {
+                keep_H = h.Hss; keep_g = h.gs; keep_sums = h.cam_sums; keep_cost = h.cost;
+                if (cal_status st = device_pass(h, xc, true, xp.data())) return st;
+                spec_live = true; ++cev;
+                cand_cost = std::isfinite(h.cost) ? h.cost : std::numeric_limits<double>::max();
+            } else if (cal_status st = eval_cost_at(xc, xp.data(), cand_cost)) return st;
+            if (cal_status st = finish_candidate(step_norm2)) return st;
         }
         // ParameterToleranceReached / FunctionToleranceReached: tested before acceptance (B.3-5)
-        if (std::sqrt(step_norm2) <= eps * (x_norm + eps)) { term = CAL_TERM_CONVERGENCE; msg = "Parameter tolerance reached."; break; }
+        if (std::sqrt(step_norm2) <= eps * (x_norm + eps)) { spec_restore(); term = CAL_TERM_CONVERGENCE; msg = "Parameter tolerance reached."; break; }
         const double cost_change = cost - cand_cost;
-        if (std::fabs(cost_change) <= eps * cost) { term = CAL_TERM_CONVERGENCE; msg = "Function tolerance reached."; break; }
+        if (std::fabs(cost_change) <= eps * cost) { spec_restore(); term = CAL_TERM_CONVERGENCE; msg = "Function tolerance reached."; break; }
         const double rho = cost_change / model_cost_change;
         if (rho > min_relative_decrease) {  // HandleSuccessfulStep
             std::swap(xd, xc);
             for (int i = 0; i < n_shared_amb; ++i) x[i] = xp[i];
-            if (cal_status st = device_pass(h, xd, true, x.data())) return st;
+            if (spec_live) spec_live = false;   // the candidate's system IS the new point's
+            else if (cal_status st = device_pass(h, xd, true, x.data(), true)) return st;
+            speculate = !views && getenv("CALIB_B200_NO_SPECULATION") == nullptr;
             ++jev; cost = h.cost;
             if (cal_status st = norms(x_norm, gmax)) return st;
             radius = std::min(max_radius, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));
             decrease_factor = 2.0; reuse_diag = false;
         } else {  // HandleUnsuccessfulStep
+            spec_restore(); speculate = false;
             radius /= decrease_factor; decrease_factor *= 2.0; reuse_diag = true;
         }
         if (o->verbose) std::printf("%4d % .6e %.2e %.2e %.2e rho=%.2e\n", iter, cost, cost_change, gmax, radius, rho);
     }
+    const bool trace = getenv("CALIB_B200_TRACE") != nullptr;
+    const auto t_lm_end = std::chrono::steady_clock::now();
+    if (trace) std::fprintf(stderr, "[calib_b200] solve: LM loop %8.2f ms (%d iterations, %d Jacobian + %d cost evaluations, %lld launches)\n",
+                            std::chrono::duration<double, std::milli>(t_lm_end - t_solve_start).count(), iter, jev, cev, (long long)h.launches);
     // download the final parameters (last accepted point)
     CUDA_TRY(cudaMemcpyAsync(x_inout, xd, sizeof(double) * na, cudaMemcpyDeviceToHost, h.st));
     CUDA_TRY(cudaStreamSynchronize(h.st));
@@ -945,6 +1033,8 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
                 }
             }
             res->covariance_ok = 1;
+            if (trace) std::fprintf(stderr, "[calib_b200] solve: covariance (block-structured, %d x %d) %8.2f ms\n", na, na,
+                                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_lm_end).count());
             return CAL_OK;
         }
         std::vector<double> Hd, gd;

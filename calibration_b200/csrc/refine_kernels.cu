@@ -161,7 +161,7 @@ int schur_num_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < 444 * 16 
 void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V, int ns,
                   double radius, cudaStream_t st) {
     if (S.n_views == 0) return;
-    k_schur_factor<<<(S.n_views + 63) / 64, 64, 0, st>>>(S, L, B, V, 1.0 / radius);
+    k_schur_factor<<<(unsigned)((L.n_blk + 127) / 128), 128, 0, st>>>(S, L, B, V, 1.0 / radius);
     const int n_cta = schur_num_ctas(S.n_views);
     const int per = (S.n_views + n_cta - 1) / n_cta;
     const int nt = (ns + 1 + kSyrkTile - 1) / kSyrkTile;
@@ -169,6 +169,16 @@ void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& 
     k_schur_syrk<<<n_cta, threads, 0, st>>>(S, L, V, ns, per);
     const int na = ns + 1;
     k_schur_reduce<<<(na * na + 127) / 128, 128, 0, st>>>(V, n_cta, ns);
+}
+
+// reduced system of one LM iteration on the device (k_reduced_solve); false: too wide for one CTA's shared memory
+bool launch_reduced_solve(const double* Sm, const double* gss, const ViewBuffers& V, int ns, int32_t* info, cudaStream_t st) {
+    if (ns > kReducedMaxN) return false;
+    const int smem = (ns * ns + ns) * (int)sizeof(double);
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(k_reduced_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (kReducedMaxN * kReducedMaxN + kReducedMaxN) * (int)sizeof(double));
+    k_reduced_solve<<<1, 256, smem, st>>>(Sm, gss, V, ns, info);
+    return true;
 }
 
 // ---------------------------------------------------------------------------

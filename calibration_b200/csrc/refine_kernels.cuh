@@ -141,6 +141,7 @@ float dfma_peak_ms(double* scratch, int blocks, int threads, int iters, cudaStre
 // ---- per-view (Schur) machinery -------------------------------------------------
 constexpr int kSyrkTile = 8;
 constexpr int kSyrkThreads = 256;
+constexpr int kReducedMaxN = 160;   // widest shared block k_reduced_solve takes (n^2 + n doubles of shared memory)
 constexpr int kSyrkMaxN = 176;  // ns + 1 must not exceed this (22 x 8 tiles, 253 <= 256 threads)
 
 struct ViewBuffers {
@@ -174,6 +175,7 @@ void launch_view_gather(const ProblemShape& S, const DevLayout& L, const EvalBuf
 void launch_view_scale(const ProblemShape& S, const ViewBuffers& V, int compute_scale, cudaStream_t st);
 void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V, int ns,
                   double radius, cudaStream_t st);
+bool launch_reduced_solve(const double* Sm, const double* gss, const ViewBuffers& V, int ns, int32_t* info, cudaStream_t st);
 void launch_backsub(const ProblemShape& S, const DevLayout& L, const ViewBuffers& V, int ns, cudaStream_t st);
 void launch_view_plus(const ProblemShape& S, const EvalBuffers& B, const ViewBuffers& V, double t, cudaStream_t st);
 void launch_view_norms(const ProblemShape& S, const EvalBuffers& B, const ViewBuffers& V, cudaStream_t st);

@@ -47,41 +47,109 @@ __global__ void k_view_scale(ProblemShape S, ViewBuffers V, int compute_scale) {
     V.dp[i] = fmin(fmax(h * s * s, 1e-6), 1e32);                      // LM diagonal clamp (B.3-1)
 }
 
-// Per view: L = chol(sp Hpp sp + dp / radius), f = L^-1 (sp o gp), and for each
-// of its blocks F_b = L^-1 (diag(sp) E_b diag(s_shared)), so that
-// E^T A^-1 E = F^T F and E^T A^-1 g = F^T f.
+// L_v = chol(sp Hpp sp + dp / radius), f_v = L_v^-1 (sp o gp), and for every residual block of the view
+// F_b = L_v^-1 (diag(sp) E_b diag(s_shared)), so that E^T A^-1 E = F^T F and E^T A^-1 g = F^T f.
+// One thread per residual BLOCK: the 6x6 factorisation (about a hundred flops) is repeated by the blocks of a view —
+// a view seen by 8 cameras has 8 threads instead of one thread walking 8 blocks x 15 columns in sequence, and the
+// loads of E_b / stores of F_b ([entry][n_blk]) are coalesced over consecutive blocks.  The first block of a view also
+// publishes L_v and f_v; a view without blocks publishes nothing (it has no rows in the Schur complement).
 __global__ void k_schur_factor(ProblemShape S, DevLayout L, EvalBuffers B, ViewBuffers V, double inv_radius) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= S.n_views) return;
-    if (!V.view_free[v]) return;
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= L.n_blk) return;
+    const int v = L.blk_view[b];
+    if (v < 0 || !V.view_free[v]) return;
     double A[36], sp[6];
     for (int i = 0; i < 6; ++i) sp[i] = V.sp[(int64_t)v * 6 + i];
     for (int i = 0; i < 6; ++i)
         for (int j = 0; j < 6; ++j) A[6 * i + j] = V.Hpp[(int64_t)v * 36 + 6 * i + j] * sp[i] * sp[j];
     for (int i = 0; i < 6; ++i) A[7 * i] += V.dp[(int64_t)v * 6 + i] * inv_radius;
-    if (!chol6(A)) { atomicExch(V.fail, 1); return; }
-    for (int i = 0; i < 36; ++i) V.Lp[(int64_t)v * 36 + i] = A[i];
-    double f[6];
-    for (int i = 0; i < 6; ++i) f[i] = V.gp[(int64_t)v * 6 + i] * sp[i];
-    for (int i = 0; i < 6; ++i) { double s = f[i]; for (int k = 0; k < i; ++k) s -= A[6 * i + k] * f[k]; f[i] = s / A[7 * i]; }
-    for (int i = 0; i < 6; ++i) V.view_f[(int64_t)v * 6 + i] = f[i];
-    const int ncb = 6 + S.PI;
-    for (int k = V.view_blk_off[v]; k < V.view_blk_off[v + 1]; ++k) {
-        const int64_t b = V.view_blk_idx[k];
-        const int cam = L.blk_cam[b];
-        for (int j = 0; j < ncb; ++j) {
-            const int col = shared_col(V, cam, j);
-            const double sc = col < 0 ? 0.0 : V.s_shared[col];
-            double e[6];
-            for (int i = 0; i < 6; ++i) {
-                const double ev = j < 6 ? B.blk_Evc[(int64_t)(6 * i + j) * L.n_blk + b]
-                                        : B.blk_Evi[(int64_t)(S.PI * i + j - 6) * L.n_blk + b];
-                e[i] = ev * sp[i] * sc;
-            }
-            for (int i = 0; i < 6; ++i) { double s = e[i]; for (int kk = 0; kk < i; ++kk) s -= A[6 * i + kk] * e[kk]; e[i] = s / A[7 * i]; }
-            for (int i = 0; i < 6; ++i) V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b] = e[i];
-        }
+    const bool first = V.view_blk_idx[V.view_blk_off[v]] == b;
+    if (!chol6(A)) { if (first) atomicExch(V.fail, 1); return; }
+    if (first) {
+        for (int i = 0; i < 36; ++i) V.Lp[(int64_t)v * 36 + i] = A[i];
+        double f[6];
+        for (int i = 0; i < 6; ++i) f[i] = V.gp[(int64_t)v * 6 + i] * sp[i];
+        for (int i = 0; i < 6; ++i) { double s = f[i]; for (int k = 0; k < i; ++k) s -= A[6 * i + k] * f[k]; f[i] = s / A[7 * i]; }
+        for (int i = 0; i < 6; ++i) V.view_f[(int64_t)v * 6 + i] = f[i];
     }
+    const int ncb = 6 + S.PI;
+    const int cam = L.blk_cam[b];
+    for (int j = 0; j < ncb; ++j) {
+        const int col = shared_col(V, cam, j);
+        const double sc = col < 0 ? 0.0 : V.s_shared[col];
+        double e[6];
+        for (int i = 0; i < 6; ++i) {
+            const double ev = j < 6 ? B.blk_Evc[(int64_t)(6 * i + j) * L.n_blk + b]
+                                    : B.blk_Evi[(int64_t)(S.PI * i + j - 6) * L.n_blk + b];
+            e[i] = ev * sp[i] * sc;
+        }
+        for (int i = 0; i < 6; ++i) { double s = e[i]; for (int kk = 0; kk < i; ++kk) s -= A[6 * i + kk] * e[kk]; e[i] = s / A[7 * i]; }
+        for (int i = 0; i < 6; ++i) V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b] = e[i];
+    }
+}
+
+// The reduced (shared-block) system of one LM iteration, solved where its inputs are: one CTA forms
+//     S = Sm - C,  rhs = gss - c      (Sm: damped Jacobi-scaled H_ss from the host, [ns][ns]; C, c: the Schur complement)
+// in shared memory, factors it by a right-looking Cholesky and solves for y (k_backsub reads y_shared next, in stream
+// order: no round trip to the host between the Schur complement and the back-substitution).  info[0] = 1 if the matrix
+// was not positive definite or y is not finite.  n <= kReducedMaxN (shared memory: n^2 + n doubles).
+__global__ void __launch_bounds__(256) k_reduced_solve(const double* __restrict__ Sm, const double* __restrict__ gss, ViewBuffers V, int n,
+                                                       int32_t* __restrict__ info) {
+#if defined(__CUDACC__)
+    extern __shared__ __align__(16) double red_sm[];
+    __shared__ int bad;
+#else   // host build of this source (tests/host_emul): one CTA runs at a time
+    static double red_sm[kReducedMaxN * kReducedMaxN + kReducedMaxN];
+    static int bad;
+#endif
+    double* A = red_sm;            // [n][n], lower triangle used
+    double* y = red_sm + (size_t)n * n;
+    const int tid = threadIdx.x;
+    if (tid == 0) bad = 0;
+    for (int i = tid; i < n * n; i += 256) A[i] = Sm[i] - V.C[i];
+    for (int i = tid; i < n; i += 256) y[i] = gss[i] - V.c[i];
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+        if (tid == 0) {
+            const double d = A[(size_t)j * n + j];
+            if (!(d > 0.0) || !isfinite(d)) bad = 1;
+            A[(size_t)j * n + j] = sqrt(d);
+        }
+        __syncthreads();
+        if (bad) break;
+        const double inv = 1.0 / A[(size_t)j * n + j];
+        for (int i = j + 1 + tid; i < n; i += 256) A[(size_t)i * n + j] *= inv;
+        __syncthreads();
+        // trailing update of the lower triangle: A[i][k] -= L[i][j] L[k][j], j < k <= i
+        const int m = n - j - 1;
+        for (int idx = tid; idx < m * m; idx += 256) {
+            const int i = j + 1 + idx / m, k = j + 1 + idx % m;
+            if (k <= i) A[(size_t)i * n + k] -= A[(size_t)i * n + j] * A[(size_t)k * n + j];
+        }
+        __syncthreads();
+    }
+    if (!bad && tid < 32) {   // the two triangular solves: one warp, lane-strided dot products in a fixed order
+        for (int i = 0; i < n; ++i) {
+            double s = 0.0;
+            for (int k = tid; k < i; k += 32) s += A[(size_t)i * n + k] * y[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (tid == 0) y[i] = (y[i] - s) / A[(size_t)i * n + i];
+            __syncwarp();
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double s = 0.0;
+            for (int k = i + 1 + tid; k < n; k += 32) s += A[(size_t)k * n + i] * y[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (tid == 0) y[i] = (y[i] - s) / A[(size_t)i * n + i];
+            __syncwarp();
+        }
+        for (int i = tid; i < n; i += 32) if (!isfinite(y[i])) bad = 1;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) V.y_shared[i] = y[i];
+    if (tid == 0) info[0] = bad;
 }
 
 // C_aug = sum_v F_v^T F_v as a tiled SYRK with a long inner dimension (6 rows per view).  The
@@ -166,7 +234,7 @@ __global__ void k_backsub(ProblemShape S, DevLayout L, ViewBuffers V, int ns) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= S.n_views) return;
     double* red = V.red + (int64_t)v * 4;
-    if (!V.view_free[v]) {
+    if (!V.view_free[v] || V.view_blk_off[v + 1] == V.view_blk_off[v]) {   // fixed, or seen by no camera: no step
         for (int i = 0; i < 6; ++i) V.delta_p[(int64_t)v * 6 + i] = 0.0;
         red[0] = red[1] = 0.0;
         return;

@@ -214,6 +214,10 @@ void cal_axxb_destroy(cal_axxb_handle* h);
 cal_status cal_axxb_eval(cal_axxb_handle* h, const double* x7, double* cost, double* g6, double* H36);
 cal_status cal_axxb_solve(cal_axxb_handle* h, const cal_optim_options* opts, double* x7_inout,
                           cal_optim_result* result, double* cov49);
+/* Benchmark hooks (no reference counterpart): `reps` residual + Jacobian passes back to back, timed with CUDA events on
+ * the handle's stream; kernels launched by the handle so far. */
+cal_status cal_axxb_bench_pass(cal_axxb_handle* h, const double* x7, int reps, float* ms_total);
+int64_t cal_axxb_launch_count(const cal_axxb_handle* h);
 
 /* ---- batched RANSAC homography: estimate_homography(view, RansacOptions)
  * (linear/homography.h:22-24) = ransac<HomographyEstimator> (common/ransac.h:121-194). */

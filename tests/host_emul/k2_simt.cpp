@@ -45,8 +45,8 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
     S.n_views = n_views; S.n_cams = n_cams; S.PI = PI;
     DevLayout L;
     L.n_blk = n_blk;
-    std::vector<int32_t> bcam(blk_cam, blk_cam + n_blk);
-    L.blk_cam = bcam.data();
+    std::vector<int32_t> bcam(blk_cam, blk_cam + n_blk), bview(blk_view, blk_view + n_blk);
+    L.blk_cam = bcam.data(); L.blk_view = bview.data();
     EvalBuffers B;
     B.blk_Hvv = const_cast<double*>(blk_Hvv); B.blk_gv = const_cast<double*>(blk_gv);
     B.blk_Evc = const_cast<double*>(blk_Evc); B.blk_Evi = const_cast<double*>(blk_Evi);
@@ -72,7 +72,7 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
     simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 1); });
     simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 0); });
     // launch_schur
-    simt::launch((unsigned)((n_views + 63) / 64), 64, [&] { k_schur_factor(S, L, B, V, 1.0 / radius); });
+    simt::launch((unsigned)((L.n_blk + 127) / 128), 128, [&] { k_schur_factor(S, L, B, V, 1.0 / radius); });
     const int per = (n_views + n_cta - 1) / n_cta, nt = (na + kSyrkTile - 1) / kSyrkTile, threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
     simt::launch((unsigned)n_cta, (unsigned)threads, [&] { k_schur_syrk(S, L, V, ns, per); });
     simt::launch((unsigned)((na * na + 127) / 128), 128, [&] { k_schur_reduce(V, n_cta, ns); });
@@ -84,6 +84,15 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
     std::vector<double> Sm((size_t)ns * ns);
     for (int i = 0; i < ns; ++i) { ys[i] = gs_scaled[i] - cv[i]; for (int j = 0; j < ns; ++j) Sm[(size_t)i * ns + j] = Hss_scaled_damped[(size_t)i * ns + j] - Cm[(size_t)i * ns + j]; }
     if (ns > 0 && !solve_spd(Sm, ns, ys.data())) return 3;
+    if (ns > 0 && ns <= kReducedMaxN) {   // the product's own reduced solve (k_reduced_solve) must agree with the dense host solve above
+        std::vector<double> y_host(ys.begin(), ys.begin() + ns), Smd(Hss_scaled_damped, Hss_scaled_damped + (size_t)ns * ns), gsd(gs_scaled, gs_scaled + ns);
+        int32_t info[2] = {0, 0};
+        simt::launch(1, 256, [&] { k_reduced_solve(Smd.data(), gsd.data(), V, ns, info); });
+        if (info[0]) return 4;
+        double ref = 0.0, dev = 0.0;
+        for (int i = 0; i < ns; ++i) { ref = std::max(ref, std::fabs(y_host[i])); dev = std::max(dev, std::fabs(y_host[i] - ys[i])); }
+        if (!(dev <= 1e-9 * (ref + 1e-300))) return 5;
+    }
     std::memcpy(y_shared, ys.data(), sizeof(double) * ns);
     simt::launch((unsigned)((n_views + 63) / 64), 64, [&] { k_backsub(S, L, V, ns); });
     simt::launch(1, 1024, [&] { k_reduce_views(V, n_views); });
@@ -107,8 +116,8 @@ extern "C" int simt_k2_cov(int n_views, int n_cams, int PI, int64_t n_blk, const
     const int64_t na_amb = 7 * (int64_t)n_views;
     DevLayout L;
     L.n_blk = n_blk;
-    std::vector<int32_t> bcam(blk_cam, blk_cam + n_blk);
-    L.blk_cam = bcam.data();
+    std::vector<int32_t> bcam(blk_cam, blk_cam + n_blk), bview(blk_view, blk_view + n_blk);
+    L.blk_cam = bcam.data(); L.blk_view = bview.data();
     EvalBuffers B;
     B.blk_Hvv = const_cast<double*>(blk_Hvv); B.blk_gv = const_cast<double*>(blk_gv);
     B.blk_Evc = const_cast<double*>(blk_Evc); B.blk_Evi = const_cast<double*>(blk_Evi);
@@ -131,7 +140,7 @@ extern "C" int simt_k2_cov(int n_views, int n_cams, int PI, int64_t n_blk, const
     simt::launch((unsigned)((n_views + 127) / 128), 128, [&] { k_view_gather(S, L, B, V); });
     simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 1); });
     // launch_schur(radius = infinity): undamped factors L_v and F_b = L_v^-1 E_b stay in V
-    simt::launch((unsigned)((n_views + 63) / 64), 64, [&] { k_schur_factor(S, L, B, V, 0.0); });
+    simt::launch((unsigned)((L.n_blk + 127) / 128), 128, [&] { k_schur_factor(S, L, B, V, 0.0); });
     const int per = (n_views + n_cta - 1) / n_cta, nt = (na + kSyrkTile - 1) / kSyrkTile, threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
     simt::launch((unsigned)n_cta, (unsigned)threads, [&] { k_schur_syrk(S, L, V, ns, per); });
     simt::launch((unsigned)((na * na + 127) / 128), 128, [&] { k_schur_reduce(V, n_cta, ns); });

@@ -150,7 +150,7 @@ void launch_reduce_views(const ViewBuffers& V, int n_views, cudaStream_t) { simt
 int schur_num_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < 444 * 16 ? (n_views + 15) / 16 : 444); }
 void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V, int ns, double radius, cudaStream_t) {
     if (S.n_views == 0) return;
-    simt::launch((unsigned)((S.n_views + 63) / 64), 64, [&] { k_schur_factor(S, L, B, V, 1.0 / radius); });
+    simt::launch((unsigned)((L.n_blk + 127) / 128), 128, [&] { k_schur_factor(S, L, B, V, 1.0 / radius); });
     const int n_cta = schur_num_ctas(S.n_views);
     const int per = (S.n_views + n_cta - 1) / n_cta;
     const int nt = (ns + 1 + kSyrkTile - 1) / kSyrkTile;
@@ -158,6 +158,11 @@ void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& 
     simt::launch((unsigned)n_cta, (unsigned)threads, [&] { k_schur_syrk(S, L, V, ns, per); });
     const int na = ns + 1;
     simt::launch((unsigned)((na * na + 127) / 128), 128, [&] { k_schur_reduce(V, n_cta, ns); });
+}
+bool launch_reduced_solve(const double* Sm, const double* gss, const ViewBuffers& V, int ns, int32_t* info, cudaStream_t) {
+    if (ns > kReducedMaxN) return false;
+    simt::launch(1, 256, [&] { k_reduced_solve(Sm, gss, V, ns, info); });
+    return true;
 }
 void launch_cov_views(const ProblemShape& S, const DevLayout& L, const ViewBuffers& V, const double* x, int ns, const double* W, double* Z, double* G,
                       double* Ainv, double* cov, int64_t na, cudaStream_t) {
