@@ -13,6 +13,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -85,6 +86,27 @@ void quat_plus_jacobian(const double* q, double* J) {  // QuaternionManifold::Pl
     J[9] = q[2];  J[10] = -q[1]; J[11] = q[0];
 }
 
+// Page-locked blocks cost milliseconds to create and to release (cudaHostAlloc / cudaFreeHost): handles borrow theirs
+// from a process-wide free list and return it on destruction; the list is never shrunk.
+struct PinPool {
+    std::mutex m;
+    std::vector<std::pair<size_t, double*>> idle;   // (doubles, block)
+    double* get(size_t n, size_t* got) {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            for (size_t i = 0; i < idle.size(); ++i)
+                if (idle[i].first >= n) { double* p = idle[i].second; *got = idle[i].first; idle.erase(idle.begin() + (long)i); return p; }
+        }
+        const size_t cap = std::max<size_t>(n, 4096);
+        double* p = nullptr;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&p), cap * sizeof(double), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        *got = cap;
+        return p;
+    }
+    void put(double* p, size_t n) { if (p) { std::lock_guard<std::mutex> lk(m); idle.emplace_back(n, p); } }
+};
+PinPool& pin_pool() { static PinPool* pool = new PinPool; return *pool; }
+
 }  // namespace
 
 struct cal_refine_handle : calk::HostModel {
@@ -138,7 +160,7 @@ struct cal_refine_handle : calk::HostModel {
     ~cal_refine_handle() {
         for (void* p : allocs) cudaFree(p);
         if (arena && st) { cudaFreeAsync(arena, st); cudaStreamSynchronize(st); }
-        if (pin) cudaFreeHost(pin);
+        pin_pool().put(pin, pin_doubles);
         if (st) cudaStreamDestroy(st);
     }
 };
@@ -445,6 +467,8 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         CUDA_TRY(h.alloc(&V.s_shared, ns)); CUDA_TRY(h.alloc(&V.y_shared, ns)); CUDA_TRY(h.alloc(&V.C, (size_t)ns * ns)); CUDA_TRY(h.alloc(&V.c, ns));
         CUDA_TRY(h.alloc(&V.partialC, (size_t)h.n_syrk_cta * (ns + 1) * (ns + 1))); CUDA_TRY(h.alloc(&V.red, (size_t)nv * 4));
         CUDA_TRY(h.alloc(&V.red_out, 4)); CUDA_TRY(h.alloc(&V.fail, 1));
+        CUDA_TRY(h.alloc(&V.red_part, (size_t)kReduceViewsCtas * 4)); CUDA_TRY(h.alloc(&V.red_ticket, 1));
+        CUDA_TRY(cudaMemsetAsync(V.red_ticket, 0, sizeof(unsigned), us));
         CUDA_TRY(cudaMemsetAsync(V.red, 0, sizeof(double) * nv * 4, us)); CUDA_TRY(cudaMemsetAsync(V.fail, 0, sizeof(int32_t), us));
         CUDA_TRY(cudaMemsetAsync(V.blk_F, 0, sizeof(double) * 6 * (6 + S.PI) * nblk, us));
         CUDA_TRY(cudaMemsetAsync(V.delta_p, 0, sizeof(double) * nv * 6, us));
@@ -452,8 +476,8 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
     }
     CUDA_TRY(h.alloc(&h.V.x_cand, h.n_amb));
     CUDA_TRY(h.alloc(&h.dSm, (size_t)std::max(h.ns, 1) * std::max(h.ns, 1))); CUDA_TRY(h.alloc(&h.dgss, std::max(h.ns, 1))); CUDA_TRY(h.alloc(&h.dinfo, 2));
-    h.pin_doubles = 16 + (size_t)std::max(h.ns, 1) + (size_t)S.n_cams * S.NV;
-    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&h.pin), h.pin_doubles * sizeof(double), cudaHostAllocDefault));
+    h.pin = pin_pool().get(16 + (size_t)std::max(h.ns, 1) + (size_t)S.n_cams * S.NV, &h.pin_doubles);
+    if (!h.pin) return fail(CAL_ERR_CUDA, "page-locked result block: allocation failed");
     std::memset(h.pin, 0, h.pin_doubles * sizeof(double));
     lap("host set-up done");
     CUDA_TRY(cudaStreamSynchronize(us));
@@ -973,9 +997,11 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
             std::vector<double> W((size_t)ns * ns), e(std::max(ns, 1));
             for (int j = 0; j < ns; ++j) { std::fill(e.begin(), e.end(), 0.0); e[j] = 1.0; chol_solve_host(Sm, ns, e.data()); for (int i = 0; i < ns; ++i) W[(size_t)i * ns + j] = e[i]; }
             double *dW = nullptr, *dZ = nullptr, *dG = nullptr, *dAinv = nullptr, *dcov = nullptr;
-            struct Free { std::vector<double**> p; ~Free() { for (auto q : p) cudaFree(*q); } } guard{{&dW, &dZ, &dG, &dAinv, &dcov}};
-            CUDA_TRY(dev_alloc(&dW, (size_t)ns * ns)); CUDA_TRY(dev_alloc(&dZ, (size_t)nv * 6 * ns)); CUDA_TRY(dev_alloc(&dG, (size_t)nv * 6 * ns));
-            CUDA_TRY(dev_alloc(&dAinv, (size_t)nv * 36)); CUDA_TRY(dev_alloc(&dcov, (size_t)na * na));
+            // stream-ordered allocations from the device's pool (kept warm by cal_refine_create): no cudaMalloc / cudaFree on this path
+            struct Free { std::vector<double**> p; cudaStream_t st; ~Free() { for (auto q : p) if (*q) cudaFreeAsync(*q, st); } } guard{{&dW, &dZ, &dG, &dAinv, &dcov}, h.st};
+            auto take = [&](double** p, size_t n) { return cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(double), h.st); };
+            CUDA_TRY(take(&dW, (size_t)ns * ns)); CUDA_TRY(take(&dZ, (size_t)nv * 6 * ns)); CUDA_TRY(take(&dG, (size_t)nv * 6 * ns));
+            CUDA_TRY(take(&dAinv, (size_t)nv * 36)); CUDA_TRY(take(&dcov, (size_t)na * na));
             CUDA_TRY(cudaMemcpyAsync(dW, W.data(), sizeof(double) * ns * ns, cudaMemcpyHostToDevice, h.st));
             CUDA_TRY(cudaMemsetAsync(dcov, 0, sizeof(double) * na * na, h.st));
             CUDA_TRY(cudaMemsetAsync(dG, 0, sizeof(double) * nv * 6 * ns, h.st));

@@ -152,7 +152,8 @@ void launch_view_norms(const ProblemShape& S, const EvalBuffers& B, const ViewBu
     k_view_norms<<<(S.n_views + 127) / 128, 128, 0, st>>>(S, B, V);
 }
 void launch_reduce_views(const ViewBuffers& V, int n_views, cudaStream_t st) {
-    k_reduce_views<<<1, 1024, 0, st>>>(V, n_views);
+    const int ctas = n_views >= 64 * 256 ? kReduceViewsCtas : (n_views + 1023) / 1024 > 0 ? (n_views + 1023) / 1024 : 1;   // >= 1024 views per CTA
+    k_reduce_views<<<ctas < kReduceViewsCtas ? ctas : kReduceViewsCtas, 256, 0, st>>>(V, n_views);
 }
 
 // up to three CTAs per SM (4-warp CTAs at the common shared-block widths), at least 16 views each

@@ -141,6 +141,7 @@ float dfma_peak_ms(double* scratch, int blocks, int threads, int iters, cudaStre
 // ---- per-view (Schur) machinery -------------------------------------------------
 constexpr int kSyrkTile = 8;
 constexpr int kSyrkThreads = 256;
+constexpr int kReduceViewsCtas = 64;  // CTAs of k_reduce_views at most; ViewBuffers::red_part holds [kReduceViewsCtas][4]
 constexpr int kReducedMaxN = 160;   // widest shared block k_reduced_solve takes (n^2 + n doubles of shared memory)
 constexpr int kSyrkMaxN = 176;  // ns + 1 must not exceed this (22 x 8 tiles, 253 <= 256 threads)
 
@@ -166,6 +167,8 @@ struct ViewBuffers {
     double* partialC = nullptr; // [n_cta][(ns+1)^2]
     double* red = nullptr;      // [n_views][4] per-view scalars to reduce
     double* red_out = nullptr;  // [4]
+    double* red_part = nullptr; // [kReduceViewsCtas][4] per-CTA partials of k_reduce_views
+    unsigned* red_ticket = nullptr;  // its arrival counter (zero between launches)
     double* x_cand = nullptr;   // candidate parameters [n_amb]
     int32_t* fail = nullptr;    // cholesky failure flag
 };

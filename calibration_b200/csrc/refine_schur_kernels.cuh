@@ -120,11 +120,10 @@ __global__ void __launch_bounds__(256) k_reduced_solve(const double* __restrict_
         const double inv = 1.0 / A[(size_t)j * n + j];
         for (int i = j + 1 + tid; i < n; i += 256) A[(size_t)i * n + j] *= inv;
         __syncthreads();
-        // trailing update of the lower triangle: A[i][k] -= L[i][j] L[k][j], j < k <= i
-        const int m = n - j - 1;
-        for (int idx = tid; idx < m * m; idx += 256) {
-            const int i = j + 1 + idx / m, k = j + 1 + idx % m;
-            if (k <= i) A[(size_t)i * n + k] -= A[(size_t)i * n + j] * A[(size_t)k * n + j];
+        // trailing update of the lower triangle: A[i][k] -= L[i][j] L[k][j], j < k <= i; threads as a 16 x 16 grid over (i, k)
+        for (int i = j + 1 + (tid >> 4); i < n; i += 16) {
+            const double lij = A[(size_t)i * n + j];
+            for (int k = j + 1 + (tid & 15); k <= i; k += 16) A[(size_t)i * n + k] = fma(-lij, A[(size_t)k * n + j], A[(size_t)i * n + k]);
         }
         __syncthreads();
     }
@@ -302,24 +301,47 @@ __global__ void k_view_norms(ProblemShape S, EvalBuffers B, ViewBuffers V) {
     V.red[(int64_t)v * 4 + 0] = x2; V.red[(int64_t)v * 4 + 3] = gm;
 }
 
-// red_out[0..2] = column sums, red_out[3] = column max; fixed-order single-CTA tree
-__global__ void __launch_bounds__(1024) k_reduce_views(ViewBuffers V, int n_views) {
-    __shared__ double sm[4][1024];
+// red_out[0..2] = column sums, red_out[3] = column max.  Every CTA reduces a contiguous slice of the views with a fixed
+// tree; the CTA that arrives last (integer ticket) combines the per-CTA partials in CTA order: deterministic, one launch.
+__global__ void __launch_bounds__(256) k_reduce_views(ViewBuffers V, int n_views) {
+    __shared__ double sm[4][256];
+#if defined(__CUDACC__)
+    __shared__ int last;
+#else
+    static int last;   // host build of this source (tests/host_emul): one CTA runs at a time
+#endif
+    const int per = (n_views + gridDim.x - 1) / gridDim.x;
+    const int v0 = blockIdx.x * per, v1 = min(n_views, v0 + per);
     double a[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int v = threadIdx.x; v < n_views; v += 1024) {
+    for (int v = v0 + threadIdx.x; v < v1; v += 256) {
         const double* r = V.red + (int64_t)v * 4;
         a[0] += r[0]; a[1] += r[1]; a[2] += r[2]; a[3] = fmax(a[3], r[3]);
     }
     for (int k = 0; k < 4; ++k) sm[k][threadIdx.x] = a[k];
     __syncthreads();
-    for (int s = 512; s > 0; s >>= 1) {
+    for (int s = 128; s > 0; s >>= 1) {
         if (threadIdx.x < s) {
             for (int k = 0; k < 3; ++k) sm[k][threadIdx.x] += sm[k][threadIdx.x + s];
             sm[3][threadIdx.x] = fmax(sm[3][threadIdx.x], sm[3][threadIdx.x + s]);
         }
         __syncthreads();
     }
-    if (threadIdx.x < 4) V.red_out[threadIdx.x] = sm[threadIdx.x][0];
+    if (threadIdx.x < 4) V.red_part[blockIdx.x * 4 + threadIdx.x] = sm[threadIdx.x][0];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(V.red_ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x < 4) {
+        double r = 0.0;
+        for (unsigned c = 0; c < gridDim.x; ++c) {
+            const double p = __ldcg(V.red_part + c * 4 + threadIdx.x);
+            r = threadIdx.x == 3 ? fmax(r, p) : r + p;
+        }
+        V.red_out[threadIdx.x] = r;
+    }
+    if (threadIdx.x == 0) *V.red_ticket = 0u;   // ready for the next launch
 }
 
 // ---- block-structured covariance of the per-view kinds (description and launcher: refine_kernels.cu) ----

@@ -66,7 +66,8 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
     V.cam_col_q = cq.data(); V.cam_col_t = ct.data(); V.cam_col_i = ci.data();
     V.Hpp = Hpp.data(); V.gp = gp.data(); V.sp = sp.data(); V.dp = dp.data(); V.Lp = Lp.data(); V.view_f = view_f.data(); V.blk_F = blk_F.data();
     V.delta_p = dlt.data(); V.s_shared = ss.data(); V.y_shared = ys.data(); V.C = Cm.data(); V.c = cv.data(); V.partialC = partialC.data();
-    V.red = red.data(); V.red_out = ro.data(); V.fail = &failed;
+    std::vector<double> rpart((size_t)kReduceViewsCtas * 4, 0.0); unsigned rticket = 0u;
+    V.red = red.data(); V.red_out = ro.data(); V.fail = &failed; V.red_part = rpart.data(); V.red_ticket = &rticket;
     // after the Jacobian pass: gather, Jacobi scaling once (compute_scale = 1); first LM iteration: the diagonal clamp
     simt::launch((unsigned)((n_views + 127) / 128), 128, [&] { k_view_gather(S, L, B, V); });
     simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 1); });
@@ -95,7 +96,7 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
     }
     std::memcpy(y_shared, ys.data(), sizeof(double) * ns);
     simt::launch((unsigned)((n_views + 63) / 64), 64, [&] { k_backsub(S, L, V, ns); });
-    simt::launch(1, 1024, [&] { k_reduce_views(V, n_views); });
+    simt::launch(n_views >= 2048 ? 2u : 1u, 256, [&] { k_reduce_views(V, n_views); });
     std::memcpy(delta_p, dlt.data(), sizeof(double) * 6 * n_views);
     std::memcpy(red_out4, ro.data(), sizeof(double) * 4);
     return 0;
@@ -178,13 +179,14 @@ extern "C" int simt_k2_plus_norms(int n_views, const double* x, const double* de
     EvalBuffers B; B.x = xs.data();
     ViewBuffers V;
     V.x_cand = xc.data(); V.delta_p = dl.data(); V.gp = g.data(); V.view_free = vfree.data(); V.red = red.data(); V.red_out = ro.data();
+    std::vector<double> rpart((size_t)kReduceViewsCtas * 4, 0.0); unsigned rticket = 0u; V.red_part = rpart.data(); V.red_ticket = &rticket;
     simt::launch((unsigned)((n_views + 127) / 128), 128, [&] { k_view_plus(S, B, V, t); });
-    simt::launch(1, 1024, [&] { k_reduce_views(V, n_views); });
+    simt::launch(n_views >= 2048 ? 2u : 1u, 256, [&] { k_reduce_views(V, n_views); });
     std::memcpy(red_plus4, ro.data(), 4 * sizeof(double));
     std::memcpy(x_cand, xc.data(), sizeof(double) * 7 * n_views);
     std::fill(red.begin(), red.end(), 0.0);
     simt::launch((unsigned)((n_views + 127) / 128), 128, [&] { k_view_norms(S, B, V); });
-    simt::launch(1, 1024, [&] { k_reduce_views(V, n_views); });
+    simt::launch(n_views >= 2048 ? 2u : 1u, 256, [&] { k_reduce_views(V, n_views); });
     std::memcpy(red_norms4, ro.data(), 4 * sizeof(double));
     return 0;
 }

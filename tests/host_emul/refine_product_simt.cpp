@@ -146,7 +146,7 @@ void launch_view_norms(const ProblemShape& S, const EvalBuffers& B, const ViewBu
     if (S.n_views == 0) return;
     simt::launch((unsigned)((S.n_views + 127) / 128), 128, [&] { k_view_norms(S, B, V); });
 }
-void launch_reduce_views(const ViewBuffers& V, int n_views, cudaStream_t) { simt::launch(1, 1024, [&] { k_reduce_views(V, n_views); }); }
+void launch_reduce_views(const ViewBuffers& V, int n_views, cudaStream_t) { simt::launch(n_views >= 2048 ? 2u : 1u, 256, [&] { k_reduce_views(V, n_views); }); }
 int schur_num_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < 444 * 16 ? (n_views + 15) / 16 : 444); }
 void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V, int ns, double radius, cudaStream_t) {
     if (S.n_views == 0) return;
