@@ -465,21 +465,21 @@ def main():
     if args.workload == "c4-pass":   # the bundle pass alone at C4 size through the C5 code path (strong-scaling runs)
         args.workload = "c4"
     elif args.workload in OTHER_WORKLOADS:
-        if rank != 0:
-            return
         import bench_workloads as W
         if args.impl == "reference":
-            print(json.dumps(W.run_reference(args)), flush=True)
+            if rank == 0:
+                print(json.dumps(W.run_reference(args)), flush=True)
             return
         sys.stdout.flush()
         saved_stdout = os.dup(1)
         os.dup2(2, 1)   # one JSON line on stdout: library chatter goes to stderr
         try:
-            out = W.run(args, ClockSampler)
+            out = W.run(args, ClockSampler, rank, world, local_rank)
         finally:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
-        print(json.dumps(out), flush=True)
+        if out is not None:
+            print(json.dumps(out), flush=True)
         return
     if args.probe_shared_board:
         run_board_probe(args)

@@ -166,16 +166,27 @@ def run_refine(args, clock_sampler_cls):
 # ----------------------------------------------------------------------------------------------------------------
 # c2: batched RANSAC homography
 # ----------------------------------------------------------------------------------------------------------------
-def run_ransac(args, clock_sampler_cls):
+def run_ransac(args, clock_sampler_cls, rank=0, world=1, local_rank=0):
+    """N > 1 (under torch.distributed.run): the batch is split by problem over the ranks, no communication on the data
+    path; every rank times its own slice with CUDA events, the step time is the maximum over the ranks."""
     import torch
     from calibration_b200 import abi, capi, synth
-    npb, n = args.ransac_problems, 500
-    x, y, u, v, _ = synth.synth_ransac(seed=17, n_problems=npb, n=n)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_total, n = args.ransac_problems, 500
+    per = (n_total + world - 1) // world
+    p0, p1 = rank * per, min(n_total, (rank + 1) * per)
+    npb = p1 - p0
+    x, y, u, v, _ = synth.synth_ransac(seed=17 + rank, n_problems=npb, n=n)
     pin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (x, y, u, v)]
     dev = [p.cuda() for p in pin]
     res = torch.empty(npb * C.sizeof(abi.RansacResult), dtype=torch.uint8, device="cuda")
     mask = torch.empty(npb * n, dtype=torch.uint8, device="cuda")
     opts = abi.RansacOptions.default()
+    opts.seed += p0   # the seed list follows the global problem index
     L = capi.lib()
     ms = C.c_float()
 
@@ -184,10 +195,17 @@ def run_ransac(args, clock_sampler_cls):
                                                C.c_void_p(mask.data_ptr()), C.byref(ms))
         assert rc == 0, L.cal_last_error()
         return ms.value
-    with clock_sampler_cls(0) as clk:
+    with clock_sampler_cls(local_rank) as clk:
         for _ in range(max(args.warmup, 3)):
             launch()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
         tot = sum(launch() for _ in range(args.steps))
+        if dist is not None:
+            t = torch.tensor([tot], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot = float(t[0])
         for _ in range(max(10, int(1500.0 / max(tot / args.steps, 0.05)))):
             launch()
     ms_step = tot / args.steps
@@ -195,15 +213,28 @@ def run_ransac(args, clock_sampler_cls):
                                                                     ("h", "f8", 9), ("rms", "f8"), ("sym", "f8"), ("mm", "f8")]))
     hyp = int(r["iters_run"].sum())
     hx = [p.numpy() for p in pin]
-    capi.ransac_homography_batch(*hx, opts, want_mask=True)
+    capi.ransac_homography_batch(*hx, opts, want_mask=True, device=local_rank)
+    if dist is not None:
+        dist.barrier()
     t0 = time.perf_counter()
-    capi.ransac_homography_batch(*hx, opts, want_mask=True)
+    capi.ransac_homography_batch(*hx, opts, want_mask=True, device=local_rank)
     e2e_s = time.perf_counter() - t0
-    alg = 32 * npb * n
+    if dist is not None:
+        t = torch.tensor([e2e_s, float(hyp)], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t[:1], op=dist.ReduceOp.MAX); dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+        e2e_s, hyp = float(t[0]), int(t[1])
+        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    npb_local, npb = npb, n_total
+    alg = 32 * npb_local * n
     out = _base(args, "image pairs/s in batched RANSAC homography (DLT hypotheses, inlier scoring, refit)", "problems/s", npb / (ms_step * 1e-3), ms_step, "c2",
-                {"problems": npb, "correspondences": n, "outlier_fraction": 0.3, "max_iters": int(opts.max_iters), "thresh": float(opts.thresh),
+                {"problems": npb, "problems_per_gpu": npb_local, "sharding": "single GPU" if world == 1 else f"problems split contiguously over {world} ranks, no communication",
+                 "correspondences": n, "outlier_fraction": 0.3, "max_iters": int(opts.max_iters), "thresh": float(opts.thresh),
                  "l2_policy": f"inputs ({alg / 1e9:.2f} GB) larger than the 126 MB L2; no flush", "hypotheses_evaluated": hyp, "mean_hypotheses_per_problem": hyp / npb,
-                 "success": int(r["success"].sum()), "mean_inliers": float(r["n_inliers"].mean())})
+                 "success_rank0": int(r["success"].sum()), "mean_inliers_rank0": float(r["n_inliers"].mean())})
+    out["n_gpus"] = world
+    out["scaling"] = "strong"
     out["clocks"] = clk.summary()
     out["gpu_launches"] = args.steps
     out["e2e"] = {"value": npb / e2e_s, "unit": "problems/s", "h2d_bytes_per_step": alg, "d2h_bytes_per_step": int(npb * (C.sizeof(abi.RansacResult) + n)),
@@ -213,7 +244,7 @@ def run_ransac(args, clock_sampler_cls):
                                 "correspondences are read once into shared memory; the kernel is bound by FP64 latency (4-point DLT by Householder QR, "
                                 "refit null vector by inverse iteration, one hypothesis per lane) and by the exact device-side replay of std::sample")
     out["roofline"]["hypothesis_point_scores_per_s"] = hyp * n / (ms_step * 1e-3)
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         O = _oracle()
         k = min(npb, 4000)
         cores = os.cpu_count() or 1
@@ -292,11 +323,13 @@ def run_axxb(args, clock_sampler_cls):
     return out
 
 
-def run(args, clock_sampler_cls):
+def run(args, clock_sampler_cls, rank=0, world=1, local_rank=0):
+    if args.workload == "c2":
+        return run_ransac(args, clock_sampler_cls, rank, world, local_rank)
+    if rank != 0:
+        return None   # the other small shapes are single-GPU workloads
     if args.workload in ("c1", "c3", "c4"):
         return run_refine(args, clock_sampler_cls)
-    if args.workload == "c2":
-        return run_ransac(args, clock_sampler_cls)
     return run_axxb(args, clock_sampler_cls)
 
 

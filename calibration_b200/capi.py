@@ -64,8 +64,11 @@ def lib():
         ("cal_axxb_eval", [hp, dp, dp, dp, dp]),
         ("cal_axxb_solve", [hp, C.POINTER(abi.OptimOptions), dp, C.POINTER(abi.OptimResult), dp]),
         ("cal_axxb_bench_pass", [hp, dp, C.c_int, C.POINTER(C.c_float)]),
+        ("cal_axxb_attach_comm", [hp, hp]),
         ("cal_ransac_homography_batch", [i64, C.c_int32, dp, dp, dp, dp, C.POINTER(abi.RansacOptions), C.c_int, C.c_int,
                                          C.POINTER(abi.RansacResult), u8p]),
+        ("cal_ransac_homography_batch_multi", [i64, C.c_int32, dp, dp, dp, dp, C.POINTER(abi.RansacOptions), C.c_int, C.c_int32,
+                                               C.POINTER(C.c_int32), C.POINTER(abi.RansacResult), u8p]),
         ("cal_seed_intrinsics", [i64, abi.c_int64_p, ip, dp, dp, dp, dp, C.c_int32, C.POINTER(abi.SeedOptions), C.c_int, dp, ip,
                                  ip, dp, dp, dp]),
         ("cal_seed_intrinsics_ransac", [i64, abi.c_int64_p, ip, dp, dp, dp, dp, C.c_int32, C.POINTER(abi.SeedOptions),
@@ -290,6 +293,11 @@ class AxxbHandle:
         _check(lib().cal_axxb_eval(self._h, abi.dptr(abi.as_f64(x7)), C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g), abi.dptr(H)))
         return cost.value, g, H
 
+    def attach_comm(self, comm):
+        """shard the pair tiles over the ranks of `comm` (a capi.Comm), 28 sums all-reduced per pass; None detaches"""
+        _check(lib().cal_axxb_attach_comm(self._h, comm._c if comm is not None else None))
+        self._comm = comm
+
     def bench_pass(self, x7, reps=1):
         """device time (ms, CUDA events on the handle's stream) of `reps` residual + Jacobian passes"""
         ms = C.c_float()
@@ -304,13 +312,20 @@ class AxxbHandle:
         return x, res, cov
 
 
-def ransac_homography_batch(x, y, u, v, opts=None, seed_per_problem=True, device=0, want_mask=True):
-    """x, y, u, v: (n_problems, n) float64.  Returns (results array, inlier mask)."""
+def ransac_homography_batch(x, y, u, v, opts=None, seed_per_problem=True, device=0, want_mask=True, devices=None):
+    """x, y, u, v: (n_problems, n) float64.  Returns (results array, inlier mask).  devices = [ids]: the batch is split by
+    problem over these devices (cal_ransac_homography_batch_multi), no communication, same results."""
     x, y, u, v = (abi.as_f64(a) for a in (x, y, u, v))
     npb, n = x.shape
     opts = opts or abi.RansacOptions.default()
     res = (abi.RansacResult * npb)()
     mask = np.zeros((npb, n), dtype=np.uint8) if want_mask else None
+    if devices is not None:
+        ids = (C.c_int32 * len(devices))(*devices)
+        _check(lib().cal_ransac_homography_batch_multi(npb, n, abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v), C.byref(opts),
+                                                       int(seed_per_problem), len(devices), ids, res,
+                                                       mask.ctypes.data_as(C.POINTER(C.c_uint8)) if want_mask else None))
+        return res, mask
     _check(lib().cal_ransac_homography_batch(npb, n, abi.dptr(x), abi.dptr(y), abi.dptr(u), abi.dptr(v), C.byref(opts),
                                              int(seed_per_problem), device, res,
                                              mask.ctypes.data_as(abi.c_uint8_p) if want_mask else None))

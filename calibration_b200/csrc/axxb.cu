@@ -17,7 +17,10 @@
 #include <vector>
 
 #include "../../include/calib_b200.h"
+#include <algorithm>
+
 #include "axxb_kernels.cuh"
+#include "comm.h"
 #include "k1_math.cuh"
 
 using namespace calk;
@@ -41,6 +44,10 @@ struct cal_axxb_handle {
     // pairs formed on the fly from the poses (cal_axxb_create_from_poses)
     bool from_poses = false;
     PairTiles tiles{};
+    // sharded over the ranks of a communicator (cal_axxb_attach_comm): this rank evaluates the tiles [tile0, tile0 + n_cta)
+    // and the 28 sums (upper 6x6, gradient, cost) are all-reduced after every pass
+    int64_t tile0 = 0;
+    calcomm::Comm* comm = nullptr;   // not owned
     double *dG = nullptr, *dC = nullptr;
     ~cal_axxb_handle() {
         cudaFree(pairs); cudaFree(x); cudaFree(partial); cudaFree(out); cudaFree(dG); cudaFree(dC); cudaFree(tiles.mask);
@@ -59,16 +66,19 @@ cal_status afail(cal_status s, const std::string& m);
 cal_status axxb_pass(cal_axxb_handle& h, const double* x7, bool jac, double* cost, double* g6, double* H36) {
     ACUDA(cudaMemcpyAsync(h.x, x7, 7 * sizeof(double), cudaMemcpyHostToDevice, h.st));
     if (h.from_poses) {
-        if (jac) k_axxb_otf<1><<<h.n_cta, 256, 0, h.st>>>(h.tiles, h.x, h.huber, h.partial);
-        else k_axxb_otf<0><<<h.n_cta, 256, 0, h.st>>>(h.tiles, h.x, h.huber, h.partial);
+        PairTiles t = h.tiles; t.tile_base = h.tile0;
+        if (jac) k_axxb_otf<1><<<h.n_cta, 256, 0, h.st>>>(t, h.x, h.huber, h.partial);
+        else k_axxb_otf<0><<<h.n_cta, 256, 0, h.st>>>(t, h.x, h.huber, h.partial);
     } else if (jac) k_axxb<1><<<h.n_cta, 256, 0, h.st>>>(h.pairs, h.n, h.x, h.huber, h.partial);
     else k_axxb<0><<<h.n_cta, 256, 0, h.st>>>(h.pairs, h.n, h.x, h.huber, h.partial);
     k_axxb_final<<<1, 32 * kAcc, 0, h.st>>>(h.partial, h.n_cta, h.out);
     h.launches += 2;
+    if (h.comm && !h.comm->allreduce_sum(h.out, kAcc, h.st)) return afail(CAL_ERR_COMM, h.comm->error());
     double o[kAcc];
     ACUDA(cudaMemcpyAsync(o, h.out, sizeof o, cudaMemcpyDeviceToHost, h.st));
     ACUDA(cudaStreamSynchronize(h.st));
     ACUDA(cudaGetLastError());
+    if (h.comm && !h.comm->check_timeout()) return afail(CAL_ERR_COMM, h.comm->error());
     if (cost) *cost = o[27];
     if (jac) {
         int k = 0;
@@ -170,6 +180,24 @@ extern "C" cal_status cal_axxb_eval(cal_axxb_handle* h, const double* x7, double
     return axxb_pass(*h, x7, g6 || H36, cost, g6, H36);
 }
 
+// Shard a from-poses handle over the ranks of a communicator: every rank holds all poses (2 x 96 B each) and
+// the pair mask, evaluates a contiguous slice of the 32 x 32 pair tiles, and the 28 sums are all-reduced after every
+// pass — the LM then runs replicated.  comm == NULL detaches (the handle evaluates every tile again).
+extern "C" cal_status cal_axxb_attach_comm(cal_axxb_handle* h, cal_comm* c) {
+    if (!h) return afail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    if (c && c->c && !h->from_poses) return afail(CAL_ERR_INVALID_ARGUMENT, "only handles created from poses can be sharded");
+    const int T = h->tiles.n_tiles_1d;
+    const int64_t n_tiles = (int64_t)T * (T + 1) / 2;
+    if (!c || !c->c) { h->comm = nullptr; h->tile0 = 0; if (h->from_poses) h->n_cta = (int)n_tiles; return CAL_OK; }
+    const int rank = c->c->rank(), world = c->c->world();
+    if (n_tiles < world) return afail(CAL_ERR_INVALID_ARGUMENT, "fewer pair tiles than ranks");
+    const int64_t per = n_tiles / world, rem = n_tiles % world;
+    h->tile0 = rank * per + std::min<int64_t>(rank, rem);
+    h->n_cta = (int)(per + (rank < rem ? 1 : 0));
+    h->comm = c->c;
+    return CAL_OK;
+}
+
 // benchmark hook: `reps` Jacobian passes back to back on the handle's stream, timed with CUDA events on that stream
 extern "C" cal_status cal_axxb_bench_pass(cal_axxb_handle* h, const double* x7, int reps, float* ms_total) {
     if (!h || !x7 || reps <= 0 || !ms_total) return afail(CAL_ERR_INVALID_ARGUMENT, "bad argument");
@@ -179,10 +207,12 @@ extern "C" cal_status cal_axxb_bench_pass(cal_axxb_handle* h, const double* x7, 
     ACUDA(cudaStreamSynchronize(h->st));
     ACUDA(cudaEventRecord(e0, h->st));
     for (int r = 0; r < reps; ++r) {
-        if (h->from_poses) k_axxb_otf<1><<<h->n_cta, 256, 0, h->st>>>(h->tiles, h->x, h->huber, h->partial);
+        PairTiles t = h->tiles; t.tile_base = h->tile0;
+        if (h->from_poses) k_axxb_otf<1><<<h->n_cta, 256, 0, h->st>>>(t, h->x, h->huber, h->partial);
         else k_axxb<1><<<h->n_cta, 256, 0, h->st>>>(h->pairs, h->n, h->x, h->huber, h->partial);
         k_axxb_final<<<1, 32 * kAcc, 0, h->st>>>(h->partial, h->n_cta, h->out);
         h->launches += 2;
+        if (h->comm && !h->comm->allreduce_sum(h->out, kAcc, h->st)) return afail(CAL_ERR_COMM, h->comm->error());
     }
     ACUDA(cudaEventRecord(e1, h->st));
     ACUDA(cudaEventSynchronize(e1));

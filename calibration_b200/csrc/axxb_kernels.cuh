@@ -234,6 +234,7 @@ struct PairTiles {
     const double* G;   // [n][12] base_se3_gripper
     const double* C;   // [n][12] cam_se3_target
     unsigned* mask;    // [tile][32] one bit per pair
+    int64_t tile_base; // first tile of this launch (a rank of a sharded handle evaluates a slice of the tile space)
 };
 
 __device__ __forceinline__ void tile_coords(int64_t t, int T, int& bi, int& bj) {
@@ -289,7 +290,8 @@ template <int JAC>
 __global__ void __launch_bounds__(256) k_axxb_otf(PairTiles P, const double* __restrict__ x7, double huber, double* __restrict__ partial) {
     __shared__ double sG[64][12], sC[64][12];
     __shared__ double sm[8][kAcc];
-    int bi, bj; tile_coords(blockIdx.x, P.n_tiles_1d, bi, bj);
+    const int64_t tile = P.tile_base + blockIdx.x;
+    int bi, bj; tile_coords(tile, P.n_tiles_1d, bi, bj);
     stage_tile(P, bi, bj, sG, sC);
     double q[4], tx[3];
 #pragma unroll
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(256) k_axxb_otf(PairTiles P, const double* __r
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int pass = 0; pass < 4; ++pass) {
         const int li = pass * 8 + warp;
-        const unsigned m = P.mask[(int64_t)blockIdx.x * 32 + li];
+        const unsigned m = P.mask[tile * 32 + li];
         if ((m >> lane) & 1u) {
             double Ra[9], Rb[9], ta[3], tb[3];
             make_pair(sG[li], sG[32 + lane], sC[li], sC[32 + lane], Ra, Rb, ta, tb);

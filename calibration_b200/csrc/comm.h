@@ -63,3 +63,6 @@ class Comm {
 };
 
 }  // namespace calcomm
+
+// the opaque communicator of the C ABI (cal_comm_create): shared by the translation units that accept one
+struct cal_comm { calcomm::Comm* c = nullptr; };

@@ -22,9 +22,12 @@
 // the 9x9 normal matrix (refit) instead of Eigen::JacobiSVD, and the inlier
 // test compares squared errors.  Inlier sets are therefore identical whenever
 // no residual lies within rounding distance of the threshold.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/calib_b200.h"
@@ -49,25 +52,50 @@ size_t smem_per_cta(int n) {
     return kWarpsPerCta * ((per_warp + 15) / 16 * 16);
 }
 
-cal_status launch(int64_t n_problems, int n, const double* x, const double* y, const double* u, const double* v,
-                  const cal_ransac_options& o, int seed_per_problem, cal_ransac_result* res, uint8_t* mask, cudaStream_t st,
-                  float* ms) {
+// device memory / events of one call, released on every exit
+struct DevBuf { void* p = nullptr; ~DevBuf() { if (p) cudaFree(p); } template <class T> T* as() const { return static_cast<T*>(p); } };
+struct Ev { cudaEvent_t e = nullptr; ~Ev() { if (e) cudaEventDestroy(e); } };
+struct Stream { cudaStream_t s = nullptr; ~Stream() { if (s) cudaStreamDestroy(s); } };
+
+// the adaptive-iteration table of calculate_iterations for this (n, options): built once per call, on the device
+cal_status upload_niter_table(int n, const cal_ransac_options& o, DevBuf& dtable, cudaStream_t st) {
+    const std::vector<int> table = build_niter_table(n, o, 4);
+    RCUDA(cudaMalloc(&dtable.p, table.size() * sizeof(int)));
+    RCUDA(cudaMemcpyAsync(dtable.p, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    RCUDA(cudaStreamSynchronize(st));   // the host vector goes out of scope
+    return CAL_OK;
+}
+
+cal_status prepare_kernel(int n, size_t* smem_out) {
     const size_t smem = smem_per_cta(n);
     if (smem > 227 * 1024) return rfail(CAL_ERR_INVALID_ARGUMENT, "too many correspondences per problem for the shared-memory RANSAC kernel (n <= ~1700)");
     RCUDA(cudaFuncSetAttribute(k_ransac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    std::vector<int> table = build_niter_table(n, o, 4);
-    int* dtable; RCUDA(cudaMalloc(reinterpret_cast<void**>(&dtable), table.size() * sizeof(int)));
-    RCUDA(cudaMemcpyAsync(dtable, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    cudaEvent_t e0, e1; RCUDA(cudaEventCreate(&e0)); RCUDA(cudaEventCreate(&e1));
-    RCUDA(cudaEventRecord(e0, st));
+    *smem_out = smem;
+    return CAL_OK;
+}
+
+// queue the kernel for problems [0, n_problems) of the given arrays; `o.seed` is the seed of problem 0
+void enqueue(int64_t n_problems, int n, const double* x, const double* y, const double* u, const double* v, const cal_ransac_options& o,
+             int seed_per_problem, const int* dtable, size_t smem, cal_ransac_result* res, uint8_t* mask, cudaStream_t st) {
     const unsigned grid = (unsigned)((n_problems + kWarpsPerCta - 1) / kWarpsPerCta);
     k_ransac<<<grid, 32 * kWarpsPerCta, smem, st>>>(n_problems, n, x, y, u, v, o, seed_per_problem, dtable, res, mask);
-    RCUDA(cudaEventRecord(e1, st));
-    RCUDA(cudaEventSynchronize(e1));
+}
+
+cal_status launch(int64_t n_problems, int n, const double* x, const double* y, const double* u, const double* v,
+                  const cal_ransac_options& o, int seed_per_problem, cal_ransac_result* res, uint8_t* mask, cudaStream_t st,
+                  float* ms) {
+    size_t smem = 0;
+    if (cal_status s = prepare_kernel(n, &smem)) return s;
+    DevBuf dtable;
+    if (cal_status s = upload_niter_table(n, o, dtable, st)) return s;
+    Ev e0, e1; RCUDA(cudaEventCreate(&e0.e)); RCUDA(cudaEventCreate(&e1.e));
+    RCUDA(cudaEventRecord(e0.e, st));
+    enqueue(n_problems, n, x, y, u, v, o, seed_per_problem, dtable.as<int>(), smem, res, mask, st);
+    RCUDA(cudaEventRecord(e1.e, st));
+    RCUDA(cudaEventSynchronize(e1.e));
     RCUDA(cudaGetLastError());
-    float t = 0; RCUDA(cudaEventElapsedTime(&t, e0, e1));
+    float t = 0; RCUDA(cudaEventElapsedTime(&t, e0.e, e1.e));
     if (ms) *ms = t;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(dtable);
     return CAL_OK;
 }
 
@@ -83,6 +111,10 @@ extern "C" cal_status cal_ransac_homography_batch_dev(int64_t n_problems, int32_
     return launch(n_problems, n, x_dev, y_dev, u_dev, v_dev, *opts, seed_per_problem, results_dev, inlier_mask_dev, nullptr, ms);
 }
 
+// Host arrays in, host results out.  The problems are cut into chunks that travel through three streams — upload of
+// chunk k + 1, kernel of chunk k, download of chunk k - 1 overlap (the arrays should be page-locked for that: a copy
+// from pageable memory is staged by the driver and serialises) — so the call takes about max(PCIe time, kernel time),
+// not their sum.  Seeds follow the problem index, so the chunking does not change any result.
 extern "C" cal_status cal_ransac_homography_batch(int64_t n_problems, int32_t n, const double* x, const double* y,
                                                   const double* u, const double* v, const cal_ransac_options* opts,
                                                   int seed_per_problem, int device, cal_ransac_result* results,
@@ -90,24 +122,77 @@ extern "C" cal_status cal_ransac_homography_batch(int64_t n_problems, int32_t n,
     if (!opts || !results || !x || !y || !u || !v || n_problems <= 0 || n <= 0) return rfail(CAL_ERR_INVALID_ARGUMENT, "bad argument");
     if (cal_device_count() <= device) return rfail(CAL_ERR_CUDA, "no CUDA device: calib_b200 has no CPU fallback");
     RCUDA(cudaSetDevice(device));
-    const size_t nb = (size_t)n_problems * n * sizeof(double);
-    // every exit releases the device buffers (cudaFree(nullptr) is a no-op)
-    double* dxyuv = nullptr; cal_ransac_result* dres = nullptr; uint8_t* dmask = nullptr;
-    auto done = [&](cal_status rc) { cudaFree(dxyuv); cudaFree(dres); cudaFree(dmask); return rc; };
-    if (cudaMalloc(reinterpret_cast<void**>(&dxyuv), 4 * nb) != cudaSuccess ||
-        cudaMalloc(reinterpret_cast<void**>(&dres), (size_t)n_problems * sizeof(cal_ransac_result)) != cudaSuccess ||
-        (inlier_mask && cudaMalloc(reinterpret_cast<void**>(&dmask), (size_t)n_problems * n) != cudaSuccess))
-        return done(rfail(CAL_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(cudaGetLastError())));
+    size_t smem = 0;
+    if (cal_status s = prepare_kernel(n, &smem)) return s;
     const size_t ne = (size_t)n_problems * n;
-    double *dx = dxyuv, *dy = dx + ne, *du = dy + ne, *dv = du + ne;
-    if (cudaMemcpy(dx, x, nb, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(dy, y, nb, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(du, u, nb, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(dv, v, nb, cudaMemcpyHostToDevice) != cudaSuccess)
-        return done(rfail(CAL_ERR_CUDA, std::string("host to device copy: ") + cudaGetErrorString(cudaGetLastError())));
-    cal_status s = launch(n_problems, n, dx, dy, du, dv, *opts, seed_per_problem, dres, dmask, nullptr, nullptr);
-    if (s == CAL_OK) {
-        if (cudaMemcpy(results, dres, (size_t)n_problems * sizeof(cal_ransac_result), cudaMemcpyDeviceToHost) != cudaSuccess ||
-            (inlier_mask && cudaMemcpy(inlier_mask, dmask, (size_t)n_problems * n, cudaMemcpyDeviceToHost) != cudaSuccess))
-            s = rfail(CAL_ERR_CUDA, std::string("device to host copy: ") + cudaGetErrorString(cudaGetLastError()));
+    DevBuf dxyuv, dres, dmask, dtable;
+    RCUDA(cudaMalloc(&dxyuv.p, 4 * ne * sizeof(double)));
+    RCUDA(cudaMalloc(&dres.p, (size_t)n_problems * sizeof(cal_ransac_result)));
+    if (inlier_mask) RCUDA(cudaMalloc(&dmask.p, ne));
+    Stream up, run, down;
+    RCUDA(cudaStreamCreateWithFlags(&up.s, cudaStreamNonBlocking)); RCUDA(cudaStreamCreateWithFlags(&run.s, cudaStreamNonBlocking));
+    RCUDA(cudaStreamCreateWithFlags(&down.s, cudaStreamNonBlocking));
+    if (cal_status s = upload_niter_table(n, *opts, dtable, run.s)) return s;
+    double* dx = dxyuv.as<double>(); double *dy = dx + ne, *du = dy + ne, *dv = du + ne;
+    // few, large chunks: a problem's iteration count is data dependent, so a launch of a few thousand problems is
+    // dominated by its slowest ones (measured: 16 chunks of 6 250 problems took 3.7x the time of one launch)
+    int64_t chunk = 25000;
+    if (const char* e = getenv("CALIB_B200_RANSAC_CHUNK")) chunk = std::max<int64_t>(1, atoll(e));   // tests: exercise the pipeline at small sizes
+    const int64_t n_chunks = std::min<int64_t>(8, std::max<int64_t>(1, n_problems / chunk));
+    const int64_t per = (n_problems + n_chunks - 1) / n_chunks;
+    std::vector<Ev> uploaded((size_t)n_chunks), computed((size_t)n_chunks);
+    for (int64_t k = 0; k < n_chunks; ++k) {   // uploads and kernels are queued first (nothing here blocks the host) ...
+        const int64_t p0 = k * per, p1 = std::min(n_problems, p0 + per);
+        if (p0 >= p1) break;
+        const size_t off = (size_t)p0 * n, cnt = (size_t)(p1 - p0) * n * sizeof(double);
+        RCUDA(cudaMemcpyAsync(dx + off, x + off, cnt, cudaMemcpyHostToDevice, up.s)); RCUDA(cudaMemcpyAsync(dy + off, y + off, cnt, cudaMemcpyHostToDevice, up.s));
+        RCUDA(cudaMemcpyAsync(du + off, u + off, cnt, cudaMemcpyHostToDevice, up.s)); RCUDA(cudaMemcpyAsync(dv + off, v + off, cnt, cudaMemcpyHostToDevice, up.s));
+        RCUDA(cudaEventCreateWithFlags(&uploaded[k].e, cudaEventDisableTiming)); RCUDA(cudaEventRecord(uploaded[k].e, up.s));
+        RCUDA(cudaStreamWaitEvent(run.s, uploaded[k].e, 0));
+        cal_ransac_options o = *opts;
+        if (seed_per_problem) o.seed += (uint64_t)p0;
+        enqueue(p1 - p0, n, dx + off, dy + off, du + off, dv + off, o, seed_per_problem, dtable.as<int>(), smem, dres.as<cal_ransac_result>() + p0,
+                inlier_mask ? dmask.as<uint8_t>() + off : nullptr, run.s);
+        RCUDA(cudaEventCreateWithFlags(&computed[k].e, cudaEventDisableTiming)); RCUDA(cudaEventRecord(computed[k].e, run.s));
     }
-    return done(s);
+    for (int64_t k = 0; k < n_chunks; ++k) {   // ... then the downloads, chunk by chunk behind their kernels (a copy into pageable
+        const int64_t p0 = k * per, p1 = std::min(n_problems, p0 + per);   // memory blocks the host until its kernel is done)
+        if (p0 >= p1) break;
+        const size_t off = (size_t)p0 * n;
+        RCUDA(cudaStreamWaitEvent(down.s, computed[k].e, 0));
+        RCUDA(cudaMemcpyAsync(results + p0, dres.as<cal_ransac_result>() + p0, (size_t)(p1 - p0) * sizeof(cal_ransac_result), cudaMemcpyDeviceToHost, down.s));
+        if (inlier_mask) RCUDA(cudaMemcpyAsync(inlier_mask + off, dmask.as<uint8_t>() + off, (size_t)(p1 - p0) * n, cudaMemcpyDeviceToHost, down.s));
+    }
+    RCUDA(cudaStreamSynchronize(down.s));
+    RCUDA(cudaStreamSynchronize(run.s));
+    RCUDA(cudaGetLastError());
+    return CAL_OK;
+}
+
+// Independent problems split over several devices of the box, no communication at all: device d takes a
+// contiguous slice, its seeds continue the global problem index, one host thread per device.  devices may repeat.
+extern "C" cal_status cal_ransac_homography_batch_multi(int64_t n_problems, int32_t n, const double* x, const double* y,
+                                                        const double* u, const double* v, const cal_ransac_options* opts,
+                                                        int seed_per_problem, int32_t n_devices, const int32_t* devices,
+                                                        cal_ransac_result* results, uint8_t* inlier_mask) {
+    if (!opts || !results || !x || !y || !u || !v || n_problems <= 0 || n <= 0 || n_devices <= 0 || !devices) return rfail(CAL_ERR_INVALID_ARGUMENT, "bad argument");
+    const int nd = (int)std::min<int64_t>(n_devices, n_problems);
+    const int64_t per = (n_problems + nd - 1) / nd;
+    std::vector<cal_status> rc((size_t)nd, CAL_OK);
+    std::vector<std::string> msg((size_t)nd);
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; ++d)
+        th.emplace_back([&, d] {
+            const int64_t p0 = d * per, p1 = std::min(n_problems, p0 + per);
+            if (p0 >= p1) return;
+            const size_t off = (size_t)p0 * n;
+            cal_ransac_options o = *opts;
+            if (seed_per_problem) o.seed += (uint64_t)p0;
+            rc[d] = cal_ransac_homography_batch(p1 - p0, n, x + off, y + off, u + off, v + off, &o, seed_per_problem, devices[d], results + p0,
+                                                inlier_mask ? inlier_mask + off : nullptr);
+            if (rc[d] != CAL_OK) msg[d] = cal_last_error();   // (thread-local in the callee's thread)
+        });
+    for (auto& t : th) t.join();
+    for (int d = 0; d < nd; ++d) if (rc[d] != CAL_OK) return rfail(rc[d], msg[d]);
+    return CAL_OK;
 }

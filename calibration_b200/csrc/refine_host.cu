@@ -982,18 +982,29 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
         // The normal equations of the last accepted point are still on the device / in the host mirrors: the LM
         // evaluates the Jacobian only at accepted points and x only moves on acceptance, so no extra pass.
         std::vector<double> xf(x_inout, x_inout + na);
-        if (views && h.comm) return CAL_OK;  // sharded per-view kinds: the dense covariance would need every rank's views
         if (views) {
+            // Sharded by views: the shared block's covariance W comes from the ALL-REDUCED Schur complement, so it is the
+            // global one on every rank; the view blocks this rank returns are those of ITS views (cov is [na][na] over the
+            // rank's own parameter vector: shared blocks + local views).  Blocks between views of different ranks are
+            // Z_v W Z_w^T with Z of both ranks and are not formed — the reference's dense matrix is only defined for a few
+            // thousand views, which one GPU holds.
             // ---- block-structured covariance (refine_kernels.cu, k_cov_*): shared block on the host, view blocks on the device ----
             CUDA_TRY(cudaMemsetAsync(V.fail, 0, sizeof(int32_t), h.st));
             launch_schur(S, h.L, h.B, V, ns, std::numeric_limits<double>::infinity(), h.st); h.launches += 3;
+            if (h.comm && !h.comm->allreduce_sum(V.C, (size_t)ns * ns, h.st)) return fail(CAL_ERR_COMM, h.comm->error());
             int32_t failed = 0;
             CUDA_TRY(cudaMemcpyAsync(Cs.data(), V.C, sizeof(double) * ns * ns, cudaMemcpyDeviceToHost, h.st));
             CUDA_TRY(cudaMemcpyAsync(&failed, V.fail, sizeof failed, cudaMemcpyDeviceToHost, h.st));
             CUDA_TRY(cudaStreamSynchronize(h.st));
-            if (failed) return CAL_OK;  // a rank-deficient view block: covariance stays empty (ceresutils.h:86-88)
+            if (h.comm) {
+                if (!h.comm->check_timeout()) return fail(CAL_ERR_COMM, h.comm->error());
+                double f = failed ? 1.0 : 0.0;
+                if (!h.comm->allreduce_host(&f, 1, true)) return fail(CAL_ERR_COMM, h.comm->error());
+                failed = f != 0.0;
+            }
+            if (failed) { if (trace) std::fprintf(stderr, "[calib_b200] covariance: a view block is rank deficient\n"); return CAL_OK; }  // covariance stays empty (ceresutils.h:86-88)
             for (int i = 0; i < ns; ++i) for (int j = 0; j < ns; ++j) Sm[(size_t)i * ns + j] = h.Hss[(size_t)i * ns + j] * s[i] * s[j] - Cs[(size_t)i * ns + j];
-            if (ns > 0 && !chol_host(Sm, ns)) return CAL_OK;
+            if (ns > 0 && !chol_host(Sm, ns)) { if (trace) std::fprintf(stderr, "[calib_b200] covariance: the reduced shared block is rank deficient\n"); return CAL_OK; }
             std::vector<double> W((size_t)ns * ns), e(std::max(ns, 1));
             for (int j = 0; j < ns; ++j) { std::fill(e.begin(), e.end(), 0.0); e[j] = 1.0; chol_solve_host(Sm, ns, e.data()); for (int i = 0; i < ns; ++i) W[(size_t)i * ns + j] = e[i]; }
             double *dW = nullptr, *dZ = nullptr, *dG = nullptr, *dAinv = nullptr, *dcov = nullptr;
@@ -1096,8 +1107,6 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
     }
     return CAL_OK;
 }
-
-struct cal_comm { calcomm::Comm* c = nullptr; };
 
 extern "C" cal_status cal_comm_create(const uint8_t unique_id[128], int rank, int world_size, int device, cal_comm** out) {
     if (!unique_id || !out) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");

@@ -214,6 +214,9 @@ void cal_axxb_destroy(cal_axxb_handle* h);
 cal_status cal_axxb_eval(cal_axxb_handle* h, const double* x7, double* cost, double* g6, double* H36);
 cal_status cal_axxb_solve(cal_axxb_handle* h, const cal_optim_options* opts, double* x7_inout,
                           cal_optim_result* result, double* cov49);
+/* Shard a handle created from poses over the ranks of a communicator (cal_comm_create, below): each rank evaluates a
+ * contiguous slice of the pair tiles, the 6x6 + 6 + 1 sums are all-reduced after every pass.  NULL detaches. */
+cal_status cal_axxb_attach_comm(cal_axxb_handle* h, cal_comm* comm);
 /* Benchmark hooks (no reference counterpart): `reps` residual + Jacobian passes back to back, timed with CUDA events on
  * the handle's stream; kernels launched by the handle so far. */
 cal_status cal_axxb_bench_pass(cal_axxb_handle* h, const double* x7, int reps, float* ms_total);
@@ -249,6 +252,13 @@ cal_status cal_ransac_homography_batch(int64_t n_problems, int32_t n, const doub
                                        const double* u, const double* v, const cal_ransac_options* opts,
                                        int seed_per_problem, int device, cal_ransac_result* results,
                                        uint8_t* inlier_mask);
+/* The same batch split by problem over several devices of the box, one host thread per device, no communication
+ * (independent-problem batches); devices[d] takes a contiguous slice and its seeds continue the global
+ * problem index, so every result is what one device returns for the whole batch.  Device ids may repeat. */
+cal_status cal_ransac_homography_batch_multi(int64_t n_problems, int32_t n, const double* x, const double* y,
+                                             const double* u, const double* v, const cal_ransac_options* opts,
+                                             int seed_per_problem, int32_t n_devices, const int32_t* devices,
+                                             cal_ransac_result* results, uint8_t* inlier_mask);
 /* Device-resident variant used by the benchmark: pointers are device memory,
  * results stay on the device; returns the CUDA-event time of the kernel. */
 cal_status cal_ransac_homography_batch_dev(int64_t n_problems, int32_t n, const double* x_dev, const double* y_dev,

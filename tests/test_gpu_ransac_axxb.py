@@ -40,6 +40,30 @@ def test_batched_ransac_bit_exact_masks():
     assert 300 < np.mean([r.n_inliers for r in rg]) < 380
 
 
+def test_batched_ransac_ten_thousand_problems_through_the_chunked_pipeline(monkeypatch):
+    """A tenth of BASELINE configs[1] (10 000 x 500): the host entry cuts the batch into chunks that overlap upload, kernel
+    and download; every chunk's seeds continue the global problem index, so the masks stay bit-exact against the oracle."""
+    x, y, u, v, _ = synth.synth_ransac(seed=23, n_problems=10000, n=500)
+    monkeypatch.setenv("CALIB_B200_RANSAC_CHUNK", "3000")   # three chunks here (the default chunk is 25 000 problems)
+    n_checked, ro, rg = compare_ransac(x, y, u, v, abi.RansacOptions.default())
+    assert n_checked >= 0.99 * 10000
+    assert sum(r.success for r in rg) == sum(r.success for r in ro) >= 9990
+
+
+def test_batch_split_over_devices_returns_what_one_device_returns():
+    """cal_ransac_homography_batch_multi (independent problems, no communication): slices on several devices — here the
+    same device three times, and every device of the box when there are more — give the single-device results bit for bit."""
+    x, y, u, v, _ = synth.synth_ransac(seed=29, n_problems=1500, n=300)
+    opts = abi.RansacOptions.default()
+    r1, m1 = capi.ransac_homography_batch(x, y, u, v, opts)
+    for devices in ([0, 0, 0], list(range(capi.device_count()))):
+        rm, mm = capi.ransac_homography_batch(x, y, u, v, opts, devices=devices)
+        assert np.array_equal(mm, m1)
+        assert bytes(rm) == bytes(r1)
+    with pytest.raises(capi.CalibCudaError):
+        capi.ransac_homography_batch(x, y, u, v, opts, devices=[0, 99])
+
+
 @pytest.mark.parametrize("n", [4, 5, 31, 33, 130, 257])
 def test_ragged_sizes(n):
     x, y, u, v, _ = synth.synth_ransac(seed=n, n_problems=40, n=n, outlier_fraction=0.2)
