@@ -36,6 +36,7 @@ def lib():
         L.orc_refine_solve.argtypes = [C.POINTER(abi.ProblemDesc), C.POINTER(abi.OptimOptions), dp,
                                        C.POINTER(abi.OptimResult), dp, C.c_int]
         L.orc_block_ssr.argtypes = [C.POINTER(abi.ProblemDesc), dp, dp, C.c_int]
+        L.orc_analytic_bundle_eval.argtypes = [C.POINTER(abi.ProblemDesc), dp, dp, dp, dp, C.c_int]
         L.orc_project.argtypes = [C.c_int, dp, dp, dp]
         L.orc_axxb_eval.argtypes = [C.POINTER(abi.AxxbDesc), dp, dp, dp, dp, C.c_int]
         L.orc_axxb_solve.argtypes = [C.POINTER(abi.AxxbDesc), C.POINTER(abi.OptimOptions), dp,
@@ -95,6 +96,17 @@ def refine_solve(prob, x0, opts=None, force_dense=False, want_cov=True):
     cov = np.zeros((len(x), len(x))) if (want_cov and opts.compute_covariance) else None
     L.orc_refine_solve(C.byref(prob.desc), C.byref(opts), abi.dptr(x), C.byref(res), abi.dptr(cov), int(force_dense))
     return x, res, cov
+
+
+def analytic_bundle_eval(prob, x, jac=True, threads=0):
+    """The conservative CPU baseline (oracle/analytic_pass.cpp): hand-derived Jacobians, OpenMP over residual blocks;
+    returns (cost, g, H) over the shared tangent blocks like refine_eval does for the bundle kind."""
+    L = lib()
+    n = int(L.orc_tangent_count(C.byref(prob.desc)))
+    cost = C.c_double(); g = np.zeros(n) if jac else None; H = np.zeros((n, n)) if jac else None
+    rc = L.orc_analytic_bundle_eval(C.byref(prob.desc), abi.dptr(abi.as_f64(x)), C.cast(C.byref(cost), abi.c_double_p), abi.dptr(g), abi.dptr(H), threads)
+    assert rc == 0
+    return cost.value, g, H
 
 
 def block_ssr(prob, x, threads=0):
