@@ -91,11 +91,14 @@ void quat_plus_jacobian(const double* q, double* J) {  // QuaternionManifold::Pl
 struct PinPool {
     std::mutex m;
     std::vector<std::pair<size_t, double*>> idle;   // (doubles, block)
+    std::vector<std::pair<size_t, double*>> lent;   // blocks handed out through cal_host_borrow
     double* get(size_t n, size_t* got) {
         {
             std::lock_guard<std::mutex> lk(m);
+            size_t best = idle.size();
             for (size_t i = 0; i < idle.size(); ++i)
-                if (idle[i].first >= n) { double* p = idle[i].second; *got = idle[i].first; idle.erase(idle.begin() + (long)i); return p; }
+                if (idle[i].first >= n && (best == idle.size() || idle[i].first < idle[best].first)) best = i;
+            if (best < idle.size()) { double* p = idle[best].second; *got = idle[best].first; idle.erase(idle.begin() + (long)best); return p; }
         }
         const size_t cap = std::max<size_t>(n, 4096);
         double* p = nullptr;
@@ -105,7 +108,8 @@ struct PinPool {
     }
     void put(double* p, size_t n) { if (p) { std::lock_guard<std::mutex> lk(m); idle.emplace_back(n, p); } }
 };
-PinPool& pin_pool() { static PinPool* pool = new PinPool; return *pool; }
+PinPool& pin_pool() { static PinPool* pool = new PinPool; return *pool; }     // small result blocks of the handles
+PinPool& host_pool() { static PinPool* pool = new PinPool; return *pool; }    // large staging blocks of callers (cal_host_borrow)
 
 }  // namespace
 
@@ -199,6 +203,31 @@ cal_status validate(const cal_problem_desc& d) {
 extern "C" const char* cal_last_error(void) { return g_err.c_str(); }
 // internal: lets the other translation units of the library report through cal_last_error()
 extern "C" void cal_set_last_error_(const char* msg) { g_err = msg ? msg : ""; }
+
+// Page-locked host memory for callers that stage large inputs (the C++ adapter packs std::vector<BundleObservation>
+// into it): borrowed from a process-wide pool that is never shrunk, so a long-running caller page-locks once.
+extern "C" cal_status cal_host_borrow(size_t bytes, void** out) {
+    if (!out) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (cal_device_count() <= 0) return fail(CAL_ERR_CUDA, "no CUDA device: calib_b200 has no CPU fallback");
+    size_t got = 0;
+    double* p = host_pool().get((bytes + 7) / 8, &got);
+    if (!p) return fail(CAL_ERR_CUDA, "page-locked allocation failed");
+    { std::lock_guard<std::mutex> lk(host_pool().m); host_pool().lent.emplace_back(got, p); }
+    *out = p;
+    return CAL_OK;
+}
+extern "C" void cal_host_return(void* ptr) {
+    if (!ptr) return;
+    PinPool& pool = host_pool();
+    size_t n = 0;
+    {
+        std::lock_guard<std::mutex> lk(pool.m);
+        for (size_t i = 0; i < pool.lent.size(); ++i)
+            if (pool.lent[i].second == ptr) { n = pool.lent[i].first; pool.lent.erase(pool.lent.begin() + (long)i); break; }
+    }
+    if (n) pool.put(static_cast<double*>(ptr), n);
+}
 
 extern "C" int cal_device_count(void) {
     int n = 0;

@@ -165,6 +165,11 @@ cal_status cal_refine_view_errors(cal_refine_handle* h, const double* x, double*
 cal_status cal_refine_solve(cal_refine_handle* h, const cal_optim_options* opts, double* x_inout,
                             cal_optim_result* result, double* cov);
 
+/* Page-locked host memory for staging large inputs (copies from it run at full PCIe speed and overlap with kernels).
+ * Blocks come from a process-wide pool that is never shrunk: a long-running caller pays the page-locking once. */
+cal_status cal_host_borrow(size_t bytes, void** out);
+void cal_host_return(void* ptr);
+
 /* Optional multi-GPU sharding (one process per GPU).  Each rank creates its
  * handle over its own shard of the residual blocks (all ranks pass identical
  * n_cams and shared parameters) and attaches a communicator; the per-camera

@@ -22,11 +22,14 @@
 // std::runtime_error, anything else -> std::runtime_error).
 #pragma once
 
+#include <algorithm>
 #include <array>
+#include <atomic>
 #include <cstdlib>
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #if __has_include(<Eigen/Core>) && __has_include("calib/estimation/optim/bundle.h")
@@ -139,6 +142,65 @@ struct Soa {
     }
 };
 
+// Large inputs (millions of observations): the AoS views — one heap vector per view — are packed by several threads
+// straight into page-locked staging borrowed from the library (cal_host_borrow: a process-wide pool, so a long-running
+// caller page-locks once), in ONE pass over the observations that also checks whether every view shows the same board
+// (then only u, v travel: 16 instead of 32 bytes per observation).  A view that differs sends the call down the general
+// path (Soa::add).  Same cal_problem_desc as the serial packing, bit for bit.
+struct BundleStage {
+    void* block = nullptr;
+    double *u = nullptr, *v = nullptr, *bTg = nullptr, *bx = nullptr, *by = nullptr;
+    int64_t* off = nullptr; int32_t* cam = nullptr;
+    int64_t n_blocks = 0, n_obs = 0; int32_t board_n = 0;
+    ~BundleStage() { if (block) cal_host_return(block); }
+    // false: the views do not share one board (or a view is empty): nothing usable was produced
+    bool pack(const std::vector<BundleObservation>& obs) {
+        n_blocks = static_cast<int64_t>(obs.size());
+        board_n = static_cast<int32_t>(obs[0].view.size());
+        if (board_n == 0) return false;
+        for (const auto& o : obs) if (static_cast<int32_t>(o.view.size()) != board_n) return false;   // ragged: general path
+        n_obs = n_blocks * board_n;
+        const size_t bytes = sizeof(double) * (2 * static_cast<size_t>(n_obs) + 12 * static_cast<size_t>(n_blocks) + 2 * static_cast<size_t>(board_n)) +
+                             sizeof(int64_t) * (static_cast<size_t>(n_blocks) + 1) + sizeof(int32_t) * static_cast<size_t>(n_blocks) + 64;
+        check(cal_host_borrow(bytes, &block));
+        u = static_cast<double*>(block); v = u + n_obs; bTg = v + n_obs; bx = bTg + 12 * n_blocks; by = bx + board_n;
+        off = reinterpret_cast<int64_t*>(by + board_n); cam = reinterpret_cast<int32_t*>(off + n_blocks + 1);
+        for (int32_t i = 0; i < board_n; ++i) { bx[i] = obs[0].view[static_cast<size_t>(i)].object_xy.x(); by[i] = obs[0].view[static_cast<size_t>(i)].object_xy.y(); }
+        const unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        std::atomic<bool> same{true};
+        for (unsigned t = 0; t < nt; ++t)
+            th.emplace_back([&, t] {
+                const int64_t b0 = n_blocks * t / nt, b1 = n_blocks * (t + 1) / nt;
+                bool ok = true;
+                for (int64_t b = b0; b < b1; ++b) {
+                    const BundleObservation& o = obs[static_cast<size_t>(b)];
+                    double* pu = u + b * board_n; double* pv = v + b * board_n;
+                    for (int32_t i = 0; i < board_n; ++i) {
+                        const auto& p = o.view[static_cast<size_t>(i)];
+                        ok = ok && p.object_xy.x() == bx[i] && p.object_xy.y() == by[i];
+                        pu[i] = p.image_uv.x(); pv[i] = p.image_uv.y();
+                    }
+                    off[b] = b * board_n; cam[b] = static_cast<int32_t>(o.camera_index);
+                    const Eigen::Matrix3d R = o.b_se3_g.linear(); const Eigen::Vector3d tr = o.b_se3_g.translation();
+                    double* g = bTg + 12 * b;
+                    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) g[3 * i + j] = R(i, j);
+                    for (int i = 0; i < 3; ++i) g[9 + i] = tr(i);
+                }
+                if (!ok) same.store(false);
+            });
+        for (auto& t : th) t.join();
+        off[n_blocks] = n_obs;
+        return same.load();
+    }
+    void fill(cal_problem_desc& d) const {
+        d.n_blocks = n_blocks; d.n_obs = n_obs;
+        d.board_x = bx; d.board_y = by; d.board_n = board_n;
+        d.img_u = u; d.img_v = v; d.block_offset = off; d.block_cam = cam; d.block_b_se3_g = bTg;
+    }
+};
+constexpr size_t kStageThreshold = size_t{1} << 20;   // observations from which the staged, threaded packing pays
+
 inline cal_optim_options to_c(const OptimOptions& o) {
     return cal_optim_options{static_cast<int32_t>(o.optimizer), o.max_iterations, o.epsilon, o.compute_covariance ? 1 : 0,
                              o.verbose ? 1 : 0, 0, 0};
@@ -173,18 +235,24 @@ auto optimize_bundle(const std::vector<BundleObservation>& observations, const s
     if (init_g_se3_c.size() != initial_cameras.size())
         throw std::invalid_argument("optimize_bundle: one initial hand-eye pose per camera required");
     b200::Soa s;
-    for (const auto& ob : observations) {
-        s.add(ob.view, static_cast<int>(ob.camera_index), -1);
-        const Eigen::Matrix3d R = ob.b_se3_g.linear(); const Eigen::Vector3d t = ob.b_se3_g.translation();
-        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) s.bTg.push_back(R(i, j));
-        for (int i = 0; i < 3; ++i) s.bTg.push_back(t(i));
-    }
+    b200::BundleStage stage;
     cal_problem_desc d{};
     d.kind = CAL_KIND_BUNDLE; d.model = b200::model_of<CameraT>(); d.n_cams = static_cast<int>(initial_cameras.size());
     d.optimize_intrinsics = opts.optimize_intrinsics; d.optimize_skew = opts.optimize_skew;
     d.optimize_target_pose = opts.optimize_target_pose; d.optimize_hand_eye = opts.optimize_hand_eye;
     d.huber_delta = opts.core.huber_delta;
-    s.fill(d);
+    const bool staged = s.shared && observations.size() * observations[0].view.size() >= b200::kStageThreshold && stage.pack(observations);
+    if (staged) {
+        stage.fill(d);
+    } else {
+        for (const auto& ob : observations) {
+            s.add(ob.view, static_cast<int>(ob.camera_index), -1);
+            const Eigen::Matrix3d R = ob.b_se3_g.linear(); const Eigen::Vector3d t = ob.b_se3_g.translation();
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) s.bTg.push_back(R(i, j));
+            for (int i = 0; i < 3; ++i) s.bTg.push_back(t(i));
+        }
+        s.fill(d);
+    }
     const size_t nc = initial_cameras.size();
     std::vector<double> x(nc * (P + 7) + 7);
     for (size_t c = 0; c < nc; ++c) {

@@ -116,6 +116,10 @@ cal_status cal_refine_create(const cal_problem_desc* desc, int, cal_refine_handl
     return CAL_OK;
 }
 void cal_refine_destroy(cal_refine_handle* h) { delete h; }
+#if !defined(STANDIN_NO_REFINE)   // (the CPU build of the product's host code brings its own)
+cal_status cal_host_borrow(size_t bytes, void** out) { *out = std::malloc(bytes ? bytes : 1); return *out ? CAL_OK : CAL_ERR_CUDA; }
+void cal_host_return(void* p) { std::free(p); }
+#endif
 
 cal_status cal_refine_solve(cal_refine_handle* h, const cal_optim_options* o, double* x, cal_optim_result* r, double* cov) {
     orc_optim_result rr{};

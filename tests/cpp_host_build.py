@@ -105,3 +105,19 @@ def build_example(real):
 
 def run(exe, env, *filters, timeout=600):
     return subprocess.run([exe, *filters], capture_output=True, text=True, timeout=timeout, env=env)
+
+
+E2E_EXAMPLE = os.path.join(ROOT, "examples", "cpp_bundle_e2e.cpp")
+
+
+def build_bundle_e2e():
+    """examples/cpp_bundle_e2e.cpp (optimize_bundle from std::vector<BundleObservation> at BASELINE configs[4] scale) against the product library."""
+    from calibration_b200 import build
+    lib = build.build()
+    libdir = os.path.dirname(lib)
+    exe = os.path.join(ROOT, "examples", "_build", "cpp_bundle_e2e")
+    if _stale(exe, [E2E_EXAMPLE, lib] + SOURCES[3:]):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.run([CXX, "-std=c++20", "-O2", "-Wall", "-Wextra", "-Werror", "-pthread", "-I", INC, E2E_EXAMPLE, "-o", exe, "-L", libdir, "-lcalib_b200",
+                        "-Wl,-rpath," + libdir], check=True)
+    return exe, dict(os.environ, LD_LIBRARY_PATH=libdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))

@@ -211,6 +211,30 @@ def test_axxb_pairs_on_the_fly_at_scale():
     assert r_f.success and np.abs(x_f - x_m).max() <= 1e-9
 
 
+def test_axxb_at_the_named_size_five_thousand_poses():
+    """BASELINE configs[3]: optimize_handeye from 5 000 robot poses.  The device forms all 12.5 M motion pairs on the fly; the
+    oracle materialises them (build_all_pairs) — same kept-pair count, same normal equations, same solution and covariance."""
+    bg, ct, X_gt = synth.make_handeye_poses(seed=3, n=5000)
+    rng = np.random.default_rng(0)
+    ct = [synth.perturb_pose(rng, T, 0.3, 0.002) for T in ct]
+    x0 = G.pack_handeye(synth.perturb_pose(rng, X_gt, 2.0, 0.01))
+    ra, rb, ta, tb = O.build_all_pairs(bg, ct, 0.5)
+    h = capi.AxxbHandle.from_poses(bg, ct, 0.05)
+    try:
+        assert h.n_pairs == len(ta) > 12_000_000
+        d = O.axxb_desc(ra, rb, ta, tb, 0.05)
+        c_o, g_o, H_o = O.axxb_eval(d, x0)
+        c_g, g_g, H_g = h.eval(x0)
+        assert abs(c_g - c_o) <= 1e-11 * c_o
+        assert np.abs(g_g - g_o).max() <= 1e-9 * np.abs(g_o).max() and np.abs(H_g - H_o).max() <= 1e-9 * np.abs(H_o).max()
+        x_o, r_o, cov_o = O.axxb_solve(d, x0)
+        x_g, r_g, cov_g = h.solve(x0)
+    finally:
+        h.close()
+    assert r_g.success == r_o.success and r_g.iterations == r_o.iterations and np.abs(x_g - x_o).max() <= 1e-8
+    assert np.abs(cov_g - cov_o).max() <= 1e-6 * np.abs(cov_o).max()
+
+
 def test_axxb_from_poses_errors_mirror_reference():
     I = [np.eye(4)] * 5
     with pytest.raises(RuntimeError, match="No valid motion pairs"):     # handeyedlt.cpp:76-79
