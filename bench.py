@@ -36,21 +36,42 @@ OTHER_WORKLOADS = ("c1", "c2", "c3", "c4", "c4-axxb")   # BASELINE configs[0]-[3
 CHUNK = 12500  # robot poses per generation chunk (8 chunks for c5)
 
 
-def k1_traffic_bytes(args, world):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch from the committed `ncu --set full` capture of this
-    very command (profiles/r1_k1_fused_ncu_full_bench_c5.csv: C5, one GPU, free intrinsics); None for any other shape."""
+K1_NCU_CSV = os.path.join("profiles", "r2_k1_fused_ncu_full_bench_c5.csv")   # ncu --set full of this command on the current kernel (tools/ncu_summary.py)
+
+
+def k1_ncu_record(args, world):
+    """What the committed `ncu --set full` capture of K1 inside this very command says (C5, one GPU, free intrinsics; None for any
+    other shape): DRAM bytes per launch (`roofline.traffic`), the capture's own duration (cold, serialised: compare shares) and the
+    executed FP64 instruction counts, from which the flop per observation of the FP64 roofline follow (DFMA = 2, DMUL / DADD = 1)."""
     if args.workload != "c5" or world != 1 or args.fixed_intrinsics:
         return None
-    path = os.path.join(ROOT, "profiles", "r1_k1_fused_ncu_full_bench_c5.csv")
+    path = os.path.join(ROOT, K1_NCU_CSV)
     if not os.path.exists(path):
         return None
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot = 0.0
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1e-3, "ms": 1.0}
+    rec = {}
     for line in open(path):
-        parts = line.strip().split(",")
-        if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            tot += float(parts[2]) * scale[parts[1]]
-    return tot or None
+        parts = line.rstrip("\n").rsplit(",", 3)
+        if len(parts) == 4 and parts[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum",
+                                            "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed",
+                                            "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed",
+                                            "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed", "sm__cycles_elapsed.avg",
+                                            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"):
+            try:
+                rec[parts[1]] = float(parts[3]) * scale.get(parts[2], 1.0)
+            except ValueError:
+                pass
+    if "dram__bytes_read.sum" not in rec:
+        return None
+    n_obs = WORKLOADS["c5"][0] * WORKLOADS["c5"][1] * 88
+    out = {"traffic": rec["dram__bytes_read.sum"] + rec.get("dram__bytes_write.sum", 0.0), "capture_ms": rec.get("gpu__time_duration.sum"),
+           "fp64_pipe_active_pct": rec.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"), "source": K1_NCU_CSV}
+    cyc = rec.get("sm__cycles_elapsed.avg")   # thread-level instruction counts = rate per elapsed cycle x elapsed cycles
+    dfma, dmul, dadd = ((rec.get(f"smsp__sass_thread_inst_executed_op_{k}_pred_on.sum.per_cycle_elapsed") or 0.0) * (cyc or 0.0) for k in ("dfma", "dmul", "dadd"))
+    if dfma:
+        out["fp64_inst_per_obs"] = {"dfma": dfma / n_obs, "dmul": dmul / n_obs, "dadd": dadd / n_obs}
+        out["flop_per_obs"] = (2 * dfma + dmul + dadd) / n_obs
+    return out
 
 
 def peaks():
@@ -262,7 +283,8 @@ def _run_b200(args, rank, world, local_rank):
     achieved_gbs = obs_bytes_local / (k1_ms_launch * 1e-3) / 1e9
     # FP64 work of K1 per observation, from the SASS instruction mix of the committed ncu capture
     # (profiles/): DFMA counts 2 flops, DMUL/DADD 1; see DESIGN.md §5.
-    flop_per_obs = args.k1_flop_per_obs
+    ncu_rec = k1_ncu_record(args, world) or {}
+    flop_per_obs = args.k1_flop_per_obs or ncu_rec.get("flop_per_obs") or 560.0
     k1_tflops = flop_per_obs * n_obs_local / (k1_ms_launch * 1e-3) / 1e12
     out = {
         "metric": "observations/s in residual+Jacobian+JtJ pass",
@@ -289,13 +311,21 @@ def _run_b200(args, rank, world, local_rank):
                                                  "PCIe-bound, the bound a caller pays who uploads for a single evaluation"}},
         "gpu_launches": launches_timed,
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                     "traffic": k1_traffic_bytes(args, world), "traffic_source": "profiles/r1_k1_fused_ncu_full_bench_c5.csv (ncu --set full of this command)",
+                     "traffic": ncu_rec.get("traffic"), "traffic_source": (K1_NCU_CSV + " (ncu --set full of this command on this kernel, not re-measured by this run; "
+                                                                           f"the capture's own launch took {ncu_rec.get('capture_ms')} ms)") if ncu_rec else None,
                      "peak_source": pk_src, "kernel": "k1_kernel", "kernel_ms_per_launch": k1_ms_launch,
                      "kernel_share_of_step": ms_k1 / ms_total,
                      "algorithmic_bytes_per_launch": obs_bytes_local,
                      "binding_roof": "fp64",
                      "fp64": {"achieved": k1_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": k1_tflops / fp64_peak,
-                              "flop_per_observation": flop_per_obs, "peak_source": "DFMA-chain microbenchmark run in this process"}},
+                              "flop_per_observation": flop_per_obs, "peak_source": "DFMA-chain microbenchmark run in this process",
+                              "flop_source": (K1_NCU_CSV + ": executed DFMA x 2 + DMUL + DADD per observation") if ncu_rec.get("flop_per_obs") and not args.k1_flop_per_obs
+                              else "--k1-flop-per-obs" if args.k1_flop_per_obs else "default (237 DFMA + 44 DMUL + 42 DADD per observation)",
+                              # the step loop issues one 64-bit shared-memory instruction per 6.2 FP64 instructions (the exchange of the Jacobian rows
+                              # between the two threads that split a block's 136-entry system); on B200 such an instruction costs the FP64 pipe
+                              # 1.6 DFMA issue slots at ANY occupancy (tools/ubench_fp64_mix.cu, profiles/r2_ubench_fp64.txt), so this mix cannot
+                              # exceed 1 / (1 + 1.6 / 6.2) of the DFMA peak
+                              "instruction_mix_bound_frac": 1.0 / (1.0 + 1.6 / 6.2)}},
         "cost_pass": {"ms_per_step": ms_c / args.steps, "kernel_ms": ms_ck / args.steps,
                       "value": n_obs_total / (ms_c / args.steps * 1e-3),
                       "hbm_frac": (obs_bytes_local / (ms_ck / args.steps * 1e-3) / 1e9) / hbm_peak},
@@ -503,9 +533,9 @@ def main():
     ap.add_argument("--cpu-sample-div", type=int, default=64)
     ap.add_argument("--no-board-probe", action="store_true", help="skip the shared-board e2e probe (N = 1 only; runs in a child process)")
     ap.add_argument("--probe-shared-board", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--k1-flop-per-obs", type=float, default=560.0,
-                    help="FP64 flop per observation of K1 from the committed ncu capture (profiles/r1_k1_fused_ncu_full_35M.csv: "
-                         "237 DFMA + 44 DMUL + 42 DADD per observation, epilogue included)")
+    ap.add_argument("--k1-flop-per-obs", type=float, default=0.0,
+                    help="override the FP64 flop per observation of K1 (default: executed DFMA x 2 + DMUL + DADD of the committed ncu capture, "
+                         "profiles/r2_k1_fused_ncu_full_bench_c5.csv, epilogue included; 560 when that file is absent)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -45,7 +45,7 @@ class ProblemDesc(C.Structure):
         ("board_x", c_double_p),
         ("board_y", c_double_p),
         ("board_n", C.c_int32),
-        ("reserved", C.c_int32),
+        ("n_views_total", C.c_int32),
     ]
 
 

@@ -174,7 +174,7 @@ namespace {
 cal_status validate(const cal_problem_desc& d) {
     if (d.kind < 0 || d.kind > 2 || d.model < 0 || d.model > 1) return fail(CAL_ERR_INVALID_ARGUMENT, "unknown problem kind / camera model");
     if (d.n_cams <= 0) return fail(CAL_ERR_INVALID_ARGUMENT, "No camera intrinsics provided");            // bundle.cpp:139-141
-    if (d.kind == CAL_KIND_INTRINSICS && d.n_views < 4)
+    if (d.kind == CAL_KIND_INTRINSICS && std::max(d.n_views, d.n_views_total) < 4)
         return fail(CAL_ERR_INVALID_ARGUMENT, "Insufficient views for calibration (at least 4 required).");  // intrinsics.cpp:92-96
     if (d.n_blocks <= 0 || d.n_obs <= 0) return fail(CAL_ERR_INVALID_ARGUMENT, "No observations provided");    // bundle.cpp:142-144
     if (d.board_n < 0) return fail(CAL_ERR_INVALID_ARGUMENT, "board_n < 0");
@@ -477,6 +477,17 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         for (int v = 0; v < S.n_views; ++v) off[v + 1] += off[v];
         idx.assign(off[S.n_views], 0);
         { std::vector<int32_t> cur(off.begin(), off.end() - 1); for (int64_t b = 0; b < nblk; ++b) if (bview[b] >= 0) idx[cur[bview[b]]++] = (int32_t)b; }
+        {   // one residual block per (view, camera): the Schur kernels place a view's rows per camera and would overwrite a duplicate
+            std::vector<char> seen(S.n_cams, 0);
+            for (int v = 0; v < S.n_views; ++v) {
+                for (int k = off[v]; k < off[v + 1]; ++k) {
+                    char& s = seen[bcam[idx[k]]];
+                    if (s) return fail(CAL_ERR_INVALID_ARGUMENT, "a (view, camera) pair appears in more than one residual block");
+                    s = 1;
+                }
+                for (int k = off[v]; k < off[v + 1]; ++k) seen[bcam[idx[k]]] = 0;
+            }
+        }
         std::vector<int32_t> vfree(S.n_views), cq(S.n_cams), ct(S.n_cams), ci(S.n_cams);
         for (int v = 0; v < S.n_views; ++v) vfree[v] = h.view_free_host[v];
         for (int c = 0; c < S.n_cams; ++c) {
@@ -492,14 +503,15 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         CUDA_TRY(upload(V.cam_col_q, cq, us)); CUDA_TRY(upload(V.cam_col_t, ct, us)); CUDA_TRY(upload(V.cam_col_i, ci, us));
         CUDA_TRY(h.alloc(&V.Hpp, (size_t)nv * 36)); CUDA_TRY(h.alloc(&V.gp, (size_t)nv * 6)); CUDA_TRY(h.alloc(&V.sp, (size_t)nv * 6));
         CUDA_TRY(h.alloc(&V.dp, (size_t)nv * 6)); CUDA_TRY(h.alloc(&V.Lp, (size_t)nv * 36)); CUDA_TRY(h.alloc(&V.view_f, (size_t)nv * 6));
-        CUDA_TRY(h.alloc(&V.blk_F, (size_t)6 * (6 + S.PI) * nblk)); CUDA_TRY(h.alloc(&V.delta_p, (size_t)nv * 6));
+        V.ns = ns; V.ncp = (ns + 1 + kSyrkTile - 1) / kSyrkTile * kSyrkTile;
+        CUDA_TRY(h.alloc(&V.Fd, (size_t)nv * 6 * V.ncp)); CUDA_TRY(h.alloc(&V.delta_p, (size_t)nv * 6));
         CUDA_TRY(h.alloc(&V.s_shared, ns)); CUDA_TRY(h.alloc(&V.y_shared, ns)); CUDA_TRY(h.alloc(&V.C, (size_t)ns * ns)); CUDA_TRY(h.alloc(&V.c, ns));
         CUDA_TRY(h.alloc(&V.partialC, (size_t)h.n_syrk_cta * (ns + 1) * (ns + 1))); CUDA_TRY(h.alloc(&V.red, (size_t)nv * 4));
         CUDA_TRY(h.alloc(&V.red_out, 4)); CUDA_TRY(h.alloc(&V.fail, 1));
         CUDA_TRY(h.alloc(&V.red_part, (size_t)kReduceViewsCtas * 4)); CUDA_TRY(h.alloc(&V.red_ticket, 1));
         CUDA_TRY(cudaMemsetAsync(V.red_ticket, 0, sizeof(unsigned), us));
         CUDA_TRY(cudaMemsetAsync(V.red, 0, sizeof(double) * nv * 4, us)); CUDA_TRY(cudaMemsetAsync(V.fail, 0, sizeof(int32_t), us));
-        CUDA_TRY(cudaMemsetAsync(V.blk_F, 0, sizeof(double) * 6 * (6 + S.PI) * nblk, us));
+        CUDA_TRY(cudaMemsetAsync(V.Fd, 0, sizeof(double) * nv * 6 * V.ncp, us));
         CUDA_TRY(cudaMemsetAsync(V.delta_p, 0, sizeof(double) * nv * 6, us));
         CUDA_TRY(cudaMemsetAsync(V.sp, 0, sizeof(double) * nv * 6, us));
     }

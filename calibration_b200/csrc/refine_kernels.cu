@@ -141,7 +141,7 @@ void launch_view_scale(const ProblemShape& S, const ViewBuffers& V, int compute_
 }
 void launch_backsub(const ProblemShape& S, const DevLayout& L, const ViewBuffers& V, int ns, cudaStream_t st) {
     if (S.n_views == 0) return;
-    k_backsub<<<(S.n_views + 63) / 64, 64, 0, st>>>(S, L, V, ns);
+    k_backsub<<<(unsigned)(((int64_t)S.n_views * 32 + 255) / 256), 256, 0, st>>>(S, L, V, ns);   // one warp per view
 }
 void launch_view_plus(const ProblemShape& S, const EvalBuffers& B, const ViewBuffers& V, double t, cudaStream_t st) {
     if (S.n_views == 0) return;
@@ -162,12 +162,15 @@ int schur_num_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < 444 * 16 
 void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V, int ns,
                   double radius, cudaStream_t st) {
     if (S.n_views == 0) return;
-    k_schur_factor<<<(unsigned)((L.n_blk + 127) / 128), 128, 0, st>>>(S, L, B, V, 1.0 / radius);
+    k_schur_factor<<<(unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, 0, st>>>(S, L, B, V, 1.0 / radius);   // one warp per view
     const int n_cta = schur_num_ctas(S.n_views);
     const int per = (S.n_views + n_cta - 1) / n_cta;
     const int nt = (ns + 1 + kSyrkTile - 1) / kSyrkTile;
     const int threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;  // one thread per 8x8 tile of the upper triangle
-    k_schur_syrk<<<n_cta, threads, 0, st>>>(S, L, V, ns, per);
+    const int smem = 2 * kSyrkViews * 6 * V.ncp * (int)sizeof(double) + 16;   // two stages of dense rows + two mbarriers
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSyrkViews * 6 * kSyrkMaxN * (int)sizeof(double) + 16);
+    k_schur_syrk<<<n_cta, threads, smem, st>>>(S, L, V, ns, per);
     const int na = ns + 1;
     k_schur_reduce<<<(na * na + 127) / 128, 128, 0, st>>>(V, n_cta, ns);
 }

@@ -158,7 +158,8 @@ struct ViewBuffers {
     double* dp = nullptr;       // clamped LM diagonal [n_views][6]
     double* Lp = nullptr;       // cholesky factors [n_views][36]
     double* view_f = nullptr;   // L^-1 (sp o gp) [n_views][6]
-    double* blk_F = nullptr;    // L^-1 E_s, [6 * (6 + PI)][n_blk]
+    double* Fd = nullptr;       // dense rows [F_v | f_v] = L_v^-1 [E_v | g_v], [n_views][6][ncp]; zeros where a camera does not see the view
+    int ncp = 0, ns = 0;        // row pitch of Fd (ns + 1 rounded up to the SYRK tile width) and the shared tangent width
     double* delta_p = nullptr;  // tangent step [n_views][6]
     double* s_shared = nullptr; // [ns] jacobi scale of the shared columns
     double* y_shared = nullptr; // [ns] reduced solution

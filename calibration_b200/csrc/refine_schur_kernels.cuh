@@ -49,34 +49,42 @@ __global__ void k_view_scale(ProblemShape S, ViewBuffers V, int compute_scale) {
 
 // L_v = chol(sp Hpp sp + dp / radius), f_v = L_v^-1 (sp o gp), and for every residual block of the view
 // F_b = L_v^-1 (diag(sp) E_b diag(s_shared)), so that E^T A^-1 E = F^T F and E^T A^-1 g = F^T f.
-// One thread per residual BLOCK: the 6x6 factorisation (about a hundred flops) is repeated by the blocks of a view —
-// a view seen by 8 cameras has 8 threads instead of one thread walking 8 blocks x 15 columns in sequence, and the
-// loads of E_b / stores of F_b ([entry][n_blk]) are coalesced over consecutive blocks.  The first block of a view also
-// publishes L_v and f_v; a view without blocks publishes nothing (it has no rows in the Schur complement).
-__global__ void k_schur_factor(ProblemShape S, DevLayout L, EvalBuffers B, ViewBuffers V, double inv_radius) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= L.n_blk) return;
-    const int v = L.blk_view[b];
-    if (v < 0 || !V.view_free[v]) return;
+// F goes to the DENSE per-view rows
+// Fd[view][6][ncp] (column = shared tangent column, column ns = f_v, zeros where a camera does not see the view — the
+// buffer is cleared once at create and the sparsity never changes): 6 x ncp contiguous doubles per view, which is what
+// the SYRK stages with one bulk copy and what the back-substitution reads as plain dot products.  Lane 0 also publishes
+// L_v and f_v; a view without blocks publishes nothing (it has no rows in the Schur complement).
+// One WARP per view, one lane per (residual block of the view, coupling column): every lane repeats the 6x6 factorisation
+// (about a hundred flops from broadcast loads), then the lanes walk the view's columns 32 at a time and store F into the
+// dense rows with consecutive lanes on consecutive columns — full-line writes; the reads of E_b ([entry][n_blk]) are 8-byte
+// gathers whose sectors are shared by the warps of the neighbouring views.
+constexpr int kFactorThreads = 256;
+__global__ void __launch_bounds__(kFactorThreads) k_schur_factor(ProblemShape S, DevLayout L, EvalBuffers B, ViewBuffers V, double inv_radius) {
+    const int v = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (v >= S.n_views || !V.view_free[v]) return;
+    const int k0 = V.view_blk_off[v], nb = V.view_blk_off[v + 1] - k0;
+    if (nb == 0) return;
     double A[36], sp[6];
     for (int i = 0; i < 6; ++i) sp[i] = V.sp[(int64_t)v * 6 + i];
     for (int i = 0; i < 6; ++i)
         for (int j = 0; j < 6; ++j) A[6 * i + j] = V.Hpp[(int64_t)v * 36 + 6 * i + j] * sp[i] * sp[j];
     for (int i = 0; i < 6; ++i) A[7 * i] += V.dp[(int64_t)v * 6 + i] * inv_radius;
-    const bool first = V.view_blk_idx[V.view_blk_off[v]] == b;
-    if (!chol6(A)) { if (first) atomicExch(V.fail, 1); return; }
-    if (first) {
+    if (!chol6(A)) { if (lane == 0) atomicExch(V.fail, 1); return; }   // (the same on every lane)
+    if (lane == 0) {
         for (int i = 0; i < 36; ++i) V.Lp[(int64_t)v * 36 + i] = A[i];
         double f[6];
         for (int i = 0; i < 6; ++i) f[i] = V.gp[(int64_t)v * 6 + i] * sp[i];
         for (int i = 0; i < 6; ++i) { double s = f[i]; for (int k = 0; k < i; ++k) s -= A[6 * i + k] * f[k]; f[i] = s / A[7 * i]; }
-        for (int i = 0; i < 6; ++i) V.view_f[(int64_t)v * 6 + i] = f[i];
+        for (int i = 0; i < 6; ++i) { V.view_f[(int64_t)v * 6 + i] = f[i]; V.Fd[((int64_t)v * 6 + i) * V.ncp + V.ns] = f[i]; }
     }
     const int ncb = 6 + S.PI;
-    const int cam = L.blk_cam[b];
-    for (int j = 0; j < ncb; ++j) {
-        const int col = shared_col(V, cam, j);
-        const double sc = col < 0 ? 0.0 : V.s_shared[col];
+    double* const Fv = V.Fd + (int64_t)v * 6 * V.ncp;
+    for (int t = lane; t < nb * ncb; t += 32) {
+        const int k = t / ncb, j = t - k * ncb;
+        const int64_t b = V.view_blk_idx[k0 + k];
+        const int col = shared_col(V, L.blk_cam[b], j);
+        if (col < 0) continue;
+        const double sc = V.s_shared[col];
         double e[6];
         for (int i = 0; i < 6; ++i) {
             const double ev = j < 6 ? B.blk_Evc[(int64_t)(6 * i + j) * L.n_blk + b]
@@ -84,7 +92,7 @@ __global__ void k_schur_factor(ProblemShape S, DevLayout L, EvalBuffers B, ViewB
             e[i] = ev * sp[i] * sc;
         }
         for (int i = 0; i < 6; ++i) { double s = e[i]; for (int kk = 0; kk < i; ++kk) s -= A[6 * i + kk] * e[kk]; e[i] = s / A[7 * i]; }
-        for (int i = 0; i < 6; ++i) V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b] = e[i];
+        for (int i = 0; i < 6; ++i) Fv[i * V.ncp + col] = e[i];
     }
 }
 
@@ -153,16 +161,25 @@ __global__ void __launch_bounds__(256) k_reduced_solve(const double* __restrict_
 
 // C_aug = sum_v F_v^T F_v as a tiled SYRK with a long inner dimension (6 rows per view).  The
 // (ns+1)^2 upper triangle is covered by 8x8 register tiles, one per thread; the CTA has exactly as many
-// warps as the tile count needs (120 tiles at ns = 114 -> 4 warps, three CTAs per SM), owns a chunk of
-// the views and stages the dense 6 x (ns+1) rows [F_v | f_v] of kSyrkViews views per barrier pair in
-// shared memory.  Per-CTA partial results are summed in a fixed order (no floating-point atomics).
+// warps as the tile count needs (120 tiles at ns = 114 -> 4 warps, three CTAs per SM) and owns a chunk of
+// the views.  The rows [F_v | f_v] of kSyrkViews consecutive views are ONE contiguous block of Fd, staged by
+// a TMA bulk copy (cp.async.bulk + mbarrier) into a two-stage shared-memory ring: the copy of the next views
+// runs under the FMAs of the current ones.  Per-CTA partial results are summed in a fixed order (no
+// floating-point atomics).  Dynamic shared memory: 2 * kSyrkViews * 6 * ncp doubles + 2 mbarriers.
 constexpr int kSyrkViews = 4;
 __global__ void __launch_bounds__(kSyrkThreads) k_schur_syrk(ProblemShape S, DevLayout L, ViewBuffers V, int ns,
                                                              int views_per_cta) {
-    __shared__ double frow[kSyrkViews * 6][kSyrkMaxN];
+#if defined(__CUDACC__)
+    extern __shared__ __align__(128) unsigned char syrk_smem[];
+#else   // host build of this source (tests/host_emul): one CTA runs at a time
+    static __attribute__((aligned(128))) unsigned char syrk_smem[2 * kSyrkViews * 6 * kSyrkMaxN * 8 + 16];
+#endif
+    const int ncp = V.ncp;
+    const int stage_doubles = kSyrkViews * 6 * ncp;
+    double* const ring = reinterpret_cast<double*>(syrk_smem);
+    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(syrk_smem + (size_t)2 * stage_doubles * 8);
     const int na = ns + 1;
     const int nt = (na + kSyrkTile - 1) / kSyrkTile;
-    const int ncol = nt * kSyrkTile;  // columns actually read by the tiles
     int ti = -1, tj = -1;
     {
         int t = threadIdx.x, row = 0;
@@ -175,36 +192,66 @@ __global__ void __launch_bounds__(kSyrkThreads) k_schur_syrk(ProblemShape S, Dev
 #pragma unroll
         for (int j = 0; j < kSyrkTile; ++j) acc[i][j] = 0.0;
     const int v0 = blockIdx.x * views_per_cta, v1 = min(S.n_views, v0 + views_per_cta);
-    const int ncb = 6 + S.PI;
-    for (int vb = v0; vb < v1; vb += kSyrkViews) {
-        const int nvb = min(kSyrkViews, v1 - vb);
-        for (int i = threadIdx.x; i < nvb * 6 * ncol; i += blockDim.x) frow[i / ncol][i % ncol] = 0.0;
-        __syncthreads();
-        for (int q = 0; q < nvb; ++q) {
-            const int v = vb + q;
-            if (!V.view_free[v]) continue;  // uniform across the CTA; its rows stay zero
-            const int nb = V.view_blk_off[v + 1] - V.view_blk_off[v];
-            for (int idx = threadIdx.x; idx < nb * ncb * 6; idx += blockDim.x) {
-                const int kb = idx / (ncb * 6), rem = idx % (ncb * 6), i = rem / ncb, j = rem % ncb;
-                const int64_t b = V.view_blk_idx[V.view_blk_off[v] + kb];
-                const int col = shared_col(V, L.blk_cam[b], j);
-                if (col >= 0) frow[q * 6 + i][col] = V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b];
-            }
-            if (threadIdx.x < 6) frow[q * 6 + threadIdx.x][ns] = V.view_f[(int64_t)v * 6 + threadIdx.x];
+    const int n_steps = v1 > v0 ? (v1 - v0 + kSyrkViews - 1) / kSyrkViews : 0;
+    // stage `st` <- the rows of the views of step k (leader thread only)
+    auto issue = [&](int k) {
+        if (k >= n_steps) return;
+        const int vb = v0 + k * kSyrkViews, nvb = min(kSyrkViews, v1 - vb);
+        const double* src = V.Fd + (int64_t)vb * 6 * ncp;
+        double* dst = ring + (k & 1) * stage_doubles;
+        const unsigned bytes = (unsigned)(nvb * 6 * ncp * 8);
+#if defined(__CUDACC__)
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(&bar[k & 1]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"(mb)
+                     : "memory");
+#else
+        for (unsigned i = 0; i < bytes / 8; ++i) dst[i] = src[i];
+#endif
+    };
+#if defined(__CUDACC__)
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+#endif
+    __syncthreads();
+    if (threadIdx.x == 0) { issue(0); issue(1); }
+#if !defined(__CUDACC__)
+    __syncthreads();
+#endif
+    for (int k = 0; k < n_steps; ++k) {
+#if defined(__CUDACC__)
+        {
+            const unsigned mb = (unsigned)__cvta_generic_to_shared(&bar[k & 1]);
+            const unsigned parity = (unsigned)(k >> 1) & 1u;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@!p bra WAIT_%=;\n\t}" ::"r"(mb), "r"(parity) : "memory");
         }
-        __syncthreads();
+#endif
+        const int nvb = min(kSyrkViews, v1 - (v0 + k * kSyrkViews));
+        const double* frow = ring + (k & 1) * stage_doubles;
         if (ti >= 0) {
             for (int r = 0; r < nvb * 6; ++r) {
                 double fa[kSyrkTile], fb[kSyrkTile];
 #pragma unroll
-                for (int i = 0; i < kSyrkTile; ++i) { fa[i] = frow[r][ti * kSyrkTile + i]; fb[i] = frow[r][tj * kSyrkTile + i]; }
+                for (int i = 0; i < kSyrkTile; ++i) { fa[i] = frow[r * ncp + ti * kSyrkTile + i]; fb[i] = frow[r * ncp + tj * kSyrkTile + i]; }
 #pragma unroll
                 for (int i = 0; i < kSyrkTile; ++i)
 #pragma unroll
                     for (int j = 0; j < kSyrkTile; ++j) acc[i][j] = fma(fa[i], fb[j], acc[i][j]);
             }
         }
+        __syncthreads();                               // every thread is done with this stage
+        if (threadIdx.x == 0) issue(k + 2);            // refill it
+#if !defined(__CUDACC__)
         __syncthreads();
+#endif
     }
     if (ti >= 0) {
         double* out = V.partialC + (int64_t)blockIdx.x * na * na;
@@ -227,31 +274,35 @@ __global__ void k_schur_reduce(ViewBuffers V, int n_cta, int ns) {
     else if (r < ns && cc == ns) V.c[r] = s;
 }
 
-// y_p = L^-T (f - sum_b F_b y_s[cols(b)]), step_p = -y_p, delta_p = step_p o sp, and the
-// per-view terms of step'g and step'H step (H undamped, Jacobi-scaled).
-__global__ void k_backsub(ProblemShape S, DevLayout L, ViewBuffers V, int ns) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+// y_p = L^-T (f - F_v y_s), step_p = -y_p, delta_p = step_p o sp, and the per-view terms of step'g and
+// step'H step (H undamped, Jacobi-scaled).  One WARP per view: q = F_v y_s are six dot products over the dense rows of
+// the view (lanes stride over the shared columns: coalesced), summed by a fixed shuffle tree; lane 0 finishes the 6x6 part.
+__global__ void __launch_bounds__(256) k_backsub(ProblemShape S, DevLayout L, ViewBuffers V, int ns) {
+    const int v = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (v >= S.n_views) return;
     double* red = V.red + (int64_t)v * 4;
     if (!V.view_free[v] || V.view_blk_off[v + 1] == V.view_blk_off[v]) {   // fixed, or seen by no camera: no step
-        for (int i = 0; i < 6; ++i) V.delta_p[(int64_t)v * 6 + i] = 0.0;
-        red[0] = red[1] = 0.0;
+        if (lane == 0) {
+            for (int i = 0; i < 6; ++i) V.delta_p[(int64_t)v * 6 + i] = 0.0;
+            red[0] = red[1] = 0.0;
+        }
         return;
     }
-    double Lm[36], q[6], f[6], sp[6];
-    for (int i = 0; i < 36; ++i) Lm[i] = V.Lp[(int64_t)v * 36 + i];
-    for (int i = 0; i < 6; ++i) { f[i] = V.view_f[(int64_t)v * 6 + i]; sp[i] = V.sp[(int64_t)v * 6 + i]; q[i] = 0.0; }
-    const int ncb = 6 + S.PI;
-    for (int k = V.view_blk_off[v]; k < V.view_blk_off[v + 1]; ++k) {
-        const int64_t b = V.view_blk_idx[k];
-        const int cam = L.blk_cam[b];
-        for (int j = 0; j < ncb; ++j) {
-            const int col = shared_col(V, cam, j);
-            if (col < 0) continue;
-            const double ys = V.y_shared[col];
-            for (int i = 0; i < 6; ++i) q[i] += V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b] * ys;
-        }
+    double q[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const double* Fv = V.Fd + (int64_t)v * 6 * V.ncp;
+    for (int c = lane; c < ns; c += 32) {
+        const double ys = V.y_shared[c];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) q[i] = fma(Fv[i * V.ncp + c], ys, q[i]);
     }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
+    if (lane != 0) return;
+    double Lm[36], f[6], sp[6];
+    for (int i = 0; i < 36; ++i) Lm[i] = V.Lp[(int64_t)v * 36 + i];
+    for (int i = 0; i < 6; ++i) { f[i] = V.view_f[(int64_t)v * 6 + i]; sp[i] = V.sp[(int64_t)v * 6 + i]; }
     double y[6];
     for (int i = 0; i < 6; ++i) y[i] = f[i] - q[i];
     for (int i = 5; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < 6; ++k) s -= Lm[6 * k + i] * y[k]; y[i] = s / Lm[7 * i]; }
@@ -354,13 +405,9 @@ __global__ void __launch_bounds__(64) k_cov_view_prep(ProblemShape S, DevLayout 
     for (int i = threadIdx.x; i < 6 * kSyrkMaxN; i += 64) (&Y[0][0])[i] = 0.0;
     if (threadIdx.x < 36) Lm[threadIdx.x] = V.Lp[(int64_t)v * 36 + threadIdx.x];
     __syncthreads();
-    const int ncb = 6 + S.PI;
-    const int nb = V.view_blk_off[v + 1] - V.view_blk_off[v];
-    for (int idx = threadIdx.x; idx < nb * ncb * 6; idx += 64) {
-        const int kb = idx / (ncb * 6), rem = idx % (ncb * 6), i = rem / ncb, j = rem % ncb;
-        const int64_t b = V.view_blk_idx[V.view_blk_off[v] + kb];
-        const int col = shared_col(V, L.blk_cam[b], j);
-        if (col >= 0) Y[i][col] = V.blk_F[(int64_t)(ncb * i + j) * L.n_blk + b];  // each (view, camera) pair has one block: no collisions
+    for (int idx = threadIdx.x; idx < 6 * ns; idx += 64) {   // Y = L_v^-1 E_v: the dense rows of the view (k_schur_factor)
+        const int i = idx / ns, c = idx % ns;
+        Y[i][c] = V.Fd[((int64_t)v * 6 + i) * V.ncp + c];
     }
     __syncthreads();
     // Z = L^-T Y, column by column

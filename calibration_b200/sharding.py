@@ -67,6 +67,7 @@ def shard_views(problem, x0, rank, world):
                       optimize_intrinsics=bool(d.optimize_intrinsics), optimize_skew=bool(d.optimize_skew),
                       optimize_extrinsics=bool(d.optimize_extrinsics), huber_delta=d.huber_delta)
     sub.desc.view_base = v0
+    sub.desc.n_views_total = nv   # the reference's minimum-view check applies to the whole problem, not to a shard
     x0 = np.asarray(x0)
     n_shared = P if d.kind == abi.KIND_INTRINSICS else (P + 7) * nc
     q = x0[n_shared:n_shared + 4 * nv].reshape(nv, 4)[v0:v1]

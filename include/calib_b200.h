@@ -86,8 +86,13 @@ typedef struct cal_problem_desc {
     const double* board_x;
     const double* board_y;
     int32_t board_n;
-    int32_t reserved;
+    int32_t n_views_total;        /* multi-GPU shards of the intrinsics kind: views of the WHOLE problem (the reference's
+                                     "at least 4 views" check, intrinsics.cpp:92-96, applies to it); 0: n_views */
 } cal_problem_desc;
+/* Limits of the per-view kinds (intrinsics, extrinsics): the shared block — intrinsics of all cameras and, for the extrinsics
+ * kind, the 6-dof poses of cameras 1 .. n_cams - 1 — may have at most 175 tangent columns (the Schur-complement kernel holds
+ * an (n_s + 1)^2 tile set per CTA): 12 pinhole or 10 Scheimpflug cameras with every block free; cal_refine_create returns
+ * CAL_ERR_INVALID_ARGUMENT beyond that.  A (view, camera) pair may appear in at most one residual block. */
 
 /* calib::OptimOptions (optim/optimize.h:24-33) */
 typedef struct cal_optim_options {

@@ -58,13 +58,13 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
     { std::vector<int32_t> cur(off.begin(), off.end() - 1); for (int64_t b = 0; b < n_blk; ++b) idx[cur[blk_view[b]]++] = (int32_t)b; }
     const int n_cta = schur_ctas(n_views), na = ns + 1, ncb = 6 + PI;
     std::vector<double> Hpp((size_t)n_views * 36), gp((size_t)n_views * 6), sp((size_t)n_views * 6, 0.0), dp((size_t)n_views * 6), Lp((size_t)n_views * 36),
-        view_f((size_t)n_views * 6), blk_F((size_t)6 * ncb * n_blk, 0.0), dlt((size_t)n_views * 6, 0.0), ss(s_shared, s_shared + ns), ys(std::max(ns, 1)),
+        view_f((size_t)n_views * 6), Fd((size_t)n_views * 6 * ((ns + 1 + kSyrkTile - 1) / kSyrkTile * kSyrkTile), 0.0), dlt((size_t)n_views * 6, 0.0), ss(s_shared, s_shared + ns), ys(std::max(ns, 1)),
         Cm((size_t)ns * ns), cv(std::max(ns, 1)), partialC((size_t)n_cta * na * na), red((size_t)n_views * 4, 0.0), ro(4, 0.0);
     int32_t failed = 0;
     ViewBuffers V;
     V.view_blk_off = off.data(); V.view_blk_idx = idx.data(); V.view_free = vfree.data();
     V.cam_col_q = cq.data(); V.cam_col_t = ct.data(); V.cam_col_i = ci.data();
-    V.Hpp = Hpp.data(); V.gp = gp.data(); V.sp = sp.data(); V.dp = dp.data(); V.Lp = Lp.data(); V.view_f = view_f.data(); V.blk_F = blk_F.data();
+    V.Hpp = Hpp.data(); V.gp = gp.data(); V.sp = sp.data(); V.dp = dp.data(); V.Lp = Lp.data(); V.view_f = view_f.data(); V.Fd = Fd.data(); V.ns = ns; V.ncp = (ns + 1 + kSyrkTile - 1) / kSyrkTile * kSyrkTile;
     V.delta_p = dlt.data(); V.s_shared = ss.data(); V.y_shared = ys.data(); V.C = Cm.data(); V.c = cv.data(); V.partialC = partialC.data();
     std::vector<double> rpart((size_t)kReduceViewsCtas * 4, 0.0); unsigned rticket = 0u;
     V.red = red.data(); V.red_out = ro.data(); V.fail = &failed; V.red_part = rpart.data(); V.red_ticket = &rticket;
@@ -73,7 +73,7 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
     simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 1); });
     simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 0); });
     // launch_schur
-    simt::launch((unsigned)((L.n_blk + 127) / 128), 128, [&] { k_schur_factor(S, L, B, V, 1.0 / radius); });
+    simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V, 1.0 / radius); });
     const int per = (n_views + n_cta - 1) / n_cta, nt = (na + kSyrkTile - 1) / kSyrkTile, threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
     simt::launch((unsigned)n_cta, (unsigned)threads, [&] { k_schur_syrk(S, L, V, ns, per); });
     simt::launch((unsigned)((na * na + 127) / 128), 128, [&] { k_schur_reduce(V, n_cta, ns); });
@@ -95,7 +95,7 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
         if (!(dev <= 1e-9 * (ref + 1e-300))) return 5;
     }
     std::memcpy(y_shared, ys.data(), sizeof(double) * ns);
-    simt::launch((unsigned)((n_views + 63) / 64), 64, [&] { k_backsub(S, L, V, ns); });
+    simt::launch((unsigned)(((int64_t)n_views * 32 + 255) / 256), 256, [&] { k_backsub(S, L, V, ns); });
     simt::launch(n_views >= 2048 ? 2u : 1u, 256, [&] { k_reduce_views(V, n_views); });
     std::memcpy(delta_p, dlt.data(), sizeof(double) * 6 * n_views);
     std::memcpy(red_out4, ro.data(), sizeof(double) * 4);
@@ -129,19 +129,19 @@ extern "C" int simt_k2_cov(int n_views, int n_cams, int PI, int64_t n_blk, const
     { std::vector<int32_t> cur(off.begin(), off.end() - 1); for (int64_t b = 0; b < n_blk; ++b) idx[cur[blk_view[b]]++] = (int32_t)b; }
     const int n_cta = schur_ctas(n_views), na = ns + 1, ncb = 6 + PI;
     std::vector<double> Hpp((size_t)n_views * 36), gp((size_t)n_views * 6), sp((size_t)n_views * 6, 0.0), dp((size_t)n_views * 6), Lp((size_t)n_views * 36),
-        view_f((size_t)n_views * 6), blk_F((size_t)6 * ncb * n_blk, 0.0), ss(s_shared, s_shared + ns), Cm((size_t)ns * ns), cv(std::max(ns, 1)),
+        view_f((size_t)n_views * 6), Fd((size_t)n_views * 6 * ((ns + 1 + kSyrkTile - 1) / kSyrkTile * kSyrkTile), 0.0), ss(s_shared, s_shared + ns), Cm((size_t)ns * ns), cv(std::max(ns, 1)),
         partialC((size_t)n_cta * na * na), x(na_amb, 0.0);
     std::memcpy(x.data(), view_quats, sizeof(double) * 4 * n_views);
     int32_t failed = 0;
     ViewBuffers V;
     V.view_blk_off = off.data(); V.view_blk_idx = idx.data(); V.view_free = vfree.data();
     V.cam_col_q = cq.data(); V.cam_col_t = ct.data(); V.cam_col_i = ci.data();
-    V.Hpp = Hpp.data(); V.gp = gp.data(); V.sp = sp.data(); V.dp = dp.data(); V.Lp = Lp.data(); V.view_f = view_f.data(); V.blk_F = blk_F.data();
+    V.Hpp = Hpp.data(); V.gp = gp.data(); V.sp = sp.data(); V.dp = dp.data(); V.Lp = Lp.data(); V.view_f = view_f.data(); V.Fd = Fd.data(); V.ns = ns; V.ncp = (ns + 1 + kSyrkTile - 1) / kSyrkTile * kSyrkTile;
     V.s_shared = ss.data(); V.C = Cm.data(); V.c = cv.data(); V.partialC = partialC.data(); V.fail = &failed;
     simt::launch((unsigned)((n_views + 127) / 128), 128, [&] { k_view_gather(S, L, B, V); });
     simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 1); });
     // launch_schur(radius = infinity): undamped factors L_v and F_b = L_v^-1 E_b stay in V
-    simt::launch((unsigned)((L.n_blk + 127) / 128), 128, [&] { k_schur_factor(S, L, B, V, 0.0); });
+    simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V, 0.0); });
     const int per = (n_views + n_cta - 1) / n_cta, nt = (na + kSyrkTile - 1) / kSyrkTile, threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
     simt::launch((unsigned)n_cta, (unsigned)threads, [&] { k_schur_syrk(S, L, V, ns, per); });
     simt::launch((unsigned)((na * na + 127) / 128), 128, [&] { k_schur_reduce(V, n_cta, ns); });

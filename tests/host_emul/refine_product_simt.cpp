@@ -136,7 +136,7 @@ void launch_view_scale(const ProblemShape& S, const ViewBuffers& V, int compute_
 }
 void launch_backsub(const ProblemShape& S, const DevLayout& L, const ViewBuffers& V, int ns, cudaStream_t) {
     if (S.n_views == 0) return;
-    simt::launch((unsigned)((S.n_views + 63) / 64), 64, [&] { k_backsub(S, L, V, ns); });
+    simt::launch((unsigned)(((int64_t)S.n_views * 32 + 255) / 256), 256, [&] { k_backsub(S, L, V, ns); });
 }
 void launch_view_plus(const ProblemShape& S, const EvalBuffers& B, const ViewBuffers& V, double t, cudaStream_t) {
     if (S.n_views == 0) return;
@@ -150,7 +150,7 @@ void launch_reduce_views(const ViewBuffers& V, int n_views, cudaStream_t) { simt
 int schur_num_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < 444 * 16 ? (n_views + 15) / 16 : 444); }
 void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V, int ns, double radius, cudaStream_t) {
     if (S.n_views == 0) return;
-    simt::launch((unsigned)((L.n_blk + 127) / 128), 128, [&] { k_schur_factor(S, L, B, V, 1.0 / radius); });
+    simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V, 1.0 / radius); });
     const int n_cta = schur_num_ctas(S.n_views);
     const int per = (S.n_views + n_cta - 1) / n_cta;
     const int nt = (ns + 1 + kSyrkTile - 1) / kSyrkTile;
