@@ -218,6 +218,7 @@ def _run_b200(args, rank, world, local_rank):
         l0 = h.launch_count()
         ms_total, ms_k1, cost = h.bench_pass(x0, reps=args.steps, jacobian=True)
         launches_timed = h.launch_count() - l0
+        ms_setup0, ms_between = h.bench_breakdown()
         barrier()
         ms_c, ms_ck, _ = h.bench_pass(x0, reps=args.steps, jacobian=False)
         t = torch.tensor([ms_total, ms_k1], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -315,6 +316,8 @@ def _run_b200(args, rank, world, local_rank):
                                                                            f"the capture's own launch took {ncu_rec.get('capture_ms')} ms)") if ncu_rec else None,
                      "peak_source": pk_src, "kernel": "k1_kernel", "kernel_ms_per_launch": k1_ms_launch,
                      "kernel_share_of_step": ms_k1 / ms_total,
+                     "rest_of_step_ms": {"first_setup_kernel": ms_setup0, "reduction_and_allreduce_plus_next_setup": ms_between,
+                                         "note": "CUDA events on rank 0's stream; on several GPUs the reduction kernel waits for the slowest rank"},
                      "algorithmic_bytes_per_launch": obs_bytes_local,
                      "binding_roof": "fp64",
                      "fp64": {"achieved": k1_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": k1_tflops / fp64_peak,

@@ -157,6 +157,13 @@ class RefineHandle:
                                            C.cast(C.byref(cost), abi.c_double_p)))
         return ms.value, k1.value, cost.value
 
+    def bench_breakdown(self):
+        """(ms of the first set-up kernel, ms of reduction (+ all-reduce) + next set-up per pass) of the last bench_pass"""
+        a = C.c_float(); b = C.c_float()
+        lib().cal_refine_bench_breakdown.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        _check(lib().cal_refine_bench_breakdown(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def launch_count(self):
         return int(lib().cal_refine_launch_count(self._h))
 

@@ -144,6 +144,7 @@ struct cal_refine_handle : calk::HostModel {
     double* pin_sums() const { return pin + 16 + std::max(ns, 1); }
     // counters
     int64_t launches = 0;
+    float bench_setup_ms = 0, bench_between_ms = 0;   // breakdown of the last cal_refine_bench_pass
 
     // all device buffers of a handle are carved from one arena (one cudaMalloc / cudaFree)
     unsigned char* arena = nullptr; size_t arena_size = 0, arena_used = 0;
@@ -669,7 +670,6 @@ extern "C" cal_status cal_refine_view_errors(cal_refine_handle* h, const double*
     CUDA_TRY(cudaMemcpyAsync(h->B.x, x, sizeof(double) * h->n_amb, cudaMemcpyHostToDevice, h->st));
     if (cal_status s = device_pass(*h, h->B.x, false, x)) return s;
     std::vector<double> ssr(h->L.n_blk);
-    std::vector<int32_t> len(h->L.n_blk + 1);
     CUDA_TRY(cudaMemcpy(ssr.data(), h->B.blk_ssr, ssr.size() * sizeof(double), cudaMemcpyDeviceToHost));
     double sum_sq = 0.0, meas = 0.0;
     for (int64_t b = 0; b < h->L.n_blk; ++b) {
@@ -689,6 +689,8 @@ extern "C" cal_status cal_refine_bench_pass(cal_refine_handle* h, const double* 
     if (!h || !x || reps <= 0) return fail(CAL_ERR_INVALID_ARGUMENT, "bad argument");
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaMemcpyAsync(h->B.x, x, sizeof(double) * h->n_amb, cudaMemcpyHostToDevice, h->st));
+    // events: [0] start, [1] end, then per repetition: before K1, after K1 (the set-up kernel runs before the first, the
+    // reduction — and the all-reduce it carries on several GPUs — after the second)
     std::vector<cudaEvent_t> ev(2 * (size_t)reps + 2);
     for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaStreamSynchronize(h->st));
@@ -704,8 +706,17 @@ extern "C" cal_status cal_refine_bench_pass(cal_refine_handle* h, const double* 
     CUDA_TRY(cudaEventRecord(ev[1], h->st));
     CUDA_TRY(cudaEventSynchronize(ev[1]));
     CUDA_TRY(cudaGetLastError());
-    float ms = 0, k1 = 0; CUDA_TRY(cudaEventElapsedTime(&ms, ev[0], ev[1]));
-    for (int r = 0; r < reps; ++r) { float t = 0; CUDA_TRY(cudaEventElapsedTime(&t, ev[2 + 2 * r], ev[3 + 2 * r])); k1 += t; }
+    if (h->comm && !h->comm->check_timeout()) return fail(CAL_ERR_COMM, h->comm->error());
+    float ms = 0, k1 = 0, setup = 0, tail = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ev[0], ev[1]));
+    for (int r = 0; r < reps; ++r) {
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, ev[2 + 2 * r], ev[3 + 2 * r])); k1 += t;
+        CUDA_TRY(cudaEventElapsedTime(&t, r == 0 ? ev[0] : ev[1 + 2 * r], ev[2 + 2 * r])); if (r > 0) tail += t; else setup += t;
+    }
+    // (between "after K1" of repetition r - 1 and "before K1" of repetition r lie reduction r - 1 and set-up r: tail holds their
+    // sum over reps - 1 repetitions, setup the first set-up alone)
+    h->bench_setup_ms = setup; h->bench_between_ms = reps > 1 ? tail / (reps - 1) : 0.0f;
     for (auto& e : ev) cudaEventDestroy(e);
     if (ms_total) *ms_total = ms;
     if (ms_k1) *ms_k1 = k1;
@@ -716,6 +727,14 @@ extern "C" cal_status cal_refine_bench_pass(cal_refine_handle* h, const double* 
         double c = 0; for (int k = 0; k < h->S.n_cams; ++k) c += cs[(size_t)k * NV + (jacobian ? h->S.NE : 0)];
         *cost = c;
     }
+    return CAL_OK;
+}
+// of the last cal_refine_bench_pass: device time of the first set-up kernel, and of [reduction (+ all-reduce) of one pass + set-up of
+// the next] averaged over the repetitions — what a pass costs besides K1
+extern "C" cal_status cal_refine_bench_breakdown(const cal_refine_handle* h, float* ms_first_setup, float* ms_reduce_plus_setup) {
+    if (!h) return fail(CAL_ERR_INVALID_ARGUMENT, "null argument");
+    if (ms_first_setup) *ms_first_setup = h->bench_setup_ms;
+    if (ms_reduce_plus_setup) *ms_reduce_plus_setup = h->bench_between_ms;
     return CAL_OK;
 }
 

@@ -148,6 +148,9 @@ cal_status cal_refine_cost(cal_refine_handle* h, const double* x, double* cost, 
  * dominant kernel (K1, or the residual-only kernel when jacobian == 0). */
 cal_status cal_refine_bench_pass(cal_refine_handle* h, const double* x, int reps, int jacobian, float* ms_total,
                                  float* ms_k1, double* cost);
+/* Of the last cal_refine_bench_pass: device time (ms) of the first set-up kernel, and of [reduction (+ all-reduce) of one pass +
+ * set-up of the next] averaged over the repetitions: what a pass costs besides K1. */
+cal_status cal_refine_bench_breakdown(const cal_refine_handle* h, float* ms_first_setup, float* ms_reduce_plus_setup);
 /* kernels launched through this handle so far */
 int64_t cal_refine_launch_count(const cal_refine_handle* h);
 /* layout facts for the roofline arithmetic: segments, 32-segment tiles, bytes of
