@@ -216,9 +216,14 @@ def run_ransac(args, clock_sampler_cls, rank=0, world=1, local_rank=0):
     capi.ransac_homography_batch(*hx, opts, want_mask=True, device=local_rank)
     if dist is not None:
         dist.barrier()
-    t0 = time.perf_counter()
-    capi.ransac_homography_batch(*hx, opts, want_mask=True, device=local_rank)
-    e2e_s = time.perf_counter() - t0
+    e2e_runs = []
+    for _ in range(3):   # three calls; the record keeps all of them, the value is the median
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        capi.ransac_homography_batch(*hx, opts, want_mask=True, device=local_rank)
+        e2e_runs.append(time.perf_counter() - t0)
+    e2e_s = sorted(e2e_runs)[1]
     if dist is not None:
         t = torch.tensor([e2e_s, float(hyp)], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t[:1], op=dist.ReduceOp.MAX); dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
@@ -239,7 +244,7 @@ def run_ransac(args, clock_sampler_cls, rank=0, world=1, local_rank=0):
     out["gpu_launches"] = args.steps
     out["e2e"] = {"value": npb / e2e_s, "unit": "problems/s", "h2d_bytes_per_step": alg, "d2h_bytes_per_step": int(npb * (C.sizeof(abi.RansacResult) + n)),
                   "what": "cal_ransac_homography_batch from pinned host arrays: H2D of the correspondences, the kernel, results and inlier masks back to the host",
-                  "wall_s": e2e_s}
+                  "wall_s": e2e_s, "wall_s_runs_rank0": e2e_runs}
     out["roofline"] = _roofline(alg, ms_step, "k_ransac", 1.0,
                                 "correspondences are read once into shared memory; the kernel is bound by FP64 latency (4-point DLT by Householder QR, "
                                 "refit null vector by inverse iteration, one hypothesis per lane) and by the exact device-side replay of std::sample")

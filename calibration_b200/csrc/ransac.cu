@@ -55,6 +55,8 @@ size_t smem_per_cta(int n) {
 // device memory / events of one call, released on every exit
 struct DevBuf { void* p = nullptr; ~DevBuf() { if (p) cudaFree(p); } template <class T> T* as() const { return static_cast<T*>(p); } };
 struct Ev { cudaEvent_t e = nullptr; ~Ev() { if (e) cudaEventDestroy(e); } };
+// stream-ordered buffer from the device's default memory pool, returned to it in stream order
+struct PoolBuf { void* p = nullptr; cudaStream_t st = nullptr; ~PoolBuf() { if (p) cudaFreeAsync(p, st); } template <class T> T* as() const { return static_cast<T*>(p); } };
 struct Stream { cudaStream_t s = nullptr; ~Stream() { if (s) cudaStreamDestroy(s); } };
 
 // the adaptive-iteration table of calculate_iterations for this (n, options): built once per call, on the device
@@ -125,13 +127,20 @@ extern "C" cal_status cal_ransac_homography_batch(int64_t n_problems, int32_t n,
     size_t smem = 0;
     if (cal_status s = prepare_kernel(n, &smem)) return s;
     const size_t ne = (size_t)n_problems * n;
-    DevBuf dxyuv, dres, dmask, dtable;
-    RCUDA(cudaMalloc(&dxyuv.p, 4 * ne * sizeof(double)));
-    RCUDA(cudaMalloc(&dres.p, (size_t)n_problems * sizeof(cal_ransac_result)));
-    if (inlier_mask) RCUDA(cudaMalloc(&dmask.p, ne));
-    Stream up, run, down;
+    Stream up, run, down;   // (declared before the buffers: the buffers are released in stream order on `run` first)
     RCUDA(cudaStreamCreateWithFlags(&up.s, cudaStreamNonBlocking)); RCUDA(cudaStreamCreateWithFlags(&run.s, cudaStreamNonBlocking));
     RCUDA(cudaStreamCreateWithFlags(&down.s, cudaStreamNonBlocking));
+    {   // the gigabytes of a call come from the device's memory pool and go back to it: repeated calls reuse the same physical memory
+        cudaMemPool_t pool; uint64_t thr = UINT64_MAX;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    PoolBuf dxyuv{nullptr, run.s}, dres{nullptr, run.s}, dmask{nullptr, run.s};
+    DevBuf dtable;
+    RCUDA(cudaMallocAsync(&dxyuv.p, 4 * ne * sizeof(double), run.s));
+    RCUDA(cudaMallocAsync(&dres.p, (size_t)n_problems * sizeof(cal_ransac_result), run.s));
+    if (inlier_mask) RCUDA(cudaMallocAsync(&dmask.p, ne, run.s));
+    Ev ready; RCUDA(cudaEventCreateWithFlags(&ready.e, cudaEventDisableTiming)); RCUDA(cudaEventRecord(ready.e, run.s));
+    RCUDA(cudaStreamWaitEvent(up.s, ready.e, 0));   // the upload stream may touch the buffers once they exist
     if (cal_status s = upload_niter_table(n, *opts, dtable, run.s)) return s;
     double* dx = dxyuv.as<double>(); double *dy = dx + ne, *du = dy + ne, *dv = du + ne;
     // few, large chunks: a problem's iteration count is data dependent, so a launch of a few thousand problems is
@@ -164,6 +173,7 @@ extern "C" cal_status cal_ransac_homography_batch(int64_t n_problems, int32_t n,
         if (inlier_mask) RCUDA(cudaMemcpyAsync(inlier_mask + off, dmask.as<uint8_t>() + off, (size_t)(p1 - p0) * n, cudaMemcpyDeviceToHost, down.s));
     }
     RCUDA(cudaStreamSynchronize(down.s));
+    RCUDA(cudaStreamSynchronize(up.s));
     RCUDA(cudaStreamSynchronize(run.s));
     RCUDA(cudaGetLastError());
     return CAL_OK;
