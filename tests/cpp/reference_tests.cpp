@@ -259,6 +259,47 @@ TEST(ReprojectionRefine, DistortionRecoveryOptional) {  // :156-210
     for (int i = 0; i < 5; ++i) EXPECT_NEAR(dist[i], cam_gt.distortion.coeffs[i], 1e-5);
 }
 
+// Large bundle inputs take the staged, threaded packing (b200::BundleStage): the descriptor it fills must equal the serial one
+// (b200::Soa) array for array, and a view that differs from the board must be noticed.
+TEST(OptimizeBundle, StagedPackingEqualsTheSerialPacking) {
+    const int board = 88, n = 12000;   // 1.056 M observations: above b200::kStageThreshold
+    std::vector<BundleObservation> obs(n);
+    RNG rng(11);
+    auto d = [&](RNG& r) { return r.uni(-1.0, 1.0); };
+    for (int b = 0; b < n; ++b) {
+        obs[b].camera_index = static_cast<size_t>(b % 3);
+        obs[b].b_se3_g = make_pose(Eigen::Vector3d(d(rng), d(rng), d(rng)), Eigen::Vector3d(d(rng), d(rng), 1.0), d(rng));
+        obs[b].view.resize(board);
+        for (int i = 0; i < board; ++i) obs[b].view[i] = {Vec2((i % 11) * 0.02, (i / 11) * 0.02), Vec2(d(rng) * 600.0, d(rng) * 300.0)};
+    }
+    ASSERT_TRUE(obs.size() * board >= b200::kStageThreshold);
+    b200::BundleStage st;
+    ASSERT_TRUE(st.pack(obs));
+    b200::Soa s;
+    for (const auto& o : obs) {
+        s.add(o.view, static_cast<int>(o.camera_index), -1);
+        const Eigen::Matrix3d R = o.b_se3_g.linear(); const Eigen::Vector3d t = o.b_se3_g.translation();
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) s.bTg.push_back(R(i, j));
+        for (int i = 0; i < 3; ++i) s.bTg.push_back(t(i));
+    }
+    cal_problem_desc a{}, c{};
+    st.fill(a); s.fill(c);
+    EXPECT_EQ(a.n_blocks, c.n_blocks); EXPECT_EQ(a.n_obs, c.n_obs);
+    if (std::getenv("CALIB_B200_PER_OBSERVATION") == nullptr) {
+        EXPECT_EQ(a.board_n, c.board_n);
+        EXPECT_TRUE(std::equal(a.board_x, a.board_x + board, c.board_x) && std::equal(a.board_y, a.board_y + board, c.board_y));
+    }
+    EXPECT_TRUE(std::equal(a.img_u, a.img_u + a.n_obs, c.img_u) && std::equal(a.img_v, a.img_v + a.n_obs, c.img_v));
+    EXPECT_TRUE(std::equal(a.block_offset, a.block_offset + n + 1, c.block_offset) && std::equal(a.block_cam, a.block_cam + n, c.block_cam));
+    EXPECT_TRUE(std::equal(a.block_b_se3_g, a.block_b_se3_g + 12 * static_cast<size_t>(n), c.block_b_se3_g));
+    obs[7777].view[40].object_xy.x() += 1e-3;   // one corner off the board: the staged form does not apply
+    b200::BundleStage st2;
+    EXPECT_FALSE(st2.pack(obs));
+    obs[7777].view.resize(60);                   // a ragged view neither
+    b200::BundleStage st3;
+    EXPECT_FALSE(st3.pack(obs));
+}
+
 TEST(OptimizeBundle, InputValidation) {  // :212-227
     std::vector<BundleObservation> observations(2);
     Camera<BrownConradyd> cam(CameraMatrix{100.0, 100.0, 64.0, 48.0}, Eigen::VectorXd::Zero(5));

@@ -34,3 +34,15 @@ def test_cpp_example_of_the_adapter_runs():
     exe, env = B.build_example(real=True)
     out = B.run(exe, env, timeout=300)
     assert out.returncode == 0 and "CONVERGENCE" in out.stdout, out.stdout + out.stderr
+
+
+def test_optimize_bundle_from_the_reference_input_type_at_scale():
+    """examples/cpp_bundle_e2e.cpp: calib::optimize_bundle(std::vector<BundleObservation>) with 8 cameras x 3 000 poses x 88 corners
+    (2.1 M observations: the staged, threaded packing into page-locked memory), twice; the program checks convergence and fx itself."""
+    import json
+    exe, env = B.build_bundle_e2e()
+    out = B.run(exe, env, "3000", "2", timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-1000:]
+    rec = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert rec["observations"] == 8 * 3000 * 88 and all(r.get("converged") and r["covariance_rows"] == 143 for r in rec["runs"])
+    assert rec["runs"][0]["final_cost"] == rec["runs"][1]["final_cost"]   # run-to-run identical
