@@ -503,7 +503,7 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         CUDA_TRY(upload(V.view_blk_off, off, us)); CUDA_TRY(upload(V.view_blk_idx, idx, us)); CUDA_TRY(upload(V.view_free, vfree, us));
         CUDA_TRY(upload(V.cam_col_q, cq, us)); CUDA_TRY(upload(V.cam_col_t, ct, us)); CUDA_TRY(upload(V.cam_col_i, ci, us));
         CUDA_TRY(h.alloc(&V.Hpp, (size_t)nv * 36)); CUDA_TRY(h.alloc(&V.gp, (size_t)nv * 6)); CUDA_TRY(h.alloc(&V.sp, (size_t)nv * 6));
-        CUDA_TRY(h.alloc(&V.dp, (size_t)nv * 6)); CUDA_TRY(h.alloc(&V.Lp, (size_t)nv * 36)); CUDA_TRY(h.alloc(&V.view_f, (size_t)nv * 6));
+        CUDA_TRY(h.alloc(&V.dp, (size_t)nv * 6)); CUDA_TRY(h.alloc(&V.Lp, (size_t)nv * 36)); CUDA_TRY(h.alloc(&V.Linv, (size_t)nv * 6)); CUDA_TRY(h.alloc(&V.view_f, (size_t)nv * 6));
         V.ns = ns; V.ncp = (ns + 1 + kSyrkTile - 1) / kSyrkTile * kSyrkTile;
         CUDA_TRY(h.alloc(&V.Fd, (size_t)nv * 6 * V.ncp)); CUDA_TRY(h.alloc(&V.delta_p, (size_t)nv * 6));
         CUDA_TRY(h.alloc(&V.s_shared, ns)); CUDA_TRY(h.alloc(&V.y_shared, ns)); CUDA_TRY(h.alloc(&V.C, (size_t)ns * ns)); CUDA_TRY(h.alloc(&V.c, ns));
@@ -897,7 +897,7 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
         bool solved_on_device = false;   // per-view kinds: y of the reduced system and the per-view scalars are already here
         if (views) {
             CUDA_TRY(cudaMemsetAsync(V.fail, 0, sizeof(int32_t), h.st));
-            launch_schur(S, h.L, B, V, ns, radius, h.st); h.launches += 3;
+            launch_schur(S, h.L, B, V, ns, radius, h.st); h.launches += 4;
             if (h.comm) {
                 if (!h.comm->allreduce_sum(V.C, (size_t)ns * ns, h.st) || !h.comm->allreduce_sum(V.c, ns, h.st)) return fail(CAL_ERR_COMM, h.comm->error());
             }
@@ -1053,7 +1053,7 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
             // thousand views, which one GPU holds.
             // ---- block-structured covariance (refine_kernels.cu, k_cov_*): shared block on the host, view blocks on the device ----
             CUDA_TRY(cudaMemsetAsync(V.fail, 0, sizeof(int32_t), h.st));
-            launch_schur(S, h.L, h.B, V, ns, std::numeric_limits<double>::infinity(), h.st); h.launches += 3;
+            launch_schur(S, h.L, h.B, V, ns, std::numeric_limits<double>::infinity(), h.st); h.launches += 4;
             if (h.comm && !h.comm->allreduce_sum(V.C, (size_t)ns * ns, h.st)) return fail(CAL_ERR_COMM, h.comm->error());
             int32_t failed = 0;
             CUDA_TRY(cudaMemcpyAsync(Cs.data(), V.C, sizeof(double) * ns * ns, cudaMemcpyDeviceToHost, h.st));

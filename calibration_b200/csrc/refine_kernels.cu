@@ -141,7 +141,7 @@ void launch_view_scale(const ProblemShape& S, const ViewBuffers& V, int compute_
 }
 void launch_backsub(const ProblemShape& S, const DevLayout& L, const ViewBuffers& V, int ns, cudaStream_t st) {
     if (S.n_views == 0) return;
-    k_backsub<<<(unsigned)(((int64_t)S.n_views * 32 + 255) / 256), 256, 0, st>>>(S, L, V, ns);   // one warp per view
+    k_backsub<<<(unsigned)((S.n_views + kBacksubViews - 1) / kBacksubViews), 256, 0, st>>>(S, L, V, ns);   // 32 views per CTA
 }
 void launch_view_plus(const ProblemShape& S, const EvalBuffers& B, const ViewBuffers& V, double t, cudaStream_t st) {
     if (S.n_views == 0) return;
@@ -162,7 +162,8 @@ int schur_num_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < 444 * 16 
 void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V, int ns,
                   double radius, cudaStream_t st) {
     if (S.n_views == 0) return;
-    k_schur_factor<<<(unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, 0, st>>>(S, L, B, V, 1.0 / radius);   // one warp per view
+    k_view_chol<<<(unsigned)((S.n_views + 127) / 128), 128, 0, st>>>(S, V, 1.0 / radius);                                                             // one thread per view
+    k_schur_factor<<<(unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, 0, st>>>(S, L, B, V);              // one warp per view
     const int n_cta = schur_num_ctas(S.n_views);
     const int per = (S.n_views + n_cta - 1) / n_cta;
     const int nt = (ns + 1 + kSyrkTile - 1) / kSyrkTile;
@@ -172,15 +173,15 @@ void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& 
     if (once.first()) cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSyrkViews * 6 * kSyrkMaxN * (int)sizeof(double) + 16);
     k_schur_syrk<<<n_cta, threads, smem, st>>>(S, L, V, ns, per);
     const int na = ns + 1;
-    k_schur_reduce<<<(na * na + 127) / 128, 128, 0, st>>>(V, n_cta, ns);
+    k_schur_reduce<<<(na * na + kSchurReduceEntries - 1) / kSchurReduceEntries, 4 * kSchurReduceEntries, 0, st>>>(V, n_cta, ns);
 }
 
 // reduced system of one LM iteration on the device (k_reduced_solve); false: too wide for one CTA's shared memory
 bool launch_reduced_solve(const double* Sm, const double* gss, const ViewBuffers& V, int ns, int32_t* info, cudaStream_t st) {
     if (ns > kReducedMaxN) return false;
-    const int smem = (ns * ns + ns) * (int)sizeof(double);
+    const int smem = (int)(reduced_solve_smem_doubles(ns) * sizeof(double));
     static PerDeviceOnce once;
-    if (once.first()) cudaFuncSetAttribute(k_reduced_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (kReducedMaxN * kReducedMaxN + kReducedMaxN) * (int)sizeof(double));
+    if (once.first()) cudaFuncSetAttribute(k_reduced_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(reduced_solve_smem_doubles(kReducedMaxN) * sizeof(double)));
     k_reduced_solve<<<1, 256, smem, st>>>(Sm, gss, V, ns, info);
     return true;
 }

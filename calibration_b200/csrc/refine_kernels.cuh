@@ -142,7 +142,7 @@ float dfma_peak_ms(double* scratch, int blocks, int threads, int iters, cudaStre
 constexpr int kSyrkTile = 8;
 constexpr int kSyrkThreads = 256;
 constexpr int kReduceViewsCtas = 64;  // CTAs of k_reduce_views at most; ViewBuffers::red_part holds [kReduceViewsCtas][4]
-constexpr int kReducedMaxN = 160;   // widest shared block k_reduced_solve takes (n^2 + n doubles of shared memory)
+constexpr int kReducedMaxN = 160;   // widest shared block k_reduced_solve takes (reduced_solve_smem_doubles(160) = 230 KB of the 227 KiB a CTA may have)
 constexpr int kSyrkMaxN = 176;  // ns + 1 must not exceed this (22 x 8 tiles, 253 <= 256 threads)
 
 struct ViewBuffers {
@@ -157,6 +157,7 @@ struct ViewBuffers {
     double* sp = nullptr;       // jacobi scale [n_views][6]
     double* dp = nullptr;       // clamped LM diagonal [n_views][6]
     double* Lp = nullptr;       // cholesky factors [n_views][36]
+    double* Linv = nullptr;     // reciprocals of their diagonals [n_views][6]
     double* view_f = nullptr;   // L^-1 (sp o gp) [n_views][6]
     double* Fd = nullptr;       // dense rows [F_v | f_v] = L_v^-1 [E_v | g_v], [n_views][6][ncp]; zeros where a camera does not see the view
     int ncp = 0, ns = 0;        // row pitch of Fd (ns + 1 rounded up to the SYRK tile width) and the shared tangent width

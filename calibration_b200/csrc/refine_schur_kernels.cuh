@@ -52,115 +52,245 @@ __global__ void k_view_scale(ProblemShape S, ViewBuffers V, int compute_scale) {
 // F goes to the DENSE per-view rows
 // Fd[view][6][ncp] (column = shared tangent column, column ns = f_v, zeros where a camera does not see the view — the
 // buffer is cleared once at create and the sparsity never changes): 6 x ncp contiguous doubles per view, which is what
-// the SYRK stages with one bulk copy and what the back-substitution reads as plain dot products.  Lane 0 also publishes
-// L_v and f_v; a view without blocks publishes nothing (it has no rows in the Schur complement).
-// One WARP per view, one lane per (residual block of the view, coupling column): every lane repeats the 6x6 factorisation
-// (about a hundred flops from broadcast loads), then the lanes walk the view's columns 32 at a time and store F into the
-// dense rows with consecutive lanes on consecutive columns — full-line writes; the reads of E_b ([entry][n_blk]) are 8-byte
-// gathers whose sectors are shared by the warps of the neighbouring views.
-constexpr int kFactorThreads = 256;
-__global__ void __launch_bounds__(kFactorThreads) k_schur_factor(ProblemShape S, DevLayout L, EvalBuffers B, ViewBuffers V, double inv_radius) {
-    const int v = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+// the SYRK stages with one bulk copy and what the back-substitution reads as plain dot products.
+// Two kernels.  k_view_chol — one THREAD per view: the 6x6 factorisation is a serial chain of about 600 dependent
+// instructions (6 square roots, 6 divisions); one thread per view has every view of the problem in flight at once,
+// where the earlier one-warp-per-view kernel repeated that chain in front of every warp's loads with 16 warps per SM
+// (0.88 ms at 100 k views x 8 cameras, 25 % issue utilisation, long scoreboard 9.4 per issue).  It publishes L_v, the
+// reciprocals of its diagonal, f_v and column ns of the dense rows; a view without blocks publishes nothing (it has no
+// rows in the Schur complement).  k_schur_factor — one WARP per view, one lane per (residual block, coupling column):
+// L_v and the per-camera column tables are staged in shared memory, the lanes walk the view's columns 32 at a time
+// (two trips' gathers in flight), forward-substitute with broadcast reads of L_v and store F into the dense rows with
+// consecutive lanes on consecutive columns — full-line writes; the reads of E_b ([entry][n_blk]) are 8-byte gathers
+// whose sectors are shared by the lanes of the neighbouring blocks.  No factorisation in this kernel: about 50
+// registers, every warp slot of the SM in use.
+__global__ void __launch_bounds__(128) k_view_chol(ProblemShape S, ViewBuffers V, double inv_radius) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= S.n_views || !V.view_free[v]) return;
-    const int k0 = V.view_blk_off[v], nb = V.view_blk_off[v + 1] - k0;
-    if (nb == 0) return;
+    if (V.view_blk_off[v + 1] == V.view_blk_off[v]) return;
     double A[36], sp[6];
     for (int i = 0; i < 6; ++i) sp[i] = V.sp[(int64_t)v * 6 + i];
     for (int i = 0; i < 6; ++i)
         for (int j = 0; j < 6; ++j) A[6 * i + j] = V.Hpp[(int64_t)v * 36 + 6 * i + j] * sp[i] * sp[j];
     for (int i = 0; i < 6; ++i) A[7 * i] += V.dp[(int64_t)v * 6 + i] * inv_radius;
-    if (!chol6(A)) { if (lane == 0) atomicExch(V.fail, 1); return; }   // (the same on every lane)
-    if (lane == 0) {
-        for (int i = 0; i < 36; ++i) V.Lp[(int64_t)v * 36 + i] = A[i];
-        double f[6];
-        for (int i = 0; i < 6; ++i) f[i] = V.gp[(int64_t)v * 6 + i] * sp[i];
-        for (int i = 0; i < 6; ++i) { double s = f[i]; for (int k = 0; k < i; ++k) s -= A[6 * i + k] * f[k]; f[i] = s / A[7 * i]; }
-        for (int i = 0; i < 6; ++i) { V.view_f[(int64_t)v * 6 + i] = f[i]; V.Fd[((int64_t)v * 6 + i) * V.ncp + V.ns] = f[i]; }
+    if (!chol6(A)) { atomicExch(V.fail, 1); return; }
+    for (int i = 0; i < 36; ++i) V.Lp[(int64_t)v * 36 + i] = A[i];
+    for (int i = 0; i < 6; ++i) V.Linv[(int64_t)v * 6 + i] = 1.0 / A[7 * i];
+    double f[6];
+    for (int i = 0; i < 6; ++i) f[i] = V.gp[(int64_t)v * 6 + i] * sp[i];
+    for (int i = 0; i < 6; ++i) { double s = f[i]; for (int k = 0; k < i; ++k) s -= A[6 * i + k] * f[k]; f[i] = s / A[7 * i]; }
+    for (int i = 0; i < 6; ++i) { V.view_f[(int64_t)v * 6 + i] = f[i]; V.Fd[((int64_t)v * 6 + i) * V.ncp + V.ns] = f[i]; }
+}
+
+constexpr int kFactorThreads = 256;
+constexpr int kFactorCamTable = 64;    // cameras whose column tables fit the shared-memory copy (more: read from global memory)
+__global__ void __launch_bounds__(kFactorThreads) k_schur_factor(ProblemShape S, DevLayout L, EvalBuffers B, ViewBuffers V) {
+    __shared__ double sL[kFactorThreads / 32][28];                    // per warp: L_v (21, packed rows) | 1 / diag (6)
+    __shared__ double s_scale[kSyrkMaxN];                             // s_shared
+    __shared__ int s_col[3][kFactorCamTable];                         // cam_col_q / _t / _i
+    for (int i = threadIdx.x; i < V.ns; i += kFactorThreads) s_scale[i] = V.s_shared[i];
+    for (int i = threadIdx.x; i < min(S.n_cams, kFactorCamTable); i += kFactorThreads) {
+        s_col[0][i] = V.cam_col_q[i]; s_col[1][i] = V.cam_col_t[i]; s_col[2][i] = V.cam_col_i[i];
     }
-    const int ncb = 6 + S.PI;
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int v = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (v >= S.n_views || !V.view_free[v]) return;
+    const int k0 = V.view_blk_off[v], nb = V.view_blk_off[v + 1] - k0;
+    if (nb == 0) return;
+    {   // lane l < 21: entry (ri, rj) of the lower triangle; lanes 21..26: the reciprocal diagonal
+        const int ri = (lane >= 1) + (lane >= 3) + (lane >= 6) + (lane >= 10) + (lane >= 15), rj = lane - ri * (ri + 1) / 2;
+        if (lane < 21) sL[w][lane] = V.Lp[(int64_t)v * 36 + 6 * ri + rj];
+        else if (lane < 27) sL[w][lane] = V.Linv[(int64_t)v * 6 + lane - 21];
+    }
+    double sp[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sp[i] = V.sp[(int64_t)v * 6 + i];
+    __syncwarp();
+    const double* const Lw = sL[w];
+    const int ncb = 6 + S.PI, n_items = nb * ncb;
+    const bool cam_table = S.n_cams <= kFactorCamTable;
     double* const Fv = V.Fd + (int64_t)v * 6 * V.ncp;
-    for (int t = lane; t < nb * ncb; t += 32) {
-        const int k = t / ncb, j = t - k * ncb;
-        const int64_t b = V.view_blk_idx[k0 + k];
-        const int col = shared_col(V, L.blk_cam[b], j);
-        if (col < 0) continue;
-        const double sc = V.s_shared[col];
-        double e[6];
-        for (int i = 0; i < 6; ++i) {
-            const double ev = j < 6 ? B.blk_Evc[(int64_t)(6 * i + j) * L.n_blk + b]
-                                    : B.blk_Evi[(int64_t)(S.PI * i + j - 6) * L.n_blk + b];
-            e[i] = ev * sp[i] * sc;
+    for (int t0 = lane; t0 < n_items; t0 += 64) {
+        double e[2][6];
+        int col[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int t = t0 + 32 * u;
+            const bool live = t < n_items;
+            const int k = live ? t / ncb : 0, j = live ? t - k * ncb : 0;
+            const int64_t b = V.view_blk_idx[k0 + k];
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+                e[u][i] = j < 6 ? B.blk_Evc[(int64_t)(6 * i + j) * L.n_blk + b] : B.blk_Evi[(int64_t)(S.PI * i + j - 6) * L.n_blk + b];
+            const int cam = L.blk_cam[b];
+            int c;
+            if (cam_table) { const int base = s_col[j < 3 ? 0 : (j < 6 ? 1 : 2)][cam]; c = base < 0 ? -1 : base + (j < 3 ? j : (j < 6 ? j - 3 : j - 6)); }
+            else c = shared_col(V, cam, j);
+            col[u] = live ? c : -1;
         }
-        for (int i = 0; i < 6; ++i) { double s = e[i]; for (int kk = 0; kk < i; ++kk) s -= A[6 * i + kk] * e[kk]; e[i] = s / A[7 * i]; }
-        for (int i = 0; i < 6; ++i) Fv[i * V.ncp + col] = e[i];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (col[u] < 0) continue;
+            const double sc = s_scale[col[u]];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double s = e[u][i] * sp[i] * sc;
+#pragma unroll
+                for (int kk = 0; kk < i; ++kk) s -= Lw[i * (i + 1) / 2 + kk] * e[u][kk];
+                e[u][i] = s * Lw[21 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Fv[i * V.ncp + col[u]] = e[u][i];
+        }
     }
 }
 
 // The reduced (shared-block) system of one LM iteration, solved where its inputs are: one CTA forms
 //     S = Sm - C,  rhs = gss - c      (Sm: damped Jacobi-scaled H_ss from the host, [ns][ns]; C, c: the Schur complement)
-// in shared memory, factors it by a right-looking Cholesky and solves for y (k_backsub reads y_shared next, in stream
-// order: no round trip to the host between the Schur complement and the back-substitution).  info[0] = 1 if the matrix
-// was not positive definite or y is not finite.  n <= kReducedMaxN (shared memory: n^2 + n doubles).
+// in shared memory, factors it by a BLOCKED right-looking Cholesky and solves for y (k_backsub reads y_shared next, in
+// stream order: no round trip to the host between the Schur complement and the back-substitution).  info[0] = 1 if the
+// matrix was not positive definite or y is not finite.  n <= kReducedMaxN.
+// The right-hand side rides along as row n of the matrix, so the forward substitution is part of the factorisation
+// (row n of the factor is L^-1 rhs).  Per panel of kRedNB columns: (1) one THREAD per row keeps its kRedNB panel entries
+// in registers and the columns are finished left-looking, the row of the diagonal block broadcast through shared memory
+// — one barrier per column; (2) the trailing matrix gets the rank-kRedNB update from the transposed panel in interleaved
+// 8x8 register tiles, one per thread (the k_schur_syrk mapping: conflict-free rows), one barrier per panel.  The
+// column-at-a-time version this replaces spent 3 barriers and a dependent load-FMA-store chain per column: 229 us at
+// n = 114 (round-2 capture), barrier stalls 8 per issue.  Back substitution: panels in reverse, the diagonal block by
+// one warp with shuffles, the rest one thread per unknown.
+// Shared memory: (n + 1) ld + kRedNB kRedPtLd + kRedNB^2 + kRedNB doubles, ld = n | 1 (odd: column walks hit distinct banks).
+constexpr int kRedNB = 16;
+constexpr int kRedPtLd = (kReducedMaxN + 1 - 1 + 7) / 8 * 8;   // the widest trailing block (n rows after a one-column panel), padded to the tile
+__host__ __device__ inline size_t reduced_solve_smem_doubles(int n) {
+    return (size_t)(n + 1) * (n | 1) + (size_t)kRedNB * kRedPtLd + kRedNB * kRedNB + kRedNB;
+}
 __global__ void __launch_bounds__(256) k_reduced_solve(const double* __restrict__ Sm, const double* __restrict__ gss, ViewBuffers V, int n,
                                                        int32_t* __restrict__ info) {
 #if defined(__CUDACC__)
     extern __shared__ __align__(16) double red_sm[];
     __shared__ int bad;
 #else   // host build of this source (tests/host_emul): one CTA runs at a time
-    static double red_sm[kReducedMaxN * kReducedMaxN + kReducedMaxN];
+    static double red_sm[(kReducedMaxN + 1) * (kReducedMaxN | 1) + kRedNB * kRedPtLd + kRedNB * kRedNB + kRedNB];
     static int bad;
 #endif
-    double* A = red_sm;            // [n][n], lower triangle used
-    double* y = red_sm + (size_t)n * n;
+    const int ld = n | 1;
+    double* const A = red_sm;                             // [n + 1][ld]: lower triangle of S, row n = right-hand side
+    double* const Pt = A + (size_t)(n + 1) * ld;          // [kRedNB][kRedPtLd]: the panel below its diagonal block, transposed
+    double* const dg = Pt + (size_t)kRedNB * kRedPtLd;    // [kRedNB][kRedNB]: rows of the panel's diagonal block
+    double* const dgi = dg + kRedNB * kRedNB;             // [kRedNB]: reciprocals of its diagonal
+    double* const z = A + (size_t)n * ld;                 // row n
     const int tid = threadIdx.x;
     if (tid == 0) bad = 0;
-    for (int i = tid; i < n * n; i += 256) A[i] = Sm[i] - V.C[i];
-    for (int i = tid; i < n; i += 256) y[i] = gss[i] - V.c[i];
+    for (int i = tid; i < n * n; i += 256) { const int r = i / n, c = i - r * n; if (c <= r) A[(size_t)r * ld + c] = Sm[i] - V.C[i]; }
+    for (int i = tid; i < n; i += 256) z[i] = gss[i] - V.c[i];
     __syncthreads();
-    for (int j = 0; j < n; ++j) {
-        if (tid == 0) {
-            const double d = A[(size_t)j * n + j];
-            if (!(d > 0.0) || !isfinite(d)) bad = 1;
-            A[(size_t)j * n + j] = sqrt(d);
+    for (int j0 = 0; j0 < n; j0 += kRedNB) {
+        const int nb = min(kRedNB, n - j0);
+        const int rows = n + 1 - j0;                      // rows j0 .. n, one thread each
+        const bool has_row = tid < rows;
+        double row[kRedNB];
+#pragma unroll
+        for (int c = 0; c < kRedNB; ++c) row[c] = (has_row && c < nb && (c <= tid || tid >= nb)) ? A[(size_t)(j0 + tid) * ld + j0 + c] : 0.0;
+#pragma unroll
+        for (int c = 0; c < kRedNB; ++c) {
+            if (c < nb) {
+                if (tid == c) {
+                    double s = row[c];
+#pragma unroll
+                    for (int k = 0; k < c; ++k) s = fma(-row[k], row[k], s);
+                    if (!(s > 0.0) || !isfinite(s)) bad = 1;
+                    const double d = sqrt(s);
+                    row[c] = d;
+#pragma unroll
+                    for (int k = 0; k <= c; ++k) dg[c * kRedNB + k] = row[k];
+                    dgi[c] = 1.0 / d;
+                }
+                __syncthreads();
+                if (has_row && tid > c && !bad) {
+                    double s = row[c];
+#pragma unroll
+                    for (int k = 0; k < c; ++k) s = fma(-row[k], dg[c * kRedNB + k], s);
+                    row[c] = s * dgi[c];
+                }
+            }
+        }
+        if (bad) break;                                   // (uniform: read after a barrier, written before it)
+        // the factor's columns go back (the diagonal holds 1 / L_jj: only the back substitution reads it again), and
+        // the rows below the diagonal block go to the transposed panel, zero-padded to the tile grid
+        const int m = rows - nb, nt = (m + 7) / 8;        // trailing rows (the right-hand side is the last one)
+#pragma unroll
+        for (int c = 0; c < kRedNB; ++c) {
+            if (c < nb) {
+                if (has_row && (c <= tid || tid >= nb)) A[(size_t)(j0 + tid) * ld + j0 + c] = (tid == c) ? dgi[c] : row[c];
+                if (tid >= nb && tid < nb + nt * 8) Pt[c * kRedPtLd + tid - nb] = row[c];   // (row[] is zero past the last row)
+            }
         }
         __syncthreads();
-        if (bad) break;
-        const double inv = 1.0 / A[(size_t)j * n + j];
-        for (int i = j + 1 + tid; i < n; i += 256) A[(size_t)i * n + j] *= inv;
-        __syncthreads();
-        // trailing update of the lower triangle: A[i][k] -= L[i][j] L[k][j], j < k <= i; threads as a 16 x 16 grid over (i, k)
-        for (int i = j + 1 + (tid >> 4); i < n; i += 16) {
-            const double lij = A[(size_t)i * n + j];
-            for (int k = j + 1 + (tid & 15); k <= i; k += 16) A[(size_t)i * n + k] = fma(-lij, A[(size_t)k * n + j], A[(size_t)i * n + k]);
+        if (m > 1) {
+            int ti = -1, tj = -1;
+            { int t = tid, r = 0; while (r < nt && t >= nt - r) { t -= nt - r; ++r; } if (r < nt) { ti = r; tj = r + t; } }
+            if (ti >= 0) {
+                double acc[8][8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+                for (int c = 0; c < nb; ++c) {
+                    double fa[8], fb[8];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) { fa[a] = Pt[c * kRedPtLd + ti + nt * a]; fb[a] = Pt[c * kRedPtLd + tj + nt * a]; }
+#pragma unroll
+                    for (int a = 0; a < 8; ++a)
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) acc[a][b] = fma(fa[a], fb[b], acc[a][b]);
+                }
+                double* const T = A + (size_t)(j0 + nb) * ld + j0 + nb;   // the trailing block
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) {
+                        const int r = ti + nt * a, cc = tj + nt * b;
+                        const int hi = max(r, cc), lo = min(r, cc);
+                        if (hi < m && lo < m - 1 && (ti != tj || a >= b)) T[(size_t)hi * ld + lo] -= acc[a][b];
+                    }
+            }
         }
         __syncthreads();
     }
-    if (!bad && tid < 32) {   // the two triangular solves: one warp, lane-strided dot products in a fixed order
-        for (int i = 0; i < n; ++i) {
-            double s = 0.0;
-            for (int k = tid; k < i; k += 32) s += A[(size_t)i * n + k] * y[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (tid == 0) y[i] = (y[i] - s) / A[(size_t)i * n + i];
-            __syncwarp();
+    if (!bad) {   // L^T y = z, panels in reverse
+        for (int j0 = (n - 1) / kRedNB * kRedNB; j0 >= 0; j0 -= kRedNB) {
+            const int nb = min(kRedNB, n - j0);
+            if (tid < 32) {
+                double x = tid < nb ? z[j0 + tid] : 0.0;
+                for (int c = nb - 1; c >= 0; --c) {
+                    if (tid == c) x *= A[(size_t)(j0 + c) * ld + j0 + c];   // (the stored reciprocal)
+                    const double xc = __shfl_sync(0xffffffffu, x, c);
+                    if (tid < c) x = fma(-A[(size_t)(j0 + c) * ld + j0 + tid], xc, x);
+                }
+                if (tid < nb) z[j0 + tid] = x;
+            }
+            __syncthreads();
+            if (tid < j0) {
+                double s = z[tid];
+                for (int c = 0; c < nb; ++c) s = fma(-A[(size_t)(j0 + c) * ld + tid], z[j0 + c], s);
+                z[tid] = s;
+            }
+            __syncthreads();
         }
-        for (int i = n - 1; i >= 0; --i) {
-            double s = 0.0;
-            for (int k = i + 1 + tid; k < n; k += 32) s += A[(size_t)k * n + i] * y[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (tid == 0) y[i] = (y[i] - s) / A[(size_t)i * n + i];
-            __syncwarp();
-        }
-        for (int i = tid; i < n; i += 32) if (!isfinite(y[i])) bad = 1;
+        for (int i = tid; i < n; i += 256) if (!isfinite(z[i])) bad = 1;
     }
     __syncthreads();
-    for (int i = tid; i < n; i += 256) V.y_shared[i] = y[i];
+    for (int i = tid; i < n; i += 256) V.y_shared[i] = z[i];
     if (tid == 0) info[0] = bad;
 }
 
 // C_aug = sum_v F_v^T F_v as a tiled SYRK with a long inner dimension (6 rows per view).  The
-// (ns+1)^2 upper triangle is covered by 8x8 register tiles, one per thread; the CTA has exactly as many
+// (ns+1)^2 matrix is covered by 8x8 register tiles, one per thread, INTERLEAVED: the tile (ti, tj), ti <= tj, holds the
+// entries (ti + nt i, tj + nt j), i, j < 8 (nt tiles per side, ncp = 8 nt).  Every unordered pair of columns belongs to
+// exactly one tile, and the lanes of a warp (consecutive tj, two to four values of ti) read consecutive doubles of a
+// staged row — one shared-memory wavefront per load.  (Contiguous 8-column tiles put the lanes 64 bytes apart: an
+// 8-way bank conflict, 85 % shared-memory pipe and 27 % FP64 pipe in the round-2 capture.)  The CTA has exactly as many
 // warps as the tile count needs (120 tiles at ns = 114 -> 4 warps, three CTAs per SM) and owns a chunk of
 // the views.  The rows [F_v | f_v] of kSyrkViews consecutive views are ONE contiguous block of Fd, staged by
 // a TMA bulk copy (cp.async.bulk + mbarrier) into a two-stage shared-memory ring: the copy of the next views
@@ -240,7 +370,7 @@ __global__ void __launch_bounds__(kSyrkThreads) k_schur_syrk(ProblemShape S, Dev
             for (int r = 0; r < nvb * 6; ++r) {
                 double fa[kSyrkTile], fb[kSyrkTile];
 #pragma unroll
-                for (int i = 0; i < kSyrkTile; ++i) { fa[i] = frow[r * ncp + ti * kSyrkTile + i]; fb[i] = frow[r * ncp + tj * kSyrkTile + i]; }
+                for (int i = 0; i < kSyrkTile; ++i) { fa[i] = frow[r * ncp + ti + nt * i]; fb[i] = frow[r * ncp + tj + nt * i]; }
 #pragma unroll
                 for (int i = 0; i < kSyrkTile; ++i)
 #pragma unroll
@@ -257,49 +387,96 @@ __global__ void __launch_bounds__(kSyrkThreads) k_schur_syrk(ProblemShape S, Dev
         double* out = V.partialC + (int64_t)blockIdx.x * na * na;
         for (int i = 0; i < kSyrkTile; ++i)
             for (int j = 0; j < kSyrkTile; ++j) {
-                const int r = ti * kSyrkTile + i, c = tj * kSyrkTile + j;
+                const int r = ti + nt * i, c = tj + nt * j;
                 if (r < na && c < na) { out[(int64_t)r * na + c] = acc[i][j]; if (ti != tj) out[(int64_t)c * na + r] = acc[i][j]; }
             }
     }
 }
 
-__global__ void k_schur_reduce(ViewBuffers V, int n_cta, int ns) {
+// The per-CTA partials of the SYRK summed in CTA order.  One thread per entry walking 444 partials is a chain of 444
+// dependent additions behind loads issued one at a time (113 us at ns = 114, round 2): four threads share an entry, each
+// sums a quarter of the partials with eight loads in flight, and the quarters are added in order — a fixed order, so
+// the result does not depend on scheduling.
+constexpr int kSchurReduceEntries = 32;   // entries per CTA (x 4 quarter sums = 128 threads)
+__global__ void __launch_bounds__(4 * kSchurReduceEntries) k_schur_reduce(ViewBuffers V, int n_cta, int ns) {
+    __shared__ double part[4][kSchurReduceEntries];
     const int na = ns + 1;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= na * na) return;
+    const int e = threadIdx.x % kSchurReduceEntries, qd = threadIdx.x / kSchurReduceEntries;
+    const int i = blockIdx.x * kSchurReduceEntries + e;
+    const int per = (n_cta + 3) / 4, c0 = qd * per, c1 = min(n_cta, c0 + per);
     double s = 0.0;
-    for (int c = 0; c < n_cta; ++c) s += V.partialC[(int64_t)c * na * na + i];
+    if (i < na * na) {
+        const double* p = V.partialC + i;
+        const int64_t stride = (int64_t)na * na;
+        int c = c0;
+        for (; c + 8 <= c1; c += 8) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = p[(c + u) * stride];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += t[u];
+        }
+        for (; c < c1; ++c) s += p[c * stride];
+    }
+    part[qd][e] = s;
+    __syncthreads();
+    if (qd != 0 || i >= na * na) return;
+    s = ((part[0][e] + part[1][e]) + part[2][e]) + part[3][e];
     const int r = i / na, cc = i % na;
     if (r < ns && cc < ns) V.C[(int64_t)r * ns + cc] = s;
     else if (r < ns && cc == ns) V.c[r] = s;
 }
 
 // y_p = L^-T (f - F_v y_s), step_p = -y_p, delta_p = step_p o sp, and the per-view terms of step'g and
-// step'H step (H undamped, Jacobi-scaled).  One WARP per view: q = F_v y_s are six dot products over the dense rows of
-// the view (lanes stride over the shared columns: coalesced), summed by a fixed shuffle tree; lane 0 finishes the 6x6 part.
+// step'H step (H undamped, Jacobi-scaled).  A CTA takes kBacksubViews = 32 consecutive views.  Phase 1: each of the 8
+// warps forms q = F_v y_s for FOUR views at once — six dot products per view over the dense rows, lanes striding over
+// the shared columns (coalesced), 24 independent loads in flight per lane — summed by a fixed shuffle tree and left in
+// shared memory.  Phase 2: warp 0, one LANE per view, finishes the 6x6 part for the 32 views side by side.  (One warp
+// per view with lane 0 walking the serial 6x6 part kept 16 warp slots per SM waiting on one lane's dependent chain:
+// 0.27 ms = 2.1 TB/s for a 576 MB read, round 2.)
+constexpr int kBacksubViews = 32;
 __global__ void __launch_bounds__(256) k_backsub(ProblemShape S, DevLayout L, ViewBuffers V, int ns) {
-    const int v = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    __shared__ double sq[kBacksubViews][6];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int vbase = blockIdx.x * kBacksubViews;
+    {
+        const int v0 = vbase + 4 * w;                      // this warp's four views
+        double q[4][6];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) q[a][i] = 0.0;
+        const double* F[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) F[a] = V.Fd + (int64_t)min(v0 + a, S.n_views - 1) * 6 * V.ncp;   // (clamped: a view past the end is not used)
+        for (int c = lane; c < ns; c += 32) {
+            const double ys = V.y_shared[c];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int i = 0; i < 6; ++i) q[a][i] = fma(F[a][i * V.ncp + c], ys, q[a][i]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) q[a][i] += __shfl_xor_sync(0xffffffffu, q[a][i], o);
+                if (lane == 0) sq[4 * w + a][i] = q[a][i];
+            }
+    }
+    __syncthreads();
+    if (w != 0) return;
+    const int v = vbase + lane;
     if (v >= S.n_views) return;
     double* red = V.red + (int64_t)v * 4;
     if (!V.view_free[v] || V.view_blk_off[v + 1] == V.view_blk_off[v]) {   // fixed, or seen by no camera: no step
-        if (lane == 0) {
-            for (int i = 0; i < 6; ++i) V.delta_p[(int64_t)v * 6 + i] = 0.0;
-            red[0] = red[1] = 0.0;
-        }
+        for (int i = 0; i < 6; ++i) V.delta_p[(int64_t)v * 6 + i] = 0.0;
+        red[0] = red[1] = 0.0;
         return;
     }
-    double q[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    const double* Fv = V.Fd + (int64_t)v * 6 * V.ncp;
-    for (int c = lane; c < ns; c += 32) {
-        const double ys = V.y_shared[c];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) q[i] = fma(Fv[i * V.ncp + c], ys, q[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) q[i] += __shfl_xor_sync(0xffffffffu, q[i], o);
-    if (lane != 0) return;
+    double q[6];
+    for (int i = 0; i < 6; ++i) q[i] = sq[lane][i];
     double Lm[36], f[6], sp[6];
     for (int i = 0; i < 36; ++i) Lm[i] = V.Lp[(int64_t)v * 36 + i];
     for (int i = 0; i < 6; ++i) { f[i] = V.view_f[(int64_t)v * 6 + i]; sp[i] = V.sp[(int64_t)v * 6 + i]; }

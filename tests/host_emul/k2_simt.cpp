@@ -57,14 +57,14 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
     for (int v = 0; v < n_views; ++v) off[v + 1] += off[v];
     { std::vector<int32_t> cur(off.begin(), off.end() - 1); for (int64_t b = 0; b < n_blk; ++b) idx[cur[blk_view[b]]++] = (int32_t)b; }
     const int n_cta = schur_ctas(n_views), na = ns + 1, ncb = 6 + PI;
-    std::vector<double> Hpp((size_t)n_views * 36), gp((size_t)n_views * 6), sp((size_t)n_views * 6, 0.0), dp((size_t)n_views * 6), Lp((size_t)n_views * 36),
+    std::vector<double> Hpp((size_t)n_views * 36), gp((size_t)n_views * 6), sp((size_t)n_views * 6, 0.0), dp((size_t)n_views * 6), Lp((size_t)n_views * 36), Linv((size_t)n_views * 6),
         view_f((size_t)n_views * 6), Fd((size_t)n_views * 6 * ((ns + 1 + kSyrkTile - 1) / kSyrkTile * kSyrkTile), 0.0), dlt((size_t)n_views * 6, 0.0), ss(s_shared, s_shared + ns), ys(std::max(ns, 1)),
         Cm((size_t)ns * ns), cv(std::max(ns, 1)), partialC((size_t)n_cta * na * na), red((size_t)n_views * 4, 0.0), ro(4, 0.0);
     int32_t failed = 0;
     ViewBuffers V;
     V.view_blk_off = off.data(); V.view_blk_idx = idx.data(); V.view_free = vfree.data();
     V.cam_col_q = cq.data(); V.cam_col_t = ct.data(); V.cam_col_i = ci.data();
-    V.Hpp = Hpp.data(); V.gp = gp.data(); V.sp = sp.data(); V.dp = dp.data(); V.Lp = Lp.data(); V.view_f = view_f.data(); V.Fd = Fd.data(); V.ns = ns; V.ncp = (ns + 1 + kSyrkTile - 1) / kSyrkTile * kSyrkTile;
+    V.Hpp = Hpp.data(); V.gp = gp.data(); V.sp = sp.data(); V.dp = dp.data(); V.Lp = Lp.data(); V.Linv = Linv.data(); V.view_f = view_f.data(); V.Fd = Fd.data(); V.ns = ns; V.ncp = (ns + 1 + kSyrkTile - 1) / kSyrkTile * kSyrkTile;
     V.delta_p = dlt.data(); V.s_shared = ss.data(); V.y_shared = ys.data(); V.C = Cm.data(); V.c = cv.data(); V.partialC = partialC.data();
     std::vector<double> rpart((size_t)kReduceViewsCtas * 4, 0.0); unsigned rticket = 0u;
     V.red = red.data(); V.red_out = ro.data(); V.fail = &failed; V.red_part = rpart.data(); V.red_ticket = &rticket;
@@ -73,10 +73,11 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
     simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 1); });
     simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 0); });
     // launch_schur
-    simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V, 1.0 / radius); });
+    simt::launch((unsigned)((S.n_views + 127) / 128), 128, [&] { k_view_chol(S, V, 1.0 / radius); });
+    simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V); });
     const int per = (n_views + n_cta - 1) / n_cta, nt = (na + kSyrkTile - 1) / kSyrkTile, threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
     simt::launch((unsigned)n_cta, (unsigned)threads, [&] { k_schur_syrk(S, L, V, ns, per); });
-    simt::launch((unsigned)((na * na + 127) / 128), 128, [&] { k_schur_reduce(V, n_cta, ns); });
+    simt::launch((unsigned)((na * na + kSchurReduceEntries - 1) / kSchurReduceEntries), 4 * kSchurReduceEntries, [&] { k_schur_reduce(V, n_cta, ns); });
     *fail = failed;
     std::memcpy(C, Cm.data(), sizeof(double) * ns * ns); std::memcpy(c, cv.data(), sizeof(double) * ns);
     std::memcpy(sp_out, sp.data(), sizeof(double) * 6 * n_views);
@@ -95,7 +96,7 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
         if (!(dev <= 1e-9 * (ref + 1e-300))) return 5;
     }
     std::memcpy(y_shared, ys.data(), sizeof(double) * ns);
-    simt::launch((unsigned)(((int64_t)n_views * 32 + 255) / 256), 256, [&] { k_backsub(S, L, V, ns); });
+    simt::launch((unsigned)((n_views + kBacksubViews - 1) / kBacksubViews), 256, [&] { k_backsub(S, L, V, ns); });
     simt::launch(n_views >= 2048 ? 2u : 1u, 256, [&] { k_reduce_views(V, n_views); });
     std::memcpy(delta_p, dlt.data(), sizeof(double) * 6 * n_views);
     std::memcpy(red_out4, ro.data(), sizeof(double) * 4);
@@ -128,7 +129,7 @@ extern "C" int simt_k2_cov(int n_views, int n_cams, int PI, int64_t n_blk, const
     for (int v = 0; v < n_views; ++v) off[v + 1] += off[v];
     { std::vector<int32_t> cur(off.begin(), off.end() - 1); for (int64_t b = 0; b < n_blk; ++b) idx[cur[blk_view[b]]++] = (int32_t)b; }
     const int n_cta = schur_ctas(n_views), na = ns + 1, ncb = 6 + PI;
-    std::vector<double> Hpp((size_t)n_views * 36), gp((size_t)n_views * 6), sp((size_t)n_views * 6, 0.0), dp((size_t)n_views * 6), Lp((size_t)n_views * 36),
+    std::vector<double> Hpp((size_t)n_views * 36), gp((size_t)n_views * 6), sp((size_t)n_views * 6, 0.0), dp((size_t)n_views * 6), Lp((size_t)n_views * 36), Linv((size_t)n_views * 6),
         view_f((size_t)n_views * 6), Fd((size_t)n_views * 6 * ((ns + 1 + kSyrkTile - 1) / kSyrkTile * kSyrkTile), 0.0), ss(s_shared, s_shared + ns), Cm((size_t)ns * ns), cv(std::max(ns, 1)),
         partialC((size_t)n_cta * na * na), x(na_amb, 0.0);
     std::memcpy(x.data(), view_quats, sizeof(double) * 4 * n_views);
@@ -136,15 +137,16 @@ extern "C" int simt_k2_cov(int n_views, int n_cams, int PI, int64_t n_blk, const
     ViewBuffers V;
     V.view_blk_off = off.data(); V.view_blk_idx = idx.data(); V.view_free = vfree.data();
     V.cam_col_q = cq.data(); V.cam_col_t = ct.data(); V.cam_col_i = ci.data();
-    V.Hpp = Hpp.data(); V.gp = gp.data(); V.sp = sp.data(); V.dp = dp.data(); V.Lp = Lp.data(); V.view_f = view_f.data(); V.Fd = Fd.data(); V.ns = ns; V.ncp = (ns + 1 + kSyrkTile - 1) / kSyrkTile * kSyrkTile;
+    V.Hpp = Hpp.data(); V.gp = gp.data(); V.sp = sp.data(); V.dp = dp.data(); V.Lp = Lp.data(); V.Linv = Linv.data(); V.view_f = view_f.data(); V.Fd = Fd.data(); V.ns = ns; V.ncp = (ns + 1 + kSyrkTile - 1) / kSyrkTile * kSyrkTile;
     V.s_shared = ss.data(); V.C = Cm.data(); V.c = cv.data(); V.partialC = partialC.data(); V.fail = &failed;
     simt::launch((unsigned)((n_views + 127) / 128), 128, [&] { k_view_gather(S, L, B, V); });
     simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 1); });
     // launch_schur(radius = infinity): undamped factors L_v and F_b = L_v^-1 E_b stay in V
-    simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V, 0.0); });
+    simt::launch((unsigned)((S.n_views + 127) / 128), 128, [&] { k_view_chol(S, V, 0.0); });
+    simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V); });
     const int per = (n_views + n_cta - 1) / n_cta, nt = (na + kSyrkTile - 1) / kSyrkTile, threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
     simt::launch((unsigned)n_cta, (unsigned)threads, [&] { k_schur_syrk(S, L, V, ns, per); });
-    simt::launch((unsigned)((na * na + 127) / 128), 128, [&] { k_schur_reduce(V, n_cta, ns); });
+    simt::launch((unsigned)((na * na + kSchurReduceEntries - 1) / kSchurReduceEntries), 4 * kSchurReduceEntries, [&] { k_schur_reduce(V, n_cta, ns); });
     if (failed) return 4;
     // host: W = (S Hss S - C)^-1, column by column (cal_refine_solve does the same with chol_host / chol_solve_host)
     std::vector<double> Sm((size_t)ns * ns), W((size_t)ns * ns), e(std::max(ns, 1));
@@ -188,5 +190,26 @@ extern "C" int simt_k2_plus_norms(int n_views, const double* x, const double* de
     simt::launch((unsigned)((n_views + 127) / 128), 128, [&] { k_view_norms(S, B, V); });
     simt::launch(n_views >= 2048 ? 2u : 1u, 256, [&] { k_reduce_views(V, n_views); });
     std::memcpy(red_norms4, ro.data(), 4 * sizeof(double));
+    return 0;
+}
+
+// The product's reduced solve alone (k_reduced_solve, one CTA): (Sm - C) y = gss - c against the dense host solve.
+// Returns 0 and the largest |y - y_ref| / max|y_ref| in err[0]; 1: the kernel flagged the matrix (info), 2: n too wide,
+// 3: the host solver found the matrix not positive definite.
+extern "C" int simt_k2_reduced_solve(int n, const double* Sm, const double* Cm, const double* gss, const double* cv, double* y_out, double* err) {
+    if (n > kReducedMaxN) return 2;
+    ViewBuffers V;
+    std::vector<double> C(Cm, Cm + (size_t)n * n), c(cv, cv + n), y(std::max(n, 1), 0.0);
+    V.C = C.data(); V.c = c.data(); V.y_shared = y.data();
+    int32_t info[2] = {0, 0};
+    simt::launch(1, 256, [&] { k_reduced_solve(Sm, gss, V, n, info); });
+    std::memcpy(y_out, y.data(), sizeof(double) * n);
+    if (info[0]) return 1;
+    std::vector<double> A((size_t)n * n), b(n);
+    for (int i = 0; i < n; ++i) { b[i] = gss[i] - cv[i]; for (int j = 0; j < n; ++j) A[(size_t)i * n + j] = Sm[(size_t)i * n + j] - Cm[(size_t)i * n + j]; }
+    if (!solve_spd(A, n, b.data())) return 3;
+    double ref = 0.0, dev = 0.0;
+    for (int i = 0; i < n; ++i) { ref = std::max(ref, std::fabs(b[i])); dev = std::max(dev, std::fabs(b[i] - y[i])); }
+    err[0] = dev / (ref + 1e-300);
     return 0;
 }

@@ -136,7 +136,7 @@ void launch_view_scale(const ProblemShape& S, const ViewBuffers& V, int compute_
 }
 void launch_backsub(const ProblemShape& S, const DevLayout& L, const ViewBuffers& V, int ns, cudaStream_t) {
     if (S.n_views == 0) return;
-    simt::launch((unsigned)(((int64_t)S.n_views * 32 + 255) / 256), 256, [&] { k_backsub(S, L, V, ns); });
+    simt::launch((unsigned)((S.n_views + kBacksubViews - 1) / kBacksubViews), 256, [&] { k_backsub(S, L, V, ns); });
 }
 void launch_view_plus(const ProblemShape& S, const EvalBuffers& B, const ViewBuffers& V, double t, cudaStream_t) {
     if (S.n_views == 0) return;
@@ -150,14 +150,15 @@ void launch_reduce_views(const ViewBuffers& V, int n_views, cudaStream_t) { simt
 int schur_num_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < 444 * 16 ? (n_views + 15) / 16 : 444); }
 void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V, int ns, double radius, cudaStream_t) {
     if (S.n_views == 0) return;
-    simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V, 1.0 / radius); });
+    simt::launch((unsigned)((S.n_views + 127) / 128), 128, [&] { k_view_chol(S, V, 1.0 / radius); });
+    simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V); });
     const int n_cta = schur_num_ctas(S.n_views);
     const int per = (S.n_views + n_cta - 1) / n_cta;
     const int nt = (ns + 1 + kSyrkTile - 1) / kSyrkTile;
     const int threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
     simt::launch((unsigned)n_cta, (unsigned)threads, [&] { k_schur_syrk(S, L, V, ns, per); });
     const int na = ns + 1;
-    simt::launch((unsigned)((na * na + 127) / 128), 128, [&] { k_schur_reduce(V, n_cta, ns); });
+    simt::launch((unsigned)((na * na + kSchurReduceEntries - 1) / kSchurReduceEntries), 4 * kSchurReduceEntries, [&] { k_schur_reduce(V, n_cta, ns); });
 }
 bool launch_reduced_solve(const double* Sm, const double* gss, const ViewBuffers& V, int ns, int32_t* info, cudaStream_t) {
     if (ns > kReducedMaxN) return false;

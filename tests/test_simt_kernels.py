@@ -740,3 +740,34 @@ def test_view_plus_and_norms_kernels_match_the_ceres_manifold(k2_simt):
     for v in np.flatnonzero(vfree):
         gm = max(gm, np.abs(q[v] - _ceres_quaternion_plus(q[v], -gp[v, :3])).max(), np.abs(gp[v, 3:]).max())
     assert abs(rn[3] - gm) <= 1e-12 * gm
+
+
+@pytest.mark.parametrize("n", [1, 7, 15, 16, 17, 31, 32, 33, 114, 145, 160])
+def test_reduced_solve_source_matches_a_dense_solve(k2_simt, n):
+    """k_reduced_solve (blocked Cholesky of the shared block in one CTA, right-hand side as an extra row, blocked back
+    substitution) against a dense host solve, at sizes around the panel width (16), at the c5-size extrinsics problem
+    (114) and at the widest block the kernel takes (160).  Replaces the host factorisation of
+    ceres-style normal equations the reference leaves to Ceres (ceresutils.h:27-43)."""
+    rng = np.random.default_rng(100 + n)
+    M = rng.standard_normal((n, n + 3))
+    S = M @ M.T + 0.5 * np.eye(n)
+    Cm = 0.1 * (lambda Q: Q @ Q.T)(rng.standard_normal((n, 2)))      # a positive semi-definite Schur complement to subtract
+    Sm = np.ascontiguousarray(S + Cm)
+    g, c = rng.standard_normal(n), rng.standard_normal(n)
+    y, err = np.zeros(n), np.zeros(1)
+    rc = k2_simt.simt_k2_reduced_solve(n, abi.dptr(Sm), abi.dptr(np.ascontiguousarray(Cm)), abi.dptr(g), abi.dptr(c), abi.dptr(y), abi.dptr(err))
+    assert rc == 0, rc
+    assert err[0] <= 1e-11, err[0]
+    assert np.abs(S @ y - (g - c)).max() <= 1e-9 * (np.abs(g - c).max() + np.abs(S).max() * np.abs(y).max())
+
+
+def test_reduced_solve_source_flags_an_indefinite_block(k2_simt):
+    n = 40
+    rng = np.random.default_rng(7)
+    M = rng.standard_normal((n, n))
+    S = M @ M.T + np.eye(n)
+    S[25, 25] = -1.0                                                  # pivot 25 (second panel) turns negative
+    y, err = np.zeros(n), np.zeros(1)
+    rc = k2_simt.simt_k2_reduced_solve(n, abi.dptr(np.ascontiguousarray(S)), abi.dptr(np.zeros((n, n))), abi.dptr(rng.standard_normal(n)), abi.dptr(np.zeros(n)),
+                                       abi.dptr(y), abi.dptr(err))
+    assert rc == 1, rc
