@@ -157,21 +157,34 @@ void launch_reduce_views(const ViewBuffers& V, int n_views, cudaStream_t st) {
 }
 
 // up to three CTAs per SM (4-warp CTAs at the common shared-block widths), at least 16 views each
-int schur_num_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < 444 * 16 ? (n_views + 15) / 16 : 444); }
+int schur_num_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < kSchurMaxCtas * 16 ? (n_views + 15) / 16 : kSchurMaxCtas); }   // an upper bound (partialC is sized by it)
 
 void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V, int ns,
                   double radius, cudaStream_t st) {
     if (S.n_views == 0) return;
     k_view_chol<<<(unsigned)((S.n_views + 127) / 128), 128, 0, st>>>(S, V, 1.0 / radius);                                                             // one thread per view
     k_schur_factor<<<(unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, 0, st>>>(S, L, B, V);              // one warp per view
-    const int n_cta = schur_num_ctas(S.n_views);
-    const int per = (S.n_views + n_cta - 1) / n_cta;
-    const int nt = (ns + 1 + kSyrkTile - 1) / kSyrkTile;
-    const int threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;  // one thread per 8x8 tile of the upper triangle
+    int bt = 0, warps = 0;
+    syrk_shape(ns, &bt, &warps);
+    const int threads = 32 * warps;                                           // one warp per block of bt x bt tiles of the upper triangle
     const int smem = 2 * kSyrkViews * 6 * V.ncp * (int)sizeof(double) + 16;   // two stages of dense rows + two mbarriers
+    const int smem_max = 2 * kSyrkViews * 6 * kSyrkMaxN * (int)sizeof(double) + 16;
+    void (*kern)(ProblemShape, ViewBuffers, int, int) = bt == 3 ? k_schur_syrk<3, 320> : (threads <= 320 ? k_schur_syrk<5, 320> : k_schur_syrk<5, 480>);
     static PerDeviceOnce once;
-    if (once.first()) cudaFuncSetAttribute(k_schur_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSyrkViews * 6 * kSyrkMaxN * (int)sizeof(double) + 16);
-    k_schur_syrk<<<n_cta, threads, smem, st>>>(S, L, V, ns, per);
+    if (once.first()) {
+        cudaFuncSetAttribute(k_schur_syrk<3, 320>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        cudaFuncSetAttribute(k_schur_syrk<5, 320>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+        cudaFuncSetAttribute(k_schur_syrk<5, 480>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    }
+    int n_cta = schur_num_ctas(S.n_views);
+    if (n_cta == kSchurMaxCtas) {   // a large problem: exactly one wave of resident CTAs (444 CTAs on 296 slots ran as one and a half)
+        int occ = 0, dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) == cudaSuccess && occ > 0)
+            n_cta = std::min(n_cta, occ * sms);
+    }
+    const int per = (S.n_views + n_cta - 1) / n_cta;
+    kern<<<n_cta, threads, smem, st>>>(S, V, ns, per);
     const int na = ns + 1;
     k_schur_reduce<<<(na * na + kSchurReduceEntries - 1) / kSchurReduceEntries, 4 * kSchurReduceEntries, 0, st>>>(V, n_cta, ns);
 }

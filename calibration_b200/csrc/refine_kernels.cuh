@@ -140,7 +140,7 @@ float dfma_peak_ms(double* scratch, int blocks, int threads, int iters, cudaStre
 
 // ---- per-view (Schur) machinery -------------------------------------------------
 constexpr int kSyrkTile = 8;
-constexpr int kSyrkThreads = 256;
+constexpr int kSyrkThreads = 480;  // at most fifteen warps (syrk_shape)
 constexpr int kReduceViewsCtas = 64;  // CTAs of k_reduce_views at most; ViewBuffers::red_part holds [kReduceViewsCtas][4]
 constexpr int kReducedMaxN = 160;   // widest shared block k_reduced_solve takes (reduced_solve_smem_doubles(160) = 230 KB of the 227 KiB a CTA may have)
 constexpr int kSyrkMaxN = 176;  // ns + 1 must not exceed this (22 x 8 tiles, 253 <= 256 threads)
@@ -174,6 +174,7 @@ struct ViewBuffers {
     double* x_cand = nullptr;   // candidate parameters [n_amb]
     int32_t* fail = nullptr;    // cholesky failure flag
 };
+constexpr int kSchurMaxCtas = 444;   // 3 x 148
 int schur_num_ctas(int n_views);
 void launch_view_gather(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V,
                         cudaStream_t st);

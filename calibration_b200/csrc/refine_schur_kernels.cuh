@@ -285,20 +285,40 @@ __global__ void __launch_bounds__(256) k_reduced_solve(const double* __restrict_
     if (tid == 0) info[0] = bad;
 }
 
-// C_aug = sum_v F_v^T F_v as a tiled SYRK with a long inner dimension (6 rows per view).  The
-// (ns+1)^2 matrix is covered by 8x8 register tiles, one per thread, INTERLEAVED: the tile (ti, tj), ti <= tj, holds the
-// entries (ti + nt i, tj + nt j), i, j < 8 (nt tiles per side, ncp = 8 nt).  Every unordered pair of columns belongs to
-// exactly one tile, and the lanes of a warp (consecutive tj, two to four values of ti) read consecutive doubles of a
-// staged row — one shared-memory wavefront per load.  (Contiguous 8-column tiles put the lanes 64 bytes apart: an
-// 8-way bank conflict, 85 % shared-memory pipe and 27 % FP64 pipe in the round-2 capture.)  The CTA has exactly as many
-// warps as the tile count needs (120 tiles at ns = 114 -> 4 warps, three CTAs per SM) and owns a chunk of
-// the views.  The rows [F_v | f_v] of kSyrkViews consecutive views are ONE contiguous block of Fd, staged by
-// a TMA bulk copy (cp.async.bulk + mbarrier) into a two-stage shared-memory ring: the copy of the next views
-// runs under the FMAs of the current ones.  Per-CTA partial results are summed in a fixed order (no
-// floating-point atomics).  Dynamic shared memory: 2 * kSyrkViews * 6 * ncp doubles + 2 mbarriers.
+// C_aug = sum_v F_v^T F_v — a SYRK with a long inner dimension (6 rows per view, 600 000 rows at 100 k views) and a
+// small output ((ns+1)^2, ns + 1 <= 176): the one GEMM-shaped operation of the path, on the FP64 TENSOR-CORE instruction
+// (mma.sync m8n8k4 f64, SASS DMMA.8x8x4).  On B200 DMMA and DFMA share one FP64 roof (tools/ubench_dmma.cu: 37.0 against
+// 36.3 TFLOP/s, no co-issue), so the gain is not a higher peak but what a DMMA does not need: one instruction per 256
+// multiply-adds and two 8-byte operands per lane, where the register-tiled DFMA version issued 16 shared-memory loads
+// per 64 DFMAs and stopped at 50 % of the FP64 pipe (an LDS costs the FP64 pipe 1.6 DFMA issue slots).
+// The upper triangle of the output is cut into blocks of BT x BT tiles of 8x8; a WARP owns one block (its accumulators:
+// 2 BT^2 doubles per lane) and per k-step of four rows loads BT + BT operand fragments for BT^2 DMMAs.  The rows
+// [F_v | f_v] of kSyrkViews consecutive views are ONE contiguous block of Fd, staged by a TMA bulk copy
+// (cp.async.bulk + mbarrier) into a two-stage shared-memory ring: the copy of the next views runs under the DMMAs of
+// the current ones.  Per-CTA partial results are summed in a fixed order by k_schur_reduce (no floating-point atomics).
+// Dynamic shared memory: 2 * kSyrkViews * 6 * ncp doubles + 2 mbarriers.
 constexpr int kSyrkViews = 4;
-__global__ void __launch_bounds__(kSyrkThreads) k_schur_syrk(ProblemShape S, DevLayout L, ViewBuffers V, int ns,
-                                                             int views_per_cta) {
+// block edge (in 8x8 tiles) and warps per CTA for a shared block of ns columns
+__host__ __device__ inline void syrk_shape(int ns, int* bt, int* warps) {
+    const int nt8 = (ns + 1 + 7) / 8;
+    const int b = nt8 <= 12 ? 3 : 5, nbk = (nt8 + b - 1) / b;   // at most 10 warps up to ns + 1 = 160, 15 warps above (the <5, 480> instance)
+    *bt = b; *warps = nbk * (nbk + 1) / 2;
+}
+// D(8x8) += A(8x4) B(4x8): lane l holds A[l >> 2][l & 3], B[l & 3][l >> 2] and D[l >> 2][2 (l & 3) + {0, 1}]
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+#if defined(__CUDACC__)
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+#else   // host build (tests/host_emul): the same contraction from shuffles
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int k = 0; k < 4; ++k) {
+        const double ak = __shfl_sync(0xffffffffu, a, g * 4 + k);
+        const double b0 = __shfl_sync(0xffffffffu, b, (2 * t) * 4 + k), b1 = __shfl_sync(0xffffffffu, b, (2 * t + 1) * 4 + k);
+        d0 = fma(ak, b0, d0); d1 = fma(ak, b1, d1);
+    }
+#endif
+}
+template <int BT, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_schur_syrk(ProblemShape S, ViewBuffers V, int ns, int views_per_cta) {
 #if defined(__CUDACC__)
     extern __shared__ __align__(128) unsigned char syrk_smem[];
 #else   // host build of this source (tests/host_emul): one CTA runs at a time
@@ -308,22 +328,21 @@ __global__ void __launch_bounds__(kSyrkThreads) k_schur_syrk(ProblemShape S, Dev
     const int stage_doubles = kSyrkViews * 6 * ncp;
     double* const ring = reinterpret_cast<double*>(syrk_smem);
     unsigned long long* const bar = reinterpret_cast<unsigned long long*>(syrk_smem + (size_t)2 * stage_doubles * 8);
-    const int na = ns + 1;
-    const int nt = (na + kSyrkTile - 1) / kSyrkTile;
-    int ti = -1, tj = -1;
-    {
-        int t = threadIdx.x, row = 0;
-        while (row < nt && t >= nt - row) { t -= nt - row; ++row; }
-        if (row < nt) { ti = row; tj = row + t; }
-    }
-    double acc[kSyrkTile][kSyrkTile];
+    const int na = ns + 1, nt8 = (na + 7) / 8, nbk = (nt8 + BT - 1) / BT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    int bi = 0, bj = 0;                                   // this warp's block of the upper triangle
+    { int w = warp; while (bi < nbk && w >= nbk - bi) { w -= nbk - bi; ++bi; } bj = bi + w; }
+    int ca[BT], cb[BT];                                   // column of lane's operand in each tile (tiles past the edge repeat the last one: computed, never stored)
 #pragma unroll
-    for (int i = 0; i < kSyrkTile; ++i)
+    for (int a = 0; a < BT; ++a) { ca[a] = min(bi * BT + a, nt8 - 1) * 8 + g; cb[a] = min(bj * BT + a, nt8 - 1) * 8 + g; }
+    double acc[BT][BT][2];
 #pragma unroll
-        for (int j = 0; j < kSyrkTile; ++j) acc[i][j] = 0.0;
+    for (int a = 0; a < BT; ++a)
+#pragma unroll
+        for (int b = 0; b < BT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
     const int v0 = blockIdx.x * views_per_cta, v1 = min(S.n_views, v0 + views_per_cta);
     const int n_steps = v1 > v0 ? (v1 - v0 + kSyrkViews - 1) / kSyrkViews : 0;
-    // stage `st` <- the rows of the views of step k (leader thread only)
+    // stage `k & 1` <- the rows of the views of step k (leader thread only)
     auto issue = [&](int k) {
         if (k >= n_steps) return;
         const int vb = v0 + k * kSyrkViews, nvb = min(kSyrkViews, v1 - vb);
@@ -354,6 +373,12 @@ __global__ void __launch_bounds__(kSyrkThreads) k_schur_syrk(ProblemShape S, Dev
     __syncthreads();
 #endif
     for (int k = 0; k < n_steps; ++k) {
+        const int nvb = min(kSyrkViews, v1 - (v0 + k * kSyrkViews));
+        double* const frow = ring + (k & 1) * stage_doubles;
+        if (nvb * 6 % 4 != 0) {   // a last, partial step of 1 or 3 views: zero the two rows that complete its last k-step (not covered by the copy)
+            for (int i = threadIdx.x; i < 2 * ncp; i += blockDim.x) frow[nvb * 6 * ncp + i] = 0.0;
+            __syncthreads();
+        }
 #if defined(__CUDACC__)
         {
             const unsigned mb = (unsigned)__cvta_generic_to_shared(&bar[k & 1]);
@@ -364,34 +389,45 @@ __global__ void __launch_bounds__(kSyrkThreads) k_schur_syrk(ProblemShape S, Dev
                 "@!p bra WAIT_%=;\n\t}" ::"r"(mb), "r"(parity) : "memory");
         }
 #endif
-        const int nvb = min(kSyrkViews, v1 - (v0 + k * kSyrkViews));
-        const double* frow = ring + (k & 1) * stage_doubles;
-        if (ti >= 0) {
-            for (int r = 0; r < nvb * 6; ++r) {
-                double fa[kSyrkTile], fb[kSyrkTile];
+        const int ksteps = (nvb * 6 + 3) / 4;
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const double* const row = frow + (4 * ks + t) * ncp;
+            double fa[BT], fb[BT];
 #pragma unroll
-                for (int i = 0; i < kSyrkTile; ++i) { fa[i] = frow[r * ncp + ti + nt * i]; fb[i] = frow[r * ncp + tj + nt * i]; }
+            for (int a = 0; a < BT; ++a) { fa[a] = row[ca[a]]; fb[a] = row[cb[a]]; }
 #pragma unroll
-                for (int i = 0; i < kSyrkTile; ++i)
+            for (int a = 0; a < BT; ++a)
 #pragma unroll
-                    for (int j = 0; j < kSyrkTile; ++j) acc[i][j] = fma(fa[i], fb[j], acc[i][j]);
-            }
+                for (int b = 0; b < BT; ++b) dmma884(acc[a][b][0], acc[a][b][1], fa[a], fb[b]);
         }
-        __syncthreads();                               // every thread is done with this stage
+        __syncthreads();                               // every warp is done with this stage
         if (threadIdx.x == 0) issue(k + 2);            // refill it
 #if !defined(__CUDACC__)
         __syncthreads();
 #endif
     }
-    if (ti >= 0) {
-        double* out = V.partialC + (int64_t)blockIdx.x * na * na;
-        for (int i = 0; i < kSyrkTile; ++i)
-            for (int j = 0; j < kSyrkTile; ++j) {
-                const int r = ti + nt * i, c = tj + nt * j;
-                if (r < na && c < na) { out[(int64_t)r * na + c] = acc[i][j]; if (ti != tj) out[(int64_t)c * na + r] = acc[i][j]; }
+    double* out = V.partialC + (int64_t)blockIdx.x * na * na;
+#pragma unroll
+    for (int a = 0; a < BT; ++a)
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+            const int ta = bi * BT + a, tb = bj * BT + b;
+            if (ta >= nt8 || tb >= nt8 || ta > tb) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = ta * 8 + g, c = tb * 8 + 2 * t + h;
+                if (r < na && c < na) { out[(int64_t)r * na + c] = acc[a][b][h]; if (ta != tb) out[(int64_t)c * na + r] = acc[a][b][h]; }
             }
-    }
+        }
 }
+
+#if !defined(__CUDACC__)
+// host build (tests/host_emul): the body a launcher runs per thread, with launch_schur's dispatch on the block edge
+inline void k_schur_syrk_any(int bt, ProblemShape S, ViewBuffers V, int ns, int views_per_cta) {
+    if (bt == 3) k_schur_syrk<3, 320>(S, V, ns, views_per_cta);
+    else k_schur_syrk<5, 320>(S, V, ns, views_per_cta);   // (the <5, 480> instance is the same source under another register cap)
+}
+#endif
 
 // The per-CTA partials of the SYRK summed in CTA order.  One thread per entry walking 444 partials is a chain of 444
 // dependent additions behind loads issued one at a time (113 us at ns = 114, round 2): four threads share an entry, each

@@ -76,7 +76,7 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
     simt::launch((unsigned)((S.n_views + 127) / 128), 128, [&] { k_view_chol(S, V, 1.0 / radius); });
     simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V); });
     const int per = (n_views + n_cta - 1) / n_cta, nt = (na + kSyrkTile - 1) / kSyrkTile, threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
-    simt::launch((unsigned)n_cta, (unsigned)threads, [&] { k_schur_syrk(S, L, V, ns, per); });
+    { int bt = 0, warps = 0; syrk_shape(ns, &bt, &warps); simt::launch((unsigned)n_cta, (unsigned)(32 * warps), [&] { k_schur_syrk_any(bt, S, V, ns, per); }); }
     simt::launch((unsigned)((na * na + kSchurReduceEntries - 1) / kSchurReduceEntries), 4 * kSchurReduceEntries, [&] { k_schur_reduce(V, n_cta, ns); });
     *fail = failed;
     std::memcpy(C, Cm.data(), sizeof(double) * ns * ns); std::memcpy(c, cv.data(), sizeof(double) * ns);
@@ -145,7 +145,7 @@ extern "C" int simt_k2_cov(int n_views, int n_cams, int PI, int64_t n_blk, const
     simt::launch((unsigned)((S.n_views + 127) / 128), 128, [&] { k_view_chol(S, V, 0.0); });
     simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V); });
     const int per = (n_views + n_cta - 1) / n_cta, nt = (na + kSyrkTile - 1) / kSyrkTile, threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
-    simt::launch((unsigned)n_cta, (unsigned)threads, [&] { k_schur_syrk(S, L, V, ns, per); });
+    { int bt = 0, warps = 0; syrk_shape(ns, &bt, &warps); simt::launch((unsigned)n_cta, (unsigned)(32 * warps), [&] { k_schur_syrk_any(bt, S, V, ns, per); }); }
     simt::launch((unsigned)((na * na + kSchurReduceEntries - 1) / kSchurReduceEntries), 4 * kSchurReduceEntries, [&] { k_schur_reduce(V, n_cta, ns); });
     if (failed) return 4;
     // host: W = (S Hss S - C)^-1, column by column (cal_refine_solve does the same with chol_host / chol_solve_host)

@@ -156,7 +156,7 @@ void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& 
     const int per = (S.n_views + n_cta - 1) / n_cta;
     const int nt = (ns + 1 + kSyrkTile - 1) / kSyrkTile;
     const int threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
-    simt::launch((unsigned)n_cta, (unsigned)threads, [&] { k_schur_syrk(S, L, V, ns, per); });
+    { int bt = 0, warps = 0; syrk_shape(ns, &bt, &warps); simt::launch((unsigned)n_cta, (unsigned)(32 * warps), [&] { k_schur_syrk_any(bt, S, V, ns, per); }); }
     const int na = ns + 1;
     simt::launch((unsigned)((na * na + kSchurReduceEntries - 1) / kSchurReduceEntries), 4 * kSchurReduceEntries, [&] { k_schur_reduce(V, n_cta, ns); });
 }

@@ -484,15 +484,17 @@ def k2_simt():
     return L
 
 
-def _k2_problem(seed, n_views, PI, radius, fixed_views=(0,), drop=0.15):
+def _k2_problem(seed, n_views, PI, radius, fixed_views=(0,), drop=0.15, n_cams=2):
     """A random normal-equation system with the block structure of the per-view kinds: per view a 6-dof pose block,
     two cameras (camera 0's pose is the gauge, camera 1's is free), PI free intrinsics per camera; every residual
     block couples ONE view with ONE camera.  Returns the per-block products K1's epilogue stores and the dense system."""
     rng = np.random.default_rng(seed)
-    n_cams = 2
-    cq = np.array([-1, PI], dtype=np.int32); ct = np.array([-1, PI + 3], dtype=np.int32); ci = np.array([0, PI + 6], dtype=np.int32)
-    ns = 2 * PI + 6
-    blocks = [(v, c) for v in range(n_views) for c in range(n_cams) if c == v % 2 or rng.random() > drop]
+    # shared columns: [intrinsics of camera 0 | pose (3 + 3) and intrinsics of camera 1 | ... of camera 2 | ...]
+    base = [PI + (c - 1) * (PI + 6) for c in range(n_cams)]
+    cq = np.array([-1] + base[1:], dtype=np.int32); ct = np.array([-1] + [b + 3 for b in base[1:]], dtype=np.int32)
+    ci = np.array([0] + [b + 6 for b in base[1:]], dtype=np.int32)
+    ns = n_cams * PI + 6 * (n_cams - 1)
+    blocks = [(v, c) for v in range(n_views) for c in range(n_cams) if c == v % n_cams or rng.random() > drop]
     nb = len(blocks)
     view_free = np.ones(n_views, dtype=np.int32); view_free[list(fixed_views)] = 0
     Hvv = np.zeros((21, nb)); gv = np.zeros((6, nb)); Evc = np.zeros((36, nb)); Evi = np.zeros((6 * max(PI, 1), nb))
@@ -526,7 +528,8 @@ def _k2_problem(seed, n_views, PI, radius, fixed_views=(0,), drop=0.15):
 
 
 @pytest.mark.parametrize("case", [dict(seed=1, n_views=37, PI=9, radius=1e4), dict(seed=2, n_views=90, PI=10, radius=3.0),
-                                  dict(seed=3, n_views=21, PI=0, radius=1e2), dict(seed=4, n_views=70, PI=11, radius=1e-2, fixed_views=(0, 5, 69))])
+                                  dict(seed=3, n_views=21, PI=0, radius=1e2), dict(seed=4, n_views=70, PI=11, radius=1e-2, fixed_views=(0, 5, 69)),
+                                  dict(seed=5, n_views=45, PI=9, radius=10.0, n_cams=7)])   # ns = 99: the 5 x 5-tile SYRK blocks, six warps, a one-view last step
 def test_k2_source_matches_a_dense_solve(k2_simt, case):
     """One LM iteration of the per-view kinds through the product's K2 kernels — Jacobi scaling, clamped LM diagonal,
     per-view Cholesky, Schur complement (tiled SYRK over several CTAs), back-substitution, the per-view terms of the model
