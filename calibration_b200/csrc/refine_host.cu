@@ -16,6 +16,7 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/calib_b200.h"
@@ -110,6 +111,53 @@ struct PinPool {
 };
 PinPool& pin_pool() { static PinPool* pool = new PinPool; return *pool; }     // small result blocks of the handles
 PinPool& host_pool() { static PinPool* pool = new PinPool; return *pool; }    // large staging blocks of callers (cal_host_borrow)
+
+// A large result (the dense covariance of the per-view kinds: 396 MB at 2 cameras x 1 000 views) into the CALLER's
+// pageable memory.  cudaMemcpy into pageable memory goes through the driver's small bounce buffers at a fraction of
+// the link rate (88 ms for those 396 MB); here the device copies 32 MB chunks into two page-locked blocks of the
+// process-wide pool at link rate while host threads move the previous chunk to its destination.
+cudaError_t download_large(double* dst, const double* src_dev, size_t n, cudaStream_t st) {
+    constexpr size_t kChunk = (size_t)4 << 20;   // doubles
+    if (n <= kChunk) {
+        cudaError_t e = cudaMemcpyAsync(dst, src_dev, n * sizeof(double), cudaMemcpyDeviceToHost, st);
+        return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+    }
+    struct Block { double* p = nullptr; size_t got = 0; cudaEvent_t ev = nullptr; ~Block() { if (ev) cudaEventDestroy(ev); host_pool().put(p, got); } } blk[2];
+    for (Block& b : blk) {
+        b.p = host_pool().get(kChunk, &b.got);
+        if (!b.p) return cudaErrorMemoryAllocation;
+        cudaError_t e = cudaEventCreateWithFlags(&b.ev, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int n_thr = (int)std::min(8u, hw);
+    auto scatter = [&](double* to, const double* from, size_t cnt) {
+        std::vector<std::thread> pool;
+        const size_t per = (cnt + n_thr - 1) / n_thr;
+        for (int t = 1; t < n_thr; ++t) {
+            const size_t a = std::min(cnt, per * t), b = std::min(cnt, per * (t + 1));
+            if (b > a) pool.emplace_back([=] { std::memcpy(to + a, from + a, (b - a) * sizeof(double)); });
+        }
+        std::memcpy(to, from, std::min(cnt, per) * sizeof(double));
+        for (std::thread& th : pool) th.join();
+    };
+    const size_t n_chunks = (n + kChunk - 1) / kChunk;
+    for (size_t c = 0; c <= n_chunks; ++c) {
+        if (c < n_chunks) {
+            const size_t off = c * kChunk, cnt = std::min(kChunk, n - off);
+            cudaError_t e = cudaMemcpyAsync(blk[c & 1].p, src_dev + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaEventRecord(blk[c & 1].ev, st);
+            if (e != cudaSuccess) return e;
+        }
+        if (c > 0) {   // chunk c - 1 has landed (chunk c is on its way): move it out
+            const size_t off = (c - 1) * kChunk, cnt = std::min(kChunk, n - off);
+            cudaError_t e = cudaEventSynchronize(blk[(c - 1) & 1].ev);
+            if (e != cudaSuccess) return e;
+            scatter(dst + off, blk[(c - 1) & 1].p, cnt);
+        }
+    }
+    return cudaSuccess;
+}
 
 }  // namespace
 
@@ -1081,7 +1129,7 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
             CUDA_TRY(cudaMemsetAsync(dG, 0, sizeof(double) * nv * 6 * ns, h.st));
             launch_cov_views(S, h.L, V, h.B.x, ns, dW, dZ, dG, dAinv, dcov, na, h.st); h.launches += 2;
             std::vector<double> Gh((size_t)nv * 6 * ns), sph((size_t)nv * 6);
-            CUDA_TRY(cudaMemcpyAsync(cov, dcov, sizeof(double) * na * na, cudaMemcpyDeviceToHost, h.st));
+            CUDA_TRY(download_large(cov, dcov, (size_t)na * na, h.st));
             CUDA_TRY(cudaMemcpyAsync(Gh.data(), dG, Gh.size() * sizeof(double), cudaMemcpyDeviceToHost, h.st));
             CUDA_TRY(cudaMemcpyAsync(sph.data(), V.sp, sph.size() * sizeof(double), cudaMemcpyDeviceToHost, h.st));
             CUDA_TRY(cudaStreamSynchronize(h.st));

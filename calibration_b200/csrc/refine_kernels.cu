@@ -163,11 +163,7 @@ void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& 
                   double radius, cudaStream_t st) {
     if (S.n_views == 0) return;
     k_view_chol<<<(unsigned)((S.n_views + 127) / 128), 128, 0, st>>>(S, V, 1.0 / radius);                                                             // one thread per view
-    if (S.n_cams <= kFactorSlots) {                                                                                                                   // a group of views per CTA
-        const int vpg = kFactorSlots / S.n_cams;
-        k_schur_factor<<<(unsigned)((S.n_views + vpg - 1) / vpg), kFactorThreads, 0, st>>>(S, L, B, V, vpg);
-    } else
-        k_schur_factor_wide<<<(unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, 0, st>>>(S, L, B, V);     // one warp per view
+    k_schur_factor<<<(unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, 0, st>>>(S, L, B, V);              // one warp per view
     int bt = 0, warps = 0;
     syrk_shape(ns, &bt, &warps);
     const int threads = 32 * warps;                                           // one warp per block of bt x bt tiles of the upper triangle

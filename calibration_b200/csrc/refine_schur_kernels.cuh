@@ -62,8 +62,12 @@ __global__ void k_view_scale(ProblemShape S, ViewBuffers V, int compute_scale) {
 // L_v and the per-camera column tables are staged in shared memory, the lanes walk the view's columns 32 at a time
 // (two trips' gathers in flight), forward-substitute with broadcast reads of L_v and store F into the dense rows with
 // consecutive lanes on consecutive columns — full-line writes; the reads of E_b ([entry][n_blk]) are 8-byte gathers
-// whose sectors are shared by the lanes of the neighbouring blocks.  No factorisation in this kernel: about 50
-// registers, every warp slot of the SM in use.
+// whose sectors are shared by the lanes of the neighbouring blocks.  No factorisation in this kernel: 64 registers,
+// 32 warps per SM.  What bounds it now is the L1 data pipe (70 % of its wavefront rate: a warp-wide gather touches 11
+// cache lines) and instruction issue, at 2.7 TB/s of DRAM traffic.  A variant that transposes E through shared memory
+// (one plane per warp-wide load, a group of 32 / n_cams views per CTA) was measured on the B200 and is 40 % SLOWER
+// (588 against 418 us at 100 k views x 8 cameras): the staging phases and their barriers cost more instructions than
+// the coalesced loads save.
 __global__ void __launch_bounds__(128) k_view_chol(ProblemShape S, ViewBuffers V, double inv_radius) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= S.n_views || !V.view_free[v]) return;
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(128) k_view_chol(ProblemShape S, ViewBuffers V
 
 constexpr int kFactorThreads = 256;
 constexpr int kFactorCamTable = 64;    // cameras whose column tables fit the shared-memory copy (more: read from global memory)
-__global__ void __launch_bounds__(kFactorThreads) k_schur_factor_wide(ProblemShape S, DevLayout L, EvalBuffers B, ViewBuffers V) {
+__global__ void __launch_bounds__(kFactorThreads) k_schur_factor(ProblemShape S, DevLayout L, EvalBuffers B, ViewBuffers V) {
     __shared__ double sL[kFactorThreads / 32][28];                    // per warp: L_v (21, packed rows) | 1 / diag (6)
     __shared__ double s_scale[kSyrkMaxN];                             // s_shared
     __shared__ int s_col[3][kFactorCamTable];                         // cam_col_q / _t / _i
@@ -143,82 +147,6 @@ __global__ void __launch_bounds__(kFactorThreads) k_schur_factor_wide(ProblemSha
 #pragma unroll
             for (int i = 0; i < 6; ++i) Fv[i * V.ncp + col[u]] = e[u][i];
         }
-    }
-}
-
-// k_schur_factor — the same forward substitution for rigs of at most kFactorSlots cameras (every rig the Schur path's width
-// limit admits with free intrinsics), with the coupling blocks TRANSPOSED THROUGH SHARED MEMORY.  K1 stores E as planes
-// [entry][n_blk] (its lanes are blocks); k_schur_factor_wide's lanes, one per (block, column), gather one double from
-// each of fifteen planes per load: 11 sectors in 11 cache lines per request, and the L1 data pipe — not DRAM — bounds
-// the kernel (70 % of its wavefront rate at 2.7 TB/s, round-2 capture).  Here a CTA takes a GROUP of
-// kFactorSlots / n_cams consecutive views (at most kFactorSlots residual blocks): each warp-wide load reads ONE plane at
-// the group's blocks — consecutive addresses in the reference's view-major block order, two cache lines per request —
-// into s_E[plane][slot]; then the threads take the group's (block, column) items from shared memory (row pitch 33:
-// the lanes of an item walk the planes, conflict-free) and store F with consecutive lanes on consecutive columns.
-constexpr int kFactorSlots = 32;
-constexpr int kFactorMaxPlanes = 6 * (6 + 12);
-__global__ void __launch_bounds__(kFactorThreads) k_schur_factor(ProblemShape S, DevLayout L, EvalBuffers B, ViewBuffers V, int views_per_group) {
-    __shared__ double s_E[kFactorMaxPlanes][kFactorSlots + 1];
-    __shared__ double s_L[kFactorSlots][28];                          // per view of the group: L_v (21, packed rows) | 1 / diag (6)
-    __shared__ double s_sp[kFactorSlots][6];
-    __shared__ double s_scale[kSyrkMaxN];
-    __shared__ int s_col[3][kFactorSlots];
-    __shared__ int s_off[kFactorSlots + 1], s_b[kFactorSlots], s_cam[kFactorSlots], s_lv[kFactorSlots], s_use[kFactorSlots];
-    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    const int v0 = blockIdx.x * views_per_group, G = min(views_per_group, S.n_views - v0);
-    const int k0 = V.view_blk_off[v0];
-    if (tid <= G) s_off[tid] = V.view_blk_off[v0 + tid] - k0;
-    for (int i = tid; i < V.ns; i += kFactorThreads) s_scale[i] = V.s_shared[i];
-    if (tid < S.n_cams) { s_col[0][tid] = V.cam_col_q[tid]; s_col[1][tid] = V.cam_col_t[tid]; s_col[2][tid] = V.cam_col_i[tid]; }
-    for (int idx = tid; idx < G * 33; idx += kFactorThreads) {       // L_v, its reciprocal diagonal and the Jacobi scale of the group's views
-        const int lv = idx / 33, e = idx - lv * 33, v = v0 + lv;
-        const bool usable = V.view_free[v] && V.view_blk_off[v + 1] > V.view_blk_off[v];
-        if (e == 0) s_use[lv] = usable;
-        if (!usable) continue;                                       // (never factorised: nothing valid to read)
-        if (e < 21) { const int ri = (e >= 1) + (e >= 3) + (e >= 6) + (e >= 10) + (e >= 15), rj = e - ri * (ri + 1) / 2; s_L[lv][e] = V.Lp[(int64_t)v * 36 + 6 * ri + rj]; }
-        else if (e < 27) s_L[lv][e] = V.Linv[(int64_t)v * 6 + e - 21];
-        else s_sp[lv][e - 27] = V.sp[(int64_t)v * 6 + e - 27];
-    }
-    __syncthreads();
-    const int nslots = s_off[G];
-    if (nslots == 0) return;                                          // (uniform)
-    if (tid < nslots) {
-        const int b = V.view_blk_idx[k0 + tid];
-        s_b[tid] = b; s_cam[tid] = L.blk_cam[b];
-        int lv = 0; while (s_off[lv + 1] <= tid) ++lv;
-        s_lv[tid] = lv;
-    }
-    __syncthreads();
-    const int ncb = 6 + S.PI, n_planes = 6 * ncb;
-    {   // plane p = i * ncb + j  <-  E_b[i][j] at the group's blocks
-        const int64_t b = lane < nslots ? s_b[lane] : s_b[0];
-#pragma unroll 4
-        for (int p = w; p < n_planes; p += kFactorThreads / 32) {
-            const int i = p / ncb, j = p - i * ncb;
-            const double* src = j < 6 ? B.blk_Evc + (int64_t)(6 * i + j) * L.n_blk : B.blk_Evi + (int64_t)(S.PI * i + j - 6) * L.n_blk;
-            if (lane < nslots) s_E[p][lane] = src[b];
-        }
-    }
-    __syncthreads();
-    for (int it = tid; it < nslots * ncb; it += kFactorThreads) {
-        const int slot = it / ncb, j = it - slot * ncb, lv = s_lv[slot];
-        if (!s_use[lv]) continue;
-        const int base = s_col[j < 3 ? 0 : (j < 6 ? 1 : 2)][s_cam[slot]];
-        if (base < 0) continue;
-        const int col = base + (j < 3 ? j : (j < 6 ? j - 3 : j - 6));
-        const double sc = s_scale[col];
-        const double* const Lw = s_L[lv];
-        double e[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            double s = s_E[i * ncb + j][slot] * s_sp[lv][i] * sc;
-#pragma unroll
-            for (int kk = 0; kk < i; ++kk) s -= Lw[i * (i + 1) / 2 + kk] * e[kk];
-            e[i] = s * Lw[21 + i];
-        }
-        double* const Fv = V.Fd + (int64_t)(v0 + lv) * 6 * V.ncp;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) Fv[i * V.ncp + col] = e[i];
     }
 }
 

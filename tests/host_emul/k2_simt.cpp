@@ -74,8 +74,7 @@ extern "C" int simt_k2_step(int n_views, int n_cams, int PI, int64_t n_blk, cons
     simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 0); });
     // launch_schur
     simt::launch((unsigned)((S.n_views + 127) / 128), 128, [&] { k_view_chol(S, V, 1.0 / radius); });
-    if (S.n_cams <= kFactorSlots) { const int vpg = kFactorSlots / S.n_cams; simt::launch((unsigned)((S.n_views + vpg - 1) / vpg), kFactorThreads, [&] { k_schur_factor(S, L, B, V, vpg); }); }
-    else simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor_wide(S, L, B, V); });
+    simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V); });
     const int per = (n_views + n_cta - 1) / n_cta, nt = (na + kSyrkTile - 1) / kSyrkTile, threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
     { int bt = 0, warps = 0; syrk_shape(ns, &bt, &warps); simt::launch((unsigned)n_cta, (unsigned)(32 * warps), [&] { k_schur_syrk_any(bt, S, V, ns, per); }); }
     simt::launch((unsigned)((na * na + kSchurReduceEntries - 1) / kSchurReduceEntries), 4 * kSchurReduceEntries, [&] { k_schur_reduce(V, n_cta, ns); });
@@ -144,8 +143,7 @@ extern "C" int simt_k2_cov(int n_views, int n_cams, int PI, int64_t n_blk, const
     simt::launch((unsigned)((n_views * 6 + 127) / 128), 128, [&] { k_view_scale(S, V, 1); });
     // launch_schur(radius = infinity): undamped factors L_v and F_b = L_v^-1 E_b stay in V
     simt::launch((unsigned)((S.n_views + 127) / 128), 128, [&] { k_view_chol(S, V, 0.0); });
-    if (S.n_cams <= kFactorSlots) { const int vpg = kFactorSlots / S.n_cams; simt::launch((unsigned)((S.n_views + vpg - 1) / vpg), kFactorThreads, [&] { k_schur_factor(S, L, B, V, vpg); }); }
-    else simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor_wide(S, L, B, V); });
+    simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V); });
     const int per = (n_views + n_cta - 1) / n_cta, nt = (na + kSyrkTile - 1) / kSyrkTile, threads = (nt * (nt + 1) / 2 + 31) / 32 * 32;
     { int bt = 0, warps = 0; syrk_shape(ns, &bt, &warps); simt::launch((unsigned)n_cta, (unsigned)(32 * warps), [&] { k_schur_syrk_any(bt, S, V, ns, per); }); }
     simt::launch((unsigned)((na * na + kSchurReduceEntries - 1) / kSchurReduceEntries), 4 * kSchurReduceEntries, [&] { k_schur_reduce(V, n_cta, ns); });

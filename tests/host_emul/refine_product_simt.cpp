@@ -151,8 +151,7 @@ int schur_num_ctas(int n_views) { return n_views < 64 ? 1 : (n_views < 444 * 16 
 void launch_schur(const ProblemShape& S, const DevLayout& L, const EvalBuffers& B, const ViewBuffers& V, int ns, double radius, cudaStream_t) {
     if (S.n_views == 0) return;
     simt::launch((unsigned)((S.n_views + 127) / 128), 128, [&] { k_view_chol(S, V, 1.0 / radius); });
-    if (S.n_cams <= kFactorSlots) { const int vpg = kFactorSlots / S.n_cams; simt::launch((unsigned)((S.n_views + vpg - 1) / vpg), kFactorThreads, [&] { k_schur_factor(S, L, B, V, vpg); }); }
-    else simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor_wide(S, L, B, V); });
+    simt::launch((unsigned)(((int64_t)S.n_views * 32 + kFactorThreads - 1) / kFactorThreads), kFactorThreads, [&] { k_schur_factor(S, L, B, V); });
     const int n_cta = schur_num_ctas(S.n_views);
     const int per = (S.n_views + n_cta - 1) / n_cta;
     const int nt = (ns + 1 + kSyrkTile - 1) / kSyrkTile;

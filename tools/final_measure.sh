@@ -4,8 +4,7 @@ for w in c1 c3 c4 c4-axxb c2; do python bench.py --workload $w > gpurun_out/r2_b
 python bench.py > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err || tail -5 gpurun_out/r2_bench_n1.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_reference_arm.json 2> gpurun_out/r2_ref.err
 { tools/ubench_fp64_occ; tools/ubench_fp64_mix; tools/ubench_k1_exchange; } > gpurun_out/r2_ubench_fp64.txt 2>&1
+tools/ubench_dmma > gpurun_out/r2_ubench_dmma.txt 2>&1
 python tools/solve_probe.py c1 c3 c4 > gpurun_out/r2_solve_probe.jsonl 2>/dev/null
-CALIB_B200_BUILD_DIR=_build_base python tools/solve_probe.py c1 c3 c4 > gpurun_out/r2_solve_probe_round1_build.jsonl 2>/dev/null
-python tools/extr_probe.py 8 100000 2>/dev/null | tail -1 > gpurun_out/r2_extr_probe.txt
-CALIB_B200_BUILD_DIR=_build_base python tools/extr_probe.py 8 100000 2>/dev/null | tail -1 > gpurun_out/r2_extr_probe_round1_build.txt
-tail -2 gpurun_out/r2_solve_probe.jsonl gpurun_out/r2_extr_probe.txt gpurun_out/r2_extr_probe_round1_build.txt
+for i in 1 2 3; do python tools/extr_probe.py 8 100000 2>/dev/null | tail -1; done > gpurun_out/r2_extr_probe.txt
+tail -n 3 gpurun_out/r2_solve_probe.jsonl gpurun_out/r2_extr_probe.txt
