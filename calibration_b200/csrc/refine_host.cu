@@ -186,6 +186,13 @@ struct cal_refine_handle : calk::HostModel {
     //   [16, 16 + ns) y of the reduced solve | then cam_sums [n_cams * NV]
     double* pin = nullptr; size_t pin_doubles = 0;
     double* dSm = nullptr; double* dgss = nullptr; int32_t* dinfo = nullptr;   // reduced system of one LM iteration (device)
+    // second set of the per-block products and per-view blocks a Jacobian pass writes (per-view kinds): the speculative pass
+    // at an LM candidate fills it while the accepted point's set stays intact (swap_view_sets)
+    double *alt_Hvv = nullptr, *alt_gv = nullptr, *alt_Evc = nullptr, *alt_Evi = nullptr, *alt_Hpp = nullptr, *alt_gp = nullptr;
+    void swap_view_sets() {
+        std::swap(B.blk_Hvv, alt_Hvv); std::swap(B.blk_gv, alt_gv); std::swap(B.blk_Evc, alt_Evc); std::swap(B.blk_Evi, alt_Evi);
+        std::swap(V.Hpp, alt_Hpp); std::swap(V.gp, alt_gp);
+    }
     double* pin_red(int k) const { return pin + 4 * k; }
     int32_t* pin_flags() const { return reinterpret_cast<int32_t*>(pin + 12); }
     double* pin_y() const { return pin + 16; }
@@ -414,7 +421,7 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         size_t bytes = (size_t)slices * 128 * 8 + (size_t)ntiles * 12 + (size_t)nseg * (12 + 8 * seg_doubles) +
                        (size_t)nblk * (4 * 4 + 8 + 8 * (36 + 2 + nbr + 12)) + (size_t)h.n_amb * 16 + (1u << 20);
         if (fused) bytes += (size_t)ntiles * nvt * 8 + (size_t)(ntiles / 32 + S.n_cams + 1) * (nvt * 8 + 64);
-        if (S.n_views > 0) bytes += (size_t)nblk * 8 * (21 + 6 + 36 + 6 * std::max(S.PI, 1) + 6 * (6 + S.PI)) + (size_t)S.n_views * 8 * 120 +
+        if (S.n_views > 0) bytes += (size_t)nblk * 8 * (2 * (21 + 6 + 36 + 6 * std::max(S.PI, 1)) + 6 * (6 + S.PI)) + (size_t)S.n_views * 8 * (120 + 42) + 8 * 256 +
                                     (size_t)schur_num_ctas(S.n_views) * (h.ns + 1) * (h.ns + 1) * 8 + (size_t)h.ns * h.ns * 8 + (1u << 20);
         bytes += 256 * 64;  // alignment slack
         CUDA_TRY(h.arena_reserve(bytes));
@@ -518,6 +525,11 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         CUDA_TRY(cudaMemsetAsync(B.blk_Hvv, 0, sizeof(double) * 21 * nblk, us)); CUDA_TRY(cudaMemsetAsync(B.blk_gv, 0, sizeof(double) * 6 * nblk, us));
         CUDA_TRY(cudaMemsetAsync(B.blk_Evc, 0, sizeof(double) * 36 * nblk, us));
         CUDA_TRY(cudaMemsetAsync(B.blk_Evi, 0, sizeof(double) * 6 * std::max(S.PI, 1) * nblk, us));
+        CUDA_TRY(h.alloc(&h.alt_Hvv, (size_t)21 * nblk)); CUDA_TRY(h.alloc(&h.alt_gv, (size_t)6 * nblk));
+        CUDA_TRY(h.alloc(&h.alt_Evc, (size_t)36 * nblk)); CUDA_TRY(h.alloc(&h.alt_Evi, (size_t)6 * std::max(S.PI, 1) * nblk));
+        CUDA_TRY(cudaMemsetAsync(h.alt_Hvv, 0, sizeof(double) * 21 * nblk, us)); CUDA_TRY(cudaMemsetAsync(h.alt_gv, 0, sizeof(double) * 6 * nblk, us));
+        CUDA_TRY(cudaMemsetAsync(h.alt_Evc, 0, sizeof(double) * 36 * nblk, us));
+        CUDA_TRY(cudaMemsetAsync(h.alt_Evi, 0, sizeof(double) * 6 * std::max(S.PI, 1) * nblk, us));
         // view CSR over device blocks
         ViewBuffers& V = h.V;
         std::vector<int32_t>& off = h.view_blk_off_host; std::vector<int32_t>& idx = h.view_blk_idx_host;
@@ -551,6 +563,7 @@ extern "C" cal_status cal_refine_create(const cal_problem_desc* dp, int device, 
         CUDA_TRY(upload(V.view_blk_off, off, us)); CUDA_TRY(upload(V.view_blk_idx, idx, us)); CUDA_TRY(upload(V.view_free, vfree, us));
         CUDA_TRY(upload(V.cam_col_q, cq, us)); CUDA_TRY(upload(V.cam_col_t, ct, us)); CUDA_TRY(upload(V.cam_col_i, ci, us));
         CUDA_TRY(h.alloc(&V.Hpp, (size_t)nv * 36)); CUDA_TRY(h.alloc(&V.gp, (size_t)nv * 6)); CUDA_TRY(h.alloc(&V.sp, (size_t)nv * 6));
+        CUDA_TRY(h.alloc(&h.alt_Hpp, (size_t)nv * 36)); CUDA_TRY(h.alloc(&h.alt_gp, (size_t)nv * 6));
         CUDA_TRY(h.alloc(&V.dp, (size_t)nv * 6)); CUDA_TRY(h.alloc(&V.Lp, (size_t)nv * 36)); CUDA_TRY(h.alloc(&V.Linv, (size_t)nv * 6)); CUDA_TRY(h.alloc(&V.view_f, (size_t)nv * 6));
         V.ns = ns; V.ncp = (ns + 1 + kSyrkTile - 1) / kSyrkTile * kSyrkTile;
         CUDA_TRY(h.alloc(&V.Fd, (size_t)nv * 6 * V.ncp)); CUDA_TRY(h.alloc(&V.delta_p, (size_t)nv * 6));
@@ -907,12 +920,25 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
     // aside and comes back when the candidate is rejected or the solve stops on it; after a rejection the next
     // candidate is evaluated cost-only (rejections cluster).  Counters keep the reference's meaning: one cost
     // evaluation per candidate, one Jacobian evaluation per accepted point.
-    bool speculate = !views && getenv("CALIB_B200_NO_SPECULATION") == nullptr;
+    // Per-view kinds: the pass also writes the per-block products and the per-view blocks on the device; the candidate's go
+    // to the handle's second set (swap_view_sets), so the accepted point's stay intact for a rejected candidate's next solve.
+    const bool may_speculate = getenv("CALIB_B200_NO_SPECULATION") == nullptr;
+    bool speculate = may_speculate;
     bool spec_live = false;                       // the host mirrors describe the candidate, not the accepted point
     std::vector<double> keep_H, keep_g, keep_sums; double keep_cost = 0;
+    auto sync_view_sets = [&]() {                 // the loop's copies of the buffer tables follow the handle's
+        B.blk_Hvv = h.B.blk_Hvv; B.blk_gv = h.B.blk_gv; B.blk_Evc = h.B.blk_Evc; B.blk_Evi = h.B.blk_Evi; V.Hpp = h.V.Hpp; V.gp = h.V.gp;
+    };
+    auto spec_pass = [&](double* xdev, const double* xhost) -> cal_status {   // full fused pass at a candidate
+        keep_H = h.Hss; keep_g = h.gs; keep_sums = h.cam_sums; keep_cost = h.cost;
+        if (views) { h.swap_view_sets(); sync_view_sets(); }
+        spec_live = true;
+        return device_pass(h, xdev, true, xhost, views);
+    };
     auto spec_restore = [&]() {
         if (!spec_live) return;
         h.Hss.swap(keep_H); h.gs.swap(keep_g); h.cam_sums.swap(keep_sums); h.cost = keep_cost; spec_live = false;
+        if (views) { h.swap_view_sets(); sync_view_sets(); }
     };
     for (int i = 0; i < ns; ++i) s[i] = 1.0 / (1.0 + std::sqrt(h.Hss[(size_t)i * ns + i]));  // jacobi_scaling, once
     if (views) {
@@ -1023,9 +1049,8 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
                 if (cal_status st = make_candidate(t)) return st;
                 double c;
                 if (speculate && ls == 0) {   // the full step: almost always accepted, so take the Jacobian along
-                    keep_H = h.Hss; keep_g = h.gs; keep_sums = h.cam_sums; keep_cost = h.cost;
-                    if (cal_status st = device_pass(h, xc, true, xp.data())) return st;
-                    spec_live = true; ++cev;
+                    if (cal_status st = spec_pass(xc, xp.data())) return st;
+                    ++cev;
                     c = std::isfinite(h.cost) ? h.cost : std::numeric_limits<double>::max();
                 } else if (cal_status st = eval_cost_at(xc, xp.data(), c)) return st;
                 if (cal_status st = finish_candidate(step_norm2)) return st;
@@ -1041,9 +1066,8 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
         if (!have_cand) {
             if (cal_status st = make_candidate(t)) return st;
             if (speculate && !h.constrained) {
-                keep_H = h.Hss; keep_g = h.gs; keep_sums = h.cam_sums; keep_cost = h.cost;
-                if (cal_status st = device_pass(h, xc, true, xp.data())) return st;
-                spec_live = true; ++cev;
+                if (cal_status st = spec_pass(xc, xp.data())) return st;
+                ++cev;
                 cand_cost = std::isfinite(h.cost) ? h.cost : std::numeric_limits<double>::max();
             } else if (cal_status st = eval_cost_at(xc, xp.data(), cand_cost)) return st;
             if (cal_status st = finish_candidate(step_norm2)) return st;
@@ -1058,7 +1082,7 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
             for (int i = 0; i < n_shared_amb; ++i) x[i] = xp[i];
             if (spec_live) spec_live = false;   // the candidate's system IS the new point's
             else if (cal_status st = device_pass(h, xd, true, x.data(), true)) return st;
-            speculate = !views && getenv("CALIB_B200_NO_SPECULATION") == nullptr;
+            speculate = may_speculate;
             ++jev; cost = h.cost;
             if (cal_status st = norms(x_norm, gmax)) return st;
             radius = std::min(max_radius, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3)));

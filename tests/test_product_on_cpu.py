@@ -143,3 +143,25 @@ def test_every_parameter_block_frozen(product_on_cpu, monkeypatch):
     assert r.success and r.iterations == 0 == r_o.iterations
     assert abs(r.final_cost - r_o.final_cost) <= 1e-12 * r_o.final_cost and r.final_cost == r.initial_cost
     assert np.array_equal(x, x0)
+
+
+@pytest.mark.parametrize("name", ["intrinsics_c1_shape", "extrinsics_stereo"])
+def test_speculative_pass_of_the_per_view_kinds_changes_nothing(product_on_cpu, monkeypatch, name):
+    """An LM candidate of the per-view kinds is evaluated with the full fused pass into the handle's second set of
+    per-block / per-view buffers (one pass per accepted step instead of a residual-only pass plus a Jacobian pass).  The
+    solve must take the same steps as with CALIB_B200_NO_SPECULATION: same counters (the reference's meaning, ceresutils.h
+    :27-43 — one cost evaluation per candidate, one Jacobian evaluation per accepted point), same parameters and
+    covariance, fewer launches."""
+    monkeypatch.setenv("CALIB_B200_FUSED", "1")
+    prob, x0, _ = CASES[name]()
+    out = []
+    for nospec in (False, True):
+        if nospec: monkeypatch.setenv("CALIB_B200_NO_SPECULATION", "1")
+        h = product_on_cpu.RefineHandle(prob)
+        x, r, cov = h.solve(x0)
+        out.append((x, (r.iterations, r.num_jac_evals, r.num_cost_evals), r.final_cost, cov, h.launch_count()))
+        h.close()
+    (xa, ca, fa, cova, la), (xb, cb, fb, covb, lb) = out
+    assert ca == cb and la < lb
+    assert np.abs(xa - xb).max() <= 1e-12 * np.abs(xb).max() and abs(fa - fb) <= 1e-12 * fb
+    assert np.abs(cova - covb).max() <= 1e-9 * np.abs(covb).max()
