@@ -117,11 +117,12 @@ PinPool& host_pool() { static PinPool* pool = new PinPool; return *pool; }    //
 // the link rate (88 ms for those 396 MB); here the device copies 32 MB chunks into two page-locked blocks of the
 // process-wide pool at link rate while host threads move the previous chunk to its destination.
 cudaError_t download_large(double* dst, const double* src_dev, size_t n, cudaStream_t st) {
-    constexpr size_t kChunk = (size_t)4 << 20;   // doubles
-    if (n <= kChunk) {
+    if (n <= ((size_t)64 << 10)) {               // small: one plain copy
         cudaError_t e = cudaMemcpyAsync(dst, src_dev, n * sizeof(double), cudaMemcpyDeviceToHost, st);
         return e != cudaSuccess ? e : cudaStreamSynchronize(st);
     }
+    // chunks of 32 MB for the big matrices, a quarter of the payload (at least 2 MB) for the 10 MB-class vectors
+    const size_t kChunk = std::min<size_t>((size_t)4 << 20, std::max<size_t>((size_t)256 << 10, (n + 3) / 4));
     struct Block { double* p = nullptr; size_t got = 0; cudaEvent_t ev = nullptr; ~Block() { if (ev) cudaEventDestroy(ev); host_pool().put(p, got); } } blk[2];
     for (Block& b : blk) {
         b.p = host_pool().get(kChunk, &b.got);
@@ -130,7 +131,7 @@ cudaError_t download_large(double* dst, const double* src_dev, size_t n, cudaStr
         if (e != cudaSuccess) return e;
     }
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int n_thr = (int)std::min(8u, hw);
+    const int n_thr = (int)std::max<size_t>(1, std::min<size_t>(std::min(8u, hw), kChunk / ((size_t)512 << 10)));   // at least 4 MB per copy thread
     auto scatter = [&](double* to, const double* from, size_t cnt) {
         std::vector<std::thread> pool;
         const size_t per = (cnt + n_thr - 1) / n_thr;
@@ -853,7 +854,7 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
     }
     double* xd = h.B.x; double* xc = h.V.x_cand;
     CUDA_TRY(cudaMemcpyAsync(xd, x.data(), sizeof(double) * na, cudaMemcpyHostToDevice, h.st));
-    CUDA_TRY(cudaMemcpyAsync(xc, x.data(), sizeof(double) * na, cudaMemcpyHostToDevice, h.st));
+    CUDA_TRY(cudaMemcpyAsync(xc, xd, sizeof(double) * na, cudaMemcpyDeviceToDevice, h.st));   // (not a second trip over PCIe: 11 MB at 100 k views)
     ViewBuffers V = h.V;
     EvalBuffers B = h.B;
     std::vector<double> s(ns, 1.0), diag(ns), y(ns), step(ns), delta(ns), gss(ns), Cs((size_t)ns * ns), cs(ns), Sm((size_t)ns * ns);
@@ -1098,8 +1099,7 @@ extern "C" cal_status cal_refine_solve(cal_refine_handle* hp, const cal_optim_op
     if (trace) std::fprintf(stderr, "[calib_b200] solve: LM loop %8.2f ms (%d iterations, %d Jacobian + %d cost evaluations, %lld launches)\n",
                             std::chrono::duration<double, std::milli>(t_lm_end - t_solve_start).count(), iter, jev, cev, (long long)h.launches);
     // download the final parameters (last accepted point)
-    CUDA_TRY(cudaMemcpyAsync(x_inout, xd, sizeof(double) * na, cudaMemcpyDeviceToHost, h.st));
-    CUDA_TRY(cudaStreamSynchronize(h.st));
+    CUDA_TRY(download_large(x_inout, xd, (size_t)na, h.st));
     if (xd != h.B.x) {  // keep the handle's buffers in their canonical roles
         CUDA_TRY(cudaMemcpyAsync(h.B.x, xd, sizeof(double) * na, cudaMemcpyDeviceToDevice, h.st));
         CUDA_TRY(cudaStreamSynchronize(h.st));
