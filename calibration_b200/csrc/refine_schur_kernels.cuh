@@ -394,6 +394,8 @@ __global__ void __launch_bounds__(MAXT) k_schur_syrk(ProblemShape S, ViewBuffers
         }
 #endif
         const int ksteps = (nvb * 6 + 3) / 4;
+        // (Loading the fragments of k-step ks + 1 before the DMMAs of k-step ks — explicit double buffering — was measured on the
+        // B200: 0.358 against 0.337 ms; ptxas already spreads the ten loads among the DMMAs of the step.)
         if (bi != bj) {
             for (int ks = 0; ks < ksteps; ++ks) {
                 const double* const row = frow + (4 * ks + t) * ncp;
