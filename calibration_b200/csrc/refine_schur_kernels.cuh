@@ -67,7 +67,9 @@ __global__ void k_view_scale(ProblemShape S, ViewBuffers V, int compute_scale) {
 // cache lines) and instruction issue, at 2.7 TB/s of DRAM traffic.  A variant that transposes E through shared memory
 // (one plane per warp-wide load, a group of 32 / n_cams views per CTA) was measured on the B200 and is 40 % SLOWER
 // (588 against 418 us at 100 k views x 8 cameras): the staging phases and their barriers cost more instructions than
-// the coalesced loads save.
+// the coalesced loads save.  So is a block-fastest item order (the lanes of one column read consecutive doubles of one
+// plane: four planes per warp-wide load instead of fifteen) with the rows assembled in a per-warp shared-memory tile and
+// written out whole: 632 us.
 __global__ void __launch_bounds__(128) k_view_chol(ProblemShape S, ViewBuffers V, double inv_radius) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= S.n_views || !V.view_free[v]) return;
