@@ -62,14 +62,15 @@ __global__ void k_view_scale(ProblemShape S, ViewBuffers V, int compute_scale) {
 // L_v and the per-camera column tables are staged in shared memory, the lanes walk the view's columns 32 at a time
 // (two trips' gathers in flight), forward-substitute with broadcast reads of L_v and store F into the dense rows with
 // consecutive lanes on consecutive columns — full-line writes; the reads of E_b ([entry][n_blk]) are 8-byte gathers
-// whose sectors are shared by the lanes of the neighbouring blocks.  No factorisation in this kernel: 64 registers,
+// whose sectors are shared by the warps of the neighbouring views (device blocks are ordered by camera, then view).  No factorisation in this kernel: 64 registers,
 // 32 warps per SM.  What bounds it now is the L1 data pipe (70 % of its wavefront rate: a warp-wide gather touches 11
 // cache lines) and instruction issue, at 2.7 TB/s of DRAM traffic.  A variant that transposes E through shared memory
 // (one plane per warp-wide load, a group of 32 / n_cams views per CTA) was measured on the B200 and is 40 % SLOWER
 // (588 against 418 us at 100 k views x 8 cameras): the staging phases and their barriers cost more instructions than
-// the coalesced loads save.  So is a block-fastest item order (the lanes of one column read consecutive doubles of one
-// plane: four planes per warp-wide load instead of fifteen) with the rows assembled in a per-warp shared-memory tile and
-// written out whole: 632 us.
+// the coalesced loads save.  So is a block-fastest item order with the rows assembled in a per-warp shared-memory tile
+// and written out whole: 632 us.  Both assumed a view's blocks to be neighbours in memory; they are n_views apart (the
+// device order is camera-major for K1's per-camera reductions), so only lanes on CONSECUTIVE VIEWS of one camera read
+// consecutive doubles — a one-lane-per-view organisation, which in turn needs L_v plane-major and scatters the stores.
 __global__ void __launch_bounds__(128) k_view_chol(ProblemShape S, ViewBuffers V, double inv_radius) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= S.n_views || !V.view_free[v]) return;
