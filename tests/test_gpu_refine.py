@@ -225,6 +225,16 @@ def test_c3_extrinsics_at_the_named_size():
     assert_solve_parity(prob, x0, abi.OptimOptions.default(compute_covariance=0))
 
 
+@pytest.mark.parametrize("n_cams,n_views", [(7, 43), (11, 26), (12, 24)])
+def test_extrinsics_wide_rigs_solve(n_cams, n_views):
+    """optimize_extrinsics (extrinsics.cpp:174-196) on rigs whose shared block is wide: 7 cameras (n_s = 99: the Schur
+    complement on 5 x 5-tile DMMA blocks, six warps, a last SYRK step of three views), 11 cameras (n_s = 159: the widest
+    reduced system k_reduced_solve takes, 230 KB of shared memory) and 12 cameras (n_s = 174: the fifteen-warp SYRK instance
+    and the reduced solve on the host) — converged parameters, iteration counts and RMS against the oracle."""
+    prob, x0, _ = synth.make_extrinsics(seed=11, n_cams=n_cams, n_views=n_views)
+    assert_solve_parity(prob, x0, abi.OptimOptions.default(compute_covariance=0))
+
+
 def test_c4_bundle_at_the_named_size():
     """BASELINE configs[3]: 4 cameras x 5 000 robot poses x 88 corners (1.76 M observations), with covariance: the fused pass
     against the oracle's, then converged parameters (1e-8 relative), RMS (1e-10 px) and the covariance."""
