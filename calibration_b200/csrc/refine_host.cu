@@ -137,7 +137,9 @@ cudaError_t download_large(double* dst, const double* src_dev, size_t n, cudaStr
         const size_t per = (cnt + n_thr - 1) / n_thr;
         for (int t = 1; t < n_thr; ++t) {
             const size_t a = std::min(cnt, per * t), b = std::min(cnt, per * (t + 1));
-            if (b > a) pool.emplace_back([=] { std::memcpy(to + a, from + a, (b - a) * sizeof(double)); });
+            if (b <= a) continue;
+            try { pool.emplace_back([=] { std::memcpy(to + a, from + a, (b - a) * sizeof(double)); }); }
+            catch (...) { std::memcpy(to + a, from + a, (b - a) * sizeof(double)); }   // no thread to be had: copy here
         }
         std::memcpy(to, from, std::min(cnt, per) * sizeof(double));
         for (std::thread& th : pool) th.join();
@@ -148,12 +150,12 @@ cudaError_t download_large(double* dst, const double* src_dev, size_t n, cudaStr
             const size_t off = c * kChunk, cnt = std::min(kChunk, n - off);
             cudaError_t e = cudaMemcpyAsync(blk[c & 1].p, src_dev + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, st);
             if (e == cudaSuccess) e = cudaEventRecord(blk[c & 1].ev, st);
-            if (e != cudaSuccess) return e;
+            if (e != cudaSuccess) { cudaStreamSynchronize(st); return e; }   // (nothing may still be writing a block that goes back to the pool)
         }
         if (c > 0) {   // chunk c - 1 has landed (chunk c is on its way): move it out
             const size_t off = (c - 1) * kChunk, cnt = std::min(kChunk, n - off);
             cudaError_t e = cudaEventSynchronize(blk[(c - 1) & 1].ev);
-            if (e != cudaSuccess) return e;
+            if (e != cudaSuccess) { cudaStreamSynchronize(st); return e; }
             scatter(dst + off, blk[(c - 1) & 1].p, cnt);
         }
     }
