@@ -529,7 +529,8 @@ def _k2_problem(seed, n_views, PI, radius, fixed_views=(0,), drop=0.15, n_cams=2
 
 @pytest.mark.parametrize("case", [dict(seed=1, n_views=37, PI=9, radius=1e4), dict(seed=2, n_views=90, PI=10, radius=3.0),
                                   dict(seed=3, n_views=21, PI=0, radius=1e2), dict(seed=4, n_views=70, PI=11, radius=1e-2, fixed_views=(0, 5, 69)),
-                                  dict(seed=5, n_views=45, PI=9, radius=10.0, n_cams=7)])   # ns = 99: the 5 x 5-tile SYRK blocks, six warps, a one-view last step
+                                  dict(seed=5, n_views=45, PI=9, radius=10.0, n_cams=7),    # ns = 99: the 5 x 5-tile SYRK blocks, six warps, a one-view last step
+                                  dict(seed=6, n_views=14, PI=9, radius=1.0, n_cams=12)])   # ns = 174: fifteen warps (5 x 5 block grid), a two-view last step, reduced solve on the host
 def test_k2_source_matches_a_dense_solve(k2_simt, case):
     """One LM iteration of the per-view kinds through the product's K2 kernels — Jacobi scaling, clamped LM diagonal,
     per-view Cholesky, Schur complement (tiled SYRK over several CTAs), back-substitution, the per-view terms of the model
