@@ -135,8 +135,12 @@ __device__ __forceinline__ void cta_reduce_store(const double* acc, double (*sm)
     }
 }
 
+// CTAs per SM of the two pair kernels (see k_axxb_otf)
+#ifndef CALK_AXXB_MINB
+#define CALK_AXXB_MINB 2
+#endif
 template <int JAC>
-__global__ void __launch_bounds__(256) k_axxb(const double* __restrict__ pairs /*[24][n]*/, int64_t n, const double* __restrict__ x7,
+__global__ void __launch_bounds__(256, CALK_AXXB_MINB) k_axxb(const double* __restrict__ pairs /*[24][n]*/, int64_t n, const double* __restrict__ x7,
                                               double huber, double* __restrict__ partial) {
     __shared__ double sm[8][kAcc];
     double q[4], tx[3];
@@ -289,9 +293,6 @@ __global__ void __launch_bounds__(256) k_pair_mask(PairTiles P, double min_angle
 // Two CTAs per SM (128 registers; ptxas spills 152 bytes in the Jacobian instance, 4 in the cost instance): the pair arithmetic
 // is one long dependent FP64 chain per thread, and with 186 registers only 8 warps per SM were there to interleave
 // (round-2 capture: FP64 pipe 38 % active, 2.1 "wait" stalls per issue).
-#ifndef CALK_AXXB_MINB
-#define CALK_AXXB_MINB 2
-#endif
 template <int JAC>
 __global__ void __launch_bounds__(256, CALK_AXXB_MINB) k_axxb_otf(PairTiles P, const double* __restrict__ x7, double huber, double* __restrict__ partial) {
     __shared__ double sG[64][12], sC[64][12];
