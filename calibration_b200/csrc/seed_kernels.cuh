@@ -160,8 +160,14 @@ struct SeedArgs {
 };
 
 // POSE = false: pixel homography + symmetric rms + Zhang rows.  POSE = true: estimate_planar_pose.
+// Three CTAs per SM (168 registers, ~50 bytes of spills): the kernel waits on global loads (long scoreboard 2.9 per issue) with few
+// warps to interleave — 1.07 ms at two CTAs per SM (184 registers), 0.75 ms at three, 0.78 ms at four (128 registers, 470 bytes of
+// spills), 160 000 views on a B200 (tools/seed_ab.sh).
+#ifndef CALK_DLT_MINB
+#define CALK_DLT_MINB 3
+#endif
 template <bool POSE>
-__global__ void __launch_bounds__(128) k_view_dlt(SeedArgs a) {
+__global__ void __launch_bounds__(128, CALK_DLT_MINB) k_view_dlt(SeedArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32;
     if (base >= a.n_views) return;
