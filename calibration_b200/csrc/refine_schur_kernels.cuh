@@ -71,6 +71,8 @@ __global__ void k_view_scale(ProblemShape S, ViewBuffers V, int compute_scale) {
 // and written out whole: 632 us.  Both assumed a view's blocks to be neighbours in memory; they are n_views apart (the
 // device order is camera-major for K1's per-camera reductions), so only lanes on CONSECUTIVE VIEWS of one camera read
 // consecutive doubles — a one-lane-per-view organisation, which in turn needs L_v plane-major and scatters the stores.
+// (A warp-per-view variant with the matrix spread over the lanes — one coalesced load, the factorisation by shuffles, no
+// local-memory frame — produces the same bits and takes the same time on the B200: 82 against 78 us at 100 k views.)
 __global__ void __launch_bounds__(128) k_view_chol(ProblemShape S, ViewBuffers V, double inv_radius) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= S.n_views || !V.view_free[v]) return;
